@@ -1,0 +1,206 @@
+/*
+ * mamdr_b200.h -- C-ABI of libmamdr_b200.so: the B200-native (sm_100a) replacement for the
+ * TensorFlow-1.12 graph that the reference executes below its meta-learning wrappers.
+ *
+ * The reference (RManLuo/MAMDR) has no FFI; the seam is the wrapper protocol
+ * (model_zoo/maml.py:153-194) plus one Keras train/eval function per mini-batch.  Each entry
+ * point below cites the reference interface it replaces (paths relative to /root/reference).
+ *
+ * Conventions
+ *   - extern "C"; every call returns int: 0 = MAMDR_OK, <0 = MAMDR_E_*; no exception crosses.
+ *   - all pointers named *_dev / documented "device" are device pointers owned by the caller
+ *     (PyTorch tensors' data_ptr()); the library never frees or retains them past the call.
+ *   - all work is enqueued on the caller's stream (a cudaStream_t passed as void*) and is
+ *     asynchronous; no host synchronisation and no allocation on hot calls (workspaces are sized
+ *     by *_workspace_bytes and passed in), so every hot call is CUDA-graph capturable.
+ *   - a ctx is bound to one device and is not thread-safe (one ctx per device per host thread).
+ *   - no float atomics on any training path: results are bit-reproducible run to run and rank to
+ *     rank (replicated DN phases on several GPUs stay bit-identical without communication).
+ */
+#ifndef MAMDR_B200_H
+#define MAMDR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MAMDR_ABI_VERSION 1
+
+#define MAMDR_OK             0
+#define MAMDR_E_INVALID     -1 /* bad argument (NULL, misaligned, out of range) */
+#define MAMDR_E_CUDA        -2 /* CUDA runtime error; text in mamdr_last_error */
+#define MAMDR_E_WORKSPACE   -3 /* workspace too small */
+#define MAMDR_E_UNSUPPORTED -4 /* shape / mode not supported by this build */
+
+#define MAMDR_MAX_LAYERS     8
+#define MAMDR_AUC_ROWS       4 /* accumulator rows: tp, fp, fn, tn */
+
+/* precision_mode of the tower GEMMs */
+#define MAMDR_PREC_FP32      0 /* fp32 FFMA (SIMT) -- the parity mode */
+#define MAMDR_PREC_TF32      1 /* tcgen05 kind::tf32, fp32 accumulate in TMEM -- speed mode */
+#define MAMDR_PREC_TF32X3    2 /* tcgen05 3xTF32 error-compensated split -- ~fp32 accuracy */
+
+/* merged_method (model_zoo/specific_base_model.py:164-172) */
+#define MAMDR_MERGE_PLUS     0
+#define MAMDR_MERGE_TIMES    1
+
+typedef struct mamdr_ctx mamdr_ctx;
+typedef void* mamdr_stream; /* cudaStream_t */
+
+/* ---- context ------------------------------------------------------------------------------ */
+int         mamdr_abi_version(void);
+int         mamdr_ctx_create(mamdr_ctx** out, int device);
+void        mamdr_ctx_destroy(mamdr_ctx* ctx);
+const char* mamdr_last_error(const mamdr_ctx* ctx); /* ctx may be NULL: last create error */
+int         mamdr_sm_count(const mamdr_ctx* ctx);
+
+/* ---- K1: embedding gather  (replaces tf.gather under Embedding, DeepCTR/deepctr.py:125-128) --
+ * out[i, 0:dim] = table[ids[i], 0:dim], i < n.  dim % 4 == 0, rows 16-byte aligned, out_stride in
+ * floats (>= dim, % 4 == 0).  Bit-exact.  ids outside [0, rows) -> row of zeros is NOT produced:
+ * the call is undefined for such ids (the reference would raise inside tf.gather). */
+int mamdr_gather_f32(mamdr_ctx* ctx, const float* table_dev, int64_t rows, int32_t dim,
+                     const int32_t* ids_dev, int64_t n, float* out_dev, int64_t out_stride,
+                     mamdr_stream stream);
+
+/* ---- K6: sparse-gradient de-duplication (replaces _deduplicate_indexed_slices = tf.unique +
+ * unsorted_segment_sum in TF's optimizer).
+ * uniq_ids = ascending unique ids (bit-exact); uniq_rows[k] = sum of grad rows whose id ==
+ * uniq_ids[k], added sequentially in batch order (== numpy add.at order, deterministic).
+ * n <= mamdr_scatter_max_n(); *n_uniq_dev receives the count (device int32). */
+int64_t mamdr_scatter_max_n(void);
+size_t  mamdr_scatter_workspace_bytes(int64_t n);
+int mamdr_scatter_dedup_f32(mamdr_ctx* ctx, const int32_t* ids_dev, const float* grad_rows_dev,
+                            int64_t grad_stride, int64_t n, int32_t dim, int32_t* uniq_ids_dev,
+                            float* uniq_rows_dev, int32_t* n_uniq_dev, void* ws_dev, size_t ws_bytes,
+                            mamdr_stream stream);
+
+/* ---- model description (replaces DeepCTR.build_inputs/build_emb/build_mlp,
+ * model_zoo/DeepCTR/deepctr.py:95-136).  Offsets are in floats into a parameter "arena": one flat
+ * fp32 buffer holding every trainable tensor in model.trainable_weights order
+ * [user_emb?, item_emb?, domain_emb, kernel0.., bias0.., dense_kernel, global_bias], each tensor
+ * start aligned to 32 floats, padding kept zero.  theta, theta_d, the live model, Adam m/v and
+ * best-snapshots all use the same layout, so every meta op is one coalesced sweep. */
+typedef struct {
+    int32_t  n_layers;                       /* hidden layers, 1..MAMDR_MAX_LAYERS */
+    int32_t  emb_dim[3];                     /* user, item, domain (each % 4 == 0) */
+    int32_t  hidden[MAMDR_MAX_LAYERS];       /* widths (each % 4 == 0) */
+    int32_t  n_domain;
+    int32_t  emb_trainable;                  /* 0: user/item tables frozen, outside the arena */
+    int64_t  n_uid, n_pid;
+    float    dropout_rate;                   /* 0 disables dropout */
+    uint32_t dropout_seed;                   /* layer l uses dropout_seed + l (DNN seed=1024) */
+    float    l2_emb;                         /* embeddings_regularizer l2 (1e-5) */
+    float    frozen_reg;                     /* l2_emb * (|E_u|^2 + |E_i|^2) for frozen tables */
+    int64_t  off_user_emb, off_item_emb;     /* -1 when frozen */
+    int64_t  off_domain_emb;
+    int64_t  off_kernel[MAMDR_MAX_LAYERS];
+    int64_t  off_bias[MAMDR_MAX_LAYERS];
+    int64_t  off_dense_kernel, off_global_bias;
+    int64_t  arena_floats;                   /* total arena length (multiple of 32) */
+} mamdr_mlp_desc;
+
+/* one mini-batch = a window of a domain-resident column store (utils/dataset.py:12-38: batch of
+ * uid, pid, domain, label with one domain id per batch, ragged tail kept) */
+typedef struct {
+    const int32_t* uid_dev;     /* [n_d] */
+    const int32_t* pid_dev;     /* [n_d] */
+    const float*   label_dev;   /* [n_d] */
+    const int32_t* order_dev;   /* [>= offset+rows] sample order of this pass, or NULL = identity */
+    int64_t        offset;      /* first position of the batch inside order */
+    int32_t        rows;        /* b, 1..max_batch */
+    int32_t        domain;      /* domain id shared by the whole batch */
+} mamdr_batch;
+
+/* ---- optimizer state (replaces tf.train.AdamOptimizer's non-slot variables beta1_power /
+ * beta2_power and Keras' iteration counter; DeepCTR/deepctr.py:54-55).  Device-resident so that
+ * captured graphs can be replayed: {int64 step; float b1pow; float b2pow; ...}. */
+size_t mamdr_opt_state_bytes(void);
+int    mamdr_opt_state_init(mamdr_ctx* ctx, void* state_dev, float beta1, float beta2,
+                            mamdr_stream stream);
+int    mamdr_opt_state_read(mamdr_ctx* ctx, const void* state_dev, int64_t* step, float* b1pow,
+                            float* b2pow, mamdr_stream stream); /* synchronises the stream */
+
+/* ---- K2-K5,K8: one training mini-batch, forward + backward (replaces the Keras train function
+ * behind Model.train_on_batch / Model.fit as driven by model_zoo/mamdr.py:54,85-97 and
+ * model_zoo/domain_negotiation.py:71-72), WITHOUT the optimizer apply.
+ *   grads_dev  : arena-shaped; every dense segment is overwritten.  With emb_trainable the table
+ *                segments are not written; the sparse part is returned de-duplicated in the
+ *                workspace (see mamdr_mlp_sparse_grads) and consumed by mamdr_adam_table_step.
+ *   loss_dev   : 1 float, mean BCE + L2 penalties of this batch (Keras 'loss' output)
+ *   probs_dev  : optional [rows] sigmoid outputs
+ *   auc_acc_dev: optional [4, num_thresholds] fp32 accumulators updated with this batch
+ *                (utils/metrics_utils.py:297-354); thresholds_dev = the fp32 threshold table.
+ * Dropout masks: Philox4x32-10, key=(dropout_seed+layer, step), see oracle/philox.py. */
+size_t mamdr_mlp_workspace_bytes(const mamdr_mlp_desc* desc, int32_t max_batch);
+int mamdr_mlp_train_step(mamdr_ctx* ctx, const mamdr_mlp_desc* desc, const mamdr_batch* batch,
+                         const float* user_table_dev, const float* item_table_dev,
+                         const float* params_dev, float* grads_dev, void* ws_dev, size_t ws_bytes,
+                         const void* opt_state_dev, float* loss_dev, float* probs_dev,
+                         float* auc_acc_dev, const float* thresholds_dev, int32_t num_thresholds,
+                         int32_t precision_mode, mamdr_stream stream);
+
+/* ---- inference mini-batch (replaces the Keras test function behind Model.evaluate,
+ * model_zoo/specific_base_model.py:82-85, model_zoo/base_model.py:130-133): no dropout. */
+int mamdr_mlp_eval_step(mamdr_ctx* ctx, const mamdr_mlp_desc* desc, const mamdr_batch* batch,
+                        const float* user_table_dev, const float* item_table_dev,
+                        const float* params_dev, void* ws_dev, size_t ws_bytes, float* loss_dev,
+                        float* probs_dev, float* auc_acc_dev, const float* thresholds_dev,
+                        int32_t num_thresholds, int32_t precision_mode, mamdr_stream stream);
+
+/* ---- K7: optimizer apply over a flat arena (replaces AdamOptimizer.apply_gradients, TF
+ * ApplyAdam kernel order of operations; bit-exact vs the oracle for equal g).
+ * Increments state.step and the beta powers once per call. */
+int mamdr_adam_step(mamdr_ctx* ctx, float* params_dev, float* m_dev, float* v_dev,
+                    const float* grads_dev, int64_t n, void* opt_state_dev, float lr, float beta1,
+                    float beta2, float eps, mamdr_stream stream);
+/* plain SGD of the finetune stage (train.GradientDescentOptimizer,
+ * model_zoo/specific_base_model.py:120, model_zoo/base_model.py:69); also bumps state.step */
+int mamdr_sgd_step(mamdr_ctx* ctx, float* params_dev, const float* grads_dev, int64_t n,
+                   void* opt_state_dev, float lr, mamdr_stream stream);
+
+/* ---- K9/K10: meta ops over arenas of identical layout (n floats) ------------------------------
+ * mamdr_copy       : dst <- src                     (SetVarOp / K.batch_get_value round trips,
+ *                                                    utils/tool.py:36-45, model_zoo/maml.py:181-194)
+ * mamdr_merge      : out <- theta (+|*) theta_i     (specific_base_model.py:164-172)
+ * mamdr_dn_update  : theta += (model - theta)*beta; model_out <- theta  (model_out may be NULL)
+ *                                                   (domain_negotiation.py:118-123, mamdr.py:57)
+ * mamdr_dr_update  : merged = theta (+|*) theta_i; theta_i += (model - merged)*beta;
+ *                    model_out <- theta (+|*) theta_i(new)               (mamdr.py:103-105,173-180)
+ * mamdr_dr_accumulate: accum += (model - merged) [* theta for 'times']   (mamdr.py:182-191)
+ * mamdr_dr_apply_accum: theta_i += accum / sample_num * beta; accum <- 0 (mamdr.py:193-196)
+ * mamdr_sub        : out <- a - b                   (mamdr.py:168-171, finetune_every_epoch)
+ * mamdr_axpy_diff  : out += (a - b) * alpha         (generic form of mamdr.py:173-180 with an explicit
+ *                                                    `merged_weights`; out may alias b)
+ * All are bit-exact vs numpy fp32 (explicit round-to-nearest mul/add, no FMA contraction). */
+int mamdr_copy(mamdr_ctx* ctx, float* dst_dev, const float* src_dev, int64_t n, mamdr_stream stream);
+int mamdr_merge(mamdr_ctx* ctx, float* out_dev, const float* theta_dev, const float* theta_i_dev,
+                int64_t n, int32_t merged_method, mamdr_stream stream);
+int mamdr_dn_update(mamdr_ctx* ctx, float* theta_dev, const float* model_dev, float beta, int64_t n,
+                    float* model_out_dev, mamdr_stream stream);
+int mamdr_dr_update(mamdr_ctx* ctx, float* theta_i_dev, const float* theta_dev,
+                    const float* model_dev, float beta, int64_t n, int32_t merged_method,
+                    float* model_out_dev, mamdr_stream stream);
+int mamdr_dr_accumulate(mamdr_ctx* ctx, float* accum_dev, const float* model_dev,
+                        const float* theta_dev, const float* theta_i_dev, int64_t n,
+                        int32_t merged_method, mamdr_stream stream);
+int mamdr_dr_apply_accum(mamdr_ctx* ctx, float* theta_i_dev, float* accum_dev, float sample_num,
+                         float beta, int64_t n, mamdr_stream stream);
+int mamdr_sub(mamdr_ctx* ctx, float* out_dev, const float* a_dev, const float* b_dev, int64_t n,
+              mamdr_stream stream);
+int mamdr_axpy_diff(mamdr_ctx* ctx, float* out_dev, const float* a_dev, const float* b_dev, float alpha,
+                    int64_t n, mamdr_stream stream);
+
+/* ---- K8: streaming AUC (replaces utils/auc.py AUC.update_state / result / reset_states) ------ */
+int mamdr_auc_update(mamdr_ctx* ctx, const float* probs_dev, const float* labels_dev, int64_t n,
+                     float* acc_dev, const float* thresholds_dev, int32_t num_thresholds,
+                     mamdr_stream stream);
+int mamdr_auc_result(mamdr_ctx* ctx, const float* acc_dev, int32_t num_thresholds, float* auc_dev,
+                     mamdr_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAMDR_B200_H */

@@ -1,0 +1,148 @@
+"""ctypes binding of ``libmamdr_b200.so`` (C-ABI in ``include/mamdr_b200.h``).
+
+The product has NO CPU fallback: if the shared library is missing or a call fails, an exception is
+raised.  Build it with ``python -m mamdr_b200.build`` (or ``__graft_entry__.build()``).
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libmamdr_b200.so")
+
+MAX_LAYERS = 8
+PREC_FP32, PREC_TF32, PREC_TF32X3 = 0, 1, 2
+MERGE_PLUS, MERGE_TIMES = 0, 1
+ABI_VERSION = 1
+
+E_NAMES = {0: "MAMDR_OK", -1: "MAMDR_E_INVALID", -2: "MAMDR_E_CUDA", -3: "MAMDR_E_WORKSPACE",
+           -4: "MAMDR_E_UNSUPPORTED"}
+
+
+class MamdrError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("%s (%d): %s" % (E_NAMES.get(code, "?"), code, msg))
+        self.code = code
+
+
+class MlpDesc(C.Structure):
+    _fields_ = [
+        ("n_layers", C.c_int32),
+        ("emb_dim", C.c_int32 * 3),
+        ("hidden", C.c_int32 * MAX_LAYERS),
+        ("n_domain", C.c_int32),
+        ("emb_trainable", C.c_int32),
+        ("n_uid", C.c_int64),
+        ("n_pid", C.c_int64),
+        ("dropout_rate", C.c_float),
+        ("dropout_seed", C.c_uint32),
+        ("l2_emb", C.c_float),
+        ("frozen_reg", C.c_float),
+        ("off_user_emb", C.c_int64),
+        ("off_item_emb", C.c_int64),
+        ("off_domain_emb", C.c_int64),
+        ("off_kernel", C.c_int64 * MAX_LAYERS),
+        ("off_bias", C.c_int64 * MAX_LAYERS),
+        ("off_dense_kernel", C.c_int64),
+        ("off_global_bias", C.c_int64),
+        ("arena_floats", C.c_int64),
+    ]
+
+
+class Batch(C.Structure):
+    _fields_ = [
+        ("uid_dev", C.c_void_p),
+        ("pid_dev", C.c_void_p),
+        ("label_dev", C.c_void_p),
+        ("order_dev", C.c_void_p),
+        ("offset", C.c_int64),
+        ("rows", C.c_int32),
+        ("domain", C.c_int32),
+    ]
+
+
+_P, _I32, _I64, _F, _SZ = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
+
+# name -> (restype, argtypes); every symbol include/mamdr_b200.h declares
+SIGNATURES = {
+    "mamdr_abi_version": (C.c_int, []),
+    "mamdr_ctx_create": (C.c_int, [C.POINTER(_P), C.c_int]),
+    "mamdr_ctx_destroy": (None, [_P]),
+    "mamdr_last_error": (C.c_char_p, [_P]),
+    "mamdr_sm_count": (C.c_int, [_P]),
+    "mamdr_gather_f32": (C.c_int, [_P, _P, _I64, _I32, _P, _I64, _P, _I64, _P]),
+    "mamdr_scatter_max_n": (_I64, []),
+    "mamdr_scatter_workspace_bytes": (_SZ, [_I64]),
+    "mamdr_scatter_dedup_f32": (C.c_int, [_P, _P, _P, _I64, _I64, _I32, _P, _P, _P, _P, _SZ, _P]),
+    "mamdr_opt_state_bytes": (_SZ, []),
+    "mamdr_opt_state_init": (C.c_int, [_P, _P, _F, _F, _P]),
+    "mamdr_opt_state_read": (C.c_int, [_P, _P, C.POINTER(_I64), C.POINTER(_F), C.POINTER(_F), _P]),
+    "mamdr_mlp_workspace_bytes": (_SZ, [C.POINTER(MlpDesc), _I32]),
+    "mamdr_mlp_train_step": (C.c_int, [_P, C.POINTER(MlpDesc), C.POINTER(Batch), _P, _P, _P, _P, _P, _SZ, _P,
+                                       _P, _P, _P, _P, _I32, _I32, _P]),
+    "mamdr_mlp_eval_step": (C.c_int, [_P, C.POINTER(MlpDesc), C.POINTER(Batch), _P, _P, _P, _P, _SZ, _P, _P, _P,
+                                      _P, _I32, _I32, _P]),
+    "mamdr_adam_step": (C.c_int, [_P, _P, _P, _P, _P, _I64, _P, _F, _F, _F, _F, _P]),
+    "mamdr_sgd_step": (C.c_int, [_P, _P, _P, _I64, _P, _F, _P]),
+    "mamdr_copy": (C.c_int, [_P, _P, _P, _I64, _P]),
+    "mamdr_merge": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _P]),
+    "mamdr_dn_update": (C.c_int, [_P, _P, _P, _F, _I64, _P, _P]),
+    "mamdr_dr_update": (C.c_int, [_P, _P, _P, _P, _F, _I64, _I32, _P, _P]),
+    "mamdr_dr_accumulate": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _P]),
+    "mamdr_dr_apply_accum": (C.c_int, [_P, _P, _P, _F, _F, _I64, _P]),
+    "mamdr_sub": (C.c_int, [_P, _P, _P, _P, _I64, _P]),
+    "mamdr_axpy_diff": (C.c_int, [_P, _P, _P, _P, _F, _I64, _P]),
+    "mamdr_auc_update": (C.c_int, [_P, _P, _P, _I64, _P, _P, _I32, _P]),
+    "mamdr_auc_result": (C.c_int, [_P, _P, _I32, _P, _P]),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen the library and bind every declared symbol.  Raises if the build is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("libmamdr_b200.so not built (%s). Run `python -m mamdr_b200.build`; there is no "
+                          "CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export it
+        fn.restype = res
+        fn.argtypes = args
+    if lib.mamdr_abi_version() != ABI_VERSION:
+        raise ImportError("libmamdr_b200.so ABI %d != expected %d" % (lib.mamdr_abi_version(), ABI_VERSION))
+    _lib = lib
+    return lib
+
+
+class Context(object):
+    """One ``mamdr_ctx`` bound to a CUDA device.  ``call`` raises MamdrError on a non-zero code."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        h = _P()
+        rc = self.lib.mamdr_ctx_create(C.byref(h), int(device))
+        if rc != 0:
+            raise MamdrError(rc, (self.lib.mamdr_last_error(None) or b"").decode())
+        self.handle = h
+        self.device = int(device)
+        self.sm_count = self.lib.mamdr_sm_count(h)
+        self.launches = 0  # kernels / memsets enqueued through this ctx (bench 'gpu_launches')
+
+    def call(self, name, *args):
+        rc = getattr(self.lib, name)(self.handle, *args)
+        if rc != 0:
+            raise MamdrError(rc, (self.lib.mamdr_last_error(self.handle) or b"").decode())
+
+    def close(self):
+        if self.handle:
+            self.lib.mamdr_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

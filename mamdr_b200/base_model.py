@@ -1,0 +1,144 @@
+"""``BaseModel`` protocol -- mirrors ``/root/reference/model_zoo/base_model.py`` (paths, early stop,
+``val_and_test``, weighted AUC, result files) over the device-resident model of ``engine.py``.
+"""
+import json
+import os
+import os.path as osp
+import time
+
+from .schedule import Schedule
+
+
+class BaseModel(object):
+    def __init__(self, dataset, config):
+        self.n_uid = dataset.n_uid
+        self.n_pid = dataset.n_pid
+        self.n_domain = dataset.n_domain
+        self.dataset = dataset
+        self.config = config
+        self.model_config = config['model']
+        self.train_config = config['train']
+        self.b200_config = config.get('b200', {})  # optional section the reference ignores
+
+        # base_model.py:23-28 -- same directory layout
+        self.checkpoint_path = osp.join(self.train_config['checkpoint_path'], self.model_config['name'],
+                                        self.dataset.conf['name'], dataset.conf['domain_split_path'],
+                                        time.strftime("%a-%b-%d-%H-%M-%S", time.localtime()),
+                                        "model_parameters.h5")
+        self.result_path = osp.join(self.train_config['result_save_path'], self.model_config['name'],
+                                    dataset.conf['name'], dataset.conf['domain_split_path'])
+        # injected schedule (python `random` is unseeded in the reference, run.py:26)
+        self.schedule = Schedule(self.b200_config.get('schedule_seed', dataset.conf['seed']))
+        self.verbose = self.b200_config.get('verbose', True)
+        self.model = self.build_model()
+        self._build_early_stop()
+
+    def log(self, *a):
+        if self.verbose:
+            print(*a)
+
+    def build_model(self):
+        raise NotImplementedError("You must implement build model")
+
+    def train(self):
+        raise NotImplementedError
+
+    # ---- training pass helper shared by every wrapper -----------------------------------------------
+    def run_train_pass(self, domain_idx, steps=None):
+        """Install the next scheduled sample order of ``domain_idx`` and run one pass (async)."""
+        d = self.dataset.train_dataset[domain_idx]
+        data = d['data']
+        data.set_order(self.schedule.batch_order(domain_idx, data.n_data))
+        n = d['n_step'] if steps is None else steps
+        self.samples_trained = getattr(self, 'samples_trained', 0) + min(data.n_data, n * data.batch_size)
+        return self.model.fit_pass(data, n)
+
+    def val_and_test(self, mode):
+        """base_model.py:111-144"""
+        if mode == "val":
+            dataset = self.dataset.val_dataset
+        elif mode == "test":
+            dataset = self.dataset.test_dataset
+            self.load_model(self.checkpoint_path)  # Load best model weights
+        else:
+            raise ValueError("Mode can be either val or test, not: {}".format(mode))
+        domain_loss, domain_auc = {}, {}
+        all_loss, all_auc = 0, 0
+        for idx, d in dataset.items():
+            p_loss, p_auc = self.model.evaluate(d['data'], steps=d['n_step'])
+            domain_loss[idx], domain_auc[idx] = p_loss, p_auc
+            all_loss += p_loss
+            all_auc += p_auc
+        avg_loss = all_loss / len(domain_loss)
+        avg_auc = all_auc / len(domain_auc)
+        self.log("Loss: ", domain_loss)
+        self._format_print_domain_metric("AUC", domain_auc)
+        weighted_auc = self._weighted_auc(mode, domain_auc)
+        self.log("Overall {} Loss: {}, AUC: {}, Weighted AUC: {}".format(mode, avg_loss, avg_auc, weighted_auc))
+        return avg_loss, avg_auc, domain_loss, domain_auc
+
+    def _format_print_domain_metric(self, name, domain_metric):
+        self.log(f"{name}: ")
+        for key, value in domain_metric.items():
+            self.log(f"{key}: {value}")
+
+    def _weighted_auc(self, mode, domain_auc):
+        """base_model.py:157-175"""
+        data_info = self.dataset.dataset_info
+        tag = 'n_train'
+        if "val" in mode:
+            tag = "n_val"
+        elif "test" in mode:
+            tag = "n_test"
+        weighted_auc, total_num = 0, 0
+        for key, value in domain_auc.items():
+            weighted_auc += data_info[key][tag] * value
+            total_num += data_info[key][tag]
+        return weighted_auc / total_num
+
+    def save_model(self, path):
+        if not osp.exists(osp.dirname(path)):
+            os.makedirs(osp.dirname(path))
+        self.model.save_weights(path)
+
+    def load_model(self, path):
+        self.model.load_weights(path)
+
+    def save_result(self, avg_loss, avg_auc, domain_loss, domain_auc):
+        """base_model.py:183-200 -- same files, same names."""
+        result_folder_name = "loss_{:.3f}_auc_{:.3f}_{}".format(avg_loss, avg_auc,
+                                                                time.strftime("%a-%b-%d-%H-%M-%S", time.localtime()))
+        result_path = osp.join(self.result_path, result_folder_name)
+        if not osp.exists(result_path):
+            os.makedirs(result_path)
+        with open(osp.join(result_path, "dataset_info.json"), 'w') as f:
+            json.dump(self.dataset.dataset_info, f)
+        with open(osp.join(result_path, "config.json.example"), 'w') as f:
+            json.dump(self.config, f)
+        with open(osp.join(result_path, "result.json"), 'w') as f:
+            json.dump({"avg_loss": avg_loss, "avg_auc": avg_auc, "domain_loss": domain_loss,
+                       "domain_auc": domain_auc}, f)
+        self.save_model(osp.join(result_path, "model_parameters.h5"))
+        return result_path
+
+    def _build_early_stop(self):
+        self.patience = self.train_config['patience']
+        self.counter = 0
+        self.best_metric = None
+        self.early_stop = False
+
+    def early_stop_step(self, metric):
+        """base_model.py:208-224 (strict improvement required)."""
+        if self.best_metric is None:
+            self.best_metric = metric
+            self.save_model(self.checkpoint_path)
+        elif metric <= self.best_metric:
+            self.counter += 1
+            self.log(f'EarlyStopping counter: {self.counter} out of {self.patience}, Best AUC: {self.best_metric}')
+            if self.counter >= self.patience:
+                self.early_stop = True
+        else:
+            self.save_model(self.checkpoint_path)
+            self.best_metric = metric
+            self.counter = 0
+        return self.early_stop

@@ -1,0 +1,61 @@
+// Shared host/device helpers for libmamdr_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/mamdr_b200.h"
+
+struct mamdr_ctx {
+    int  device;
+    int  sm_count;
+    int  max_smem_optin;
+    char err[512];
+};
+
+// optimizer / step state, device resident (see mamdr_opt_state_* in the header)
+struct OptState {
+    long long    step;    // number of optimizer applies so far (dropout global step)
+    float        b1pow;   // beta1^(step+1), fp32 running product like TF's beta1_power variable
+    float        b2pow;
+    unsigned int ticket;  // last-block-done counter of the optimizer sweep
+    unsigned int pad[3];
+};
+
+extern char g_mamdr_create_err[512];
+
+#define MAMDR_SET_ERR(ctx, ...)                                         \
+    do {                                                                \
+        if (ctx) snprintf((ctx)->err, sizeof((ctx)->err), __VA_ARGS__); \
+    } while (0)
+
+#define MAMDR_REQUIRE(ctx, cond, code, ...)  \
+    do {                                     \
+        if (!(cond)) {                       \
+            MAMDR_SET_ERR(ctx, __VA_ARGS__); \
+            return (code);                   \
+        }                                    \
+    } while (0)
+
+#define MAMDR_CUDA_OK(ctx, expr)                                                              \
+    do {                                                                                      \
+        cudaError_t e__ = (expr);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            MAMDR_SET_ERR(ctx, "%s:%d: %s -> %s", __FILE__, __LINE__, #expr,                  \
+                          cudaGetErrorString(e__));                                           \
+            return MAMDR_E_CUDA;                                                              \
+        }                                                                                     \
+    } while (0)
+
+#define MAMDR_LAUNCH_OK(ctx) MAMDR_CUDA_OK(ctx, cudaGetLastError())
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// streaming (evict-first) 128-bit accesses for one-touch sweeps
+__device__ __forceinline__ float4 ld_stream_f4(const float* p) {
+    return __ldcs(reinterpret_cast<const float4*>(p));
+}
+__device__ __forceinline__ void st_stream_f4(float* p, float4 v) { __stcs(reinterpret_cast<float4*>(p), v); }

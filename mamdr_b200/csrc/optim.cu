@@ -1,0 +1,283 @@
+// K7, K9, K10: multi-tensor optimizer apply and DN / DR meta updates as single coalesced sweeps
+// over flat parameter arenas (every trainable tensor of the model lives in ONE fp32 buffer, so
+// "multi-tensor" is one 128-bit vectorised grid-stride loop; HBM-bound at Amazon sizes, L2-resident
+// at Taobao sizes).
+//
+// Replaces: tf.train.AdamOptimizer.apply_gradients (/root/reference/model_zoo/DeepCTR/deepctr.py:54-55),
+// SetVarOp / K.batch_get_value round trips (utils/tool.py:36-45, model_zoo/maml.py:181-194), and the
+// host numpy algebra of model_zoo/domain_negotiation.py:118-123, model_zoo/mamdr.py:168-196,
+// model_zoo/specific_base_model.py:164-172.
+//
+// Arithmetic is written with explicit round-to-nearest intrinsics (__fmul_rn/__fadd_rn/...) in the
+// operation order of TF's ApplyAdam kernel and of the reference's numpy expressions, so each op is
+// bit-exact against the fp32 numpy oracle for identical inputs (no FMA contraction).
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+inline int sweep_grid(const mamdr_ctx* ctx, int64_t n_vec) {
+    const int64_t want = ceil_div64(n_vec, kThreads);
+    const int64_t cap = (int64_t)ctx->sm_count * 8;
+    return (int)(want < 1 ? 1 : (want < cap ? want : cap));
+}
+
+__global__ void opt_state_init_kernel(OptState* s, float b1, float b2) {
+    s->step = 0;
+    s->b1pow = b1;
+    s->b2pow = b2;
+    s->ticket = 0;
+    s->pad[0] = s->pad[1] = s->pad[2] = 0;
+}
+
+// last-block-done: every block reads the beta powers before it arrives; the block that draws the
+// final ticket advances them (and the step) after all others have read.
+__device__ __forceinline__ void finish_step(OptState* st, float beta1, float beta2, bool adam) {
+    __shared__ bool last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(&st->ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        if (adam) {
+            st->b1pow = __fmul_rn(st->b1pow, beta1);
+            st->b2pow = __fmul_rn(st->b2pow, beta2);
+        }
+        st->step += 1;
+        st->ticket = 0;
+    }
+}
+
+__device__ __forceinline__ void adam1(float& p, float& m, float& v, float g, float alpha, float omb1, float omb2,
+                                      float eps) {
+    m = __fadd_rn(m, __fmul_rn(__fsub_rn(g, m), omb1));
+    v = __fadd_rn(v, __fmul_rn(__fsub_rn(__fmul_rn(g, g), v), omb2));
+    p = __fsub_rn(p, __fdiv_rn(__fmul_rn(m, alpha), __fadd_rn(__fsqrt_rn(v), eps)));
+}
+
+__global__ void __launch_bounds__(kThreads)
+adam_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ g,
+            int64_t n, OptState* st, float lr, float beta1, float beta2, float eps) {
+    const float b1p = st->b1pow, b2p = st->b2pow;
+    const float alpha = __fdiv_rn(__fmul_rn(lr, __fsqrt_rn(__fsub_rn(1.0f, b2p))), __fsub_rn(1.0f, b1p));
+    const float omb1 = __fsub_rn(1.0f, beta1), omb2 = __fsub_rn(1.0f, beta2);
+    const int64_t nv = n >> 2;
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < nv; i += stride) {
+        float4 P = *reinterpret_cast<float4*>(p + 4 * i), M = *reinterpret_cast<float4*>(m + 4 * i);
+        float4 V = *reinterpret_cast<float4*>(v + 4 * i);
+        const float4 G = *reinterpret_cast<const float4*>(g + 4 * i);
+        adam1(P.x, M.x, V.x, G.x, alpha, omb1, omb2, eps);
+        adam1(P.y, M.y, V.y, G.y, alpha, omb1, omb2, eps);
+        adam1(P.z, M.z, V.z, G.z, alpha, omb1, omb2, eps);
+        adam1(P.w, M.w, V.w, G.w, alpha, omb1, omb2, eps);
+        *reinterpret_cast<float4*>(p + 4 * i) = P;
+        *reinterpret_cast<float4*>(m + 4 * i) = M;
+        *reinterpret_cast<float4*>(v + 4 * i) = V;
+    }
+    finish_step(st, beta1, beta2, true);
+}
+
+__global__ void __launch_bounds__(kThreads)
+sgd_kernel(float* __restrict__ p, const float* __restrict__ g, int64_t n, OptState* st, float lr) {
+    const int64_t nv = n >> 2;
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < nv; i += stride) {
+        float4 P = *reinterpret_cast<float4*>(p + 4 * i);
+        const float4 G = *reinterpret_cast<const float4*>(g + 4 * i);
+        P.x = __fsub_rn(P.x, __fmul_rn(G.x, lr));
+        P.y = __fsub_rn(P.y, __fmul_rn(G.y, lr));
+        P.z = __fsub_rn(P.z, __fmul_rn(G.z, lr));
+        P.w = __fsub_rn(P.w, __fmul_rn(G.w, lr));
+        *reinterpret_cast<float4*>(p + 4 * i) = P;
+    }
+    finish_step(st, 0.f, 0.f, false);
+}
+
+// ---- element-wise meta functors ---------------------------------------------------------------
+__device__ __forceinline__ float merge1(float t, float ti, int method) {
+    return method == MAMDR_MERGE_PLUS ? __fadd_rn(t, ti) : __fmul_rn(t, ti);
+}
+
+enum MetaOp { OP_COPY, OP_MERGE, OP_DN, OP_DR, OP_DR_ACC, OP_DR_APPLY, OP_SUB, OP_AXPY_DIFF };
+
+struct MetaArgs {
+    float*       w0;  // primary output / in-out
+    float*       w1;  // secondary output (may be NULL)
+    const float* r0;
+    const float* r1;
+    const float* r2;
+    float        f0, f1;
+    int          method;
+    int64_t      n;
+};
+
+#define COMP(v, k) (reinterpret_cast<const float*>(&(v))[k])
+#define COMPW(v, k) (reinterpret_cast<float*>(&(v))[k])
+
+template <int OP>
+__global__ void __launch_bounds__(kThreads) meta_kernel(MetaArgs a) {
+    const int64_t nv = a.n >> 2;
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < nv; i += stride) {
+        float4 W0 = make_float4(0, 0, 0, 0), W1 = make_float4(0, 0, 0, 0);
+        float4 R0 = make_float4(0, 0, 0, 0), R1 = R0, R2 = R0;
+        if (OP == OP_DN || OP == OP_DR || OP == OP_DR_ACC || OP == OP_DR_APPLY || OP == OP_AXPY_DIFF) W0 = *reinterpret_cast<float4*>(a.w0 + 4 * i);
+        if (OP == OP_DR_APPLY) W1 = *reinterpret_cast<float4*>(a.w1 + 4 * i);
+        R0 = *reinterpret_cast<const float4*>((OP == OP_DR_APPLY ? a.w1 : a.r0) + 4 * i);
+        if (OP == OP_MERGE || OP == OP_DR || OP == OP_DR_ACC || OP == OP_SUB || OP == OP_AXPY_DIFF) R1 = *reinterpret_cast<const float4*>(a.r1 + 4 * i);
+        if (OP == OP_DR_ACC) R2 = *reinterpret_cast<const float4*>(a.r2 + 4 * i);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (OP == OP_COPY) {
+                COMPW(W0, k) = COMP(R0, k);
+            } else if (OP == OP_MERGE) {  // out = theta (+|*) theta_i
+                COMPW(W0, k) = merge1(COMP(R0, k), COMP(R1, k), a.method);
+            } else if (OP == OP_DN) {  // theta += (model - theta) * beta ; model_out = theta
+                const float t = COMP(W0, k);
+                const float nt = __fadd_rn(t, __fmul_rn(__fsub_rn(COMP(R0, k), t), a.f0));
+                COMPW(W0, k) = nt;
+                COMPW(W1, k) = nt;
+            } else if (OP == OP_DR) {  // W0 = theta_i, R0 = model, R1 = theta
+                const float ti = COMP(W0, k), t = COMP(R1, k);
+                const float merged = merge1(t, ti, a.method);
+                const float nti = __fadd_rn(ti, __fmul_rn(__fsub_rn(COMP(R0, k), merged), a.f0));
+                COMPW(W0, k) = nti;
+                COMPW(W1, k) = merge1(t, nti, a.method);
+            } else if (OP == OP_DR_ACC) {  // W0 = accum, R0 = model, R1 = theta, R2 = theta_i
+                const float t = COMP(R1, k);
+                const float merged = merge1(t, COMP(R2, k), a.method);
+                float d = __fsub_rn(COMP(R0, k), merged);
+                if (a.method == MAMDR_MERGE_TIMES) d = __fmul_rn(d, t);
+                COMPW(W0, k) = __fadd_rn(COMP(W0, k), d);
+            } else if (OP == OP_DR_APPLY) {  // W0 = theta_i, W1/R0 = accum ; f0 = sample_num, f1 = beta
+                COMPW(W0, k) = __fadd_rn(COMP(W0, k), __fmul_rn(__fdiv_rn(COMP(R0, k), a.f0), a.f1));
+                COMPW(W1, k) = 0.f;
+            } else if (OP == OP_SUB) {
+                COMPW(W0, k) = __fsub_rn(COMP(R0, k), COMP(R1, k));
+            } else if (OP == OP_AXPY_DIFF) {  // out += (a - b) * alpha
+                COMPW(W0, k) = __fadd_rn(COMP(W0, k), __fmul_rn(__fsub_rn(COMP(R0, k), COMP(R1, k)), a.f0));
+            }
+        }
+        *reinterpret_cast<float4*>(a.w0 + 4 * i) = W0;
+        if ((OP == OP_DN || OP == OP_DR) && a.w1) *reinterpret_cast<float4*>(a.w1 + 4 * i) = W1;
+        if (OP == OP_DR_APPLY) *reinterpret_cast<float4*>(a.w1 + 4 * i) = W1;
+    }
+}
+
+template <int OP>
+int launch_meta(mamdr_ctx* ctx, MetaArgs a, mamdr_stream stream) {
+    MAMDR_REQUIRE(ctx, ctx != nullptr, MAMDR_E_INVALID, "ctx is NULL");
+    MAMDR_REQUIRE(ctx, a.n >= 0 && a.n % 4 == 0, MAMDR_E_INVALID, "arena length must be a multiple of 4 floats");
+    if (a.n == 0) return MAMDR_OK;
+    const void* ptrs[5] = {a.w0, a.w1, a.r0, a.r1, a.r2};
+    for (int i = 0; i < 5; ++i) MAMDR_REQUIRE(ctx, aligned16(ptrs[i]), MAMDR_E_INVALID, "arena pointer misaligned");
+    meta_kernel<OP><<<sweep_grid(ctx, a.n >> 2), kThreads, 0, (cudaStream_t)stream>>>(a);
+    MAMDR_LAUNCH_OK(ctx);
+    return MAMDR_OK;
+}
+
+}  // namespace
+
+extern "C" size_t mamdr_opt_state_bytes(void) { return sizeof(OptState); }
+
+extern "C" int mamdr_opt_state_init(mamdr_ctx* ctx, void* state, float beta1, float beta2, mamdr_stream stream) {
+    MAMDR_REQUIRE(ctx, ctx && state, MAMDR_E_INVALID, "NULL ctx/state");
+    opt_state_init_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((OptState*)state, beta1, beta2);
+    MAMDR_LAUNCH_OK(ctx);
+    return MAMDR_OK;
+}
+
+extern "C" int mamdr_opt_state_read(mamdr_ctx* ctx, const void* state, int64_t* step, float* b1pow, float* b2pow,
+                                    mamdr_stream stream) {
+    MAMDR_REQUIRE(ctx, ctx && state, MAMDR_E_INVALID, "NULL ctx/state");
+    OptState h;
+    MAMDR_CUDA_OK(ctx, cudaMemcpyAsync(&h, state, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    MAMDR_CUDA_OK(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+    if (step) *step = h.step;
+    if (b1pow) *b1pow = h.b1pow;
+    if (b2pow) *b2pow = h.b2pow;
+    return MAMDR_OK;
+}
+
+extern "C" int mamdr_adam_step(mamdr_ctx* ctx, float* p, float* m, float* v, const float* g, int64_t n, void* state,
+                               float lr, float beta1, float beta2, float eps, mamdr_stream stream) {
+    MAMDR_REQUIRE(ctx, ctx != nullptr, MAMDR_E_INVALID, "ctx is NULL");
+    MAMDR_REQUIRE(ctx, p && m && v && g && state, MAMDR_E_INVALID, "NULL pointer");
+    MAMDR_REQUIRE(ctx, n > 0 && n % 4 == 0, MAMDR_E_INVALID, "arena length must be a positive multiple of 4");
+    MAMDR_REQUIRE(ctx, aligned16(p) && aligned16(m) && aligned16(v) && aligned16(g), MAMDR_E_INVALID, "misaligned arena");
+    adam_kernel<<<sweep_grid(ctx, n >> 2), kThreads, 0, (cudaStream_t)stream>>>(p, m, v, g, n, (OptState*)state, lr,
+                                                                               beta1, beta2, eps);
+    MAMDR_LAUNCH_OK(ctx);
+    return MAMDR_OK;
+}
+
+extern "C" int mamdr_sgd_step(mamdr_ctx* ctx, float* p, const float* g, int64_t n, void* state, float lr,
+                              mamdr_stream stream) {
+    MAMDR_REQUIRE(ctx, ctx != nullptr, MAMDR_E_INVALID, "ctx is NULL");
+    MAMDR_REQUIRE(ctx, p && g && state, MAMDR_E_INVALID, "NULL pointer");
+    MAMDR_REQUIRE(ctx, n > 0 && n % 4 == 0, MAMDR_E_INVALID, "arena length must be a positive multiple of 4");
+    MAMDR_REQUIRE(ctx, aligned16(p) && aligned16(g), MAMDR_E_INVALID, "misaligned arena");
+    sgd_kernel<<<sweep_grid(ctx, n >> 2), kThreads, 0, (cudaStream_t)stream>>>(p, g, n, (OptState*)state, lr);
+    MAMDR_LAUNCH_OK(ctx);
+    return MAMDR_OK;
+}
+
+extern "C" int mamdr_copy(mamdr_ctx* ctx, float* dst, const float* src, int64_t n, mamdr_stream stream) {
+    MAMDR_REQUIRE(ctx, ctx && dst && src, MAMDR_E_INVALID, "NULL pointer");
+    MetaArgs a{dst, nullptr, src, nullptr, nullptr, 0.f, 0.f, 0, n};
+    return launch_meta<OP_COPY>(ctx, a, stream);
+}
+
+extern "C" int mamdr_merge(mamdr_ctx* ctx, float* out, const float* theta, const float* theta_i, int64_t n,
+                           int32_t method, mamdr_stream stream) {
+    MAMDR_REQUIRE(ctx, ctx && out && theta && theta_i, MAMDR_E_INVALID, "NULL pointer");
+    MAMDR_REQUIRE(ctx, method == MAMDR_MERGE_PLUS || method == MAMDR_MERGE_TIMES, MAMDR_E_INVALID, "bad merged_method");
+    MetaArgs a{out, nullptr, theta, theta_i, nullptr, 0.f, 0.f, method, n};
+    return launch_meta<OP_MERGE>(ctx, a, stream);
+}
+
+extern "C" int mamdr_dn_update(mamdr_ctx* ctx, float* theta, const float* model, float beta, int64_t n,
+                               float* model_out, mamdr_stream stream) {
+    MAMDR_REQUIRE(ctx, ctx && theta && model, MAMDR_E_INVALID, "NULL pointer");
+    MetaArgs a{theta, model_out, model, nullptr, nullptr, beta, 0.f, 0, n};
+    return launch_meta<OP_DN>(ctx, a, stream);
+}
+
+extern "C" int mamdr_dr_update(mamdr_ctx* ctx, float* theta_i, const float* theta, const float* model, float beta,
+                               int64_t n, int32_t method, float* model_out, mamdr_stream stream) {
+    MAMDR_REQUIRE(ctx, ctx && theta_i && theta && model, MAMDR_E_INVALID, "NULL pointer");
+    MAMDR_REQUIRE(ctx, method == MAMDR_MERGE_PLUS || method == MAMDR_MERGE_TIMES, MAMDR_E_INVALID, "bad merged_method");
+    MetaArgs a{theta_i, model_out, model, theta, nullptr, beta, 0.f, method, n};
+    return launch_meta<OP_DR>(ctx, a, stream);
+}
+
+extern "C" int mamdr_dr_accumulate(mamdr_ctx* ctx, float* accum, const float* model, const float* theta,
+                                   const float* theta_i, int64_t n, int32_t method, mamdr_stream stream) {
+    MAMDR_REQUIRE(ctx, ctx && accum && model && theta && theta_i, MAMDR_E_INVALID, "NULL pointer");
+    MAMDR_REQUIRE(ctx, method == MAMDR_MERGE_PLUS || method == MAMDR_MERGE_TIMES, MAMDR_E_INVALID, "bad merged_method");
+    MetaArgs a{accum, nullptr, model, theta, theta_i, 0.f, 0.f, method, n};
+    return launch_meta<OP_DR_ACC>(ctx, a, stream);
+}
+
+extern "C" int mamdr_dr_apply_accum(mamdr_ctx* ctx, float* theta_i, float* accum, float sample_num, float beta,
+                                    int64_t n, mamdr_stream stream) {
+    MAMDR_REQUIRE(ctx, ctx && theta_i && accum, MAMDR_E_INVALID, "NULL pointer");
+    MAMDR_REQUIRE(ctx, sample_num != 0.f, MAMDR_E_INVALID, "sample_num is 0");
+    MetaArgs a{theta_i, accum, nullptr, nullptr, nullptr, sample_num, beta, 0, n};
+    return launch_meta<OP_DR_APPLY>(ctx, a, stream);
+}
+
+extern "C" int mamdr_sub(mamdr_ctx* ctx, float* out, const float* a_, const float* b_, int64_t n, mamdr_stream stream) {
+    MAMDR_REQUIRE(ctx, ctx && out && a_ && b_, MAMDR_E_INVALID, "NULL pointer");
+    MetaArgs a{out, nullptr, a_, b_, nullptr, 0.f, 0.f, 0, n};
+    return launch_meta<OP_SUB>(ctx, a, stream);
+}
+
+extern "C" int mamdr_axpy_diff(mamdr_ctx* ctx, float* out, const float* a_, const float* b_, float alpha, int64_t n,
+                               mamdr_stream stream) {
+    MAMDR_REQUIRE(ctx, ctx && out && a_ && b_, MAMDR_E_INVALID, "NULL pointer");
+    MetaArgs a{out, nullptr, a_, b_, nullptr, alpha, 0.f, 0, n};
+    return launch_meta<OP_AXPY_DIFF>(ctx, a, stream);
+}

@@ -1,0 +1,320 @@
+"""Device-resident mlp model: the stand-in for the compiled ``tf.keras.Model`` that the reference
+builds in ``/root/reference/model_zoo/DeepCTR/deepctr.py:20-61`` (BCE loss, ``AdamOptimizer``,
+``AUC(num_thresholds=500)``) and drives with ``train_on_batch`` / ``fit`` / ``evaluate``.
+
+All arithmetic runs in ``libmamdr_b200.so`` through the C-ABI; PyTorch only owns device memory and
+streams.  Nothing here falls back to the CPU.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .auc import thresholds as auc_thresholds
+from .layout import mlp_layout
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class DomainData(object):
+    """One domain's split as a device-resident column store (``uid, pid, label``), the replacement
+    for the per-domain ``tf.data`` CSV pipeline of ``utils/dataset.py:20-38`` (which re-reads and
+    re-parses the CSV on every pass).  ``n_step = ceil(n / batch_size)``, ragged tail kept."""
+
+    def __init__(self, uid, pid, label, domain, batch_size, device):
+        self.domain = int(domain)
+        self.n_data = int(len(uid))
+        self.batch_size = int(batch_size)
+        self.n_step = int(np.ceil(self.n_data / float(batch_size))) if self.n_data else 0
+        self.host = {"uid": np.ascontiguousarray(uid, dtype=np.int32),
+                     "pid": np.ascontiguousarray(pid, dtype=np.int32),
+                     "label": np.ascontiguousarray(label, dtype=np.float32)}
+        self.device = device
+        self.uid = self.pid = self.label = self.order = None
+        if device is not None:
+            self.upload()
+
+    def upload(self, non_blocking=False):
+        dev = self.device
+        self.uid = torch.from_numpy(self.host["uid"]).to(dev, non_blocking=non_blocking)
+        self.pid = torch.from_numpy(self.host["pid"]).to(dev, non_blocking=non_blocking)
+        self.label = torch.from_numpy(self.host["label"]).to(dev, non_blocking=non_blocking)
+        if self.order is None:
+            self.order = torch.arange(max(self.n_data, 1), dtype=torch.int32, device=dev)
+
+    def set_order(self, order):
+        """Install the sample order of the next training pass (host numpy or device tensor)."""
+        if isinstance(order, np.ndarray):
+            order = torch.from_numpy(np.ascontiguousarray(order, dtype=np.int32))
+        self.order.copy_(order, non_blocking=True)
+
+
+class NamedWeight(object):
+    """Minimal stand-in for a ``tf.Variable`` in ``model.trainable_weights`` (has ``.name``)."""
+
+    def __init__(self, name, view, offset, numel):
+        self.name, self.value, self.offset, self.numel = name, view, offset, numel
+        self.shape = tuple(view.shape)
+
+    def __repr__(self):
+        return "<NamedWeight %s %s>" % (self.name, self.shape)
+
+
+class MLPModel(object):
+    # variable names as DeepCTR 0.9.0 creates them: used by the substring matching
+    # of ``model_zoo/maml.py:160-177`` ("emb" in p.name ...)
+    TF_NAMES = {"user_emb": "sparse_emb_user_emb/embeddings:0", "item_emb": "sparse_emb_item_emb/embeddings:0",
+                "domain_emb": "sparse_emb_domain_emb/embeddings:0", "dense_kernel": "dense/kernel:0",
+                "global_bias": "prediction_layer/global_bias:0"}
+
+    def __init__(self, n_uid, n_pid, n_domain, emb_dim=(128, 128, 128), hidden=(256, 128, 64), dropout=0.5,
+                 dropout_seed=1024, l2_emb=1e-5, emb_trainable=False, user_table=None, item_table=None,
+                 init_weights=None, lr=1e-3, max_batch=1024, precision=_lib.PREC_FP32, device="cuda:0",
+                 use_graphs=True):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("mamdr_b200 runs on CUDA devices only (no CPU fallback)")
+        torch.cuda.set_device(self.device)
+        self.ctx = _lib.Context(self.device.index or 0)
+        self.layout = mlp_layout(n_uid, n_pid, n_domain, emb_dim, hidden, emb_trainable)
+        self.n_uid, self.n_pid, self.n_domain = int(n_uid), int(n_pid), int(n_domain)
+        self.emb_dim, self.hidden = tuple(emb_dim), tuple(hidden)
+        self.emb_trainable = bool(emb_trainable)
+        self.lr, self.beta1, self.beta2, self.eps = float(lr), 0.9, 0.999, 1e-8
+        self.max_batch = int(max_batch)
+        self.precision = int(precision)
+        self.use_graphs = bool(use_graphs)
+        self.optimizer = "adam"
+        self.sgd_lr = 0.0
+        dev = self.device
+        P = self.layout.total
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.params = torch.zeros(P, **f32)
+        self.grads = torch.zeros(P, **f32)
+        self.m = torch.zeros(P, **f32)
+        self.v = torch.zeros(P, **f32)
+        if init_weights is not None:
+            self.params.copy_(torch.from_numpy(self.layout.pack(init_weights)))
+        self.frozen_reg = 0.0
+        if not emb_trainable:
+            if user_table is None or item_table is None:
+                raise ValueError("frozen embeddings need user_table and item_table")
+            ut = np.ascontiguousarray(user_table, dtype=np.float32)
+            it = np.ascontiguousarray(item_table, dtype=np.float32)
+            assert ut.shape == (n_uid, emb_dim[0]) and it.shape == (n_pid, emb_dim[1])
+            self.frozen_reg = float(l2_emb * (np.sum(ut.astype(np.float64) ** 2) + np.sum(it.astype(np.float64) ** 2)))
+            self.user_table = torch.from_numpy(ut).to(dev)
+            self.item_table = torch.from_numpy(it).to(dev)
+        else:
+            self.user_table = self.item_table = None
+        # ---- C-ABI descriptor
+        d = _lib.MlpDesc()
+        d.n_layers = len(hidden)
+        for i in range(3):
+            d.emb_dim[i] = int(emb_dim[i])
+        for i, h in enumerate(hidden):
+            d.hidden[i] = int(h)
+        d.n_domain, d.emb_trainable = int(n_domain), int(emb_trainable)
+        d.n_uid, d.n_pid = int(n_uid), int(n_pid)
+        d.dropout_rate, d.dropout_seed, d.l2_emb = float(dropout), int(dropout_seed), float(l2_emb)
+        d.frozen_reg = self.frozen_reg
+        lo = self.layout
+        d.off_user_emb, d.off_item_emb = lo.offset("user_emb"), lo.offset("item_emb")
+        d.off_domain_emb = lo.offset("domain_emb")
+        for i in range(len(hidden)):
+            d.off_kernel[i], d.off_bias[i] = lo.offset("kernel%d" % i), lo.offset("bias%d" % i)
+        d.off_dense_kernel, d.off_global_bias = lo.offset("dense_kernel"), lo.offset("global_bias")
+        d.arena_floats = P
+        self.desc = d
+        lib = self.ctx.lib
+        ws_bytes = lib.mamdr_mlp_workspace_bytes(C.byref(d), self.max_batch)
+        if ws_bytes == 0:
+            raise _lib.MamdrError(-1, "mamdr_mlp_workspace_bytes rejected the descriptor")
+        self.ws = torch.zeros(ws_bytes, dtype=torch.uint8, device=dev)
+        self.ws_bytes = ws_bytes
+        self.opt_state = torch.zeros(lib.mamdr_opt_state_bytes(), dtype=torch.uint8, device=dev)
+        self.num_thresholds = 500
+        self.thresholds = torch.from_numpy(auc_thresholds(self.num_thresholds)).to(dev)
+        self.auc_acc = torch.zeros(4, self.num_thresholds, **f32)
+        self._auc_out = torch.zeros(1, **f32)
+        self.reset_optimizer()
+        self._graphs = {}
+        self._loss_bufs = {}
+
+    # ---- Keras-like surface -------------------------------------------------------------------------
+    @property
+    def stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @property
+    def trainable_weights(self):
+        out = []
+        for name, view, off, n in zip(self.layout.names, self.layout.views(self.params), self.layout.offsets,
+                                      self.layout.numels):
+            tf_name = self.TF_NAMES.get(name)
+            if tf_name is None:
+                kind, idx = ("kernel", name[6:]) if name.startswith("kernel") else ("bias", name[4:])
+                tf_name = "dnn/%s%s:0" % (kind, idx)
+            out.append(NamedWeight(tf_name, view, off, n))
+        return out
+
+    @property
+    def stateful_metric_functions(self):
+        return [self]  # the AUC metric lives on the model; exposes reset_states()
+
+    def reset_states(self):
+        """``AUC.reset_states`` (utils/auc.py:283-284)."""
+        self.auc_acc.zero_()
+
+    def reset_optimizer(self):
+        """``tf.global_variables_initializer()`` on the optimizer slots
+        (model_zoo/mamdr.py:35, model_zoo/domain_negotiation.py:31): m = v = 0, beta powers reset."""
+        self.m.zero_()
+        self.v.zero_()
+        self.ctx.call("mamdr_opt_state_init", _ptr(self.opt_state), self.beta1, self.beta2, self.stream)
+        self.ctx.launches += 1
+
+    def compile(self, optimizer="adam", lr=None):
+        """``model.compile`` with ``AdamOptimizer`` (DeepCTR/deepctr.py:54-60) or the finetune stage's
+        ``GradientDescentOptimizer`` (specific_base_model.py:120, base_model.py:69)."""
+        if optimizer not in ("adam", "sgd"):
+            raise ValueError("optimizer must be 'adam' or 'sgd'")
+        self.optimizer = optimizer
+        if optimizer == "sgd":
+            self.sgd_lr = float(lr)
+        elif lr is not None:
+            self.lr = float(lr)
+
+    def get_weights(self):
+        return self.params.clone()
+
+    def set_weights(self, flat):
+        self.copy_(self.params, flat)
+
+    def copy_(self, dst, src):
+        self.ctx.call("mamdr_copy", _ptr(dst), _ptr(src), dst.numel(), self.stream)
+        self.ctx.launches += 1
+
+    def read_step(self):
+        step, b1, b2 = C.c_int64(), C.c_float(), C.c_float()
+        self.ctx.call("mamdr_opt_state_read", _ptr(self.opt_state), C.byref(step), C.byref(b1), C.byref(b2),
+                      self.stream)
+        return step.value, b1.value, b2.value
+
+    # ---- one mini-batch ---------------------------------------------------------------------------------
+    def _batch(self, data, offset, rows, use_order):
+        b = _lib.Batch()
+        b.uid_dev, b.pid_dev, b.label_dev = data.uid.data_ptr(), data.pid.data_ptr(), data.label.data_ptr()
+        b.order_dev = data.order.data_ptr() if use_order else None
+        b.offset, b.rows, b.domain = int(offset), int(rows), int(data.domain)
+        return b
+
+    def _train_step(self, data, offset, rows, loss_slot, probs=None, with_auc=True):
+        b = self._batch(data, offset, rows, True)
+        st = self.stream
+        self.ctx.call("mamdr_mlp_train_step", C.byref(self.desc), C.byref(b), _ptr(self.user_table),
+                      _ptr(self.item_table), _ptr(self.params), _ptr(self.grads), _ptr(self.ws), self.ws_bytes,
+                      _ptr(self.opt_state), _ptr(loss_slot), _ptr(probs), _ptr(self.auc_acc if with_auc else None),
+                      _ptr(self.thresholds), self.num_thresholds, self.precision, st)
+        if self.optimizer == "adam":
+            self.ctx.call("mamdr_adam_step", _ptr(self.params), _ptr(self.m), _ptr(self.v), _ptr(self.grads),
+                          self.params.numel(), _ptr(self.opt_state), self.lr, self.beta1, self.beta2, self.eps, st)
+        else:
+            self.ctx.call("mamdr_sgd_step", _ptr(self.params), _ptr(self.grads), self.params.numel(),
+                          _ptr(self.opt_state), self.sgd_lr, st)
+        self.ctx.launches += 3 + 3 * len(self.hidden) + 3  # memset, assemble, L fwd, head, L-1 dH, L dW, colsum, dEd, opt
+
+    def train_on_batch(self, data, offset, rows):
+        """``Model.train_on_batch`` -> (loss, auc) host floats.  Synchronises: debugging / parity only;
+        the wrappers use ``fit_pass``."""
+        loss = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._train_step(data, offset, rows, loss)
+        return float(loss.item()), self.auc_result()
+
+    def _pass_plan(self, data, steps):
+        bs = data.batch_size
+        return [(s * bs, min(bs, data.n_data - s * bs)) for s in range(steps)]
+
+    def fit_pass(self, data, steps=None):
+        """One pass of ``steps`` mini-batches over ``data`` in the order installed by
+        ``data.set_order`` (== the ``for step in range(train_step): model.train_on_batch(iter)`` loops
+        of mamdr.py:85-97 and domain_negotiation.py:71-72, and ``model.fit(iter, steps_per_epoch)`` of
+        mamdr.py:54).  Asynchronous; returns the device tensor of per-batch losses.  The whole pass is
+        captured once into a CUDA graph per (domain split, steps, optimizer) and replayed."""
+        steps = data.n_step if steps is None else int(steps)
+        if steps <= 0:
+            return torch.zeros(0, dtype=torch.float32, device=self.device)
+        if data.batch_size > self.max_batch:
+            raise ValueError("batch_size %d exceeds max_batch %d" % (data.batch_size, self.max_batch))
+        key = (id(data), steps, self.optimizer, self.sgd_lr, self.lr)
+        losses = self._loss_bufs.get(key)
+        if losses is None:
+            losses = self._loss_bufs[key] = torch.zeros(steps, dtype=torch.float32, device=self.device)
+        plan = self._pass_plan(data, steps)
+        if not self.use_graphs:
+            for s, (off, rows) in enumerate(plan):
+                self._train_step(data, off, rows, losses[s:s + 1])
+            return losses
+        g = self._graphs.get(key)
+        if g is None:
+            # capture happens on a side stream; the launches recorded there are not executed
+            before = self.ctx.launches
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize(self.device)
+            with torch.cuda.graph(g):
+                for s, (off, rows) in enumerate(plan):
+                    self._train_step(data, off, rows, losses[s:s + 1])
+            self._graphs[key] = (g, self.ctx.launches - before)
+            self.ctx.launches = before
+            g = self._graphs[key]
+        g[0].replay()
+        self.ctx.launches += g[1]
+        return losses
+
+    # ---- evaluate ---------------------------------------------------------------------------------------
+    def evaluate(self, data, steps=None):
+        """``Model.evaluate(dataset, steps)`` -> (mean of per-batch losses, AUC) as host floats: resets
+        the stateful AUC, runs the inference forward (no dropout) batch by batch in file order."""
+        steps = data.n_step if steps is None else int(steps)
+        self.reset_states()
+        losses = torch.zeros(max(steps, 1), dtype=torch.float32, device=self.device)
+        st = self.stream
+        for s, (off, rows) in enumerate(self._pass_plan(data, steps)):
+            b = self._batch(data, off, rows, False)
+            self.ctx.call("mamdr_mlp_eval_step", C.byref(self.desc), C.byref(b), _ptr(self.user_table),
+                          _ptr(self.item_table), _ptr(self.params), _ptr(self.ws), self.ws_bytes,
+                          _ptr(losses[s:s + 1]), None, _ptr(self.auc_acc), _ptr(self.thresholds),
+                          self.num_thresholds, self.precision, st)
+            self.ctx.launches += 2 + len(self.hidden)
+        auc = self.auc_result()
+        return float(losses[:steps].double().mean().item()) if steps else 0.0, auc
+
+    def predict(self, data, offset, rows, use_order=False):
+        """Sigmoid outputs of one inference mini-batch (device tensor) -- test hook."""
+        probs = torch.zeros(rows, dtype=torch.float32, device=self.device)
+        loss = torch.zeros(1, dtype=torch.float32, device=self.device)
+        b = self._batch(data, offset, rows, use_order)
+        self.ctx.call("mamdr_mlp_eval_step", C.byref(self.desc), C.byref(b), _ptr(self.user_table),
+                      _ptr(self.item_table), _ptr(self.params), _ptr(self.ws), self.ws_bytes, _ptr(loss),
+                      _ptr(probs), None, None, 0, self.precision, self.stream)
+        self.ctx.launches += 2 + len(self.hidden)
+        return probs, loss
+
+    def auc_result(self):
+        self.ctx.call("mamdr_auc_result", _ptr(self.auc_acc), self.num_thresholds, _ptr(self._auc_out), self.stream)
+        self.ctx.launches += 1
+        return float(self._auc_out.item())
+
+    # ---- persistence (the reference writes Keras h5; SURVEY.md 8(f) row f3 keeps the directory layout)
+    def save_weights(self, path):
+        torch.save({"names": self.layout.names, "shapes": self.layout.shapes,
+                    "weights": [w.cpu() for w in self.layout.views(self.params)]}, path)
+
+    def load_weights(self, path):
+        blob = torch.load(path, map_location="cpu")
+        if blob["names"] != self.layout.names:
+            raise ValueError("checkpoint layout mismatch")
+        self.params.copy_(torch.from_numpy(self.layout.pack([w.numpy() for w in blob["weights"]])))

@@ -1,0 +1,141 @@
+"""MAMDR = Domain Negotiation on the shared parameters + Domain Regularization on the
+domain-specific parameters -- mirrors ``/root/reference/model_zoo/mamdr.py`` (``train`` :18-166 and
+the update helpers :168-196).  Control flow is the reference's; every weight set is a device arena
+and every update is one fused sweep in ``libmamdr_b200.so`` (no host round trips).
+"""
+import torch
+
+from .engine import _ptr
+from .maml import MetaWeights
+from .specific_base_model import SpecificBase
+
+
+class MAMDR(SpecificBase):
+    def __init__(self, base_model):
+        super(MAMDR, self).__init__(base_model)
+
+    def train(self):
+        self.log("Start MAMDR on model: {}".format(self.model_config['name']))
+        self.prepare()
+        for epoch in range(self.train_config['epoch']):              # :41
+            self.log("Epoch: {}".format(epoch), "-" * 30)
+            self.train_epoch(epoch)
+            if epoch % self.train_config['val_every_step'] == 0:     # :145-159
+                val_avg_loss, val_avg_auc, val_domain_loss, val_domain_auc = self.val()
+                val_metric = val_domain_auc[self.train_config['target_domain']] \
+                    if self.train_config['target_domain'] >= 0 else val_avg_auc
+                if self.early_stop_step(val_metric):
+                    break
+                self.log("Test Result: ")
+                self.val_and_test("test")
+
+    def prepare(self):
+        """:26-37 -- theta = the model's first initialisation; theta_d^0 = an independent
+        re-initialisation per domain; optimizer slots zeroed; meta sequence built."""
+        self._get_model_meta_parms()
+        self.meta_weights = self._get_meta_weights()
+        self.domain_weights = {}
+        for domain_idx in range(self.n_domain):
+            self.init_layer(self.model)
+            self.domain_weights[domain_idx] = self._get_meta_weights()
+        self.model.reset_optimizer()
+        self.train_sequence = self.build_meta_data_split()
+        self._accum = None
+
+    def train_epoch(self, epoch=0):
+        """One MAMDR meta-step: the body of the epoch loop, :44-143."""
+        tc = self.train_config
+        beta = tc['meta_learning_rate']
+        if tc['shuffle_sequence']:                                   # :45-46
+            self.train_sequence = self.schedule.shuffle_sequence(self.train_sequence)
+        train_sequence = self.train_sequence
+
+        # ---- Update Shared (DN), :48-57
+        self._set_model_meta_parms(self.meta_weights)
+        for idx in train_sequence:
+            self.run_train_pass(idx)
+        self._update_meta_weight(self.meta_weights, meta_lr=beta)
+
+        # ---- Update specific (DR), :59-108
+        batch_mode = "batch" in self.model_config['name']
+        for idx in train_sequence:
+            d = self.dataset.train_dataset[idx]
+            candidate_domains = list(train_sequence)
+            candidate_domains.remove(idx)
+            aux_idxs = self.schedule.sample_support(candidate_domains, tc['sample_num'])   # :68
+            if tc['add_query_domain']:
+                aux_idxs = list(aux_idxs) + [idx]
+            theta_i = self.domain_weights[idx]
+            # merged = theta (+|*) theta_i is never materialised on the host: model <- merged (:72,78)
+            self._set_model_merged(self.meta_weights, theta_i)
+            if batch_mode:
+                self._zero_accum()
+            for k, aux_idx in enumerate(aux_idxs):
+                self.log(f"Support Domain: {aux_idx}, Query Domain: {idx}")
+                self.run_train_pass(aux_idx)                         # :85-86
+                train_step = d['n_step']                             # :92-97
+                if tc['domain_regulation_step'] > 0:
+                    train_step = min(train_step, tc['domain_regulation_step'])
+                self.run_train_pass(idx, train_step)
+                if batch_mode:                                       # :100-101
+                    self._accumulate_grad(theta_i)
+                    self._set_model_merged(self.meta_weights, theta_i)
+                else:                                                # :103-105 + next iteration's :78
+                    self._dr_update(theta_i, beta)
+            if batch_mode:                                           # :107-108
+                self._update_meta_weight_by_grads(theta_i)
+
+            if tc['finetune_every_epoch']:                           # :110-143
+                merged = self._merge_weights(self.meta_weights, theta_i)
+                self._set_model_meta_parms(merged)
+                for m in self.model.stateful_metric_functions:
+                    m.reset_states()
+                self.run_train_pass(idx)
+                self._update_domain_weights(theta_i, merged)
+
+    # ---- :168-171
+    def _update_domain_weights(self, domain_weights, merged_weights):
+        m = self.model
+        for n, (out, a, b) in self._ranges(domain_weights.flat, m.params, merged_weights.flat):
+            m.ctx.call("mamdr_sub", _ptr(out), _ptr(a), _ptr(b), n, m.stream)
+            m.ctx.launches += 1
+
+    # ---- :173-180
+    def _update_meta_weight(self, update_vars, merged_weights=None, meta_lr=1):
+        """update += (model - old) * meta_lr with old = merged_weights if given else update itself."""
+        m = self.model
+        old = merged_weights if merged_weights is not None else update_vars
+        for n, (upd, model, o) in self._ranges(update_vars.flat, m.params, old.flat):
+            m.ctx.call("mamdr_axpy_diff", _ptr(upd), _ptr(model), _ptr(o), meta_lr, n, m.stream)
+            m.ctx.launches += 1
+
+    def _dr_update(self, theta_i, beta):
+        """Fused :103-105 and the following :78: theta_i += (model - (theta (+|*) theta_i)) * beta, then
+        model <- theta (+|*) theta_i.  20 B / parameter, one sweep."""
+        m = self.model
+        for n, (ti, th, model) in self._ranges(theta_i.flat, self.meta_weights.flat, m.params):
+            m.ctx.call("mamdr_dr_update", _ptr(ti), _ptr(th), _ptr(model), beta, n, self._merge_method(),
+                       _ptr(model), m.stream)
+            m.ctx.launches += 1
+
+    # ---- :182-196 ("batch" names)
+    def _zero_accum(self):
+        if self._accum is None:
+            self._accum = torch.zeros_like(self.model.params)
+        else:
+            self._accum.zero_()
+
+    def _accumulate_grad(self, theta_i):
+        m = self.model
+        for n, (acc, model, th, ti) in self._ranges(self._accum, m.params, self.meta_weights.flat, theta_i.flat):
+            m.ctx.call("mamdr_dr_accumulate", _ptr(acc), _ptr(model), _ptr(th), _ptr(ti), n, self._merge_method(),
+                       m.stream)
+            m.ctx.launches += 1
+
+    def _update_meta_weight_by_grads(self, theta_i):
+        m = self.model
+        tc = self.train_config
+        for n, (ti, acc) in self._ranges(theta_i.flat, self._accum):
+            m.ctx.call("mamdr_dr_apply_accum", _ptr(ti), _ptr(acc), float(tc['sample_num']),
+                       tc['meta_learning_rate'], n, m.stream)
+            m.ctx.launches += 1

@@ -1,0 +1,239 @@
+"""Domain Negotiation / Domain Regularization outer loops, numpy restatement.
+TEST INFRASTRUCTURE (see oracle/__init__.py).
+
+Follows, line by line, the host control flow of the reference:
+  * ``model_zoo/domain_negotiation.py:37-116,118-123``   (DN, Alg. 1)
+  * ``model_zoo/mamdr.py:41-159,168-196``               (DN on shared + DR on specific)
+  * ``model_zoo/specific_base_model.py:44-97,164-172``  (early stop snapshots, val/test, merge)
+  * ``model_zoo/base_model.py:111-175,208-224``         (plain val/test, weighted AUC, early stop)
+  * ``model_zoo/DeepCTR/deepctr.py:63-93``              (joint 'alternate' training)
+
+Python's ``random`` is unseeded in the reference (``run.py:26`` seeds TF only), so the
+domain order, the DR support samples and the per-pass batch order are *injected* through a
+``schedule`` object exposing ``shuffle_sequence(seq)``, ``sample_support(candidates, k)`` and
+``batch_order(domain, n)``; the product consumes the same object type
+(``mamdr_b200/schedule.py``) so both sides see identical draws in identical order.
+
+``data`` is ``{'train'|'val'|'test': {domain: {'uid','pid','label'}}}`` of numpy arrays.
+"""
+from copy import deepcopy
+
+import numpy as np
+
+
+def n_steps(n, batch_size):
+    return int(np.ceil(n / float(batch_size)))  # utils/dataset.py:25
+
+
+def train_pass(model, d, domain, order, batch_size, max_steps=0, optimizer='adam', sgd_lr=None):
+    """One full pass (``train_step`` mini-batches, ragged tail kept) over a domain's train set."""
+    n = len(order)
+    steps = n_steps(n, batch_size)
+    if max_steps and max_steps > 0:
+        steps = min(steps, max_steps)
+    tot, auc = 0.0, 0.0
+    for s in range(steps):
+        sel = order[s * batch_size:(s + 1) * batch_size]
+        loss, auc = model.train_on_batch(d['uid'][sel], d['pid'][sel], domain, d['label'][sel],
+                                         optimizer=optimizer, sgd_lr=sgd_lr)
+        tot += loss
+    return tot / max(steps, 1), auc, steps
+
+
+def merge_weights(shared, specific, method):  # specific_base_model.py:164-172
+    if method == 'plus':
+        return [x + y for x, y in zip(shared, specific)]
+    if method == 'times':
+        return [x * y for x, y in zip(shared, specific)]
+    return []
+
+
+def weighted_auc(data, mode, domain_auc):  # base_model.py:157-175
+    num = sum(len(data[mode][k]['uid']) * v for k, v in domain_auc.items())
+    den = sum(len(data[mode][k]['uid']) for k in domain_auc)
+    return num / den
+
+
+class EarlyStop(object):  # base_model.py:202-224
+    def __init__(self, patience):
+        self.patience, self.counter, self.best_metric, self.early_stop = patience, 0, None, False
+
+    def step(self, metric, on_improve):
+        if self.best_metric is None:
+            self.best_metric = metric
+            on_improve()
+        elif metric <= self.best_metric:
+            self.counter += 1
+            if self.counter >= self.patience:
+                self.early_stop = True
+        else:
+            on_improve()
+            self.best_metric = metric
+            self.counter = 0
+        return self.early_stop
+
+
+class OracleDN(object):
+    """``DomainNegotiation.train`` with ``target_domain=-1`` (every shipped config)."""
+
+    def __init__(self, model, data, train_config, batch_size, schedule):
+        self.model, self.data, self.tc, self.bs, self.schedule = model, data, train_config, batch_size, schedule
+        self.meta_weights = model.get_weights()                     # :29
+        self.sequence = sorted(data['train'].keys())                # :135-141
+        if isinstance(train_config.get('meta_sequence'), list):    # :142-145
+            if len(train_config['meta_sequence']) != len(self.sequence):
+                raise ValueError("All the domains must be given in the sequence")
+            self.sequence = list(train_config['meta_sequence'])
+        self.es = EarlyStop(train_config['patience'])
+        self.best_weights = None
+        self.log = []
+
+    def train_epoch(self):
+        tc = self.tc
+        if tc['shuffle_sequence']:                                   # :41-42
+            self.sequence = self.schedule.shuffle_sequence(self.sequence)
+        self.model.set_weights(self.meta_weights)                    # :50
+        for idx in self.sequence:                                    # :53-84
+            self.model.auc.reset_states()                            # :56-57
+            d = self.data['train'][idx]
+            order = self.schedule.batch_order(idx, len(d['uid']))
+            loss, auc, steps = train_pass(self.model, d, idx, order, self.bs, tc.get('meta_train_step', 0))
+            self.log.append((idx, loss, auc, steps))
+        new = self.model.get_weights()                               # :118-123
+        beta = tc['meta_learning_rate']
+        for var in range(len(new)):
+            self.meta_weights[var] += (new[var] - self.meta_weights[var]) * beta
+        self.model.set_weights(self.meta_weights)                    # :88
+
+    def val_and_test(self, mode, weights=None):  # base_model.py:111-144
+        if mode not in ('val', 'test'):
+            raise ValueError("Mode can be either val or test, not: {}".format(mode))
+        if mode == 'test' and self.best_weights is not None:
+            self.model.set_weights(self.best_weights)                # load_model(best h5), :121
+        domain_loss, domain_auc = {}, {}
+        for idx, d in self.data[mode].items():
+            l, a = self.model.evaluate(d['uid'], d['pid'], idx, d['label'], self.bs)
+            domain_loss[idx], domain_auc[idx] = float(l), float(a)
+        avg_loss = sum(domain_loss.values()) / len(domain_loss)
+        avg_auc = sum(domain_auc.values()) / len(domain_auc)
+        return avg_loss, avg_auc, domain_loss, domain_auc
+
+    def early_stop_step(self, metric):
+        def keep():
+            self.best_weights = self.model.get_weights()             # save_model(h5)
+        return self.es.step(metric, keep)
+
+
+class OracleMAMDR(object):
+    """``MAMDR.train`` (``model_zoo/mamdr.py:18-166``) with ``target_domain=-1``."""
+
+    def __init__(self, model, data, train_config, batch_size, schedule, domain_weights, name='mlp_meta_mamdr'):
+        self.model, self.data, self.tc, self.bs, self.schedule = model, data, train_config, batch_size, schedule
+        self.name = name
+        self.meta_weights = model.get_weights()                      # :29
+        # :30-33  theta_d^0 = an independent re-initialisation of every layer (injected)
+        self.domain_weights = {k: [np.array(w, dtype=model.dtype) for w in v] for k, v in domain_weights.items()}
+        self.sequence = sorted(data['train'].keys())
+        if isinstance(train_config.get('meta_sequence'), list):
+            if len(train_config['meta_sequence']) != len(self.sequence):
+                raise ValueError("All the domains must be given in the sequence")
+            self.sequence = list(train_config['meta_sequence'])
+        self.es = EarlyStop(train_config['patience'])
+        self.best_shared_weights = None
+        self.best_domain_weights = None
+
+    def _update_meta_weight(self, update_vars, merged_weights=None, meta_lr=1):  # :173-180
+        new_vars = self.model.get_weights()
+        old_vars = merged_weights if merged_weights is not None else update_vars
+        for var in range(len(new_vars)):
+            update_vars[var] += (new_vars[var] - old_vars[var]) * meta_lr
+
+    def _accumulate_grad(self, accum, old_vars, shared):  # :182-191
+        new_vars = self.model.get_weights()
+        for var in range(len(accum)):
+            if self.tc['merged_method'] == 'plus':
+                accum[var] += (new_vars[var] - old_vars[var]) / 1
+            elif self.tc['merged_method'] == 'times':
+                accum[var] += (new_vars[var] - old_vars[var]) * shared[var] / 1
+
+    def _update_meta_weight_by_grads(self, grads, old_vars):  # :193-196
+        for var in range(len(old_vars)):
+            old_vars[var] += grads[var] / self.tc['sample_num'] * self.tc['meta_learning_rate']
+            grads[var] = np.zeros_like(grads[var])
+
+    def train_epoch(self):
+        tc, model = self.tc, self.model
+        beta = tc['meta_learning_rate']
+        if tc['shuffle_sequence']:                                   # :45-46
+            self.sequence = self.schedule.shuffle_sequence(self.sequence)
+        seq = self.sequence
+        # ---- DN on the shared parameters (:48-57)
+        model.set_weights(self.meta_weights)
+        for idx in seq:
+            d = self.data['train'][idx]
+            train_pass(model, d, idx, self.schedule.batch_order(idx, len(d['uid'])), self.bs)
+        self._update_meta_weight(self.meta_weights, meta_lr=beta)
+        # ---- DR on the specific parameters (:59-108)
+        for idx in seq:
+            d = self.data['train'][idx]
+            cands = list(seq)
+            cands.remove(idx)
+            aux_idxs = self.schedule.sample_support(cands, tc['sample_num'])
+            if tc['add_query_domain']:
+                aux_idxs = list(aux_idxs) + [idx]
+            merged = merge_weights(self.meta_weights, self.domain_weights[idx], tc['merged_method'])
+            accum = [np.zeros_like(w) for w in merged]
+            for aux_idx in aux_idxs:
+                model.set_weights(merged)                            # :78
+                aux_d = self.data['train'][aux_idx]
+                train_pass(model, aux_d, aux_idx, self.schedule.batch_order(aux_idx, len(aux_d['uid'])), self.bs)
+                train_pass(model, d, idx, self.schedule.batch_order(idx, len(d['uid'])), self.bs,
+                           tc.get('domain_regulation_step', 0))
+                if 'batch' in self.name:                             # :100-105
+                    self._accumulate_grad(accum, merged, self.meta_weights)
+                else:
+                    self._update_meta_weight(self.domain_weights[idx], merged, meta_lr=beta)
+                    merged = merge_weights(self.meta_weights, self.domain_weights[idx], tc['merged_method'])
+            if 'batch' in self.name:                                 # :107-108
+                self._update_meta_weight_by_grads(accum, self.domain_weights[idx])
+            if tc.get('finetune_every_epoch'):                       # :110-143
+                merged = merge_weights(self.meta_weights, self.domain_weights[idx], tc['merged_method'])
+                model.set_weights(merged)
+                model.auc.reset_states()
+                train_pass(model, d, idx, self.schedule.batch_order(idx, len(d['uid'])), self.bs)
+                new_vars = model.get_weights()                       # :168-171
+                for var in range(len(new_vars)):
+                    self.domain_weights[idx][var] = new_vars[var] - merged[var]
+
+    def val_and_test(self, mode):  # specific_base_model.py:64-97
+        if mode == 'val':
+            shared, specific = deepcopy(self.meta_weights), deepcopy(self.domain_weights)
+        elif mode == 'test':
+            shared, specific = deepcopy(self.best_shared_weights), deepcopy(self.best_domain_weights)
+        else:
+            raise ValueError("Mode can be either val or test, not: {}".format(mode))
+        domain_loss, domain_auc = {}, {}
+        for idx, d in self.data[mode].items():
+            self.model.set_weights(merge_weights(shared, specific[idx], self.tc['merged_method']))
+            l, a = self.model.evaluate(d['uid'], d['pid'], idx, d['label'], self.bs)
+            domain_loss[idx], domain_auc[idx] = float(l), float(a)
+        avg_loss = sum(domain_loss.values()) / len(domain_loss)
+        avg_auc = sum(domain_auc.values()) / len(domain_auc)
+        return avg_loss, avg_auc, domain_loss, domain_auc
+
+    def early_stop_step(self, metric):  # specific_base_model.py:44-62
+        def keep():
+            self.best_shared_weights = deepcopy(self.meta_weights)
+            self.best_domain_weights = deepcopy(self.domain_weights)
+        return self.es.step(metric, keep)
+
+
+def joint_train_epoch(model, data, batch_size, schedule, sequence):
+    """``DeepCTR.train`` inner part (``model_zoo/DeepCTR/deepctr.py:70-78``): shuffle the
+    domains, then one full ``model.fit`` pass per domain with the single Adam."""
+    sequence = schedule.shuffle_sequence(sequence)
+    for idx in sequence:
+        d = data['train'][idx]
+        model.auc.reset_states()   # Keras fit() resets stateful metrics at epoch start
+        train_pass(model, d, idx, schedule.batch_order(idx, len(d['uid'])), batch_size)
+    return sequence

@@ -1,0 +1,209 @@
+"""-m gpu: bit-exact parity of the integer / element-wise kernels against the oracle, through the C-ABI."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import auc as oauc
+from oracle.mlp import AdamState
+
+pytestmark = pytest.mark.gpu
+
+from gpu_util import bits, ctx, dev, ptr, stream  # noqa: E402
+
+
+# ---- K1 gather -------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rows,dim,n", [(6932, 128, 1024), (1000, 128, 977), (50, 4, 1), (300, 36, 4097),
+                                        (23778, 128, 100000)])
+def test_gather_bit_exact(rows, dim, n):
+    rng = np.random.default_rng(rows + n)
+    table = rng.standard_normal((rows, dim)).astype(np.float32)
+    table[rng.integers(0, rows, 8)] = np.float32(np.nan)  # payload bits must survive
+    ids = rng.integers(0, rows, n).astype(np.int32)
+    ids[: min(n, 16)] = ids[0]  # duplicates
+    t, i = dev(table), dev(ids)
+    out = torch.full((n, dim + 4), -7.0, device="cuda")
+    ctx().call("mamdr_gather_f32", ptr(t), rows, dim, ptr(i), n, ptr(out), dim + 4, stream())
+    got = out.cpu().numpy()
+    np.testing.assert_array_equal(bits(got[:, :dim]), bits(table[ids]))
+    assert np.all(got[:, dim:] == -7.0)  # the stride padding is untouched
+
+
+def test_gather_empty_and_errors():
+    from mamdr_b200._lib import MamdrError
+    t = torch.zeros(4, 8, device="cuda")
+    i = torch.zeros(1, dtype=torch.int32, device="cuda")
+    o = torch.zeros(1, 8, device="cuda")
+    ctx().call("mamdr_gather_f32", ptr(t), 4, 8, ptr(i), 0, ptr(o), 8, stream())  # n == 0 is a no-op
+    with pytest.raises(MamdrError):
+        ctx().call("mamdr_gather_f32", ptr(t), 4, 6, ptr(i), 1, ptr(o), 8, stream())  # dim % 4
+    with pytest.raises(MamdrError):
+        ctx().call("mamdr_gather_f32", None, 4, 8, ptr(i), 1, ptr(o), 8, stream())
+    with pytest.raises(MamdrError):
+        ctx().call("mamdr_gather_f32", ptr(t), 4, 8, ptr(i), 1, ptr(o), 4, stream())  # stride < dim
+
+
+# ---- K6 dedup ----------------------------------------------------------------------------------------------
+def _oracle_dedup(ids, rows):
+    uniq = np.unique(ids)
+    out = np.zeros((len(uniq), rows.shape[1]), dtype=np.float32)
+    first = np.ones(len(uniq), bool)
+    pos = {int(u): k for k, u in enumerate(uniq)}
+    for i, r in zip(ids, rows):      # sequential adds in batch order == np.add.at order
+        k = pos[int(i)]
+        out[k] = r if first[k] else (out[k] + r).astype(np.float32)
+        first[k] = False
+    return uniq.astype(np.int32), out
+
+
+@pytest.mark.parametrize("n,n_ids,dim", [(1024, 200, 128), (977, 100000, 128), (1, 5, 8), (4096, 3, 64),
+                                         (8192, 5000, 128)])
+def test_scatter_dedup_bit_exact(n, n_ids, dim):
+    rng = np.random.default_rng(n)
+    ids = rng.integers(0, n_ids, n).astype(np.int32)
+    rows = rng.standard_normal((n, dim)).astype(np.float32)
+    lib = ctx().lib
+    ws = torch.zeros(lib.mamdr_scatter_workspace_bytes(n), dtype=torch.uint8, device="cuda")
+    uo = torch.full((n,), -1, dtype=torch.int32, device="cuda")
+    ro = torch.zeros(n, dim, device="cuda")
+    nu = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ctx().call("mamdr_scatter_dedup_f32", ptr(dev(ids)), ptr(dev(rows)), dim, n, dim, ptr(uo), ptr(ro), ptr(nu),
+               ptr(ws), ws.numel(), stream())
+    k = int(nu.item())
+    eu, er = _oracle_dedup(ids, rows)
+    assert k == len(eu)
+    np.testing.assert_array_equal(uo[:k].cpu().numpy(), eu)           # sorted unique ids, bit-exact
+    np.testing.assert_array_equal(bits(ro[:k].cpu().numpy()), bits(er))
+
+
+# ---- K7 Adam / SGD --------------------------------------------------------------------------------------------
+def test_adam_bit_exact_over_steps():
+    rng = np.random.default_rng(3)
+    n = 4096 + 32
+    w = [rng.standard_normal(n).astype(np.float32)]
+    st = AdamState(w, lr=1e-3)
+    lib = ctx().lib
+    p, m, v = dev(w[0]), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    state = torch.zeros(lib.mamdr_opt_state_bytes(), dtype=torch.uint8, device="cuda")
+    ctx().call("mamdr_opt_state_init", ptr(state), 0.9, 0.999, stream())
+    for t in range(25):
+        g = (rng.standard_normal(n) * 10.0 ** rng.integers(-6, 1)).astype(np.float32)
+        g[:7] = 0.0
+        st.apply(w, [g])
+        ctx().call("mamdr_adam_step", ptr(p), ptr(m), ptr(v), ptr(dev(g)), n, ptr(state), 1e-3, 0.9, 0.999, 1e-8,
+                   stream())
+        np.testing.assert_array_equal(bits(p.cpu().numpy()), bits(w[0]), err_msg="step %d" % t)
+    np.testing.assert_array_equal(bits(m.cpu().numpy()), bits(st.m[0]))
+    np.testing.assert_array_equal(bits(v.cpu().numpy()), bits(st.v[0]))
+    step, b1, b2 = C.c_int64(), C.c_float(), C.c_float()
+    ctx().call("mamdr_opt_state_read", ptr(state), C.byref(step), C.byref(b1), C.byref(b2), stream())
+    assert step.value == 25 and np.float32(b1.value) == st.b1pow and np.float32(b2.value) == st.b2pow
+
+
+def test_sgd_bit_exact():
+    rng = np.random.default_rng(4)
+    n = 1024
+    w = rng.standard_normal(n).astype(np.float32)
+    g = rng.standard_normal(n).astype(np.float32)
+    lib = ctx().lib
+    state = torch.zeros(lib.mamdr_opt_state_bytes(), dtype=torch.uint8, device="cuda")
+    ctx().call("mamdr_opt_state_init", ptr(state), 0.9, 0.999, stream())
+    p = dev(w)
+    ctx().call("mamdr_sgd_step", ptr(p), ptr(dev(g)), n, ptr(state), 0.001, stream())
+    np.testing.assert_array_equal(bits(p.cpu().numpy()), bits(w - g * np.float32(0.001)))
+
+
+# ---- K9 / K10 meta ops ----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("method", [0, 1])
+def test_meta_ops_bit_exact(method):
+    rng = np.random.default_rng(5)
+    n = 141088
+    th, ti, mo = (rng.standard_normal(n).astype(np.float32) for _ in range(3))
+    beta = np.float32(0.1)
+    mg = (lambda a, b: a + b) if method == 0 else (lambda a, b: a * b)
+    c = ctx()
+    # merge
+    out = torch.zeros(n, device="cuda")
+    c.call("mamdr_merge", ptr(out), ptr(dev(th)), ptr(dev(ti)), n, method, stream())
+    np.testing.assert_array_equal(bits(out.cpu().numpy()), bits(mg(th, ti)))
+    # DN: theta += (model - theta) * beta ; model <- theta
+    t, m_ = dev(th), dev(mo)
+    c.call("mamdr_dn_update", ptr(t), ptr(m_), 0.1, n, ptr(m_), stream())
+    exp = th + (mo - th) * beta
+    np.testing.assert_array_equal(bits(t.cpu().numpy()), bits(exp))
+    np.testing.assert_array_equal(bits(m_.cpu().numpy()), bits(exp))
+    # DR: theta_i += (model - merged) * beta ; model <- theta (+|*) theta_i
+    tii, m_ = dev(ti), dev(mo)
+    c.call("mamdr_dr_update", ptr(tii), ptr(dev(th)), ptr(m_), 0.1, n, method, ptr(m_), stream())
+    nti = ti + (mo - mg(th, ti)) * beta
+    np.testing.assert_array_equal(bits(tii.cpu().numpy()), bits(nti))
+    np.testing.assert_array_equal(bits(m_.cpu().numpy()), bits(mg(th, nti)))
+    # batch variant: accumulate + apply
+    acc0 = rng.standard_normal(n).astype(np.float32)
+    acc = dev(acc0)
+    c.call("mamdr_dr_accumulate", ptr(acc), ptr(dev(mo)), ptr(dev(th)), ptr(dev(ti)), n, method, stream())
+    d = mo - mg(th, ti)
+    eacc = acc0 + (d if method == 0 else d * th)
+    np.testing.assert_array_equal(bits(acc.cpu().numpy()), bits(eacc))
+    tii = dev(ti)
+    c.call("mamdr_dr_apply_accum", ptr(tii), ptr(acc), 5.0, 0.1, n, stream())
+    np.testing.assert_array_equal(bits(tii.cpu().numpy()), bits(ti + eacc / 5 * beta))
+    assert float(acc.abs().max()) == 0.0
+    # sub, axpy_diff, copy
+    out = torch.zeros(n, device="cuda")
+    c.call("mamdr_sub", ptr(out), ptr(dev(mo)), ptr(dev(th)), n, stream())
+    np.testing.assert_array_equal(bits(out.cpu().numpy()), bits(mo - th))
+    u = dev(ti)
+    c.call("mamdr_axpy_diff", ptr(u), ptr(dev(mo)), ptr(dev(th)), 0.1, n, stream())
+    np.testing.assert_array_equal(bits(u.cpu().numpy()), bits(ti + (mo - th) * beta))
+    c.call("mamdr_copy", ptr(out), ptr(u), n, stream())
+    assert torch.equal(out, u)
+
+
+def test_meta_idempotence_and_linearity_full_size():
+    """size-independent properties at Amazon-6 arena size (79.3 M floats)."""
+    n = 79301152
+    g = torch.Generator(device="cuda").manual_seed(1)
+    th = torch.randn(n, device="cuda", generator=g)
+    mo = torch.randn(n, device="cuda", generator=g)
+    c = ctx()
+    t = th.clone()
+    c.call("mamdr_dn_update", ptr(t), ptr(th), 0.1, n, None, stream())   # model == theta -> fixed point
+    assert torch.equal(t, th)
+    t = th.clone()
+    c.call("mamdr_dn_update", ptr(t), ptr(mo), 1.0, n, None, stream())   # beta = 1 -> theta + (model - theta)
+    assert torch.equal(t, th + (mo - th))
+    z = torch.zeros(n, device="cuda")
+    c.call("mamdr_merge", ptr(z), ptr(th), ptr(torch.zeros(n, device="cuda")), n, 0, stream())
+    assert torch.equal(z, th)
+
+
+# ---- K8 AUC -----------------------------------------------------------------------------------------------------
+def test_auc_kat_and_counts_bit_exact():
+    c = ctx()
+    # the reference's doc-string example (utils/auc.py:44-56)
+    thr3 = dev(oauc.thresholds(3))
+    acc = torch.zeros(4, 3, device="cuda")
+    c.call("mamdr_auc_update", ptr(dev(np.float32([0, 0.5, 0.3, 0.9]))), ptr(dev(np.float32([0, 0, 1, 1]))), 4,
+           ptr(acc), ptr(thr3), 3, stream())
+    np.testing.assert_array_equal(acc.cpu().numpy(), [[2, 1, 0], [2, 0, 0], [0, 1, 2], [0, 2, 2]])
+    out = torch.zeros(1, device="cuda")
+    c.call("mamdr_auc_result", ptr(acc), 3, ptr(out), stream())
+    assert abs(out.item() - 0.75) < 1e-7
+    # 500 thresholds, streaming, predictions sitting exactly on thresholds and on 0 / 1
+    rng = np.random.default_rng(9)
+    thr = oauc.thresholds(500)
+    o = oauc.AUC(500)
+    acc = torch.zeros(4, 500, device="cuda")
+    for n in (1024, 1024, 977, 1, 5000):
+        y = (rng.random(n) < 0.3).astype(np.float32)
+        p = np.clip(0.25 * y + rng.random(n) * 0.75, 0, 1).astype(np.float32)
+        p[: min(n, 64)] = thr[rng.integers(1, 499, min(n, 64))]
+        if n > 2:
+            p[-1], p[-2] = 0.0, 1.0
+        o.update_state(y, p)
+        c.call("mamdr_auc_update", ptr(dev(p)), ptr(dev(y)), n, ptr(acc), ptr(dev(thr)), 500, stream())
+    np.testing.assert_array_equal(acc.cpu().numpy(), o.acc)
+    c.call("mamdr_auc_result", ptr(acc), 500, ptr(out), stream())
+    assert abs(out.item() - o.result()) < 2e-6
