@@ -1,0 +1,405 @@
+"""bench.py -- MAMDR meta-train throughput on the synthetic Taobao-10 shape (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload Taobao-10]
+
+A "step" is ONE MAMDR meta-step (meta-epoch): DN over the shuffled domain sequence + DR
+(sample_num + 1 support/query pass pairs per query domain) at batch 1024, exactly the body of the
+epoch loop of /root/reference/model_zoo/mamdr.py:41-143, validation / test excluded.
+value = real samples pushed through training mini-batches per second, whole job.
+
+  --impl b200       our path: one process per GPU (torchrun for N > 1), DN replicated, DR query domains
+                    sharded, one NCCL all-reduce per meta-step.  Prints ONE JSON line on rank 0.
+  --impl reference  the CPU oracle restatement of the reference's TF path (TF 1.12 cannot be installed:
+                    BASELINE.md section 2) timed on the host cores, a bounded sample per step.
+"""
+import argparse
+import copy
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD_CONFIG = {"Taobao-10": "config/Taobao-10/deepctr_DN+DR.json", "Taobao-20": "config/Taobao_20/deepctr_DN+DR.json",
+                   "Taobao-30": "config/Taobao_30/deepctr_DN+DR.json"}
+METRIC = "MAMDR meta-train samples/sec (Taobao-10 shape)"
+
+
+def load_config(workload):
+    with open(os.path.join(ROOT, WORKLOAD_CONFIG[workload])) as f:
+        c = json.load(f)
+    c.setdefault("b200", {})["verbose"] = False
+    c["train"]["result_save_path"] = "/tmp/mamdr_bench/result"
+    c["train"]["checkpoint_path"] = "/tmp/mamdr_bench/checkpoint"
+    return c
+
+
+# ---- clocks during the timed region (B200_PROFILING.md) ------------------------------------------------
+class ClockSampler(object):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---- the reference arm / cpu_baseline: the oracle on the host cores --------------------------------------
+def oracle_sample_runner(config, max_batches):
+    """Returns (run_once, cores, description).  run_once() executes the first `max_batches`
+    mini-batches of a MAMDR meta-step (DN passes first, then DR) with the CPU oracle and returns
+    (samples, seconds)."""
+    import numpy as np
+    import torch
+    from mamdr_b200 import synth
+    from mamdr_b200.layout import init_mlp_weights, mlp_layout
+    from mamdr_b200.schedule import Schedule
+    from oracle import build as obuild
+    from oracle.mlp import MLPSpec, OracleMLP
+    try:
+        obuild.build()
+    except Exception:
+        pass
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sc = config["dataset"]["synthetic"]
+    g = synth.generate(sc["shape"], seed=sc.get("seed", config["dataset"]["seed"]), scale=sc.get("scale", 1.0),
+                       signal=sc.get("signal", 1.0))
+    mc = config["model"]
+    emb = (mc["user_dim"], mc["item_dim"], mc["domain_dim"])
+    lo = mlp_layout(g["n_uid"], g["n_pid"], g["n_domain"], emb, mc["hidden_dim"], False)
+    spec = MLPSpec(g["n_uid"], g["n_pid"], g["n_domain"], emb, tuple(mc["hidden_dim"]), dropout=mc["dropout"])
+    model = OracleMLP(spec, init_mlp_weights(lo, [123, 0]), g["user_emb"], g["item_emb"],
+                      lr=config["train"]["learning_rate"])
+    bs = config["dataset"]["batch_size"]
+    sched = Schedule(config["dataset"]["seed"])
+    D = g["n_domain"]
+
+    def run_once():
+        seq = sched.shuffle_sequence(list(range(D)))
+        done, samples = 0, 0
+        t0 = time.perf_counter()
+        theta = model.get_weights()
+        while done < max_batches:      # DN-style sequential passes over the shuffled domains, repeated
+            for idx in seq:
+                d = g["train"][idx]
+                order = sched.batch_order(idx, len(d["uid"]))
+                for s in range(0, len(order), bs):
+                    sel = order[s:s + bs]
+                    model.train_on_batch(d["uid"][sel], d["pid"][sel], idx, d["label"][sel])
+                    done += 1
+                    samples += len(sel)
+                    if done >= max_batches:
+                        break
+                if done >= max_batches:
+                    break
+            new = model.get_weights()     # the outer interpolation + set (numpy, as the reference does)
+            for a, b in zip(theta, new):
+                a += (b - a) * np.float32(0.1)
+            model.set_weights(theta)
+        return samples, time.perf_counter() - t0
+
+    desc = ("first %d mini-batches (batch %d) of a meta-step on synthetic %s, CPU oracle "
+            "(numpy + torch-CPU GEMM + C Philox/AUC)" % (max_batches, bs, sc["shape"]))
+    return run_once, cores, desc
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    config = load_config(args.workload)
+    per_step = 300
+    run_once, cores, desc = oracle_sample_runner(config, per_step)
+    for _ in range(args.warmup):
+        run_once()
+    tot_s, tot_t = 0, 0.0
+    for _ in range(args.steps):
+        s, t = run_once()
+        tot_s += s
+        tot_t += t
+    v = tot_s / tot_t
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_desc(config, args.workload, args.gpus),
+            "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": desc},
+            "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_desc(config, workload, n_gpus):
+    tc = config["train"]
+    return {"workload": "%s synthetic %s: DN + DR(sample_num=%d%s), batch %d, mlp %s, frozen 128-d embeddings, "
+                        "one meta-step per bench step" % (config["model"]["name"], workload, tc["sample_num"],
+                                                          "+query" if tc["add_query_domain"] else "",
+                                                          config["dataset"]["batch_size"],
+                                                          "/".join(str(h) for h in config["model"]["hidden_dim"])),
+            "parallelism": "dr-shard%d" % n_gpus if n_gpus > 1 else "single",
+            "precision": config.get("b200", {}).get("precision", "fp32"),
+            "l2": "working set (15.7 MB tables + 0.6 MB parameters) is L2-resident by construction; a 256 MiB "
+                  "buffer is written between timed steps to flush L2"}
+
+
+# ---- roofline of the dominant kernels (measured live with CUDA events) -----------------------------------
+def micro_rooflines(model, peaks, torch):
+    """HBM-scale micro-benchmarks of the two HBM-bound kernels named by the north star (gather, fused
+    Adam sweep) + the per-step launch mix.  Algorithmic bytes: gather 2*n*dim*4; Adam 28 B/param."""
+    import ctypes as C
+    from mamdr_b200.engine import _ptr
+    ctx = model.ctx
+    out = {}
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    st = model.stream
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    # gather: 4 Mi rows of 128 floats from a 2 Mi-row table (1 GiB) -> 2 GiB written, 2+ GiB read
+    rows, dim, n = 1 << 21, 128, 1 << 22
+    table = torch.empty(rows, dim, device=model.device).normal_()
+    ids = torch.randint(0, rows, (n,), dtype=torch.int32, device=model.device)
+    dst = torch.empty(n, dim, device=model.device)
+    for _ in range(3):
+        ctx.call("mamdr_gather_f32", _ptr(table), rows, dim, _ptr(ids), n, _ptr(dst), dim, st)
+    a, b = ev(), ev()
+    reps = 10
+    a.record()
+    for _ in range(reps):
+        ctx.call("mamdr_gather_f32", _ptr(table), rows, dim, _ptr(ids), n, _ptr(dst), dim, st)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / reps
+    gb = 2.0 * n * dim * 4 / 1e9
+    out["gather"] = {"bound": "hbm", "achieved": gb / (ms * 1e-3), "peak": hbm, "unit": "GB/s",
+                     "frac": gb / (ms * 1e-3) / hbm, "rows": n, "dim": dim, "ms": ms}
+    del table, ids, dst
+    # Adam sweep at the Amazon-6 arena size (79.3 M params)
+    P = 79301152
+    p = torch.empty(P, device=model.device).normal_()
+    m = torch.zeros(P, device=model.device)
+    v = torch.zeros(P, device=model.device)
+    g = torch.empty(P, device=model.device).normal_()
+    state = torch.zeros(ctx.lib.mamdr_opt_state_bytes(), dtype=torch.uint8, device=model.device)
+    ctx.call("mamdr_opt_state_init", _ptr(state), 0.9, 0.999, st)
+    for _ in range(3):
+        ctx.call("mamdr_adam_step", _ptr(p), _ptr(m), _ptr(v), _ptr(g), P, _ptr(state), 1e-3, 0.9, 0.999, 1e-8, st)
+    a, b = ev(), ev()
+    a.record()
+    for _ in range(reps):
+        ctx.call("mamdr_adam_step", _ptr(p), _ptr(m), _ptr(v), _ptr(g), P, _ptr(state), 1e-3, 0.9, 0.999, 1e-8, st)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / reps
+    gb = 28.0 * P / 1e9
+    out["adam"] = {"bound": "hbm", "achieved": gb / (ms * 1e-3), "peak": hbm, "unit": "GB/s",
+                   "frac": gb / (ms * 1e-3) / hbm, "params": P, "ms": ms}
+    return out
+
+
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import run as runpy
+    from mamdr_b200 import dist as mdist
+
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    rank, world = mdist.init_from_env("nccl")
+    if world != args.gpus:
+        raise SystemExit("--gpus %d but WORLD_SIZE is %d (launch N > 1 with torchrun)" % (args.gpus, world))
+    config = load_config(args.workload)
+    config["b200"]["device"] = "cuda:%d" % local_rank
+    if args.precision:
+        config["b200"]["precision"] = args.precision
+    wrapper = runpy.build(config)
+    base = wrapper.base_model
+    model = base.model
+    wrapper.prepare()
+    dev = model.device
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step(e2e):
+        """One meta-step.  e2e: the step's inputs (every domain's train columns) come from pinned host
+        memory inside the timed region and the per-pass losses of the last pass are read back."""
+        h2d = 0
+        if e2e:
+            for d in base.dataset.train_dataset.values():
+                dd = d["data"]
+                for k in ("uid", "pid", "label"):
+                    getattr(dd, k).copy_(pinned[(dd.domain, k)], non_blocking=True)
+                    h2d += pinned[(dd.domain, k)].numel() * 4
+        before = getattr(base, "h2d_bytes", 0)
+        wrapper.train_epoch(0)
+        h2d += getattr(base, "h2d_bytes", 0) - before
+        d2h = 0
+        if e2e:
+            host = base.last_pass_losses.cpu()   # D2H read of the step's result (per-batch losses of the last pass)
+            d2h = host.numel() * 4
+        return h2d, d2h
+
+    pinned = {}
+    for d in base.dataset.train_dataset.values():
+        dd = d["data"]
+        for k in ("uid", "pid", "label"):
+            pinned[(dd.domain, k)] = torch.from_numpy(dd.host[k]).pin_memory()
+
+    for _ in range(max(args.warmup, 3)):
+        one_step(False)
+    barrier()
+    # ---- device-resident timing: K steps, per-step CUDA events, L2 flushed between steps
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    base.samples_trained = 0
+    launches0 = model.ctx.launches
+    evs = []
+    barrier()
+    t_wall = time.perf_counter()
+    for _ in range(args.steps):
+        flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        one_step(False)
+        b.record()
+        evs.append((a, b))
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    clocks = sampler.stop()
+    ms = sum(a.elapsed_time(b) for a, b in evs)
+    launches = model.ctx.launches - launches0
+    my_samples = base.samples_trained
+    # whole-job samples: DN passes are replicated (count once), DR passes are sharded (sum over ranks)
+    dn_samples = args.steps * sum(d["n_data"] for d in base.dataset.train_dataset.values())
+    t = torch.tensor([ms, float(my_samples - dn_samples)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ms, dr_samples = float(tmax[0]), float(t[1])
+    else:
+        dr_samples = float(t[1])
+    total_samples = dn_samples + dr_samples
+    value = total_samples / (ms * 1e-3)
+
+    # ---- end-to-end through the public API with host buffers
+    for _ in range(2):
+        one_step(True)
+    barrier()
+    base.samples_trained = 0
+    t0 = time.perf_counter()
+    h2d = d2h = 0
+    for _ in range(args.steps):
+        x, y = one_step(True)
+        h2d, d2h = x, y
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = total_samples / float(t[0])
+
+    if rank != 0:
+        return
+    # ---- roofline + cpu baseline (rank 0)
+    steps_per_epoch = total_samples / args.steps / config["dataset"]["batch_size"]
+    P = sum(model.layout.numels)
+    alg_bytes_step = 1572864 + 12288 + 4096 + 2 * 4 * (P - model.n_domain * 128) + 28 * P   # 6.65 MB
+    flops_step = 0.72e9
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    mb_per_s = value / config["dataset"]["batch_size"]
+    roof = {"bound": "hbm", "achieved": alg_bytes_step * mb_per_s / 1e9, "peak": hbm, "unit": "GB/s",
+            "frac": alg_bytes_step * mb_per_s / 1e9 / hbm, "traffic": None,
+            "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+            "note": "whole mini-batch step against the 6.65 MB/step algorithmic-traffic model; at the Taobao "
+                    "shape the step is launch/latency-bound, the HBM-scale kernel rooflines are under 'micro'",
+            "tensor_tflops_achieved": flops_step * mb_per_s / 1e12}
+    micro = {}
+    if not args.no_micro and args.gpus == 1:
+        micro = micro_rooflines(model, peaks, torch)
+    cpu = None
+    if args.gpus == 1 and not args.no_cpu:
+        run_once, cores, desc = oracle_sample_runner(config, 600)
+        run_once()
+        s, tsec = run_once()
+        s2, tsec2 = run_once()
+        cpu = {"value": (s + s2) / (tsec + tsec2), "unit": "samples/s", "cores": cores, "kind": "port", "sample": desc}
+    line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_desc(config, args.workload, args.gpus),
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "micro": micro, "cpu_baseline": cpu,
+            "minibatches_per_step": steps_per_epoch, "wall_s": t_wall}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="Taobao-10", choices=sorted(WORKLOAD_CONFIG))
+    ap.add_argument("--precision", default=None, choices=[None, "fp32", "tf32", "tf32x3"])
+    ap.add_argument("--no-micro", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

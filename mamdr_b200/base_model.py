@@ -43,15 +43,65 @@ class BaseModel(object):
     def train(self):
         raise NotImplementedError
 
-    # ---- training pass helper shared by every wrapper -----------------------------------------------
+    # ---- training pass helpers shared by every wrapper ----------------------------------------------
+    def stage_epoch_orders(self, passes, mine=None):
+        """Draw the sample order of every training pass of one meta-step up-front (in execution order,
+        so the draws equal the reference-ordered interleaved ones), write them into ONE pinned host
+        buffer and ship them with ONE async H2D copy.  A per-pass upload from pageable memory would
+        synchronise the stream before every pass.  ``mine`` (list of bool) selects the passes this rank
+        executes when the meta-step is sharded; ids stay global."""
+        import collections
+        import torch
+        first_id = self.schedule.reserve(len(passes))
+        ids = [first_id + k for k in range(len(passes))]
+        if mine is not None:
+            ids = [i for i, m in zip(ids, mine) if m]
+            passes = [p for p, m in zip(passes, mine) if m]
+        sizes = [self.dataset.train_dataset[i]['n_data'] for i in passes]
+        total = int(sum(sizes))
+        # two pinned staging buffers used alternately; an event guards the reuse of each
+        self._order_flip = 1 - getattr(self, '_order_flip', 1)
+        pools = getattr(self, '_order_pools', None)
+        if pools is None:
+            pools = self._order_pools = [None, None]
+        pool = pools[self._order_flip]
+        if pool is None or pool[0].numel() < total:
+            cap = max(total, 1)
+            if pool is not None:
+                pool[2].synchronize()
+            pool = [torch.empty(cap, dtype=torch.int32).pin_memory(),
+                    torch.empty(cap, dtype=torch.int32, device=self.model.device), torch.cuda.Event()]
+            pools[self._order_flip] = pool
+        else:
+            pool[2].synchronize()   # the H2D copy that last read this pinned buffer has completed
+        self._order_pool = pool
+        host = pool[0].numpy()
+        staged, off = collections.deque(), 0
+        for i, n, pid in zip(passes, sizes, ids):
+            host[off:off + n] = self.schedule.batch_order_at(pid, i, n)
+            staged.append((i, off, n))
+            off += n
+        pool[1][:total].copy_(pool[0][:total], non_blocking=True)
+        pool[2].record(torch.cuda.current_stream(self.model.device))
+        self._staged_orders = staged
+        self.h2d_bytes = getattr(self, 'h2d_bytes', 0) + 4 * total
+        return total
+
     def run_train_pass(self, domain_idx, steps=None):
         """Install the next scheduled sample order of ``domain_idx`` and run one pass (async)."""
         d = self.dataset.train_dataset[domain_idx]
         data = d['data']
-        data.set_order(self.schedule.batch_order(domain_idx, data.n_data))
+        staged = getattr(self, '_staged_orders', None)
+        if staged:
+            i, off, n = staged.popleft()
+            assert i == domain_idx and n == data.n_data, "staged schedule out of step with the loop"
+            data.order.copy_(self._order_pool[1][off:off + n], non_blocking=True)   # D2D, async
+        else:
+            data.set_order(self.schedule.batch_order(domain_idx, data.n_data))
         n = d['n_step'] if steps is None else steps
         self.samples_trained = getattr(self, 'samples_trained', 0) + min(data.n_data, n * data.batch_size)
-        return self.model.fit_pass(data, n)
+        self.last_pass_losses = self.model.fit_pass(data, n)
+        return self.last_pass_losses
 
     def val_and_test(self, mode):
         """base_model.py:111-144"""

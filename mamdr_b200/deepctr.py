@@ -69,6 +69,7 @@ class DeepCTR(BaseModel):
         for epoch in range(self.train_config['epoch']):
             self.log("Epoch: {}".format(epoch), "-" * 30)
             train_sequence = self.schedule.shuffle_sequence(train_sequence)
+            self.stage_epoch_orders(list(train_sequence))
             for idx in train_sequence:
                 self.log("Train on: Domain {}".format(idx))
                 old_time = time.time()

@@ -35,6 +35,7 @@ class DomainNegotiation(MAML):
             raise NotImplementedError("target_domain >= 0 is not used by any shipped config")
         if tc['shuffle_sequence']:                            # :41-42
             self.meta_sequence = self.schedule.shuffle_sequence(self.meta_sequence)
+        self.stage_epoch_orders(list(self.meta_sequence))
         self._set_model_meta_parms(self.meta_weights)         # :50
         for idx in self.meta_sequence:                        # :53-84
             d = self.dataset.train_dataset[idx]

@@ -198,6 +198,18 @@ class MLPModel(object):
         self.ctx.call("mamdr_copy", _ptr(dst), _ptr(src), dst.numel(), self.stream)
         self.ctx.launches += 1
 
+    def opt_words(self):
+        """(step, b1pow, b2pow) of the device optimizer state as a float32 device tensor [3] (no sync)."""
+        st = self.opt_state
+        return torch.stack([st[:8].view(torch.int64)[0].to(torch.float32), st[8:12].view(torch.float32)[0],
+                            st[12:16].view(torch.float32)[0]])
+
+    def set_opt_words(self, words):
+        st = self.opt_state
+        st[:8].view(torch.int64)[0] = words[0].to(torch.int64)
+        st[8:12].view(torch.float32)[0] = words[1]
+        st[12:16].view(torch.float32)[0] = words[2]
+
     def read_step(self):
         step, b1, b2 = C.c_int64(), C.c_float(), C.c_float()
         self.ctx.call("mamdr_opt_state_read", _ptr(self.opt_state), C.byref(step), C.byref(b1), C.byref(b2),

@@ -5,6 +5,7 @@ and every update is one fused sweep in ``libmamdr_b200.so`` (no host round trips
 """
 import torch
 
+from . import dist as mdist
 from .engine import _ptr
 from .maml import MetaWeights
 from .specific_base_model import SpecificBase
@@ -49,6 +50,31 @@ class MAMDR(SpecificBase):
         if tc['shuffle_sequence']:                                   # :45-46
             self.train_sequence = self.schedule.shuffle_sequence(self.train_sequence)
         train_sequence = self.train_sequence
+        # the DR support samples (:66-70) are drawn up-front, in the reference's order (the per-pass
+        # sample orders come from an independent keyed stream), so the whole meta-step can be staged
+        supports = {}
+        for idx in train_sequence:
+            candidate_domains = list(train_sequence)
+            candidate_domains.remove(idx)
+            aux_idxs = self.schedule.sample_support(candidate_domains, tc['sample_num'])   # :68
+            if tc['add_query_domain']:
+                aux_idxs = list(aux_idxs) + [idx]
+            supports[idx] = aux_idxs
+        # multi-GPU: DN replicated, DR query domains LPT-sharded (mamdr_b200/dist.py)
+        rank, world = mdist.world()
+        n_step = {i: self.dataset.train_dataset[i]['n_step'] for i in train_sequence}
+        owner = mdist.lpt_assign(mdist.dr_chain_costs(train_sequence, supports, n_step,
+                                                      tc['domain_regulation_step']), world)
+        self.dr_owner = owner
+        passes, mine = list(train_sequence), [True] * len(train_sequence)
+        for idx in train_sequence:
+            k = 2 * len(supports[idx]) + (1 if tc['finetune_every_epoch'] else 0)
+            for aux_idx in supports[idx]:
+                passes += [aux_idx, idx]
+            if tc['finetune_every_epoch']:
+                passes.append(idx)
+            mine += [owner[idx] == rank] * k
+        self.stage_epoch_orders(passes, mine if world > 1 else None)
 
         # ---- Update Shared (DN), :48-57
         self._set_model_meta_parms(self.meta_weights)
@@ -59,12 +85,10 @@ class MAMDR(SpecificBase):
         # ---- Update specific (DR), :59-108
         batch_mode = "batch" in self.model_config['name']
         for idx in train_sequence:
+            if owner[idx] != rank:
+                continue
             d = self.dataset.train_dataset[idx]
-            candidate_domains = list(train_sequence)
-            candidate_domains.remove(idx)
-            aux_idxs = self.schedule.sample_support(candidate_domains, tc['sample_num'])   # :68
-            if tc['add_query_domain']:
-                aux_idxs = list(aux_idxs) + [idx]
+            aux_idxs = supports[idx]
             theta_i = self.domain_weights[idx]
             # merged = theta (+|*) theta_i is never materialised on the host: model <- merged (:72,78)
             self._set_model_merged(self.meta_weights, theta_i)
@@ -92,6 +116,15 @@ class MAMDR(SpecificBase):
                     m.reset_states()
                 self.run_train_pass(idx)
                 self._update_domain_weights(theta_i, merged)
+
+        if world > 1:
+            # the one collective of the meta-step: theta_i from their owners + the Adam slots of the rank
+            # that owns the last query domain of the sequence
+            m = self.model
+            words = m.opt_words()
+            self.comm_bytes = mdist.exchange(owner, rank, {k: v.flat for k, v in self.domain_weights.items()},
+                                             m.m, m.v, words, owner[train_sequence[-1]])
+            m.set_opt_words(words)
 
     # ---- :168-171
     def _update_domain_weights(self, domain_weights, merged_weights):

@@ -27,10 +27,21 @@ class Schedule(object):
     def sample_support(self, candidates, k):
         return self._rng.sample(list(candidates), k=k)
 
+    def reserve(self, k):
+        """Reserve the ids of the next ``k`` training passes (the passes of one meta-step, numbered in
+        the reference's sequential execution order) and return the first id.  A rank that runs only a
+        shard of the passes still uses the global ids, so a pass's sample order does not depend on the
+        sharding."""
+        first = self._pass + 1
+        self._pass += int(k)
+        return first
+
     def batch_order(self, domain, n):
         """Sample order of the next training pass over ``domain`` (a fresh permutation per pass)."""
-        self._pass += 1
+        return self.batch_order_at(self.reserve(1), domain, n)
+
+    def batch_order_at(self, pass_id, domain, n):
         if not self.shuffle_batches:
             return np.arange(n, dtype=np.int32)
-        g = np.random.Generator(np.random.PCG64([self.seed, self._pass, int(domain)]))
+        g = np.random.Generator(np.random.PCG64([self.seed, int(pass_id), int(domain)]))
         return g.permutation(n).astype(np.int32)

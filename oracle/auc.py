@@ -30,7 +30,16 @@ class AUC(object):
     def reset_states(self):  # utils/auc.py:283-284
         self.acc[...] = 0
 
-    def update_state(self, y_true, y_pred):  # metrics_utils.py:245-354
+    def update_state(self, y_true, y_pred, use_c=True):  # metrics_utils.py:245-354
+        if use_c:
+            from . import build as _b
+            lib = _b.load()
+            if lib is not None:
+                p = np.ascontiguousarray(y_pred, dtype=np.float32).reshape(-1)
+                y = np.ascontiguousarray(y_true, dtype=np.float32).reshape(-1)
+                lib.oracle_auc_update(p.ctypes.data, y.ctypes.data, p.size, self.thresholds.ctypes.data,
+                                      self.num_thresholds, self.acc.ctypes.data)
+                return
         y_pred = np.asarray(y_pred, dtype=np.float32).reshape(1, -1)
         label_pos = np.asarray(y_true, dtype=np.float32).reshape(1, -1).astype(bool)
         pred_pos = y_pred > self.thresholds.reshape(-1, 1)  # strict, fp32 compare

@@ -205,6 +205,76 @@ class OracleMAMDR(object):
                 for var in range(len(new_vars)):
                     self.domain_weights[idx][var] = new_vars[var] - merged[var]
 
+    def train_epoch_sharded(self, world):
+        """The multi-GPU semantics DEFINED in SURVEY.md 8(e) (not in the reference, which is
+        single-process), simulated rank by rank on the CPU: DN replicated; the DR query domains are
+        LPT-sharded by cost sum_j (S_j + S_i); every rank continues from the post-DN Adam state with its
+        own chains in sequence order; afterwards all ranks adopt the Adam state of the rank owning the
+        last query domain of the sequence.  Sample orders use the global (sequential) pass ids.
+        Non-'batch' names, 'plus'/'times' merge, no finetune_every_epoch."""
+        tc, model = self.tc, self.model
+        beta = tc['meta_learning_rate']
+        if tc['shuffle_sequence']:
+            self.sequence = self.schedule.shuffle_sequence(self.sequence)
+        seq = self.sequence
+        supports = {}
+        for idx in seq:
+            cands = list(seq)
+            cands.remove(idx)
+            aux = self.schedule.sample_support(cands, tc['sample_num'])
+            supports[idx] = list(aux) + ([idx] if tc['add_query_domain'] else [])
+        S = {i: n_steps(len(self.data['train'][i]['uid']), self.bs) for i in seq}
+        cost = {i: sum(S[j] + S[i] for j in supports[i]) for i in seq}
+        load, owner = [0] * world, {}
+        for i in sorted(cost, key=lambda k: (-cost[k], k)):
+            r = min(range(world), key=lambda q: (load[q], q))
+            owner[i] = r
+            load[r] += cost[i]
+        n_pass = len(seq) + sum(2 * len(supports[i]) for i in seq)
+        pid = self.schedule.reserve(n_pass)
+        # ---- DN (replicated)
+        model.set_weights(self.meta_weights)
+        for idx in seq:
+            d = self.data['train'][idx]
+            train_pass(model, d, idx, self.schedule.batch_order_at(pid, idx, len(d['uid'])), self.bs)
+            pid += 1
+        self._update_meta_weight(self.meta_weights, meta_lr=beta)
+        ids = {}
+        for idx in seq:
+            ids[idx] = pid
+            pid += 2 * len(supports[idx])
+        adam = model.adam
+        snap = (deepcopy(adam.m), deepcopy(adam.v), adam.b1pow, adam.b2pow, adam.step)
+        final = None
+        for r in range(world):
+            for mm_, s_ in zip(adam.m, snap[0]):
+                mm_[...] = s_
+            for vv_, s_ in zip(adam.v, snap[1]):
+                vv_[...] = s_
+            adam.b1pow, adam.b2pow, adam.step = snap[2], snap[3], snap[4]
+            for idx in seq:
+                if owner[idx] != r:
+                    continue
+                d = self.data['train'][idx]
+                p = ids[idx]
+                merged = merge_weights(self.meta_weights, self.domain_weights[idx], tc['merged_method'])
+                for aux_idx in supports[idx]:
+                    model.set_weights(merged)
+                    aux_d = self.data['train'][aux_idx]
+                    train_pass(model, aux_d, aux_idx, self.schedule.batch_order_at(p, aux_idx, len(aux_d['uid'])), self.bs)
+                    train_pass(model, d, idx, self.schedule.batch_order_at(p + 1, idx, len(d['uid'])), self.bs)
+                    p += 2
+                    self._update_meta_weight(self.domain_weights[idx], merged, meta_lr=beta)
+                    merged = merge_weights(self.meta_weights, self.domain_weights[idx], tc['merged_method'])
+            if r == owner[seq[-1]]:
+                final = (deepcopy(adam.m), deepcopy(adam.v), adam.b1pow, adam.b2pow, adam.step)
+        for mm_, s_ in zip(adam.m, final[0]):
+            mm_[...] = s_
+        for vv_, s_ in zip(adam.v, final[1]):
+            vv_[...] = s_
+        adam.b1pow, adam.b2pow, adam.step = final[2], final[3], final[4]
+        return owner
+
     def val_and_test(self, mode):  # specific_base_model.py:64-97
         if mode == 'val':
             shared, specific = deepcopy(self.meta_weights), deepcopy(self.domain_weights)

@@ -18,6 +18,20 @@ import numpy as np
 from . import philox
 from .auc import AUC
 
+try:  # CPU GEMM backend: torch (MKL/oneDNN) is 10-50x faster than this image's OpenBLAS; numpy otherwise
+    import torch as _torch
+except Exception:  # pragma: no cover
+    _torch = None
+MATMUL_BACKEND = "torch" if _torch is not None else "numpy"
+
+
+def mm(a, b):
+    """a @ b.  Both backends are plain fp32 (or fp64) CPU GEMMs; they differ only in summation order."""
+    if MATMUL_BACKEND == "torch" and a.dtype == b.dtype and a.dtype in (np.float32, np.float64):
+        return _torch.matmul(_torch.from_numpy(a), _torch.from_numpy(b)).numpy()
+    return a @ b
+
+
 CLIP_LO = np.float32(1e-7)
 CLIP_HI = np.float32(1.0) - np.float32(1e-7)
 
@@ -138,14 +152,14 @@ class OracleMLP(object):
         H = [X]
         L = len(sp.hidden)
         for l in range(L):
-            Z = H[l] @ self.w('kernel%d' % l) + self.w('bias%d' % l)
+            Z = mm(H[l], self.w('kernel%d' % l)) + self.w('bias%d' % l)
             A = np.maximum(Z, dt(0))
             if train and sp.dropout > 0:
                 M = masks[l] if masks is not None else philox.dropout_mask(
                     b, sp.hidden[l], sp.dropout_seed + l, self.adam.step, sp.dropout, self.dtype.type)
                 A = A * M
             H.append(A)
-        z = H[L] @ self.w('dense_kernel')                      # [b,1]
+        z = mm(H[L], self.w('dense_kernel'))                   # [b,1]
         s = z[:, 0] + self.w('global_bias')[0]
         p = dt(1) / (dt(1) + np.exp(-s))
         return H, p
@@ -175,14 +189,14 @@ class OracleMLP(object):
         ds = np.where((p >= dt(CLIP_LO)) & (p <= dt(CLIP_HI)), ds, dt(0)).astype(self.dtype)
         g = {}
         g['global_bias'] = np.array([np.sum(ds)], dtype=self.dtype)
-        g['dense_kernel'] = H[L].T @ ds.reshape(-1, 1)
+        g['dense_kernel'] = mm(H[L].T, ds.reshape(-1, 1))
         dH = ds.reshape(-1, 1) * self.w('dense_kernel').reshape(1, -1)
         for l in range(L - 1, -1, -1):
             # H[l+1] = relu(Z) * M  =>  M * 1[Z>0] == inv_keep * 1[H[l+1] > 0]
             dZ = dH * np.where(H[l + 1] > 0, inv_keep, dt(0)).astype(self.dtype)
-            g['kernel%d' % l] = H[l].T @ dZ
+            g['kernel%d' % l] = mm(H[l].T, dZ)
             g['bias%d' % l] = np.sum(dZ, axis=0)
-            dH = dZ @ self.w('kernel%d' % l).T
+            dH = mm(dZ, self.w('kernel%d' % l).T)
         du, di = sp.emb_dim[0], sp.emb_dim[1]
         two_l2 = dt(2.0 * sp.l2_emb)
         gEd = two_l2 * self.w('domain_emb')

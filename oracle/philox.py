@@ -57,9 +57,19 @@ def dropout_random_u32(rows, cols, seed, step):
     return np.stack(r, axis=1).reshape(rows, cols)
 
 
-def dropout_mask(rows, cols, seed, step, rate, dtype=np.float32):
+def dropout_mask(rows, cols, seed, step, rate, dtype=np.float32, use_c=True):
     """Inverted-dropout mask M in {0, 1/keep}^{rows x cols}."""
     keep = 1.0 - float(rate)
+    if use_c:
+        from . import build as _b
+        lib = _b.load()
+        if lib is not None:
+            assert cols % 4 == 0
+            out = np.empty((rows, cols), dtype=np.float32)
+            lib.oracle_dropout_mask_f32(rows * cols, int(seed) & 0xFFFFFFFF, int(step) & 0xFFFFFFFF,
+                                        keep_threshold(keep), float(np.float32(1.0) / np.float32(keep)),
+                                        out.ctypes.data)
+            return out.astype(dtype, copy=False)
     r = dropout_random_u32(rows, cols, seed, step)
     scale = (np.float32(1.0) / np.float32(keep)).astype(dtype)
     return np.where(r.astype(np.uint64) < np.uint64(keep_threshold(keep)), scale, dtype(0)).astype(dtype)

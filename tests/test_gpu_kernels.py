@@ -68,7 +68,8 @@ def test_scatter_dedup_bit_exact(n, n_ids, dim):
     uo = torch.full((n,), -1, dtype=torch.int32, device="cuda")
     ro = torch.zeros(n, dim, device="cuda")
     nu = torch.zeros(1, dtype=torch.int32, device="cuda")
-    ctx().call("mamdr_scatter_dedup_f32", ptr(dev(ids)), ptr(dev(rows)), dim, n, dim, ptr(uo), ptr(ro), ptr(nu),
+    d_ids, d_rows = dev(ids), dev(rows)   # keep the device inputs alive across the async call
+    ctx().call("mamdr_scatter_dedup_f32", ptr(d_ids), ptr(d_rows), dim, n, dim, ptr(uo), ptr(ro), ptr(nu),
                ptr(ws), ws.numel(), stream())
     k = int(nu.item())
     eu, er = _oracle_dedup(ids, rows)
@@ -91,7 +92,8 @@ def test_adam_bit_exact_over_steps():
         g = (rng.standard_normal(n) * 10.0 ** rng.integers(-6, 1)).astype(np.float32)
         g[:7] = 0.0
         st.apply(w, [g])
-        ctx().call("mamdr_adam_step", ptr(p), ptr(m), ptr(v), ptr(dev(g)), n, ptr(state), 1e-3, 0.9, 0.999, 1e-8,
+        d_g = dev(g)
+        ctx().call("mamdr_adam_step", ptr(p), ptr(m), ptr(v), ptr(d_g), n, ptr(state), 1e-3, 0.9, 0.999, 1e-8,
                    stream())
         np.testing.assert_array_equal(bits(p.cpu().numpy()), bits(w[0]), err_msg="step %d" % t)
     np.testing.assert_array_equal(bits(m.cpu().numpy()), bits(st.m[0]))
@@ -109,8 +111,8 @@ def test_sgd_bit_exact():
     lib = ctx().lib
     state = torch.zeros(lib.mamdr_opt_state_bytes(), dtype=torch.uint8, device="cuda")
     ctx().call("mamdr_opt_state_init", ptr(state), 0.9, 0.999, stream())
-    p = dev(w)
-    ctx().call("mamdr_sgd_step", ptr(p), ptr(dev(g)), n, ptr(state), 0.001, stream())
+    p, d_g = dev(w), dev(g)
+    ctx().call("mamdr_sgd_step", ptr(p), ptr(d_g), n, ptr(state), 0.001, stream())
     np.testing.assert_array_equal(bits(p.cpu().numpy()), bits(w - g * np.float32(0.001)))
 
 
@@ -123,9 +125,10 @@ def test_meta_ops_bit_exact(method):
     beta = np.float32(0.1)
     mg = (lambda a, b: a + b) if method == 0 else (lambda a, b: a * b)
     c = ctx()
+    d_th, d_ti, d_mo = dev(th), dev(ti), dev(mo)   # read-only device copies kept alive for the whole test
     # merge
     out = torch.zeros(n, device="cuda")
-    c.call("mamdr_merge", ptr(out), ptr(dev(th)), ptr(dev(ti)), n, method, stream())
+    c.call("mamdr_merge", ptr(out), ptr(d_th), ptr(d_ti), n, method, stream())
     np.testing.assert_array_equal(bits(out.cpu().numpy()), bits(mg(th, ti)))
     # DN: theta += (model - theta) * beta ; model <- theta
     t, m_ = dev(th), dev(mo)
@@ -135,14 +138,14 @@ def test_meta_ops_bit_exact(method):
     np.testing.assert_array_equal(bits(m_.cpu().numpy()), bits(exp))
     # DR: theta_i += (model - merged) * beta ; model <- theta (+|*) theta_i
     tii, m_ = dev(ti), dev(mo)
-    c.call("mamdr_dr_update", ptr(tii), ptr(dev(th)), ptr(m_), 0.1, n, method, ptr(m_), stream())
+    c.call("mamdr_dr_update", ptr(tii), ptr(d_th), ptr(m_), 0.1, n, method, ptr(m_), stream())
     nti = ti + (mo - mg(th, ti)) * beta
     np.testing.assert_array_equal(bits(tii.cpu().numpy()), bits(nti))
     np.testing.assert_array_equal(bits(m_.cpu().numpy()), bits(mg(th, nti)))
     # batch variant: accumulate + apply
     acc0 = rng.standard_normal(n).astype(np.float32)
     acc = dev(acc0)
-    c.call("mamdr_dr_accumulate", ptr(acc), ptr(dev(mo)), ptr(dev(th)), ptr(dev(ti)), n, method, stream())
+    c.call("mamdr_dr_accumulate", ptr(acc), ptr(d_mo), ptr(d_th), ptr(d_ti), n, method, stream())
     d = mo - mg(th, ti)
     eacc = acc0 + (d if method == 0 else d * th)
     np.testing.assert_array_equal(bits(acc.cpu().numpy()), bits(eacc))
@@ -152,10 +155,10 @@ def test_meta_ops_bit_exact(method):
     assert float(acc.abs().max()) == 0.0
     # sub, axpy_diff, copy
     out = torch.zeros(n, device="cuda")
-    c.call("mamdr_sub", ptr(out), ptr(dev(mo)), ptr(dev(th)), n, stream())
+    c.call("mamdr_sub", ptr(out), ptr(d_mo), ptr(d_th), n, stream())
     np.testing.assert_array_equal(bits(out.cpu().numpy()), bits(mo - th))
     u = dev(ti)
-    c.call("mamdr_axpy_diff", ptr(u), ptr(dev(mo)), ptr(dev(th)), 0.1, n, stream())
+    c.call("mamdr_axpy_diff", ptr(u), ptr(d_mo), ptr(d_th), 0.1, n, stream())
     np.testing.assert_array_equal(bits(u.cpu().numpy()), bits(ti + (mo - th) * beta))
     c.call("mamdr_copy", ptr(out), ptr(u), n, stream())
     assert torch.equal(out, u)
@@ -175,7 +178,8 @@ def test_meta_idempotence_and_linearity_full_size():
     c.call("mamdr_dn_update", ptr(t), ptr(mo), 1.0, n, None, stream())   # beta = 1 -> theta + (model - theta)
     assert torch.equal(t, th + (mo - th))
     z = torch.zeros(n, device="cuda")
-    c.call("mamdr_merge", ptr(z), ptr(th), ptr(torch.zeros(n, device="cuda")), n, 0, stream())
+    zero = torch.zeros(n, device="cuda")
+    c.call("mamdr_merge", ptr(z), ptr(th), ptr(zero), n, 0, stream())
     assert torch.equal(z, th)
 
 
@@ -185,8 +189,8 @@ def test_auc_kat_and_counts_bit_exact():
     # the reference's doc-string example (utils/auc.py:44-56)
     thr3 = dev(oauc.thresholds(3))
     acc = torch.zeros(4, 3, device="cuda")
-    c.call("mamdr_auc_update", ptr(dev(np.float32([0, 0.5, 0.3, 0.9]))), ptr(dev(np.float32([0, 0, 1, 1]))), 4,
-           ptr(acc), ptr(thr3), 3, stream())
+    d_p, d_y = dev(np.float32([0, 0.5, 0.3, 0.9])), dev(np.float32([0, 0, 1, 1]))
+    c.call("mamdr_auc_update", ptr(d_p), ptr(d_y), 4, ptr(acc), ptr(thr3), 3, stream())
     np.testing.assert_array_equal(acc.cpu().numpy(), [[2, 1, 0], [2, 0, 0], [0, 1, 2], [0, 2, 2]])
     out = torch.zeros(1, device="cuda")
     c.call("mamdr_auc_result", ptr(acc), 3, ptr(out), stream())
@@ -196,6 +200,7 @@ def test_auc_kat_and_counts_bit_exact():
     thr = oauc.thresholds(500)
     o = oauc.AUC(500)
     acc = torch.zeros(4, 500, device="cuda")
+    d_thr = dev(thr)
     for n in (1024, 1024, 977, 1, 5000):
         y = (rng.random(n) < 0.3).astype(np.float32)
         p = np.clip(0.25 * y + rng.random(n) * 0.75, 0, 1).astype(np.float32)
@@ -203,7 +208,8 @@ def test_auc_kat_and_counts_bit_exact():
         if n > 2:
             p[-1], p[-2] = 0.0, 1.0
         o.update_state(y, p)
-        c.call("mamdr_auc_update", ptr(dev(p)), ptr(dev(y)), n, ptr(acc), ptr(dev(thr)), 500, stream())
+        d_p, d_y = dev(p), dev(y)
+        c.call("mamdr_auc_update", ptr(d_p), ptr(d_y), n, ptr(acc), ptr(d_thr), 500, stream())
     np.testing.assert_array_equal(acc.cpu().numpy(), o.acc)
     c.call("mamdr_auc_result", ptr(acc), 500, ptr(out), stream())
     assert abs(out.item() - o.result()) < 2e-6

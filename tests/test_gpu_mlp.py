@@ -61,8 +61,9 @@ def test_dropout_mask_bits_match_oracle():
     m.params.copy_(torch.from_numpy(m.layout.pack(w)))
     data = base.dataset.train_dataset[1]['data']
     rows = min(1000, data.n_data)
+    loss = torch.zeros(1, device="cuda")
     for step in range(3):
-        m._train_step(data, 0, rows, torch.zeros(1, device="cuda"))
+        m._train_step(data, 0, rows, loss)
         # read H_1..H_3 back from the workspace through the documented layout: easier -- compare dZ-free
         # quantity: grads of bias via oracle with the same masks
         o = _oracle_for(base, weights=w)
