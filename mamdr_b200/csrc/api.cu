@@ -7,6 +7,7 @@ char g_mamdr_create_err[512] = "";
 
 int mamdr_mlp_init_kernels(mamdr_ctx* ctx);
 int mamdr_scatter_init_kernels(mamdr_ctx* ctx);
+void mamdr_mlp_free_ctx(mamdr_ctx* ctx);
 
 extern "C" int mamdr_abi_version(void) { return MAMDR_ABI_VERSION; }
 
@@ -59,7 +60,11 @@ extern "C" int mamdr_ctx_create(mamdr_ctx** out, int device) {
     return MAMDR_OK;
 }
 
-extern "C" void mamdr_ctx_destroy(mamdr_ctx* ctx) { free(ctx); }
+extern "C" void mamdr_ctx_destroy(mamdr_ctx* ctx) {
+    if (!ctx) return;
+    mamdr_mlp_free_ctx(ctx);
+    free(ctx);
+}
 
 extern "C" const char* mamdr_last_error(const mamdr_ctx* ctx) { return ctx ? ctx->err : g_mamdr_create_err; }
 

@@ -8,10 +8,11 @@
 #include "../../include/mamdr_b200.h"
 
 struct mamdr_ctx {
-    int  device;
-    int  sm_count;
-    int  max_smem_optin;
-    char err[512];
+    int   device;
+    int   sm_count;
+    int   max_smem_optin;
+    void* tmap_cache;  // tensor-map cache of the tcgen05 path (mlp_tc.cu)
+    char  err[512];
 };
 
 // optimizer / step state, device resident (see mamdr_opt_state_* in the header)
