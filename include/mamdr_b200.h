@@ -150,6 +150,54 @@ int mamdr_mlp_eval_step(mamdr_ctx* ctx, const mamdr_mlp_desc* desc, const mamdr_
                         float* probs_dev, float* auc_acc_dev, const float* thresholds_dev,
                         int32_t num_thresholds, int32_t precision_mode, mamdr_stream stream);
 
+/* ---- one whole domain pass in ONE persistent cooperative launch (tcgen05 modes, frozen tables) ----
+ * mamdr_mlp_train_pass replaces `model.fit(train_iter, steps_per_epoch=S)` (model_zoo/mamdr.py:54) and
+ * the `for step in range(train_step): model.train_on_batch(train_iter)` loops (mamdr.py:85-97,
+ * model_zoo/domain_negotiation.py:71-72): `steps` consecutive mini-batches (batch s = positions
+ * [s*batch_size, min((s+1)*batch_size, n_data)) of order_dev, or of the split itself when order_dev is
+ * NULL) of forward + BCE head + backward + optimizer apply (optimizer 0 = Adam, TF ApplyAdam order of
+ * operations; 1 = plain SGD of the finetune stage, model_zoo/specific_base_model.py:120).
+ * mamdr_mlp_eval_pass replaces `model.evaluate(dataset, steps)` (specific_base_model.py:82-85,
+ * base_model.py:130-133): inference forward, per-batch losses, optional probabilities [n rows].
+ *   losses_dev  : [steps] Keras loss value of every mini-batch
+ *   auc_acc_dev : optional [4, num_thresholds] accumulators, updated once with the whole pass
+ *   grads_dev   : optional arena-shaped; receives the gradients of the LAST mini-batch (test hook)
+ *   ws_dev      : mamdr_mlp_pass_workspace_bytes(desc, batch_size) bytes, zero-initialised once by the
+ *                 caller (rows past a ragged batch are multiplied by zeros, so they must be finite)
+ * precision_mode must be MAMDR_PREC_TF32 or MAMDR_PREC_TF32X3.  Both calls enqueue a 64-byte memset and
+ * one cooperative kernel launch on `stream`; the device must be otherwise idle enough for one CTA per
+ * SM to be co-resident (cudaLaunchCooperativeKernel fails otherwise -> MAMDR_E_CUDA).
+ * mamdr_mlp_pass_supported returns MAMDR_OK when the descriptor fits the pass kernel (frozen tables,
+ * hidden widths 32 or multiples of 64, last width 32/64, user+item width a multiple of 32). */
+typedef struct {
+    const int32_t* uid_dev;     /* [n_data] */
+    const int32_t* pid_dev;     /* [n_data] */
+    const float*   label_dev;   /* [n_data] */
+    const int32_t* order_dev;   /* [n_data] sample order of this pass, or NULL = identity */
+    int64_t        n_data;
+    int32_t        batch_size;
+    int32_t        steps;       /* 1 .. ceil(n_data / batch_size) */
+    int32_t        domain;
+} mamdr_pass;
+
+size_t mamdr_mlp_pass_workspace_bytes(const mamdr_mlp_desc* desc, int32_t max_batch);
+int    mamdr_mlp_pass_supported(mamdr_ctx* ctx, const mamdr_mlp_desc* desc, int32_t max_batch);
+int mamdr_mlp_train_pass(mamdr_ctx* ctx, const mamdr_mlp_desc* desc, const mamdr_pass* pass,
+                         const float* user_table_dev, const float* item_table_dev, float* params_dev,
+                         float* m_dev, float* v_dev, float* grads_dev, void* ws_dev, size_t ws_bytes,
+                         void* opt_state_dev, float* losses_dev, float* auc_acc_dev,
+                         const float* thresholds_dev, int32_t num_thresholds, int32_t optimizer, float lr,
+                         float beta1, float beta2, float eps, int32_t precision_mode, mamdr_stream stream);
+int mamdr_mlp_eval_pass(mamdr_ctx* ctx, const mamdr_mlp_desc* desc, const mamdr_pass* pass,
+                        const float* user_table_dev, const float* item_table_dev, const float* params_dev,
+                        void* ws_dev, size_t ws_bytes, void* opt_state_dev, float* losses_dev,
+                        float* probs_dev, float* auc_acc_dev, const float* thresholds_dev,
+                        int32_t num_thresholds, int32_t precision_mode, mamdr_stream stream);
+
+/* debug hook: when buf_dev != NULL the next pass launches write globaltimer stamps
+ * [step][phase][cta][2] (phase start, jobs done) into buf_dev (capacity in uint64 words). */
+int mamdr_debug_pass_timing(mamdr_ctx* ctx, void* buf_dev, int64_t capacity_u64);
+
 /* ---- K7: optimizer apply over a flat arena (replaces AdamOptimizer.apply_gradients, TF
  * ApplyAdam kernel order of operations; bit-exact vs the oracle for equal g).
  * Increments state.step and the beta powers once per call. */

@@ -60,6 +60,19 @@ class Batch(C.Structure):
     ]
 
 
+class Pass(C.Structure):
+    _fields_ = [
+        ("uid_dev", C.c_void_p),
+        ("pid_dev", C.c_void_p),
+        ("label_dev", C.c_void_p),
+        ("order_dev", C.c_void_p),
+        ("n_data", C.c_int64),
+        ("batch_size", C.c_int32),
+        ("steps", C.c_int32),
+        ("domain", C.c_int32),
+    ]
+
+
 _P, _I32, _I64, _F, _SZ = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
 
 # name -> (restype, argtypes); every symbol include/mamdr_b200.h declares
@@ -81,6 +94,13 @@ SIGNATURES = {
                                        _P, _P, _P, _P, _I32, _I32, _P]),
     "mamdr_mlp_eval_step": (C.c_int, [_P, C.POINTER(MlpDesc), C.POINTER(Batch), _P, _P, _P, _P, _SZ, _P, _P, _P,
                                       _P, _I32, _I32, _P]),
+    "mamdr_mlp_pass_workspace_bytes": (_SZ, [C.POINTER(MlpDesc), _I32]),
+    "mamdr_mlp_pass_supported": (C.c_int, [_P, C.POINTER(MlpDesc), _I32]),
+    "mamdr_mlp_train_pass": (C.c_int, [_P, C.POINTER(MlpDesc), C.POINTER(Pass), _P, _P, _P, _P, _P, _P, _P, _SZ, _P,
+                                       _P, _P, _P, _I32, _I32, _F, _F, _F, _F, _I32, _P]),
+    "mamdr_mlp_eval_pass": (C.c_int, [_P, C.POINTER(MlpDesc), C.POINTER(Pass), _P, _P, _P, _P, _SZ, _P, _P, _P, _P,
+                                      _P, _I32, _I32, _P]),
+    "mamdr_debug_pass_timing": (C.c_int, [_P, _P, _I64]),
     "mamdr_adam_step": (C.c_int, [_P, _P, _P, _P, _P, _I64, _P, _F, _F, _F, _F, _P]),
     "mamdr_sgd_step": (C.c_int, [_P, _P, _P, _I64, _P, _F, _P]),
     "mamdr_copy": (C.c_int, [_P, _P, _P, _I64, _P]),

@@ -7,7 +7,8 @@ char g_mamdr_create_err[512] = "";
 
 int mamdr_mlp_init_kernels(mamdr_ctx* ctx);
 int mamdr_scatter_init_kernels(mamdr_ctx* ctx);
-void mamdr_mlp_free_ctx(mamdr_ctx* ctx);
+int mamdr_pass_init_kernels(mamdr_ctx* ctx);
+void mamdr_pass_free_ctx(mamdr_ctx* ctx);
 
 extern "C" int mamdr_abi_version(void) { return MAMDR_ABI_VERSION; }
 
@@ -51,6 +52,7 @@ extern "C" int mamdr_ctx_create(mamdr_ctx** out, int device) {
     c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     int rc = mamdr_mlp_init_kernels(c);
     if (rc == MAMDR_OK) rc = mamdr_scatter_init_kernels(c);
+    if (rc == MAMDR_OK) rc = mamdr_pass_init_kernels(c);
     if (rc != MAMDR_OK) {
         snprintf(g_mamdr_create_err, sizeof(g_mamdr_create_err), "%s", c->err);
         free(c);
@@ -62,7 +64,7 @@ extern "C" int mamdr_ctx_create(mamdr_ctx** out, int device) {
 
 extern "C" void mamdr_ctx_destroy(mamdr_ctx* ctx) {
     if (!ctx) return;
-    mamdr_mlp_free_ctx(ctx);
+    mamdr_pass_free_ctx(ctx);
     free(ctx);
 }
 

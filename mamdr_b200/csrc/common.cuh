@@ -11,7 +11,9 @@ struct mamdr_ctx {
     int   device;
     int   sm_count;
     int   max_smem_optin;
-    void* tmap_cache;  // tensor-map cache of the tcgen05 path (mlp_tc.cu)
+    void* tmap_cache;  // tensor-map cache of the pass kernel (tc_tmap.cuh)
+    void* dbg_timing;  // debug: phase time stamps of the pass kernel (mamdr_debug_pass_timing)
+    long long dbg_timing_cap;
     char  err[512];
 };
 

@@ -7,7 +7,6 @@
 // element group, consecutive lanes on consecutive 16-byte chunks of the same row (a dim-128 row is
 // exactly one 512-byte warp access), 4 independent row loads in flight per thread.
 #include "common.cuh"
-#include "tc_gemm.cuh"
 
 namespace {
 
@@ -54,7 +53,7 @@ assemble_batch_kernel(const float* __restrict__ Eu, const float* __restrict__ Ei
                       const float* __restrict__ Ed, const int32_t* __restrict__ uid,
                       const int32_t* __restrict__ pid, const float* __restrict__ label,
                       const int32_t* __restrict__ order, int64_t offset, int rows, int domain, int du,
-                      int di, int dd, float* __restrict__ X, float* __restrict__ Xlo, float* __restrict__ y,
+                      int di, int dd, float* __restrict__ X, float* __restrict__ y,
                       int32_t* __restrict__ uid_b, int32_t* __restrict__ pid_b) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -67,12 +66,7 @@ assemble_batch_kernel(const float* __restrict__ Eu, const float* __restrict__ Ei
         const float* su = Eu + u * du;
         const float* si = Ei + p * di;
         const float* sd = Ed + (int64_t)domain * dd;
-        float* lr = Xlo ? Xlo + (int64_t)r * in_dim : nullptr;
-        auto put = [&](int dst, const float* src) {
-            const float4 v = ldg_f4(src);
-            *reinterpret_cast<float4*>(xr + dst) = v;
-            if (lr) *reinterpret_cast<float4*>(lr + dst) = make_float4(tcg::tf32_lo(v.x), tcg::tf32_lo(v.y), tcg::tf32_lo(v.z), tcg::tf32_lo(v.w));
-        };
+        auto put = [&](int dst, const float* src) { *reinterpret_cast<float4*>(xr + dst) = ldg_f4(src); };
         for (int c = lane * 4; c < du; c += 128) put(c, su + c);
         for (int c = lane * 4; c < di; c += 128) put(du + c, si + c);
         for (int c = lane * 4; c < dd; c += 128) put(du + di + c, sd + c);
@@ -108,13 +102,13 @@ extern "C" int mamdr_gather_f32(mamdr_ctx* ctx, const float* table, int64_t rows
 
 // internal (used by mlp.cu)
 int mamdr_assemble_batch(mamdr_ctx* ctx, const float* Eu, const float* Ei, const float* Ed,
-                         const mamdr_batch* b, int du, int di, int dd, float* X, float* X_lo, float* y,
+                         const mamdr_batch* b, int du, int di, int dd, float* X, float* y,
                          int32_t* uid_b, int32_t* pid_b, cudaStream_t stream) {
     const int warps_per_block = 8;
     const int grid = (b->rows + warps_per_block - 1) / warps_per_block;
     assemble_batch_kernel<<<grid, warps_per_block * 32, 0, stream>>>(
         Eu, Ei, Ed, b->uid_dev, b->pid_dev, b->label_dev, b->order_dev, b->offset, b->rows, b->domain, du,
-        di, dd, X, X_lo, y, uid_b, pid_b);
+        di, dd, X, y, uid_b, pid_b);
     MAMDR_LAUNCH_OK(ctx);
     return MAMDR_OK;
 }

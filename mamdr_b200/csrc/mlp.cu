@@ -1,4 +1,5 @@
-// K2-K5, K8: the MLP tower mini-batch (forward, sigmoid-BCE head, backward) -- fp32 SIMT path.
+// K2-K5, K8: the MLP tower mini-batch (forward, sigmoid-BCE head, backward) -- fp32 SIMT path (MAMDR_PREC_FP32,
+// the parity mode).  The tensor-core modes live in mlp_pass.cu (one persistent kernel per domain pass).
 //
 // Replaces the Keras train / test functions that the reference drives once per mini-batch
 // (/root/reference/model_zoo/mamdr.py:54,85-97; model_zoo/domain_negotiation.py:71-72;
@@ -11,12 +12,11 @@
 //   -> (L-1) x dH GEMM(+mask) -> L x dW GEMM (deterministic split-K) -> colsum(db) -> domain-emb grad
 #include "common.cuh"
 #include "gemm_simt.cuh"
-#include "mlp_tc.cuh"
 #include "mlp_ws.cuh"
 #include "philox.cuh"
 
 int mamdr_assemble_batch(mamdr_ctx* ctx, const float* Eu, const float* Ei, const float* Ed,
-                         const mamdr_batch* b, int du, int di, int dd, float* X, float* X_lo, float* y,
+                         const mamdr_batch* b, int du, int di, int dd, float* X, float* y,
                          int32_t* uid_b, int32_t* pid_b, cudaStream_t stream);
 
 namespace {
@@ -298,16 +298,9 @@ int validate(mamdr_ctx* ctx, const mamdr_mlp_desc* d, const mamdr_batch* b, cons
                   ws_bytes, ws_layout(*d, b->rows).total);
     MAMDR_REQUIRE(ctx, precision_mode == MAMDR_PREC_FP32 || precision_mode == MAMDR_PREC_TF32 || precision_mode == MAMDR_PREC_TF32X3,
                   MAMDR_E_INVALID, "unknown precision_mode %d", precision_mode);
-    if (precision_mode != MAMDR_PREC_FP32) {
-        // tcgen05 path: 32-float K chunks and 32-wide N tiles; the head epilogue holds one full row in registers
-        const int in_dim = d->emb_dim[0] + d->emb_dim[1] + d->emb_dim[2];
-        MAMDR_REQUIRE(ctx, in_dim % 32 == 0, MAMDR_E_UNSUPPORTED, "tcgen05 path needs the input width to be a multiple of 32");
-        for (int l = 0; l < d->n_layers; ++l)
-            MAMDR_REQUIRE(ctx, d->hidden[l] % 32 == 0, MAMDR_E_UNSUPPORTED, "tcgen05 path needs hidden widths that are multiples of 32");
-        const int nl = d->hidden[d->n_layers - 1];
-        MAMDR_REQUIRE(ctx, nl == 32 || nl == 64, MAMDR_E_UNSUPPORTED, "tcgen05 path needs a last hidden width of 32 or 64 (use fp32)");
-        MAMDR_REQUIRE(ctx, b->rows <= 128 * mlptc::kMaxMTiles, MAMDR_E_UNSUPPORTED, "batch too large for the tcgen05 path");
-    }
+    MAMDR_REQUIRE(ctx, precision_mode == MAMDR_PREC_FP32, MAMDR_E_UNSUPPORTED,
+                  "the per-mini-batch entry points run the fp32 SIMT tower; the tcgen05 modes are served by "
+                  "mamdr_mlp_train_pass / mamdr_mlp_eval_pass");
     if (!d->emb_trainable) MAMDR_REQUIRE(ctx, ut && it, MAMDR_E_INVALID, "frozen tables are NULL");
     MAMDR_REQUIRE(ctx, !d->emb_trainable, MAMDR_E_UNSUPPORTED, "trainable user/item tables not built yet");
     return MAMDR_OK;
@@ -320,7 +313,7 @@ int run_forward(mamdr_ctx* ctx, const mamdr_mlp_desc* d, const mamdr_batch* b, c
     const float* Eu = d->emb_trainable ? params + d->off_user_emb : ut;
     const float* Ei = d->emb_trainable ? params + d->off_item_emb : it;
     const float* Ed = params + d->off_domain_emb;
-    int rc = mamdr_assemble_batch(ctx, Eu, Ei, Ed, b, du, di, dd, (float*)(ws + w.H[0]), nullptr, (float*)(ws + w.y),
+    int rc = mamdr_assemble_batch(ctx, Eu, Ei, Ed, b, du, di, dd, (float*)(ws + w.H[0]), (float*)(ws + w.y),
                                   (int32_t*)(ws + w.uid_b), (int32_t*)(ws + w.pid_b), st);
     if (rc) return rc;
     int K = du + di + dd;
@@ -385,253 +378,12 @@ int run_head(mamdr_ctx* ctx, const mamdr_mlp_desc* d, const mamdr_batch* b, cons
 }
 
 
-// =================================================================================================================
-// tcgen05 path (host orchestration)
-// =================================================================================================================
-constexpr int kTcStages = 4;
-
-template <class K>
-int set_smem(mamdr_ctx* ctx, K kernel, size_t bytes) {
-    MAMDR_CUDA_OK(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    return MAMDR_OK;
-}
-
-struct TcCommon {
-    const mamdr_mlp_desc* d;
-    const mamdr_batch*    b;
-    const float*          params;
-    const float*          params_lo;   // arena-indexed (already offset so that params_lo[off] pairs with params[off])
-    unsigned char*        ws;
-    WsLayout              w;
-    int                   passes;
-    cudaStream_t          st;
-};
-
-inline float* wsf(const TcCommon& c, size_t off) { return reinterpret_cast<float*>(c.ws + off); }
-
-int tc_prologue(mamdr_ctx* ctx, TcCommon& c, const float* ut, const float* it) {
-    const mamdr_mlp_desc* d = c.d;
-    const int du = d->emb_dim[0], di = d->emb_dim[1], dd = d->emb_dim[2];
-    const float* Eu = d->emb_trainable ? c.params + d->off_user_emb : ut;
-    const float* Ei = d->emb_trainable ? c.params + d->off_item_emb : it;
-    int rc = mamdr_assemble_batch(ctx, Eu, Ei, c.params + d->off_domain_emb, c.b, du, di, dd, wsf(c, c.w.H[0]),
-                                  c.passes == 3 ? wsf(c, c.w.Hlo[0]) : nullptr, wsf(c, c.w.y), (int32_t*)(c.ws + c.w.uid_b),
-                                  (int32_t*)(c.ws + c.w.pid_b), c.st);
-    if (rc) return rc;
-    if (c.passes == 3) {
-        const int64_t n4 = (d->arena_floats - d->off_domain_emb) / 4;
-        const int grid = (int)((n4 + 255) / 256 < 1 ? 1 : ((n4 + 255) / 256 > 1184 ? 1184 : (n4 + 255) / 256));
-        mlptc::split_lo_kernel<<<grid, 256, 0, c.st>>>(c.params + d->off_domain_emb, wsf(c, c.w.params_lo), n4);
-        MAMDR_LAUNCH_OK(ctx);
-    }
-    return MAMDR_OK;
-}
-
-DropoutParams make_dp(const mamdr_mlp_desc* d, int layer, bool train) {
-    DropoutParams dp;
-    const float keep = 1.0f - d->dropout_rate;
-    dp.enabled = (train && d->dropout_rate > 0.f) ? 1 : 0;
-    dp.seed = d->dropout_seed + (uint32_t)layer;
-    dp.step = 0;
-    const double thr = floor((double)keep * 4294967296.0);
-    dp.threshold = thr >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)thr;
-    dp.scale = 1.0f / keep;
-    return dp;
-}
-
-// forward chain; the last layer's GEMM carries the head in its epilogue
-template <int NL>
-int tc_forward(mamdr_ctx* ctx, TcCommon& c, const OptState* state, bool train, float* grads, float* probs,
-               const float* thr, int T, bool with_auc) {
-    const mamdr_mlp_desc* d = c.d;
-    const int rows = c.b->rows, L = d->n_layers;
-    const int mtiles = (rows + 127) / 128;
-    int K = d->emb_dim[0] + d->emb_dim[1] + d->emb_dim[2];
-    const tcg::SplitK nosplit{nullptr, nullptr};
-    for (int l = 0; l < L; ++l) {
-        const int N = d->hidden[l];
-        tcg::Maps maps;
-        bool ok = mlptc::kmajor_map(ctx, &maps.a, wsf(c, c.w.H[l]), rows, K, 128) &&
-                  mlptc::mnmajor_map(ctx, &maps.b, c.params + d->off_kernel[l], K, N);
-        if (c.passes == 3)
-            ok = ok && mlptc::kmajor_map(ctx, &maps.a_lo, wsf(c, c.w.Hlo[l]), rows, K, 128) &&
-                 mlptc::mnmajor_map(ctx, &maps.b_lo, c.params_lo + d->off_kernel[l], K, N);
-        else { maps.a_lo = maps.a; maps.b_lo = maps.b; }
-        MAMDR_REQUIRE(ctx, ok, MAMDR_E_CUDA, "cuTensorMapEncodeTiled failed (fwd layer %d)", l);
-        if (l < L - 1) {
-            mlptc::FwdHiddenEpi epi;
-            epi.bias = c.params + d->off_bias[l];
-            epi.out = wsf(c, c.w.H[l + 1]);
-            epi.out_lo = c.passes == 3 ? wsf(c, c.w.Hlo[l + 1]) : nullptr;
-            epi.N = N;
-            epi.state = state;
-            epi.dp = make_dp(d, l, train);
-            auto kern = tcg::gemm_kernel<32, false, true, kTcStages, mlptc::FwdHiddenEpi>;
-            kern<<<dim3(N / 32, mtiles, 1), 128, tcg::smem_bytes<32, kTcStages>(), c.st>>>(maps, rows, K / 32, K / 32, c.passes, nosplit, epi);
-            MAMDR_LAUNCH_OK(ctx);
-        } else {
-            mlptc::FwdHeadEpi<NL> epi;
-            epi.bias = c.params + d->off_bias[l];
-            epi.w = c.params + d->off_dense_kernel;
-            epi.g = c.params + d->off_global_bias;
-            epi.y = wsf(c, c.w.y);
-            epi.state = state;
-            epi.dp = make_dp(d, l, train);
-            epi.rows_total = rows;
-            epi.train = train ? 1 : 0;
-            epi.inv_keep = (train && d->dropout_rate > 0.f) ? 1.0f / (1.0f - d->dropout_rate) : 1.0f;
-            epi.p_out = wsf(c, c.w.p);
-            epi.probs = probs;
-            epi.ds_out = wsf(c, c.w.ds);
-            epi.dZ = wsf(c, c.w.dZ[L - 1]);
-            epi.dZ_lo = c.passes == 3 ? wsf(c, c.w.dZlo[L - 1]) : nullptr;
-            epi.part.dw = wsf(c, c.w.hp_dw);
-            epi.part.db_last = wsf(c, c.w.hp_db[L - 1]);
-            epi.part.loss = reinterpret_cast<double*>(c.ws + c.w.hp_loss);
-            epi.part.dg = wsf(c, c.w.hp_dg);
-            epi.part.hist = reinterpret_cast<int*>(c.ws + c.w.hist);
-            epi.thr = with_auc ? thr : nullptr;
-            epi.T = T;
-            auto kern = tcg::gemm_kernel<NL, false, true, kTcStages, mlptc::FwdHeadEpi<NL>>;
-            kern<<<dim3(1, mtiles, 1), 128, tcg::smem_bytes<NL, kTcStages>(), c.st>>>(maps, rows, K / 32, K / 32, c.passes, nosplit, epi);
-            MAMDR_LAUNCH_OK(ctx);
-        }
-        K = N;
-    }
-    return MAMDR_OK;
-}
-
-int tc_finalize(mamdr_ctx* ctx, TcCommon& c, bool train, float* grads, float* loss, float* auc_acc, int T) {
-    const mamdr_mlp_desc* d = c.d;
-    const int L = d->n_layers;
-    mlptc::FinalizeArgs a;
-    a.n_layers = L;
-    a.mtiles = (c.b->rows + 127) / 128;
-    a.rows = c.b->rows;
-    a.train = train ? 1 : 0;
-    for (int l = 0; l < L; ++l) {
-        a.hidden[l] = d->hidden[l];
-        a.db_part[l] = wsf(c, c.w.hp_db[l]);
-        a.g_bias[l] = train ? grads + d->off_bias[l] : nullptr;
-    }
-    a.dw_part = wsf(c, c.w.hp_dw);
-    a.g_w = train ? grads + d->off_dense_kernel : nullptr;
-    a.dg_part = wsf(c, c.w.hp_dg);
-    a.g_g = train ? grads + d->off_global_bias : nullptr;
-    a.loss_part = reinterpret_cast<const double*>(c.ws + c.w.hp_loss);
-    a.loss = loss;
-    a.Ed = c.params + d->off_domain_emb;
-    a.g_Ed = train ? grads + d->off_domain_emb : nullptr;
-    a.W0dom = c.params + d->off_kernel[0] + (int64_t)(d->emb_dim[0] + d->emb_dim[1]) * d->hidden[0];
-    a.n_domain = d->n_domain;
-    a.dd = d->emb_dim[2];
-    a.n1 = d->hidden[0];
-    a.dom = c.b->domain;
-    a.l2_emb = d->l2_emb;
-    a.frozen_reg = d->frozen_reg;
-    a.hist = reinterpret_cast<int*>(c.ws + c.w.hist);
-    a.auc_acc = auc_acc;
-    a.T = auc_acc ? T : 0;
-    mlptc::finalize_kernel<<<1, 1024, 0, c.st>>>(a);
-    MAMDR_LAUNCH_OK(ctx);
-    return MAMDR_OK;
-}
-
-int tc_backward(mamdr_ctx* ctx, TcCommon& c, float* grads) {
-    const mamdr_mlp_desc* d = c.d;
-    const int rows = c.b->rows, L = d->n_layers;
-    const int mtiles = (rows + 127) / 128;
-    const int in_dim = d->emb_dim[0] + d->emb_dim[1] + d->emb_dim[2];
-    const float inv_keep = d->dropout_rate > 0.f ? 1.0f / (1.0f - d->dropout_rate) : 1.0f;
-    const tcg::SplitK nosplit{nullptr, nullptr};
-    // ---- dZ_{l-1} = (dZ_l . W_l^T) * mask(H_l)  (+ db_{l-1} partials)
-    for (int l = L - 1; l >= 1; --l) {
-        const int Kd = d->hidden[l], Nd = d->hidden[l - 1];
-        tcg::Maps maps;
-        bool ok = mlptc::kmajor_map(ctx, &maps.a, wsf(c, c.w.dZ[l]), rows, Kd, 128) &&
-                  mlptc::kmajor_map(ctx, &maps.b, c.params + d->off_kernel[l], Nd, Kd, 32);
-        if (c.passes == 3)
-            ok = ok && mlptc::kmajor_map(ctx, &maps.a_lo, wsf(c, c.w.dZlo[l]), rows, Kd, 128) &&
-                 mlptc::kmajor_map(ctx, &maps.b_lo, c.params_lo + d->off_kernel[l], Nd, Kd, 32);
-        else { maps.a_lo = maps.a; maps.b_lo = maps.b; }
-        MAMDR_REQUIRE(ctx, ok, MAMDR_E_CUDA, "cuTensorMapEncodeTiled failed (dH layer %d)", l);
-        mlptc::DhEpi<32> epi;
-        epi.H = wsf(c, c.w.H[l]);
-        epi.out = wsf(c, c.w.dZ[l - 1]);
-        epi.out_lo = c.passes == 3 ? wsf(c, c.w.dZlo[l - 1]) : nullptr;
-        epi.db_part = wsf(c, c.w.hp_db[l - 1]);
-        epi.N = Nd;
-        epi.inv_keep = inv_keep;
-        auto kern = tcg::gemm_kernel<32, false, false, kTcStages, mlptc::DhEpi<32>>;
-        kern<<<dim3(Nd / 32, mtiles, 1), 128, tcg::smem_bytes<32, kTcStages>(), c.st>>>(maps, rows, Kd / 32, Kd / 32, c.passes, nosplit, epi);
-        MAMDR_LAUNCH_OK(ctx);
-    }
-    // ---- dW_l = H_l^T . dZ_l   (K = batch rows, split-K with the deterministic fix-up)
-    const int chunks = (rows + 31) / 32;
-    for (int l = 0; l < L; ++l) {
-        const int Md = l == 0 ? in_dim : d->hidden[l - 1], Nd = d->hidden[l];
-        tcg::Maps maps;
-        bool ok = mlptc::mnmajor_map(ctx, &maps.a, wsf(c, c.w.H[l]), rows, Md) &&
-                  mlptc::mnmajor_map(ctx, &maps.b, wsf(c, c.w.dZ[l]), rows, Nd);
-        if (c.passes == 3)
-            ok = ok && mlptc::mnmajor_map(ctx, &maps.a_lo, wsf(c, c.w.Hlo[l]), rows, Md) &&
-                 mlptc::mnmajor_map(ctx, &maps.b_lo, wsf(c, c.w.dZlo[l]), rows, Nd);
-        else { maps.a_lo = maps.a; maps.b_lo = maps.b; }
-        MAMDR_REQUIRE(ctx, ok, MAMDR_E_CUDA, "cuTensorMapEncodeTiled failed (dW layer %d)", l);
-        const int mt = (Md + 127) / 128, nt = (Nd + 63) / 64;
-        int split = ctx->sm_count / (mt * nt);
-        if (split > kMaxSplit) split = kMaxSplit;
-        if (split > chunks) split = chunks;
-        if (split < 1) split = 1;
-        const int cps = (chunks + split - 1) / split;
-        split = (chunks + cps - 1) / cps;
-        MAMDR_REQUIRE(ctx, mt * nt <= kMaxTiles, MAMDR_E_UNSUPPORTED, "layer too large for the ticket table");
-        tcg::SplitK sk{wsf(c, c.w.partials), reinterpret_cast<unsigned int*>(c.ws + c.w.tickets)};
-        mlptc::StoreEpi epi{grads + d->off_kernel[l], Nd};
-        auto kern = tcg::gemm_kernel<64, true, true, kTcStages, mlptc::StoreEpi>;
-        kern<<<dim3(nt, mt, split), 128, tcg::smem_bytes<64, kTcStages>(), c.st>>>(maps, Md, chunks, cps, c.passes, sk, epi);
-        MAMDR_LAUNCH_OK(ctx);
-    }
-    return MAMDR_OK;
-}
-
-int tc_step(mamdr_ctx* ctx, const mamdr_mlp_desc* d, const mamdr_batch* b, const float* ut, const float* it, const float* params,
-            float* grads, unsigned char* ws, const OptState* state, bool train, float* loss, float* probs, float* auc_acc,
-            const float* thr, int T, int precision_mode, cudaStream_t st) {
-    MAMDR_REQUIRE(ctx, loss != nullptr, MAMDR_E_INVALID, "loss_dev is NULL");
-    if (auc_acc) MAMDR_REQUIRE(ctx, thr && T >= 2 && T <= 1023, MAMDR_E_INVALID, "bad AUC thresholds (2 <= T <= 1023)");
-    TcCommon c;
-    c.d = d; c.b = b; c.params = params; c.ws = ws; c.st = st;
-    c.w = ws_layout(*d, b->rows);
-    c.passes = precision_mode == MAMDR_PREC_TF32X3 ? 3 : 1;
-    c.params_lo = reinterpret_cast<const float*>(ws + c.w.params_lo) - d->off_domain_emb;
-    MAMDR_CUDA_OK(ctx, cudaMemsetAsync(ws + c.w.tickets, 0, (size_t)kMaxTiles * 4, st));
-    int rc = tc_prologue(ctx, c, ut, it);
-    if (rc) return rc;
-    const int nl = d->hidden[d->n_layers - 1];
-    if (nl == 64) rc = tc_forward<64>(ctx, c, state, train, grads, probs, thr, T, auc_acc != nullptr);
-    else rc = tc_forward<32>(ctx, c, state, train, grads, probs, thr, T, auc_acc != nullptr);
-    if (rc) return rc;
-    if (train) {
-        rc = tc_backward(ctx, c, grads);
-        if (rc) return rc;
-    }
-    return tc_finalize(ctx, c, train, grads, loss, auc_acc, T);
-}
-
 }  // namespace
 
 int mamdr_mlp_init_kernels(mamdr_ctx* ctx) {
     MAMDR_CUDA_OK(ctx, cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    int rc = set_smem(ctx, tcg::gemm_kernel<32, false, true, kTcStages, mlptc::FwdHiddenEpi>, tcg::smem_bytes<32, kTcStages>());
-    if (!rc) rc = set_smem(ctx, tcg::gemm_kernel<64, false, true, kTcStages, mlptc::FwdHeadEpi<64>>, tcg::smem_bytes<64, kTcStages>());
-    if (!rc) rc = set_smem(ctx, tcg::gemm_kernel<32, false, true, kTcStages, mlptc::FwdHeadEpi<32>>, tcg::smem_bytes<32, kTcStages>());
-    if (!rc) rc = set_smem(ctx, tcg::gemm_kernel<32, false, false, kTcStages, mlptc::DhEpi<32>>, tcg::smem_bytes<32, kTcStages>());
-    if (!rc) rc = set_smem(ctx, tcg::gemm_kernel<64, true, true, kTcStages, mlptc::StoreEpi>, tcg::smem_bytes<64, kTcStages>());
-    return rc;
+    return MAMDR_OK;
 }
-
-void mamdr_mlp_free_ctx(mamdr_ctx* ctx) { mlptc::free_tmap_cache(ctx); }
 
 extern "C" size_t mamdr_mlp_workspace_bytes(const mamdr_mlp_desc* desc, int32_t max_batch) {
     if (!desc || max_batch < 1 || desc->n_layers < 1 || desc->n_layers > MAMDR_MAX_LAYERS) return 0;
@@ -647,8 +399,6 @@ extern "C" int mamdr_mlp_eval_step(mamdr_ctx* ctx, const mamdr_mlp_desc* d, cons
     MAMDR_REQUIRE(ctx, params && aligned16(params), MAMDR_E_INVALID, "params NULL or misaligned");
     cudaStream_t st = (cudaStream_t)stream;
     unsigned char* ws = (unsigned char*)ws_;
-    if (precision_mode != MAMDR_PREC_FP32)
-        return tc_step(ctx, d, b, ut, it, params, nullptr, ws, nullptr, false, loss, probs, auc_acc, thr, T, precision_mode, st);
     const WsLayout w = ws_layout(*d, b->rows);
     rc = run_forward(ctx, d, b, ut, it, params, ws, w, nullptr, false, st);
     if (rc) return rc;
@@ -667,9 +417,6 @@ extern "C" int mamdr_mlp_train_step(mamdr_ctx* ctx, const mamdr_mlp_desc* d, con
     MAMDR_REQUIRE(ctx, opt_state != nullptr, MAMDR_E_INVALID, "opt_state is NULL");
     cudaStream_t st = (cudaStream_t)stream;
     unsigned char* ws = (unsigned char*)ws_;
-    if (precision_mode != MAMDR_PREC_FP32)
-        return tc_step(ctx, d, b, ut, it, params, grads, ws, (const OptState*)opt_state, true, loss, probs, auc_acc, thr, T,
-                       precision_mode, st);
     const WsLayout w = ws_layout(*d, b->rows);
     const int L = d->n_layers, rows = b->rows;
     const int in_dim = d->emb_dim[0] + d->emb_dim[1] + d->emb_dim[2];

