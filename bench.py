@@ -180,6 +180,8 @@ def workload_desc(config, workload, n_gpus):
                                                           "/".join(str(h) for h in config["model"]["hidden_dim"])),
             "parallelism": "dr-shard%d" % n_gpus if n_gpus > 1 else "single",
             "precision": config.get("b200", {}).get("precision", "fp32"),
+            "precision_note": "fp32 storage everywhere; tf32x3 = tcgen05 kind::tf32 MMAs with the 3xTF32 error-compensated "
+                              "split (~2^-21 per product, fp32 accumulate in TMEM); tf32 = 1 pass; fp32 = FFMA SIMT",
             "l2": "working set (15.7 MB tables + 0.6 MB parameters) is L2-resident by construction; a 256 MiB "
                   "buffer is written between timed steps to flush L2"}
 
@@ -251,8 +253,7 @@ def run_b200(args):
         raise SystemExit("--gpus %d but WORLD_SIZE is %d (launch N > 1 with torchrun)" % (args.gpus, world))
     config = load_config(args.workload)
     config["b200"]["device"] = "cuda:%d" % local_rank
-    if args.precision:
-        config["b200"]["precision"] = args.precision
+    config["b200"]["precision"] = args.precision or "tf32x3"
     wrapper = runpy.build(config)
     base = wrapper.base_model
     model = base.model
@@ -349,21 +350,54 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = total_samples / float(t[0])
 
+    # ---- the dominant kernel, timed live: CUDA events around every launch of the per-pass kernel (pass_kernel in
+    # the tcgen05 modes; the captured per-mini-batch graph in fp32 mode) over one extra, untimed-for-value meta-step
+    P = sum(model.layout.numels)
+    alg_bytes_mb = 1572864 + 12288 + 4096 + 2 * 4 * (P - model.n_domain * 128) + 28 * P   # 6.65 MB / mini-batch
+    flops_mb = 0.72e9
+    orig_fit = model.fit_pass
+    launches_ev = []
+
+    def timed_fit(data, steps=None):
+        n = data.n_step if steps is None else int(steps)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = orig_fit(data, steps)
+        b.record()
+        launches_ev.append((a, b, n))
+        return out
+    model.fit_pass = timed_fit
+    one_step(False)
+    torch.cuda.synchronize()
+    model.fit_pass = orig_fit
+    k_ms = sum(a.elapsed_time(b) for a, b, _ in launches_ev)
+    k_mb = sum(n for _, _, n in launches_ev)
+    k_launches = len(launches_ev)
+
     if rank != 0:
         return
     # ---- roofline + cpu baseline (rank 0)
     steps_per_epoch = total_samples / args.steps / config["dataset"]["batch_size"]
-    P = sum(model.layout.numels)
-    alg_bytes_step = 1572864 + 12288 + 4096 + 2 * 4 * (P - model.n_domain * 128) + 28 * P   # 6.65 MB
-    flops_step = 0.72e9
     hbm = peaks.get("hbm_gbs", 6650.0)
-    mb_per_s = value / config["dataset"]["batch_size"]
-    roof = {"bound": "hbm", "achieved": alg_bytes_step * mb_per_s / 1e9, "peak": hbm, "unit": "GB/s",
-            "frac": alg_bytes_step * mb_per_s / 1e9 / hbm, "traffic": None,
-            "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
-            "note": "whole mini-batch step against the 6.65 MB/step algorithmic-traffic model; at the Taobao "
-                    "shape the step is launch/latency-bound, the HBM-scale kernel rooflines are under 'micro'",
-            "tensor_tflops_achieved": flops_step * mb_per_s / 1e12}
+    avg_launch_ms = k_ms / max(k_launches, 1)
+    alg_bytes_launch = alg_bytes_mb * k_mb / max(k_launches, 1)
+    achieved = alg_bytes_launch / (avg_launch_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_pass_kernel_ncu.json"))).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    kname = "passk::pass_kernel (one launch per domain pass)" if model.pass_kernel else "per-mini-batch SIMT graph"
+    roof = {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic,
+            "peak_source": "MEASURED_PEAKS.json (burst copy bandwidth)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+            "kernel": kname, "launches_per_meta_step": k_launches, "avg_launch_us": 1e3 * avg_launch_ms,
+            "minibatches_per_launch": k_mb / max(k_launches, 1), "alg_bytes_per_minibatch": alg_bytes_mb,
+            "us_per_minibatch_in_kernel": 1e3 * k_ms / max(k_mb, 1), "kernel_share_of_step": k_ms / (ms / args.steps),
+            "note": "algorithmic bytes = 6.65 MB per mini-batch (SURVEY.md 8(d)) x mini-batches of the launch; at batch "
+                    "1024 the whole working set (2.3 MB) is L2-resident and the kernel is bound by dependent-phase "
+                    "latency (7 grid barriers + TMA fill per mini-batch), not by HBM: see DESIGN.md; HBM-scale "
+                    "rooflines of the gather / Adam sweeps are under 'micro'",
+            "tensor_tflops_achieved": flops_mb * k_mb / (k_ms * 1e-3) / 1e12}
     micro = {}
     if not args.no_micro and args.gpus == 1:
         micro = micro_rooflines(model, peaks, torch)
@@ -391,7 +425,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="Taobao-10", choices=sorted(WORKLOAD_CONFIG))
-    ap.add_argument("--precision", default=None, choices=[None, "fp32", "tf32", "tf32x3"])
+    ap.add_argument("--precision", default=None, choices=[None, "fp32", "tf32", "tf32x3"],
+                    help="tower GEMM mode (default tf32x3: tcgen05 with fp32-equivalent products)")
     ap.add_argument("--no-micro", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
