@@ -236,6 +236,30 @@ def micro_rooflines(model, peaks, torch):
     gb = 28.0 * P / 1e9
     out["adam"] = {"bound": "hbm", "achieved": gb / (ms * 1e-3), "peak": hbm, "unit": "GB/s",
                    "frac": gb / (ms * 1e-3) / hbm, "params": P, "ms": ms}
+    del g
+    # fused table sweep (sparse rows + l2 + non-lazy Adam) on the Amazon-6 user table: 24 B per element
+    rows_t, dim_t = 445789, 128
+    n_el = rows_t * dim_t
+    tp, tm, tv = p[:n_el], m[:n_el], v[:n_el]
+    slot = torch.full((rows_t,), -1, dtype=torch.int32, device=model.device)
+    tws = torch.zeros(ctx.lib.mamdr_adam_table_workspace_bytes(), dtype=torch.uint8, device=model.device)
+    uids = torch.unique(torch.randint(0, rows_t, (1024,), dtype=torch.int32, device=model.device))
+    urows = torch.randn(1024, dim_t, device=model.device)
+    ucnt = torch.tensor([uids.numel()], dtype=torch.int32, device=model.device)
+    args = (_ptr(tp), _ptr(tm), _ptr(tv), rows_t, dim_t, _ptr(uids), _ptr(urows), _ptr(ucnt), 1024, _ptr(slot), 1e-5,
+            _ptr(state), 1e-3, 0.9, 0.999, 1e-8, None, _ptr(tws), tws.numel(), st)
+    for _ in range(3):
+        ctx.call("mamdr_adam_table_step", *args)
+    a, b = ev(), ev()
+    a.record()
+    for _ in range(reps):
+        ctx.call("mamdr_adam_table_step", *args)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / reps
+    gb = (24.0 * n_el + 4.0 * rows_t) / 1e9
+    out["table_adam"] = {"bound": "hbm", "achieved": gb / (ms * 1e-3), "peak": hbm, "unit": "GB/s",
+                         "frac": gb / (ms * 1e-3) / hbm, "rows": rows_t, "dim": dim_t, "ms": ms}
     return out
 
 

@@ -142,6 +142,13 @@ int mamdr_mlp_train_step(mamdr_ctx* ctx, const mamdr_mlp_desc* desc, const mamdr
                          float* auc_acc_dev, const float* thresholds_dev, int32_t num_thresholds,
                          int32_t precision_mode, mamdr_stream stream);
 
+/* With emb_trainable the sparse user (table 0) / item (table 1) gradients of the last mamdr_mlp_train_step are left
+ * de-duplicated in the workspace (sorted unique ids, summed rows [n_uniq, emb_dim], device count); `rows` must be
+ * the batch's row count.  They feed mamdr_adam_table_step. */
+int mamdr_mlp_sparse_grads(const mamdr_mlp_desc* desc, int32_t rows, void* ws_dev, int32_t table,
+                           const int32_t** uniq_ids_dev, const float** uniq_rows_dev,
+                           const int32_t** n_uniq_dev);
+
 /* ---- inference mini-batch (replaces the Keras test function behind Model.evaluate,
  * model_zoo/specific_base_model.py:82-85, model_zoo/base_model.py:130-133): no dropout. */
 int mamdr_mlp_eval_step(mamdr_ctx* ctx, const mamdr_mlp_desc* desc, const mamdr_batch* batch,
@@ -204,6 +211,25 @@ int mamdr_debug_pass_timing(mamdr_ctx* ctx, void* buf_dev, int64_t capacity_u64)
 int mamdr_adam_step(mamdr_ctx* ctx, float* params_dev, float* m_dev, float* v_dev,
                     const float* grads_dev, int64_t n, void* opt_state_dev, float lr, float beta1,
                     float beta2, float eps, mamdr_stream stream);
+/* ---- K6 + K7 fused for a trainable embedding table (replaces TF's aggregation of the IndexedSlices gather gradient
+ * with the dense l2 regulariser gradient and the NON-lazy Adam apply over the whole variable,
+ * DeepCTR/deepctr.py:54-55,104-126):
+ *   g[r,:] = 2*l2*E[r,:] (+ uniq_rows[k,:] if r == uniq_ids[k]);  Adam on every row;  *loss_dev += l2*sum(E^2)
+ * (pre-update values; loss_dev optional).  Reads the beta powers of opt_state_dev without advancing them: call it
+ * BEFORE the mamdr_adam_step of the same mini-batch.  slot_map_dev: int32 [rows], all -1 between calls (the call
+ * fills and clears it).  max_uniq bounds *n_uniq_dev (0 = no sparse part).  24 B per element: HBM-bound. */
+size_t mamdr_adam_table_workspace_bytes(void);
+int mamdr_adam_table_step(mamdr_ctx* ctx, float* table_dev, float* m_dev, float* v_dev, int64_t rows, int32_t dim,
+                          const int32_t* uniq_ids_dev, const float* uniq_rows_dev, const int32_t* n_uniq_dev,
+                          int64_t max_uniq, int32_t* slot_map_dev, float l2, const void* opt_state_dev, float lr,
+                          float beta1, float beta2, float eps, float* loss_dev, void* ws_dev, size_t ws_bytes,
+                          mamdr_stream stream);
+
+/* sum(x^2) in double with a fixed reduction order (the l2 penalty of a trainable table in `evaluate`); ws as for
+ * mamdr_adam_table_step; *out_dev is a device double */
+int mamdr_sum_squares_f64(mamdr_ctx* ctx, const float* x_dev, int64_t n, double* out_dev, void* ws_dev,
+                          size_t ws_bytes, mamdr_stream stream);
+
 /* plain SGD of the finetune stage (train.GradientDescentOptimizer,
  * model_zoo/specific_base_model.py:120, model_zoo/base_model.py:69); also bumps state.step */
 int mamdr_sgd_step(mamdr_ctx* ctx, float* params_dev, const float* grads_dev, int64_t n,

@@ -302,7 +302,7 @@ int validate(mamdr_ctx* ctx, const mamdr_mlp_desc* d, const mamdr_batch* b, cons
                   "the per-mini-batch entry points run the fp32 SIMT tower; the tcgen05 modes are served by "
                   "mamdr_mlp_train_pass / mamdr_mlp_eval_pass");
     if (!d->emb_trainable) MAMDR_REQUIRE(ctx, ut && it, MAMDR_E_INVALID, "frozen tables are NULL");
-    MAMDR_REQUIRE(ctx, !d->emb_trainable, MAMDR_E_UNSUPPORTED, "trainable user/item tables not built yet");
+    if (d->emb_trainable) MAMDR_REQUIRE(ctx, b->rows <= mamdr_scatter_max_n(), MAMDR_E_UNSUPPORTED, "batch too large for the sparse-gradient dedup");
     return MAMDR_OK;
 }
 
@@ -390,6 +390,17 @@ extern "C" size_t mamdr_mlp_workspace_bytes(const mamdr_mlp_desc* desc, int32_t 
     return ws_layout(*desc, max_batch).total;
 }
 
+extern "C" int mamdr_mlp_sparse_grads(const mamdr_mlp_desc* desc, int32_t rows, void* ws_dev, int32_t table,
+                                      const int32_t** uniq_ids_dev, const float** uniq_rows_dev, const int32_t** n_uniq_dev) {
+    if (!desc || !ws_dev || !desc->emb_trainable || table < 0 || table > 1 || rows < 1) return MAMDR_E_INVALID;
+    const WsLayout w = ws_layout(*desc, rows);
+    unsigned char* ws = (unsigned char*)ws_dev;
+    if (uniq_ids_dev) *uniq_ids_dev = (const int32_t*)(ws + w.sp_ids[table]);
+    if (uniq_rows_dev) *uniq_rows_dev = (const float*)(ws + w.sp_rows[table]);
+    if (n_uniq_dev) *n_uniq_dev = (const int32_t*)(ws + w.sp_n[table]);
+    return MAMDR_OK;
+}
+
 extern "C" int mamdr_mlp_eval_step(mamdr_ctx* ctx, const mamdr_mlp_desc* d, const mamdr_batch* b,
                                    const float* ut, const float* it, const float* params, void* ws_,
                                    size_t ws_bytes, float* loss, float* probs, float* auc_acc,
@@ -437,6 +448,23 @@ extern "C" int mamdr_mlp_train_step(mamdr_ctx* ctx, const mamdr_mlp_desc* d, con
         simt::gemm_kernel<true, false, DhEpilogue><<<p.grid, simt::THREADS, 0, st>>>(
             (const float*)(ws + w.dZ[l]), params + d->off_kernel[l], s, p.k_chunk, nullptr, nullptr, epi);
         MAMDR_LAUNCH_OK(ctx);
+    }
+    // ---- trainable tables: dX[:, 0:du+di] = dZ_0 . W_0[0:du+di, :]^T, then per table sort + segment-sum (K6)
+    if (d->emb_trainable) {
+        const int dui = d->emb_dim[0] + d->emb_dim[1], n1 = d->hidden[0];
+        StoreEpilogue epi{(float*)(ws + w.dX), dui};
+        simt::GemmShape s{rows, dui, n1, n1, n1};   // A = dZ_0 [rows, n1]; B = W_0 rows [0, dui) stored [dui, n1]
+        simt::LaunchPlan p = simt::plan(rows, dui, n1, 0, 1);
+        simt::gemm_kernel<true, false, StoreEpilogue><<<p.grid, simt::THREADS, 0, st>>>(
+            (const float*)(ws + w.dZ[0]), params + d->off_kernel[0], s, p.k_chunk, nullptr, nullptr, epi);
+        MAMDR_LAUNCH_OK(ctx);
+        for (int t = 0; t < 2; ++t) {
+            rc = mamdr_scatter_dedup_f32(ctx, (const int32_t*)(ws + (t == 0 ? w.uid_b : w.pid_b)),
+                                         (const float*)(ws + w.dX) + (t == 0 ? 0 : d->emb_dim[0]), dui, rows, d->emb_dim[t],
+                                         (int32_t*)(ws + w.sp_ids[t]), (float*)(ws + w.sp_rows[t]), (int32_t*)(ws + w.sp_n[t]),
+                                         ws + w.sp_ws, mamdr_scatter_workspace_bytes(rows), stream);
+            if (rc) return rc;
+        }
     }
     // ---- dW_l = H_l^T . dZ_l   (reduction over the batch rows; deterministic split-K)
     for (int l = 0; l < L; ++l) {

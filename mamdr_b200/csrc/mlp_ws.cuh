@@ -15,6 +15,8 @@ struct WsLayout {
     size_t dZ[MAMDR_MAX_LAYERS];
     size_t y, p, ds, uid_b, pid_b, partials, tickets, colsum, total;
     size_t hist;
+    // trainable user / item tables: input gradient of layer 0 and the de-duplicated sparse gradients
+    size_t dX, sp_ids[2], sp_rows[2], sp_n[2], sp_ws;
 };
 
 inline WsLayout ws_layout(const mamdr_mlp_desc& d, int B) {
@@ -51,6 +53,17 @@ inline WsLayout ws_layout(const mamdr_mlp_desc& d, int B) {
     size_t hsum = 0;
     for (int l = 0; l < d.n_layers; ++l) hsum += d.hidden[l];
     w.colsum = take(hsum * 4);
+    w.dX = w.sp_ws = 0;
+    w.sp_ids[0] = w.sp_ids[1] = w.sp_rows[0] = w.sp_rows[1] = w.sp_n[0] = w.sp_n[1] = 0;
+    if (d.emb_trainable) {
+        w.dX = take((size_t)B * (d.emb_dim[0] + d.emb_dim[1]) * 4);
+        for (int t = 0; t < 2; ++t) {
+            w.sp_ids[t] = take((size_t)B * 4);
+            w.sp_rows[t] = take((size_t)B * d.emb_dim[t] * 4);
+            w.sp_n[t] = take(16);
+        }
+        w.sp_ws = take(mamdr_scatter_workspace_bytes(B));
+    }
     w.total = off;
     return w;
 }

@@ -109,7 +109,10 @@ class MLPModel(object):
             self.user_table = torch.from_numpy(ut).to(dev)
             self.item_table = torch.from_numpy(it).to(dev)
         else:
+            # trainable tables live inside the arena (user_emb, item_emb first, like model.trainable_weights)
             self.user_table = self.item_table = None
+            if self.precision != _lib.PREC_FP32:
+                raise ValueError("trainable embedding tables run in the fp32 mode (b200.precision = 'fp32')")
         # ---- C-ABI descriptor
         d = _lib.MlpDesc()
         d.n_layers = len(hidden)
@@ -143,6 +146,17 @@ class MLPModel(object):
         self.reset_optimizer()
         self._graphs = {}
         self._loss_bufs = {}
+        if self.emb_trainable:
+            lo = self.layout
+            self._tables = []   # (arena offset, rows, dim, slot map)
+            for name, n_rows, dim in (("user_emb", self.n_uid, emb_dim[0]), ("item_emb", self.n_pid, emb_dim[1])):
+                self._tables.append((lo.offset(name), int(n_rows), int(dim),
+                                     torch.full((int(n_rows),), -1, dtype=torch.int32, device=dev)))
+            self.table_ws_bytes = lib.mamdr_adam_table_workspace_bytes()
+            self.table_ws = torch.zeros(self.table_ws_bytes, dtype=torch.uint8, device=dev)
+            self.l2_emb = float(l2_emb)
+            self._sq = torch.zeros(1, dtype=torch.float64, device=dev)
+            self.dense_off = lo.offset("domain_emb")
         # the tcgen05 modes are served by the persistent pass kernel only (one cooperative launch per domain
         # pass); fp32 is the per-mini-batch SIMT path.  No silent fallback between them.
         self.pass_kernel = False
@@ -274,11 +288,34 @@ class MLPModel(object):
             return
         b = self._batch(data, offset, rows, True)
         st = self.stream
+        if self.emb_trainable:
+            self.desc.frozen_reg = 0.0   # training adds the tables' l2 penalty inside the fused table sweep
         self.ctx.call("mamdr_mlp_train_step", C.byref(self.desc), C.byref(b), _ptr(self.user_table),
                       _ptr(self.item_table), _ptr(self.params), _ptr(self.grads), _ptr(self.ws), self.ws_bytes,
                       _ptr(self.opt_state), _ptr(loss_slot), _ptr(probs), _ptr(self.auc_acc if with_auc else None),
                       _ptr(self.thresholds), self.num_thresholds, self.precision, st)
-        if self.optimizer == "adam":
+        if self.emb_trainable:
+            # K6 + K7 fused per table: de-duplicated sparse rows + dense l2 term + Adam over every row, BEFORE the
+            # dense apply advances the beta powers; then the dense part of the arena
+            if self.optimizer != "adam":
+                raise NotImplementedError("trainable tables are updated by Adam only (the finetune SGD stage follows frozen-table configs)")
+            for t, (off, n_rows, dim, slot) in enumerate(self._tables):
+                ids, srows, cnt = C.c_void_p(), C.c_void_p(), C.c_void_p()
+                rc = self.ctx.lib.mamdr_mlp_sparse_grads(C.byref(self.desc), int(rows), _ptr(self.ws), t, C.byref(ids),
+                                                         C.byref(srows), C.byref(cnt))
+                if rc != 0:
+                    raise _lib.MamdrError(rc, "mamdr_mlp_sparse_grads")
+                n_el = n_rows * dim
+                self.ctx.call("mamdr_adam_table_step", _ptr(self.params[off:off + n_el]), _ptr(self.m[off:off + n_el]),
+                              _ptr(self.v[off:off + n_el]), n_rows, dim, ids, srows, cnt, int(rows), _ptr(slot),
+                              self.l2_emb, _ptr(self.opt_state), self.lr, self.beta1, self.beta2, self.eps,
+                              _ptr(loss_slot), _ptr(self.table_ws), self.table_ws_bytes, st)
+            do = self.dense_off
+            self.ctx.call("mamdr_adam_step", _ptr(self.params[do:]), _ptr(self.m[do:]), _ptr(self.v[do:]),
+                          _ptr(self.grads[do:]), self.params.numel() - do, _ptr(self.opt_state), self.lr, self.beta1,
+                          self.beta2, self.eps, st)
+            self.ctx.launches += 4 + 2 * 2 + 1   # dX GEMM, 2 x (sort, segment-sum), 2 x (slot scatter, table sweep)
+        elif self.optimizer == "adam":
             self.ctx.call("mamdr_adam_step", _ptr(self.params), _ptr(self.m), _ptr(self.v), _ptr(self.grads),
                           self.params.numel(), _ptr(self.opt_state), self.lr, self.beta1, self.beta2, self.eps, st)
         else:
@@ -346,6 +383,8 @@ class MLPModel(object):
         st = self.stream
         if data.batch_size > self.max_batch:
             raise ValueError("batch_size %d exceeds max_batch %d" % (data.batch_size, self.max_batch))
+        if self.emb_trainable:
+            self._refresh_table_reg()
         if self.pass_kernel and steps > 0:
             self._eval_pass(self._pass(data, steps, False), losses)
             auc = self.auc_result()
@@ -360,10 +399,23 @@ class MLPModel(object):
         auc = self.auc_result()
         return float(losses[:steps].double().mean().item()) if steps else 0.0, auc
 
+    def _refresh_table_reg(self):
+        """Inference loss with trainable tables: the l2 penalty of the two tables enters through ``frozen_reg``
+        (training adds it inside the fused table sweep)."""
+        tot = 0.0
+        for off, n_rows, dim, _ in self._tables:
+            self.ctx.call("mamdr_sum_squares_f64", _ptr(self.params[off:off + n_rows * dim]), n_rows * dim, _ptr(self._sq),
+                          _ptr(self.table_ws), self.table_ws_bytes, self.stream)
+            self.ctx.launches += 1
+            tot += float(self._sq.item())
+        self.desc.frozen_reg = self.l2_emb * tot
+
     def predict(self, data, offset, rows, use_order=False):
         """Sigmoid outputs of one inference mini-batch (device tensor) -- test hook."""
         probs = torch.zeros(rows, dtype=torch.float32, device=self.device)
         loss = torch.zeros(1, dtype=torch.float32, device=self.device)
+        if self.emb_trainable:
+            self._refresh_table_reg()
         if self.pass_kernel:
             self._eval_pass(self._pass(data, 1, use_order, offset, rows), loss, probs, with_auc=False)
             return probs, loss

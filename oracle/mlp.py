@@ -203,11 +203,13 @@ class OracleMLP(object):
         gEd[domain] += np.sum(dH[:, du + di:], axis=0)
         g['domain_emb'] = gEd
         if sp.emb_trainable:
-            gEu = two_l2 * self.w('user_emb')
-            np.add.at(gEu, uid, dH[:, :du])
-            gEi = two_l2 * self.w('item_emb')
-            np.add.at(gEi, pid, dH[:, du:du + di])
-            g['user_emb'], g['item_emb'] = gEu, gEi
+            # TF order: the IndexedSlices gradient is de-duplicated first (unsorted_segment_sum:
+            # duplicates of one id added in batch order), THEN aggregated with the dense regulariser gradient
+            su = np.zeros_like(self.w('user_emb'))
+            np.add.at(su, uid, dH[:, :du])
+            si = np.zeros_like(self.w('item_emb'))
+            np.add.at(si, pid, dH[:, du:du + di])
+            g['user_emb'], g['item_emb'] = two_l2 * self.w('user_emb') + su, two_l2 * self.w('item_emb') + si
         return loss, p, [g[n] for n in sp.names]
 
     def train_on_batch(self, uid, pid, domain, label, masks=None, optimizer='adam', sgd_lr=None):

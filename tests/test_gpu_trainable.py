@@ -1,0 +1,132 @@
+"""-m gpu: BASELINE config #2 -- the joint `mlp` baseline with TRAINABLE embedding tables (Amazon shape,
+`load_pretrain_emb: false`): gather from the arena tables, sparse embedding backward (sort + segment-sum dedup, K6)
+and the fused L2 + non-lazy Adam sweep over every table row (K7), against the CPU oracle.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import make_config, rel_err
+from mamdr_b200.schedule import Schedule
+from oracle.meta import joint_train_epoch
+from test_gpu_mlp import _build, _oracle_for, _weights
+
+pytestmark = pytest.mark.gpu
+
+
+def _amazon(scale=0.002, **over):
+    kw = {"model.name": "mlp", "train.load_pretrain_emb": False, "dataset.name": "Amazon",
+          "dataset.synthetic.shape": "Amazon-6", "dataset.synthetic.scale": scale, "b200.precision": "fp32"}
+    kw.update(over)
+    return make_config(**kw)
+
+
+@pytest.mark.parametrize("rows", [1024, 333])
+def test_trainable_step_matches_oracle(rows):
+    base = _build(_amazon())
+    m = base.model
+    assert m.emb_trainable and base.layout.names[:2] == ['user_emb', 'item_emb']
+    # lift the tables off their 1e-4 init so the data gradient and the l2 term are both visible
+    rng = np.random.default_rng(0)
+    w = _weights(m)
+    for i, n in enumerate(m.layout.names):
+        if n.endswith('_emb'):
+            w[i] = (rng.standard_normal(w[i].shape) * 0.05).astype(np.float32)
+    m.params.copy_(torch.from_numpy(m.layout.pack(w)))
+    o = _oracle_for(base, weights=w)
+    data = base.dataset.train_dataset[0]['data']
+    rows = min(rows, data.n_data)
+    order = Schedule(1).batch_order(0, data.n_data)
+    data.set_order(order)
+    loss = torch.zeros(1, device="cuda")
+    m._train_step(data, 0, rows, loss)
+    torch.cuda.synchronize()
+    h = data.host
+    sel = order[:rows]
+    # de-duplicated ids are bit-exact: sorted unique of the batch ids
+    for t, col in enumerate(("uid", "pid")):
+        ids, srows, cnt = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        assert m.ctx.lib.mamdr_mlp_sparse_grads(C.byref(m.desc), rows, C.c_void_p(m.ws.data_ptr()), t, C.byref(ids),
+                                                C.byref(srows), C.byref(cnt)) == 0
+        off = ids.value - m.ws.data_ptr()
+        noff = cnt.value - m.ws.data_ptr()
+        n_u = int(m.ws[noff:noff + 4].view(torch.int32).item())
+        got = m.ws[off:off + 4 * n_u].view(torch.int32).cpu().numpy()
+        assert np.array_equal(got, np.unique(h[col][sel]))
+    ol, _, og = o.gradients(h['uid'][sel], h['pid'][sel], 0, h['label'][sel])
+    assert abs(loss.item() - ol) < 2e-5 * abs(ol)
+    o.adam.apply(o.weights, og)
+    for name, a, b in zip(m.layout.names, _weights(m), o.weights):
+        assert rel_err(a, b) < 1e-5, (name, rel_err(a, b))
+    # every row moved (non-lazy Adam + l2 on all rows), and the slot maps were left clean
+    assert not np.array_equal(_weights(m)[0], w[0])
+    for _, _, _, slot in m._tables:
+        assert int((slot != -1).sum().item()) == 0
+    step, b1, b2 = m.read_step()
+    assert step == 1 and np.float32(b1) == o.adam.b1pow
+
+
+def test_joint_training_epoch_matches_oracle():
+    """`DeepCTR.train` (deepctr.py:63-93): shuffled domains, one full pass each, one Adam -- two epochs."""
+    c = _amazon(scale=0.001)
+    base = _build(c)
+    m = base.model
+    m.reset_optimizer()
+    o = _oracle_for(base)
+    seed = c['dataset']['seed']
+    data = base.dataset.host_splits()
+    base.schedule = Schedule(seed)
+    osched = Schedule(seed)
+    seq_g, seq_o = list(range(base.n_domain)), list(range(base.n_domain))
+    for epoch in range(2):
+        seq_g = base.schedule.shuffle_sequence(seq_g)
+        base.stage_epoch_orders(list(seq_g))
+        for idx in seq_g:
+            m.reset_states()
+            base.run_train_pass(idx)
+        seq_o = joint_train_epoch(o, data, base.dataset.batch_size, osched, seq_o)
+        assert seq_g == seq_o
+    for name, a, b in zip(m.layout.names, _weights(m), o.weights):
+        assert rel_err(a, b) < 1e-4, (name, rel_err(a, b))
+    d = base.dataset.val_dataset[0]
+    loss, auc = m.evaluate(d['data'], d['n_step'])
+    hv = d['data'].host
+    ol, oa = o.evaluate(hv['uid'], hv['pid'], 0, hv['label'], base.dataset.batch_size)
+    assert abs(loss - ol) < 2e-5 * abs(ol) and abs(auc - oa) < 1e-3
+
+
+def test_table_sweep_properties_at_amazon6_size():
+    """Size-independent properties of the fused table sweep at the real Amazon-6 user table (445 789 x 128):
+    rows without a sparse gradient see g = 2*l2*E exactly; a second call with n_uniq = 0 touches nothing sparse;
+    sum(E^2) returned through the loss slot matches torch's fp64 reduction."""
+    from gpu_util import ctx, ptr, stream
+    c = ctx()
+    rows, dim = 445789, 128
+    g = torch.Generator(device="cuda").manual_seed(0)
+    p = torch.randn(rows, dim, device="cuda", generator=g) * 0.05
+    p0 = p.clone()
+    mm, vv = torch.zeros_like(p), torch.zeros_like(p)
+    state = torch.zeros(c.lib.mamdr_opt_state_bytes(), dtype=torch.uint8, device="cuda")
+    c.call("mamdr_opt_state_init", ptr(state), 0.9, 0.999, stream())
+    slot = torch.full((rows,), -1, dtype=torch.int32, device="cuda")
+    ws = torch.zeros(c.lib.mamdr_adam_table_workspace_bytes(), dtype=torch.uint8, device="cuda")
+    ids = torch.tensor([5, 77, 445788], dtype=torch.int32, device="cuda")
+    srows = torch.ones(3, dim, device="cuda")
+    cnt = torch.tensor([3], dtype=torch.int32, device="cuda")
+    loss = torch.zeros(1, device="cuda")
+    c.call("mamdr_adam_table_step", ptr(p), ptr(mm), ptr(vv), rows, dim, ptr(ids), ptr(srows), ptr(cnt), 3, ptr(slot), 1e-5,
+           ptr(state), 1e-3, 0.9, 0.999, 1e-8, ptr(loss), ptr(ws), ws.numel(), stream())
+    torch.cuda.synchronize()
+    assert int((slot != -1).sum().item()) == 0
+    ref = 1e-5 * float((p0.double() ** 2).sum().item())
+    assert abs(loss.item() - ref) < 1e-6 * ref
+    # first Adam step from zero slots: p -= lr * g / (|g| + eps')  ~  lr * sign(g); touched rows have g ~ +1
+    delta = (p - p0)
+    assert torch.all(delta[ids.long()] < 0)
+    untouched = torch.ones(rows, dtype=torch.bool, device="cuda")
+    untouched[ids.long()] = False
+    gl2 = (2e-5 * p0[untouched])
+    expect = -1e-3 * gl2 / (gl2.abs() + 1e-8 / (1 - 0.999) ** 0.5)
+    assert torch.allclose(delta[untouched], expect, rtol=2e-3, atol=1e-9)
