@@ -379,21 +379,27 @@ def run_b200(args):
     P = sum(model.layout.numels)
     alg_bytes_mb = 1572864 + 12288 + 4096 + 2 * 4 * (P - model.n_domain * 128) + 28 * P   # 6.65 MB / mini-batch
     flops_mb = 0.72e9
-    orig_fit = model.fit_pass
-    launches_ev = []
+    if model.pass_kernel:
+        model.launch_times = []
+        one_step(False)
+        torch.cuda.synchronize()
+        launches_ev, model.launch_times = model.launch_times, None
+    else:
+        orig_fit = model.fit_pass
+        launches_ev = []
 
-    def timed_fit(data, steps=None):
-        n = data.n_step if steps is None else int(steps)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        out = orig_fit(data, steps)
-        b.record()
-        launches_ev.append((a, b, n))
-        return out
-    model.fit_pass = timed_fit
-    one_step(False)
-    torch.cuda.synchronize()
-    model.fit_pass = orig_fit
+        def timed_fit(data, steps=None, order=None):
+            n = data.n_step if steps is None else int(steps)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            out = orig_fit(data, steps, order=order)
+            b.record()
+            launches_ev.append((a, b, n))
+            return out
+        model.fit_pass = timed_fit
+        one_step(False)
+        torch.cuda.synchronize()
+        model.fit_pass = orig_fit
     k_ms = sum(a.elapsed_time(b) for a, b, _ in launches_ev)
     k_mb = sum(n for _, _, n in launches_ev)
     k_launches = len(launches_ev)
@@ -411,7 +417,8 @@ def run_b200(args):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_pass_kernel_ncu.json"))).get("dram_bytes_per_launch")
     except Exception:
         pass
-    kname = "passk::pass_kernel (one launch per domain pass)" if model.pass_kernel else "per-mini-batch SIMT graph"
+    kname = ("passk::pass_kernel (one persistent launch per DN phase / DR chain: passes + meta sweeps in-kernel)"
+             if model.pass_kernel else "per-mini-batch SIMT graph")
     roof = {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic,
             "peak_source": "MEASURED_PEAKS.json (burst copy bandwidth)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
             "kernel": kname, "launches_per_meta_step": k_launches, "avg_launch_us": 1e3 * avg_launch_ms,

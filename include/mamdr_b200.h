@@ -201,6 +201,20 @@ int mamdr_mlp_eval_pass(mamdr_ctx* ctx, const mamdr_mlp_desc* desc, const mamdr_
                         float* probs_dev, float* auc_acc_dev, const float* thresholds_dev,
                         int32_t num_thresholds, int32_t precision_mode, mamdr_stream stream);
 
+/* ---- a whole meta-step in ONE launch: deferred execution of passes and meta sweeps ------------------------------
+ * Between mamdr_program_begin and mamdr_program_end, mamdr_mlp_train_pass and the K9/K10 meta sweeps (mamdr_copy,
+ * mamdr_merge, mamdr_dn_update, mamdr_dr_update, mamdr_dr_accumulate, mamdr_dr_apply_accum, mamdr_sub,
+ * mamdr_axpy_diff) are RECORDED in call order instead of launched; mamdr_program_end uploads the op list into
+ * ops_dev (>= n_ops * mamdr_program_op_bytes() bytes of device memory, 16-byte aligned) and runs it as one
+ * persistent cooperative kernel (the body of a MAMDR / DN meta-step, model_zoo/mamdr.py:48-108, without the ~130
+ * launch + prologue round trips).  All recorded passes must share model, workspace, batch size, optimizer and
+ * precision; every pointer handed to a recorded call must stay valid until the launch has run.  Other entry points
+ * return MAMDR_E_INVALID while recording.  A program without a pass replays its sweeps as ordinary launches. */
+int     mamdr_program_begin(mamdr_ctx* ctx);
+int     mamdr_program_end(mamdr_ctx* ctx, void* ops_dev, size_t ops_dev_bytes, int32_t* n_ops_out, mamdr_stream stream);
+void    mamdr_program_abort(mamdr_ctx* ctx);
+int64_t mamdr_program_op_bytes(void);
+
 /* debug hook: when buf_dev != NULL the next pass launches write globaltimer stamps
  * [step][phase][cta][2] (phase start, jobs done) into buf_dev (capacity in uint64 words). */
 int mamdr_debug_pass_timing(mamdr_ctx* ctx, void* buf_dev, int64_t capacity_u64);

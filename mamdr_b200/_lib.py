@@ -100,6 +100,10 @@ SIGNATURES = {
                                        _P, _P, _P, _I32, _I32, _F, _F, _F, _F, _I32, _P]),
     "mamdr_mlp_eval_pass": (C.c_int, [_P, C.POINTER(MlpDesc), C.POINTER(Pass), _P, _P, _P, _P, _SZ, _P, _P, _P, _P,
                                       _P, _I32, _I32, _P]),
+    "mamdr_program_begin": (C.c_int, [_P]),
+    "mamdr_program_end": (C.c_int, [_P, _P, _SZ, C.POINTER(_I32), _P]),
+    "mamdr_program_abort": (None, [_P]),
+    "mamdr_program_op_bytes": (_I64, []),
     "mamdr_debug_pass_timing": (C.c_int, [_P, _P, _I64]),
     "mamdr_mlp_sparse_grads": (C.c_int, [C.POINTER(MlpDesc), _I32, _P, _I32, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
     "mamdr_adam_table_workspace_bytes": (_SZ, []),

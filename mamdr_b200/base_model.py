@@ -92,15 +92,16 @@ class BaseModel(object):
         d = self.dataset.train_dataset[domain_idx]
         data = d['data']
         staged = getattr(self, '_staged_orders', None)
+        order = None
         if staged:
             i, off, n = staged.popleft()
             assert i == domain_idx and n == data.n_data, "staged schedule out of step with the loop"
-            data.order.copy_(self._order_pool[1][off:off + n], non_blocking=True)   # D2D, async
+            order = self._order_pool[1][off:off + n]   # the pass reads its window of the staged pool directly
         else:
             data.set_order(self.schedule.batch_order(domain_idx, data.n_data))
         n = d['n_step'] if steps is None else steps
         self.samples_trained = getattr(self, 'samples_trained', 0) + min(data.n_data, n * data.batch_size)
-        self.last_pass_losses = self.model.fit_pass(data, n)
+        self.last_pass_losses = self.model.fit_pass(data, n, order=order)
         return self.last_pass_losses
 
     def val_and_test(self, mode):

@@ -12,6 +12,7 @@ struct mamdr_ctx {
     int   sm_count;
     int   max_smem_optin;
     void* tmap_cache;  // tensor-map cache of the pass kernel (tc_tmap.cuh)
+    void* prog;        // program being recorded (mamdr_program_begin .. mamdr_program_end), else NULL
     void* dbg_timing;  // debug: phase time stamps of the pass kernel (mamdr_debug_pass_timing)
     long long dbg_timing_cap;
     char  err[512];

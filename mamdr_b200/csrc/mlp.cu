@@ -283,6 +283,7 @@ domain_emb_grad_kernel(const float* __restrict__ Ed, const float* __restrict__ W
 int validate(mamdr_ctx* ctx, const mamdr_mlp_desc* d, const mamdr_batch* b, const void* ws, size_t ws_bytes,
              int precision_mode, const float* ut, const float* it) {
     MAMDR_REQUIRE(ctx, ctx && d && b, MAMDR_E_INVALID, "NULL ctx/desc/batch");
+    MAMDR_REQUIRE(ctx, ctx->prog == nullptr, MAMDR_E_INVALID, "per-mini-batch calls cannot be recorded into a program");
     MAMDR_REQUIRE(ctx, d->n_layers >= 1 && d->n_layers <= MAMDR_MAX_LAYERS, MAMDR_E_INVALID, "n_layers out of range");
     for (int i = 0; i < 3; ++i)
         MAMDR_REQUIRE(ctx, d->emb_dim[i] > 0 && d->emb_dim[i] % 4 == 0, MAMDR_E_INVALID, "emb_dim must be a multiple of 4");

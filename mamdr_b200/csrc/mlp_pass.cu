@@ -28,8 +28,12 @@
 // No float atomics anywhere: results are bit-reproducible run to run and rank to rank.
 #include <cooperative_groups.h>
 
+#include <vector>
+
 #include "common.cuh"
+#include "meta_ops.cuh"
 #include "philox.cuh"
+#include "program.cuh"
 #include "tc_gemm.cuh"
 #include "tc_tmap.cuh"
 
@@ -65,10 +69,22 @@ struct MapTable {   // kernel parameter (param space is a legal tensor-map addre
 
 struct Seg { long long off; int numel; int kind; int layer; };
 
+struct PassDyn {   // the per-pass fields, loaded from the current ProgOp
+    int dom, steps;
+    long long n_data;
+    const int32_t *uid, *pid, *order;
+    const float* label;
+    float *losses, *probs;
+};
+
 struct PassArgs {
+    // ---- program: ops == NULL -> the single inline op (one pass per launch)
+    const ProgOp* ops;
+    int n_ops;
+    ProgOp inline_op;
     // ---- model
     int L, n[MAMDR_MAX_LAYERS + 1];   // n[0] = K0 = du + di (the domain block is folded), n[l+1] = hidden[l]
-    int du, di, dd, n_domain, dom;
+    int du, di, dd, n_domain;
     long long off_Ed, off_W[MAMDR_MAX_LAYERS], off_b[MAMDR_MAX_LAYERS], off_w, off_g, arena;
     int nseg;
     Seg seg[2 * MAMDR_MAX_LAYERS + 3];
@@ -76,10 +92,7 @@ struct PassArgs {
     float* wshadow;                   // arena-indexed tf32-rounded copy of the kernels (1-pass TF32 mode)
     const float *Eu, *Ei;
     // ---- data
-    const int32_t *uid, *pid, *order;
-    const float* label;
-    long long n_data;
-    int bs, steps, max_rows;
+    int bs, max_rows;
     // ---- workspace
     float *X[2], *y[2], *H[MAMDR_MAX_LAYERS], *dZ[MAMDR_MAX_LAYERS], *partials[MAMDR_MAX_LAYERS], *db_part[MAMDR_MAX_LAYERS];
     float *dw_part, *dg_part, *db0_red, *gEd_row, *ed_row;
@@ -93,7 +106,7 @@ struct PassArgs {
     int dropout_enabled;
     uint32_t dropout_seed, dropout_threshold;
     float dropout_scale, l2_emb, frozen_reg;
-    float *losses, *auc_acc, *probs;
+    float* auc_acc;
     const float* thr;
     int T, train, passes, stages;
     unsigned long long* timing;   // debug: [step][phase][cta][16] time stamps (NULL in production)
@@ -220,22 +233,22 @@ __device__ __forceinline__ void adam1(float& p, float& m, float& v, float g, flo
 }
 
 // gather the rows of mini-batch `step` into X[buf] / y[buf]; one warp per row, 16-byte lanes
-__device__ __forceinline__ void gather_rows(const PassArgs& a, int step, int buf, int warp_rank, int n_warps, int lane, bool rnd) {
+__device__ __forceinline__ void gather_rows(const PassArgs& a, const PassDyn& pd, int step, int buf, int warp_rank, int n_warps, int lane, bool rnd) {
     const long long off = (long long)step * a.bs;
-    const long long left = a.n_data - off;
+    const long long left = pd.n_data - off;
     const int rows = left < a.bs ? (int)left : a.bs;
     const int K0 = a.du + a.di;
     float* X = a.X[buf];
     float* y = a.y[buf];
     for (int r = warp_rank; r < rows; r += n_warps) {
-        const long long o = a.order ? (long long)__ldg(a.order + off + r) : off + r;
-        const long long u = __ldg(a.uid + o), p = __ldg(a.pid + o);
+        const long long o = pd.order ? (long long)__ldg(pd.order + off + r) : off + r;
+        const long long u = __ldg(pd.uid + o), p = __ldg(pd.pid + o);
         const float* su = a.Eu + u * a.du;
         const float* si = a.Ei + p * a.di;
         float* xr = X + (long long)r * K0;
         for (int c = lane * 4; c < a.du; c += 128) { const float4 q = ldg_f4(su + c); *reinterpret_cast<float4*>(xr + c) = rnd ? rn_tf32_4(q) : q; }
         for (int c = lane * 4; c < a.di; c += 128) { const float4 q = ldg_f4(si + c); *reinterpret_cast<float4*>(xr + a.du + c) = rnd ? rn_tf32_4(q) : q; }
-        if (lane == 0) y[r] = __ldg(a.label + o);
+        if (lane == 0) y[r] = __ldg(pd.label + o);
     }
 }
 
@@ -294,7 +307,28 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
     const float inv_keep = a.dropout_enabled && a.train ? a.dropout_scale : 1.0f;
     const bool rnd = passes == 1;   // 1-pass TF32: GEMM operands are stored pre-rounded (RN) to tf32
 
-    // ---- prologue: gather mini-batch 0; tf32-rounded weight shadow; |E_d|^2 for the inference loss
+    const ProgOp* ops = a.ops ? a.ops : &a.inline_op;
+    int pass_idx = 0;
+    for (int oi = 0; oi < a.n_ops; ++oi) {
+    const ProgOp& op = ops[oi];
+    if (op.kind == PROG_META) {
+        // ---------- element-wise DN / DR meta sweep over arenas (K9 / K10), all CTAs
+        MetaArgs ma;
+        ma.w0 = op.w0; ma.w1 = op.w1; ma.r0 = op.r0; ma.r1 = op.r1; ma.r2 = op.r2;
+        ma.f0 = op.f0; ma.f1 = op.f1; ma.method = op.method >> 8; ma.n = op.n;
+        const int mop = op.method & 0xff;
+        const int64_t nv4 = op.n >> 2;
+        for (int64_t i = (int64_t)cta * kThreads + tid; i < nv4; i += (int64_t)G * kThreads) meta_float4(mop, ma, i);
+        grid_barrier(a.bar, bar_target);
+        continue;
+    }
+    PassDyn pd;
+    pd.dom = op.domain; pd.steps = op.steps; pd.n_data = op.n_data;
+    pd.uid = op.uid; pd.pid = op.pid; pd.order = op.order; pd.label = op.label;
+    pd.losses = op.losses; pd.probs = op.probs;
+    int* const hist_cur = a.hist + (pass_idx & 1) * (2 * (kMaxThr + 1));
+
+    // ---- prologue of a pass: gather mini-batch 0; tf32-rounded weight shadow; |E_d|^2 for the inference loss
     if (rnd) {
         for (int q = 0; q < a.nseg; ++q) {
             if (a.seg[q].kind != SEG_KERNEL) continue;
@@ -304,7 +338,7 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
         }
     }
     if (warp < 4) {
-        gather_rows(a, 0, 0, cta * 4 + warp, G * 4, lane, rnd);
+        gather_rows(a, pd, 0, 0, cta * 4 + warp, G * 4, lane, rnd);
         if (!a.train && cta == G - 1) {
             double sq = 0.0;
             for (int i = tid; i < a.n_domain * a.dd; i += kWorkers) { const double e = ldcg_f(a.params + a.off_Ed + i); sq += e * e; }
@@ -319,8 +353,8 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
     grid_barrier(a.bar, bar_target);
 
     const int n_phases = a.train ? 2 * L + 1 : L;
-    for (int step = 0; step < a.steps; ++step) {
-        const long long left = a.n_data - (long long)step * a.bs;
+    for (int step = 0; step < pd.steps; ++step) {
+        const long long left = pd.n_data - (long long)step * a.bs;
         const int rows = left < a.bs ? (int)left : a.bs;
         const int mt = cdiv(rows, 128);
         const int buf = step & 1;
@@ -367,7 +401,7 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
 #pragma unroll
                                 for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
                                 if (lane == 0) red[warp] = sq;
-                                for (int k = tid; k < a.dd; k += kWorkers) a.ed_row[k] = ldcg_f(a.params + a.off_Ed + (long long)a.dom * a.dd + k);
+                                for (int k = tid; k < a.dd; k += kWorkers) a.ed_row[k] = ldcg_f(a.params + a.off_Ed + (long long)pd.dom * a.dd + k);
                             }
                             worker_sync();
                             if (J.m_tile == 0 && tid == 0) *a.ed_sq = red[0] + red[1] + red[2] + red[3];
@@ -487,7 +521,7 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                                 const int groups = kWorkers / bn, per = cdiv(a.dd, groups);
                                 const int c = tid % bn, gq = tid / bn;
                                 const float* W0dom = a.params + a.off_W[0] + (long long)K0 * N + col0 + c;
-                                const float* ed = a.params + a.off_Ed + (long long)a.dom * a.dd;
+                                const float* ed = a.params + a.off_Ed + (long long)pd.dom * a.dd;
                                 float s = 0.f;
                                 const int k_end = (gq + 1) * per < a.dd ? (gq + 1) * per : a.dd;
 #pragma unroll 8
@@ -495,9 +529,9 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                                 part[gq * bn + c] = s;
                                 worker_sync();
                                 if (tid < bn) {
-                                    float d = 0.f;
-                                    for (int q = 0; q < groups; ++q) d += part[q * bn + tid];
-                                    s_beff[tid] = ldcg_f(a.params + a.off_b[0] + col0 + tid) + d;
+                                    float dsum = 0.f;
+                                    for (int q = 0; q < groups; ++q) dsum += part[q * bn + tid];
+                                    s_beff[tid] = ldcg_f(a.params + a.off_b[0] + col0 + tid) + dsum;
                                 }
                             } else if (tid < bn) {
                                 s_beff[tid] = ldcg_f(a.params + a.off_b[l] + col0 + tid);
@@ -616,7 +650,7 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                                 const float ph = fminf(fmaxf(pv, lo_c), hi_c);
                                 const float lg = logf(ph / (1.0f - ph));
                                 bce = (double)(fmaxf(lg, 0.f) - lg * yv + log1pf(expf(-fabsf(lg))));
-                                if (a.probs) a.probs[(long long)step * a.bs + row] = pv;
+                                if (pd.probs) pd.probs[(long long)step * a.bs + row] = pv;
                                 if (a.train) dsv = (pv >= lo_c && pv <= hi_c) ? __fdiv_rn(__fsub_rn(pv, yv), (float)rows) : 0.f;
                                 if (a.auc_acc) {
                                     int lo_i = 0, hi_i = a.T;
@@ -624,7 +658,7 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                                         const int mid = (lo_i + hi_i) >> 1;
                                         if (s_thr[mid] < pv) lo_i = mid + 1; else hi_i = mid;
                                     }
-                                    atomicAdd(&a.hist[(yv != 0.f ? (a.T + 1) : 0) + lo_i], 1);
+                                    atomicAdd(&hist_cur[(yv != 0.f ? (a.T + 1) : 0) + lo_i], 1);
                                 }
                             }
                             WSTAMP(9);
@@ -776,9 +810,9 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                     ++njob;
                 }
                 // while the few head tiles run, everyone else stages the next mini-batch
-                if (phase == L - 1 && step + 1 < a.steps && warp < 4) {
+                if (phase == L - 1 && step + 1 < pd.steps && warp < 4) {
                     const int first = G > 2 * mt ? mt : 0;
-                    if (cta >= first) gather_rows(a, step + 1, buf ^ 1, (cta - first) * 4 + warp, (G - first) * 4, lane, rnd);
+                    if (cta >= first) gather_rows(a, pd, step + 1, buf ^ 1, (cta - first) * 4 + warp, (G - first) * 4, lane, rnd);
                 }
             } else {
                 // ---------- update phase: fixed-order reduction of the partials fused with the optimizer apply
@@ -849,8 +883,8 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                     } else {   // SEG_ED: L2 term on every row (+ the batch row's data gradient)
                         const float4 p4 = P;
                         g[0] = __fmul_rn(two_l2, p4.x); g[1] = __fmul_rn(two_l2, p4.y); g[2] = __fmul_rn(two_l2, p4.z); g[3] = __fmul_rn(two_l2, p4.w);
-                        if (e / a.dd == a.dom) {
-                            const float4 d4 = ldcg_f4(a.gEd_row + (e - a.dom * a.dd));
+                        if (e / a.dd == pd.dom) {
+                            const float4 d4 = ldcg_f4(a.gEd_row + (e - pd.dom * a.dd));
                             g[0] = __fadd_rn(g[0], d4.x); g[1] = __fadd_rn(g[1], d4.y); g[2] = __fadd_rn(g[2], d4.z); g[3] = __fadd_rn(g[3], d4.w);
                         }
                     }
@@ -886,21 +920,17 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
         if (cta == G - 1 && tid == 0) {
             double bs = 0.0;
             for (int m = 0; m < mt; ++m) bs += __ldcg(a.loss_part + buf * kMaxMT + m);
-            a.losses[step] = (float)(bs / (double)rows + (double)a.frozen_reg + (double)a.l2_emb * __ldcg(a.ed_sq));
+            pd.losses[step] = (float)(bs / (double)rows + (double)a.frozen_reg + (double)a.l2_emb * __ldcg(a.ed_sq));
         }
     }
 
-    // ---- epilogue of the pass: optimizer scalars, AUC accumulators (suffix sums of the pass histogram)
+    // ---- epilogue of the pass: AUC accumulators (suffix sums of the pass histogram; the histogram is double-buffered
+    // by pass parity, so the next pass of a program may already be filling the other one)
     if (cta == 0) {
-        if (tid == 0 && a.train) {
-            a.state->step = step_ctr;
-            a.state->b1pow = b1pow;
-            a.state->b2pow = b2pow;
-        }
         if (a.auc_acc && warp < 2) {
             // warp 0: negatives, warp 1: positives.  lane owns a contiguous run of bins; suffix scan across lanes.
             const int T1 = a.T + 1;
-            int* hsrc = a.hist + warp * T1;
+            int* hsrc = hist_cur + warp * T1;
             int* sfx = reinterpret_cast<int*>(scratch) + warp * (kMaxThr + 32);
             const int per = cdiv(T1, 32);
             const int b0 = lane * per, b1 = (b0 + per < T1) ? b0 + per : T1;
@@ -929,6 +959,17 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                 a.auc_acc[3 * a.T + j] += (float)(nneg - fp);
             }
         }
+        __syncthreads();
+    }
+    // the next op of a program may reset or read the accumulators: order it after the fold
+    if (a.auc_acc && oi + 1 < a.n_ops) grid_barrier(a.bar, bar_target);
+    ++pass_idx;
+    }   // program ops
+
+    if (cta == 0 && tid == 0 && a.train) {
+        a.state->step = step_ctr;
+        a.state->b1pow = b1pow;
+        a.state->b2pow = b2pow;
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -954,7 +995,7 @@ inline PassWs pass_ws(const mamdr_mlp_desc& d, int B) {
     const int Bp = (B + 127) / 128 * 128;   // whole 128-row tiles: the epilogues write zero rows up to the tile edge
     const int mt = Bp / 128;
     w.bar = take(64);
-    w.hist = take((size_t)2 * (kMaxThr + 1) * 4);
+    w.hist = take((size_t)2 * 2 * (kMaxThr + 1) * 4);   // double-buffered by pass parity
     for (int b = 0; b < 2; ++b) { w.X[b] = take((size_t)Bp * K0 * 4); w.y[b] = take((size_t)Bp * 4); }
     for (int l = 0; l < L; ++l) {
         w.H[l] = l >= 1 ? take((size_t)Bp * d.hidden[l - 1] * 4) : 0;
@@ -1009,6 +1050,8 @@ int mamdr_pass_init_kernels(mamdr_ctx* ctx) {
 }
 
 // debug hook (not part of the product contract): per-phase globaltimer stamps of the next pass launches
+extern "C" void mamdr_program_abort(mamdr_ctx* ctx);
+
 extern "C" int mamdr_debug_pass_timing(mamdr_ctx* ctx, void* buf_dev, int64_t capacity_u64) {
     if (!ctx) return MAMDR_E_INVALID;
     ctx->dbg_timing = buf_dev;
@@ -1016,7 +1059,10 @@ extern "C" int mamdr_debug_pass_timing(mamdr_ctx* ctx, void* buf_dev, int64_t ca
     return MAMDR_OK;
 }
 
-void mamdr_pass_free_ctx(mamdr_ctx* ctx) { mlptc::free_tmap_cache(ctx); }
+void mamdr_pass_free_ctx(mamdr_ctx* ctx) {
+    mlptc::free_tmap_cache(ctx);
+    mamdr_program_abort(ctx);
+}
 
 extern "C" size_t mamdr_mlp_pass_workspace_bytes(const mamdr_mlp_desc* desc, int32_t max_batch) {
     if (!desc || max_batch < 1 || desc->n_layers < 1 || desc->n_layers > MAMDR_MAX_LAYERS) return 0;
@@ -1026,6 +1072,24 @@ extern "C" size_t mamdr_mlp_pass_workspace_bytes(const mamdr_mlp_desc* desc, int
 extern "C" int mamdr_mlp_pass_supported(mamdr_ctx* ctx, const mamdr_mlp_desc* desc, int32_t max_batch) {
     if (!ctx || !desc) return MAMDR_E_INVALID;
     return pass_supported(ctx, desc, max_batch);
+}
+
+struct Program {
+    std::vector<ProgOp> ops;
+    bool has_pass = false;
+    PassArgs a;
+    MapTable mp;
+};
+
+int mamdr_meta_launch(mamdr_ctx* ctx, int meta_op, const MetaArgs& a, mamdr_stream stream);   // optim.cu
+
+static int launch_program(mamdr_ctx* ctx, const MapTable& mp, const PassArgs& a, cudaStream_t st) {
+    MAMDR_CUDA_OK(ctx, cudaMemsetAsync(a.bar, 0, 64, st));
+    const size_t smem = smem_bytes(a.passes, a.stages);
+    void* kargs[] = {(void*)&mp, (void*)&a};
+    const void* fn = a.n[a.L] == 64 ? (const void*)pass_kernel<64> : (const void*)pass_kernel<32>;
+    MAMDR_CUDA_OK(ctx, cudaLaunchCooperativeKernel(fn, dim3(ctx->sm_count), dim3(kThreads), kargs, smem, st));
+    return MAMDR_OK;
 }
 
 static int run_pass(mamdr_ctx* ctx, const mamdr_mlp_desc* d, const mamdr_pass* ps, const float* ut, const float* it, float* params,
@@ -1056,7 +1120,7 @@ static int run_pass(mamdr_ctx* ctx, const mamdr_mlp_desc* d, const mamdr_pass* p
     a.n[0] = d->emb_dim[0] + d->emb_dim[1];
     for (int l = 0; l < L; ++l) a.n[l + 1] = d->hidden[l];
     a.du = d->emb_dim[0]; a.di = d->emb_dim[1]; a.dd = d->emb_dim[2];
-    a.n_domain = d->n_domain; a.dom = ps->domain;
+    a.n_domain = d->n_domain;
     a.off_Ed = d->off_domain_emb; a.off_w = d->off_dense_kernel; a.off_g = d->off_global_bias; a.arena = d->arena_floats;
     int ns = 0;
     a.seg[ns++] = Seg{d->off_domain_emb, d->n_domain * d->emb_dim[2], SEG_ED, 0};
@@ -1070,8 +1134,12 @@ static int run_pass(mamdr_ctx* ctx, const mamdr_mlp_desc* d, const mamdr_pass* p
     a.seg[ns++] = Seg{d->off_global_bias, 1, SEG_GBIAS, 0};
     a.nseg = ns;
     a.params = params; a.m = m; a.v = v; a.grads = grads; a.Eu = ut; a.Ei = it;
-    a.uid = ps->uid_dev; a.pid = ps->pid_dev; a.order = ps->order_dev; a.label = ps->label_dev;
-    a.n_data = ps->n_data; a.bs = ps->batch_size; a.steps = ps->steps; a.max_rows = Bp;
+    a.bs = ps->batch_size; a.max_rows = Bp;
+    ProgOp op;
+    memset(&op, 0, sizeof(op));
+    op.kind = PROG_PASS; op.domain = ps->domain; op.steps = ps->steps; op.n_data = ps->n_data;
+    op.uid = ps->uid_dev; op.pid = ps->pid_dev; op.order = ps->order_dev; op.label = ps->label_dev;
+    op.losses = losses; op.probs = probs;
     for (int b = 0; b < 2; ++b) { a.X[b] = (float*)(ws + w.X[b]); a.y[b] = (float*)(ws + w.y[b]); }
     for (int l = 0; l < L; ++l) {
         a.H[l] = l >= 1 ? (float*)(ws + w.H[l]) : nullptr;
@@ -1094,7 +1162,7 @@ static int run_pass(mamdr_ctx* ctx, const mamdr_mlp_desc* d, const mamdr_pass* p
     a.dropout_threshold = thrd >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)thrd;
     a.dropout_scale = 1.0f / keep;
     a.l2_emb = d->l2_emb; a.frozen_reg = d->frozen_reg;
-    a.losses = losses; a.auc_acc = auc_acc; a.probs = probs; a.thr = thr; a.T = auc_acc ? T : 0;
+    a.auc_acc = auc_acc; a.thr = thr; a.T = auc_acc ? T : 0;
     a.train = train ? 1 : 0;
     a.passes = precision_mode == MAMDR_PREC_TF32X3 ? 3 : 1;
     a.stages = a.passes == 3 ? 3 : kMaxStages;
@@ -1119,12 +1187,86 @@ static int run_pass(mamdr_ctx* ctx, const mamdr_mlp_desc* d, const mamdr_pass* p
     }
     MAMDR_REQUIRE(ctx, ok, MAMDR_E_CUDA, "cuTensorMapEncodeTiled failed (pass kernel)");
 
-    MAMDR_CUDA_OK(ctx, cudaMemsetAsync(a.bar, 0, 64, st));
-    const size_t smem = smem_bytes(a.passes, a.stages);
-    void* kargs[] = {(void*)&mp, (void*)&a};
-    const void* fn = a.n[L] == 64 ? (const void*)pass_kernel<64> : (const void*)pass_kernel<32>;
-    MAMDR_CUDA_OK(ctx, cudaLaunchCooperativeKernel(fn, dim3(ctx->sm_count), dim3(kThreads), kargs, smem, st));
+    if (ctx->prog) {
+        // recording: the first pass fixes the launch-wide arguments, later passes must agree with them
+        Program* pr = static_cast<Program*>(ctx->prog);
+        MAMDR_REQUIRE(ctx, train, MAMDR_E_INVALID, "only training passes and meta sweeps can be recorded into a program");
+        if (!pr->has_pass) {
+            pr->a = a; pr->mp = mp; pr->has_pass = true;
+        } else {
+            const PassArgs& c = pr->a;
+            MAMDR_REQUIRE(ctx, c.params == a.params && c.m == a.m && c.v == a.v && c.X[0] == a.X[0] && c.bs == a.bs && c.passes == a.passes &&
+                              c.opt_kind == a.opt_kind && c.lr == a.lr && c.Eu == a.Eu && c.Ei == a.Ei && c.state == a.state &&
+                              c.auc_acc == a.auc_acc && c.grads == a.grads && c.arena == a.arena,
+                          MAMDR_E_INVALID, "passes of one program must share model, workspace, batch size, optimizer and precision");
+        }
+        pr->ops.push_back(op);
+        return MAMDR_OK;
+    }
+    a.ops = nullptr; a.n_ops = 1; a.inline_op = op;
+    return launch_program(ctx, mp, a, st);
+}
+
+bool mamdr_prog_recording(const mamdr_ctx* ctx) { return ctx && ctx->prog; }
+
+int mamdr_prog_push_meta(mamdr_ctx* ctx, int meta_op, const MetaArgs& m) {
+    Program* pr = static_cast<Program*>(ctx->prog);
+    ProgOp op;
+    memset(&op, 0, sizeof(op));
+    op.kind = PROG_META; op.method = (meta_op & 0xff) | (m.method << 8); op.n = m.n;
+    op.w0 = m.w0; op.w1 = m.w1; op.r0 = m.r0; op.r1 = m.r1; op.r2 = m.r2; op.f0 = m.f0; op.f1 = m.f1;
+    pr->ops.push_back(op);
     return MAMDR_OK;
+}
+
+extern "C" int mamdr_program_begin(mamdr_ctx* ctx) {
+    MAMDR_REQUIRE(ctx, ctx != nullptr, MAMDR_E_INVALID, "ctx is NULL");
+    MAMDR_REQUIRE(ctx, ctx->prog == nullptr, MAMDR_E_INVALID, "a program is already being recorded");
+    ctx->prog = new Program();
+    return MAMDR_OK;
+}
+
+extern "C" void mamdr_program_abort(mamdr_ctx* ctx) {
+    if (!ctx || !ctx->prog) return;
+    delete static_cast<Program*>(ctx->prog);
+    ctx->prog = nullptr;
+}
+
+extern "C" int64_t mamdr_program_op_bytes(void) { return (int64_t)sizeof(ProgOp); }
+
+extern "C" int mamdr_program_end(mamdr_ctx* ctx, void* ops_dev, size_t ops_dev_bytes, int32_t* n_ops_out, mamdr_stream stream) {
+    MAMDR_REQUIRE(ctx, ctx && ctx->prog, MAMDR_E_INVALID, "no program is being recorded");
+    Program* pr = static_cast<Program*>(ctx->prog);
+    ctx->prog = nullptr;   // from here on every call executes immediately again
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = pr->ops.size();
+    if (n_ops_out) *n_ops_out = (int32_t)n;
+    int rc = MAMDR_OK;
+    if (n == 0) {
+        // nothing recorded
+    } else if (!pr->has_pass) {
+        // meta sweeps only: replay them as ordinary launches
+        for (size_t i = 0; i < n && rc == MAMDR_OK; ++i) {
+            const ProgOp& o = pr->ops[i];
+            MetaArgs m{o.w0, o.w1, o.r0, o.r1, o.r2, o.f0, o.f1, o.method >> 8, (int64_t)o.n};
+            rc = mamdr_meta_launch(ctx, o.method & 0xff, m, stream);
+        }
+    } else if (!ops_dev || ops_dev_bytes < n * sizeof(ProgOp) || !aligned16(ops_dev)) {
+        MAMDR_SET_ERR(ctx, "program buffer too small or misaligned: %zu ops need %zu bytes", n, n * sizeof(ProgOp));
+        rc = MAMDR_E_WORKSPACE;
+    } else {
+        cudaError_t e = cudaMemcpyAsync(ops_dev, pr->ops.data(), n * sizeof(ProgOp), cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) {
+            MAMDR_SET_ERR(ctx, "cudaMemcpyAsync(program): %s", cudaGetErrorString(e));
+            rc = MAMDR_E_CUDA;
+        } else {
+            pr->a.ops = (const ProgOp*)ops_dev;
+            pr->a.n_ops = (int)n;
+            rc = launch_program(ctx, pr->mp, pr->a, st);
+        }
+    }
+    delete pr;
+    return rc;
 }
 
 extern "C" int mamdr_mlp_train_pass(mamdr_ctx* ctx, const mamdr_mlp_desc* desc, const mamdr_pass* pass,

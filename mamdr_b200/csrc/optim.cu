@@ -12,6 +12,8 @@
 // operation order of TF's ApplyAdam kernel and of the reference's numpy expressions, so each op is
 // bit-exact against the fp32 numpy oracle for identical inputs (no FMA contraction).
 #include "common.cuh"
+#include "meta_ops.cuh"
+#include "program.cuh"
 
 namespace {
 
@@ -95,75 +97,12 @@ sgd_kernel(float* __restrict__ p, const float* __restrict__ g, int64_t n, OptSta
     finish_step(st, 0.f, 0.f, false);
 }
 
-// ---- element-wise meta functors ---------------------------------------------------------------
-__device__ __forceinline__ float merge1(float t, float ti, int method) {
-    return method == MAMDR_MERGE_PLUS ? __fadd_rn(t, ti) : __fmul_rn(t, ti);
-}
-
-enum MetaOp { OP_COPY, OP_MERGE, OP_DN, OP_DR, OP_DR_ACC, OP_DR_APPLY, OP_SUB, OP_AXPY_DIFF };
-
-struct MetaArgs {
-    float*       w0;  // primary output / in-out
-    float*       w1;  // secondary output (may be NULL)
-    const float* r0;
-    const float* r1;
-    const float* r2;
-    float        f0, f1;
-    int          method;
-    int64_t      n;
-};
-
-#define COMP(v, k) (reinterpret_cast<const float*>(&(v))[k])
-#define COMPW(v, k) (reinterpret_cast<float*>(&(v))[k])
-
+// ---- element-wise meta sweeps (meta_ops.cuh) ---------------------------------------------------------
 template <int OP>
 __global__ void __launch_bounds__(kThreads) meta_kernel(MetaArgs a) {
     const int64_t nv = a.n >> 2;
     const int64_t stride = (int64_t)gridDim.x * kThreads;
-    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < nv; i += stride) {
-        float4 W0 = make_float4(0, 0, 0, 0), W1 = make_float4(0, 0, 0, 0);
-        float4 R0 = make_float4(0, 0, 0, 0), R1 = R0, R2 = R0;
-        if (OP == OP_DN || OP == OP_DR || OP == OP_DR_ACC || OP == OP_DR_APPLY || OP == OP_AXPY_DIFF) W0 = *reinterpret_cast<float4*>(a.w0 + 4 * i);
-        if (OP == OP_DR_APPLY) W1 = *reinterpret_cast<float4*>(a.w1 + 4 * i);
-        R0 = *reinterpret_cast<const float4*>((OP == OP_DR_APPLY ? a.w1 : a.r0) + 4 * i);
-        if (OP == OP_MERGE || OP == OP_DR || OP == OP_DR_ACC || OP == OP_SUB || OP == OP_AXPY_DIFF) R1 = *reinterpret_cast<const float4*>(a.r1 + 4 * i);
-        if (OP == OP_DR_ACC) R2 = *reinterpret_cast<const float4*>(a.r2 + 4 * i);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (OP == OP_COPY) {
-                COMPW(W0, k) = COMP(R0, k);
-            } else if (OP == OP_MERGE) {  // out = theta (+|*) theta_i
-                COMPW(W0, k) = merge1(COMP(R0, k), COMP(R1, k), a.method);
-            } else if (OP == OP_DN) {  // theta += (model - theta) * beta ; model_out = theta
-                const float t = COMP(W0, k);
-                const float nt = __fadd_rn(t, __fmul_rn(__fsub_rn(COMP(R0, k), t), a.f0));
-                COMPW(W0, k) = nt;
-                COMPW(W1, k) = nt;
-            } else if (OP == OP_DR) {  // W0 = theta_i, R0 = model, R1 = theta
-                const float ti = COMP(W0, k), t = COMP(R1, k);
-                const float merged = merge1(t, ti, a.method);
-                const float nti = __fadd_rn(ti, __fmul_rn(__fsub_rn(COMP(R0, k), merged), a.f0));
-                COMPW(W0, k) = nti;
-                COMPW(W1, k) = merge1(t, nti, a.method);
-            } else if (OP == OP_DR_ACC) {  // W0 = accum, R0 = model, R1 = theta, R2 = theta_i
-                const float t = COMP(R1, k);
-                const float merged = merge1(t, COMP(R2, k), a.method);
-                float d = __fsub_rn(COMP(R0, k), merged);
-                if (a.method == MAMDR_MERGE_TIMES) d = __fmul_rn(d, t);
-                COMPW(W0, k) = __fadd_rn(COMP(W0, k), d);
-            } else if (OP == OP_DR_APPLY) {  // W0 = theta_i, W1/R0 = accum ; f0 = sample_num, f1 = beta
-                COMPW(W0, k) = __fadd_rn(COMP(W0, k), __fmul_rn(__fdiv_rn(COMP(R0, k), a.f0), a.f1));
-                COMPW(W1, k) = 0.f;
-            } else if (OP == OP_SUB) {
-                COMPW(W0, k) = __fsub_rn(COMP(R0, k), COMP(R1, k));
-            } else if (OP == OP_AXPY_DIFF) {  // out += (a - b) * alpha
-                COMPW(W0, k) = __fadd_rn(COMP(W0, k), __fmul_rn(__fsub_rn(COMP(R0, k), COMP(R1, k)), a.f0));
-            }
-        }
-        *reinterpret_cast<float4*>(a.w0 + 4 * i) = W0;
-        if ((OP == OP_DN || OP == OP_DR) && a.w1) *reinterpret_cast<float4*>(a.w1 + 4 * i) = W1;
-        if (OP == OP_DR_APPLY) *reinterpret_cast<float4*>(a.w1 + 4 * i) = W1;
-    }
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < nv; i += stride) meta_float4(OP, a, i);
 }
 
 template <int OP>
@@ -173,12 +112,29 @@ int launch_meta(mamdr_ctx* ctx, MetaArgs a, mamdr_stream stream) {
     if (a.n == 0) return MAMDR_OK;
     const void* ptrs[5] = {a.w0, a.w1, a.r0, a.r1, a.r2};
     for (int i = 0; i < 5; ++i) MAMDR_REQUIRE(ctx, aligned16(ptrs[i]), MAMDR_E_INVALID, "arena pointer misaligned");
+    if (mamdr_prog_recording(ctx)) return mamdr_prog_push_meta(ctx, OP, a);   // deferred into the program kernel
     meta_kernel<OP><<<sweep_grid(ctx, a.n >> 2), kThreads, 0, (cudaStream_t)stream>>>(a);
     MAMDR_LAUNCH_OK(ctx);
     return MAMDR_OK;
 }
 
 }  // namespace
+
+// run-time dispatch used when a recorded program holds no pass (program.cuh)
+int mamdr_meta_launch(mamdr_ctx* ctx, int meta_op, const MetaArgs& a, mamdr_stream stream) {
+    switch (meta_op) {
+        case OP_COPY: return launch_meta<OP_COPY>(ctx, a, stream);
+        case OP_MERGE: return launch_meta<OP_MERGE>(ctx, a, stream);
+        case OP_DN: return launch_meta<OP_DN>(ctx, a, stream);
+        case OP_DR: return launch_meta<OP_DR>(ctx, a, stream);
+        case OP_DR_ACC: return launch_meta<OP_DR_ACC>(ctx, a, stream);
+        case OP_DR_APPLY: return launch_meta<OP_DR_APPLY>(ctx, a, stream);
+        case OP_SUB: return launch_meta<OP_SUB>(ctx, a, stream);
+        case OP_AXPY_DIFF: return launch_meta<OP_AXPY_DIFF>(ctx, a, stream);
+    }
+    MAMDR_SET_ERR(ctx, "unknown meta op %d", meta_op);
+    return MAMDR_E_INVALID;
+}
 
 extern "C" size_t mamdr_opt_state_bytes(void) { return sizeof(OptState); }
 
@@ -205,6 +161,7 @@ extern "C" int mamdr_adam_step(mamdr_ctx* ctx, float* p, float* m, float* v, con
                                float lr, float beta1, float beta2, float eps, mamdr_stream stream) {
     MAMDR_REQUIRE(ctx, ctx != nullptr, MAMDR_E_INVALID, "ctx is NULL");
     MAMDR_REQUIRE(ctx, p && m && v && g && state, MAMDR_E_INVALID, "NULL pointer");
+    MAMDR_REQUIRE(ctx, !mamdr_prog_recording(ctx), MAMDR_E_INVALID, "mamdr_adam_step cannot be recorded into a program");
     MAMDR_REQUIRE(ctx, n > 0 && n % 4 == 0, MAMDR_E_INVALID, "arena length must be a positive multiple of 4");
     MAMDR_REQUIRE(ctx, aligned16(p) && aligned16(m) && aligned16(v) && aligned16(g), MAMDR_E_INVALID, "misaligned arena");
     adam_kernel<<<sweep_grid(ctx, n >> 2), kThreads, 0, (cudaStream_t)stream>>>(p, m, v, g, n, (OptState*)state, lr,

@@ -36,19 +36,21 @@ class DomainNegotiation(MAML):
         if tc['shuffle_sequence']:                            # :41-42
             self.meta_sequence = self.schedule.shuffle_sequence(self.meta_sequence)
         self.stage_epoch_orders(list(self.meta_sequence))
-        self._set_model_meta_parms(self.meta_weights)         # :50
-        for idx in self.meta_sequence:                        # :53-84
-            d = self.dataset.train_dataset[idx]
-            for m in self.model.stateful_metric_functions:    # :56-57
-                m.reset_states()
-            train_step = d['n_step']
-            if tc['meta_train_step'] > 0:
-                train_step = min(train_step, tc['meta_train_step'])
-            # per-pass loss / AUC prints of :80-84 would force a host sync per pass; the per-batch
-            # losses stay on the device (fit_pass returns them) and are read only on request
-            self.last_pass_losses = self.run_train_pass(idx, train_step)
-        self._update_meta_weight(self.meta_weights)           # :87
-        # :88 _set_model_meta_parms(meta_weights) is fused into the update (model_out)
+        # the whole meta-step is recorded and runs as ONE persistent launch in the tcgen05 modes (engine.program)
+        with self.model.program(self.b200_config.get('program', True)):
+            self._set_model_meta_parms(self.meta_weights)         # :50
+            for idx in self.meta_sequence:                        # :53-84
+                d = self.dataset.train_dataset[idx]
+                for m in self.model.stateful_metric_functions:    # :56-57
+                    m.reset_states()
+                train_step = d['n_step']
+                if tc['meta_train_step'] > 0:
+                    train_step = min(train_step, tc['meta_train_step'])
+                # per-pass loss / AUC prints of :80-84 would force a host sync per pass; the per-batch
+                # losses stay on the device (fit_pass returns them) and are read only on request
+                self.last_pass_losses = self.run_train_pass(idx, train_step)
+            self._update_meta_weight(self.meta_weights)           # :87
+            # :88 _set_model_meta_parms(meta_weights) is fused into the update (model_out)
 
     def _update_meta_weight(self, old_vars):
         """:118-123  old += (new - old) * meta_learning_rate, and the model is reloaded with it (:88)."""

@@ -5,6 +5,7 @@ builds in ``/root/reference/model_zoo/DeepCTR/deepctr.py:20-61`` (BCE loss, ``Ad
 All arithmetic runs in ``libmamdr_b200.so`` through the C-ABI; PyTorch only owns device memory and
 streams.  Nothing here falls back to the CPU.
 """
+import contextlib
 import ctypes as C
 
 import numpy as np
@@ -143,6 +144,8 @@ class MLPModel(object):
         self.thresholds = torch.from_numpy(auc_thresholds(self.num_thresholds)).to(dev)
         self.auc_acc = torch.zeros(4, self.num_thresholds, **f32)
         self._auc_out = torch.zeros(1, **f32)
+        self._auc_zero = torch.zeros(4, self.num_thresholds, **f32)
+        self._recording = False
         self.reset_optimizer()
         self._graphs = {}
         self._loss_bufs = {}
@@ -168,6 +171,10 @@ class MLPModel(object):
             self.pass_ws_bytes = lib.mamdr_mlp_pass_workspace_bytes(C.byref(d), self.max_batch)
             self.pass_ws = torch.zeros(self.pass_ws_bytes, dtype=torch.uint8, device=dev)
             self.pass_kernel = True
+            self._prog_buf = torch.zeros(4096 * int(lib.mamdr_program_op_bytes()), dtype=torch.uint8, device=dev)
+        self._recording = False
+        self.program_ops = 0
+        self.launch_times = None
 
     # ---- Keras-like surface -------------------------------------------------------------------------
     @property
@@ -192,7 +199,10 @@ class MLPModel(object):
 
     def reset_states(self):
         """``AUC.reset_states`` (utils/auc.py:283-284)."""
-        self.auc_acc.zero_()
+        if self._recording:   # keep the reset in program order
+            self.ctx.call("mamdr_copy", _ptr(self.auc_acc), _ptr(self._auc_zero), self.auc_acc.numel(), self.stream)
+        else:
+            self.auc_acc.zero_()
 
     def reset_optimizer(self):
         """``tf.global_variables_initializer()`` on the optimizer slots
@@ -249,12 +259,39 @@ class MLPModel(object):
         b.offset, b.rows, b.domain = int(offset), int(rows), int(data.domain)
         return b
 
-    def _pass(self, data, steps, use_order, offset=0, rows=None):
-        """Descriptor of a pass over ``data``; with ``rows`` given: the single mini-batch [offset, offset+rows)."""
+    @contextlib.contextmanager
+    def program(self, enabled=True):
+        """Deferred execution: every training pass and meta sweep issued inside the block is recorded and the whole
+        sequence runs as ONE persistent cooperative launch at the end of the block (``mamdr_program_begin / _end``).
+        Only the tcgen05 modes have the in-kernel executor; otherwise (or with ``enabled=False``) this is a no-op and
+        calls execute immediately."""
+        if not (enabled and self.pass_kernel) or self._recording:
+            yield False
+            return
+        self.ctx.call("mamdr_program_begin")
+        self._recording = True
+        self._prog_minibatches = 0
+        try:
+            yield True
+        except BaseException:
+            self._recording = False
+            self.ctx.lib.mamdr_program_abort(self.ctx.handle)
+            raise
+        self._recording = False
+        n_ops = C.c_int32(0)
+        ev = self._launch_event()
+        self.ctx.call("mamdr_program_end", _ptr(self._prog_buf), self._prog_buf.numel(), C.byref(n_ops), self.stream)
+        self._launch_event(ev, self._prog_minibatches)
+        self.ctx.launches += 3   # H2D of the op list, barrier memset, the persistent kernel
+        self.program_ops = n_ops.value
+
+    def _pass(self, data, steps, use_order, offset=0, rows=None, order=None):
+        """Descriptor of a pass over ``data``; with ``rows`` given: the single mini-batch [offset, offset+rows).
+        ``order``: an int32 device tensor holding the pass's sample order (default: ``data.order``)."""
         ps = _lib.Pass()
         ps.uid_dev, ps.pid_dev, ps.label_dev = data.uid.data_ptr(), data.pid.data_ptr(), data.label.data_ptr()
         ps.n_data, ps.batch_size, ps.steps, ps.domain = data.n_data, data.batch_size, int(steps), int(data.domain)
-        ps.order_dev = data.order.data_ptr() if use_order else None
+        ps.order_dev = (order if order is not None else data.order).data_ptr() if use_order else None
         if rows is not None:
             ps.n_data, ps.batch_size, ps.steps = int(rows), int(rows), 1
             if use_order:
@@ -264,15 +301,31 @@ class MLPModel(object):
                 ps.label_dev = data.label.data_ptr() + 4 * int(offset)
         return ps
 
+    def _launch_event(self, start=None, minibatches=0):
+        """bench hook: with ``self.launch_times`` set to a list, every launch of the persistent kernel is bracketed
+        by CUDA events on its stream and (start, end, mini-batches) is appended."""
+        if self.launch_times is None:
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(torch.cuda.current_stream(self.device))
+        if start is not None:
+            self.launch_times.append((start, e, minibatches))
+        return e
+
     def _train_pass(self, ps, losses, with_auc=True):
         adam = self.optimizer == "adam"
+        ev = None if self._recording else self._launch_event()
         self.ctx.call("mamdr_mlp_train_pass", C.byref(self.desc), C.byref(ps), _ptr(self.user_table),
                       _ptr(self.item_table), _ptr(self.params), _ptr(self.m), _ptr(self.v), _ptr(self.grads),
                       _ptr(self.pass_ws), self.pass_ws_bytes, _ptr(self.opt_state), _ptr(losses),
                       _ptr(self.auc_acc if with_auc else None), _ptr(self.thresholds), self.num_thresholds,
                       0 if adam else 1, self.lr if adam else self.sgd_lr, self.beta1, self.beta2, self.eps,
                       self.precision, self.stream)
-        self.ctx.launches += 2   # 64-byte barrier memset + the persistent kernel
+        if self._recording:
+            self._prog_minibatches += ps.steps
+        else:
+            self.ctx.launches += 2   # 64-byte barrier memset + the persistent kernel
+            self._launch_event(ev, ps.steps)
 
     def _eval_pass(self, ps, losses, probs=None, with_auc=True):
         self.ctx.call("mamdr_mlp_eval_pass", C.byref(self.desc), C.byref(ps), _ptr(self.user_table),
@@ -334,7 +387,7 @@ class MLPModel(object):
         bs = data.batch_size
         return [(s * bs, min(bs, data.n_data - s * bs)) for s in range(steps)]
 
-    def fit_pass(self, data, steps=None):
+    def fit_pass(self, data, steps=None, order=None):
         """One pass of ``steps`` mini-batches over ``data`` in the order installed by
         ``data.set_order`` (== the ``for step in range(train_step): model.train_on_batch(iter)`` loops
         of mamdr.py:85-97 and domain_negotiation.py:71-72, and ``model.fit(iter, steps_per_epoch)`` of
@@ -350,8 +403,10 @@ class MLPModel(object):
         if losses is None:
             losses = self._loss_bufs[key] = torch.zeros(steps, dtype=torch.float32, device=self.device)
         if self.pass_kernel:
-            self._train_pass(self._pass(data, steps, True), losses)
+            self._train_pass(self._pass(data, steps, True, order=order), losses)
             return losses
+        if order is not None:
+            data.order.copy_(order, non_blocking=True)   # the captured graphs read data.order
         plan = self._pass_plan(data, steps)
         if not self.use_graphs:
             for s, (off, rows) in enumerate(plan):

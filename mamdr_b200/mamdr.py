@@ -76,46 +76,52 @@ class MAMDR(SpecificBase):
             mine += [owner[idx] == rank] * k
         self.stage_epoch_orders(passes, mine if world > 1 else None)
 
-        # ---- Update Shared (DN), :48-57
-        self._set_model_meta_parms(self.meta_weights)
-        for idx in train_sequence:
-            self.run_train_pass(idx)
-        self._update_meta_weight(self.meta_weights, meta_lr=beta)
+        # In the tcgen05 modes the DN phase and every DR chain of this rank are each recorded and run as ONE persistent
+        # launch (engine.program: passes + meta sweeps executed in-kernel); recording chain k+1 overlaps the execution
+        # of chain k.  finetune_every_epoch allocates temporaries -> immediate mode.
+        use_program = self.b200_config.get('program', True) and not tc['finetune_every_epoch']
+        with self.model.program(use_program):
+            # ---- Update Shared (DN), :48-57
+            self._set_model_meta_parms(self.meta_weights)
+            for idx in train_sequence:
+                self.run_train_pass(idx)
+            self._update_meta_weight(self.meta_weights, meta_lr=beta)
 
         # ---- Update specific (DR), :59-108
         batch_mode = "batch" in self.model_config['name']
         for idx in train_sequence:
             if owner[idx] != rank:
                 continue
-            d = self.dataset.train_dataset[idx]
-            aux_idxs = supports[idx]
-            theta_i = self.domain_weights[idx]
-            # merged = theta (+|*) theta_i is never materialised on the host: model <- merged (:72,78)
-            self._set_model_merged(self.meta_weights, theta_i)
-            if batch_mode:
-                self._zero_accum()
-            for k, aux_idx in enumerate(aux_idxs):
-                self.log(f"Support Domain: {aux_idx}, Query Domain: {idx}")
-                self.run_train_pass(aux_idx)                         # :85-86
-                train_step = d['n_step']                             # :92-97
-                if tc['domain_regulation_step'] > 0:
-                    train_step = min(train_step, tc['domain_regulation_step'])
-                self.run_train_pass(idx, train_step)
-                if batch_mode:                                       # :100-101
-                    self._accumulate_grad(theta_i)
-                    self._set_model_merged(self.meta_weights, theta_i)
-                else:                                                # :103-105 + next iteration's :78
-                    self._dr_update(theta_i, beta)
-            if batch_mode:                                           # :107-108
-                self._update_meta_weight_by_grads(theta_i)
+            with self.model.program(use_program):
+                d = self.dataset.train_dataset[idx]
+                aux_idxs = supports[idx]
+                theta_i = self.domain_weights[idx]
+                # merged = theta (+|*) theta_i is never materialised on the host: model <- merged (:72,78)
+                self._set_model_merged(self.meta_weights, theta_i)
+                if batch_mode:
+                    self._zero_accum()
+                for k, aux_idx in enumerate(aux_idxs):
+                    self.log(f"Support Domain: {aux_idx}, Query Domain: {idx}")
+                    self.run_train_pass(aux_idx)                         # :85-86
+                    train_step = d['n_step']                             # :92-97
+                    if tc['domain_regulation_step'] > 0:
+                        train_step = min(train_step, tc['domain_regulation_step'])
+                    self.run_train_pass(idx, train_step)
+                    if batch_mode:                                       # :100-101
+                        self._accumulate_grad(theta_i)
+                        self._set_model_merged(self.meta_weights, theta_i)
+                    else:                                                # :103-105 + next iteration's :78
+                        self._dr_update(theta_i, beta)
+                if batch_mode:                                           # :107-108
+                    self._update_meta_weight_by_grads(theta_i)
 
-            if tc['finetune_every_epoch']:                           # :110-143
-                merged = self._merge_weights(self.meta_weights, theta_i)
-                self._set_model_meta_parms(merged)
-                for m in self.model.stateful_metric_functions:
-                    m.reset_states()
-                self.run_train_pass(idx)
-                self._update_domain_weights(theta_i, merged)
+                if tc['finetune_every_epoch']:                           # :110-143
+                    merged = self._merge_weights(self.meta_weights, theta_i)
+                    self._set_model_meta_parms(merged)
+                    for m in self.model.stateful_metric_functions:
+                        m.reset_states()
+                    self.run_train_pass(idx)
+                    self._update_domain_weights(theta_i, merged)
 
         if world > 1:
             # the one collective of the meta-step: theta_i from their owners + the Adam slots of the rank
