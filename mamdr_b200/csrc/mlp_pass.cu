@@ -379,6 +379,102 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
         dp.step = (uint32_t)(step_ctr & 0xffffffffll);
         dp.seed = a.dropout_seed;
 
+        const int jobs_last_bwd = a.train ? phase_jobs(a, 2 * L - 1, rows) : 0;
+        const bool early_done = a.train && G - jobs_last_bwd >= G / 4;   // enough idle CTAs in the last backward phase
+        // fixed-order reduction of the split-K / per-tile partials fused with the optimizer apply, for the float4 items
+        // first, first + stride, ...;  which: 0 = all, 1 = early items only, 2 = late items only
+        auto update_items = [&](long long first, long long stride, int which) {
+            int chunks, S, cps;
+            split_plan(rows, chunks, S, cps);
+            const float alpha = __fdiv_rn(__fmul_rn(a.lr, __fsqrt_rn(__fsub_rn(1.0f, b2pow))), __fsub_rn(1.0f, b1pow));
+            const float omb1 = __fsub_rn(1.0f, a.beta1), omb2 = __fsub_rn(1.0f, a.beta2);
+            const float two_l2 = 2.0f * a.l2_emb;
+            const long long nv4 = a.arena >> 2;
+            for (long long i4 = first; i4 < nv4; i4 += stride) {
+                const long long o = i4 << 2;
+                int si = -1;
+                for (int q = 0; q < a.nseg; ++q)
+                    if (o >= a.seg[q].off && o < a.seg[q].off + a.seg[q].numel) si = q;
+                if (si < 0) continue;   // alignment padding stays zero
+                const Seg sg = a.seg[si];
+                // early items: everything whose gradient is final before the last backward phase (layers >= 1, dense, global bias)
+                const bool late = sg.kind == SEG_ED || ((sg.kind == SEG_KERNEL || sg.kind == SEG_BIAS) && sg.layer == 0);
+                if ((which == 1 && late) || (which == 2 && !late)) continue;
+                const int e = (int)(o - sg.off);
+                const float4 P = ldcg_f4(a.params + o);
+                float4 M = make_float4(0.f, 0.f, 0.f, 0.f), V = M;
+                if (a.opt_kind == 0) { M = ldcg_f4(a.m + o); V = ldcg_f4(a.v + o); }
+                float g[4] = {0.f, 0.f, 0.f, 0.f};
+                if (sg.kind == SEG_KERNEL) {
+                    const int l = sg.layer, N = a.n[l + 1];
+                    const int k = e / N, c = e - k * N;
+                    if (l == 0 && k >= K0) {   // domain block: rank-1  E_d[dom]^T (x) db_0
+                        const float ev = ldcg_f(a.ed_row + (k - K0));
+                        const float4 d4 = ldcg_f4(a.db0_red + c);
+                        g[0] = __fmul_rn(ev, d4.x); g[1] = __fmul_rn(ev, d4.y); g[2] = __fmul_rn(ev, d4.z); g[3] = __fmul_rn(ev, d4.w);
+                    } else {
+                        const int bn = dw_bn(a, l), NT = N / bn, tiles = cdiv(a.n[l], 128) * NT;
+                        const int tile = (k >> 7) * NT + c / bn;
+                        const float* src = a.partials[l] + ((long long)tile * 128 + (k & 127)) * bn + (c % bn);
+                        const long long zstride = (long long)tiles * 128 * bn;
+                        float4 q4[kMaxSplit];
+#pragma unroll
+                        for (int z = 0; z < kMaxSplit; ++z) q4[z] = z < S ? ldcg_f4(src + z * zstride) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int z = 0; z < kMaxSplit; ++z)
+                            if (z < S) { g[0] += q4[z].x; g[1] += q4[z].y; g[2] += q4[z].z; g[3] += q4[z].w; }
+                    }
+                } else if (sg.kind == SEG_BIAS) {
+                    const int N = a.n[sg.layer + 1];
+                    const float* src = sg.layer == 0 ? nullptr : a.db_part[sg.layer] + e;
+                    if (sg.layer == 0) {
+                        const float4 q4 = ldcg_f4(a.db0_red + e);
+                        g[0] = q4.x; g[1] = q4.y; g[2] = q4.z; g[3] = q4.w;
+                    } else {
+                        for (int m0 = 0; m0 < mt; m0 += 8) {
+                            float4 q4[8];
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) q4[u] = m0 + u < mt ? ldcg_f4(src + (long long)(m0 + u) * N) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                            for (int u = 0; u < 8; ++u)
+                                if (m0 + u < mt) { g[0] += q4[u].x; g[1] += q4[u].y; g[2] += q4[u].z; g[3] += q4[u].w; }
+                        }
+                    }
+                } else if (sg.kind == SEG_DENSE) {
+                    for (int m0 = 0; m0 < mt; m0 += 8) {
+                        float4 q4[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) q4[u] = m0 + u < mt ? ldcg_f4(a.dw_part + (m0 + u) * NL + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                            if (m0 + u < mt) { g[0] += q4[u].x; g[1] += q4[u].y; g[2] += q4[u].z; g[3] += q4[u].w; }
+                    }
+                } else if (sg.kind == SEG_GBIAS) {
+                    for (int m = 0; m < mt; ++m) g[0] += ldcg_f(a.dg_part + m);
+                } else {   // SEG_ED: L2 term on every row (+ the batch row's data gradient)
+                    const float4 p4 = P;
+                    g[0] = __fmul_rn(two_l2, p4.x); g[1] = __fmul_rn(two_l2, p4.y); g[2] = __fmul_rn(two_l2, p4.z); g[3] = __fmul_rn(two_l2, p4.w);
+                    if (e / a.dd == pd.dom) {
+                        const float4 d4 = ldcg_f4(a.gEd_row + (e - pd.dom * a.dd));
+                        g[0] = __fadd_rn(g[0], d4.x); g[1] = __fadd_rn(g[1], d4.y); g[2] = __fadd_rn(g[2], d4.z); g[3] = __fadd_rn(g[3], d4.w);
+                    }
+                }
+                float pp[4] = {P.x, P.y, P.z, P.w};
+                if (a.opt_kind == 0) {
+                    float mm[4] = {M.x, M.y, M.z, M.w}, vv[4] = {V.x, V.y, V.z, V.w};
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) adam1(pp[t], mm[t], vv[t], g[t], alpha, omb1, omb2, a.eps);
+                    *reinterpret_cast<float4*>(a.m + o) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+                    *reinterpret_cast<float4*>(a.v + o) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) pp[t] = __fsub_rn(pp[t], __fmul_rn(g[t], a.lr));
+                }
+                *reinterpret_cast<float4*>(a.params + o) = make_float4(pp[0], pp[1], pp[2], pp[3]);
+                if (rnd && sg.kind == SEG_KERNEL) *reinterpret_cast<float4*>(a.wshadow + o) = rn_tf32_4(make_float4(pp[0], pp[1], pp[2], pp[3]));
+                if (a.grads) *reinterpret_cast<float4*>(a.grads + o) = make_float4(g[0], g[1], g[2], g[3]);
+            }
+        };
         for (int phase = 0; phase < n_phases; ++phase) {
             const long long tslot = (((long long)step * n_phases + phase) * G + cta) * 16;
             const bool tim = a.timing && tslot + 15 < a.timing_cap;
@@ -866,100 +962,17 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                     }
                     ++njob;
                 }
+                if (phase == 2 * L - 1 && early_done && cta >= jobs_last_bwd)
+                    update_items((long long)(cta - jobs_last_bwd) * kThreads + tid, (long long)(G - jobs_last_bwd) * kThreads, 1);
                 // while the few head tiles run, everyone else stages the next mini-batch
                 if (phase == L - 1 && step + 1 < pd.steps && warp < 4) {
                     const int first = G > 2 * mt ? mt : 0;
                     if (cta >= first) gather_rows(a, pd, step + 1, buf ^ 1, (cta - first) * 4 + warp, (G - first) * 4, lane, rnd);
                 }
             } else {
-                // ---------- update phase: fixed-order reduction of the partials fused with the optimizer apply
-                int chunks, S, cps;
-                split_plan(rows, chunks, S, cps);
-                const float alpha = __fdiv_rn(__fmul_rn(a.lr, __fsqrt_rn(__fsub_rn(1.0f, b2pow))), __fsub_rn(1.0f, b1pow));
-                const float omb1 = __fsub_rn(1.0f, a.beta1), omb2 = __fsub_rn(1.0f, a.beta2);
-                const float two_l2 = 2.0f * a.l2_emb;
-                const long long nv4 = a.arena >> 2;
-                for (long long i4 = (long long)cta * kThreads + tid; i4 < nv4; i4 += (long long)G * kThreads) {
-                    const long long o = i4 << 2;
-                    int si = -1;
-                    for (int q = 0; q < a.nseg; ++q)
-                        if (o >= a.seg[q].off && o < a.seg[q].off + a.seg[q].numel) si = q;
-                    if (si < 0) continue;   // alignment padding stays zero
-                    const Seg sg = a.seg[si];
-                    const int e = (int)(o - sg.off);
-                    const float4 P = ldcg_f4(a.params + o);
-                    float4 M = make_float4(0.f, 0.f, 0.f, 0.f), V = M;
-                    if (a.opt_kind == 0) { M = ldcg_f4(a.m + o); V = ldcg_f4(a.v + o); }
-                    float g[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (sg.kind == SEG_KERNEL) {
-                        const int l = sg.layer, N = a.n[l + 1];
-                        const int k = e / N, c = e - k * N;
-                        if (l == 0 && k >= K0) {   // domain block: rank-1  E_d[dom]^T (x) db_0
-                            const float ev = ldcg_f(a.ed_row + (k - K0));
-                            const float4 d4 = ldcg_f4(a.db0_red + c);
-                            g[0] = __fmul_rn(ev, d4.x); g[1] = __fmul_rn(ev, d4.y); g[2] = __fmul_rn(ev, d4.z); g[3] = __fmul_rn(ev, d4.w);
-                        } else {
-                            const int bn = dw_bn(a, l), NT = N / bn, tiles = cdiv(a.n[l], 128) * NT;
-                            const int tile = (k >> 7) * NT + c / bn;
-                            const float* src = a.partials[l] + ((long long)tile * 128 + (k & 127)) * bn + (c % bn);
-                            const long long zstride = (long long)tiles * 128 * bn;
-                            float4 q4[kMaxSplit];
-#pragma unroll
-                            for (int z = 0; z < kMaxSplit; ++z) q4[z] = z < S ? ldcg_f4(src + z * zstride) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                            for (int z = 0; z < kMaxSplit; ++z)
-                                if (z < S) { g[0] += q4[z].x; g[1] += q4[z].y; g[2] += q4[z].z; g[3] += q4[z].w; }
-                        }
-                    } else if (sg.kind == SEG_BIAS) {
-                        const int N = a.n[sg.layer + 1];
-                        const float* src = sg.layer == 0 ? nullptr : a.db_part[sg.layer] + e;
-                        if (sg.layer == 0) {
-                            const float4 q4 = ldcg_f4(a.db0_red + e);
-                            g[0] = q4.x; g[1] = q4.y; g[2] = q4.z; g[3] = q4.w;
-                        } else {
-                            for (int m0 = 0; m0 < mt; m0 += 8) {
-                                float4 q4[8];
-#pragma unroll
-                                for (int u = 0; u < 8; ++u) q4[u] = m0 + u < mt ? ldcg_f4(src + (long long)(m0 + u) * N) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                                for (int u = 0; u < 8; ++u)
-                                    if (m0 + u < mt) { g[0] += q4[u].x; g[1] += q4[u].y; g[2] += q4[u].z; g[3] += q4[u].w; }
-                            }
-                        }
-                    } else if (sg.kind == SEG_DENSE) {
-                        for (int m0 = 0; m0 < mt; m0 += 8) {
-                            float4 q4[8];
-#pragma unroll
-                            for (int u = 0; u < 8; ++u) q4[u] = m0 + u < mt ? ldcg_f4(a.dw_part + (m0 + u) * NL + e) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                            for (int u = 0; u < 8; ++u)
-                                if (m0 + u < mt) { g[0] += q4[u].x; g[1] += q4[u].y; g[2] += q4[u].z; g[3] += q4[u].w; }
-                        }
-                    } else if (sg.kind == SEG_GBIAS) {
-                        for (int m = 0; m < mt; ++m) g[0] += ldcg_f(a.dg_part + m);
-                    } else {   // SEG_ED: L2 term on every row (+ the batch row's data gradient)
-                        const float4 p4 = P;
-                        g[0] = __fmul_rn(two_l2, p4.x); g[1] = __fmul_rn(two_l2, p4.y); g[2] = __fmul_rn(two_l2, p4.z); g[3] = __fmul_rn(two_l2, p4.w);
-                        if (e / a.dd == pd.dom) {
-                            const float4 d4 = ldcg_f4(a.gEd_row + (e - pd.dom * a.dd));
-                            g[0] = __fadd_rn(g[0], d4.x); g[1] = __fadd_rn(g[1], d4.y); g[2] = __fadd_rn(g[2], d4.z); g[3] = __fadd_rn(g[3], d4.w);
-                        }
-                    }
-                    float pp[4] = {P.x, P.y, P.z, P.w};
-                    if (a.opt_kind == 0) {
-                        float mm[4] = {M.x, M.y, M.z, M.w}, vv[4] = {V.x, V.y, V.z, V.w};
-#pragma unroll
-                        for (int t = 0; t < 4; ++t) adam1(pp[t], mm[t], vv[t], g[t], alpha, omb1, omb2, a.eps);
-                        *reinterpret_cast<float4*>(a.m + o) = make_float4(mm[0], mm[1], mm[2], mm[3]);
-                        *reinterpret_cast<float4*>(a.v + o) = make_float4(vv[0], vv[1], vv[2], vv[3]);
-                    } else {
-#pragma unroll
-                        for (int t = 0; t < 4; ++t) pp[t] = __fsub_rn(pp[t], __fmul_rn(g[t], a.lr));
-                    }
-                    *reinterpret_cast<float4*>(a.params + o) = make_float4(pp[0], pp[1], pp[2], pp[3]);
-                    if (rnd && sg.kind == SEG_KERNEL) *reinterpret_cast<float4*>(a.wshadow + o) = rn_tf32_4(make_float4(pp[0], pp[1], pp[2], pp[3]));
-                    if (a.grads) *reinterpret_cast<float4*>(a.grads + o) = make_float4(g[0], g[1], g[2], g[3]);
-                }
+                // ---------- update phase: Adam / SGD on the parameters whose gradients became final in the last backward
+                // phase (E_d, W_0, b_0); the rest was already applied by the idle CTAs of that phase (early_done)
+                update_items((long long)cta * kThreads + tid, (long long)G * kThreads, early_done ? 2 : 0);
                 if (a.opt_kind == 0) {
                     b1pow = __fmul_rn(b1pow, a.beta1);
                     b2pow = __fmul_rn(b2pow, a.beta2);
