@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libmamdr_b200.so")
+LIB_PATH = os.environ.get("MAMDR_B200_LIB") or os.path.join(_HERE, "lib", "libmamdr_b200.so")   # env override: A/B kernel builds
 
 MAX_LAYERS = 8
 PREC_FP32, PREC_TF32, PREC_TF32X3 = 0, 1, 2

@@ -48,7 +48,6 @@ constexpr int A_BYTES = 128 * KCH * 4;        // 16 KB
 constexpr int B_BYTES = 64 * KCH * 4;         // 8 KB (BN <= 64)
 constexpr int kMaxStages = 6;
 constexpr int kScratchBytes = 36 * 1024;
-constexpr int kStageOutBytes = 32 * 1024;      // epilogue staging: two 128-row x 128-byte swizzled boxes for TMA stores
 constexpr int kMaxThr = 1024;
 constexpr int kMaxSplit = 8;
 constexpr int kDomJobs = 8;                   // the domain-embedding gradient GEMV is split over this many CTAs
@@ -62,11 +61,10 @@ struct MapTable {   // kernel parameter (param space is a legal tensor-map addre
     CUtensorMap xk[2], xmn[2];                  // X double buffer: K-major [B, K0] / MN-major view
     CUtensorMap hk[MAMDR_MAX_LAYERS];           // H_l  K-major  (A of fwd l),      l = 1..L-1
     CUtensorMap hmn[MAMDR_MAX_LAYERS];          // H_l  MN-major (A of dW_l)
-    CUtensorMap dzk[MAMDR_MAX_LAYERS];          // dZ_l K-major  (A of dH_l; store target of the epilogues), l = 0..L-1
+    CUtensorMap dzk[MAMDR_MAX_LAYERS];          // dZ_l K-major  (A of dH_l),       l = 1..L-1
     CUtensorMap dzmn[MAMDR_MAX_LAYERS];         // dZ_l MN-major (B of dW_l),       l = 0..L-1
     CUtensorMap wf[MAMDR_MAX_LAYERS];           // W_l  MN-major [K, N] (B of fwd l)
     CUtensorMap wb[MAMDR_MAX_LAYERS];           // W_l  K-major  [N = in, K = out] (B of dH_l), l = 1..L-1
-    CUtensorMap pk[MAMDR_MAX_LAYERS];           // split-K partials of dW_l as rows of bn floats (store target)
 };
 
 struct Seg { long long off; int numel; int kind; int layer; };
@@ -226,10 +224,6 @@ __device__ __forceinline__ float rn_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
-// 3xTF32 low part: x - trunc_tf32(x) is exact; one cvt.rna rounds it to tf32 (3 instructions per element)
-__device__ __forceinline__ float tf32_lo_rna(float x) {
-    return rn_tf32(x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u));
-}
 __device__ __forceinline__ float4 rn_tf32_4(float4 v) { return make_float4(rn_tf32(v.x), rn_tf32(v.y), rn_tf32(v.z), rn_tf32(v.w)); }
 
 __device__ __forceinline__ void adam1(float& p, float& m, float& v, float g, float alpha, float omb1, float omb2, float eps) {
@@ -237,9 +231,6 @@ __device__ __forceinline__ void adam1(float& p, float& m, float& v, float g, flo
     v = __fadd_rn(v, __fmul_rn(__fsub_rn(__fmul_rn(g, g), v), omb2));
     p = __fsub_rn(p, __fdiv_rn(__fmul_rn(m, alpha), __fadd_rn(__fsqrt_rn(v), eps)));
 }
-
-// byte offset of 16-byte chunk j (0..7) of row r inside a 128-row x 128-byte SWIZZLE_128B box
-__device__ __forceinline__ uint32_t swz128(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
 
 // gather the rows of mini-batch `step` into X[buf] / y[buf]; one warp per row, 16-byte lanes
 __device__ __forceinline__ void gather_rows(const PassArgs& a, const PassDyn& pd, int step, int buf, int warp_rank, int n_warps, int lane, bool rnd) {
@@ -279,7 +270,6 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
     const int passes = a.passes;
     const uint32_t stage_bytes = (uint32_t)(A_BYTES + B_BYTES) * (passes == 3 ? 2u : 1u);
     unsigned char* scratch = smem + (size_t)STAGES * stage_bytes;
-    unsigned char* stage_out = scratch + kScratchBytes;   // 1024-byte aligned (all region sizes are multiples of 1024)
 
     if (tid == 0) {
         for (int s = 0; s < kMaxStages; ++s) {
@@ -363,10 +353,6 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
     grid_barrier(a.bar, bar_target);
 
     const int n_phases = a.train ? 2 * L + 1 : L;
-    bool pre_ok = false;
-    int pre_njobs = 0;
-    Job pre_job;
-    pre_job.type = J_NONE;
     for (int step = 0; step < pd.steps; ++step) {
         const long long left = pd.n_data - (long long)step * a.bs;
         const int rows = left < a.bs ? (int)left : a.bs;
@@ -480,10 +466,9 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
             const bool tim = a.timing && tslot + 15 < a.timing_cap;
             if (tim && tid == 0) { a.timing[tslot] = gtime(); a.timing[tslot + 7] = (unsigned long long)clock64(); }
             if (phase < 2 * L) {
-                // the first job of this phase was decoded while waiting at the previous barrier (pre_*)
-                const int njobs = pre_ok ? pre_njobs : phase_jobs(a, phase, rows);
+                const int njobs = phase_jobs(a, phase, rows);
                 for (int j = cta; j < njobs; j += G) {
-                    const Job J = (pre_ok && j == cta) ? pre_job : decode_job(a, phase, rows, j);
+                    const Job J = decode_job(a, phase, rows, j);
                     const int l = J.layer;
                     if (J.type == J_DOM) {
                         // ---------- domain-embedding job q of kDomJobs (workers): db_0 (every job, into smem), rows
@@ -560,7 +545,6 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                             for (int i = 0; i < J.nch; ++i, ++it) {
                                 const int s = it % STAGES, c = J.c_beg + i;
                                 if (it >= (uint32_t)STAGES) tc::mbar_wait(&bar_empty[s], ((it / STAGES) - 1) & 1);
-                                if (tim && i == STAGES) a.timing[tslot + 9] = (unsigned long long)clock64();
                                 unsigned char* st = smem + (size_t)s * stage_bytes;
                                 unsigned char *sA = st, *sB = st + A_BYTES;
                                 tc::mbar_arrive_expect_tx(&bar_full[s], tx);
@@ -596,28 +580,21 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                                 tc::tc_fence_after();
                                 if (tim && i == 0) a.timing[tslot + 4] = (unsigned long long)clock64();
                                 const uint32_t st = tc::smem_u32(smem + (size_t)s * stage_bytes);
-                                const uint32_t aA = st, aB = st + A_BYTES;   // lo halves sit A_BYTES + B_BYTES further
-                                // descriptors differ only in their 14-bit start-address field: build one per operand and
-                                // bump it (K-major: +32 B per 8-float k step; MN-major: +1024 B)
-                                const uint64_t dA = a_mn ? tc::make_smem_desc(aA, 4096, 512, 1) : tc::make_smem_desc(aA, 16, 1024, tc::kSwizzle128B);
-                                const uint64_t dB = b_mn ? tc::make_smem_desc(aB, 4096, 512, 1) : tc::make_smem_desc(aB, 16, 1024, tc::kSwizzle128B);
-                                const uint64_t stepA = a_mn ? (1024 >> 4) : (32 >> 4), stepB = b_mn ? (1024 >> 4) : (32 >> 4);
-                                const uint64_t loA = (uint64_t)((A_BYTES + B_BYTES) >> 4), loB = (uint64_t)((A_BYTES + B_BYTES) >> 4);
+                                const uint32_t aA = st, aB = st + A_BYTES, aAlo = st + A_BYTES + B_BYTES, aBlo = aAlo + A_BYTES;
+                                for (int pass = 0; pass < passes; ++pass) {
+                                    const uint32_t pa = (pass == 2) ? aAlo : aA;   // pass 0: A*B, 1: A*B_lo, 2: A_lo*B
+                                    const uint32_t pb = (pass == 1) ? aBlo : aB;
 #pragma unroll
-                                for (int k = 0; k < KCH / 8; ++k) {                 // pass 0: A * B
-                                    tc::mma_tf32(tmem, dA + k * stepA, dB + k * stepB, idesc, acc);
-                                    acc = 1;
-                                }
-                                if (passes == 3) {
-#pragma unroll
-                                    for (int k = 0; k < KCH / 8; ++k)               // pass 1: A * B_lo
-                                        tc::mma_tf32(tmem, dA + k * stepA, dB + loB + k * stepB, idesc, 1u);
-#pragma unroll
-                                    for (int k = 0; k < KCH / 8; ++k)               // pass 2: A_lo * B
-                                        tc::mma_tf32(tmem, dA + loA + k * stepA, dB + k * stepB, idesc, 1u);
+                                    for (int k = 0; k < KCH / 8; ++k) {
+                                        const uint64_t da = a_mn ? tc::make_smem_desc(pa + k * 1024, 4096, 512, 1)
+                                                                 : tc::make_smem_desc(pa + k * 32, 16, 1024, tc::kSwizzle128B);
+                                        const uint64_t db = b_mn ? tc::make_smem_desc(pb + k * 1024, 4096, 512, 1)
+                                                                 : tc::make_smem_desc(pb + k * 32, 16, 1024, tc::kSwizzle128B);
+                                        tc::mma_tf32(tmem, da, db, idesc, acc);
+                                        acc = 1;
+                                    }
                                 }
                                 tc::mma_commit(&bar_empty[s]);
-                                if (tim && i == 0) a.timing[tslot + 11] = (unsigned long long)clock64();
                             }
                             tc::mma_commit(&bar_done);
                             if (tim) a.timing[tslot + 5] = (unsigned long long)clock64();
@@ -641,13 +618,10 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                                 const int c = tid % bn, gq = tid / bn;
                                 const float* W0dom = a.params + a.off_W[0] + (long long)K0 * N + col0 + c;
                                 const float* ed = a.params + a.off_Ed + (long long)pd.dom * a.dd;
-                                float* s_ed = part + 4 * 64;                       // [dd] the batch's domain row
-                                for (int k = tid; k < a.dd; k += kWorkers) s_ed[k] = ldcg_f(ed + k);
-                                worker_sync();
                                 float s = 0.f;
                                 const int k_end = (gq + 1) * per < a.dd ? (gq + 1) * per : a.dd;
 #pragma unroll 8
-                                for (int k = gq * per; k < k_end; ++k) s = fmaf(s_ed[k], ldcg_f(W0dom + (long long)k * N), s);
+                                for (int k = gq * per; k < k_end; ++k) s = fmaf(ldcg_f(ed + k), ldcg_f(W0dom + (long long)k * N), s);
                                 part[gq * bn + c] = s;
                                 worker_sync();
                                 if (tid < bn) {
@@ -667,23 +641,15 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                             for (int i = 0; i < J.nch; ++i, ++it) {
                                 const int s = it % STAGES;
                                 tc::mbar_wait(&bar_full[s], (it / STAGES) & 1);
-                                if (i == 0) WSTAMP(14);
                                 float4* hi = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
                                 float4* lo = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + A_BYTES + B_BYTES);
-                                // A_lo sits at +0, B_lo at +A_BYTES inside the lo half (same offsets as the hi half)
-                                for (int q0 = tid; q0 < nv; q0 += 4 * kWorkers) {
-                                    float4 x[4];
-#pragma unroll
-                                    for (int u = 0; u < 4; ++u) x[u] = q0 + u * kWorkers < nv ? hi[q0 + u * kWorkers] : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                                    for (int u = 0; u < 4; ++u)
-                                        if (q0 + u * kWorkers < nv)
-                                            lo[q0 + u * kWorkers] = make_float4(tf32_lo_rna(x[u].x), tf32_lo_rna(x[u].y), tf32_lo_rna(x[u].z), tf32_lo_rna(x[u].w));
+                                for (int q = tid; q < nv; q += kWorkers) {
+                                    const float4 x = hi[q];
+                                    // A_lo sits at +0, B_lo at +A_BYTES inside the lo half (same offsets as the hi half)
+                                    lo[q] = make_float4(tcg::tf32_lo(x.x), tcg::tf32_lo(x.y), tcg::tf32_lo(x.z), tcg::tf32_lo(x.w));
                                 }
-                                if (i == 0) WSTAMP(15);
                                 tc::fence_proxy_async();
                                 tc::mbar_arrive(&bar_split[s]);
-                                if (i == 0) WSTAMP(10);
                             }
                         } else {
                             it += J.nch;
@@ -720,35 +686,28 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
 
                         if (J.type == J_FWD) {
                             WSTAMP(8);
-                            // the 128 x 32 output tile is staged in shared memory (128B-swizzled) and written by ONE TMA
-                            // store: row-per-thread 16-byte global stores cost 32 LSU wavefronts per instruction
+                            float* out = a.H[l + 1];
                             const float dscale = dp.enabled ? dp.scale : 1.0f;
 #pragma unroll
                             for (int n0 = 0; n0 < 32; n0 += 16) {
                                 float vv[16];
                                 tc::tmem_ld16(tlane + n0, vv);
+                                if (valid) {
 #pragma unroll
-                                for (int jx = 0; jx < 16; jx += 4) {
-                                    float h[4];
+                                    for (int jx = 0; jx < 16; jx += 4) {
+                                        float h[4];
 #pragma unroll
-                                    for (int t = 0; t < 4; ++t) {
-                                        h[t] = fmaxf(vv[jx + t] + s_beff[n0 + jx + t], 0.f);
-                                        h[t] = (keepmask >> (n0 + jx + t)) & 1ull ? h[t] * dscale : 0.f;
+                                        for (int t = 0; t < 4; ++t) {
+                                            h[t] = fmaxf(vv[jx + t] + s_beff[n0 + jx + t], 0.f);
+                                            h[t] = (keepmask >> (n0 + jx + t)) & 1ull ? h[t] * dscale : 0.f;
+                                        }
+                                        const float4 hv = make_float4(h[0], h[1], h[2], h[3]);
+                                        *reinterpret_cast<float4*>(out + (long long)row * N + col0 + n0 + jx) = rnd ? rn_tf32_4(hv) : hv;
                                     }
-                                    const float4 hv = make_float4(h[0], h[1], h[2], h[3]);
-                                    *reinterpret_cast<float4*>(stage_out + swz128(tid, (n0 + jx) >> 2)) = rnd ? rn_tf32_4(hv) : hv;
                                 }
                             }
                             tc::tc_fence_before();
                             tc::mbar_arrive(&bar_tfree);
-                            tc::fence_proxy_async();
-                            worker_sync();
-                            if (tid == 0) {
-                                tc::tma_store_2d(&maps.hk[l + 1], stage_out, col0, J.m_tile * 128);
-                                tc::tma_store_commit();
-                                tc::tma_store_wait_all();
-                            }
-                            worker_sync();   // staging buffer free again
                             WSTAMP(9);
                         } else if (J.type == J_HEAD) {
                             // last hidden layer + Dense(1) + sigmoid + BCE + ds + dZ_{L-1} + per-tile partials + AUC bins
@@ -812,6 +771,8 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                             }
                             if (lane == 0) { red_d[warp] = bs; red_f[warp] = dgs; }
                             if (a.train) {
+                                float* dZ = a.dZ[L - 1];
+                                const bool store = row < a.max_rows;
 #pragma unroll
                                 for (int c = 0; c < NL; c += 4) {
                                     const float4 wv = *reinterpret_cast<const float4*>(s_wd + c);
@@ -824,22 +785,18 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                                         colbuf[tid * (NL + 1) + c + t] = h[c + t] * dsv;
                                         h[c + t] = dz[t];
                                     }
-                                    // rows past the batch get zeros: dW's K loop runs over whole 32-row chunks.  Staged
-                                    // (128B-swizzled boxes of 32 columns) for the TMA store below.
-                                    const float4 dv = make_float4(dz[0], dz[1], dz[2], dz[3]);
-                                    *reinterpret_cast<float4*>(stage_out + (c >> 5) * 16384 + swz128(tid, (c & 31) >> 2)) = rnd ? rn_tf32_4(dv) : dv;
+                                    // rows past the batch get zeros: dW's K loop runs over whole 32-row chunks
+                                    if (store) {
+                                        const float4 dv = make_float4(dz[0], dz[1], dz[2], dz[3]);
+                                        *reinterpret_cast<float4*>(dZ + (long long)row * NL + c) = rnd ? rn_tf32_4(dv) : dv;
+                                    }
                                 }
-                                tc::fence_proxy_async();
                             }
                             WSTAMP(10);
                             worker_sync();
                             if (tid == 0) {
                                 a.loss_part[buf * kMaxMT + J.m_tile] = red_d[0] + red_d[1] + red_d[2] + red_d[3];
                                 a.dg_part[J.m_tile] = red_f[0] + red_f[1] + red_f[2] + red_f[3];
-                                if (a.train) {
-                                    for (int bx = 0; bx < NL / 32; ++bx) tc::tma_store_2d(&maps.dzk[L - 1], stage_out + bx * 16384, bx * 32, J.m_tile * 128);
-                                    tc::tma_store_commit();
-                                }
                             }
                             if (a.train) {
                                 constexpr int GROUPS = 128 / NL, RPG = 128 / GROUPS;
@@ -880,14 +837,15 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                                     for (int g2 = 0; g2 < GROUPS; ++g2) s += gsum[g2 * NL + tid];
                                     a.db_part[L - 1][J.m_tile * NL + tid] = s;
                                 }
-                                if (tid == 0) tc::tma_store_wait_all();
                             }
                             worker_sync();
                             WSTAMP(11);
                         } else if (J.type == J_DH) {
                             // dZ_{l-1}[row, col0..col0+32) = acc * inv_keep * 1[H_l > 0]; per-tile column sums -> db_{l-1}
                             const float* Hm = a.H[l];
+                            float* out = a.dZ[l - 1];
                             float dzv[32];
+                            const bool store = row < a.max_rows;
                             float4 hmask[8];   // all loads first: the stores below may alias as far as the compiler knows
 #pragma unroll
                             for (int u = 0; u < 8; ++u)
@@ -907,9 +865,9 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                                         r4[2] = hq.z > 0.f ? vv[jx + 2] * inv_keep : 0.f;
                                         r4[3] = hq.w > 0.f ? vv[jx + 3] * inv_keep : 0.f;
                                     }
-                                    {   // invalid rows carry zeros (dW's K loop runs over whole 32-row chunks)
+                                    if (store) {
                                         const float4 dv = make_float4(r4[0], r4[1], r4[2], r4[3]);
-                                        *reinterpret_cast<float4*>(stage_out + swz128(tid, (n0 + jx) >> 2)) = rnd ? rn_tf32_4(dv) : dv;
+                                        *reinterpret_cast<float4*>(out + o) = rnd ? rn_tf32_4(dv) : dv;
                                     }
 #pragma unroll
                                     for (int t = 0; t < 4; ++t) dzv[n0 + jx + t] = r4[t];
@@ -917,16 +875,11 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                             }
                             tc::tc_fence_before();
                             tc::mbar_arrive(&bar_tfree);
-                            tc::fence_proxy_async();
                             float* colbuf = reinterpret_cast<float*>(scratch);                    // [128][33]
                             float* gsum = reinterpret_cast<float*>(scratch + 128 * 33 * 4);       // [4][32]
 #pragma unroll
                             for (int c = 0; c < 32; ++c) colbuf[tid * 33 + c] = dzv[c];
                             worker_sync();
-                            if (tid == 0) {
-                                tc::tma_store_2d(&maps.dzk[l - 1], stage_out, col0, J.m_tile * 128);
-                                tc::tma_store_commit();
-                            }
                             {
                                 const int c = tid & 31, gq = tid >> 5;
                                 float s = 0.f;
@@ -935,29 +888,19 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                             }
                             worker_sync();
                             if (tid < 32) a.db_part[l - 1][(long long)J.m_tile * N + col0 + tid] = gsum[tid] + gsum[32 + tid] + gsum[64 + tid] + gsum[96 + tid];
-                            if (tid == 0) tc::tma_store_wait_all();
                             worker_sync();
                         } else {   // J_DW: split-K partial of dW_l -> partials[l][z][tile][128][bn]
                             const int tile = J.m_tile * J.NT + J.n_tile;
-                            const int prow = (J.z * J.tiles + tile) * 128;   // first row of this partial tile in the [*, bn] partial matrix
+                            float* mine = a.partials[l] + (((long long)J.z * J.tiles + tile) * 128 + tid) * J.bn;
                             for (int n0 = 0; n0 < J.bn; n0 += 16) {
                                 float vv[16];
                                 tc::tmem_ld16(tlane + n0, vv);
 #pragma unroll
                                 for (int jx = 0; jx < 16; jx += 4)
-                                    *reinterpret_cast<float4*>(stage_out + (n0 >> 5) * 16384 + swz128(tid, ((n0 & 31) + jx) >> 2)) =
-                                        make_float4(vv[jx], vv[jx + 1], vv[jx + 2], vv[jx + 3]);
+                                    __stcg(reinterpret_cast<float4*>(mine + n0 + jx), make_float4(vv[jx], vv[jx + 1], vv[jx + 2], vv[jx + 3]));
                             }
                             tc::tc_fence_before();
                             tc::mbar_arrive(&bar_tfree);
-                            tc::fence_proxy_async();
-                            worker_sync();
-                            if (tid == 0) {
-                                for (int bx = 0; bx < J.bn / 32; ++bx) tc::tma_store_2d(&maps.pk[l], stage_out + bx * 16384, bx * 32, prow);
-                                tc::tma_store_commit();
-                                tc::tma_store_wait_all();
-                            }
-                            worker_sync();
                         }
                     }
                     ++njob;
@@ -982,39 +925,6 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
             if (a.timing) {
                 __syncthreads();
                 if (tid == 0 && tim) a.timing[tslot + 1] = gtime();
-            }
-            // decode the next phase's first job now: the integer divisions hide behind the barrier wait
-            pre_ok = false;
-            {
-                int nphase = phase + 1, nrows = rows;
-                bool have = true;
-                if (nphase == n_phases) {
-                    nphase = 0;
-                    const long long nleft = pd.n_data - (long long)(step + 1) * a.bs;
-                    nrows = nleft < a.bs ? (int)nleft : a.bs;
-                    have = step + 1 < pd.steps;
-                }
-                if (have && nphase < 2 * L) {
-                    pre_njobs = phase_jobs(a, nphase, nrows);
-                    if (cta < pre_njobs) {
-                        pre_job = decode_job(a, nphase, nrows, cta);
-                        if (warp == 4 && lane == 0 && pre_job.type != J_DOM) {
-                            // warm the TMA descriptor cache for the job's two operands
-                            const int pl = pre_job.layer, nbuf = (nphase == 0) ? (buf ^ 1) : buf;
-                            if (pre_job.type == J_FWD || pre_job.type == J_HEAD) {
-                                tc::tma_prefetch_desc(pl == 0 ? &maps.xk[nbuf] : &maps.hk[pl]);
-                                tc::tma_prefetch_desc(&maps.wf[pl]);
-                            } else if (pre_job.type == J_DH) {
-                                tc::tma_prefetch_desc(&maps.dzk[pl]);
-                                tc::tma_prefetch_desc(&maps.wb[pl]);
-                            } else {
-                                tc::tma_prefetch_desc(pl == 0 ? &maps.xmn[nbuf] : &maps.hmn[pl]);
-                                tc::tma_prefetch_desc(&maps.dzmn[pl]);
-                            }
-                        }
-                    }
-                    pre_ok = true;
-                }
             }
             grid_barrier(a.bar, bar_target);
         }
@@ -1122,7 +1032,7 @@ inline PassWs pass_ws(const mamdr_mlp_desc& d, int B) {
 }
 
 inline size_t smem_bytes(int passes, int stages) {
-    return (size_t)stages * (A_BYTES + B_BYTES) * (passes == 3 ? 2 : 1) + kScratchBytes + kStageOutBytes + 1024;
+    return (size_t)stages * (A_BYTES + B_BYTES) * (passes == 3 ? 2 : 1) + kScratchBytes + 1024;
 }
 
 }  // namespace passk
@@ -1282,12 +1192,8 @@ static int run_pass(mamdr_ctx* ctx, const mamdr_mlp_desc* d, const mamdr_pass* p
     for (int l = 0; l < L; ++l) {
         if (l >= 1) {
             ok = ok && mlptc::kmajor_map(ctx, &mp.hk[l], a.H[l], Bp, a.n[l], 128) && mlptc::mnmajor_map(ctx, &mp.hmn[l], a.H[l], Bp, a.n[l]);
+            ok = ok && mlptc::kmajor_map(ctx, &mp.dzk[l], a.dZ[l], Bp, a.n[l + 1], 128);
             ok = ok && mlptc::kmajor_map(ctx, &mp.wb[l], wsrc + d->off_kernel[l], a.n[l], a.n[l + 1], 32);
-        }
-        ok = ok && mlptc::kmajor_map(ctx, &mp.dzk[l], a.dZ[l], Bp, a.n[l + 1], 128);
-        {   // split-K partials of dW_l: [kMaxSplit * tiles * 128 rows, bn] (rows of bn floats)
-            const int bn = dw_bn(a, l);
-            ok = ok && mlptc::kmajor_map(ctx, &mp.pk[l], a.partials[l], (uint64_t)kMaxSplit * dw_tiles(a, l) * 128, bn, 128);
         }
         ok = ok && mlptc::mnmajor_map(ctx, &mp.dzmn[l], a.dZ[l], Bp, a.n[l + 1]);
         ok = ok && mlptc::mnmajor_map(ctx, &mp.wf[l], wsrc + d->off_kernel[l], a.n[l], a.n[l + 1]);
