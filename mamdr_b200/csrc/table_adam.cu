@@ -52,26 +52,41 @@ __global__ void __launch_bounds__(kThreads) adam_table_kernel(TableArgs a) {
     const long long gwarp = (long long)blockIdx.x * (kThreads / 32) + warp;
     const long long nwarps = (long long)gridDim.x * (kThreads / 32);
     double sq = 0.0;
-    for (long long row = gwarp; row < a.rows; row += nwarps) {
-        const int slot = a.slot[row];
-        const long long base = row * a.dim;
+    // two rows per warp and trip: six 512-byte loads in flight per warp before the first dependent instruction
+    for (long long row0 = gwarp; row0 < a.rows; row0 += 2 * nwarps) {
+        const long long row1 = row0 + nwarps;
+        const bool has1 = row1 < a.rows;
+        const int slot0 = a.slot[row0], slot1 = has1 ? a.slot[row1] : -1;
         for (int c = lane * 4; c < a.dim; c += 128) {
-            float4 P = ld_stream_f4(a.p + base + c), M = ld_stream_f4(a.m + base + c), V = ld_stream_f4(a.v + base + c);
-            float4 G = make_float4(__fmul_rn(two_l2, P.x), __fmul_rn(two_l2, P.y), __fmul_rn(two_l2, P.z), __fmul_rn(two_l2, P.w));
-            if (slot >= 0) {
-                const float4 s = ldg_f4(a.uniq_rows + (long long)slot * a.dim + c);
-                G.x = __fadd_rn(G.x, s.x); G.y = __fadd_rn(G.y, s.y); G.z = __fadd_rn(G.z, s.z); G.w = __fadd_rn(G.w, s.w);
+            const long long o0 = row0 * a.dim + c, o1 = row1 * a.dim + c;
+            float4 P[2], M[2], V[2], S[2];
+            P[0] = ld_stream_f4(a.p + o0); M[0] = ld_stream_f4(a.m + o0); V[0] = ld_stream_f4(a.v + o0);
+            if (has1) { P[1] = ld_stream_f4(a.p + o1); M[1] = ld_stream_f4(a.m + o1); V[1] = ld_stream_f4(a.v + o1); }
+            S[0] = slot0 >= 0 ? ldg_f4(a.uniq_rows + (long long)slot0 * a.dim + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            S[1] = slot1 >= 0 ? ldg_f4(a.uniq_rows + (long long)slot1 * a.dim + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                if (r == 1 && !has1) break;
+                const int slot = r == 0 ? slot0 : slot1;
+                float4 G = make_float4(__fmul_rn(two_l2, P[r].x), __fmul_rn(two_l2, P[r].y), __fmul_rn(two_l2, P[r].z), __fmul_rn(two_l2, P[r].w));
+                if (slot >= 0) {
+                    G.x = __fadd_rn(G.x, S[r].x); G.y = __fadd_rn(G.y, S[r].y); G.z = __fadd_rn(G.z, S[r].z); G.w = __fadd_rn(G.w, S[r].w);
+                }
+                sq += (double)P[r].x * P[r].x + (double)P[r].y * P[r].y + (double)P[r].z * P[r].z + (double)P[r].w * P[r].w;
+                adam1(P[r].x, M[r].x, V[r].x, G.x, alpha, omb1, omb2, a.eps);
+                adam1(P[r].y, M[r].y, V[r].y, G.y, alpha, omb1, omb2, a.eps);
+                adam1(P[r].z, M[r].z, V[r].z, G.z, alpha, omb1, omb2, a.eps);
+                adam1(P[r].w, M[r].w, V[r].w, G.w, alpha, omb1, omb2, a.eps);
+                const long long o = r == 0 ? o0 : o1;
+                st_stream_f4(a.p + o, P[r]);
+                st_stream_f4(a.m + o, M[r]);
+                st_stream_f4(a.v + o, V[r]);
             }
-            sq += (double)P.x * P.x + (double)P.y * P.y + (double)P.z * P.z + (double)P.w * P.w;
-            adam1(P.x, M.x, V.x, G.x, alpha, omb1, omb2, a.eps);
-            adam1(P.y, M.y, V.y, G.y, alpha, omb1, omb2, a.eps);
-            adam1(P.z, M.z, V.z, G.z, alpha, omb1, omb2, a.eps);
-            adam1(P.w, M.w, V.w, G.w, alpha, omb1, omb2, a.eps);
-            st_stream_f4(a.p + base + c, P);
-            st_stream_f4(a.m + base + c, M);
-            st_stream_f4(a.v + base + c, V);
         }
-        if (slot >= 0 && lane == 0) a.slot[row] = -1;   // leave the map clean for the next mini-batch
+        if (lane == 0) {   // leave the map clean for the next mini-batch
+            if (slot0 >= 0) a.slot[row0] = -1;
+            if (slot1 >= 0) a.slot[row1] = -1;
+        }
     }
     // ---- l2 * sum(E^2): warp shuffle -> block (fixed order) -> last block sums the per-block partials in order
     __shared__ double wsum[kThreads / 32];
