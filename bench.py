@@ -491,7 +491,8 @@ def run_b200(args):
         s, tsec = run_once()
         s2, tsec2 = run_once()
         cpu = {"value": (s + s2) / (tsec + tsec2), "unit": "samples/s", "cores": cores, "kind": "port", "sample": desc}
-    line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
+    metric = METRIC if args.workload == "Taobao-10" else METRIC.replace("Taobao-10", args.workload)
+    line = {"metric": metric, "value": value, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_desc(config, args.workload, args.gpus),
