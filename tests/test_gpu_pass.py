@@ -200,3 +200,62 @@ def test_program_mode_is_bit_identical_to_immediate_mode(name):
         outs.append((torch.cat([f.flatten() for f in flats]).cpu(), wrapper.model.read_step()))
     assert torch.equal(outs[0][0], outs[1][0])
     assert outs[0][1] == outs[1][1]
+
+
+@pytest.mark.parametrize("hidden,emb", [([128, 64], (128, 128, 128)), ([64], (64, 64, 32)), ([256, 256, 128, 32], (128, 128, 128)),
+                                         ([32, 32], (32, 32, 64))])
+def test_pass_kernel_other_tower_shapes(hidden, emb):
+    """1-, 2- and 4-layer towers, 32-wide last layers, 64- / 32-wide embeddings: a short ragged pass vs the oracle."""
+    from oracle.meta import train_pass
+    from oracle.mlp import MLPSpec, OracleMLP
+    import run
+    c = make_config(**{"model.name": "mlp", "dataset.synthetic.scale": 0.1, "b200.precision": "tf32x3", "dataset.batch_size": 640,
+                       "model.hidden_dim": hidden, "model.user_dim": emb[0], "model.item_dim": emb[1], "model.domain_dim": emb[2]})
+    # the synthetic generator draws 128-d tables: slice them to the requested widths
+    import mamdr_b200.dataset as ds
+    orig = ds.MultiDomainDataset._from_synthetic
+
+    def sliced(self, sconf):
+        orig(self, sconf)
+        self.user_table = np.ascontiguousarray(self.user_table[:, :emb[0]])
+        self.item_table = np.ascontiguousarray(self.item_table[:, :emb[1]])
+    ds.MultiDomainDataset._from_synthetic = sliced
+    try:
+        base = run.build(c)
+    finally:
+        ds.MultiDomainDataset._from_synthetic = orig
+    m = base.model
+    assert m.pass_kernel
+    w = _perturb(base)
+    spec = MLPSpec(base.n_uid, base.n_pid, base.n_domain, emb, tuple(hidden), dropout=0.5)
+    o = OracleMLP(spec, w, base.dataset.user_table, base.dataset.item_table, lr=1e-3)
+    data = base.dataset.train_dataset[1]['data']
+    assert data.n_data > 640 and data.n_data % 640 != 0
+    order = Schedule(2).batch_order(1, data.n_data)
+    data.set_order(order)
+    losses = m.fit_pass(data)
+    h = data.host
+    o_loss, _, steps = train_pass(o, {"uid": h['uid'], "pid": h['pid'], "label": h['label']}, 1, order, 640)
+    assert steps == data.n_step
+    for name, a, b in zip(m.layout.names, _weights(m), o.weights):
+        assert rel_err(a, b) < 2e-5, (name, rel_err(a, b))
+    assert abs(float(losses.double().mean().item()) - o_loss) < 2e-5 * abs(o_loss)
+
+
+def test_finetune_stage_runs_sgd_through_the_pass_kernel(tmp_path):
+    """`*_finetune` names: per-domain plain-SGD passes (specific_base_model.py:99-162) in the tcgen05 mode vs the same
+    stage in the fp32 mode (identical schedule): AUCs within 1e-3."""
+    res = {}
+    for prec in ("tf32x3", "fp32"):
+        c = make_config(tmp_path, **{"model.name": "mlp_meta_mamdr_finetune", "dataset.synthetic.scale": 0.1, "train.epoch": 2,
+                                     "b200.precision": prec})
+        wrapper = _build(c)
+        wrapper.prepare()
+        wrapper.base_model.schedule = Schedule(4)
+        wrapper.train_epoch(0)
+        _, a, _, _ = wrapper.val()
+        wrapper.early_stop_step(a)
+        res[prec] = wrapper.separate_train_val_test(init_parms=False)
+    assert abs(res["tf32x3"][1] - res["fp32"][1]) < 1e-3
+    for k in res["fp32"][3]:
+        assert abs(res["tf32x3"][3][k] - res["fp32"][3][k]) < 2e-3
