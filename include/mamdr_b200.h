@@ -157,6 +157,42 @@ int mamdr_mlp_eval_step(mamdr_ctx* ctx, const mamdr_mlp_desc* desc, const mamdr_
                         float* probs_dev, float* auc_acc_dev, const float* thresholds_dev,
                         int32_t num_thresholds, int32_t precision_mode, mamdr_stream stream);
 
+/* ---- STAR tower (BASELINE config #4; replaces the Keras train / test function of model_zoo/Star/star.py:70-113:
+ * PartitionedNorm -> StarFCN x L -> Dense(1, sigmoid); Star/partitioned_norm.py:102-203, Star/star_fcn.py:105-139).
+ * Arena order = Keras creation order: [domain_emb, gamma_specific [D,n], beta_specific [D,n], gamma_shared [n],
+ * beta_shared [n], (kernel_specific [D,in,out], bias_specific [D,out], kernel_shared [in,out], bias_shared [out]) x L,
+ * out_kernel [h_L,1], out_bias [1]], n = sum(emb_dim); user / item tables frozen, outside the arena.  pn_state_dev
+ * (mamdr_star_state_bytes, non-trainable): moving mean / variance and their zero-debiased accumulators per domain;
+ * initialise moving_var (second [D,n] block) to 1 and everything else to 0.  fp32 only.  The train step overwrites
+ * the WHOLE gradient arena (untouched domain slices are zero) and is followed by mamdr_adam_step over the arena. */
+typedef struct {
+    int32_t n_layers;
+    int32_t emb_dim[3];
+    int32_t hidden[MAMDR_MAX_LAYERS];
+    int32_t n_domain;
+    int64_t n_uid, n_pid;
+    float   pn_eps, pn_momentum;             /* 1e-3, 0.99 (Keras BatchNormalization defaults) */
+    int64_t off_domain_emb, off_gamma_sp, off_beta_sp, off_gamma_sh, off_beta_sh;
+    int64_t off_ksp[MAMDR_MAX_LAYERS], off_bsp[MAMDR_MAX_LAYERS], off_ksh[MAMDR_MAX_LAYERS], off_bsh[MAMDR_MAX_LAYERS];
+    int64_t off_out_kernel, off_out_bias;
+    int64_t arena_floats;
+} mamdr_star_desc;
+
+size_t mamdr_star_workspace_bytes(const mamdr_star_desc* desc, int32_t max_batch);
+size_t mamdr_star_state_bytes(const mamdr_star_desc* desc);
+/* debug hook: workspace byte offsets [X, xhat, dY, H_0..H_L, dZ_0..dZ_{L-1}] for a batch of `rows` */
+int    mamdr_star_debug_offsets(const mamdr_star_desc* desc, int32_t rows, int64_t* out);
+int mamdr_star_train_step(mamdr_ctx* ctx, const mamdr_star_desc* desc, const mamdr_batch* batch,
+                          const float* user_table_dev, const float* item_table_dev, const float* params_dev,
+                          float* grads_dev, void* pn_state_dev, void* ws_dev, size_t ws_bytes, float* loss_dev,
+                          float* probs_dev, float* auc_acc_dev, const float* thresholds_dev,
+                          int32_t num_thresholds, mamdr_stream stream);
+int mamdr_star_eval_step(mamdr_ctx* ctx, const mamdr_star_desc* desc, const mamdr_batch* batch,
+                         const float* user_table_dev, const float* item_table_dev, const float* params_dev,
+                         void* pn_state_dev, void* ws_dev, size_t ws_bytes, float* loss_dev, float* probs_dev,
+                         float* auc_acc_dev, const float* thresholds_dev, int32_t num_thresholds,
+                         mamdr_stream stream);
+
 /* ---- one whole domain pass in ONE persistent cooperative launch (tcgen05 modes, frozen tables) ----
  * mamdr_mlp_train_pass replaces `model.fit(train_iter, steps_per_epoch=S)` (model_zoo/mamdr.py:54) and
  * the `for step in range(train_step): model.train_on_batch(train_iter)` loops (mamdr.py:85-97,

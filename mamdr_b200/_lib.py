@@ -60,6 +60,16 @@ class Batch(C.Structure):
     ]
 
 
+class StarDesc(C.Structure):
+    _fields_ = [("n_layers", C.c_int32), ("emb_dim", C.c_int32 * 3), ("hidden", C.c_int32 * MAX_LAYERS),
+                ("n_domain", C.c_int32), ("n_uid", C.c_int64), ("n_pid", C.c_int64), ("pn_eps", C.c_float),
+                ("pn_momentum", C.c_float), ("off_domain_emb", C.c_int64), ("off_gamma_sp", C.c_int64),
+                ("off_beta_sp", C.c_int64), ("off_gamma_sh", C.c_int64), ("off_beta_sh", C.c_int64),
+                ("off_ksp", C.c_int64 * MAX_LAYERS), ("off_bsp", C.c_int64 * MAX_LAYERS),
+                ("off_ksh", C.c_int64 * MAX_LAYERS), ("off_bsh", C.c_int64 * MAX_LAYERS),
+                ("off_out_kernel", C.c_int64), ("off_out_bias", C.c_int64), ("arena_floats", C.c_int64)]
+
+
 class Pass(C.Structure):
     _fields_ = [
         ("uid_dev", C.c_void_p),
@@ -100,6 +110,13 @@ SIGNATURES = {
                                        _P, _P, _P, _I32, _I32, _F, _F, _F, _F, _I32, _P]),
     "mamdr_mlp_eval_pass": (C.c_int, [_P, C.POINTER(MlpDesc), C.POINTER(Pass), _P, _P, _P, _P, _SZ, _P, _P, _P, _P,
                                       _P, _I32, _I32, _P]),
+    "mamdr_star_workspace_bytes": (_SZ, [C.POINTER(StarDesc), _I32]),
+    "mamdr_star_state_bytes": (_SZ, [C.POINTER(StarDesc)]),
+    "mamdr_star_debug_offsets": (C.c_int, [C.POINTER(StarDesc), _I32, C.POINTER(_I64)]),
+    "mamdr_star_train_step": (C.c_int, [_P, C.POINTER(StarDesc), C.POINTER(Batch), _P, _P, _P, _P, _P, _P, _SZ, _P, _P, _P, _P,
+                                        _I32, _P]),
+    "mamdr_star_eval_step": (C.c_int, [_P, C.POINTER(StarDesc), C.POINTER(Batch), _P, _P, _P, _P, _P, _SZ, _P, _P, _P, _P, _I32,
+                                       _P]),
     "mamdr_program_begin": (C.c_int, [_P]),
     "mamdr_program_end": (C.c_int, [_P, _P, _SZ, C.POINTER(_I32), _P]),
     "mamdr_program_abort": (None, [_P]),

@@ -54,6 +54,11 @@ extern char g_mamdr_create_err[512];
 
 #define MAMDR_LAUNCH_OK(ctx) MAMDR_CUDA_OK(ctx, cudaGetLastError())
 
+// Keras clips p to [1e-7, 1 - 1e-7] before the BCE, which zeroes the gradient of saturated rows.  In exact arithmetic
+// that is |logit| <= ln((1 - 1e-7) / 1e-7); deciding it on the fp32 LOGIT (instead of on p, whose spacing next to 1 is
+// 6e-8, i.e. a 0.7-wide band of logits) makes the indicator robust to the last ulp of expf.  oracle/mlp.py: LOGIT_CLIP.
+#define MAMDR_LOGIT_CLIP 16.118095f
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

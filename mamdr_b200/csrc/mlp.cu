@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(HeadArgs a) {
         const float yv = a.y[r];
         float dsv = 0.f;
         if (a.train) {
-            dsv = (p >= lo && p <= hi) ? __fdiv_rn(__fsub_rn(p, yv), fb) : 0.f;
+            dsv = (fabsf(s) <= MAMDR_LOGIT_CLIP) ? __fdiv_rn(__fsub_rn(p, yv), fb) : 0.f;
 #pragma unroll
             for (int j = 0; j < kHeadMaxN / 32; ++j) {
                 const int c = lane + 32 * j;
@@ -380,6 +380,8 @@ int run_head(mamdr_ctx* ctx, const mamdr_mlp_desc* d, const mamdr_batch* b, cons
 
 
 }  // namespace
+
+#include "star.cuh"
 
 int mamdr_mlp_init_kernels(mamdr_ctx* ctx) {
     MAMDR_CUDA_OK(ctx, cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));

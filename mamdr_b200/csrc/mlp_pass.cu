@@ -747,7 +747,7 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                                 const float lg = logf(ph / (1.0f - ph));
                                 bce = (double)(fmaxf(lg, 0.f) - lg * yv + log1pf(expf(-fabsf(lg))));
                                 if (pd.probs) pd.probs[(long long)step * a.bs + row] = pv;
-                                if (a.train) dsv = (pv >= lo_c && pv <= hi_c) ? __fdiv_rn(__fsub_rn(pv, yv), (float)rows) : 0.f;
+                                if (a.train) dsv = (fabsf(sgm) <= MAMDR_LOGIT_CLIP) ? __fdiv_rn(__fsub_rn(pv, yv), (float)rows) : 0.f;
                                 if (a.auc_acc) {
                                     int lo_i = 0, hi_i = a.T;
                                     while (lo_i < hi_i) {

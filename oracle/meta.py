@@ -124,6 +124,26 @@ class OracleDN(object):
         return self.es.step(metric, keep)
 
 
+class MetaSubset(object):
+    """View of a model whose ``get_weights`` / ``set_weights`` only cover the meta parameters selected by
+    ``MAML._get_model_meta_parms`` (``model_zoo/maml.py:153-179``: name-substring lists such as STAR's
+    ["emb", "kernel_shared", "bias_shared"]); everything else is delegated, so the remaining tensors keep training
+    continuously underneath the DN / DR algebra."""
+
+    def __init__(self, model, index):
+        self._model, self._index = model, list(index)
+
+    def get_weights(self):
+        return [self._model.weights[i].copy() for i in self._index]
+
+    def set_weights(self, values):
+        for i, v in zip(self._index, values):
+            self._model.weights[i][...] = v
+
+    def __getattr__(self, item):
+        return getattr(self._model, item)
+
+
 class OracleMAMDR(object):
     """``MAMDR.train`` (``model_zoo/mamdr.py:18-166``) with ``target_domain=-1``."""
 

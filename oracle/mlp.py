@@ -34,6 +34,9 @@ def mm(a, b):
 
 CLIP_LO = np.float32(1e-7)
 CLIP_HI = np.float32(1.0) - np.float32(1e-7)
+# the clip's zero-gradient region expressed on the logit: |s| > ln((1 - 1e-7) / 1e-7).  Exact-arithmetic equivalent of
+# `CLIP_LO <= p <= CLIP_HI`, but robust in fp32 where p's spacing next to 1 (6e-8) spans a 0.7-wide band of logits.
+LOGIT_CLIP = np.float32(16.118095)
 
 
 class MLPSpec(object):
@@ -161,6 +164,7 @@ class OracleMLP(object):
             H.append(A)
         z = mm(H[L], self.w('dense_kernel'))                   # [b,1]
         s = z[:, 0] + self.w('global_bias')[0]
+        self._last_logit = s
         p = dt(1) / (dt(1) + np.exp(-s))
         return H, p
 
@@ -186,7 +190,7 @@ class OracleMLP(object):
         L = len(sp.hidden)
         inv_keep = (np.float32(1.0) / np.float32(1.0 - sp.dropout)).astype(self.dtype) if sp.dropout > 0 else dt(1)
         ds = (p - y) / dt(b)
-        ds = np.where((p >= dt(CLIP_LO)) & (p <= dt(CLIP_HI)), ds, dt(0)).astype(self.dtype)
+        ds = np.where(np.abs(self._last_logit) <= dt(LOGIT_CLIP), ds, dt(0)).astype(self.dtype)
         g = {}
         g['global_bias'] = np.array([np.sum(ds)], dtype=self.dtype)
         g['dense_kernel'] = mm(H[L].T, ds.reshape(-1, 1))

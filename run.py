@@ -32,7 +32,8 @@ def build(config, dataset=None):
     deep_ctr_list = ['mlp', 'wdl', 'nfm', 'autoint', 'ccpm', 'pnn', 'deepfm']
     mtl_deep_ctr_list = ['shared_bottom', 'mmoe', 'ple']
     if 'star' in name:
-        raise NotImplementedError("base model 'star' (SURVEY.md 8(a) row a20) is not built yet")
+        from mamdr_b200.star import Star
+        model = Star(dataset, config)
     elif in_name_list(name, deep_ctr_list):
         model = DeepCTR(dataset, config)
     elif in_name_list(name, mtl_deep_ctr_list):

@@ -127,8 +127,7 @@ def test_dispatch_rules(monkeypatch):
     from mamdr_b200.dataset import MultiDomainDataset
     c = make_config(**{"dataset.synthetic.scale": 0.002})
     ds = MultiDomainDataset(c["dataset"], device=None)
-    for name, exc in [("star", NotImplementedError), ("mmoe", NotImplementedError), ("nothing", ValueError),
-                      ("wdl", NotImplementedError)]:
+    for name, exc in [("mmoe", NotImplementedError), ("nothing", ValueError), ("wdl", NotImplementedError)]:
         c["model"]["name"] = name
         with pytest.raises(exc):
             run.build(c, dataset=ds)
@@ -144,6 +143,13 @@ def test_dispatch_rules(monkeypatch):
     assert type(run.build(c, dataset=ds)) is MAMDR
     c["model"]["name"] = "mlp"
     assert type(run.build(c, dataset=ds)) is dc.DeepCTR
+    # 'star' is tested first (run.py:40): star_* names build the Star base model, then the same wrappers
+    import mamdr_b200.star as st
+    monkeypatch.setattr(st.Star, "__init__", lambda self, dataset, config: built.append(config['model']['name']))
+    c["model"]["name"] = "star"
+    assert type(run.build(c, dataset=ds)) is st.Star
+    c["model"]["name"] = "star_meta_mamdr_finetune"
+    assert type(run.build(c, dataset=ds)) is MAMDR
     for name in ("mlp_meta_reptile_finetune", "mlp_meta_mldg", "mlp_meta_maml_finetune", "mlp_pcgrad",
                  "mlp_uncertainty_weight"):
         c["model"]["name"] = name
