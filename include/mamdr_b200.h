@@ -149,6 +149,13 @@ int mamdr_mlp_sparse_grads(const mamdr_mlp_desc* desc, int32_t rows, void* ws_de
                            const int32_t** uniq_ids_dev, const float** uniq_rows_dev,
                            const int32_t** n_uniq_dev);
 
+/* Gradient rows of the gathered user / item embeddings of the LAST mamdr_mlp_train_step (`rows` rows):
+ * dX_out[r, 0:du+di] = dZ_0[r, :] . W_0[0:du+di, :]^T.  For tables that live outside the arena -- row-sharded across
+ * GPUs (mamdr_b200/sharded.py): the rows travel back to their owners by NCCL all-to-all, are de-duplicated with
+ * mamdr_scatter_dedup_f32 and applied with mamdr_adam_table_step on the owner's shard. */
+int mamdr_mlp_input_grads(mamdr_ctx* ctx, const mamdr_mlp_desc* desc, int32_t rows, const float* params_dev,
+                          void* ws_dev, size_t ws_bytes, float* dX_out_dev, mamdr_stream stream);
+
 /* ---- inference mini-batch (replaces the Keras test function behind Model.evaluate,
  * model_zoo/specific_base_model.py:82-85, model_zoo/base_model.py:130-133): no dropout. */
 int mamdr_mlp_eval_step(mamdr_ctx* ctx, const mamdr_mlp_desc* desc, const mamdr_batch* batch,

@@ -404,6 +404,26 @@ extern "C" int mamdr_mlp_sparse_grads(const mamdr_mlp_desc* desc, int32_t rows, 
     return MAMDR_OK;
 }
 
+// dX[:, 0:du+di] = dZ_0 . W_0[0:du+di, :]^T from the workspace of the LAST train step of `rows` rows: the gradient rows of
+// the gathered user / item embeddings.  Used when the tables live outside the arena (row-sharded across GPUs).
+extern "C" int mamdr_mlp_input_grads(mamdr_ctx* ctx, const mamdr_mlp_desc* d, int32_t rows, const float* params, void* ws_,
+                                     size_t ws_bytes, float* dX_out, mamdr_stream stream) {
+    MAMDR_REQUIRE(ctx, ctx && d && params && ws_ && dX_out, MAMDR_E_INVALID, "NULL pointer");
+    MAMDR_REQUIRE(ctx, rows >= 1 && aligned16(dX_out) && aligned16(ws_) && aligned16(params), MAMDR_E_INVALID, "bad rows / misaligned pointer");
+    MAMDR_REQUIRE(ctx, ctx->prog == nullptr, MAMDR_E_INVALID, "per-mini-batch calls cannot be recorded into a program");
+    const WsLayout w = ws_layout(*d, rows);
+    MAMDR_REQUIRE(ctx, ws_bytes >= w.total, MAMDR_E_WORKSPACE, "workspace too small");
+    unsigned char* ws = (unsigned char*)ws_;
+    const int dui = d->emb_dim[0] + d->emb_dim[1], n1 = d->hidden[0];
+    StoreEpilogue epi{dX_out, dui};
+    simt::GemmShape s{rows, dui, n1, n1, n1};
+    simt::LaunchPlan p = simt::plan(rows, dui, n1, 0, 1);
+    simt::gemm_kernel<true, false, StoreEpilogue><<<p.grid, simt::THREADS, 0, (cudaStream_t)stream>>>(
+        (const float*)(ws + w.dZ[0]), params + d->off_kernel[0], s, p.k_chunk, nullptr, nullptr, epi);
+    MAMDR_LAUNCH_OK(ctx);
+    return MAMDR_OK;
+}
+
 extern "C" int mamdr_mlp_eval_step(mamdr_ctx* ctx, const mamdr_mlp_desc* d, const mamdr_batch* b,
                                    const float* ut, const float* it, const float* params, void* ws_,
                                    size_t ws_bytes, float* loss, float* probs, float* auc_acc,

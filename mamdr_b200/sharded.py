@@ -1,0 +1,211 @@
+"""Row-sharded trainable embedding tables with NCCL all-to-all (BASELINE config #5's table layout, north_star: "embedding
+tables that exceed a single GPU are row-sharded with NCCL all-to-all"), driving the joint `mlp` baseline of
+``/root/reference/model_zoo/DeepCTR/deepctr.py:63-93`` data-parallel over the mini-batch.
+
+The reference is single-process (``run.py:27-30``) and keeps whole tables in one TF variable; the sharded semantics are
+the mathematically identical data-parallel restatement of one Keras train step on a batch of B rows:
+
+  * table row r lives on rank ``r % G`` at local index ``r // G`` together with its Adam slots (m, v) and slot map;
+  * every rank takes a contiguous slice of the batch (B_r rows) and runs the tower on it (fp32 per-mini-batch kernels);
+  * forward : all-to-all(ids) -> owners gather their rows (``mamdr_gather_f32``) -> all-to-all(rows);
+  * backward: ``mamdr_mlp_input_grads`` -> all-to-all(gradient rows, weighted B_r / B) -> owners de-duplicate
+    (``mamdr_scatter_dedup_f32``) and run the fused l2 + non-lazy Adam sweep over their shard (``mamdr_adam_table_step``);
+  * dense tower gradients: one all-reduce(sum) of the B_r / B weighted arenas, then ``mamdr_adam_step`` on every rank
+    (replicas stay bit-identical: same reduced bits, same update).
+Index bucketing (sort by owner, bincount, inverse permutation) uses torch tensor ops: plumbing around the collectives.
+Dropout masks are indexed by the LOCAL row, so with dropout > 0 the masks are a different (equally distributed) draw than
+the single-GPU schedule; parity against the oracle is asserted with dropout = 0 (tests/test_gpu_sharded.py).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .engine import DomainData, MLPModel, _ptr
+
+
+class _Plan(object):
+    """Routing of one id column: who owns each row, in which order rows are sent, how many go where."""
+
+    def __init__(self, ids, world):
+        self.n = int(ids.numel())
+        owner = (ids % world).to(torch.int64)
+        self.perm = torch.argsort(owner, stable=True)
+        self.send_idx = (ids[self.perm] // world).to(torch.int32).contiguous()
+        send_counts = torch.bincount(owner, minlength=world)
+        recv_counts = torch.empty_like(send_counts)
+        dist.all_to_all_single(recv_counts, send_counts)
+        self.send_splits = send_counts.tolist()     # host sync: the split sizes of the variable-length exchanges
+        self.recv_splits = recv_counts.tolist()
+        self.n_recv = int(sum(self.recv_splits))
+        self.recv_idx = torch.empty(self.n_recv, dtype=torch.int32, device=ids.device)
+        dist.all_to_all_single(self.recv_idx, self.send_idx, self.recv_splits, self.send_splits)
+
+
+class ShardedTable(object):
+    def __init__(self, ctx, full_init, rank, world, device, l2, max_recv):
+        self.ctx, self.rank, self.world, self.l2 = ctx, rank, world, float(l2)
+        local = np.ascontiguousarray(full_init[rank::world], dtype=np.float32)
+        self.rows, self.dim = int(local.shape[0]), int(local.shape[1])
+        self.table = torch.from_numpy(local).to(device)
+        self.m, self.v = torch.zeros_like(self.table), torch.zeros_like(self.table)
+        self.slot = torch.full((max(self.rows, 1),), -1, dtype=torch.int32, device=device)
+        self.ws_bytes = ctx.lib.mamdr_adam_table_workspace_bytes()
+        self.ws = torch.zeros(self.ws_bytes, dtype=torch.uint8, device=device)
+        self.sc_bytes = ctx.lib.mamdr_scatter_workspace_bytes(max_recv)
+        self.sc_ws = torch.zeros(max(self.sc_bytes, 16), dtype=torch.uint8, device=device)
+        self.uniq_ids = torch.zeros(max_recv, dtype=torch.int32, device=device)
+        self.uniq_rows = torch.zeros(max_recv, self.dim, dtype=torch.float32, device=device)
+        self.n_uniq = torch.zeros(4, dtype=torch.int32, device=device)
+        self.max_recv = int(max_recv)
+
+    def fetch(self, plan, stream):
+        """Rows of the ids behind ``plan`` in their original order: all-to-all(ids) was done by the plan."""
+        got = torch.empty(plan.n_recv, self.dim, dtype=torch.float32, device=self.table.device)
+        if plan.n_recv:
+            self.ctx.call("mamdr_gather_f32", _ptr(self.table), self.rows, self.dim, _ptr(plan.recv_idx), plan.n_recv, _ptr(got),
+                          self.dim, stream)
+            self.ctx.launches += 1
+        back = torch.empty(plan.n, self.dim, dtype=torch.float32, device=self.table.device)
+        dist.all_to_all_single(back, got, [s for s in plan.send_splits], [s for s in plan.recv_splits])
+        out = torch.empty_like(back)
+        out[plan.perm] = back
+        return out
+
+    def apply(self, plan, grad_rows, opt_state, lr, beta1, beta2, eps, loss_slot, stream):
+        """Send the gradient rows to their owners, de-duplicate, fused l2 + Adam over the local shard."""
+        send = grad_rows[plan.perm].contiguous()
+        recv = torch.empty(plan.n_recv, self.dim, dtype=torch.float32, device=self.table.device)
+        dist.all_to_all_single(recv, send, [s for s in plan.recv_splits], [s for s in plan.send_splits])
+        if plan.n_recv > self.max_recv:
+            raise ValueError("more gradient rows received (%d) than the shard was sized for (%d)" % (plan.n_recv, self.max_recv))
+        if plan.n_recv:
+            self.ctx.call("mamdr_scatter_dedup_f32", _ptr(plan.recv_idx), _ptr(recv), self.dim, plan.n_recv, self.dim,
+                          _ptr(self.uniq_ids), _ptr(self.uniq_rows), _ptr(self.n_uniq), _ptr(self.sc_ws), self.sc_ws.numel(), stream)
+            self.ctx.launches += 2
+        if self.rows:
+            self.ctx.call("mamdr_adam_table_step", _ptr(self.table), _ptr(self.m), _ptr(self.v), self.rows, self.dim,
+                          _ptr(self.uniq_ids), _ptr(self.uniq_rows), _ptr(self.n_uniq), plan.n_recv, _ptr(self.slot), self.l2,
+                          _ptr(opt_state), lr, beta1, beta2, eps, _ptr(loss_slot), _ptr(self.ws), self.ws_bytes, stream)
+            self.ctx.launches += 2
+
+    def full(self):
+        """All-gather of the shard into the full table (tests / checkpoints)."""
+        world = self.world
+        sizes = [torch.zeros(1, dtype=torch.int64, device=self.table.device) for _ in range(world)]
+        dist.all_gather(sizes, torch.tensor([self.rows], dtype=torch.int64, device=self.table.device))
+        parts = [torch.empty(int(s.item()), self.dim, dtype=torch.float32, device=self.table.device) for s in sizes]
+        dist.all_gather(parts, self.table) if len(set(int(s.item()) for s in sizes)) == 1 else _uneven_gather(parts, self.table, sizes)
+        n = sum(p.shape[0] for p in parts)
+        out = torch.empty(n, self.dim, dtype=torch.float32, device=self.table.device)
+        for r, p in enumerate(parts):
+            out[r::world] = p
+        return out
+
+
+def _uneven_gather(parts, mine, sizes):
+    mx = max(int(s.item()) for s in sizes)
+    pad = torch.zeros(mx, mine.shape[1], dtype=mine.dtype, device=mine.device)
+    pad[:mine.shape[0]] = mine
+    bufs = [torch.empty_like(pad) for _ in parts]
+    dist.all_gather(bufs, pad)
+    for p, b in zip(parts, bufs):
+        p.copy_(b[:p.shape[0]])
+
+
+class ShardedJointTrainer(object):
+    """Joint `mlp` training (``DeepCTR.train``) with row-sharded trainable tables; one instance per rank."""
+
+    def __init__(self, n_uid, n_pid, n_domain, user_init, item_init, dense_init, emb_dim=(128, 128, 128), hidden=(256, 128, 64),
+                 dropout=0.0, lr=1e-3, l2_emb=1e-5, batch_size=1024, device="cuda:0"):
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.device = torch.device(device)
+        self.batch_size = int(batch_size)
+        bl = (self.batch_size + self.world - 1) // self.world
+        self.max_local = bl
+        # the tower runs in frozen-table mode on the rows received for this rank's slice of the batch
+        z_u = np.zeros((bl, emb_dim[0]), dtype=np.float32)
+        z_i = np.zeros((bl, emb_dim[1]), dtype=np.float32)
+        self.model = MLPModel(bl, bl, n_domain, emb_dim=emb_dim, hidden=hidden, dropout=dropout, l2_emb=l2_emb, emb_trainable=False,
+                              user_table=z_u, item_table=z_i, init_weights=dense_init, lr=lr, max_batch=bl, precision=_lib.PREC_FP32,
+                              device=device, use_graphs=False)
+        m = self.model
+        m.desc.frozen_reg = 0.0
+        ctx = m.ctx
+        self.users = ShardedTable(ctx, user_init, self.rank, self.world, self.device, l2_emb, self.batch_size)
+        self.items = ShardedTable(ctx, item_init, self.rank, self.world, self.device, l2_emb, self.batch_size)
+        self.arange = torch.arange(bl, dtype=torch.int32, device=self.device)
+        self.dX = torch.zeros(bl, emb_dim[0] + emb_dim[1], dtype=torch.float32, device=self.device)
+        self.loss_local = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.loss_tab = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.comm_bytes = 0
+
+    def _slice(self, n):
+        """Contiguous split of a batch of n rows over the ranks (numpy.array_split sizes)."""
+        base, rem = divmod(n, self.world)
+        sizes = [base + (1 if r < rem else 0) for r in range(self.world)]
+        start = sum(sizes[:self.rank])
+        return start, sizes[self.rank]
+
+    def _local_data(self, y, domain, rows):
+        d = DomainData.__new__(DomainData)
+        d.domain, d.n_data, d.batch_size, d.n_step = int(domain), int(rows), self.max_local, 1
+        d.uid, d.pid, d.label, d.order, d.device = self.arange, self.arange, y, self.arange, self.device
+        return d
+
+    def train_on_batch(self, uid, pid, label, domain):
+        """One Keras train step on the GLOBAL batch (device int32 / fp32 columns, identical on every rank)."""
+        m = self.model
+        st = m.stream
+        n = int(uid.numel())
+        start, bl = self._slice(n)
+        u, p, y = uid[start:start + bl].contiguous(), pid[start:start + bl].contiguous(), label[start:start + bl].contiguous()
+        plan_u, plan_i = _Plan(u, self.world), _Plan(p, self.world)
+        rows_u, rows_i = self.users.fetch(plan_u, st), self.items.fetch(plan_i, st)
+        w = float(bl) / float(n)                         # this rank's share of the batch mean
+        self.loss_local.zero_()
+        self.loss_tab.zero_()
+        if bl:
+            m.user_table, m.item_table = rows_u, rows_i
+            data = self._local_data(y, domain, bl)
+            b = m._batch(data, 0, bl, False)
+            m.ctx.call("mamdr_mlp_train_step", C.byref(m.desc), C.byref(b), _ptr(rows_u), _ptr(rows_i), _ptr(m.params), _ptr(m.grads),
+                       _ptr(m.ws), m.ws_bytes, _ptr(m.opt_state), _ptr(self.loss_local), None, _ptr(m.auc_acc), _ptr(m.thresholds),
+                       m.num_thresholds, m.precision, st)
+            m.ctx.call("mamdr_mlp_input_grads", C.byref(m.desc), bl, _ptr(m.params), _ptr(m.ws), m.ws_bytes, _ptr(self.dX), st)
+            m.ctx.launches += 14
+            m.grads.mul_(w)
+            self.loss_local.mul_(w)
+            du = self.users.dim
+            gu, gi = (self.dX[:bl, :du] * w).contiguous(), (self.dX[:bl, du:] * w).contiguous()
+        else:
+            m.grads.zero_()
+            gu = torch.zeros(0, self.users.dim, dtype=torch.float32, device=self.device)
+            gi = torch.zeros(0, self.items.dim, dtype=torch.float32, device=self.device)
+        # tables first (they read the beta powers), then the dense arena (its apply advances them)
+        self.users.apply(plan_u, gu, m.opt_state, m.lr, m.beta1, m.beta2, m.eps, self.loss_tab, st)
+        self.items.apply(plan_i, gi, m.opt_state, m.lr, m.beta1, m.beta2, m.eps, self.loss_tab, st)
+        dist.all_reduce(m.grads)
+        m.ctx.call("mamdr_adam_step", _ptr(m.params), _ptr(m.m), _ptr(m.v), _ptr(m.grads), m.params.numel(), _ptr(m.opt_state), m.lr,
+                   m.beta1, m.beta2, m.eps, st)
+        m.ctx.launches += 1
+        self.comm_bytes += 4 * m.grads.numel() + 2 * 4 * (plan_u.n + plan_i.n) * (1 + self.users.dim)
+        both = torch.cat([self.loss_local, self.loss_tab])
+        dist.all_reduce(both)
+        return both   # [mean BCE + l2 |E_d|^2, l2 (|E_u|^2 + |E_i|^2)]; their sum is the Keras loss
+
+    def train_pass(self, host_split, domain, order, dev_cols=None):
+        """One pass over a domain's training split in the given sample order (numpy), batch by batch."""
+        uid = torch.from_numpy(np.ascontiguousarray(host_split['uid'][order], dtype=np.int32)).to(self.device)
+        pid = torch.from_numpy(np.ascontiguousarray(host_split['pid'][order], dtype=np.int32)).to(self.device)
+        lab = torch.from_numpy(np.ascontiguousarray(host_split['label'][order], dtype=np.float32)).to(self.device)
+        losses = []
+        for s in range(0, len(order), self.batch_size):
+            e = min(len(order), s + self.batch_size)
+            losses.append(self.train_on_batch(uid[s:e], pid[s:e], lab[s:e], domain))
+        return losses
+
+    def dense_weights(self):
+        return self.model.layout.unpack(self.model.params.cpu().numpy())
