@@ -25,7 +25,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOAD_CONFIG = {"Taobao-10": "config/Taobao-10/deepctr_DN+DR.json", "Taobao-20": "config/Taobao_20/deepctr_DN+DR.json",
-                   "Taobao-30": "config/Taobao_30/deepctr_DN+DR.json", "Amazon-6": "config/Amazon_6/deepctr.json"}
+                   "Taobao-30": "config/Taobao_30/deepctr_DN+DR.json", "Amazon-6": "config/Amazon_6/deepctr.json",
+                   "Amazon-13-sharded": "config/Amazon_6/deepctr.json"}
 METRIC = "MAMDR meta-train samples/sec (Taobao-10 shape)"
 
 
@@ -315,6 +316,68 @@ def run_amazon(args):
     print(json.dumps(line), flush=True)
 
 
+def run_sharded(args):
+    """BASELINE config #5's table layout (secondary workload): trainable 128-d tables of the synthetic Amazon-13 shape
+    (502 222 + 215 403 rows) row-sharded over the ranks, joint `mlp` steps data-parallel over a 1024-row batch, NCCL
+    all-to-all for ids / rows / gradient rows + one all-reduce of the dense gradients per step (mamdr_b200/sharded.py)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from mamdr_b200 import synth
+    from mamdr_b200.layout import init_mlp_weights, mlp_layout
+    from mamdr_b200.sharded import ShardedJointTrainer
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29577")
+        os.environ.setdefault("RANK", "0")
+        os.environ.setdefault("WORLD_SIZE", "1")
+        dist.init_process_group("nccl")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    n_uid, n_pid, D = 502222, 215403, 13
+    lo = mlp_layout(n_uid, n_pid, D, (128, 128, 128), (256, 128, 64), True)
+    rng = np.random.Generator(np.random.PCG64(7))
+    user0 = (rng.standard_normal((n_uid, 128)) * 1e-4).astype(np.float32)
+    item0 = (rng.standard_normal((n_pid, 128)) * 1e-4).astype(np.float32)
+    lo_d = mlp_layout(n_uid, n_pid, D, (128, 128, 128), (256, 128, 64), False)
+    dense0 = init_mlp_weights(lo_d, [7, 0])
+    t = ShardedJointTrainer(n_uid, n_pid, D, user0, item0, dense0, dropout=0.5, batch_size=1024, device="cuda:%d" % local_rank)
+    g = torch.Generator(device="cuda").manual_seed(11)     # same Zipf-ish id stream on every rank
+    mb = 30
+    uid = (torch.rand(mb, 1024, device="cuda", generator=g) ** 3 * n_uid).to(torch.int32).clamp_(0, n_uid - 1)
+    pid = (torch.rand(mb, 1024, device="cuda", generator=g) ** 3 * n_pid).to(torch.int32).clamp_(0, n_pid - 1)
+    lab = (torch.rand(mb, 1024, device="cuda", generator=g) < 0.3).float()
+
+    def step():
+        for k in range(mb):
+            t.train_on_batch(uid[k], pid[k], lab[k], k % D)
+    for _ in range(max(args.warmup, 1)):
+        step()
+    dist.barrier()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+        step()
+    b.record()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([a.elapsed_time(b) / args.steps], dtype=torch.float64, device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        msv = float(ms.item())
+        alg = 24.0 * (n_uid + n_pid) * 128
+        print(json.dumps({"metric": "joint-train samples/sec (Amazon-13 shape, row-sharded trainable tables)", "value": mb * 1024 / (msv * 1e-3),
+                          "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": msv,
+                          "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": "mlp joint steps, trainable tables row-sharded over %d rank(s), NCCL all-to-all, %d mini-batches of 1024 per step" % (world, mb)},
+                          "roofline": {"bound": "hbm", "achieved": alg * mb / (msv * 1e-3) / 1e9, "unit": "GB/s",
+                                       "note": "aggregate table-sweep bytes (24 B per table element per mini-batch) over all ranks / step time"},
+                          "us_per_minibatch": 1e3 * msv / mb}), flush=True)
+    dist.destroy_process_group()
+
+
 def run_b200(args):
     import numpy as np
     import torch
@@ -518,6 +581,8 @@ def main():
         run_reference(args)
     elif args.workload == "Amazon-6":
         run_amazon(args)
+    elif args.workload == "Amazon-13-sharded":
+        run_sharded(args)
     else:
         run_b200(args)
         import torch.distributed as dist
