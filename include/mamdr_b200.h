@@ -200,6 +200,66 @@ int mamdr_star_eval_step(mamdr_ctx* ctx, const mamdr_star_desc* desc, const mamd
                          float* auc_acc_dev, const float* thresholds_dev, int32_t num_thresholds,
                          mamdr_stream stream);
 
+/* ---- multi-task towers (BASELINE config #5; replace the Keras train / test function of the per-domain sub-models
+ * `Model(inputs, outputs[t])` that model_zoo/DeepMTLCTR/deep_mtl_ctr.py:57-65 compiles over deepctr's MMOE / PLE
+ * (num_levels = 1) / SharedBottom (:25-48), all sharing one AdamOptimizer (:53)).  fp32.
+ *   X -> the k experts domain t mixes (each DNN(expert_hidden)) ; gate t: DNN(gate_hidden)(X) . G_t -> softmax [k] ;
+ *   mix = sum_j a_j * expert_j ; tower t: DNN(tower_hidden)(mix) . w_t + g_t -> sigmoid ; BCE (+ embedding l2).
+ * mamdr_mtl_desc holds the dimensions; mamdr_mtl_domain the arena offsets of ONE domain's sub-model (its experts in
+ * gate-column order, gate, tower) -- the host builds one per domain.  has_gate = 0 (SharedBottom): k = 1, no gate.
+ * The train step writes the gradients of the sub-model's dense variables into grads_dev (positions of variables that
+ * output t does not reach are left untouched; the optimizer never reads them) and, with emb_trainable, leaves the
+ * de-duplicated sparse user / item gradients in the workspace (mamdr_mtl_sparse_grads).  Follow it with
+ * mamdr_adam_table_step per table (trainable tables) and ONE mamdr_adam_ranges_step over the sub-model's arena
+ * ranges: TF applies Adam to the variables of sub-model t only -- all other variables keep their value and slots --
+ * while the optimizer's beta powers advance once per step.
+ * Dropout streams (philox.cuh): seed = dropout_seed + 8*e + l (expert e), + 4096 + 8*t + l (gate t),
+ * + 8192 + 8*t + l (tower t). */
+#define MAMDR_MTL_MAX_K 8
+typedef struct {
+    int32_t emb_dim[3];
+    int32_t n_domain;
+    int64_t n_uid, n_pid;
+    int32_t emb_trainable;
+    int32_t has_gate;
+    int32_t k;                               /* experts mixed per domain, 1..MAMDR_MTL_MAX_K */
+    int32_t n_expert_layers, n_gate_layers, n_tower_layers;        /* each 1..MAMDR_MAX_LAYERS (gate: if has_gate) */
+    int32_t expert_hidden[MAMDR_MAX_LAYERS], gate_hidden[MAMDR_MAX_LAYERS], tower_hidden[MAMDR_MAX_LAYERS];
+    float   dropout_rate;
+    uint32_t dropout_seed;
+    float   l2_emb, frozen_reg;
+    int64_t off_user_emb, off_item_emb, off_domain_emb;
+    int64_t arena_floats;
+} mamdr_mtl_desc;
+
+typedef struct {
+    int32_t domain;
+    int32_t expert_id[MAMDR_MTL_MAX_K];                            /* global expert index (dropout stream) */
+    int64_t off_expert_kernel[MAMDR_MTL_MAX_K][MAMDR_MAX_LAYERS], off_expert_bias[MAMDR_MTL_MAX_K][MAMDR_MAX_LAYERS];
+    int64_t off_gate_kernel[MAMDR_MAX_LAYERS], off_gate_bias[MAMDR_MAX_LAYERS], off_gate_out;   /* gate_out [g_last, k] */
+    int64_t off_tower_kernel[MAMDR_MAX_LAYERS], off_tower_bias[MAMDR_MAX_LAYERS], off_tower_out, off_bias;
+} mamdr_mtl_domain;
+
+size_t mamdr_mtl_workspace_bytes(const mamdr_mtl_desc* desc, int32_t max_batch);
+int mamdr_mtl_train_step(mamdr_ctx* ctx, const mamdr_mtl_desc* desc, const mamdr_mtl_domain* dom,
+                         const mamdr_batch* batch, const float* user_table_dev, const float* item_table_dev,
+                         const float* params_dev, float* grads_dev, void* ws_dev, size_t ws_bytes,
+                         const void* opt_state_dev, float* loss_dev, float* probs_dev, float* auc_acc_dev,
+                         const float* thresholds_dev, int32_t num_thresholds, mamdr_stream stream);
+int mamdr_mtl_eval_step(mamdr_ctx* ctx, const mamdr_mtl_desc* desc, const mamdr_mtl_domain* dom,
+                        const mamdr_batch* batch, const float* user_table_dev, const float* item_table_dev,
+                        const float* params_dev, void* ws_dev, size_t ws_bytes, float* loss_dev, float* probs_dev,
+                        float* auc_acc_dev, const float* thresholds_dev, int32_t num_thresholds,
+                        mamdr_stream stream);
+/* views of the de-duplicated sparse gradients left by the last train step of `rows` rows (table 0 = user, 1 = item) */
+int mamdr_mtl_sparse_grads(const mamdr_mtl_desc* desc, int32_t rows, void* ws_dev, int32_t table,
+                           const int32_t** uniq_ids_dev, const float** uniq_rows_dev, const int32_t** n_uniq_dev);
+/* TF ApplyAdam over n_ranges (<= 16) arena ranges [begin, begin + len) (floats, multiples of 4) of one arena; the beta
+ * powers / step advance once.  begin / len are HOST arrays. */
+int mamdr_adam_ranges_step(mamdr_ctx* ctx, float* params_dev, float* m_dev, float* v_dev, const float* grads_dev,
+                           const int64_t* begin, const int64_t* len, int32_t n_ranges, void* opt_state_dev,
+                           float lr, float beta1, float beta2, float eps, mamdr_stream stream);
+
 /* ---- one whole domain pass in ONE persistent cooperative launch (tcgen05 modes, frozen tables) ----
  * mamdr_mlp_train_pass replaces `model.fit(train_iter, steps_per_epoch=S)` (model_zoo/mamdr.py:54) and
  * the `for step in range(train_step): model.train_on_batch(train_iter)` loops (mamdr.py:85-97,

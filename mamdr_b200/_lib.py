@@ -70,6 +70,28 @@ class StarDesc(C.Structure):
                 ("off_out_kernel", C.c_int64), ("off_out_bias", C.c_int64), ("arena_floats", C.c_int64)]
 
 
+MTL_MAX_K = 8
+
+
+class MtlDesc(C.Structure):
+    _fields_ = [("emb_dim", C.c_int32 * 3), ("n_domain", C.c_int32), ("n_uid", C.c_int64), ("n_pid", C.c_int64),
+                ("emb_trainable", C.c_int32), ("has_gate", C.c_int32), ("k", C.c_int32),
+                ("n_expert_layers", C.c_int32), ("n_gate_layers", C.c_int32), ("n_tower_layers", C.c_int32),
+                ("expert_hidden", C.c_int32 * MAX_LAYERS), ("gate_hidden", C.c_int32 * MAX_LAYERS),
+                ("tower_hidden", C.c_int32 * MAX_LAYERS), ("dropout_rate", C.c_float), ("dropout_seed", C.c_uint32),
+                ("l2_emb", C.c_float), ("frozen_reg", C.c_float), ("off_user_emb", C.c_int64),
+                ("off_item_emb", C.c_int64), ("off_domain_emb", C.c_int64), ("arena_floats", C.c_int64)]
+
+
+class MtlDomain(C.Structure):
+    _fields_ = [("domain", C.c_int32), ("expert_id", C.c_int32 * MTL_MAX_K),
+                ("off_expert_kernel", (C.c_int64 * MAX_LAYERS) * MTL_MAX_K),
+                ("off_expert_bias", (C.c_int64 * MAX_LAYERS) * MTL_MAX_K),
+                ("off_gate_kernel", C.c_int64 * MAX_LAYERS), ("off_gate_bias", C.c_int64 * MAX_LAYERS),
+                ("off_gate_out", C.c_int64), ("off_tower_kernel", C.c_int64 * MAX_LAYERS),
+                ("off_tower_bias", C.c_int64 * MAX_LAYERS), ("off_tower_out", C.c_int64), ("off_bias", C.c_int64)]
+
+
 class Pass(C.Structure):
     _fields_ = [
         ("uid_dev", C.c_void_p),
@@ -117,6 +139,13 @@ SIGNATURES = {
                                         _I32, _P]),
     "mamdr_star_eval_step": (C.c_int, [_P, C.POINTER(StarDesc), C.POINTER(Batch), _P, _P, _P, _P, _P, _SZ, _P, _P, _P, _P, _I32,
                                        _P]),
+    "mamdr_mtl_workspace_bytes": (_SZ, [C.POINTER(MtlDesc), _I32]),
+    "mamdr_mtl_train_step": (C.c_int, [_P, C.POINTER(MtlDesc), C.POINTER(MtlDomain), C.POINTER(Batch), _P, _P, _P, _P, _P, _SZ,
+                                       _P, _P, _P, _P, _P, _I32, _P]),
+    "mamdr_mtl_eval_step": (C.c_int, [_P, C.POINTER(MtlDesc), C.POINTER(MtlDomain), C.POINTER(Batch), _P, _P, _P, _P, _SZ, _P,
+                                      _P, _P, _P, _I32, _P]),
+    "mamdr_mtl_sparse_grads": (C.c_int, [C.POINTER(MtlDesc), _I32, _P, _I32, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
+    "mamdr_adam_ranges_step": (C.c_int, [_P, _P, _P, _P, _P, C.POINTER(_I64), C.POINTER(_I64), _I32, _P, _F, _F, _F, _F, _P]),
     "mamdr_program_begin": (C.c_int, [_P]),
     "mamdr_program_end": (C.c_int, [_P, _P, _SZ, C.POINTER(_I32), _P]),
     "mamdr_program_abort": (None, [_P]),

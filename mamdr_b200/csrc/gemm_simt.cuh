@@ -22,10 +22,12 @@ struct GemmShape {
     int lda, ldb;  // leading dimensions (floats) of A and B in their stored orientation
 };
 
+// One CTA's tile; (zi, zn) = this CTA's split-K slice and the number of slices.
 template <bool A_KCONTIG, bool B_NCONTIG, class Epilogue>
-__global__ void __launch_bounds__(THREADS)
-gemm_kernel(const float* __restrict__ A, const float* __restrict__ B, GemmShape s, int k_chunk,
-            float* __restrict__ partials, unsigned int* __restrict__ tickets, Epilogue epi) {
+__device__ __forceinline__ void
+gemm_tile(const float* __restrict__ A, const float* __restrict__ B, const GemmShape& s, int k_chunk,
+          float* __restrict__ partials, unsigned int* __restrict__ tickets, const Epilogue& epi, const unsigned int zi,
+          const unsigned int zn) {
     __shared__ __align__(16) float As[BK][BM + APAD];
     __shared__ __align__(16) float Bs[BK][BN];
     __shared__ bool is_last;
@@ -33,7 +35,7 @@ gemm_kernel(const float* __restrict__ A, const float* __restrict__ B, GemmShape 
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    const int kbeg = blockIdx.z * k_chunk;
+    const int kbeg = (int)zi * k_chunk;
     const int kend = min(s.K, kbeg + k_chunk);
 
     float acc[4][4];
@@ -109,11 +111,11 @@ gemm_kernel(const float* __restrict__ A, const float* __restrict__ B, GemmShape 
     }
 
     const int gn = n0 + tx * 4;
-    if (gridDim.z > 1) {
+    if (zn > 1) {
         // park the partial tile: layout [z][tile][BM][BN]
         const int tile = blockIdx.y * gridDim.x + blockIdx.x;
         const int64_t tile_elems = (int64_t)BM * BN;
-        float* mine = partials + ((int64_t)blockIdx.z * gridDim.x * gridDim.y + tile) * tile_elems;
+        float* mine = partials + ((int64_t)zi * gridDim.x * gridDim.y + tile) * tile_elems;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
             *reinterpret_cast<float4*>(mine + (ty * 4 + i) * BN + tx * 4) =
@@ -122,7 +124,7 @@ gemm_kernel(const float* __restrict__ A, const float* __restrict__ B, GemmShape 
         __syncthreads();
         if (tid == 0) {
             const unsigned int t = atomicAdd(&tickets[tile], 1u);
-            is_last = (t == gridDim.z - 1);
+            is_last = (t == zn - 1);
         }
         __syncthreads();
         if (!is_last) return;
@@ -131,7 +133,7 @@ gemm_kernel(const float* __restrict__ A, const float* __restrict__ B, GemmShape 
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-        for (unsigned int z = 0; z < gridDim.z; ++z) {
+        for (unsigned int z = 0; z < zn; ++z) {
             const float* src = partials + ((int64_t)z * gridDim.x * gridDim.y + tile) * tile_elems;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -148,6 +150,35 @@ gemm_kernel(const float* __restrict__ A, const float* __restrict__ B, GemmShape 
             if (gm < s.M) epi(gm, gn, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
         }
     }
+}
+
+template <bool A_KCONTIG, bool B_NCONTIG, class Epilogue>
+__global__ void __launch_bounds__(THREADS)
+gemm_kernel(const float* __restrict__ A, const float* __restrict__ B, GemmShape s, int k_chunk,
+            float* __restrict__ partials, unsigned int* __restrict__ tickets, Epilogue epi) {
+    gemm_tile<A_KCONTIG, B_NCONTIG, Epilogue>(A, B, s, k_chunk, partials, tickets, epi, blockIdx.z, gridDim.z);
+}
+
+// Grouped variant: up to MAX_GROUPS independent GEMMs of ONE shape in a single launch (the experts of a multi-task
+// tower).  gridDim.z = n_groups * split; group g owns ticket / partial slices of its own.
+constexpr int MAX_GROUPS = 8;
+template <class Epilogue>
+struct GroupedArgs {
+    const float* A[MAX_GROUPS];
+    const float* B[MAX_GROUPS];
+    Epilogue     epi[MAX_GROUPS];
+    int          split;           // split-K slices per group
+    int64_t      partial_stride;  // floats between the partial regions of consecutive groups
+    int          ticket_stride;   // tiles per group
+};
+
+template <bool A_KCONTIG, bool B_NCONTIG, class Epilogue>
+__global__ void __launch_bounds__(THREADS)
+gemm_grouped_kernel(const __grid_constant__ GroupedArgs<Epilogue> a, GemmShape s, int k_chunk, float* __restrict__ partials,
+                    unsigned int* __restrict__ tickets) {
+    const unsigned int g = blockIdx.z / a.split, z = blockIdx.z % a.split;
+    gemm_tile<A_KCONTIG, B_NCONTIG, Epilogue>(a.A[g], a.B[g], s, k_chunk, partials + g * a.partial_stride,
+                                              tickets + g * a.ticket_stride, a.epi[g], z, (unsigned int)a.split);
 }
 
 struct LaunchPlan {

@@ -382,6 +382,7 @@ int run_head(mamdr_ctx* ctx, const mamdr_mlp_desc* d, const mamdr_batch* b, cons
 }  // namespace
 
 #include "star.cuh"
+#include "mtl.cuh"
 
 int mamdr_mlp_init_kernels(mamdr_ctx* ctx) {
     MAMDR_CUDA_OK(ctx, cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));

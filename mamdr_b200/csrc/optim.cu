@@ -81,6 +81,41 @@ adam_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
     finish_step(st, beta1, beta2, true);
 }
 
+// ApplyAdam over a handful of arena ranges (the variables of ONE sub-model of a multi-task tower): everything outside
+// the ranges keeps its value and its slots; the beta powers advance once.
+constexpr int kMaxRanges = 16;
+struct RangeArgs {
+    int64_t begin4[kMaxRanges];   // first float4 of range q
+    int64_t cum4[kMaxRanges + 1]; // float4s before range q
+    int     n;
+};
+
+__global__ void __launch_bounds__(kThreads)
+adam_ranges_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ g,
+                   const __grid_constant__ RangeArgs r, OptState* st, float lr, float beta1, float beta2, float eps) {
+    const float b1p = st->b1pow, b2p = st->b2pow;
+    const float alpha = __fdiv_rn(__fmul_rn(lr, __fsqrt_rn(__fsub_rn(1.0f, b2p))), __fsub_rn(1.0f, b1p));
+    const float omb1 = __fsub_rn(1.0f, beta1), omb2 = __fsub_rn(1.0f, beta2);
+    const int64_t nv = r.cum4[r.n];
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    for (int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x; t < nv; t += stride) {
+        int q = 0;
+        while (q + 1 < r.n && t >= r.cum4[q + 1]) ++q;
+        const int64_t i = r.begin4[q] + (t - r.cum4[q]);
+        float4 P = *reinterpret_cast<float4*>(p + 4 * i), M = *reinterpret_cast<float4*>(m + 4 * i);
+        float4 V = *reinterpret_cast<float4*>(v + 4 * i);
+        const float4 G = *reinterpret_cast<const float4*>(g + 4 * i);
+        adam1(P.x, M.x, V.x, G.x, alpha, omb1, omb2, eps);
+        adam1(P.y, M.y, V.y, G.y, alpha, omb1, omb2, eps);
+        adam1(P.z, M.z, V.z, G.z, alpha, omb1, omb2, eps);
+        adam1(P.w, M.w, V.w, G.w, alpha, omb1, omb2, eps);
+        *reinterpret_cast<float4*>(p + 4 * i) = P;
+        *reinterpret_cast<float4*>(m + 4 * i) = M;
+        *reinterpret_cast<float4*>(v + 4 * i) = V;
+    }
+    finish_step(st, beta1, beta2, true);
+}
+
 __global__ void __launch_bounds__(kThreads)
 sgd_kernel(float* __restrict__ p, const float* __restrict__ g, int64_t n, OptState* st, float lr) {
     const int64_t nv = n >> 2;
@@ -166,6 +201,29 @@ extern "C" int mamdr_adam_step(mamdr_ctx* ctx, float* p, float* m, float* v, con
     MAMDR_REQUIRE(ctx, aligned16(p) && aligned16(m) && aligned16(v) && aligned16(g), MAMDR_E_INVALID, "misaligned arena");
     adam_kernel<<<sweep_grid(ctx, n >> 2), kThreads, 0, (cudaStream_t)stream>>>(p, m, v, g, n, (OptState*)state, lr,
                                                                                beta1, beta2, eps);
+    MAMDR_LAUNCH_OK(ctx);
+    return MAMDR_OK;
+}
+
+extern "C" int mamdr_adam_ranges_step(mamdr_ctx* ctx, float* p, float* m, float* v, const float* g, const int64_t* begin,
+                                      const int64_t* len, int32_t n_ranges, void* state, float lr, float beta1, float beta2,
+                                      float eps, mamdr_stream stream) {
+    MAMDR_REQUIRE(ctx, ctx != nullptr, MAMDR_E_INVALID, "ctx is NULL");
+    MAMDR_REQUIRE(ctx, p && m && v && g && state && begin && len, MAMDR_E_INVALID, "NULL pointer");
+    MAMDR_REQUIRE(ctx, !mamdr_prog_recording(ctx), MAMDR_E_INVALID, "mamdr_adam_ranges_step cannot be recorded into a program");
+    MAMDR_REQUIRE(ctx, n_ranges >= 1 && n_ranges <= kMaxRanges, MAMDR_E_INVALID, "n_ranges must be in 1..%d", kMaxRanges);
+    MAMDR_REQUIRE(ctx, aligned16(p) && aligned16(m) && aligned16(v) && aligned16(g), MAMDR_E_INVALID, "misaligned arena");
+    RangeArgs r;
+    memset(&r, 0, sizeof(r));
+    r.n = n_ranges;
+    for (int q = 0; q < n_ranges; ++q) {
+        MAMDR_REQUIRE(ctx, begin[q] >= 0 && len[q] > 0 && begin[q] % 4 == 0 && len[q] % 4 == 0, MAMDR_E_INVALID,
+                      "range %d: begin / len must be non-negative multiples of 4", q);
+        r.begin4[q] = begin[q] >> 2;
+        r.cum4[q + 1] = r.cum4[q] + (len[q] >> 2);
+    }
+    adam_ranges_kernel<<<sweep_grid(ctx, r.cum4[n_ranges]), kThreads, 0, (cudaStream_t)stream>>>(p, m, v, g, r, (OptState*)state, lr, beta1,
+                                                                                                beta2, eps);
     MAMDR_LAUNCH_OK(ctx);
     return MAMDR_OK;
 }

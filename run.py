@@ -37,7 +37,8 @@ def build(config, dataset=None):
     elif in_name_list(name, deep_ctr_list):
         model = DeepCTR(dataset, config)
     elif in_name_list(name, mtl_deep_ctr_list):
-        raise NotImplementedError("MTL base models (SURVEY.md 8(a) row a21) are not built yet")
+        from mamdr_b200.deep_mtl_ctr import DeepMTLCTR
+        model = DeepMTLCTR(dataset, config)
     else:
         print("model: {} not found".format(name))
         raise ValueError("model: {} not found".format(name))

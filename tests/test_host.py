@@ -127,7 +127,7 @@ def test_dispatch_rules(monkeypatch):
     from mamdr_b200.dataset import MultiDomainDataset
     c = make_config(**{"dataset.synthetic.scale": 0.002})
     ds = MultiDomainDataset(c["dataset"], device=None)
-    for name, exc in [("mmoe", NotImplementedError), ("nothing", ValueError), ("wdl", NotImplementedError)]:
+    for name, exc in [("nothing", ValueError), ("wdl", NotImplementedError)]:
         c["model"]["name"] = name
         with pytest.raises(exc):
             run.build(c, dataset=ds)
@@ -150,8 +150,50 @@ def test_dispatch_rules(monkeypatch):
     assert type(run.build(c, dataset=ds)) is st.Star
     c["model"]["name"] = "star_meta_mamdr_finetune"
     assert type(run.build(c, dataset=ds)) is MAMDR
+    # multi-task towers (run.py:38,44-45): mmoe / ple / shared_bottom -> DeepMTLCTR, then the same wrappers
+    import mamdr_b200.deep_mtl_ctr as mt
+    monkeypatch.setattr(mt.DeepMTLCTR, "__init__", lambda self, dataset, config: built.append(config['model']['name']))
+    for name in ("mmoe", "ple", "shared_bottom"):
+        c["model"]["name"] = name
+        assert type(run.build(c, dataset=ds)) is mt.DeepMTLCTR
+    c["model"]["name"] = "ple_meta_domain_negotiation"
+    assert type(run.build(c, dataset=ds)) is DomainNegotiation
     for name in ("mlp_meta_reptile_finetune", "mlp_meta_mldg", "mlp_meta_maml_finetune", "mlp_pcgrad",
                  "mlp_uncertainty_weight"):
         c["model"]["name"] = name
         with pytest.raises(NotImplementedError):
             run.build(c, dataset=ds)
+
+
+def test_mtl_topology_matches_oracle_layout():
+    """Host logic of BASELINE config #5 (no GPU): the product's weight order / sub-model reachability equal the oracle's,
+    and the variables of sub-model t form at most two contiguous arena spans (shared block, domain block)."""
+    from mamdr_b200.deep_mtl_ctr import MTLTopology, init_mtl_weights
+    from oracle.mtl import MTLSpec
+    for kind in ("mmoe", "ple", "shared_bottom"):
+        for trainable in (True, False):
+            topo = MTLTopology(kind, 50, 40, 4, (16, 16, 8), (24, 12), (8,), (4,), num_experts=3, specific_expert_num=2,
+                               shared_expert_num=2, emb_trainable=trainable)
+            spec = MTLSpec(50, 40, 4, kind=kind, emb_dim=(16, 16, 8), expert_hidden=(24, 12), tower_hidden=(8,), gate_hidden=(4,),
+                           num_experts=3, specific_expert_num=2, shared_expert_num=2, emb_trainable=trainable)
+            assert topo.layout.names == spec.names and topo.layout.shapes == [tuple(s) for s in spec.shapes]
+            assert topo.expert_sets == spec.expert_sets and topo.k == spec.k
+            lo = topo.layout
+            for t in range(4):
+                assert sorted(topo.reachable(t)) == sorted(spec.reachable(t))
+                spans = topo.dense_spans(t)
+                assert 1 <= len(spans) <= 2
+                covered = np.zeros(lo.total, dtype=bool)
+                for b, n in spans:
+                    assert b % 4 == 0 and n % 4 == 0
+                    covered[b:b + n] = True
+                for name, off, numel in zip(lo.names, lo.offsets, lo.numels):
+                    if name in ('user_emb', 'item_emb'):
+                        assert not covered[off:off + numel].any()
+                    else:
+                        assert covered[off:off + numel].all() == (name in topo.reachable(t))
+                        assert covered[off:off + numel].any() == (name in topo.reachable(t))
+            w = init_mtl_weights(lo, [1, 0])
+            assert [x.shape for x in w] == lo.shapes and all(x.dtype == np.float32 for x in w)
+    with pytest.raises(ValueError):
+        MTLTopology("cgc", 5, 5, 2, (8, 8, 8), (8,), (8,), (4,))
