@@ -26,7 +26,8 @@ sys.path.insert(0, ROOT)
 
 WORKLOAD_CONFIG = {"Taobao-10": "config/Taobao-10/deepctr_DN+DR.json", "Taobao-20": "config/Taobao_20/deepctr_DN+DR.json",
                    "Taobao-30": "config/Taobao_30/deepctr_DN+DR.json", "Amazon-6": "config/Amazon_6/deepctr.json",
-                   "Amazon-13-sharded": "config/Amazon_6/deepctr.json"}
+                   "Amazon-13-sharded": "config/Amazon_6/deepctr.json", "Amazon-13-mmoe": "config/Amazon_13/mmoe_DN.json",
+                   "Amazon-13-ple": "config/Amazon_13/ple_DN.json"}
 METRIC = "MAMDR meta-train samples/sec (Taobao-10 shape)"
 
 
@@ -274,6 +275,7 @@ def run_amazon(args):
     config = load_config(args.workload)
     config["b200"]["precision"] = "fp32"
     base = runpy.build(config)
+    base = getattr(base, "base_model", base)   # config #5 wraps the MTL base model in DomainNegotiation
     model = base.model
     model.reset_optimizer()
     peaks = {}
@@ -290,6 +292,7 @@ def run_amazon(args):
     sampler = ClockSampler(0)
     sampler.start()
     evs = []
+    launches0 = model.ctx.launches
     for _ in range(args.steps):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
@@ -300,16 +303,20 @@ def run_amazon(args):
     clocks = sampler.stop()
     ms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
     n_table = sum(r * d for _, r, d, _ in model._tables)
-    alg_bytes = 24.0 * n_table + 28.0 * (model.params.numel() - n_table)
+    mtl = hasattr(model, "spans")
+    # dense part: the whole arena for the mlp; for a multi-task tower only the spans of the sub-model that trains
+    n_dense = sum(int(x) for x in model.spans[idx][1]) if mtl else model.params.numel() - n_table
+    alg_bytes = 24.0 * n_table + 28.0 * n_dense
     hbm = peaks.get("hbm_gbs", 6650.0)
     achieved = alg_bytes * mb / (ms * 1e-3) / 1e9
-    line = {"metric": "joint-train samples/sec (Amazon-6 shape, trainable 128-d tables)", "value": mb * 1024 / (ms * 1e-3),
+    shape = config["dataset"]["synthetic"]["shape"]
+    line = {"metric": "joint-train samples/sec (%s shape, trainable 128-d tables)" % shape, "value": mb * 1024 / (ms * 1e-3),
             "unit": "samples/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "mlp joint baseline, trainable user/item tables, synthetic Amazon-6 (445 789 + 172 653 rows x 128), "
-                                   "%d mini-batches of 1024 per step" % mb, "precision": "fp32",
-                       "l2": "tables + Adam slots = 950 MB per sweep, far beyond L2"},
-            "gpu_launches": None, "clocks": clocks,
+            "config": {"workload": "%s train steps of sub-model %d, trainable user/item tables, synthetic %s (%d + %d rows x 128), "
+                                   "%d mini-batches of 1024 per step" % (config["model"]["name"], idx, shape, model.n_uid, model.n_pid, mb),
+                       "precision": "fp32", "l2": "tables + Adam slots (%.0f MB per sweep) are far beyond L2" % (12e-6 * n_table)},
+            "gpu_launches": model.ctx.launches - launches0, "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
                          "kernel": "adam_table_kernel (fused sparse merge + l2 + Adam over every table row) within the whole mini-batch",
                          "alg_bytes_per_minibatch": alg_bytes, "us_per_minibatch": 1e3 * ms / mb}}
@@ -579,7 +586,7 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
-    elif args.workload == "Amazon-6":
+    elif args.workload in ("Amazon-6", "Amazon-13-mmoe", "Amazon-13-ple"):
         run_amazon(args)
     elif args.workload == "Amazon-13-sharded":
         run_sharded(args)

@@ -27,6 +27,22 @@ struct OptState {
     unsigned int pad[3];
 };
 
+// one id list to de-duplicate (scatter.cu); two jobs (user + item table of a mini-batch) share the launches
+struct DedupJob {
+    const int32_t* ids;        // [n]
+    const float*   grad_rows;  // [n, grad_stride]
+    int64_t        grad_stride;
+    int            dim;
+    int32_t*       uniq_ids;   // [n]
+    float*         uniq_rows;  // [n, dim]
+    int32_t*       n_uniq;     // [1]
+    int32_t*       perm;       // [n]   workspace (mamdr_scatter_job_ws)
+    int32_t*       seg_start;  // [n+1] workspace
+};
+struct DedupArgs { DedupJob job[2]; int n, npow2; };
+int  mamdr_scatter_dedup_jobs(mamdr_ctx* ctx, const DedupJob* jobs, int n_jobs, int n, cudaStream_t st);
+void mamdr_scatter_job_ws(DedupJob* job, void* ws, int64_t n);
+
 extern char g_mamdr_create_err[512];
 
 #define MAMDR_SET_ERR(ctx, ...)                                         \

@@ -22,28 +22,16 @@ struct GemmShape {
     int lda, ldb;  // leading dimensions (floats) of A and B in their stored orientation
 };
 
-// One CTA's tile; (zi, zn) = this CTA's split-K slice and the number of slices.
-template <bool A_KCONTIG, bool B_NCONTIG, class Epilogue>
+// acc += A[:, kbeg:kend] . B[kbeg:kend, :] for this CTA's 32 x 64 tile (all threads of the CTA must call it)
+template <bool A_KCONTIG, bool B_NCONTIG>
 __device__ __forceinline__ void
-gemm_tile(const float* __restrict__ A, const float* __restrict__ B, const GemmShape& s, int k_chunk,
-          float* __restrict__ partials, unsigned int* __restrict__ tickets, const Epilogue& epi, const unsigned int zi,
-          const unsigned int zn) {
+mainloop(const float* __restrict__ A, const float* __restrict__ B, const GemmShape& s, const int kbeg, const int kend,
+         float (&acc)[4][4]) {
     __shared__ __align__(16) float As[BK][BM + APAD];
     __shared__ __align__(16) float Bs[BK][BN];
-    __shared__ bool is_last;
-
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    const int kbeg = (int)zi * k_chunk;
-    const int kend = min(s.K, kbeg + k_chunk);
-
-    float acc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-
     for (int k0 = kbeg; k0 < kend; k0 += BK) {
         // ---- stage A tile (BM x BK) into As[k][m]
         if (A_KCONTIG) {
@@ -109,7 +97,40 @@ gemm_tile(const float* __restrict__ A, const float* __restrict__ B, const GemmSh
         }
         __syncthreads();
     }
+}
 
+template <class Epilogue>
+__device__ __forceinline__ void finish_tile(float (&acc)[4][4], int M, int N, float* __restrict__ partials,
+                                            unsigned int* __restrict__ tickets, const Epilogue& epi, unsigned int zi, unsigned int zn);
+
+// One CTA's tile; (zi, zn) = this CTA's split-K slice and the number of slices.
+template <bool A_KCONTIG, bool B_NCONTIG, class Epilogue>
+__device__ __forceinline__ void
+gemm_tile(const float* __restrict__ A, const float* __restrict__ B, const GemmShape& s, int k_chunk,
+          float* __restrict__ partials, unsigned int* __restrict__ tickets, const Epilogue& epi, const unsigned int zi,
+          const unsigned int zn) {
+    const int kbeg = (int)zi * k_chunk;
+    const int kend = min(s.K, kbeg + k_chunk);
+
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    mainloop<A_KCONTIG, B_NCONTIG>(A, B, s, kbeg, kend, acc);
+    finish_tile(acc, s.M, s.N, partials, tickets, epi, zi, zn);
+}
+
+// Split-K fix-up + epilogue of one CTA's tile: with zn > 1 every CTA parks its partial tile; the last one to arrive
+// (ticket) re-reads ALL partials in z order and runs the epilogue.
+template <class Epilogue>
+__device__ __forceinline__ void
+finish_tile(float (&acc)[4][4], const int M, const int N, float* __restrict__ partials, unsigned int* __restrict__ tickets,
+            const Epilogue& epi, const unsigned int zi, const unsigned int zn) {
+    __shared__ bool is_last;
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const int gn = n0 + tx * 4;
     if (zn > 1) {
         // park the partial tile: layout [z][tile][BM][BN]
@@ -143,11 +164,11 @@ gemm_tile(const float* __restrict__ A, const float* __restrict__ B, const GemmSh
         }
         if (tid == 0) tickets[tile] = 0;  // re-arm for the next launch
     }
-    if (gn < s.N) {
+    if (gn < N) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int gm = m0 + ty * 4 + i;
-            if (gm < s.M) epi(gm, gn, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+            if (gm < M) epi(gm, gn, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
         }
     }
 }
@@ -179,6 +200,31 @@ gemm_grouped_kernel(const __grid_constant__ GroupedArgs<Epilogue> a, GemmShape s
     const unsigned int g = blockIdx.z / a.split, z = blockIdx.z % a.split;
     gemm_tile<A_KCONTIG, B_NCONTIG, Epilogue>(a.A[g], a.B[g], s, k_chunk, partials + g * a.partial_stride,
                                               tickets + g * a.ticket_stride, a.epi[g], z, (unsigned int)a.split);
+}
+
+// K-segmented variant: C = sum_g A_g . B_g over up to MAX_GROUPS operand pairs that share M and N but not K (the input
+// gradient of a layer fed to several experts: dX = sum_j dZ_j . W_j^T).  One CTA per (tile, segment); the deterministic
+// split-K fix-up adds the segments in order.
+struct SegmentArgs {
+    const float* A[MAX_GROUPS + 1];
+    const float* B[MAX_GROUPS + 1];
+    int          K[MAX_GROUPS + 1];   // also lda / ldb of the segment (k-contiguous operands)
+    int          n;
+};
+
+template <class Epilogue>
+__global__ void __launch_bounds__(THREADS)
+gemm_ksegments_kernel(const __grid_constant__ SegmentArgs a, int M, int N, float* __restrict__ partials,
+                      unsigned int* __restrict__ tickets, Epilogue epi) {
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const int g = blockIdx.z;   // gridDim.z == a.n: one segment per slice, summed in segment order by the fix-up
+    const GemmShape s{M, N, a.K[g], a.K[g], a.K[g]};
+    mainloop<true, false>(a.A[g], a.B[g], s, 0, a.K[g], acc);
+    finish_tile(acc, M, N, partials, tickets, epi, blockIdx.z, gridDim.z);
 }
 
 struct LaunchPlan {

@@ -100,7 +100,7 @@ struct HeadArgs {
 
 __global__ void __launch_bounds__(kHeadThreads) head_kernel(HeadArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: w[n] | dw_part[32][n] | red_d[32] (double) | red_f[32] | hist[2][T+1] (int)
+    // layout: w[n] | dw_part[32][n] | red_d[32] (double) | red_f[32] | hist[2][T+1] (int) | thr[T] | sz[1024]
     float*  sw      = reinterpret_cast<float*>(smem_raw);
     float*  dw_part = sw + a.n;
     double* red_d   = reinterpret_cast<double*>(dw_part + 32 * a.n + ((32 * a.n + a.n) & 1));
@@ -108,69 +108,108 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(HeadArgs a) {
     int*    hist    = reinterpret_cast<int*>(red_f + 32);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int T1 = a.T + 1;
+    float*  sthr    = reinterpret_cast<float*>(hist + 2 * T1);   // threshold table: the binary search runs in smem
+    float*  sz      = sthr + a.T;                                // per-row logit, then per-row ds, of a 1024-row chunk
 
     for (int c = tid; c < a.n; c += kHeadThreads) sw[c] = a.w[c];
-    if (a.auc_acc)
+    if (a.auc_acc) {
         for (int i = tid; i < 2 * T1; i += kHeadThreads) hist[i] = 0;
+        for (int i = tid; i < a.T; i += kHeadThreads) sthr[i] = a.thr[i];
+    }
     __syncthreads();
 
     const float gbias = a.g[0];
     const float fb = (float)a.b;
     const float lo = 1e-7f, hi = 1.0f - 1e-7f;
-    double bce_sum = 0.0;   // lane 0 of each warp
-    float  dg_sum  = 0.f;   // lane 0
+    double bce_sum = 0.0;   // per thread (thread t owns rows t, t + 1024, ...)
+    float  dg_sum  = 0.f;
     // per-lane partial dw for columns c = lane + 32*j, j < n/32 (n <= kHeadMaxN => <= 16 regs)
     float dwacc[kHeadMaxN / 32];
 #pragma unroll
     for (int j = 0; j < kHeadMaxN / 32; ++j) dwacc[j] = 0.f;
 
-    for (int r = warp; r < a.b; r += 32) {
-        const float* h = a.HL + (int64_t)r * a.n;
-        float hv[kHeadMaxN / 32];
-        float z = 0.f;
+    for (int r0 = 0; r0 < a.b; r0 += kHeadThreads) {
+        // ---- phase A: logits, one warp per row, four rows in flight (coalesced row reads, shuffle reduction)
+        for (int i0 = 0; i0 < 32; i0 += 4) {
+            float z[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int j = 0; j < kHeadMaxN / 32; ++j) {
-            const int c = lane + 32 * j;
-            hv[j] = c < a.n ? h[c] : 0.f;
-            z = fmaf(hv[j], c < a.n ? sw[c] : 0.f, z);
+            for (int q = 0; q < 4; ++q) {
+                const int r = r0 + warp + 32 * (i0 + q);
+                if (r < a.b) {
+                    const float* h = a.HL + (int64_t)r * a.n;
+#pragma unroll
+                    for (int j = 0; j < kHeadMaxN / 32; ++j) {
+                        const int c = lane + 32 * j;
+                        if (c < a.n) z[q] = fmaf(h[c], sw[c], z[q]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) z[q] += __shfl_xor_sync(0xffffffffu, z[q], o);
+                if (lane == 0) sz[warp + 32 * (i0 + q)] = z[q];
+            }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
-        const float s = z + gbias;
-        const float p = 1.0f / (1.0f + expf(-s));
-        const float yv = a.y[r];
-        float dsv = 0.f;
+        __syncthreads();
+        // ---- phase B: the scalar chain of a row (sigmoid, BCE, ds, AUC bin) -- one THREAD per row
+        {
+            const int r = r0 + tid;
+            float dsv = 0.f;
+            if (r < a.b) {
+                const float s = sz[tid] + gbias;
+                const float p = 1.0f / (1.0f + expf(-s));
+                const float yv = a.y[r];
+                if (a.train) dsv = (fabsf(s) <= MAMDR_LOGIT_CLIP) ? __fdiv_rn(__fsub_rn(p, yv), fb) : 0.f;
+                const float ph = fminf(fmaxf(p, lo), hi);
+                const float lg = logf(ph / (1.0f - ph));
+                const float bce = fmaxf(lg, 0.f) - lg * yv + log1pf(expf(-fabsf(lg)));
+                bce_sum += (double)bce;
+                dg_sum += dsv;
+                a.p_out[r] = p;
+                if (a.probs) a.probs[r] = p;
+                if (a.train) a.ds[r] = dsv;
+                if (a.auc_acc) {
+                    // k = number of thresholds strictly below p  (pred_is_pos[j] = p > thr[j]  <=>  j < k)
+                    int lo_i = 0, hi_i = a.T;
+                    while (lo_i < hi_i) {
+                        const int mid = (lo_i + hi_i) >> 1;
+                        if (sthr[mid] < p) lo_i = mid + 1; else hi_i = mid;
+                    }
+                    atomicAdd(&hist[(yv != 0.f ? T1 : 0) + lo_i], 1);
+                }
+            }
+            sz[tid] = dsv;
+        }
+        __syncthreads();
+        // ---- phase C: dZ of the last hidden layer and the per-lane partials of dw, one warp per row
         if (a.train) {
-            dsv = (fabsf(s) <= MAMDR_LOGIT_CLIP) ? __fdiv_rn(__fsub_rn(p, yv), fb) : 0.f;
+#pragma unroll 4
+            for (int i = 0; i < 32; ++i) {
+                const int r = r0 + warp + 32 * i;
+                if (r < a.b) {
+                    const float dsv = sz[warp + 32 * i];
+                    const float* h = a.HL + (int64_t)r * a.n;
 #pragma unroll
-            for (int j = 0; j < kHeadMaxN / 32; ++j) {
-                const int c = lane + 32 * j;
-                if (c < a.n) {
-                    dwacc[j] = fmaf(hv[j], dsv, dwacc[j]);
-                    const float dh = __fmul_rn(dsv, sw[c]);
-                    a.dZ[(int64_t)r * a.n + c] = hv[j] > 0.f ? __fmul_rn(dh, a.inv_keep) : 0.f;
+                    for (int j = 0; j < kHeadMaxN / 32; ++j) {
+                        const int c = lane + 32 * j;
+                        if (c < a.n) {
+                            const float hv = h[c];
+                            dwacc[j] = fmaf(hv, dsv, dwacc[j]);
+                            const float dh = __fmul_rn(dsv, sw[c]);
+                            a.dZ[(int64_t)r * a.n + c] = hv > 0.f ? __fmul_rn(dh, a.inv_keep) : 0.f;
+                        }
+                    }
                 }
             }
         }
-        if (lane == 0) {
-            const float ph = fminf(fmaxf(p, lo), hi);
-            const float lg = logf(ph / (1.0f - ph));
-            const float bce = fmaxf(lg, 0.f) - lg * yv + log1pf(expf(-fabsf(lg)));
-            bce_sum += (double)bce;
-            dg_sum += dsv;
-            a.p_out[r] = p;
-            if (a.probs) a.probs[r] = p;
-            if (a.train) a.ds[r] = dsv;
-            if (a.auc_acc) {
-                // k = number of thresholds strictly below p  (pred_is_pos[j] = p > thr[j]  <=>  j < k)
-                int lo_i = 0, hi_i = a.T;
-                while (lo_i < hi_i) {
-                    const int mid = (lo_i + hi_i) >> 1;
-                    if (a.thr[mid] < p) lo_i = mid + 1; else hi_i = mid;
-                }
-                atomicAdd(&hist[(yv != 0.f ? T1 : 0) + lo_i], 1);
-            }
-        }
+        __syncthreads();
+    }
+    // warp totals in a fixed (butterfly) order
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        bce_sum += __shfl_xor_sync(0xffffffffu, bce_sum, o);
+        dg_sum += __shfl_xor_sync(0xffffffffu, dg_sum, o);
     }
     // ---- fixed-order cross-warp reductions
     if (lane == 0) { red_d[warp] = bce_sum; red_f[warp] = dg_sum; }
@@ -233,27 +272,39 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(HeadArgs a) {
 size_t head_smem_bytes(int n, int T) {
     size_t floats = (size_t)n + 32 * (size_t)n;
     floats += (floats & 1);
-    return floats * 4 + 32 * 8 + 32 * 4 + 2 * (size_t)(T + 1) * 4 + 16;
+    return floats * 4 + 32 * 8 + 32 * 4 + 2 * (size_t)(T + 1) * 4 + (size_t)T * 4 + (size_t)kHeadThreads * 4 + 16;
 }
 
 // ---- column sums: db_l[c] = sum_r dZ_l[r, c], fixed order ------------------------------------------
 struct ColsumJob { const float* src; float* dst; int n; };
 struct ColsumArgs { ColsumJob job[MAMDR_MAX_LAYERS]; int rows; };
 
-__global__ void __launch_bounds__(256) colsum_kernel(ColsumArgs a) {
-    const ColsumJob j = a.job[blockIdx.y];
-    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int ty = threadIdx.x >> 5;  // 8 row groups
-    __shared__ float part[8][32];
+// 32 columns x 32 row groups per CTA; every thread keeps 4 independent loads in flight and adds them in a fixed order
+constexpr int kColsumThreads = 1024;
+__device__ __forceinline__ float colsum_thread(const float* __restrict__ src, int rows, int ld, int c, int ty) {
     float s = 0.f;
-    if (c < j.n)
-        for (int r = ty; r < a.rows; r += 8) s += j.src[(int64_t)r * j.n + c];
-    part[ty][threadIdx.x & 31] = s;
+    int r = ty;
+    for (; r + 96 < rows; r += 128) {
+        const float v0 = src[(int64_t)r * ld + c], v1 = src[(int64_t)(r + 32) * ld + c];
+        const float v2 = src[(int64_t)(r + 64) * ld + c], v3 = src[(int64_t)(r + 96) * ld + c];
+        s += v0; s += v1; s += v2; s += v3;
+    }
+    for (; r < rows; r += 32) s += src[(int64_t)r * ld + c];
+    return s;
+}
+
+__global__ void __launch_bounds__(kColsumThreads) colsum_kernel(ColsumArgs a) {
+    const ColsumJob j = a.job[blockIdx.y];
+    if (blockIdx.x * 32 >= j.n) return;
+    const int lx = threadIdx.x & 31, c = blockIdx.x * 32 + lx;
+    const int ty = threadIdx.x >> 5;  // 32 row groups
+    __shared__ float part[32][33];
+    part[ty][lx] = c < j.n ? colsum_thread(j.src, a.rows, j.n, c, ty) : 0.f;
     __syncthreads();
     if (ty == 0 && c < j.n) {
         float t = 0.f;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) t += part[k][threadIdx.x & 31];
+        for (int k = 0; k < 32; ++k) t += part[k][lx];
         j.dst[c] = t;
     }
 }
@@ -482,13 +533,14 @@ extern "C" int mamdr_mlp_train_step(mamdr_ctx* ctx, const mamdr_mlp_desc* d, con
         simt::gemm_kernel<true, false, StoreEpilogue><<<p.grid, simt::THREADS, 0, st>>>(
             (const float*)(ws + w.dZ[0]), params + d->off_kernel[0], s, p.k_chunk, nullptr, nullptr, epi);
         MAMDR_LAUNCH_OK(ctx);
+        DedupJob jobs[2];   // both tables: one sort launch + one segment-sum launch
         for (int t = 0; t < 2; ++t) {
-            rc = mamdr_scatter_dedup_f32(ctx, (const int32_t*)(ws + (t == 0 ? w.uid_b : w.pid_b)),
-                                         (const float*)(ws + w.dX) + (t == 0 ? 0 : d->emb_dim[0]), dui, rows, d->emb_dim[t],
-                                         (int32_t*)(ws + w.sp_ids[t]), (float*)(ws + w.sp_rows[t]), (int32_t*)(ws + w.sp_n[t]),
-                                         ws + w.sp_ws, mamdr_scatter_workspace_bytes(rows), stream);
-            if (rc) return rc;
+            jobs[t] = DedupJob{(const int32_t*)(ws + (t == 0 ? w.uid_b : w.pid_b)), (const float*)(ws + w.dX) + (t == 0 ? 0 : d->emb_dim[0]), dui,
+                               d->emb_dim[t], (int32_t*)(ws + w.sp_ids[t]), (float*)(ws + w.sp_rows[t]), (int32_t*)(ws + w.sp_n[t]), nullptr, nullptr};
+            mamdr_scatter_job_ws(&jobs[t], ws + w.sp_ws + t * mamdr_scatter_workspace_bytes(rows), rows);
         }
+        rc = mamdr_scatter_dedup_jobs(ctx, jobs, 2, rows, st);
+        if (rc) return rc;
     }
     // ---- dW_l = H_l^T . dZ_l   (reduction over the batch rows; deterministic split-K)
     for (int l = 0; l < L; ++l) {
@@ -511,7 +563,7 @@ extern "C" int mamdr_mlp_train_step(mamdr_ctx* ctx, const mamdr_mlp_desc* d, con
             if (d->hidden[l] > maxn) maxn = d->hidden[l];
         }
         ca.rows = rows;
-        colsum_kernel<<<dim3((maxn + 31) / 32, L), 256, 0, st>>>(ca);
+        colsum_kernel<<<dim3((maxn + 31) / 32, L), kColsumThreads, 0, st>>>(ca);
         MAMDR_LAUNCH_OK(ctx);
     }
     // ---- domain embedding gradient (uses db_0 just written)

@@ -62,7 +62,7 @@ inline WsLayout ws_layout(const mamdr_mlp_desc& d, int B) {
             w.sp_rows[t] = take((size_t)B * d.emb_dim[t] * 4);
             w.sp_n[t] = take(16);
         }
-        w.sp_ws = take(mamdr_scatter_workspace_bytes(B));
+        w.sp_ws = take(2 * mamdr_scatter_workspace_bytes(B));   // one per table
     }
     w.total = off;
     return w;

@@ -9,8 +9,8 @@
 //   assemble X | experts: Le x grouped fwd GEMM (all k experts of a layer in ONE launch, bias + ReLU + dropout fused) |
 //   gate DNN fwd | gate_mix (logits, softmax, mixture) | tower fwd | head (sigmoid, BCE, ds, dZ of the last tower layer)
 //   | tower dH chain | dMix GEMM | mix_backward (da, softmax backward, masked expert / gate upstream gradients) |
-//   gate_out gradient | grouped expert dH chain | gate dH chain | dX = sum_j dZ0_j . W0_j^T (+ gate), accumulated in
-//   expert order | grouped expert dW (deterministic split-K) | gate / tower dW | all bias gradients in one column-sum
+//   gate_out gradient | grouped expert dH chain | gate dH chain | dX = sum_j dZ0_j . W0_j^T (+ gate) as ONE K-segmented
+//   GEMM | grouped expert dW (deterministic split-K) | gate / tower dW | all bias gradients in one column-sum
 //   launch | domain-embedding gradient | sparse de-duplication of the user / item gradient rows (trainable tables)
 #pragma once
 #include <algorithm>
@@ -18,6 +18,8 @@
 namespace mtl {
 
 constexpr int kMaxK = MAMDR_MTL_MAX_K;
+static_assert(kMaxK == 8, "gate kernels load the softmax rows as two float4");
+constexpr int kSmallSplit = 4;       // split-K bound of a lone narrow forward / dH layer
 constexpr int kGroupSplit = 4;       // split-K bound of the grouped expert dW GEMMs
 constexpr int kMaxColsumJobs = 80;   // k * Le + Lg + Lt + 1 (domain columns of dX)
 
@@ -91,14 +93,17 @@ inline Ws ws_layout(const mamdr_mtl_desc& d, int B) {
     w.dx_ld = in - w.dx_c0;
     w.dX = take((size_t)B * w.dx_ld * 4);
     w.dsum = take((size_t)d.emb_dim[2] * 4);
-    w.partials = take(std::max(grouped, single) * 4);
+    for (int l = 0; l < Lg; ++l) single = std::max(single, tile_area(B, d.gate_hidden[l]) * kSmallSplit);
+    for (int l = 0; l < Lt; ++l) single = std::max(single, tile_area(B, d.tower_hidden[l]) * kSmallSplit);
+    const size_t dx_part = tile_area(B, w.dx_ld) * (d.k + 1);   // one partial tile set per segment of the dX GEMM
+    w.partials = take(std::max(std::max(grouped, single), dx_part) * 4);
     if (d.emb_trainable) {
         for (int t = 0; t < 2; ++t) {
             w.sp_ids[t] = take((size_t)B * 4);
             w.sp_rows[t] = take((size_t)B * d.emb_dim[t] * 4);
             w.sp_n[t] = take(16);
         }
-        w.sp_ws = take(mamdr_scatter_workspace_bytes(B));
+        w.sp_ws = take(2 * mamdr_scatter_workspace_bytes(B));   // one per table
     }
     w.total = off;
     return w;
@@ -235,52 +240,50 @@ __global__ void __launch_bounds__(256) mix_backward_kernel(MixBwdArgs A) {
 }
 
 // ---- gradient of the gate's output kernel: gGout[c, j] = sum_r G_last[r, c] * dlogit[r, j], fixed order
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 gate_out_grad_kernel(const float* __restrict__ Gl, const float* __restrict__ dlogit, int rows, int g, int k, float* __restrict__ gGout) {
-    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int ty = threadIdx.x >> 5;
-    __shared__ float part[8][32][kMaxK + 1];
+    const int lx = threadIdx.x & 31, c = blockIdx.x * 32 + lx;
+    const int ty = threadIdx.x >> 5;   // 32 row groups
+    __shared__ float part[32][32][kMaxK + 1];
     float acc[kMaxK];
 #pragma unroll
     for (int j = 0; j < kMaxK; ++j) acc[j] = 0.f;
-    if (c < g)
-        for (int r = ty; r < rows; r += 8) {
+    if (c < g) {
+#pragma unroll 4
+        for (int r = ty; r < rows; r += 32) {
             const float h = Gl[(int64_t)r * g + c];
-#pragma unroll
-            for (int j = 0; j < kMaxK; ++j) acc[j] = fmaf(h, dlogit[(int64_t)r * kMaxK + j], acc[j]);
+            const float4 d0 = ldg_f4(dlogit + (int64_t)r * kMaxK), d1 = ldg_f4(dlogit + (int64_t)r * kMaxK + 4);
+            acc[0] = fmaf(h, d0.x, acc[0]); acc[1] = fmaf(h, d0.y, acc[1]); acc[2] = fmaf(h, d0.z, acc[2]); acc[3] = fmaf(h, d0.w, acc[3]);
+            acc[4] = fmaf(h, d1.x, acc[4]); acc[5] = fmaf(h, d1.y, acc[5]); acc[6] = fmaf(h, d1.z, acc[6]); acc[7] = fmaf(h, d1.w, acc[7]);
         }
+    }
 #pragma unroll
-    for (int j = 0; j < kMaxK; ++j) part[ty][threadIdx.x & 31][j] = acc[j];
+    for (int j = 0; j < kMaxK; ++j) part[ty][lx][j] = acc[j];
     __syncthreads();
-    if (ty == 0 && c < g)
-        for (int j = 0; j < k; ++j) {
-            float t = 0.f;
+    if (ty < k && c < g) {      // row group ty reduces gate column ty
+        float t = 0.f;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) t += part[q][threadIdx.x & 31][j];
-            gGout[c * k + j] = t;
-        }
+        for (int q = 0; q < 32; ++q) t += part[q][lx][ty];
+        gGout[c * k + ty] = t;
+    }
 }
 
 // ---- column sums with a leading dimension (all bias gradients + the domain columns of dX in one launch)
 struct ColJob { const float* src; float* dst; int n, ld; };
 struct ColArgs { ColJob job[kMaxColsumJobs]; int rows; };
 
-__global__ void __launch_bounds__(256) colsum_ld_kernel(const __grid_constant__ ColArgs args) {
+__global__ void __launch_bounds__(kColsumThreads) colsum_ld_kernel(const __grid_constant__ ColArgs args) {
     const ColJob j = args.job[blockIdx.y];
-    const int rows = args.rows;
-    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
     if (blockIdx.x * 32 >= j.n) return;
+    const int lx = threadIdx.x & 31, c = blockIdx.x * 32 + lx;
     const int ty = threadIdx.x >> 5;
-    __shared__ float part[8][32];
-    float s = 0.f;
-    if (c < j.n)
-        for (int r = ty; r < rows; r += 8) s += j.src[(int64_t)r * j.ld + c];
-    part[ty][threadIdx.x & 31] = s;
+    __shared__ float part[32][33];
+    part[ty][lx] = c < j.n ? colsum_thread(j.src, args.rows, j.ld, c, ty) : 0.f;
     __syncthreads();
     if (ty == 0 && c < j.n) {
         float t = 0.f;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) t += part[q][threadIdx.x & 31];
+        for (int q = 0; q < 32; ++q) t += part[q][lx];
         j.dst[c] = t;
     }
 }
@@ -294,20 +297,6 @@ domain_grad_kernel(const float* __restrict__ Ed, const float* __restrict__ dsum,
         gEd[i] = (i / dd == dom) ? __fadd_rn(reg, dsum[i - dom * dd]) : reg;
     }
 }
-
-struct AccumEpilogue {  // out (+)= acc with leading dimension
-    float* out;
-    int    ld;
-    int    accumulate;
-    __device__ __forceinline__ void operator()(int m, int n, float4 a) const {
-        float4* p = reinterpret_cast<float4*>(out + (int64_t)m * ld + n);
-        if (accumulate) {
-            const float4 o = *p;
-            a.x = __fadd_rn(o.x, a.x); a.y = __fadd_rn(o.y, a.y); a.z = __fadd_rn(o.z, a.z); a.w = __fadd_rn(o.w, a.w);
-        }
-        *p = a;
-    }
-};
 
 inline DropoutParams dropout_params(const mamdr_mtl_desc& d, bool train, uint32_t stream) {
     DropoutParams dp;
@@ -353,9 +342,10 @@ static int validate(mamdr_ctx* ctx, const mamdr_mtl_desc* d, const mamdr_mtl_dom
 // one dense layer forward (bias + ReLU + dropout fused) for `ng` independent inputs / kernels of one shape
 static int fwd_layer(mamdr_ctx* ctx, int ng, const float* const* A, const float* const* W, const float* const* bias, float* const* out,
                      const uint32_t* streams, const mamdr_mtl_desc* d, bool train, const OptState* state, int rows, int K, int N,
-                     cudaStream_t st) {
+                     float* partials, unsigned int* tickets, cudaStream_t st) {
     simt::GemmShape s{rows, N, K, K, N};
-    simt::LaunchPlan p = simt::plan(rows, N, K, 0, 1);
+    // a lone narrow layer (gate, tower) has too few tiles to fill the GPU: split K, the last CTA of a tile runs the epilogue
+    simt::LaunchPlan p = simt::plan(rows, N, K, ng == 1 ? ctx->sm_count : 0, ng == 1 ? kSmallSplit : 1);
     simt::GroupedArgs<FwdEpilogue> ga;
     memset(&ga, 0, sizeof(ga));
     for (int g = 0; g < ng; ++g) {
@@ -367,18 +357,18 @@ static int fwd_layer(mamdr_ctx* ctx, int ng, const float* const* A, const float*
         ga.epi[g].state = state;
         ga.epi[g].dp = dropout_params(*d, train, streams[g]);
     }
-    ga.split = 1; ga.partial_stride = 0; ga.ticket_stride = 0;
-    p.grid.z = ng;
-    simt::gemm_grouped_kernel<true, true, FwdEpilogue><<<p.grid, simt::THREADS, 0, st>>>(ga, s, p.k_chunk, nullptr, nullptr);
+    ga.split = (int)p.grid.z; ga.partial_stride = 0; ga.ticket_stride = 0;
+    p.grid.z = ga.split * ng;
+    simt::gemm_grouped_kernel<true, true, FwdEpilogue><<<p.grid, simt::THREADS, 0, st>>>(ga, s, p.k_chunk, partials, tickets);
     MAMDR_LAUNCH_OK(ctx);
     return MAMDR_OK;
 }
 
 // dZ_prev = (dZ . W^T) * mask(H_prev) for `ng` groups
 static int dh_layer(mamdr_ctx* ctx, int ng, const float* const* dZ, const float* const* W, const float* const* Hprev, float* const* out,
-                    float inv_keep, int rows, int Kd, int Nd, cudaStream_t st) {
+                    float inv_keep, int rows, int Kd, int Nd, float* partials, unsigned int* tickets, cudaStream_t st) {
     simt::GemmShape s{rows, Nd, Kd, Kd, Kd};
-    simt::LaunchPlan p = simt::plan(rows, Nd, Kd, 0, 1);
+    simt::LaunchPlan p = simt::plan(rows, Nd, Kd, ng == 1 ? ctx->sm_count : 0, ng == 1 ? kSmallSplit : 1);
     simt::GroupedArgs<DhEpilogue> ga;
     memset(&ga, 0, sizeof(ga));
     for (int g = 0; g < ng; ++g) {
@@ -386,9 +376,9 @@ static int dh_layer(mamdr_ctx* ctx, int ng, const float* const* dZ, const float*
         ga.B[g] = W[g];
         ga.epi[g] = DhEpilogue{Hprev[g], out[g], Nd, inv_keep};
     }
-    ga.split = 1;
-    p.grid.z = ng;
-    simt::gemm_grouped_kernel<true, false, DhEpilogue><<<p.grid, simt::THREADS, 0, st>>>(ga, s, p.k_chunk, nullptr, nullptr);
+    ga.split = (int)p.grid.z;
+    p.grid.z = ga.split * ng;
+    simt::gemm_grouped_kernel<true, false, DhEpilogue><<<p.grid, simt::THREADS, 0, st>>>(ga, s, p.k_chunk, partials, tickets);
     MAMDR_LAUNCH_OK(ctx);
     return MAMDR_OK;
 }
@@ -398,7 +388,7 @@ static int dw_layer(mamdr_ctx* ctx, int ng, const float* const* H, const float* 
                     unsigned char* ws, const Ws& w, cudaStream_t st) {
     simt::GemmShape s{Md, Nd, rows, Md, Nd};
     const int max_split = ng > 1 ? kGroupSplit : kMaxSplit;
-    simt::LaunchPlan p = simt::plan(Md, Nd, rows, std::max(1, 2 * ctx->sm_count / ng), max_split);
+    simt::LaunchPlan p = simt::plan(Md, Nd, rows, std::max(1, 8 * ctx->sm_count / ng), max_split);
     const int tiles = (int)(p.grid.x * p.grid.y);
     MAMDR_REQUIRE(ctx, tiles * ng <= kMaxTiles, MAMDR_E_UNSUPPORTED, "layer too large for the ticket table");
     simt::GroupedArgs<StoreEpilogue> ga;
@@ -439,7 +429,7 @@ static int forward(mamdr_ctx* ctx, const mamdr_mtl_desc* d, const mamdr_mtl_doma
             out[j] = (float*)(ws + w.E[j][l + 1]);
             streams[j] = 8u * (uint32_t)dm->expert_id[j] + (uint32_t)l;
         }
-        rc = fwd_layer(ctx, k, A, W, bs, out, streams, d, train, state, rows, K, N, st);
+        rc = fwd_layer(ctx, k, A, W, bs, out, streams, d, train, state, rows, K, N, (float*)(ws + w.partials), (unsigned int*)(ws + w.tickets), st);
         if (rc) return rc;
         K = N;
     }
@@ -453,7 +443,7 @@ static int forward(mamdr_ctx* ctx, const mamdr_mtl_desc* d, const mamdr_mtl_doma
             bs[0] = params + dm->off_gate_bias[l];
             out[0] = (float*)(ws + w.G[l + 1]);
             streams[0] = 4096u + 8u * (uint32_t)t + (uint32_t)l;
-            rc = fwd_layer(ctx, 1, A, W, bs, out, streams, d, train, state, rows, K, N, st);
+            rc = fwd_layer(ctx, 1, A, W, bs, out, streams, d, train, state, rows, K, N, (float*)(ws + w.partials), (unsigned int*)(ws + w.tickets), st);
             if (rc) return rc;
             K = N;
         }
@@ -475,7 +465,7 @@ static int forward(mamdr_ctx* ctx, const mamdr_mtl_desc* d, const mamdr_mtl_doma
         bs[0] = params + dm->off_tower_bias[l];
         out[0] = (float*)(ws + w.T[l + 1]);
         streams[0] = 8192u + 8u * (uint32_t)t + (uint32_t)l;
-        rc = fwd_layer(ctx, 1, A, W, bs, out, streams, d, train, state, rows, K, N, st);
+        rc = fwd_layer(ctx, 1, A, W, bs, out, streams, d, train, state, rows, K, N, (float*)(ws + w.partials), (unsigned int*)(ws + w.tickets), st);
         if (rc) return rc;
         K = N;
     }
@@ -570,7 +560,7 @@ extern "C" int mamdr_mtl_train_step(mamdr_ctx* ctx, const mamdr_mtl_desc* d, con
     for (int l = Lt - 1; l >= 1; --l) {
         A[0] = (const float*)(ws + w.dZt[l]); W[0] = params + dm->off_tower_kernel[l];
         Hp[0] = (const float*)(ws + w.T[l]); out[0] = (float*)(ws + w.dZt[l - 1]);
-        rc = dh_layer(ctx, 1, A, W, Hp, out, inv_keep, rows, d->tower_hidden[l], d->tower_hidden[l - 1], st);
+        rc = dh_layer(ctx, 1, A, W, Hp, out, inv_keep, rows, d->tower_hidden[l], d->tower_hidden[l - 1], (float*)(ws + w.partials), (unsigned int*)(ws + w.tickets), st);
         if (rc) return rc;
     }
     // ---- gradient w.r.t. the tower input (the mixture; for SharedBottom the bottom's output, masked like a hidden layer)
@@ -605,7 +595,7 @@ extern "C" int mamdr_mtl_train_step(mamdr_ctx* ctx, const mamdr_mtl_desc* d, con
         ma.rows = rows; ma.g = g; ma.k = k; ma.n = e_last; ma.inv_keep = inv_keep;
         mix_backward_kernel<<<(rows + 7) / 8, 256, (size_t)g * k * 4, st>>>(ma);
         MAMDR_LAUNCH_OK(ctx);
-        gate_out_grad_kernel<<<(g + 31) / 32, 256, 0, st>>>((const float*)(ws + w.G[Lg]), (const float*)(ws + w.dlogit), rows, g, k,
+        gate_out_grad_kernel<<<(g + 31) / 32, 1024, 0, st>>>((const float*)(ws + w.G[Lg]), (const float*)(ws + w.dlogit), rows, g, k,
                                                           grads + dm->off_gate_out);
         MAMDR_LAUNCH_OK(ctx);
     }
@@ -615,25 +605,32 @@ extern "C" int mamdr_mtl_train_step(mamdr_ctx* ctx, const mamdr_mtl_desc* d, con
             A[j] = (const float*)(ws + w.dZe[j][l]); W[j] = params + dm->off_expert_kernel[j][l];
             Hp[j] = (const float*)(ws + w.E[j][l]); out[j] = (float*)(ws + w.dZe[j][l - 1]);
         }
-        rc = dh_layer(ctx, k, A, W, Hp, out, inv_keep, rows, d->expert_hidden[l], d->expert_hidden[l - 1], st);
+        rc = dh_layer(ctx, k, A, W, Hp, out, inv_keep, rows, d->expert_hidden[l], d->expert_hidden[l - 1], (float*)(ws + w.partials), (unsigned int*)(ws + w.tickets), st);
         if (rc) return rc;
     }
     for (int l = Lg - 1; l >= 1; --l) {
         A[0] = (const float*)(ws + w.dZg[l]); W[0] = params + dm->off_gate_kernel[l];
         Hp[0] = (const float*)(ws + w.G[l]); out[0] = (float*)(ws + w.dZg[l - 1]);
-        rc = dh_layer(ctx, 1, A, W, Hp, out, inv_keep, rows, d->gate_hidden[l], d->gate_hidden[l - 1], st);
+        rc = dh_layer(ctx, 1, A, W, Hp, out, inv_keep, rows, d->gate_hidden[l], d->gate_hidden[l - 1], (float*)(ws + w.partials), (unsigned int*)(ws + w.tickets), st);
         if (rc) return rc;
     }
-    // ---- dX[:, c0:in] = sum_j dZe0_j . We0_j[c0:in, :]^T (+ the gate's), accumulated in gate-column order
-    for (int j = 0; j < k + (d->has_gate ? 1 : 0); ++j) {
-        const bool gate = j == k;
-        const int Kd = gate ? d->gate_hidden[0] : d->expert_hidden[0];
-        const float* dZ0 = (const float*)(ws + (gate ? w.dZg[0] : w.dZe[j][0]));
-        const float* W0 = params + (gate ? dm->off_gate_kernel[0] : dm->off_expert_kernel[j][0]) + (int64_t)w.dx_c0 * Kd;
-        AccumEpilogue epi{(float*)(ws + w.dX), w.dx_ld, j > 0 ? 1 : 0};
-        simt::GemmShape s{rows, w.dx_ld, Kd, Kd, Kd};
-        simt::LaunchPlan p = simt::plan(rows, w.dx_ld, Kd, 0, 1);
-        simt::gemm_kernel<true, false, AccumEpilogue><<<p.grid, simt::THREADS, 0, st>>>(dZ0, W0, s, p.k_chunk, nullptr, nullptr, epi);
+    // ---- dX[:, c0:in] = sum_j dZe0_j . We0_j[c0:in, :]^T (+ the gate's): ONE launch, segments accumulated in gate-column order
+    {
+        simt::SegmentArgs sa;
+        memset(&sa, 0, sizeof(sa));
+        sa.n = k + (d->has_gate ? 1 : 0);
+        for (int j = 0; j < sa.n; ++j) {
+            const bool gate = j == k;
+            const int Kd = gate ? d->gate_hidden[0] : d->expert_hidden[0];
+            sa.A[j] = (const float*)(ws + (gate ? w.dZg[0] : w.dZe[j][0]));
+            sa.B[j] = params + (gate ? dm->off_gate_kernel[0] : dm->off_expert_kernel[j][0]) + (int64_t)w.dx_c0 * Kd;
+            sa.K[j] = Kd;
+        }
+        StoreEpilogue epi{(float*)(ws + w.dX), w.dx_ld};
+        const dim3 grid((w.dx_ld + simt::BN - 1) / simt::BN, (rows + simt::BM - 1) / simt::BM, sa.n);
+        MAMDR_REQUIRE(ctx, (int)(grid.x * grid.y) <= kMaxTiles, MAMDR_E_UNSUPPORTED, "batch too large for the ticket table");
+        simt::gemm_ksegments_kernel<StoreEpilogue><<<grid, simt::THREADS, 0, st>>>(sa, rows, w.dx_ld, (float*)(ws + w.partials),
+                                                                                   (unsigned int*)(ws + w.tickets), epi);
         MAMDR_LAUNCH_OK(ctx);
     }
     // ---- kernels: dW = H^T . dZ
@@ -669,19 +666,21 @@ extern "C" int mamdr_mtl_train_step(mamdr_ctx* ctx, const mamdr_mtl_desc* d, con
         ca.job[nj++] = ColJob{(const float*)(ws + w.dX) + (du + di - w.dx_c0), (float*)(ws + w.dsum), dd, w.dx_ld};
         for (int q = 0; q < nj; ++q) maxn = std::max(maxn, ca.job[q].n);
         ca.rows = rows;
-        colsum_ld_kernel<<<dim3((maxn + 31) / 32, nj), 256, 0, st>>>(ca);
+        colsum_ld_kernel<<<dim3((maxn + 31) / 32, nj), kColsumThreads, 0, st>>>(ca);
         MAMDR_LAUNCH_OK(ctx);
         domain_grad_kernel<<<(d->n_domain * dd + 255) / 256, 256, 0, st>>>(params + d->off_domain_emb, (const float*)(ws + w.dsum), d->n_domain, dd,
                                                                           dm->domain, 2.0f * d->l2_emb, grads + d->off_domain_emb);
         MAMDR_LAUNCH_OK(ctx);
     }
-    if (d->emb_trainable) {
+    if (d->emb_trainable) {   // both tables' sparse gradients: one sort launch + one segment-sum launch
+        DedupJob jobs[2];
         for (int t = 0; t < 2; ++t) {
-            rc = mamdr_scatter_dedup_f32(ctx, (const int32_t*)(ws + (t == 0 ? w.uid_b : w.pid_b)), (const float*)(ws + w.dX) + (t == 0 ? 0 : du), w.dx_ld,
-                                         rows, d->emb_dim[t], (int32_t*)(ws + w.sp_ids[t]), (float*)(ws + w.sp_rows[t]), (int32_t*)(ws + w.sp_n[t]),
-                                         ws + w.sp_ws, mamdr_scatter_workspace_bytes(rows), stream);
-            if (rc) return rc;
+            jobs[t] = DedupJob{(const int32_t*)(ws + (t == 0 ? w.uid_b : w.pid_b)), (const float*)(ws + w.dX) + (t == 0 ? 0 : du), w.dx_ld,
+                               d->emb_dim[t], (int32_t*)(ws + w.sp_ids[t]), (float*)(ws + w.sp_rows[t]), (int32_t*)(ws + w.sp_n[t]), nullptr, nullptr};
+            mamdr_scatter_job_ws(&jobs[t], ws + w.sp_ws + t * mamdr_scatter_workspace_bytes(rows), rows);
         }
+        rc = mamdr_scatter_dedup_jobs(ctx, jobs, 2, rows, st);
+        if (rc) return rc;
     }
     return MAMDR_OK;
 }

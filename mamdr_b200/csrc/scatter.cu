@@ -17,16 +17,15 @@ namespace {
 constexpr int kSortThreads = 1024;
 constexpr int kMaxN = 8192;
 
-struct ScatterWs {
-    int32_t* perm;       // [n]   batch positions in sorted order
-    int32_t* seg_start;  // [n+1] first sorted index of each unique id
-};
-
-__global__ void __launch_bounds__(kSortThreads)
-sort_unique_kernel(const int32_t* __restrict__ ids, int n, int npow2, int32_t* __restrict__ uniq_ids,
-                   int32_t* __restrict__ perm, int32_t* __restrict__ seg_start, int32_t* __restrict__ n_uniq) {
+__global__ void __launch_bounds__(kSortThreads) sort_unique_kernel(const __grid_constant__ DedupArgs a) {
     extern __shared__ __align__(16) unsigned long long keys[];  // [npow2]
     __shared__ int scan_part[kSortThreads];
+    const DedupJob& J = a.job[blockIdx.x];
+    const int32_t* __restrict__ ids = J.ids;
+    int32_t* __restrict__ uniq_ids = J.uniq_ids;
+    int32_t* __restrict__ perm = J.perm;
+    int32_t* __restrict__ seg_start = J.seg_start;
+    const int n = a.n, npow2 = a.npow2;
     const int tid = threadIdx.x;
     for (int i = tid; i < npow2; i += kSortThreads)
         keys[i] = i < n ? (((unsigned long long)(uint32_t)ids[i]) << 32) | (uint32_t)i : ~0ull;
@@ -36,9 +35,9 @@ sort_unique_kernel(const int32_t* __restrict__ ids, int n, int npow2, int32_t* _
             for (int i = tid; i < npow2; i += kSortThreads) {
                 const int ixj = i ^ j;
                 if (ixj > i) {
-                    const unsigned long long a = keys[i], b = keys[ixj];
+                    const unsigned long long x = keys[i], y = keys[ixj];
                     const bool up = (i & k) == 0;
-                    if ((a > b) == up) { keys[i] = b; keys[ixj] = a; }
+                    if ((x > y) == up) { keys[i] = y; keys[ixj] = x; }
                 }
             }
             __syncthreads();
@@ -75,29 +74,57 @@ sort_unique_kernel(const int32_t* __restrict__ ids, int n, int npow2, int32_t* _
     }
     if (tid == kSortThreads - 1) {
         const int total = scan_part[tid];
-        n_uniq[0] = total;
+        J.n_uniq[0] = total;
         seg_start[total] = n;
     }
 }
 
-__global__ void __launch_bounds__(256)
-segment_sum_kernel(const float* __restrict__ grad_rows, int64_t grad_stride, int n, int dim,
-                   const int32_t* __restrict__ perm, const int32_t* __restrict__ seg_start,
-                   const int32_t* __restrict__ n_uniq, float* __restrict__ uniq_rows) {
+// warp per unique id; the rows of one id are added sequentially in batch order (bit-identical to numpy add.at).  The
+// permutation entries of a segment are fetched 32 at a time and the row loads run 4 deep ahead of the ordered adds.
+__global__ void __launch_bounds__(256) segment_sum_kernel(const __grid_constant__ DedupArgs a) {
+    const DedupJob& J = a.job[blockIdx.y];
+    const float* __restrict__ grad_rows = J.grad_rows;
+    const int64_t grad_stride = J.grad_stride;
+    const int dim = J.dim;
+    const int32_t* __restrict__ perm = J.perm;
+    const int32_t* __restrict__ seg_start = J.seg_start;
+    float* __restrict__ uniq_rows = J.uniq_rows;
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    const int nu = n_uniq[0];
+    const int nu = J.n_uniq[0];
     for (int k = warp; k < nu; k += nwarps) {
         const int s = seg_start[k], e = seg_start[k + 1];
-        for (int c = lane * 4; c < dim; c += 128) {
-            float4 acc = *reinterpret_cast<const float4*>(grad_rows + (int64_t)perm[s] * grad_stride + c);
-            for (int i = s + 1; i < e; ++i) {
-                const float4 v = *reinterpret_cast<const float4*>(grad_rows + (int64_t)perm[i] * grad_stride + c);
-                acc.x = __fadd_rn(acc.x, v.x); acc.y = __fadd_rn(acc.y, v.y);
-                acc.z = __fadd_rn(acc.z, v.z); acc.w = __fadd_rn(acc.w, v.w);
+        for (int base = s; base < e; base += 32) {
+            const int cnt = min(32, e - base);
+            const int myp = lane < cnt ? perm[base + lane] : 0;
+            for (int cc = 0; cc < dim; cc += 128) {
+                const int c = cc + lane * 4;
+                const bool active = c < dim;
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (base != s && active) acc = *reinterpret_cast<const float4*>(uniq_rows + (int64_t)k * dim + c);
+                for (int i = 0; i < cnt; i += 4) {
+                    int p[4];
+                    float4 v[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) p[q] = __shfl_sync(0xffffffffu, myp, min(i + q, cnt - 1));
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        v[q] = (active && i + q < cnt) ? *reinterpret_cast<const float4*>(grad_rows + (int64_t)p[q] * grad_stride + c)
+                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (i + q >= cnt) break;
+                        if (base == s && i + q == 0) {
+                            acc = v[q];
+                        } else {
+                            acc.x = __fadd_rn(acc.x, v[q].x); acc.y = __fadd_rn(acc.y, v[q].y);
+                            acc.z = __fadd_rn(acc.z, v[q].z); acc.w = __fadd_rn(acc.w, v[q].w);
+                        }
+                    }
+                }
+                if (active) *reinterpret_cast<float4*>(uniq_rows + (int64_t)k * dim + c) = acc;
             }
-            *reinterpret_cast<float4*>(uniq_rows + (int64_t)k * dim + c) = acc;
         }
     }
 }
@@ -119,6 +146,35 @@ extern "C" size_t mamdr_scatter_workspace_bytes(int64_t n) {
     return al((size_t)n * 4) + al((size_t)(n + 1) * 4);
 }
 
+// de-duplicate `n_jobs` (<= 2: the user and the item table of one mini-batch) id lists of n entries in two launches
+int mamdr_scatter_dedup_jobs(mamdr_ctx* ctx, const DedupJob* jobs, int n_jobs, int n, cudaStream_t st) {
+    MAMDR_REQUIRE(ctx, ctx != nullptr && jobs != nullptr, MAMDR_E_INVALID, "ctx / jobs is NULL");
+    MAMDR_REQUIRE(ctx, n_jobs >= 1 && n_jobs <= 2, MAMDR_E_INVALID, "n_jobs must be 1 or 2");
+    MAMDR_REQUIRE(ctx, n >= 1 && n <= kMaxN, MAMDR_E_UNSUPPORTED, "n=%d outside 1..%d", n, kMaxN);
+    DedupArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int q = 0; q < n_jobs; ++q) {
+        const DedupJob& J = jobs[q];
+        MAMDR_REQUIRE(ctx, J.ids && J.grad_rows && J.uniq_ids && J.uniq_rows && J.n_uniq && J.perm && J.seg_start, MAMDR_E_INVALID, "NULL pointer");
+        MAMDR_REQUIRE(ctx, J.dim > 0 && J.dim % 4 == 0 && J.grad_stride >= J.dim && J.grad_stride % 4 == 0, MAMDR_E_INVALID, "bad dim/stride");
+        MAMDR_REQUIRE(ctx, aligned16(J.grad_rows) && aligned16(J.uniq_rows), MAMDR_E_INVALID, "misaligned pointer");
+        a.job[q] = J;
+    }
+    a.n = n;
+    a.npow2 = 1;
+    while (a.npow2 < n) a.npow2 <<= 1;
+    sort_unique_kernel<<<n_jobs, kSortThreads, (size_t)a.npow2 * sizeof(unsigned long long), st>>>(a);
+    MAMDR_LAUNCH_OK(ctx);
+    segment_sum_kernel<<<dim3((n + 7) / 8, n_jobs), 256, 0, st>>>(a);   // n bounds the number of unique ids
+    MAMDR_LAUNCH_OK(ctx);
+    return MAMDR_OK;
+}
+
+void mamdr_scatter_job_ws(DedupJob* job, void* ws, int64_t n) {
+    job->perm = (int32_t*)ws;
+    job->seg_start = (int32_t*)((unsigned char*)ws + al((size_t)n * 4));
+}
+
 extern "C" int mamdr_scatter_dedup_f32(mamdr_ctx* ctx, const int32_t* ids, const float* grad_rows, int64_t grad_stride,
                                        int64_t n, int32_t dim, int32_t* uniq_ids, float* uniq_rows, int32_t* n_uniq,
                                        void* ws, size_t ws_bytes, mamdr_stream stream) {
@@ -130,20 +186,9 @@ extern "C" int mamdr_scatter_dedup_f32(mamdr_ctx* ctx, const int32_t* ids, const
         MAMDR_CUDA_OK(ctx, cudaMemsetAsync(n_uniq, 0, 4, st));
         return MAMDR_OK;
     }
-    MAMDR_REQUIRE(ctx, ids && grad_rows && uniq_ids && uniq_rows && ws, MAMDR_E_INVALID, "NULL pointer");
-    MAMDR_REQUIRE(ctx, dim > 0 && dim % 4 == 0 && grad_stride >= dim && grad_stride % 4 == 0, MAMDR_E_INVALID, "bad dim/stride");
-    MAMDR_REQUIRE(ctx, aligned16(grad_rows) && aligned16(uniq_rows) && aligned16(ws), MAMDR_E_INVALID, "misaligned pointer");
+    MAMDR_REQUIRE(ctx, ws && aligned16(ws), MAMDR_E_INVALID, "workspace NULL or misaligned");
     MAMDR_REQUIRE(ctx, ws_bytes >= mamdr_scatter_workspace_bytes(n), MAMDR_E_WORKSPACE, "workspace too small");
-    int32_t* perm = (int32_t*)ws;
-    int32_t* seg_start = (int32_t*)((unsigned char*)ws + al((size_t)n * 4));
-    int npow2 = 1;
-    while (npow2 < n) npow2 <<= 1;
-    sort_unique_kernel<<<1, kSortThreads, (size_t)npow2 * sizeof(unsigned long long), st>>>(ids, (int)n, npow2, uniq_ids, perm,
-                                                                                          seg_start, n_uniq);
-    MAMDR_LAUNCH_OK(ctx);
-    const int warps = (int)n;  // upper bound on the number of unique ids
-    const int grid = (warps + 7) / 8;
-    segment_sum_kernel<<<grid, 256, 0, st>>>(grad_rows, grad_stride, (int)n, dim, perm, seg_start, n_uniq, uniq_rows);
-    MAMDR_LAUNCH_OK(ctx);
-    return MAMDR_OK;
+    DedupJob J{ids, grad_rows, grad_stride, dim, uniq_ids, uniq_rows, n_uniq, nullptr, nullptr};
+    mamdr_scatter_job_ws(&J, ws, n);
+    return mamdr_scatter_dedup_jobs(ctx, &J, 1, (int)n, st);
 }

@@ -408,7 +408,7 @@ extern "C" int mamdr_star_train_step(mamdr_ctx* ctx, const mamdr_star_desc* d, c
         if (Nd > maxn) maxn = Nd;
     }
     ca.rows = rows;
-    colsum_kernel<<<dim3((maxn + 31) / 32, L), 256, 0, st>>>(ca);
+    colsum_kernel<<<dim3((maxn + 31) / 32, L), kColsumThreads, 0, st>>>(ca);
     MAMDR_LAUNCH_OK(ctx);
     StarGradArgs ga;
     ga.n_layers = L;

@@ -231,8 +231,8 @@ class MTLModel(MLPModel):
         Le, Lg, Lt = len(t.expert_hidden), (len(t.gate_hidden) if t.has_gate else 0), len(t.tower_hidden)
         n = 2 + Le + Lg + (1 if t.has_gate else 0) + Lt + 1          # memset, assemble, fwd, gate_mix, head
         n += (Lt - 1) + 1 + (2 if t.has_gate else 0) + (Le - 1) + max(Lg - 1, 0)   # dH chains, dMix, mix bwd, gate_out grad
-        n += t.k + (1 if t.has_gate else 0) + Le + Lg + Lt + 2       # dX, dW, colsum, domain grad
-        n += (4 + 4 if self.emb_trainable else 0) + 1                # 2 x (sort, segment sum), 2 x (slot scatter, sweep), ranges Adam
+        n += 1 + Le + Lg + Lt + 2                                    # dX (K-segmented), dW, colsum, domain grad
+        n += (2 + 4 if self.emb_trainable else 0) + 1                # sort + segment sum, 2 x (slot scatter, sweep), ranges Adam
         return n
 
     def _train_step(self, data, offset, rows, loss_slot, probs=None, with_auc=True):

