@@ -27,7 +27,8 @@ sys.path.insert(0, ROOT)
 WORKLOAD_CONFIG = {"Taobao-10": "config/Taobao-10/deepctr_DN+DR.json", "Taobao-20": "config/Taobao_20/deepctr_DN+DR.json",
                    "Taobao-30": "config/Taobao_30/deepctr_DN+DR.json", "Amazon-6": "config/Amazon_6/deepctr.json",
                    "Amazon-13-sharded": "config/Amazon_6/deepctr.json", "Amazon-13-mmoe": "config/Amazon_13/mmoe_DN.json",
-                   "Amazon-13-ple": "config/Amazon_13/ple_DN.json"}
+                   "Amazon-13-ple": "config/Amazon_13/ple_DN.json", "Amazon-13-mmoe-sharded": "config/Amazon_13/mmoe_DN.json",
+                   "Amazon-13-ple-sharded": "config/Amazon_13/ple_DN.json"}
 METRIC = "MAMDR meta-train samples/sec (Taobao-10 shape)"
 
 
@@ -349,7 +350,20 @@ def run_sharded(args):
     item0 = (rng.standard_normal((n_pid, 128)) * 1e-4).astype(np.float32)
     lo_d = mlp_layout(n_uid, n_pid, D, (128, 128, 128), (256, 128, 64), False)
     dense0 = init_mlp_weights(lo_d, [7, 0])
-    t = ShardedJointTrainer(n_uid, n_pid, D, user0, item0, dense0, dropout=0.5, batch_size=1024, device="cuda:%d" % local_rank)
+    tower = "mlp"
+    if args.workload != "Amazon-13-sharded":      # config #5 proper: the MMOE / PLE sub-models over the sharded tables
+        from mamdr_b200.deep_mtl_ctr import MTLTopology, init_mtl_weights
+        from mamdr_b200.sharded import ShardedMTLTrainer
+        mc = load_config(args.workload)["model"]
+        tower = "ple" if "ple" in mc["name"] else "mmoe"
+        arch = dict(expert_hidden=tuple(mc["hidden_dim"]), tower_hidden=tuple(mc["tower_hidden_dim"]), gate_hidden=tuple(mc["gate_dnn_hidden_units"]),
+                    num_experts=mc.get("num_experts", 0), specific_expert_num=mc.get("specific_expert_num", 0),
+                    shared_expert_num=mc.get("shared_expert_num", 0))
+        topo_d = MTLTopology(tower, 4, 4, D, (128, 128, 128), emb_trainable=False, **arch)
+        t = ShardedMTLTrainer(tower, n_uid, n_pid, D, user0, item0, init_mtl_weights(topo_d.layout, [7, 0]), dropout=mc["dropout"], lr=1e-4,
+                              batch_size=1024, device="cuda:%d" % local_rank, **arch)
+    else:
+        t = ShardedJointTrainer(n_uid, n_pid, D, user0, item0, dense0, dropout=0.5, batch_size=1024, device="cuda:%d" % local_rank)
     g = torch.Generator(device="cuda").manual_seed(11)     # same Zipf-ish id stream on every rank
     mb = 30
     uid = (torch.rand(mb, 1024, device="cuda", generator=g) ** 3 * n_uid).to(torch.int32).clamp_(0, n_uid - 1)
@@ -378,7 +392,7 @@ def run_sharded(args):
         print(json.dumps({"metric": "joint-train samples/sec (Amazon-13 shape, row-sharded trainable tables)", "value": mb * 1024 / (msv * 1e-3),
                           "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": msv,
                           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                          "config": {"workload": "mlp joint steps, trainable tables row-sharded over %d rank(s), NCCL all-to-all, %d mini-batches of 1024 per step" % (world, mb)},
+                          "config": {"workload": "%s train steps, trainable tables row-sharded over %d rank(s), NCCL all-to-all, %d mini-batches of 1024 per step" % (tower, world, mb)},
                           "roofline": {"bound": "hbm", "achieved": alg * mb / (msv * 1e-3) / 1e9, "unit": "GB/s",
                                        "note": "aggregate table-sweep bytes (24 B per table element per mini-batch) over all ranks / step time"},
                           "us_per_minibatch": 1e3 * msv / mb}), flush=True)
@@ -588,7 +602,7 @@ def main():
         run_reference(args)
     elif args.workload in ("Amazon-6", "Amazon-13-mmoe", "Amazon-13-ple"):
         run_amazon(args)
-    elif args.workload == "Amazon-13-sharded":
+    elif args.workload.endswith("-sharded"):
         run_sharded(args)
     else:
         run_b200(args)

@@ -254,6 +254,11 @@ int mamdr_mtl_eval_step(mamdr_ctx* ctx, const mamdr_mtl_desc* desc, const mamdr_
 /* views of the de-duplicated sparse gradients left by the last train step of `rows` rows (table 0 = user, 1 = item) */
 int mamdr_mtl_sparse_grads(const mamdr_mtl_desc* desc, int32_t rows, void* ws_dev, int32_t table,
                            const int32_t** uniq_ids_dev, const float** uniq_rows_dev, const int32_t** n_uniq_dev);
+/* Gradient rows of the gathered user / item embeddings of the LAST mamdr_mtl_train_step of sub-model `dom` (`rows` rows):
+ * dX_out[r, 0:du+di].  For tables that live outside the arena -- row-sharded across GPUs (mamdr_b200/sharded.py); the
+ * counterpart of mamdr_mlp_input_grads. */
+int mamdr_mtl_input_grads(mamdr_ctx* ctx, const mamdr_mtl_desc* desc, const mamdr_mtl_domain* dom, int32_t rows,
+                          const float* params_dev, void* ws_dev, size_t ws_bytes, float* dX_out_dev, mamdr_stream stream);
 /* TF ApplyAdam over n_ranges (<= 16) arena ranges [begin, begin + len) (floats, multiples of 4) of one arena; the beta
  * powers / step advance once.  begin / len are HOST arrays. */
 int mamdr_adam_ranges_step(mamdr_ctx* ctx, float* params_dev, float* m_dev, float* v_dev, const float* grads_dev,

@@ -145,6 +145,7 @@ SIGNATURES = {
     "mamdr_mtl_eval_step": (C.c_int, [_P, C.POINTER(MtlDesc), C.POINTER(MtlDomain), C.POINTER(Batch), _P, _P, _P, _P, _SZ, _P,
                                       _P, _P, _P, _I32, _P]),
     "mamdr_mtl_sparse_grads": (C.c_int, [C.POINTER(MtlDesc), _I32, _P, _I32, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
+    "mamdr_mtl_input_grads": (C.c_int, [_P, C.POINTER(MtlDesc), C.POINTER(MtlDomain), _I32, _P, _P, _SZ, _P, _P]),
     "mamdr_adam_ranges_step": (C.c_int, [_P, _P, _P, _P, _P, C.POINTER(_I64), C.POINTER(_I64), _I32, _P, _F, _F, _F, _F, _P]),
     "mamdr_program_begin": (C.c_int, [_P]),
     "mamdr_program_end": (C.c_int, [_P, _P, _SZ, C.POINTER(_I32), _P]),

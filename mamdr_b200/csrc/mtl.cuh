@@ -95,7 +95,7 @@ inline Ws ws_layout(const mamdr_mtl_desc& d, int B) {
     w.dsum = take((size_t)d.emb_dim[2] * 4);
     for (int l = 0; l < Lg; ++l) single = std::max(single, tile_area(B, d.gate_hidden[l]) * kSmallSplit);
     for (int l = 0; l < Lt; ++l) single = std::max(single, tile_area(B, d.tower_hidden[l]) * kSmallSplit);
-    const size_t dx_part = tile_area(B, w.dx_ld) * (d.k + 1);   // one partial tile set per segment of the dX GEMM
+    const size_t dx_part = tile_area(B, in) * (d.k + 1);        // one partial tile set per segment of the dX GEMM
     w.partials = take(std::max(std::max(grouped, single), dx_part) * 4);
     if (d.emb_trainable) {
         for (int t = 0; t < 2; ++t) {
@@ -518,6 +518,41 @@ extern "C" int mamdr_mtl_sparse_grads(const mamdr_mtl_desc* desc, int32_t rows, 
     return MAMDR_OK;
 }
 
+// dX[:, c0:c0+width] = sum_j dZe0_j . We0_j[c0:c0+width, :]^T (+ the gate's): ONE launch, segments added in gate-column order
+static int mtl_input_grad_gemm(mamdr_ctx* ctx, const mamdr_mtl_desc* d, const mamdr_mtl_domain* dm, int rows, const float* params,
+                               unsigned char* ws, const mtl::Ws& w, int c0, int width, float* out, cudaStream_t st) {
+    simt::SegmentArgs sa;
+    memset(&sa, 0, sizeof(sa));
+    sa.n = d->k + (d->has_gate ? 1 : 0);
+    for (int j = 0; j < sa.n; ++j) {
+        const bool gate = j == d->k;
+        const int Kd = gate ? d->gate_hidden[0] : d->expert_hidden[0];
+        sa.A[j] = (const float*)(ws + (gate ? w.dZg[0] : w.dZe[j][0]));
+        sa.B[j] = params + (gate ? dm->off_gate_kernel[0] : dm->off_expert_kernel[j][0]) + (int64_t)c0 * Kd;
+        sa.K[j] = Kd;
+    }
+    StoreEpilogue epi{out, width};
+    const dim3 grid((width + simt::BN - 1) / simt::BN, (rows + simt::BM - 1) / simt::BM, sa.n);
+    MAMDR_REQUIRE(ctx, (int)(grid.x * grid.y) <= mlpws::kMaxTiles, MAMDR_E_UNSUPPORTED, "batch too large for the ticket table");
+    simt::gemm_ksegments_kernel<StoreEpilogue><<<grid, simt::THREADS, 0, st>>>(sa, rows, width, (float*)(ws + w.partials),
+                                                                               (unsigned int*)(ws + w.tickets), epi);
+    MAMDR_LAUNCH_OK(ctx);
+    return MAMDR_OK;
+}
+
+// Gradient rows of the gathered user / item embeddings of the LAST mamdr_mtl_train_step of sub-model `dm` (`rows` rows):
+// for tables that live outside the arena (row-sharded across GPUs, mamdr_b200/sharded.py).
+extern "C" int mamdr_mtl_input_grads(mamdr_ctx* ctx, const mamdr_mtl_desc* d, const mamdr_mtl_domain* dm, int32_t rows, const float* params,
+                                     void* ws_, size_t ws_bytes, float* dX_out, mamdr_stream stream) {
+    MAMDR_REQUIRE(ctx, ctx && d && dm && params && ws_ && dX_out, MAMDR_E_INVALID, "NULL pointer");
+    MAMDR_REQUIRE(ctx, rows >= 1 && aligned16(dX_out) && aligned16(ws_) && aligned16(params), MAMDR_E_INVALID, "bad rows / misaligned pointer");
+    MAMDR_REQUIRE(ctx, ctx->prog == nullptr, MAMDR_E_INVALID, "per-mini-batch calls cannot be recorded into a program");
+    MAMDR_REQUIRE(ctx, d->k >= 1 && d->k <= mtl::kMaxK && d->n_expert_layers >= 1 && d->n_expert_layers <= MAMDR_MAX_LAYERS, MAMDR_E_INVALID, "bad descriptor");
+    const mtl::Ws w = mtl::ws_layout(*d, rows);
+    MAMDR_REQUIRE(ctx, ws_bytes >= w.total, MAMDR_E_WORKSPACE, "workspace too small");
+    return mtl_input_grad_gemm(ctx, d, dm, rows, params, (unsigned char*)ws_, w, 0, d->emb_dim[0] + d->emb_dim[1], dX_out, (cudaStream_t)stream);
+}
+
 extern "C" int mamdr_mtl_eval_step(mamdr_ctx* ctx, const mamdr_mtl_desc* d, const mamdr_mtl_domain* dm, const mamdr_batch* b, const float* ut,
                                    const float* it, const float* params, void* ws_, size_t ws_bytes, float* loss, float* probs,
                                    float* auc_acc, const float* thr, int32_t T, mamdr_stream stream) {
@@ -614,25 +649,9 @@ extern "C" int mamdr_mtl_train_step(mamdr_ctx* ctx, const mamdr_mtl_desc* d, con
         rc = dh_layer(ctx, 1, A, W, Hp, out, inv_keep, rows, d->gate_hidden[l], d->gate_hidden[l - 1], (float*)(ws + w.partials), (unsigned int*)(ws + w.tickets), st);
         if (rc) return rc;
     }
-    // ---- dX[:, c0:in] = sum_j dZe0_j . We0_j[c0:in, :]^T (+ the gate's): ONE launch, segments accumulated in gate-column order
-    {
-        simt::SegmentArgs sa;
-        memset(&sa, 0, sizeof(sa));
-        sa.n = k + (d->has_gate ? 1 : 0);
-        for (int j = 0; j < sa.n; ++j) {
-            const bool gate = j == k;
-            const int Kd = gate ? d->gate_hidden[0] : d->expert_hidden[0];
-            sa.A[j] = (const float*)(ws + (gate ? w.dZg[0] : w.dZe[j][0]));
-            sa.B[j] = params + (gate ? dm->off_gate_kernel[0] : dm->off_expert_kernel[j][0]) + (int64_t)w.dx_c0 * Kd;
-            sa.K[j] = Kd;
-        }
-        StoreEpilogue epi{(float*)(ws + w.dX), w.dx_ld};
-        const dim3 grid((w.dx_ld + simt::BN - 1) / simt::BN, (rows + simt::BM - 1) / simt::BM, sa.n);
-        MAMDR_REQUIRE(ctx, (int)(grid.x * grid.y) <= kMaxTiles, MAMDR_E_UNSUPPORTED, "batch too large for the ticket table");
-        simt::gemm_ksegments_kernel<StoreEpilogue><<<grid, simt::THREADS, 0, st>>>(sa, rows, w.dx_ld, (float*)(ws + w.partials),
-                                                                                   (unsigned int*)(ws + w.tickets), epi);
-        MAMDR_LAUNCH_OK(ctx);
-    }
+    // ---- dX[:, c0:in] = sum_j dZe0_j . We0_j[c0:in, :]^T (+ the gate's): ONE launch, segments added in gate-column order
+    rc = mtl_input_grad_gemm(ctx, d, dm, rows, params, ws, w, w.dx_c0, w.dx_ld, (float*)(ws + w.dX), st);
+    if (rc) return rc;
     // ---- kernels: dW = H^T . dZ
     {
         float* gW[kMaxK];

@@ -209,3 +209,139 @@ class ShardedJointTrainer(object):
 
     def dense_weights(self):
         return self.model.layout.unpack(self.model.params.cpu().numpy())
+
+
+class ShardedMTLTrainer(object):
+    """BASELINE config #5 end to end: DomainNegotiation (``model_zoo/domain_negotiation.py:18-123``) over an MMOE / PLE /
+    SharedBottom tower (``DeepMTLCTR/deep_mtl_ctr.py:21-66``) whose trainable user / item tables are row-sharded over the
+    ranks.  One instance per rank.  A Keras train step of sub-model t on a global batch: all-to-all(ids) -> owners gather ->
+    all-to-all(rows) -> ``mamdr_mtl_train_step`` on this rank's slice -> ``mamdr_mtl_input_grads`` -> all-to-all(gradient
+    rows x B_r / B) -> owners de-duplicate + fused l2 / Adam sweep of their shard; the gradients of sub-model t's two arena
+    spans take one all-reduce each and ``mamdr_adam_ranges_step`` runs on every rank (replicas stay bit-identical).
+    theta of the DN outer update is kept like the model: dense arena replicated, one theta shard per table shard."""
+
+    def __init__(self, kind, n_uid, n_pid, n_domain, user_init, item_init, dense_init, emb_dim=(128, 128, 128), expert_hidden=(256, 128),
+                 tower_hidden=(64,), gate_hidden=(64,), num_experts=0, specific_expert_num=0, shared_expert_num=0, dropout=0.0,
+                 lr=1e-4, l2_emb=1e-5, batch_size=1024, device="cuda:0"):
+        from .deep_mtl_ctr import MTLModel, MTLTopology
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.device = torch.device(device)
+        self.batch_size = int(batch_size)
+        bl = (self.batch_size + self.world - 1) // self.world
+        self.max_local = bl
+        # the tower runs in frozen-table mode on the rows received for this rank's slice of the batch
+        topo = MTLTopology(kind, bl, bl, n_domain, emb_dim, expert_hidden, tower_hidden, gate_hidden, num_experts=num_experts,
+                           specific_expert_num=specific_expert_num, shared_expert_num=shared_expert_num, emb_trainable=False)
+        self.model = MTLModel(topo, dense_init, user_table=np.zeros((bl, emb_dim[0]), dtype=np.float32),
+                              item_table=np.zeros((bl, emb_dim[1]), dtype=np.float32), dropout=dropout, l2_emb=l2_emb, lr=lr,
+                              max_batch=bl, device=device, use_graphs=False)
+        m = self.model
+        m.desc.frozen_reg = 0.0
+        self.users = ShardedTable(m.ctx, user_init, self.rank, self.world, self.device, l2_emb, self.batch_size)
+        self.items = ShardedTable(m.ctx, item_init, self.rank, self.world, self.device, l2_emb, self.batch_size)
+        self.arange = torch.arange(bl, dtype=torch.int32, device=self.device)
+        self.dX = torch.zeros(bl, emb_dim[0] + emb_dim[1], dtype=torch.float32, device=self.device)
+        self.loss_local = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.loss_tab = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.theta = None
+        self.comm_bytes = 0
+
+    _slice = ShardedJointTrainer._slice
+    _local_data = ShardedJointTrainer._local_data
+
+    def train_on_batch(self, uid, pid, label, domain):
+        """One Keras train step of sub-model `domain` on the GLOBAL batch (device columns, identical on every rank)."""
+        m = self.model
+        st = m.stream
+        t = int(domain)
+        n = int(uid.numel())
+        start, bl = self._slice(n)
+        u, p, y = uid[start:start + bl].contiguous(), pid[start:start + bl].contiguous(), label[start:start + bl].contiguous()
+        plan_u, plan_i = _Plan(u, self.world), _Plan(p, self.world)
+        rows_u, rows_i = self.users.fetch(plan_u, st), self.items.fetch(plan_i, st)
+        w = float(bl) / float(n)
+        self.loss_local.zero_()
+        self.loss_tab.zero_()
+        begin, length, n_spans = m.spans[t]
+        spans = [m.grads[int(begin[q]):int(begin[q]) + int(length[q])] for q in range(n_spans)]
+        if bl:
+            data = self._local_data(y, t, bl)
+            b = m._batch(data, 0, bl, False)
+            m.ctx.call("mamdr_mtl_train_step", C.byref(m.desc), C.byref(m.domains[t]), C.byref(b), _ptr(rows_u), _ptr(rows_i),
+                       _ptr(m.params), _ptr(m.grads), _ptr(m.ws), m.ws_bytes, _ptr(m.opt_state), _ptr(self.loss_local), None,
+                       _ptr(m.auc_acc), _ptr(m.thresholds), m.num_thresholds, st)
+            m.ctx.call("mamdr_mtl_input_grads", C.byref(m.desc), C.byref(m.domains[t]), bl, _ptr(m.params), _ptr(m.ws), m.ws_bytes,
+                       _ptr(self.dX), st)
+            m.ctx.launches += m.launches_per_train_step()
+            for g in spans:
+                g.mul_(w)
+            self.loss_local.mul_(w)
+            du = self.users.dim
+            gu, gi = (self.dX[:bl, :du] * w).contiguous(), (self.dX[:bl, du:] * w).contiguous()
+        else:
+            for g in spans:
+                g.zero_()
+            gu = torch.zeros(0, self.users.dim, dtype=torch.float32, device=self.device)
+            gi = torch.zeros(0, self.items.dim, dtype=torch.float32, device=self.device)
+        # tables first (they read the beta powers), then sub-model t's spans of the dense arena (that apply advances them)
+        self.users.apply(plan_u, gu, m.opt_state, m.lr, m.beta1, m.beta2, m.eps, self.loss_tab, st)
+        self.items.apply(plan_i, gi, m.opt_state, m.lr, m.beta1, m.beta2, m.eps, self.loss_tab, st)
+        for g in spans:
+            dist.all_reduce(g)
+        m.ctx.call("mamdr_adam_ranges_step", _ptr(m.params), _ptr(m.m), _ptr(m.v), _ptr(m.grads), begin, length, n_spans,
+                   _ptr(m.opt_state), m.lr, m.beta1, m.beta2, m.eps, st)
+        self.comm_bytes += 4 * sum(g.numel() for g in spans) + 2 * 4 * (plan_u.n + plan_i.n) * (1 + self.users.dim)
+        both = torch.cat([self.loss_local, self.loss_tab])
+        dist.all_reduce(both)
+        return both
+
+    train_pass = ShardedJointTrainer.train_pass
+
+    # ---- DomainNegotiation over the sharded model ------------------------------------------------------------------
+    def dn_prepare(self):
+        """domain_negotiation.py:27-31 -- theta <- the model's weights; the optimizer slots start at zero."""
+        m = self.model
+        self.theta = {"dense": m.params.clone(), "user": self.users.table.clone(), "item": self.items.table.clone()}
+        m.reset_optimizer()
+        for tab in (self.users, self.items):
+            tab.m.zero_()
+            tab.v.zero_()
+
+    def _triples(self):
+        m = self.model
+        return ((self.theta["dense"], m.params), (self.theta["user"], self.users.table), (self.theta["item"], self.items.table))
+
+    def dn_meta_step(self, splits, sequence, orders, meta_lr, max_steps=0):
+        """One DN meta-step (domain_negotiation.py:41-88): model <- theta; one pass of sub-model idx per domain of the
+        (already shuffled) sequence, the single Adam threading through; theta += beta (model - theta); model <- theta."""
+        m = self.model
+        for theta, live in self._triples():
+            if live.numel():
+                m.copy_(live.view(-1), theta.view(-1))
+        losses = []
+        for idx, order in zip(sequence, orders):
+            if max_steps and max_steps > 0:
+                order = order[:max_steps * self.batch_size]
+            m.reset_states()
+            losses.append(self.train_pass(splits[idx], idx, order))
+        for theta, live in self._triples():
+            if live.numel():
+                m.ctx.call("mamdr_dn_update", _ptr(theta), _ptr(live), float(meta_lr), live.numel(), _ptr(live), m.stream)
+                m.ctx.launches += 1
+        return losses
+
+    def dense_weights(self):
+        return self.model.layout.unpack(self.model.params.cpu().numpy())
+
+    def theta_dense(self):
+        return self.model.layout.unpack(self.theta["dense"].cpu().numpy())
+
+    def theta_tables(self):
+        """Full theta tables (all-gather of the shards) -- tests / checkpoints."""
+        out = []
+        for tab, key in ((self.users, "user"), (self.items, "item")):
+            live = tab.table
+            tab.table = self.theta[key]
+            out.append(tab.full())
+            tab.table = live
+        return out
