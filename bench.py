@@ -361,9 +361,10 @@ def run_sharded(args):
                     shared_expert_num=mc.get("shared_expert_num", 0))
         topo_d = MTLTopology(tower, 4, 4, D, (128, 128, 128), emb_trainable=False, **arch)
         t = ShardedMTLTrainer(tower, n_uid, n_pid, D, user0, item0, init_mtl_weights(topo_d.layout, [7, 0]), dropout=mc["dropout"], lr=1e-4,
-                              batch_size=1024, device="cuda:%d" % local_rank, **arch)
+                              batch_size=1024, device="cuda:%d" % local_rank, use_graphs=args.graphs, **arch)
     else:
-        t = ShardedJointTrainer(n_uid, n_pid, D, user0, item0, dense0, dropout=0.5, batch_size=1024, device="cuda:%d" % local_rank)
+        t = ShardedJointTrainer(n_uid, n_pid, D, user0, item0, dense0, dropout=0.5, batch_size=1024, device="cuda:%d" % local_rank,
+                                use_graphs=args.graphs)
     g = torch.Generator(device="cuda").manual_seed(11)     # same Zipf-ish id stream on every rank
     mb = 30
     uid = (torch.rand(mb, 1024, device="cuda", generator=g) ** 3 * n_uid).to(torch.int32).clamp_(0, n_uid - 1)
@@ -372,7 +373,7 @@ def run_sharded(args):
 
     def step():
         for k in range(mb):
-            t.train_on_batch(uid[k], pid[k], lab[k], k % D)
+            t.step(uid[k], pid[k], lab[k], k % D)
     for _ in range(max(args.warmup, 1)):
         step()
     dist.barrier()
@@ -392,7 +393,7 @@ def run_sharded(args):
         print(json.dumps({"metric": "joint-train samples/sec (Amazon-13 shape, row-sharded trainable tables)", "value": mb * 1024 / (msv * 1e-3),
                           "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": msv,
                           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                          "config": {"workload": "%s train steps, trainable tables row-sharded over %d rank(s), NCCL all-to-all, %d mini-batches of 1024 per step" % (tower, world, mb)},
+                          "config": {"workload": "%s train steps, trainable tables row-sharded over %d rank(s), NCCL all-to-all, %d mini-batches of 1024 per step%s" % (tower, world, mb, ", one CUDA graph per (sub-model, rows) incl. the collectives" if args.graphs else "")},
                           "roofline": {"bound": "hbm", "achieved": alg * mb / (msv * 1e-3) / 1e9, "unit": "GB/s",
                                        "note": "aggregate table-sweep bytes (24 B per table element per mini-batch) over all ranks / step time"},
                           "us_per_minibatch": 1e3 * msv / mb}), flush=True)
@@ -596,6 +597,8 @@ def main():
     ap.add_argument("--precision", default=None, choices=[None, "fp32", "tf32", "tf32x3"],
                     help="tower GEMM mode (default tf32x3: tcgen05 with fp32-equivalent products)")
     ap.add_argument("--no-micro", action="store_true")
+    ap.add_argument("--graphs", action="store_true", help="sharded workloads: replay each step from a CUDA graph that includes the "
+                    "NCCL collectives (opt-in: measured 1.7x at 2 GPUs, but a capture hung on this stack for two other shapes)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

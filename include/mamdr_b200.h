@@ -69,7 +69,8 @@ int mamdr_gather_f32(mamdr_ctx* ctx, const float* table_dev, int64_t rows, int32
  * unsorted_segment_sum in TF's optimizer).
  * uniq_ids = ascending unique ids (bit-exact); uniq_rows[k] = sum of grad rows whose id ==
  * uniq_ids[k], added sequentially in batch order (== numpy add.at order, deterministic).
- * n <= mamdr_scatter_max_n(); *n_uniq_dev receives the count (device int32). */
+ * n <= mamdr_scatter_max_n(); *n_uniq_dev receives the count (device int32).  Negative ids are padding and are
+ * skipped together with their rows (fixed-capacity exchange buffers of the row-sharded tables). */
 int64_t mamdr_scatter_max_n(void);
 size_t  mamdr_scatter_workspace_bytes(int64_t n);
 int mamdr_scatter_dedup_f32(mamdr_ctx* ctx, const int32_t* ids_dev, const float* grad_rows_dev,

@@ -27,8 +27,11 @@ __global__ void __launch_bounds__(kSortThreads) sort_unique_kernel(const __grid_
     int32_t* __restrict__ seg_start = J.seg_start;
     const int n = a.n, npow2 = a.npow2;
     const int tid = threadIdx.x;
+    __shared__ int n_valid;
+    if (tid == 0) n_valid = 0;
+    // negative ids are padding (fixed-capacity all-to-all buffers of the row-sharded tables): they sort behind every real id
     for (int i = tid; i < npow2; i += kSortThreads)
-        keys[i] = i < n ? (((unsigned long long)(uint32_t)ids[i]) << 32) | (uint32_t)i : ~0ull;
+        keys[i] = (i < n && ids[i] >= 0) ? (((unsigned long long)(uint32_t)ids[i]) << 32) | (uint32_t)i : ~0ull;
     __syncthreads();
     for (int k = 2; k <= npow2; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
@@ -48,9 +51,11 @@ __global__ void __launch_bounds__(kSortThreads) sort_unique_kernel(const __grid_
     const int beg = tid * per, end = min(n, beg + per);
     int cnt = 0;
     for (int i = beg; i < end; ++i) {
+        if (keys[i] == ~0ull) break;
         const uint32_t id = (uint32_t)(keys[i] >> 32);
         const bool head = (i == 0) || ((uint32_t)(keys[i - 1] >> 32) != id);
         cnt += head ? 1 : 0;
+        if (i + 1 == n || keys[i + 1] == ~0ull) n_valid = i + 1;   // exactly one thread sees the last real entry
     }
     scan_part[tid] = cnt;
     __syncthreads();
@@ -63,6 +68,7 @@ __global__ void __launch_bounds__(kSortThreads) sort_unique_kernel(const __grid_
     }
     int seg = scan_part[tid] - cnt;  // exclusive prefix
     for (int i = beg; i < end; ++i) {
+        if (keys[i] == ~0ull) break;
         const uint32_t id = (uint32_t)(keys[i] >> 32);
         const bool head = (i == 0) || ((uint32_t)(keys[i - 1] >> 32) != id);
         if (head) {
@@ -75,7 +81,7 @@ __global__ void __launch_bounds__(kSortThreads) sort_unique_kernel(const __grid_
     if (tid == kSortThreads - 1) {
         const int total = scan_part[tid];
         J.n_uniq[0] = total;
-        seg_start[total] = n;
+        seg_start[total] = n_valid;
     }
 }
 

@@ -12,7 +12,9 @@ the mathematically identical data-parallel restatement of one Keras train step o
     (``mamdr_scatter_dedup_f32``) and run the fused l2 + non-lazy Adam sweep over their shard (``mamdr_adam_table_step``);
   * dense tower gradients: one all-reduce(sum) of the B_r / B weighted arenas, then ``mamdr_adam_step`` on every rank
     (replicas stay bit-identical: same reduced bits, same update).
-Index bucketing (sort by owner, bincount, inverse permutation) uses torch tensor ops: plumbing around the collectives.
+Index bucketing (sort by owner, bincount, inverse permutation) uses torch tensor ops: plumbing around the collectives.  The
+exchange buffers have a FIXED capacity (world x local-batch entries, -1 padded ids that the de-duplication skips), so every
+all-to-all has static, equal splits and a step never synchronises with the host.
 Dropout masks are indexed by the LOCAL row, so with dropout > 0 the masks are a different (equally distributed) draw than
 the single-GPU schedule; parity against the oracle is asserted with dropout = 0 (tests/test_gpu_sharded.py).
 """
@@ -27,25 +29,29 @@ from .engine import DomainData, MLPModel, _ptr
 
 
 class _Plan(object):
-    """Routing of one id column: who owns each row, in which order rows are sent, how many go where."""
+    """Routing of one id column with FIXED-capacity exchange buffers: every rank sends each owner a `cap`-entry block
+    (local row index, -1 = padding), so all split sizes are static -- no host synchronisation anywhere in a step."""
 
-    def __init__(self, ids, world):
-        self.n = int(ids.numel())
-        owner = (ids % world).to(torch.int64)
+    def __init__(self, ids, world, cap):
+        self.n, self.world, self.cap = int(ids.numel()), int(world), int(cap)
+        dev = ids.device
+        ids64 = ids.to(torch.int64)
+        owner = ids64 % world
         self.perm = torch.argsort(owner, stable=True)
-        self.send_idx = (ids[self.perm] // world).to(torch.int32).contiguous()
-        send_counts = torch.bincount(owner, minlength=world)
-        recv_counts = torch.empty_like(send_counts)
-        dist.all_to_all_single(recv_counts, send_counts)
-        self.send_splits = send_counts.tolist()     # host sync: the split sizes of the variable-length exchanges
-        self.recv_splits = recv_counts.tolist()
-        self.n_recv = int(sum(self.recv_splits))
-        self.recv_idx = torch.empty(self.n_recv, dtype=torch.int32, device=ids.device)
-        dist.all_to_all_single(self.recv_idx, self.send_idx, self.recv_splits, self.send_splits)
+        sorted_owner = owner[self.perm]
+        counts = (owner.unsqueeze(1) == torch.arange(world, device=dev).unsqueeze(0)).sum(0)   # bincount would sync the host
+        starts = torch.cumsum(counts, 0) - counts
+        pos = torch.arange(self.n, device=dev) - starts[sorted_owner]
+        self.flat = sorted_owner * cap + pos                       # slot of the perm-ordered rows in the exchange buffers
+        send = torch.full((world * cap,), -1, dtype=torch.int32, device=dev)
+        send[self.flat] = (ids64[self.perm] // world).to(torch.int32)
+        self.recv_idx = torch.empty_like(send)                     # [world * cap]: block r = the rows rank r asks of me
+        dist.all_to_all_single(self.recv_idx, send)
+        self.n_recv = world * cap
 
 
 class ShardedTable(object):
-    def __init__(self, ctx, full_init, rank, world, device, l2, max_recv):
+    def __init__(self, ctx, full_init, rank, world, device, l2, cap):
         self.ctx, self.rank, self.world, self.l2 = ctx, rank, world, float(l2)
         local = np.ascontiguousarray(full_init[rank::world], dtype=np.float32)
         self.rows, self.dim = int(local.shape[0]), int(local.shape[1])
@@ -54,37 +60,38 @@ class ShardedTable(object):
         self.slot = torch.full((max(self.rows, 1),), -1, dtype=torch.int32, device=device)
         self.ws_bytes = ctx.lib.mamdr_adam_table_workspace_bytes()
         self.ws = torch.zeros(self.ws_bytes, dtype=torch.uint8, device=device)
+        max_recv = int(world) * int(cap)
+        if max_recv > ctx.lib.mamdr_scatter_max_n():
+            raise ValueError("world x local batch = %d exceeds the de-duplication limit %d" % (max_recv, ctx.lib.mamdr_scatter_max_n()))
         self.sc_bytes = ctx.lib.mamdr_scatter_workspace_bytes(max_recv)
         self.sc_ws = torch.zeros(max(self.sc_bytes, 16), dtype=torch.uint8, device=device)
         self.uniq_ids = torch.zeros(max_recv, dtype=torch.int32, device=device)
         self.uniq_rows = torch.zeros(max_recv, self.dim, dtype=torch.float32, device=device)
         self.n_uniq = torch.zeros(4, dtype=torch.int32, device=device)
-        self.max_recv = int(max_recv)
+        self.max_recv = max_recv
+        f32 = dict(dtype=torch.float32, device=device)
+        self.got, self.back = torch.zeros(max_recv, self.dim, **f32), torch.zeros(max_recv, self.dim, **f32)
+        self.send, self.recv = torch.zeros(max_recv, self.dim, **f32), torch.zeros(max_recv, self.dim, **f32)
 
     def fetch(self, plan, stream):
-        """Rows of the ids behind ``plan`` in their original order: all-to-all(ids) was done by the plan."""
-        got = torch.empty(plan.n_recv, self.dim, dtype=torch.float32, device=self.table.device)
-        if plan.n_recv:
-            self.ctx.call("mamdr_gather_f32", _ptr(self.table), self.rows, self.dim, _ptr(plan.recv_idx), plan.n_recv, _ptr(got),
-                          self.dim, stream)
+        """Rows of the ids behind ``plan`` in their original order (the plan already exchanged the ids)."""
+        if self.rows:
+            self.ctx.call("mamdr_gather_f32", _ptr(self.table), self.rows, self.dim, _ptr(plan.recv_idx.clamp_min(0)), plan.n_recv,
+                          _ptr(self.got), self.dim, stream)
             self.ctx.launches += 1
-        back = torch.empty(plan.n, self.dim, dtype=torch.float32, device=self.table.device)
-        dist.all_to_all_single(back, got, [s for s in plan.send_splits], [s for s in plan.recv_splits])
-        out = torch.empty_like(back)
-        out[plan.perm] = back
+        dist.all_to_all_single(self.back, self.got)
+        out = torch.empty(plan.n, self.dim, dtype=torch.float32, device=self.table.device)
+        out[plan.perm] = self.back[plan.flat]
         return out
 
     def apply(self, plan, grad_rows, opt_state, lr, beta1, beta2, eps, loss_slot, stream):
         """Send the gradient rows to their owners, de-duplicate, fused l2 + Adam over the local shard."""
-        send = grad_rows[plan.perm].contiguous()
-        recv = torch.empty(plan.n_recv, self.dim, dtype=torch.float32, device=self.table.device)
-        dist.all_to_all_single(recv, send, [s for s in plan.recv_splits], [s for s in plan.send_splits])
-        if plan.n_recv > self.max_recv:
-            raise ValueError("more gradient rows received (%d) than the shard was sized for (%d)" % (plan.n_recv, self.max_recv))
-        if plan.n_recv:
-            self.ctx.call("mamdr_scatter_dedup_f32", _ptr(plan.recv_idx), _ptr(recv), self.dim, plan.n_recv, self.dim,
-                          _ptr(self.uniq_ids), _ptr(self.uniq_rows), _ptr(self.n_uniq), _ptr(self.sc_ws), self.sc_ws.numel(), stream)
-            self.ctx.launches += 2
+        self.send.zero_()
+        self.send[plan.flat] = grad_rows[plan.perm]
+        dist.all_to_all_single(self.recv, self.send)
+        self.ctx.call("mamdr_scatter_dedup_f32", _ptr(plan.recv_idx), _ptr(self.recv), self.dim, plan.n_recv, self.dim,
+                      _ptr(self.uniq_ids), _ptr(self.uniq_rows), _ptr(self.n_uniq), _ptr(self.sc_ws), self.sc_ws.numel(), stream)
+        self.ctx.launches += 2
         if self.rows:
             self.ctx.call("mamdr_adam_table_step", _ptr(self.table), _ptr(self.m), _ptr(self.v), self.rows, self.dim,
                           _ptr(self.uniq_ids), _ptr(self.uniq_rows), _ptr(self.n_uniq), plan.n_recv, _ptr(self.slot), self.l2,
@@ -115,14 +122,61 @@ def _uneven_gather(parts, mine, sizes):
         p.copy_(b[:p.shape[0]])
 
 
-class ShardedJointTrainer(object):
+class _GraphedSteps(object):
+    """CUDA-graph replay of whole train steps, NCCL collectives included: with fixed-capacity exchange buffers every shape
+    in a step is static, so one graph per (sub-model, batch rows) is captured on first use and replayed afterwards -- the
+    ~100 host-side launches / collectives of a step collapse into one `cudaGraphLaunch`."""
+
+    def _init_graphs(self, use_graphs):
+        self.use_graphs = bool(use_graphs)
+        self._graphs = {}
+        bs = self.batch_size
+        self._in_uid = torch.zeros(bs, dtype=torch.int32, device=self.device)
+        self._in_pid = torch.zeros(bs, dtype=torch.int32, device=self.device)
+        self._in_lab = torch.zeros(bs, dtype=torch.float32, device=self.device)
+        if self.use_graphs:
+            # the communicator and every peer-to-peer / ring connection are established eagerly, before any capture (NCCL
+            # sets connections up lazily on first use; doing that inside a capture can dead-lock against a peer that is
+            # already replaying)
+            x = torch.zeros(4 * self.world, dtype=torch.float32, device=self.device)
+            y = torch.empty_like(x)
+            dist.all_to_all_single(y, x)
+            dist.all_reduce(x)
+            dist.barrier()
+            torch.cuda.synchronize(self.device)
+
+    def step(self, uid, pid, label, domain):
+        """`train_on_batch`, replayed from a CUDA graph when enabled.  Returns a fresh [2] loss tensor."""
+        if not self.use_graphs:
+            return self.train_on_batch(uid, pid, label, domain)
+        n = int(uid.numel())
+        self._in_uid[:n].copy_(uid)
+        self._in_pid[:n].copy_(pid)
+        self._in_lab[:n].copy_(label)
+        key = (int(domain), n)
+        entry = self._graphs.get(key)
+        if entry is None:
+            g = torch.cuda.CUDAGraph()
+            before = self.model.ctx.launches
+            torch.cuda.synchronize(self.device)
+            with torch.cuda.graph(g):
+                out = self.train_on_batch(self._in_uid[:n], self._in_pid[:n], self._in_lab[:n], domain)
+            entry = self._graphs[key] = (g, out, self.model.ctx.launches - before)
+            self.model.ctx.launches = before
+        entry[0].replay()
+        self.model.ctx.launches += entry[2]
+        return entry[1].clone()
+
+
+class ShardedJointTrainer(_GraphedSteps):
     """Joint `mlp` training (``DeepCTR.train``) with row-sharded trainable tables; one instance per rank."""
 
     def __init__(self, n_uid, n_pid, n_domain, user_init, item_init, dense_init, emb_dim=(128, 128, 128), hidden=(256, 128, 64),
-                 dropout=0.0, lr=1e-3, l2_emb=1e-5, batch_size=1024, device="cuda:0"):
+                 dropout=0.0, lr=1e-3, l2_emb=1e-5, batch_size=1024, device="cuda:0", use_graphs=False):
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.device = torch.device(device)
         self.batch_size = int(batch_size)
+        self._init_graphs(use_graphs)
         bl = (self.batch_size + self.world - 1) // self.world
         self.max_local = bl
         # the tower runs in frozen-table mode on the rows received for this rank's slice of the batch
@@ -134,8 +188,8 @@ class ShardedJointTrainer(object):
         m = self.model
         m.desc.frozen_reg = 0.0
         ctx = m.ctx
-        self.users = ShardedTable(ctx, user_init, self.rank, self.world, self.device, l2_emb, self.batch_size)
-        self.items = ShardedTable(ctx, item_init, self.rank, self.world, self.device, l2_emb, self.batch_size)
+        self.users = ShardedTable(ctx, user_init, self.rank, self.world, self.device, l2_emb, bl)
+        self.items = ShardedTable(ctx, item_init, self.rank, self.world, self.device, l2_emb, bl)
         self.arange = torch.arange(bl, dtype=torch.int32, device=self.device)
         self.dX = torch.zeros(bl, emb_dim[0] + emb_dim[1], dtype=torch.float32, device=self.device)
         self.loss_local = torch.zeros(1, dtype=torch.float32, device=self.device)
@@ -162,7 +216,7 @@ class ShardedJointTrainer(object):
         n = int(uid.numel())
         start, bl = self._slice(n)
         u, p, y = uid[start:start + bl].contiguous(), pid[start:start + bl].contiguous(), label[start:start + bl].contiguous()
-        plan_u, plan_i = _Plan(u, self.world), _Plan(p, self.world)
+        plan_u, plan_i = _Plan(u, self.world, self.max_local), _Plan(p, self.world, self.max_local)
         rows_u, rows_i = self.users.fetch(plan_u, st), self.items.fetch(plan_i, st)
         w = float(bl) / float(n)                         # this rank's share of the batch mean
         self.loss_local.zero_()
@@ -204,14 +258,14 @@ class ShardedJointTrainer(object):
         losses = []
         for s in range(0, len(order), self.batch_size):
             e = min(len(order), s + self.batch_size)
-            losses.append(self.train_on_batch(uid[s:e], pid[s:e], lab[s:e], domain))
+            losses.append(self.step(uid[s:e], pid[s:e], lab[s:e], domain))
         return losses
 
     def dense_weights(self):
         return self.model.layout.unpack(self.model.params.cpu().numpy())
 
 
-class ShardedMTLTrainer(object):
+class ShardedMTLTrainer(_GraphedSteps):
     """BASELINE config #5 end to end: DomainNegotiation (``model_zoo/domain_negotiation.py:18-123``) over an MMOE / PLE /
     SharedBottom tower (``DeepMTLCTR/deep_mtl_ctr.py:21-66``) whose trainable user / item tables are row-sharded over the
     ranks.  One instance per rank.  A Keras train step of sub-model t on a global batch: all-to-all(ids) -> owners gather ->
@@ -222,11 +276,12 @@ class ShardedMTLTrainer(object):
 
     def __init__(self, kind, n_uid, n_pid, n_domain, user_init, item_init, dense_init, emb_dim=(128, 128, 128), expert_hidden=(256, 128),
                  tower_hidden=(64,), gate_hidden=(64,), num_experts=0, specific_expert_num=0, shared_expert_num=0, dropout=0.0,
-                 lr=1e-4, l2_emb=1e-5, batch_size=1024, device="cuda:0"):
+                 lr=1e-4, l2_emb=1e-5, batch_size=1024, device="cuda:0", use_graphs=False):
         from .deep_mtl_ctr import MTLModel, MTLTopology
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.device = torch.device(device)
         self.batch_size = int(batch_size)
+        self._init_graphs(use_graphs)
         bl = (self.batch_size + self.world - 1) // self.world
         self.max_local = bl
         # the tower runs in frozen-table mode on the rows received for this rank's slice of the batch
@@ -237,8 +292,8 @@ class ShardedMTLTrainer(object):
                               max_batch=bl, device=device, use_graphs=False)
         m = self.model
         m.desc.frozen_reg = 0.0
-        self.users = ShardedTable(m.ctx, user_init, self.rank, self.world, self.device, l2_emb, self.batch_size)
-        self.items = ShardedTable(m.ctx, item_init, self.rank, self.world, self.device, l2_emb, self.batch_size)
+        self.users = ShardedTable(m.ctx, user_init, self.rank, self.world, self.device, l2_emb, bl)
+        self.items = ShardedTable(m.ctx, item_init, self.rank, self.world, self.device, l2_emb, bl)
         self.arange = torch.arange(bl, dtype=torch.int32, device=self.device)
         self.dX = torch.zeros(bl, emb_dim[0] + emb_dim[1], dtype=torch.float32, device=self.device)
         self.loss_local = torch.zeros(1, dtype=torch.float32, device=self.device)
@@ -257,7 +312,7 @@ class ShardedMTLTrainer(object):
         n = int(uid.numel())
         start, bl = self._slice(n)
         u, p, y = uid[start:start + bl].contiguous(), pid[start:start + bl].contiguous(), label[start:start + bl].contiguous()
-        plan_u, plan_i = _Plan(u, self.world), _Plan(p, self.world)
+        plan_u, plan_i = _Plan(u, self.world, self.max_local), _Plan(p, self.world, self.max_local)
         rows_u, rows_i = self.users.fetch(plan_u, st), self.items.fetch(plan_i, st)
         w = float(bl) / float(n)
         self.loss_local.zero_()

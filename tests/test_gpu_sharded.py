@@ -63,6 +63,7 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
+@pytest.mark.timeout(240)
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="row-sharded tables need 2 GPUs (NCCL all-to-all)")
 def test_row_sharded_tables_two_ranks_match_oracle(tmp_path):
     import torch.multiprocessing as mp
@@ -139,6 +140,7 @@ def _mtl_worker(rank, world, port, out_dir, kind):
     dist.destroy_process_group()
 
 
+@pytest.mark.timeout(240)
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="row-sharded tables need 2 GPUs (NCCL all-to-all)")
 @pytest.mark.parametrize("kind", ["mmoe", "ple"])
 def test_sharded_mtl_domain_negotiation_two_ranks_match_oracle(tmp_path, kind):

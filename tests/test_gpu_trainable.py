@@ -73,8 +73,19 @@ def test_joint_training_epoch_matches_oracle():
     c = _amazon(scale=0.001)
     base = _build(c)
     m = base.model
+    # Free-running from the raw init (tables N(0, 1e-4^2), zero biases) every pre-activation sits within ~1e-3 of zero and
+    # Adam's first steps amplify last-bit differences into ReLU-gate flips: the outcome then depends on the summation order
+    # of the ORACLE's CPU GEMMs, i.e. on the host's core count (seen: within 1e-4 on the 1-GPU box, 1.5e-3 on the 2-GPU box, same GPU code).  The
+    # trajectory test starts from a lifted state (as tests/test_gpu_sharded.py does); the raw init is covered step by step
+    # in test_trainable_step_matches_oracle and tests/test_gpu_mtl.py::test_mtl_trajectory_step_by_step.
+    rng = np.random.default_rng(0)
+    w = _weights(m)
+    for i, n in enumerate(m.layout.names):
+        if n.endswith('_emb') or n.startswith('bias'):
+            w[i] = (rng.standard_normal(w[i].shape) * 0.05).astype(np.float32)
+    m.params.copy_(torch.from_numpy(m.layout.pack(w)))
     m.reset_optimizer()
-    o = _oracle_for(base)
+    o = _oracle_for(base, weights=w)
     seed = c['dataset']['seed']
     data = base.dataset.host_splits()
     base.schedule = Schedule(seed)
