@@ -101,3 +101,63 @@ def test_sharded_oracle_equals_sequential_oracle_at_world1():
     for d in outs[0].domain_weights:
         for a, b in zip(outs[0].domain_weights[d], outs[1].domain_weights[d]):
             assert np.array_equal(a, b)
+
+
+# ---- row-sharded tables: the fixed-capacity routing plan of mamdr_b200/sharded.py (host logic; the kernels need a GPU) ----
+def _routing_worker(rank, world, port, out_dir):
+    os.environ.update({"MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port), "RANK": str(rank), "WORLD_SIZE": str(world)})
+    dist.init_process_group("gloo")
+    from mamdr_b200.sharded import _Plan
+    n_rows, dim, cap = 37, 4, 16
+    g = torch.Generator().manual_seed(7)
+    full = torch.randn(n_rows, dim, generator=g)                     # the "true" table, same on both ranks
+    local = full[rank::world].contiguous()                           # row r lives on rank r % world at index r // world
+    gi = torch.Generator().manual_seed(100 + rank)
+    n = cap - 3 * rank                                               # ragged slices: ranks hold different row counts
+    ids = torch.randint(0, n_rows, (n,), generator=gi, dtype=torch.int32)
+    ids[: n // 3] = ids[0]                                           # a hot id (duplicates) like the Zipf batches
+    plan = _Plan(ids, world, cap)
+    assert plan.recv_idx.numel() == world * cap and plan.n_recv == world * cap
+    valid = plan.recv_idx >= 0
+    assert int(valid.sum()) <= world * cap and bool((plan.recv_idx[valid] < local.shape[0]).all())
+    # fetch: owners gather (padding -> any row), equal-split all-to-all back, un-permute
+    got = local[plan.recv_idx.clamp_min(0).long()]
+    back = torch.empty_like(got)
+    dist.all_to_all_single(back, got)
+    out = torch.empty(n, dim)
+    out[plan.perm] = back[plan.flat]
+    assert torch.equal(out, full[ids.long()])
+    # apply: gradient rows travel to their owners aligned with recv_idx; padding rows are zero and carry id -1
+    grads = torch.randn(n, dim, generator=gi)
+    send = torch.zeros(world * cap, dim)
+    send[plan.flat] = grads[plan.perm]
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send)
+    assert bool((recv[~valid] == 0).all())
+    mine = torch.zeros_like(local)
+    mine.index_add_(0, plan.recv_idx[valid].long(), recv[valid])
+    # the truth: scatter-add of every rank's gradient rows into the full table, restricted to my rows
+    all_ids = [torch.empty(cap, dtype=torch.int32) for _ in range(world)]
+    all_g = [torch.empty(cap, dim) for _ in range(world)]
+    pad_ids = torch.full((cap,), -1, dtype=torch.int32)
+    pad_ids[:n] = ids
+    pad_g = torch.zeros(cap, dim)
+    pad_g[:n] = grads
+    dist.all_gather(all_ids, pad_ids)
+    dist.all_gather(all_g, pad_g)
+    truth = torch.zeros(n_rows, dim)
+    for i_, g_ in zip(all_ids, all_g):
+        ok = i_ >= 0
+        truth.index_add_(0, i_[ok].long(), g_[ok])
+    assert torch.allclose(mine, truth[rank::world], atol=1e-6)
+    torch.save({"ok": True}, os.path.join(out_dir, "routing%d.pt" % rank))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_fixed_capacity_routing_plan_world2_gloo(tmp_path):
+    """`_Plan`: ids -> owners with static, equal all-to-all splits (-1 padded), rows back in the original order, gradient rows
+    to their owners; checked against the unsharded table on two gloo ranks."""
+    port = _free_port()
+    mp.spawn(_routing_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(os.path.join(str(tmp_path), "routing0.pt")) and os.path.exists(os.path.join(str(tmp_path), "routing1.pt"))
