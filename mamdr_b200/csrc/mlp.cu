@@ -74,7 +74,7 @@ struct StoreEpilogue {  // plain store with leading dimension
 // One CTA of 1024 threads = 32 warps, warp per row (coalesced row reads, shuffle reduction);
 // all cross-row reductions are fixed-order => deterministic.
 constexpr int kHeadThreads = 1024;
-constexpr int kHeadMaxN = 512;  // widest last hidden layer supported by the head's smem partials
+// kHeadMaxN, kHeadCtas and the layout of the per-CTA partial records: mlp_ws.cuh
 
 struct HeadArgs {
     const float* HL;      // [b, n]
@@ -96,6 +96,9 @@ struct HeadArgs {
     float*       auc_acc; // optional [4, T]
     const float* thr;
     int          T;
+    float*       part;    // [gridDim.x][kHeadPartStride] per-CTA partials (dw, dg, bce, AUC bins), workspace
+    unsigned int* ticket; // last-CTA-done counter (zero between launches)
+    int          rows_per_cta;
 };
 
 __global__ void __launch_bounds__(kHeadThreads) head_kernel(HeadArgs a) {
@@ -128,14 +131,15 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(HeadArgs a) {
 #pragma unroll
     for (int j = 0; j < kHeadMaxN / 32; ++j) dwacc[j] = 0.f;
 
-    for (int r0 = 0; r0 < a.b; r0 += kHeadThreads) {
+    const int row_beg = blockIdx.x * a.rows_per_cta, row_end = min(a.b, row_beg + a.rows_per_cta);
+    for (int r0 = row_beg; r0 < row_end; r0 += kHeadThreads) {
         // ---- phase A: logits, one warp per row, four rows in flight (coalesced row reads, shuffle reduction)
         for (int i0 = 0; i0 < 32; i0 += 4) {
             float z[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const int r = r0 + warp + 32 * (i0 + q);
-                if (r < a.b) {
+                if (r < row_end) {
                     const float* h = a.HL + (int64_t)r * a.n;
 #pragma unroll
                     for (int j = 0; j < kHeadMaxN / 32; ++j) {
@@ -156,7 +160,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(HeadArgs a) {
         {
             const int r = r0 + tid;
             float dsv = 0.f;
-            if (r < a.b) {
+            if (r < row_end) {
                 const float s = sz[tid] + gbias;
                 const float p = 1.0f / (1.0f + expf(-s));
                 const float yv = a.y[r];
@@ -187,7 +191,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(HeadArgs a) {
 #pragma unroll 4
             for (int i = 0; i < 32; ++i) {
                 const int r = r0 + warp + 32 * i;
-                if (r < a.b) {
+                if (r < row_end) {
                     const float dsv = sz[warp + 32 * i];
                     const float* h = a.HL + (int64_t)r * a.n;
 #pragma unroll
@@ -211,7 +215,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(HeadArgs a) {
         bce_sum += __shfl_xor_sync(0xffffffffu, bce_sum, o);
         dg_sum += __shfl_xor_sync(0xffffffffu, dg_sum, o);
     }
-    // ---- fixed-order cross-warp reductions
+    // ---- fixed-order reductions inside the CTA, parked as this CTA's partial record
     if (lane == 0) { red_d[warp] = bce_sum; red_f[warp] = dg_sum; }
     if (a.train) {
 #pragma unroll
@@ -221,11 +225,44 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(HeadArgs a) {
         }
     }
     __syncthreads();
+    float* mine = a.part + (size_t)blockIdx.x * kHeadPartStride;
     if (a.train) {
         for (int c = tid; c < a.n; c += kHeadThreads) {
             float s = 0.f;
             for (int wv = 0; wv < 32; ++wv) s += dw_part[wv * a.n + c];
+            mine[c] = s;
+        }
+    }
+    if (tid == 0) {
+        double bs = 0.0;
+        float dg = 0.f;
+        for (int wv = 0; wv < 32; ++wv) { bs += red_d[wv]; dg += red_f[wv]; }
+        mine[kHeadPartDg] = dg;
+        *reinterpret_cast<double*>(mine + kHeadPartBce) = bs;
+    }
+    if (a.auc_acc)
+        for (int i = tid; i < 2 * T1; i += kHeadThreads) reinterpret_cast<int*>(mine + kHeadPartHist)[i] = hist[i];
+    // ---- the last CTA to arrive combines the records in CTA order
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) is_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const int G = gridDim.x;
+    if (a.train) {
+        for (int c = tid; c < a.n; c += kHeadThreads) {
+            float s = 0.f;
+            for (int g = 0; g < G; ++g) s += __ldcg(a.part + (size_t)g * kHeadPartStride + c);
             a.g_w[c] = s;
+        }
+    }
+    if (a.auc_acc) {
+        for (int i = tid; i < 2 * T1; i += kHeadThreads) {
+            int v = 0;
+            for (int g = 0; g < G; ++g) v += __ldcg(reinterpret_cast<const int*>(a.part + (size_t)g * kHeadPartStride + kHeadPartHist) + i);
+            hist[i] = v;
         }
     }
     // L2 penalty of the (always trainable) domain table: sum of squares in double, fixed order
@@ -239,9 +276,14 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(HeadArgs a) {
     if (tid == 0) {
         double bs = 0.0, sqs = 0.0;
         float dg = 0.f;
-        for (int wv = 0; wv < 32; ++wv) { bs += red_d[wv]; dg += red_f[wv]; sqs += sq_part[wv]; }
+        for (int g = 0; g < G; ++g) {
+            bs += __ldcg(reinterpret_cast<const double*>(a.part + (size_t)g * kHeadPartStride + kHeadPartBce));
+            dg += __ldcg(a.part + (size_t)g * kHeadPartStride + kHeadPartDg);
+        }
+        for (int wv = 0; wv < 32; ++wv) sqs += sq_part[wv];
         a.loss[0] = (float)(bs / (double)a.b + (double)a.frozen_reg + (double)a.l2_emb * sqs);
         if (a.train) a.g_g[0] = dg;
+        *a.ticket = 0;   // re-arm for the next launch
     }
     // ---- AUC: suffix sums of the two histograms -> tp/fp/fn/tn increments
     if (a.auc_acc) {
@@ -267,6 +309,18 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(HeadArgs a) {
             a.auc_acc[3 * a.T + tid] += (float)(nneg - fp);
         }
     }
+}
+
+// rows are split over up to kHeadCtas CTAs (>= 128 rows each); `part_ws` = head_part_bytes() of workspace, zero between launches
+inline void launch_head(HeadArgs a, void* part_ws, size_t smem, cudaStream_t st) {
+    int G = (a.b + 127) / 128;
+    if (G > kHeadCtas) G = kHeadCtas;
+    if (G < 1) G = 1;
+    a.rows_per_cta = (a.b + G - 1) / G;
+    G = (a.b + a.rows_per_cta - 1) / a.rows_per_cta;
+    a.part = (float*)part_ws;
+    a.ticket = (unsigned int*)((unsigned char*)part_ws + (size_t)kHeadCtas * kHeadPartStride * 4);
+    head_kernel<<<G, kHeadThreads, smem, st>>>(a);
 }
 
 size_t head_smem_bytes(int n, int T) {
@@ -424,7 +478,7 @@ int run_head(mamdr_ctx* ctx, const mamdr_mlp_desc* d, const mamdr_batch* b, cons
     a.T = auc_acc ? T : 0;
     const size_t smem = head_smem_bytes(n, a.T);
     MAMDR_REQUIRE(ctx, smem <= 100 * 1024, MAMDR_E_UNSUPPORTED, "head smem %zu too large", smem);
-    head_kernel<<<1, kHeadThreads, smem, st>>>(a);
+    launch_head(a, ws + w.hist, smem, st);
     MAMDR_LAUNCH_OK(ctx);
     return MAMDR_OK;
 }

@@ -7,6 +7,13 @@ namespace mlpws {
 
 constexpr int kMaxSplit = 16;
 constexpr int kMaxTiles = 4096;
+// the sigmoid-BCE head (mlp.cu) splits the rows of a mini-batch over up to kHeadCtas CTAs; each parks a partial record
+// (floats): dw[kHeadMaxN] | dg, pad | bce (double) | hist[2][1025] (int); a ticket follows the records
+constexpr int kHeadMaxN = 512;  // widest last hidden layer supported by the head's smem partials
+constexpr int kHeadCtas = 8;
+constexpr int kHeadPartDg = kHeadMaxN, kHeadPartBce = kHeadMaxN + 2, kHeadPartHist = kHeadMaxN + 4;
+constexpr int kHeadPartStride = kHeadMaxN + 4 + 2 * 1025 + 2;   // 2568 floats, a 16-byte multiple
+inline size_t head_part_bytes() { return (size_t)kHeadCtas * kHeadPartStride * 4 + 64; }
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -32,7 +39,7 @@ inline WsLayout ws_layout(const mamdr_mlp_desc& d, int B) {
     // bins are left zeroed by their consumers) come first: their offsets must not depend on B, which
     // changes on the ragged last batch of a pass
     w.tickets = take((size_t)kMaxTiles * 4);
-    w.hist = take((size_t)2 * 1025 * 4);
+    w.hist = take(head_part_bytes());   // per-CTA partial records of the head + its ticket (mlp.cu: kHeadCtas x kHeadPartStride floats)
     w.H[0] = take((size_t)B * in_dim * 4);
     for (int l = 0; l < d.n_layers; ++l) w.H[l + 1] = take((size_t)B * d.hidden[l] * 4);
     for (int l = 0; l < d.n_layers; ++l) w.dZ[l] = take((size_t)B * d.hidden[l] * 4);

@@ -48,7 +48,7 @@ inline Ws ws_layout(const mamdr_mtl_desc& d, int B) {
     };
     const int in = d.emb_dim[0] + d.emb_dim[1] + d.emb_dim[2];
     w.tickets = take((size_t)kMaxTiles * 4);
-    w.hist = take((size_t)2 * 1025 * 4);
+    w.hist = take(head_part_bytes());   // per-CTA partial records of the head + its ticket
     w.X = take((size_t)B * in * 4);
     w.y = take((size_t)B * 4);
     w.p = take((size_t)B * 4);
@@ -493,7 +493,7 @@ static int head(mamdr_ctx* ctx, const mamdr_mtl_desc* d, const mamdr_mtl_domain*
     a.loss = loss; a.auc_acc = auc_acc; a.thr = thr; a.T = auc_acc ? T : 0;
     const size_t smem = head_smem_bytes(nl, a.T);
     MAMDR_REQUIRE(ctx, smem <= 100 * 1024, MAMDR_E_UNSUPPORTED, "head smem %zu too large", smem);
-    head_kernel<<<1, kHeadThreads, smem, st>>>(a);
+    launch_head(a, ws + w.hist, smem, st);
     MAMDR_LAUNCH_OK(ctx);
     return MAMDR_OK;
 }
