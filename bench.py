@@ -309,8 +309,35 @@ def run_amazon(args):
     n_dense = sum(int(x) for x in model.spans[idx][1]) if mtl else model.params.numel() - n_table
     alg_bytes = 24.0 * n_table + 28.0 * n_dense
     hbm = peaks.get("hbm_gbs", 6650.0)
-    achieved = alg_bytes * mb / (ms * 1e-3) / 1e9
+    step_achieved = alg_bytes * mb / (ms * 1e-3) / 1e9
     shape = config["dataset"]["synthetic"]["shape"]
+    # the dominant kernel (fused table sweep), timed live on the model's own tables: CUDA events around 10 launches per table
+    import ctypes as C
+    from mamdr_b200.engine import _ptr
+    k_bytes, k_ms, k_n = 0.0, 0.0, 0
+    for off, n_rows, dim, slot in model._tables:
+        n_el = n_rows * dim
+        targs = (_ptr(model.params[off:off + n_el]), _ptr(model.m[off:off + n_el]), _ptr(model.v[off:off + n_el]), n_rows, dim, None, None,
+                 None, 0, _ptr(slot), model.l2_emb, _ptr(model.opt_state), model.lr, model.beta1, model.beta2, model.eps, None,
+                 _ptr(model.table_ws), model.table_ws_bytes, model.stream)
+        for _ in range(2):
+            model.ctx.call("mamdr_adam_table_step", *targs)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(10):
+            model.ctx.call("mamdr_adam_table_step", *targs)
+        b.record()
+        torch.cuda.synchronize()
+        k_ms += a.elapsed_time(b)
+        k_bytes += 10 * (24.0 * n_el + 4.0 * n_rows)
+        k_n += 10
+    achieved = k_bytes / (k_ms * 1e-3) / 1e9
+    traffic = None
+    if shape == "Amazon-13":
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_v5_table_sweep_ncu.json"))).get("dram_bytes_per_launch")
+        except Exception:
+            pass
     line = {"metric": "joint-train samples/sec (%s shape, trainable 128-d tables)" % shape, "value": mb * 1024 / (ms * 1e-3),
             "unit": "samples/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -318,9 +345,16 @@ def run_amazon(args):
                                    "%d mini-batches of 1024 per step" % (config["model"]["name"], idx, shape, model.n_uid, model.n_pid, mb),
                        "precision": "fp32", "l2": "tables + Adam slots (%.0f MB per sweep) are far beyond L2" % (12e-6 * n_table)},
             "gpu_launches": model.ctx.launches - launches0, "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
-                         "kernel": "adam_table_kernel (fused sparse merge + l2 + Adam over every table row) within the whole mini-batch",
-                         "alg_bytes_per_minibatch": alg_bytes, "us_per_minibatch": 1e3 * ms / mb}}
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic,
+                         "peak_source": "MEASURED_PEAKS.json (burst copy bandwidth)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                         "kernel": "adam_table_kernel (fused sparse merge + l2 + non-lazy Adam over every table row; 2 launches per mini-batch), "
+                                   "timed live on the model's tables",
+                         "alg_bytes_per_launch": k_bytes / k_n, "avg_launch_us": 1e3 * k_ms / k_n,
+                         "kernel_share_of_step": 2.0 * (k_ms / k_n) / (ms / mb),
+                         "step_achieved": step_achieved, "step_frac": step_achieved / hbm,
+                         "alg_bytes_per_minibatch": alg_bytes, "us_per_minibatch": 1e3 * ms / mb,
+                         "note": "achieved / frac = the table sweep alone (24 B per table element + 4 B per row); step_* = all algorithmic "
+                                 "bytes of a mini-batch (tables + 28 B per dense parameter that trains) over the whole step time"}}
     print(json.dumps(line), flush=True)
 
 
@@ -598,7 +632,7 @@ def main():
                     help="tower GEMM mode (default tf32x3: tcgen05 with fp32-equivalent products)")
     ap.add_argument("--no-micro", action="store_true")
     ap.add_argument("--graphs", action="store_true", help="sharded workloads: replay each step from a CUDA graph that includes the "
-                    "NCCL collectives (opt-in: measured 1.7x at 2 GPUs, but a capture hung on this stack for two other shapes)")
+                    "NCCL collectives (opt-in, unreliable: 1.7x at 2 GPUs for the mmoe tower, but the capture hangs for the mlp tower)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
