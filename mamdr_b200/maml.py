@@ -8,6 +8,8 @@ weight set is one device arena (``MetaWeights``) and get / set are device-side m
 """
 import ctypes as C
 
+import torch
+
 from .engine import _ptr
 
 
@@ -96,3 +98,71 @@ class MAML(object):
             raise NotImplementedError("meta_finetune_step > 0 is not used by any shipped DN / MAMDR config")
         self.log("Val Result: ")
         return self.val_and_test("val")
+
+    # ---- resume (what the reference lacks -- theta, theta_d[], the Adam state and the schedule are
+    # only in RAM there, base_model.py:177-181 saves the live Keras weights alone) ------------------------------------
+    _STATE_TENSORS = ("params", "m", "v", "opt_state", "pn_state")
+    _STATE_SEQS = ("meta_sequence", "train_sequence")
+
+    def save_state(self, path, epoch=0):
+        """Everything a meta-training run needs to continue bit-identically after `epoch`: the live model arena, the Adam
+        slots and beta powers, theta, every theta_d and best snapshot, the domain sequence, the schedule's RNG state and the
+        early-stop bookkeeping."""
+        m = self.model
+        base = self.base_model
+        sched = base.schedule
+        blob = {"epoch": int(epoch), "names": m.layout.names,
+                "model": {k: getattr(m, k).detach().cpu() for k in self._STATE_TENSORS if getattr(m, k, None) is not None},
+                "meta_weights": self.meta_weights.flat.cpu(),
+                "schedule": {"seed": sched.seed, "rng": sched._rng.getstate(), "pass": sched._pass},
+                "early_stop": {"counter": base.counter, "best_metric": base.best_metric, "early_stop": base.early_stop}}
+        for k in self._STATE_SEQS:
+            if hasattr(self, k):
+                blob[k] = list(getattr(self, k))
+        for k in ("domain_weights", "best_domain_weights"):
+            if getattr(self, k, None):
+                blob[k] = {d: w.flat.cpu() for d, w in getattr(self, k).items()}
+        if getattr(self, "best_shared_weights", None) is not None:
+            blob["best_shared_weights"] = self.best_shared_weights.flat.cpu()
+        if getattr(self, "accum_grads", None) is not None:
+            blob["accum_grads"] = self.accum_grads.cpu()
+        torch.save(blob, path)
+        return path
+
+    def load_state(self, path):
+        """Restore a `save_state` blob into a freshly built (and `prepare`d, where the wrapper has one) wrapper.  Returns the
+        epoch the state was saved after."""
+        blob = torch.load(path, map_location="cpu", weights_only=False)
+        m = self.model
+        base = self.base_model
+        if blob["names"] != m.layout.names:
+            raise ValueError("state layout mismatch")
+        if not hasattr(self, "model_meta_parms"):
+            self._get_model_meta_parms()
+        for k, v in blob["model"].items():
+            getattr(m, k).copy_(v)
+        if getattr(self, "meta_weights", None) is None:
+            self.meta_weights = self._get_meta_weights()
+        self.meta_weights.flat.copy_(blob["meta_weights"])
+        for k in self._STATE_SEQS:
+            if k in blob:
+                setattr(self, k, list(blob[k]))
+        for k in ("domain_weights", "best_domain_weights"):
+            if k in blob:
+                cur = getattr(self, k, None) or {}
+                for d, w in blob[k].items():
+                    if d not in cur:
+                        cur[d] = self.meta_weights.clone()
+                    cur[d].flat.copy_(w)
+                setattr(self, k, cur)
+        if "best_shared_weights" in blob:
+            self.best_shared_weights = self.meta_weights.clone()
+            self.best_shared_weights.flat.copy_(blob["best_shared_weights"])
+        if "accum_grads" in blob and getattr(self, "accum_grads", None) is not None:
+            self.accum_grads.copy_(blob["accum_grads"])
+        sched = base.schedule
+        sched.seed, sched._pass = blob["schedule"]["seed"], blob["schedule"]["pass"]
+        sched._rng.setstate(blob["schedule"]["rng"])
+        es = blob["early_stop"]
+        base.counter, base.best_metric, base.early_stop = es["counter"], es["best_metric"], es["early_stop"]
+        return blob["epoch"]

@@ -124,6 +124,41 @@ class OracleDN(object):
         return self.es.step(metric, keep)
 
 
+class OracleReptile(OracleDN):
+    """``Reptile.train`` with ``target_domain=-1`` (``model_zoo/reptile.py:45-99,127-142``): the model is reset to theta
+    before every domain; theta moves after every domain, or (``batch`` names) once per epoch by the summed deltas."""
+
+    def __init__(self, model, data, train_config, batch_size, schedule, name='mlp_meta_reptile'):
+        OracleDN.__init__(self, model, data, train_config, batch_size, schedule)
+        self.name = name
+        self.sequence = list(range(len(data['train'])))             # :36
+        self.accum = [np.zeros_like(w) for w in self.meta_weights]  # :31
+
+    def train_epoch(self):
+        tc = self.tc
+        beta = np.float32(tc['meta_learning_rate'])
+        self.sequence = self.schedule.shuffle_sequence(self.sequence)   # :46
+        for idx in self.sequence:
+            self.model.auc.reset_states()                            # :53-54
+            self.model.set_weights(self.meta_weights)                # :57
+            d = self.data['train'][idx]
+            order = self.schedule.batch_order(idx, len(d['uid']))
+            loss, auc, steps = train_pass(self.model, d, idx, order, self.bs, tc.get('meta_train_step', 0))
+            self.log.append((idx, loss, auc, steps))
+            new = self.model.get_weights()
+            if "batch" in self.name:                                 # :134-137
+                for var in range(len(new)):
+                    self.accum[var] += new[var] - self.meta_weights[var]
+            else:                                                    # :127-132
+                for var in range(len(new)):
+                    self.meta_weights[var] += (new[var] - self.meta_weights[var]) * beta
+        if "batch" in self.name:                                     # :139-142
+            for var in range(len(self.accum)):
+                self.meta_weights[var] += self.accum[var] * beta
+                self.accum[var] = np.zeros_like(self.accum[var])
+        self.model.set_weights(self.meta_weights)                    # :99
+
+
 class MetaSubset(object):
     """View of a model whose ``get_weights`` / ``set_weights`` only cover the meta parameters selected by
     ``MAML._get_model_meta_parms`` (``model_zoo/maml.py:153-179``: name-substring lists such as STAR's

@@ -54,7 +54,8 @@ def build(config, dataset=None):
         elif "mamdr" in name:
             model = MAMDR(model)
         elif "reptile" in name:
-            raise NotImplementedError("reptile is out of scope (baseline method, SURVEY.md 2.1 #7)")
+            from mamdr_b200.reptile import Reptile
+            model = Reptile(model)
         elif "mldg" in name:
             raise NotImplementedError("mldg is out of scope (baseline method, SURVEY.md 2.1 #8)")
         else:

@@ -234,3 +234,65 @@ def test_tf32_single_pass_is_close_but_not_fp32():
         errs[prec] = float(np.max(np.abs(probs.cpu().numpy() - p)))
     assert errs["tf32"] < 1e-3
     assert errs["tf32x3"] < 1e-6 and errs["tf32x3"] < errs["tf32"]
+
+
+@pytest.mark.parametrize("name,prec", [("mlp_meta_reptile", "fp32"), ("mlp_meta_reptile_batch", "fp32"), ("mlp_meta_reptile", "tf32x3")])
+def test_reptile_epochs_match_oracle(name, prec):
+    """`Reptile.train` (reptile.py:45-99,127-142) on the same kernels -- two epochs, theta vs the oracle."""
+    from oracle.meta import OracleReptile
+    c = make_config(**{"model.name": name, "dataset.synthetic.scale": 0.05, "b200.precision": prec})
+    wrapper = _build(c)
+    base = wrapper.base_model
+    seed = c['dataset']['seed']
+    wrapper.prepare()
+    o = _oracle_for(wrapper, weights=wrapper.meta_weights.numpy())
+    om = OracleReptile(o, base.dataset.host_splits(), c['train'], base.dataset.batch_size, Schedule(seed), name=name)
+    base.schedule = Schedule(seed)
+    for e in range(2):
+        wrapper.train_epoch(e)
+        om.train_epoch()
+    assert wrapper.train_sequence == om.sequence
+    for n_, a, b in zip(wrapper.model.layout.names, wrapper.meta_weights.numpy(), om.meta_weights):
+        assert rel_err(a, b) < _param_tol(prec, n_), (n_, rel_err(a, b))
+    for n_, a, b in zip(wrapper.model.layout.names, _weights(wrapper.model), om.meta_weights):
+        assert rel_err(a, b) < _param_tol(prec, n_), ("live model == theta", n_, rel_err(a, b))
+    step, b1, _ = wrapper.model.read_step()
+    assert step == om.model.adam.step and np.float32(b1) == om.model.adam.b1pow
+    _, a, _, da = wrapper.val_and_test("val")
+    _, oa, _, oda = om.val_and_test("val")
+    assert abs(a - oa) < 1e-3
+
+
+@pytest.mark.parametrize("name,prec", [("mlp_meta_mamdr_finetune", "fp32"), ("mlp_meta_domain_negotiation_finetune", "tf32x3"),
+                                       ("mlp_meta_reptile_batch", "fp32")])
+def test_save_state_resume_is_bit_identical(tmp_path, name, prec):
+    """SURVEY.md 8(f) row f3 (what the reference lacks): theta, theta_d[], the Adam slots / beta powers, the domain sequence
+    and the schedule's RNG survive a save / load -- a resumed run continues bit-identically."""
+    c = make_config(**{"model.name": name, "dataset.synthetic.scale": 0.03, "b200.precision": prec})
+
+    def fresh():
+        w = _build(c)
+        if hasattr(w, "prepare"):
+            w.prepare()
+        else:
+            w._get_model_meta_parms()
+            w.meta_weights = w._get_meta_weights()
+            w.model.reset_optimizer()
+            w.meta_sequence = w.build_meta_data_split()
+        w.base_model.schedule = Schedule(c['dataset']['seed'])
+        return w
+
+    a = fresh()
+    a.train_epoch(0)
+    path = a.save_state(str(tmp_path / "state.pt"), epoch=0)
+    a.train_epoch(1)
+    torch.cuda.synchronize()
+    b = fresh()
+    assert b.load_state(path) == 0
+    b.train_epoch(1)
+    torch.cuda.synchronize()
+    assert torch.equal(a.meta_weights.flat, b.meta_weights.flat) and torch.equal(a.model.params, b.model.params)
+    assert torch.equal(a.model.m, b.model.m) and torch.equal(a.model.v, b.model.v) and a.model.read_step() == b.model.read_step()
+    if getattr(a, "domain_weights", None):
+        for d in a.domain_weights:
+            assert torch.equal(a.domain_weights[d].flat, b.domain_weights[d].flat), d

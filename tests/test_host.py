@@ -158,8 +158,11 @@ def test_dispatch_rules(monkeypatch):
         assert type(run.build(c, dataset=ds)) is mt.DeepMTLCTR
     c["model"]["name"] = "ple_meta_domain_negotiation"
     assert type(run.build(c, dataset=ds)) is DomainNegotiation
-    for name in ("mlp_meta_reptile_finetune", "mlp_meta_mldg", "mlp_meta_maml_finetune", "mlp_pcgrad",
-                 "mlp_uncertainty_weight"):
+    from mamdr_b200.reptile import Reptile
+    for name in ("mlp_meta_reptile_finetune", "mlp_meta_reptile_batch"):
+        c["model"]["name"] = name
+        assert type(run.build(c, dataset=ds)) is Reptile
+    for name in ("mlp_meta_mldg", "mlp_meta_maml_finetune", "mlp_pcgrad", "mlp_uncertainty_weight"):
         c["model"]["name"] = name
         with pytest.raises(NotImplementedError):
             run.build(c, dataset=ds)

@@ -106,3 +106,47 @@ def test_dr_update_closed_form_plus_and_batch():
             for d in range(10):
                 for a, b in zip(mm.domain_weights[d], ref[d]):
                     np.testing.assert_allclose(a, b, rtol=0, atol=1e-9)
+
+
+def test_reptile_oracle_algebra():
+    """`Reptile.train` (reptile.py:45-99,127-142): the model restarts from theta for every domain; with one domain the
+    `batch` variant equals the per-domain one; with beta = 1 and one domain theta becomes the trained weights."""
+    import copy
+    from oracle.meta import OracleReptile
+
+    class Toy(object):   # a "model" whose pass adds (domain + 1) to every weight: makes the meta algebra visible
+        def __init__(self):
+            self.weights = [np.zeros(3, dtype=np.float32), np.ones((2, 2), dtype=np.float32)]
+
+            class A(object):
+                def reset_states(self):
+                    pass
+            self.auc = A()
+
+        def get_weights(self):
+            return [w.copy() for w in self.weights]
+
+        def set_weights(self, ws):
+            for a, b in zip(self.weights, ws):
+                a[...] = b
+
+        def train_on_batch(self, uid, pid, domain, label, optimizer='adam', sgd_lr=None):
+            for w in self.weights:
+                w += np.float32(domain + 1)
+            return 0.0, 0.5
+
+    data = {'train': {d: {'uid': np.zeros(5, np.int32), 'pid': np.zeros(5, np.int32), 'label': np.zeros(5, np.float32)} for d in range(3)}}
+    tc = {'meta_learning_rate': 0.5, 'patience': 3, 'meta_train_step': 0}
+    from mamdr_b200.schedule import Schedule
+    r = OracleReptile(Toy(), copy.deepcopy(data), tc, 8, Schedule(1), name='mlp_meta_reptile')
+    r.train_epoch()
+    # sequential: theta_k = theta_{k-1} + 0.5 * ((theta_{k-1} + (d_k + 1)) - theta_{k-1}) = theta_{k-1} + 0.5 (d_k + 1), any order
+    assert np.allclose(r.meta_weights[0], 0.5 * (1 + 2 + 3)) and np.allclose(r.meta_weights[1], 1 + 0.5 * 6)
+    assert np.array_equal(r.model.weights[0], r.meta_weights[0])          # model <- theta at the end (:99)
+    rb = OracleReptile(Toy(), copy.deepcopy(data), tc, 8, Schedule(1), name='mlp_meta_reptile_batch')
+    rb.train_epoch()
+    assert np.allclose(rb.meta_weights[0], 0.5 * 6) and all(not a.any() for a in rb.accum)   # summed deltas, cleared
+    one = {'train': {0: data['train'][0]}}
+    r1 = OracleReptile(Toy(), one, dict(tc, meta_learning_rate=1.0), 8, Schedule(1))
+    r1.train_epoch()
+    assert np.allclose(r1.meta_weights[0], 1.0)
