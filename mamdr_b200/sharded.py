@@ -245,7 +245,7 @@ class ShardedJointTrainer(_GraphedSteps):
         m.ctx.call("mamdr_adam_step", _ptr(m.params), _ptr(m.m), _ptr(m.v), _ptr(m.grads), m.params.numel(), _ptr(m.opt_state), m.lr,
                    m.beta1, m.beta2, m.eps, st)
         m.ctx.launches += 1
-        self.comm_bytes += 4 * m.grads.numel() + 2 * 4 * (plan_u.n + plan_i.n) * (1 + self.users.dim)
+        self.comm_bytes += 4 * m.grads.numel() + 4 * (plan_u.n_recv + plan_i.n_recv) * (1 + 2 * self.users.dim)   # ids + rows out + gradient rows back, fixed-capacity blocks
         both = torch.cat([self.loss_local, self.loss_tab])
         dist.all_reduce(both)
         return both   # [mean BCE + l2 |E_d|^2, l2 (|E_u|^2 + |E_i|^2)]; their sum is the Keras loss
@@ -345,7 +345,7 @@ class ShardedMTLTrainer(_GraphedSteps):
             dist.all_reduce(g)
         m.ctx.call("mamdr_adam_ranges_step", _ptr(m.params), _ptr(m.m), _ptr(m.v), _ptr(m.grads), begin, length, n_spans,
                    _ptr(m.opt_state), m.lr, m.beta1, m.beta2, m.eps, st)
-        self.comm_bytes += 4 * sum(g.numel() for g in spans) + 2 * 4 * (plan_u.n + plan_i.n) * (1 + self.users.dim)
+        self.comm_bytes += 4 * sum(g.numel() for g in spans) + 4 * (plan_u.n_recv + plan_i.n_recv) * (1 + 2 * self.users.dim)
         both = torch.cat([self.loss_local, self.loss_tab])
         dist.all_reduce(both)
         return both

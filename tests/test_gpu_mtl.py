@@ -243,3 +243,68 @@ def test_mtl_domain_negotiation(name, arch):
     for k in dom_auc:
         n_val = base.dataset.val_dataset[k]['n_data']
         assert abs(dom_auc[k] - o_dom[k]) < max(1e-3, 2.0 / n_val), (k, n_val, dom_auc[k], o_dom[k])
+
+
+def test_mtl_full_size_properties():
+    """Size-independent properties of one MMOE sub-model step at the FULL Amazon-13 table sizes (502 222 + 215 403 rows x 128,
+    config/Amazon_13/mmoe.json architecture), where the oracle would take minutes: de-duplicated ids bit-exact vs torch.unique,
+    variables and slots outside sub-model t bit-untouched, slot maps left clean, rows outside the batch moved by the closed
+    form of Adam's first step on g = 2 l2 E, the beta powers advanced once per step, and the streaming AUC counts consistent."""
+    from mamdr_b200.deep_mtl_ctr import MTLModel, MTLTopology, init_mtl_weights
+    from mamdr_b200.engine import DomainData
+    n_uid, n_pid, D, t = 502222, 215403, 13, 5
+    topo = MTLTopology("mmoe", n_uid, n_pid, D, (128, 128, 128), (256, 128), (64,), (64,), num_experts=5, emb_trainable=True)
+    w = init_mtl_weights(topo.layout, [3, 0])
+    rng = np.random.default_rng(0)
+    for i, n in enumerate(topo.layout.names):
+        if n.endswith('_emb'):
+            w[i] = (rng.standard_normal(w[i].shape, dtype=np.float32) * np.float32(0.05))
+    m = MTLModel(topo, w, dropout=0.5, lr=1e-3, max_batch=1024)
+    n = 2048
+    uid = (rng.random(n) ** 3 * n_uid).astype(np.int32)          # Zipf-ish: hot ids repeat inside a batch
+    pid = (rng.random(n) ** 3 * n_pid).astype(np.int32)
+    y = (rng.random(n) < 0.3).astype(np.float32)
+    data = DomainData(uid, pid, y, t, 1024, m.device)
+    before = m.params.clone()
+    loss = torch.zeros(2, device="cuda")
+    m._train_step(data, 0, 1024, loss[0:1])
+    torch.cuda.synchronize()
+    assert np.isfinite(loss[0].item()) and 0.3 < loss[0].item() < 30.0
+    lo = m.layout
+    # (1) de-duplicated ids: sorted unique of the batch ids, bit-exact
+    for ti, col in enumerate((uid, pid)):
+        ids, srows, cnt = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        assert m.ctx.lib.mamdr_mtl_sparse_grads(C.byref(m.desc), 1024, C.c_void_p(m.ws.data_ptr()), ti, C.byref(ids), C.byref(srows),
+                                                C.byref(cnt)) == 0
+        off, noff = ids.value - m.ws.data_ptr(), cnt.value - m.ws.data_ptr()
+        n_u = int(m.ws[noff:noff + 4].view(torch.int32).item())
+        got = m.ws[off:off + 4 * n_u].view(torch.int32).cpu().numpy()
+        assert np.array_equal(got, np.unique(col[:1024]))
+    # (2) everything outside sub-model t: values and Adam slots bit-untouched; inside: every variable moved
+    reach = set(topo.reachable(t))
+    for name, o, k in zip(lo.names, lo.offsets, lo.numels):
+        same = torch.equal(m.params[o:o + k], before[o:o + k])
+        if name in reach:
+            assert not same, name
+        else:
+            assert same and not m.m[o:o + k].any().item() and not m.v[o:o + k].any().item(), name
+    # (3) slot maps clean; (4) rows outside the batch: first Adam step on the l2 gradient alone
+    for (o, rows, dim, slot), col in zip(m._tables, (uid, pid)):
+        assert int((slot != -1).sum().item()) == 0
+        untouched = torch.ones(rows, dtype=torch.bool, device="cuda")
+        untouched[torch.from_numpy(np.unique(col[:1024])).long().cuda()] = False
+        p0 = before[o:o + rows * dim].view(rows, dim)[untouched]
+        p1 = m.params[o:o + rows * dim].view(rows, dim)[untouched]
+        g = 2e-5 * p0
+        expect = -1e-3 * g / (g.abs() + 1e-8 / (1 - 0.999) ** 0.5)
+        assert torch.allclose(p1 - p0, expect, rtol=2e-3, atol=1e-9)
+    # (5) a second step (the ragged remainder of another pass position): the beta powers advance once per step
+    m._train_step(data, 1024, 1000, loss[1:2])
+    step, b1, b2 = m.read_step()
+    assert step == 2 and np.float32(b1) == np.float32(np.float32(0.9) * np.float32(0.9) * np.float32(0.9))
+    # (6) inference + streaming AUC: tp + fn = positives, fp + tn = negatives at every threshold; AUC in [0, 1]
+    ev_loss, auc = m.evaluate(data, 2)
+    acc = m.auc_acc.cpu().numpy()
+    assert np.all(acc[0] + acc[2] == float(y.sum())) and np.all(acc[1] + acc[3] == float(n - y.sum()))
+    assert np.all(np.diff(acc[0]) <= 0) and np.all(np.diff(acc[1]) <= 0)      # tp / fp fall as the threshold rises
+    assert 0.0 <= auc <= 1.0 and np.isfinite(ev_loss)
