@@ -25,6 +25,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOAD_CONFIG = {"Taobao-10": "config/Taobao-10/deepctr_DN+DR.json", "Taobao-20": "config/Taobao_20/deepctr_DN+DR.json",
+                   "Taobao-20-star": "config/Taobao_20/star_DN+DR.json",
                    "Taobao-30": "config/Taobao_30/deepctr_DN+DR.json", "Amazon-6": "config/Amazon_6/deepctr.json",
                    "Amazon-13-sharded": "config/Amazon_6/deepctr.json", "Amazon-13-mmoe": "config/Amazon_13/mmoe_DN.json",
                    "Amazon-13-ple": "config/Amazon_13/ple_DN.json", "Amazon-13-mmoe-sharded": "config/Amazon_13/mmoe_DN.json",
@@ -176,10 +177,11 @@ def run_reference(args):
 
 def workload_desc(config, workload, n_gpus):
     tc = config["train"]
-    return {"workload": "%s synthetic %s: DN + DR(sample_num=%d%s), batch %d, mlp %s, frozen 128-d embeddings, "
+    return {"workload": "%s synthetic %s: DN + DR(sample_num=%d%s), batch %d, %s %s, frozen 128-d embeddings, "
                         "one meta-step per bench step" % (config["model"]["name"], workload, tc["sample_num"],
                                                           "+query" if tc["add_query_domain"] else "",
                                                           config["dataset"]["batch_size"],
+                                                          "star (PartitionedNorm + StarFCN)" if "star" in config["model"]["name"] else "mlp",
                                                           "/".join(str(h) for h in config["model"]["hidden_dim"])),
             "parallelism": "dr-shard%d" % n_gpus if n_gpus > 1 else "single",
             "precision": config.get("b200", {}).get("precision", "fp32"),
@@ -448,7 +450,7 @@ def run_b200(args):
         raise SystemExit("--gpus %d but WORLD_SIZE is %d (launch N > 1 with torchrun)" % (args.gpus, world))
     config = load_config(args.workload)
     config["b200"]["device"] = "cuda:%d" % local_rank
-    config["b200"]["precision"] = args.precision or "tf32x3"
+    config["b200"]["precision"] = args.precision or ("fp32" if "star" in config["model"]["name"] else "tf32x3")   # STAR: fp32 path only
     wrapper = runpy.build(config)
     base = wrapper.base_model
     model = base.model
@@ -549,6 +551,11 @@ def run_b200(args):
     # the tcgen05 modes; the captured per-mini-batch graph in fp32 mode) over one extra, untimed-for-value meta-step
     P = sum(model.layout.numels)
     alg_bytes_mb = 1572864 + 12288 + 4096 + 2 * 4 * (P - model.n_domain * 128) + 28 * P   # 6.65 MB / mini-batch
+    is_star = "star" in config["model"]["name"]
+    if is_star:
+        # STAR (config #4): gather + the effective-weight build / forward / backward reads of ONE domain's slices (~6 x 4 B x 141 K)
+        # + the gradient-arena memset and the non-lazy Adam over the WHOLE arena (every domain's specific tensors): 32 B / parameter
+        alg_bytes_mb = 1572864 + 12288 + 4096 + 6 * 4 * 141057 + 32 * P
     flops_mb = 0.72e9
     if model.pass_kernel:
         model.launch_times = []
@@ -585,7 +592,8 @@ def run_b200(args):
     achieved = alg_bytes_launch / (avg_launch_ms * 1e-3) / 1e9
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_pass_kernel_ncu.json"))).get("dram_bytes_per_launch")
+        if model.pass_kernel:   # the ncu --set full capture is of passk::pass_kernel
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_pass_kernel_ncu.json"))).get("dram_bytes_per_launch")
     except Exception:
         pass
     kname = ("passk::pass_kernel (one persistent launch per DN phase / DR chain: passes + meta sweeps in-kernel)"
@@ -595,7 +603,9 @@ def run_b200(args):
             "kernel": kname, "launches_per_meta_step": k_launches, "avg_launch_us": 1e3 * avg_launch_ms,
             "minibatches_per_launch": k_mb / max(k_launches, 1), "alg_bytes_per_minibatch": alg_bytes_mb,
             "us_per_minibatch_in_kernel": 1e3 * k_ms / max(k_mb, 1), "kernel_share_of_step": k_ms / (ms / args.steps),
-            "note": "algorithmic bytes = 6.65 MB per mini-batch (SURVEY.md 8(d)) x mini-batches of the launch; at batch "
+            "note": ("STAR: algorithmic bytes = gather + one domain's weight slices + 32 B per arena parameter (memset + non-lazy Adam over "
+                     "every domain's specific tensors) per mini-batch; ~21 launches per mini-batch replayed as one CUDA graph per pass")
+            if is_star else "algorithmic bytes = 6.65 MB per mini-batch (SURVEY.md 8(d)) x mini-batches of the launch; at batch "
                     "1024 the whole working set (2.3 MB) is L2-resident and the kernel is bound by dependent-phase "
                     "latency (7 grid barriers + TMA fill per mini-batch), not by HBM: see DESIGN.md; HBM-scale "
                     "rooflines of the gather / Adam sweeps are under 'micro'",
