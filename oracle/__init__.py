@@ -17,7 +17,12 @@ What it restates (citations are into ``/root/reference``):
   ``utils/metrics_utils.py:245-354``;
 * batching contract: ``utils/dataset.py:12-38,73-99``.
 
-PARITY STATUS: **parity unpinned** for everything except the AUC metric.
+PARITY STATUS: the META ALGEBRA (``mamdr.py:168-196``, ``domain_negotiation.py:118-123``,
+``specific_base_model.py:164-172``, ``reptile.py:127-142``) and the early-stop / weighted-AUC
+bookkeeping (``base_model.py:157-175,208-224``) are PINNED to the reference: those methods are plain
+Python + numpy, ``tests/golden/make_reference_golden.py`` executes the reference's own code (TF / deepctr
+stubbed out) and ``tests/test_reference_golden.py`` holds the oracle to the committed vectors bit for bit.
+**Parity unpinned** for the train step itself (everything below ``model.fit`` / ``train_on_batch``):
 The arithmetic of the train step lives in un-vendored third-party packages
 (``tensorflow-gpu==1.12.0``, ``deepctr==0.9.0``; ``requirements.txt:1,6``)
 which cannot be installed in this image (no wheels for CPython 3.12, no

@@ -15,6 +15,9 @@ domain order, the DR support samples and the per-pass batch order are *injected*
 (``mamdr_b200/schedule.py``) so both sides see identical draws in identical order.
 
 ``data`` is ``{'train'|'val'|'test': {domain: {'uid','pid','label'}}}`` of numpy arrays.
+
+Pinned: the update rules / merge / accumulate / early-stop / weighted-AUC functions below reproduce, bit for bit, vectors
+obtained by executing the reference's own methods (tests/golden/reference_meta_v1.npz, tests/test_reference_golden.py).
 """
 from copy import deepcopy
 

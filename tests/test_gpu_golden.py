@@ -123,3 +123,56 @@ def test_golden_mmoe_train_step():
         off, noff = ids.value - m.ws.data_ptr(), cnt.value - m.ws.data_ptr()
         n_u = int(m.ws[noff:noff + 4].view(torch.int32).item())
         np.testing.assert_array_equal(m.ws[off:off + 4 * n_u].view(torch.int32).cpu().numpy(), np.unique(col))
+
+
+def test_cuda_meta_sweeps_match_the_reference_executed_vectors():
+    """tests/golden/reference_meta_v1.npz was produced by EXECUTING the reference's own numpy algebra (mamdr.py:168-196,
+    domain_negotiation.py:118-123, specific_base_model.py:164-172, reptile.py:127-142; generator: make_reference_golden.py).
+    The K9 / K10 sweeps reproduce it bit for bit."""
+    ref = np.load(os.path.join(ROOT, "tests", "golden", "reference_meta_v1.npz"))
+    c = ctx()
+    n_real = ref["theta"].size
+    n = (n_real + 3) // 4 * 4
+
+    def pad(a):
+        out = np.zeros(n, dtype=np.float32)
+        out[:a.size] = a
+        return out
+
+    def same(t, key):
+        np.testing.assert_array_equal(bits(t.cpu().numpy()[:n_real]), bits(ref[key]), err_msg=key)
+
+    th, ti, mo = pad(ref["theta"]), pad(ref["theta_i"]), pad(ref["model"])
+    d_th, d_ti, d_mo = dev(th), dev(ti), dev(mo)
+    t = dev(th)
+    c.call("mamdr_dn_update", ptr(t), ptr(d_mo), 0.1, n, None, stream())
+    same(t, "dn_update")
+    same(t, "mamdr_dn_form")
+    same(t, "reptile_update")
+    for method, name in ((0, "plus"), (1, "times")):
+        merged = torch.zeros(n, device="cuda")
+        c.call("mamdr_merge", ptr(merged), ptr(d_th), ptr(d_ti), n, method, stream())
+        same(merged, "merge_" + name)
+        x = dev(ti)
+        c.call("mamdr_dr_update", ptr(x), ptr(d_th), ptr(d_mo), 0.1, n, method, None, stream())
+        same(x, "dr_update_" + name)
+        acc = dev(pad(ref["accum0"]))
+        c.call("mamdr_dr_accumulate", ptr(acc), ptr(d_mo), ptr(d_th), ptr(d_ti), n, method, stream())
+        same(acc, "accumulate_" + name)
+        x = dev(ti)
+        c.call("mamdr_dr_apply_accum", ptr(x), ptr(acc), 5.0, 0.1, n, stream())
+        same(x, "apply_accum_" + name)
+        assert float(acc.abs().max()) == 0.0
+        out = torch.zeros(n, device="cuda")
+        c.call("mamdr_sub", ptr(out), ptr(d_mo), ptr(merged), n, stream())
+        same(out, "update_domain_weights_" + name)
+    # Reptile, batch names: three deltas against the same theta, applied once
+    acc, zeros = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    for k in range(3):
+        shifted = dev(pad(ref["model"] + np.float32(0.25 * k)))
+        c.call("mamdr_axpy_diff", ptr(acc), ptr(shifted), ptr(d_th), 1.0, n, stream())
+        torch.cuda.synchronize()
+    same(acc, "reptile_accum3")
+    t = dev(th)
+    c.call("mamdr_axpy_diff", ptr(t), ptr(acc), ptr(zeros), 0.1, n, stream())
+    same(t, "reptile_apply")

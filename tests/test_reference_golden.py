@@ -1,0 +1,161 @@
+"""CPU: the oracle's meta algebra against vectors produced by EXECUTING THE REFERENCE'S OWN CODE
+(tests/golden/reference_meta_v1.npz, written by tests/golden/make_reference_golden.py from /root/reference with TF / deepctr
+stubbed out): SURVEY.md section 8 rows a2-a5, a8, a18 and Reptile's rules (f4) -- bit-exact.  /root/reference is NOT read here."""
+import os
+import types
+
+import numpy as np
+
+from conftest import ROOT
+from oracle import meta as ometa
+
+REF = np.load(os.path.join(ROOT, "tests", "golden", "reference_meta_v1.npz"))
+SHAPES = [(7, 5), (5,), (3, 4), (1,)]
+TC = {"meta_learning_rate": 0.1, "domain_meta_learning_rate": 0.1, "sample_num": 5, "merged_method": "plus", "patience": 3}
+
+
+def _split(flat):
+    out, o = [], 0
+    for s in SHAPES:
+        n = int(np.prod(s))
+        out.append(np.array(flat[o:o + n], dtype=np.float32).reshape(s))
+        o += n
+    return out
+
+
+def _flat(ws):
+    return np.concatenate([np.asarray(w, dtype=np.float32).reshape(-1) for w in ws])
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def _same(got, key):
+    np.testing.assert_array_equal(_bits(_flat(got)), _bits(REF[key]), err_msg=key)
+
+
+class _Model(object):
+    dtype = np.dtype(np.float32)
+
+    def __init__(self, ws):
+        self.ws = ws
+        self.auc = types.SimpleNamespace(reset_states=lambda: None)
+
+    def get_weights(self):
+        return [w.copy() for w in self.ws]
+
+    def set_weights(self, ws):
+        pass
+
+
+def _mamdr(method):
+    o = ometa.OracleMAMDR.__new__(ometa.OracleMAMDR)
+    o.model, o.tc = _Model(_split(REF["model"])), dict(TC, merged_method=method)
+    return o
+
+
+def test_merge_and_dr_updates_match_the_reference():
+    theta, theta_i = _split(REF["theta"]), _split(REF["theta_i"])
+    for method in ("plus", "times"):
+        merged = ometa.merge_weights(theta, theta_i, method)                      # a5
+        _same(merged, "merge_" + method)
+        o = _mamdr(method)
+        ti = [w.copy() for w in theta_i]
+        o._update_meta_weight(ti, merged, TC["domain_meta_learning_rate"])        # a2 (DR form)
+        _same(ti, "dr_update_" + method)
+        acc = _split(REF["accum0"])
+        o._accumulate_grad(acc, merged, theta)                                    # a3
+        _same(acc, "accumulate_" + method)
+        ti = [w.copy() for w in theta_i]
+        o._update_meta_weight_by_grads(acc, ti)
+        _same(ti, "apply_accum_" + method)
+        assert not _flat(acc).any()
+        new = o.model.get_weights()                                               # a4: theta_i = model - merged
+        _same([n - m for n, m in zip(new, merged)], "update_domain_weights_" + method)
+    o = _mamdr("plus")
+    t = [w.copy() for w in theta]
+    o._update_meta_weight(t, None, TC["meta_learning_rate"])                      # a2 (DN form inside MAMDR)
+    _same(t, "mamdr_dn_form")
+
+
+class _PassSetsWeights(object):
+    """A stand-in model whose training pass lands on fixed weights: isolates the outer update of the DN / Reptile loops."""
+    dtype = np.dtype(np.float32)
+
+    def __init__(self, start, after_pass):
+        self.weights = [w.copy() for w in start]
+        self.after = after_pass
+        self.calls = 0
+        self.auc = types.SimpleNamespace(reset_states=lambda: None)
+
+    def get_weights(self):
+        return [w.copy() for w in self.weights]
+
+    def set_weights(self, ws):
+        for a, b in zip(self.weights, ws):
+            a[...] = b
+
+    def train_on_batch(self, uid, pid, domain, label, optimizer='adam', sgd_lr=None):
+        tgt = self.after(self.calls) if callable(self.after) else self.after
+        self.calls += 1
+        for a, b in zip(self.weights, tgt):
+            a[...] = b
+        return 0.0, 0.5
+
+
+def _data(n_domain):
+    return {'train': {d: {'uid': np.zeros(3, np.int32), 'pid': np.zeros(3, np.int32), 'label': np.zeros(3, np.float32)} for d in range(n_domain)}}
+
+
+def test_dn_and_reptile_outer_updates_match_the_reference():
+    from mamdr_b200.schedule import Schedule
+    theta, model = _split(REF["theta"]), _split(REF["model"])
+    tc = dict(TC, shuffle_sequence=False, meta_train_step=0)
+    dn = ometa.OracleDN(_PassSetsWeights(theta, model), _data(1), tc, 8, Schedule(1))      # a8
+    dn.train_epoch()
+    _same(dn.meta_weights, "dn_update")
+    rp = ometa.OracleReptile(_PassSetsWeights(theta, model), _data(1), tc, 8, Schedule(1))  # f4, per-domain rule
+    rp.train_epoch()
+    _same(rp.meta_weights, "reptile_update")
+    # f4, batch rule: three domains whose passes land on model + 0.25 k, deltas summed against the SAME theta, applied once
+    shifted = lambda k: [w + np.float32(0.25 * k) for w in model]   # noqa: E731
+    rb = ometa.OracleReptile(_PassSetsWeights(theta, shifted), _data(3), tc, 8, Schedule(1), name="mlp_meta_reptile_batch")
+    orig = rb.schedule.shuffle_sequence
+    rb.schedule.shuffle_sequence = lambda seq: list(seq)              # keep 0, 1, 2: the reference vector used k = 0, 1, 2
+    rb.train_epoch()
+    rb.schedule.shuffle_sequence = orig
+    _same(rb.meta_weights, "reptile_apply")
+
+
+def test_early_stop_and_weighted_auc_match_the_reference():
+    es = ometa.EarlyStop(TC["patience"])
+    saved = []
+    trace = []
+    for mval in REF["early_stop_metrics"]:
+        stop = es.step(float(mval), lambda: saved.append(1))
+        trace.append([es.counter, float(es.best_metric), float(bool(stop)), float(len(saved))])
+    np.testing.assert_array_equal(np.array(trace), REF["early_stop_trace"])
+    sizes = {0: (10, 4, 6), 1: (30, 9, 1), 2: (5, 2, 3)}
+    data = {m: {k: {'uid': np.zeros(v[i])} for k, v in sizes.items()} for i, m in enumerate(("train", "val", "test"))}
+    auc = {0: 0.61, 1: 0.72, 2: 0.55}
+    got = np.array([ometa.weighted_auc(data, m, auc) for m in ("train", "val", "test")])
+    np.testing.assert_allclose(got, REF["weighted_auc"], rtol=1e-15)
+
+
+def test_product_early_stop_matches_the_reference():
+    """mamdr_b200/base_model.py:early_stop_step / _weighted_auc (host code, no GPU) on the same trace."""
+    from mamdr_b200.base_model import BaseModel
+    s = types.SimpleNamespace(train_config=TC, checkpoint_path="/dev/null", saved=[], log=lambda *a: None)
+    s.save_model = lambda path: s.saved.append(1)
+    BaseModel._build_early_stop(s)
+    trace = []
+    for mval in REF["early_stop_metrics"]:
+        stop = BaseModel.early_stop_step(s, float(mval))
+        trace.append([s.counter, float(s.best_metric), float(bool(stop)), float(len(s.saved))])
+    np.testing.assert_array_equal(np.array(trace), REF["early_stop_trace"])
+    info = {0: {"n_train": 10, "n_val": 4, "n_test": 6}, 1: {"n_train": 30, "n_val": 9, "n_test": 1}, 2: {"n_train": 5, "n_val": 2, "n_test": 3}}
+    s.dataset = types.SimpleNamespace(dataset_info=info)
+    auc = {0: 0.61, 1: 0.72, 2: 0.55}
+    got = np.array([BaseModel._weighted_auc(s, m, auc) for m in ("train", "val", "test")])
+    np.testing.assert_allclose(got, REF["weighted_auc"], rtol=1e-15)
