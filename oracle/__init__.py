@@ -17,7 +17,10 @@ What it restates (citations are into ``/root/reference``):
   ``utils/metrics_utils.py:245-354``;
 * batching contract: ``utils/dataset.py:12-38,73-99``.
 
-PARITY STATUS: the META ALGEBRA (``mamdr.py:168-196``, ``domain_negotiation.py:118-123``,
+PARITY STATUS: the HOST SIDE is pinned to the reference by executing the reference's own code (TF / deepctr stubbed,
+``tests/golden/make_reference_golden.py``): the training loops ``MAMDR.train`` / ``DomainNegotiation.train`` /
+``Reptile.train`` over a toy Keras stand-in (sequence of train steps, theta, theta_d, best snapshots, early stop: the
+oracle's loops replay them bit for bit), and the META ALGEBRA (``mamdr.py:168-196``, ``domain_negotiation.py:118-123``,
 ``specific_base_model.py:164-172``, ``reptile.py:127-142``) and the early-stop / weighted-AUC
 bookkeeping (``base_model.py:157-175,208-224``) are PINNED to the reference: those methods are plain
 Python + numpy, ``tests/golden/make_reference_golden.py`` executes the reference's own code (TF / deepctr

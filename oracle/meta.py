@@ -117,8 +117,12 @@ class OracleDN(object):
         for idx, d in self.data[mode].items():
             l, a = self.model.evaluate(d['uid'], d['pid'], idx, d['label'], self.bs)
             domain_loss[idx], domain_auc[idx] = float(l), float(a)
-        avg_loss = sum(domain_loss.values()) / len(domain_loss)
-        avg_auc = sum(domain_auc.values()) / len(domain_auc)
+        all_loss, all_auc = 0, 0          # plain left-to-right adds like the reference (Python >= 3.12's sum() is compensated)
+        for k in domain_loss:
+            all_loss += domain_loss[k]
+            all_auc += domain_auc[k]
+        avg_loss = all_loss / len(domain_loss)
+        avg_auc = all_auc / len(domain_auc)
         return avg_loss, avg_auc, domain_loss, domain_auc
 
     def early_stop_step(self, metric):
@@ -345,8 +349,12 @@ class OracleMAMDR(object):
             self.model.set_weights(merge_weights(shared, specific[idx], self.tc['merged_method']))
             l, a = self.model.evaluate(d['uid'], d['pid'], idx, d['label'], self.bs)
             domain_loss[idx], domain_auc[idx] = float(l), float(a)
-        avg_loss = sum(domain_loss.values()) / len(domain_loss)
-        avg_auc = sum(domain_auc.values()) / len(domain_auc)
+        all_loss, all_auc = 0, 0          # plain left-to-right adds like the reference (Python >= 3.12's sum() is compensated)
+        for k in domain_loss:
+            all_loss += domain_loss[k]
+            all_auc += domain_auc[k]
+        avg_loss = all_loss / len(domain_loss)
+        avg_auc = all_auc / len(domain_auc)
         return avg_loss, avg_auc, domain_loss, domain_auc
 
     def early_stop_step(self, metric):  # specific_base_model.py:44-62

@@ -68,8 +68,9 @@ class _StubFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
 
 
 def import_reference():
-    sys.meta_path.insert(0, _StubFinder())
-    sys.path.insert(0, REFERENCE)
+    if not any(isinstance(f, _StubFinder) for f in sys.meta_path):
+        sys.meta_path.insert(0, _StubFinder())
+        sys.path.insert(0, REFERENCE)
     import model_zoo.base_model as base_model
     import model_zoo.domain_negotiation as domain_negotiation
     import model_zoo.mamdr as mamdr
@@ -164,9 +165,243 @@ def make():
     return g
 
 
+# ---- the reference's TRAINING LOOPS executed over a toy Keras stand-in ------------------------------------------------------
+# MAMDR.train (mamdr.py:18-166), DomainNegotiation.train (domain_negotiation.py:18-116) and Reptile.train (reptile.py:17-125) are
+# host-side Python: with a stand-in for the compiled Keras model (a train step is a fixed affine map that depends on the domain,
+# so the ORDER of every step matters) and Python's `random` seeded, running them records the exact control flow -- which domain
+# trains when, from which weights, which deltas are applied, which snapshots are kept.  The oracle replays the same loops with
+# `Schedule(seed)` (the same `random.Random` draws in the same order) and must land on the same bits (tests/test_reference_golden.py).
+N_STEP = {0: 3, 1: 2, 2: 2, 3: 1}
+LOOP_SEED = 321
+
+
+def toy_step(weights, domain):
+    for w in weights:
+        w[...] = w * np.float32(0.9) + np.float32(0.01 * (domain + 1))
+
+
+def toy_eval(weights, domain):
+    tot = float(sum(np.asarray(w, dtype=np.float64).sum() for w in weights))
+    import math
+    return tot, 0.5 + 0.4 * math.tanh(tot * (domain + 1) * 0.01)
+
+
+def toy_init(k):
+    """Weights after the k-th (re-)initialisation of the layers: k = 0 is the model build."""
+    rng = np.random.default_rng(1000 + k)
+    return [rng.standard_normal((3, 2)).astype(np.float32), rng.standard_normal((4,)).astype(np.float32)]
+
+
+class _ToyData(object):
+    def __init__(self, domain):
+        self.domain = domain
+
+    def make_initializable_iterator(self):
+        return types.SimpleNamespace(domain=self.domain, initializer=None)
+
+
+class _ToyKeras(object):
+    def __init__(self):
+        self.weights = toy_init(0)
+        self.steps = []                    # the domain of every train step, in execution order
+        self.stateful_metric_functions = []
+        self.layers = []
+
+    def fit(self, it, steps_per_epoch=1, **kw):
+        for _ in range(steps_per_epoch):
+            self.train_on_batch(it)
+
+    def train_on_batch(self, it):
+        toy_step(self.weights, it.domain)
+        self.steps.append(it.domain)
+        return 0.0, 0.5
+
+    def evaluate(self, data, steps=1, verbose=0):
+        return toy_eval(self.weights, data.domain)
+
+
+def _toy_wrapper(cls, base_model_mod, train_config, name):
+    import collections
+    model = _ToyKeras()
+    mk = lambda: collections.OrderedDict((d, {"data": _ToyData(d), "n_step": N_STEP[d]}) for d in sorted(N_STEP))   # noqa: E731
+    info = {d: {"n_train": 4 * N_STEP[d], "n_val": 2 + d, "n_test": 3 + d} for d in N_STEP}
+    dataset = types.SimpleNamespace(train_dataset=mk(), val_dataset=mk(), test_dataset=mk(), dataset_info=info)
+    base = types.SimpleNamespace(train_config=train_config, model_config={"name": name}, dataset=dataset, model=model,
+                                 n_domain=len(N_STEP), checkpoint_path="/tmp/unused/model.h5", saved=None)
+    B = base_model_mod.BaseModel
+    for meth in ("val_and_test", "early_stop_step", "_weighted_auc", "_format_print_domain_metric", "_build_early_stop"):
+        setattr(base, meth, types.MethodType(getattr(B, meth), base))
+    base.save_model = lambda path: setattr(base, "saved", [w.copy() for w in model.weights])
+    base.load_model = lambda path: [a.__setitem__(Ellipsis, b) for a, b in zip(model.weights, base.saved)]
+    base._build_early_stop()
+    obj = cls.__new__(cls)
+    obj.base_model = base
+    inits = [0]
+    obj._get_model_meta_parms = lambda: setattr(obj, "model_meta_parms", [types.SimpleNamespace()] * len(model.weights))
+    obj._get_meta_weights = lambda: [w.copy() for w in model.weights]
+    base.last_set = None
+
+    def set_parms(ws):      # MAML._set_model_meta_parms (maml.py:181-187); the last call of a run carries the final theta
+        base.last_set = [np.array(w, dtype=np.float32) for w in ws]
+        for a, b in zip(model.weights, ws):
+            a[...] = b
+    obj._set_model_meta_parms = set_parms
+
+    def init_layer(m):
+        inits[0] += 1
+        for a, b in zip(model.weights, toy_init(inits[0])):
+            a[...] = b
+    obj.init_layer = init_layer
+    return obj, model, base
+
+
+LOOP_TC = {"epoch": 2, "shuffle_sequence": True, "sample_num": 2, "add_query_domain": True, "merged_method": "plus",
+           "meta_learning_rate": 0.1, "domain_meta_learning_rate": 0.1, "finetune_every_epoch": False, "domain_regulation_step": 0,
+           "meta_train_step": 0, "meta_finetune_step": 0, "val_every_step": 1, "target_domain": -1, "patience": 3, "histogram_freq": 0,
+           "meta_sequence": "random"}
+LOOP_CASES = [("mamdr", "mlp_meta_mamdr", "plus"), ("mamdr", "mlp_meta_mamdr_batch", "plus"), ("mamdr", "mlp_meta_mamdr", "times"),
+              ("dn", "mlp_meta_domain_negotiation", "plus"), ("reptile", "mlp_meta_reptile", "plus"),
+              ("reptile", "mlp_meta_reptile_batch", "plus")]
+
+
+def make_loops():
+    import contextlib
+    import io
+    import random
+    base_model, dn, mamdr, reptile, sbm = import_reference()
+    import numpy
+    g = {}
+    for kind, name, method in LOOP_CASES:
+        cls = {"mamdr": mamdr.MAMDR, "dn": dn.DomainNegotiation, "reptile": reptile.Reptile}[kind]
+        tc = dict(LOOP_TC, merged_method=method)
+        obj, model, base = _toy_wrapper(cls, base_model, tc, name)
+        if kind == "mamdr":
+            # mamdr.py:75 sizes the `batch` accumulators with K.int_shape / K.dtype of the Keras variables (TF): stand-ins only
+            mod_K = mamdr.K
+            mod_K.int_shape = staticmethod(lambda p: p.shape)
+            mod_K.dtype = staticmethod(lambda p: "float32")
+            obj._get_model_meta_parms = lambda o=obj, m=model: setattr(o, "model_meta_parms", [types.SimpleNamespace(shape=w.shape) for w in m.weights])
+        if kind == "reptile":
+            mod_K = reptile.K
+            mod_K.int_shape = staticmethod(lambda p: p.shape)
+            mod_K.dtype = staticmethod(lambda p: "float32")
+            obj._get_model_meta_parms = lambda o=obj, m=model: setattr(o, "model_meta_parms", [types.SimpleNamespace(shape=w.shape) for w in m.weights])
+        random.seed(LOOP_SEED)
+        with contextlib.redirect_stdout(io.StringIO()):
+            obj.train()
+        key = "%s|%s|" % (name, method)
+        g[key + "steps"] = numpy.array(model.steps, dtype=numpy.int32)
+        if kind == "mamdr":
+            g[key + "theta"] = flat_any(obj.meta_weights)
+            for d in sorted(N_STEP):
+                g[key + "theta_%d" % d] = flat_any(obj.domain_weights[d])
+                g[key + "best_theta_%d" % d] = flat_any(obj.best_domain_weights[d])
+            g[key + "best_theta"] = flat_any(obj.best_shared_weights)
+            g[key + "es"] = numpy.array([obj.counter, obj.best_metric], dtype=numpy.float64)
+        else:
+            g[key + "theta"] = flat_any(base.last_set)      # theta is a local of these loops; their last _set_model_meta_parms
+            #                                                  (domain_negotiation.py:88, reptile.py:99) loads it into the model
+            g[key + "best"] = flat_any(base.saved)
+            g[key + "es"] = numpy.array([base.counter, base.best_metric], dtype=numpy.float64)
+    return g
+
+
+# ---- the reference's CLI dispatch (run.py:22-87) and meta-parameter selection (maml.py:153-179) -------------------------------
+DISPATCH_NAMES = ["mlp", "mlp_meta_mamdr_finetune", "mlp_meta_mamdr_batch", "mlp_meta_domain_negotiation_finetune",
+                  "mlp_meta_domain_negotiation", "star", "star_meta_mamdr_finetune", "mmoe", "ple", "shared_bottom",
+                  "mmoe_meta_domain_negotiation", "ple_meta_domain_negotiation", "mlp_meta_reptile_finetune", "mlp_meta_reptile_batch",
+                  "mlp_separate", "wdl", "mlp_meta_mldg", "mlp_meta", "mlp_pcgrad", "mlp_uncertainty_weight", "nothing"]
+VAR_NAMES = {
+    "mlp_frozen": ["sparse_emb_domain_emb/embeddings:0", "dnn/kernel0:0", "dnn/kernel1:0", "dnn/kernel2:0", "dnn/bias0:0", "dnn/bias1:0",
+                   "dnn/bias2:0", "dense/kernel:0", "prediction_layer/global_bias:0"],
+    "star": ["domain_emb/embeddings:0", "partitioned_norm/gamma_specific:0", "partitioned_norm/beta_specific:0",
+             "partitioned_norm/gamma_shared:0", "partitioned_norm/beta_shared:0", "star_fcn/kernel_specific:0", "star_fcn/bias_specific:0",
+             "star_fcn/kernel_shared:0", "star_fcn/bias_shared:0", "star_fcn_1/kernel_specific:0", "star_fcn_1/bias_specific:0",
+             "star_fcn_1/kernel_shared:0", "star_fcn_1/bias_shared:0", "dense/kernel:0", "dense/bias:0"]}
+META_PARMS_CASES = [("mlp_frozen", ["all"]), ("mlp_frozen", ["all_hidden"]), ("mlp_frozen", ["dnn"]), ("mlp_frozen", ["bias", "dense"]),
+                    ("mlp_frozen", ["emb", "nope"]), ("star", ["emb", "kernel_shared", "bias_shared"]), ("star", ["all_hidden"]),
+                    ("star", ["specific"])]
+
+
+class _Recorder(object):
+    """Stand-in for every class run.py instantiates: records construction and the calls main() makes on the final object."""
+    trace = None
+
+    def __init__(self, *args, **kwargs):
+        type(self).trace.append(type(self).__name__)
+        self.train_config = {"meta_finetune_step": 0}
+        self.checkpoint_path = "ckpt"
+
+    def train(self):
+        self.trace.append("train")
+
+    def val_and_test(self, mode):
+        self.trace.append("val_and_test:" + mode)
+        return 0.0, 0.5, {}, {}
+
+    def separate_train_val_test(self, init_parms=True):
+        self.trace.append("separate_train_val_test:init_parms=%s" % init_parms)
+        return 0.0, 0.5, {}, {}
+
+    def load_model(self, path):
+        self.trace.append("load_model")
+
+    def save_result(self, *a):
+        self.trace.append("save_result")
+
+
+def recorder_classes(names, trace):
+    return {n: type(n, (_Recorder,), {"trace": trace}) for n in names}
+
+
+def make_dispatch():
+    import contextlib
+    import io
+    import_reference()
+    import run as ref_run
+    assert ref_run.__file__.startswith(REFERENCE)
+    out = {"dispatch": {}, "meta_parms": []}
+    classes = ["MultiDomainDataset", "Star", "DeepCTR", "DeepMTLCTR", "UncertaintyWeight", "PCGrad", "DomainNegotiation", "MAMDR", "Reptile",
+               "MLDG", "MAML"]
+    for name in DISPATCH_NAMES:
+        trace = []
+        for k, v in recorder_classes(classes, trace).items():
+            setattr(ref_run, k, v)
+        try:
+            with contextlib.redirect_stdout(io.StringIO()):
+                ref_run.main({"model": {"name": name}, "dataset": {"seed": 1}})
+        except Exception as e:        # run.py:47 only prints for an unknown model, then crashes on None
+            trace.append("raises:" + type(e).__name__)
+        out["dispatch"][name] = trace
+    import model_zoo.maml as maml
+    maml.tool.SetVarOp = lambda parms: None          # utils/tool.py:16-45 builds TF assign ops; not part of the selection logic
+    for model_kind, meta_parms in META_PARMS_CASES:
+        tw = [types.SimpleNamespace(name=n) for n in VAR_NAMES[model_kind]]
+        s = types.SimpleNamespace(train_config={"meta_parms": meta_parms}, model=types.SimpleNamespace(trainable_weights=tw))
+        try:
+            maml.MAML._get_model_meta_parms(s)
+            res = [p.name for p in s.model_meta_parms]
+        except ValueError as e:
+            res = "ValueError: " + str(e)
+        out["meta_parms"].append({"model": model_kind, "meta_parms": meta_parms, "selected": res})
+    return out
+
+
+def flat_any(ws):
+    return np.concatenate([np.asarray(w, dtype=np.float32).reshape(-1) for w in ws])
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REFERENCE):
         raise SystemExit("the reference tree is not available here; the committed .npz is the artefact")
     out = os.path.join(HERE, "reference_meta_v1.npz")
     np.savez_compressed(out, **make())
+    print(out, os.path.getsize(out), "bytes")
+    out = os.path.join(HERE, "reference_loops_v1.npz")
+    np.savez_compressed(out, **make_loops())
+    print(out, os.path.getsize(out), "bytes")
+    import json
+    out = os.path.join(HERE, "reference_dispatch_v1.json")
+    with open(out, "w") as f:
+        json.dump(make_dispatch(), f, indent=1)
     print(out, os.path.getsize(out), "bytes")

@@ -159,3 +159,151 @@ def test_product_early_stop_matches_the_reference():
     auc = {0: 0.61, 1: 0.72, 2: 0.55}
     got = np.array([BaseModel._weighted_auc(s, m, auc) for m in ("train", "val", "test")])
     np.testing.assert_allclose(got, REF["weighted_auc"], rtol=1e-15)
+
+
+# ---- the reference's TRAINING LOOPS (executed over a toy Keras stand-in) vs the oracle's loops ---------------------------------
+import sys  # noqa: E402
+
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+import make_reference_golden as mrg  # noqa: E402  (toy definitions only: /root/reference is not touched by importing it)
+
+LOOPS = np.load(os.path.join(ROOT, "tests", "golden", "reference_loops_v1.npz"))
+
+
+class _ToyOracleModel(object):
+    dtype = np.dtype(np.float32)
+
+    def __init__(self):
+        self.weights = mrg.toy_init(0)
+        self.steps = []
+        self.auc = types.SimpleNamespace(reset_states=lambda: None)
+
+    def get_weights(self):
+        return [w.copy() for w in self.weights]
+
+    def set_weights(self, ws):
+        for a, b in zip(self.weights, ws):
+            a[...] = b
+
+    def train_on_batch(self, uid, pid, domain, label, optimizer='adam', sgd_lr=None):
+        mrg.toy_step(self.weights, domain)
+        self.steps.append(domain)
+        return 0.0, 0.5
+
+    def evaluate(self, uid, pid, domain, label, batch_size):
+        return mrg.toy_eval(self.weights, domain)
+
+
+def _toy_data(bs):
+    col = lambda n: {'uid': np.zeros(n, np.int32), 'pid': np.zeros(n, np.int32), 'label': np.zeros(n, np.float32)}   # noqa: E731
+    return {'train': {d: col(bs * s) for d, s in sorted(mrg.N_STEP.items())},
+            'val': {d: col(2 + d) for d in sorted(mrg.N_STEP)}, 'test': {d: col(3 + d) for d in sorted(mrg.N_STEP)}}
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("kind,name,method", mrg.LOOP_CASES)
+def test_oracle_loops_replay_the_reference_loops(kind, name, method):
+    """MAMDR.train / DomainNegotiation.train / Reptile.train of the reference, run for two epochs over a toy model whose train
+    step depends on the domain (so every re-ordering shows), against the oracle's loops with `Schedule(seed)`: the same
+    sequence of train steps, theta, every theta_d, the kept best snapshots and the early-stop counters -- bit for bit."""
+    from mamdr_b200.schedule import Schedule
+    bs = 4
+    tc = dict(mrg.LOOP_TC, merged_method=method)
+    model = _ToyOracleModel()
+    key = "%s|%s|" % (name, method)
+    if kind == "mamdr":
+        om = ometa.OracleMAMDR(model, _toy_data(bs), tc, bs, Schedule(mrg.LOOP_SEED), {d: mrg.toy_init(d + 1) for d in mrg.N_STEP}, name=name)
+    elif kind == "dn":
+        om = ometa.OracleDN(model, _toy_data(bs), tc, bs, Schedule(mrg.LOOP_SEED))
+    else:
+        om = ometa.OracleReptile(model, _toy_data(bs), tc, bs, Schedule(mrg.LOOP_SEED), name=name)
+    for epoch in range(tc["epoch"]):
+        om.train_epoch()
+        _, val_auc, _, _ = om.val_and_test("val")
+        if om.early_stop_step(val_auc):
+            break
+        om.val_and_test("test")
+    np.testing.assert_array_equal(np.array(model.steps, dtype=np.int32), LOOPS[key + "steps"])
+    np.testing.assert_array_equal(_bits(mrg.flat_any(om.meta_weights)), _bits(LOOPS[key + "theta"]))
+    np.testing.assert_array_equal(np.array([om.es.counter, om.es.best_metric], dtype=np.float64), LOOPS[key + "es"])
+    if kind == "mamdr":
+        for d in sorted(mrg.N_STEP):
+            np.testing.assert_array_equal(_bits(mrg.flat_any(om.domain_weights[d])), _bits(LOOPS[key + "theta_%d" % d]), err_msg="theta_%d" % d)
+            np.testing.assert_array_equal(_bits(mrg.flat_any(om.best_domain_weights[d])), _bits(LOOPS[key + "best_theta_%d" % d]))
+        np.testing.assert_array_equal(_bits(mrg.flat_any(om.best_shared_weights)), _bits(LOOPS[key + "best_theta"]))
+    else:
+        np.testing.assert_array_equal(_bits(mrg.flat_any(om.best_weights)), _bits(LOOPS[key + "best"]))
+
+
+# ---- the reference's CLI dispatch (run.py:22-87) and meta-parameter selection (maml.py:153-179), executed -> product -----------
+import json  # noqa: E402
+
+DISPATCH = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_dispatch_v1.json")))
+OUT_OF_SCOPE = {"mlp_meta_mldg": NotImplementedError, "mlp_meta": NotImplementedError, "mlp_pcgrad": NotImplementedError,
+                "mlp_uncertainty_weight": NotImplementedError, "nothing": ValueError}
+
+
+@pytest.mark.parametrize("name", sorted(DISPATCH["dispatch"]))
+def test_product_cli_dispatch_matches_the_reference(monkeypatch, name):
+    """Which base model / wrapper is built for a model name and which calls `main` then makes (train, test, the finetune stage
+    after `load_model`, `separate`, `save_result`) -- the trace recorded by running the reference's run.main over recording
+    stand-ins, against this repo's run.main over the same stand-ins.  Names outside the hot-path scope raise instead."""
+    import run as prod_run
+    import mamdr_b200.dataset as p_dataset
+    import mamdr_b200.deep_mtl_ctr as p_mtl
+    import mamdr_b200.deepctr as p_ctr
+    import mamdr_b200.domain_negotiation as p_dn
+    import mamdr_b200.mamdr as p_mamdr
+    import mamdr_b200.reptile as p_rep
+    import mamdr_b200.star as p_star
+    trace = []
+    rec = mrg.recorder_classes(["MultiDomainDataset", "Star", "DeepCTR", "DeepMTLCTR", "DomainNegotiation", "MAMDR", "Reptile"], trace)
+    for mod, cls in ((p_dataset, "MultiDomainDataset"), (p_star, "Star"), (p_ctr, "DeepCTR"), (p_mtl, "DeepMTLCTR"),
+                     (p_dn, "DomainNegotiation"), (p_mamdr, "MAMDR"), (p_rep, "Reptile")):
+        monkeypatch.setattr(mod, cls, rec[cls])
+    config = {"model": {"name": name}, "dataset": {"seed": 1}}
+    if name in OUT_OF_SCOPE:
+        with pytest.raises(OUT_OF_SCOPE[name]):
+            prod_run.main(config)
+        return
+    prod_run.main(config)
+    assert trace == DISPATCH["dispatch"][name]
+
+
+@pytest.mark.parametrize("case", DISPATCH["meta_parms"], ids=lambda c: "%s-%s" % (c["model"], "+".join(c["meta_parms"])))
+def test_product_meta_parameter_selection_matches_the_reference(case):
+    """maml.py:153-179 executed on the variable names of the mlp / STAR models vs mamdr_b200/maml.py on the same names: the
+    same variables in the same order ("all", "all_hidden", substring lists), the same ValueError for an unmatched name."""
+    from mamdr_b200.maml import MAML
+    names = mrg.VAR_NAMES[case["model"]]
+    tw = [types.SimpleNamespace(name=n, offset=32 * i, numel=8) for i, n in enumerate(names)]
+    w = MAML(types.SimpleNamespace(train_config={"meta_parms": case["meta_parms"]}, model=types.SimpleNamespace(trainable_weights=tw)))
+    if isinstance(case["selected"], str):
+        with pytest.raises(ValueError) as e:
+            w._get_model_meta_parms()
+        assert "ValueError: " + str(e.value) == case["selected"]
+        return
+    w._get_model_meta_parms()
+    assert [p.name for p in w.model_meta_parms] == case["selected"]
+    # the arena spans cover exactly the selected variables
+    covered = set()
+    for off, n in w.meta_ranges:
+        covered |= set(range(off // 32, (off + n) // 32))
+    assert covered == {names.index(n) for n in case["selected"]}
+
+
+def test_product_variable_names_are_the_ones_the_selection_was_pinned_on():
+    """The names the product gives its variables (engine.MLPModel.TF_NAMES / star naming) are the ones used above."""
+    from mamdr_b200.engine import MLPModel
+    from mamdr_b200.layout import mlp_layout
+    lo = mlp_layout(10, 10, 3, (128, 128, 128), (256, 128, 64), False)
+    got = []
+    for name in lo.names:
+        tf_name = MLPModel.TF_NAMES.get(name)
+        if tf_name is None:
+            kind, idx = ("kernel", name[6:]) if name.startswith("kernel") else ("bias", name[4:])
+            tf_name = "dnn/%s%s:0" % (kind, idx)
+        got.append(tf_name)
+    assert got == mrg.VAR_NAMES["mlp_frozen"]
