@@ -387,6 +387,51 @@ def make_dispatch():
     return out
 
 
+# ---- the reference's on-disk ingest (utils/dataset.py:41-131) and pretrained-embedding parse (DeepCTR/deepctr.py:105-110) -----
+ONDISK = dict(shape="Taobao-10", seed=5, scale=0.004, batch_size=64)
+
+
+def write_ondisk(root):
+    """The tiny on-disk dataset both sides read (written in the reference's layout by tests/test_host.py's writer)."""
+    for extra in (os.path.dirname(HERE), os.path.dirname(os.path.dirname(HERE))):   # tests/ and the repo root
+        if extra not in sys.path:
+            sys.path.append(extra)
+    from mamdr_b200 import synth
+    from test_host import _write_reference_layout
+    g = synth.generate(ONDISK["shape"], seed=ONDISK["seed"], scale=ONDISK["scale"])
+    _write_reference_layout(root, g)
+    return {"name": "Taobao", "dataset_path": root, "domain_split_path": "split_by_theme_x", "batch_size": ONDISK["batch_size"],
+            "shuffle_buffer_size": 10000, "num_parallel_reads": 8, "seed": 123}
+
+
+def make_dataset():
+    import contextlib
+    import io
+    import tempfile
+    import_reference()
+    import utils.dataset as ref_dataset
+    import model_zoo.DeepCTR.deepctr as ref_deepctr
+    root = tempfile.mkdtemp(prefix="mamdr_ref_ondisk_")
+    conf = write_ondisk(root)
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+        ds = ref_dataset.MultiDomainDataset(conf)
+    info = ds.dataset_info
+    out = {"n_uid": ds.n_uid, "n_pid": ds.n_pid, "n_domain": ds.n_domain,
+           "dataset_info": {str(k): v for k, v in info.items()},
+           "n_step": {split: {str(k): v["n_step"] for k, v in getattr(ds, split + "_dataset").items()} for split in ("train", "val", "test")}}
+    # build_emb: capture the matrix handed to tf.keras.initializers.Constant
+    captured = {}
+    ref_deepctr.tf = types.SimpleNamespace(keras=types.SimpleNamespace(initializers=types.SimpleNamespace(
+        Constant=lambda m: captured.setdefault("m", np.array(m)))))
+    s = types.SimpleNamespace(train_config={"load_pretrain_emb": True, "emb_trainable": False}, dataset=ds)
+    mats = {}
+    for emb_name, n in (("user_emb", ds.n_uid), ("item_emb", ds.n_pid)):
+        captured.clear()
+        ref_deepctr.DeepCTR.build_emb(s, "x", emb_name, n, 128, trainable=False)
+        mats[emb_name] = captured["m"]
+    return out, mats
+
+
 def flat_any(ws):
     return np.concatenate([np.asarray(w, dtype=np.float32).reshape(-1) for w in ws])
 
@@ -404,4 +449,14 @@ if __name__ == "__main__":
     out = os.path.join(HERE, "reference_dispatch_v1.json")
     with open(out, "w") as f:
         json.dump(make_dispatch(), f, indent=1)
+    print(out, os.path.getsize(out), "bytes")
+    info, mats = make_dataset()
+    out = os.path.join(HERE, "reference_dataset_v1.json")
+    with open(out, "w") as f:
+        json.dump(info, f, indent=1)
+    print(out, os.path.getsize(out), "bytes")
+    out = os.path.join(HERE, "reference_dataset_emb_v1.npz")
+    np.savez_compressed(out, **{k: v.astype(np.float32) for k, v in mats.items()})
+    for k, v in mats.items():
+        assert np.array_equal(v.astype(np.float32).astype(v.dtype), v), "the float64 matrix holds float32 values"
     print(out, os.path.getsize(out), "bytes")

@@ -307,3 +307,24 @@ def test_product_variable_names_are_the_ones_the_selection_was_pinned_on():
             tf_name = "dnn/%s%s:0" % (kind, idx)
         got.append(tf_name)
     assert got == mrg.VAR_NAMES["mlp_frozen"]
+
+
+# ---- the reference's on-disk ingest and pretrained-embedding parse, executed -> product ---------------------------------------
+def test_product_ondisk_ingest_matches_the_reference(tmp_path):
+    """`utils.dataset.MultiDomainDataset` (utils/dataset.py:41-131: id counts, domain discovery,
+    `wc -l` sizes, n_step = ceil(n / batch), ctr_ratio, dataset_info) and `DeepCTR.build_emb`'s parse of the `"f f f ..."`
+    embedding strings (DeepCTR/deepctr.py:105-110) were EXECUTED on a tiny on-disk dataset; this repo's reader must agree."""
+    from mamdr_b200.dataset import MultiDomainDataset
+    ref = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_dataset_v1.json")))
+    emb = np.load(os.path.join(ROOT, "tests", "golden", "reference_dataset_emb_v1.npz"))
+    conf = mrg.write_ondisk(str(tmp_path))
+    ds = MultiDomainDataset(conf, device=None)
+    assert (ds.n_uid, ds.n_pid, ds.n_domain) == (ref["n_uid"], ref["n_pid"], ref["n_domain"])
+    info = {str(k): v for k, v in ds.dataset_info.items()}
+    assert info == ref["dataset_info"]
+    for split in ("train", "val", "test"):
+        got = {str(k): v["n_step"] for k, v in getattr(ds, split + "_dataset").items()}
+        assert got == ref["n_step"][split]
+        assert list(getattr(ds, split + "_dataset").keys()) == sorted(getattr(ds, split + "_dataset").keys())   # domains in numeric order
+    np.testing.assert_array_equal(_bits(ds.user_table), _bits(emb["user_emb"]))
+    np.testing.assert_array_equal(_bits(ds.item_table), _bits(emb["item_emb"]))
