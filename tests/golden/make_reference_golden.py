@@ -220,7 +220,7 @@ class _ToyKeras(object):
         return toy_eval(self.weights, data.domain)
 
 
-def _toy_wrapper(cls, base_model_mod, train_config, name):
+def _toy_wrapper(cls, base_model_mod, train_config, name, meta_idx=None):
     import collections
     model = _ToyKeras()
     mk = lambda: collections.OrderedDict((d, {"data": _ToyData(d), "n_step": N_STEP[d]}) for d in sorted(N_STEP))   # noqa: E731
@@ -237,14 +237,15 @@ def _toy_wrapper(cls, base_model_mod, train_config, name):
     obj = cls.__new__(cls)
     obj.base_model = base
     inits = [0]
-    obj._get_model_meta_parms = lambda: setattr(obj, "model_meta_parms", [types.SimpleNamespace()] * len(model.weights))
-    obj._get_meta_weights = lambda: [w.copy() for w in model.weights]
+    sel = list(range(len(model.weights))) if meta_idx is None else list(meta_idx)   # the meta parameters (maml.py:153-179)
+    obj._get_model_meta_parms = lambda: setattr(obj, "model_meta_parms", [types.SimpleNamespace(shape=model.weights[i].shape) for i in sel])
+    obj._get_meta_weights = lambda: [model.weights[i].copy() for i in sel]            # K.batch_get_value(model_meta_parms)
     base.last_set = None
 
     def set_parms(ws):      # MAML._set_model_meta_parms (maml.py:181-187); the last call of a run carries the final theta
         base.last_set = [np.array(w, dtype=np.float32) for w in ws]
-        for a, b in zip(model.weights, ws):
-            a[...] = b
+        for i, b in zip(sel, ws):
+            model.weights[i][...] = b
     obj._set_model_meta_parms = set_parms
 
     def init_layer(m):
@@ -259,6 +260,10 @@ LOOP_TC = {"epoch": 2, "shuffle_sequence": True, "sample_num": 2, "add_query_dom
            "meta_learning_rate": 0.1, "domain_meta_learning_rate": 0.1, "finetune_every_epoch": False, "domain_regulation_step": 0,
            "meta_train_step": 0, "meta_finetune_step": 0, "val_every_step": 1, "target_domain": -1, "patience": 3, "histogram_freq": 0,
            "meta_sequence": "random"}
+# meta parameters = a SUBSET of the variables (config #4: meta_parms = ["emb", "kernel_shared", "bias_shared"]): the other
+# variables are re-initialised by every init_layer call, never reloaded from theta, and evolve freely through all passes
+SUBSET_CASES = [("mamdr", "mlp_meta_mamdr", "plus"), ("dn", "mlp_meta_domain_negotiation", "plus"), ("reptile", "mlp_meta_reptile", "plus")]
+SUBSET_META_IDX = [0]
 LOOP_CASES = [("mamdr", "mlp_meta_mamdr", "plus"), ("mamdr", "mlp_meta_mamdr_batch", "plus"), ("mamdr", "mlp_meta_mamdr", "times"),
               ("dn", "mlp_meta_domain_negotiation", "plus"), ("reptile", "mlp_meta_reptile", "plus"),
               ("reptile", "mlp_meta_reptile_batch", "plus")]
@@ -271,25 +276,19 @@ def make_loops():
     base_model, dn, mamdr, reptile, sbm = import_reference()
     import numpy
     g = {}
-    for kind, name, method in LOOP_CASES:
+    # mamdr.py:75 / reptile.py:31 size the `batch` accumulators with K.int_shape / K.dtype of the Keras variables (TF): stand-ins only
+    for mod_K in (mamdr.K, reptile.K):
+        mod_K.int_shape = staticmethod(lambda p: p.shape)
+        mod_K.dtype = staticmethod(lambda p: "float32")
+    for kind, name, method, meta_idx in [c + (None,) for c in LOOP_CASES] + [c + (SUBSET_META_IDX,) for c in SUBSET_CASES]:
         cls = {"mamdr": mamdr.MAMDR, "dn": dn.DomainNegotiation, "reptile": reptile.Reptile}[kind]
         tc = dict(LOOP_TC, merged_method=method)
-        obj, model, base = _toy_wrapper(cls, base_model, tc, name)
-        if kind == "mamdr":
-            # mamdr.py:75 sizes the `batch` accumulators with K.int_shape / K.dtype of the Keras variables (TF): stand-ins only
-            mod_K = mamdr.K
-            mod_K.int_shape = staticmethod(lambda p: p.shape)
-            mod_K.dtype = staticmethod(lambda p: "float32")
-            obj._get_model_meta_parms = lambda o=obj, m=model: setattr(o, "model_meta_parms", [types.SimpleNamespace(shape=w.shape) for w in m.weights])
-        if kind == "reptile":
-            mod_K = reptile.K
-            mod_K.int_shape = staticmethod(lambda p: p.shape)
-            mod_K.dtype = staticmethod(lambda p: "float32")
-            obj._get_model_meta_parms = lambda o=obj, m=model: setattr(o, "model_meta_parms", [types.SimpleNamespace(shape=w.shape) for w in m.weights])
+        obj, model, base = _toy_wrapper(cls, base_model, tc, name, meta_idx)
         random.seed(LOOP_SEED)
         with contextlib.redirect_stdout(io.StringIO()):
             obj.train()
-        key = "%s|%s|" % (name, method)
+        key = "%s|%s|" % (name, method) + ("" if meta_idx is None else "subset|")
+        g[key + "live"] = flat_any(model.weights)               # the live model when train() returns (non-meta variables included)
         g[key + "steps"] = numpy.array(model.steps, dtype=numpy.int32)
         if kind == "mamdr":
             g[key + "theta"] = flat_any(obj.meta_weights)

@@ -1,0 +1,210 @@
+"""CPU: the PRODUCT's wrapper control flow (mamdr_b200/{mamdr,domain_negotiation,reptile,specific_base_model,maml}.py -- the real
+code, unmodified) against the reference's training loops EXECUTED in this repo's build container
+(tests/golden/reference_loops_v1.npz, make_reference_golden.py): the same sequence of train steps, theta, every theta_d, best
+snapshots and early-stop state, bit for bit.
+
+The wrappers drive the device through two seams only: `model.ctx.call(<C-ABI entry point>, pointers...)` and the base model's
+`run_train_pass`.  Here both are replaced by TEST stand-ins -- a numpy interpreter of the eight K9 / K10 meta sweeps acting on
+the pointed-to (CPU) arenas with the kernels' formulas, and the toy train step of the reference run -- so that the host logic
+runs without a GPU.  This is a test harness, not a product path: the product has no CPU fallback (tests/test_abi.py)."""
+import contextlib
+import ctypes as C
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from mamdr_b200.base_model import BaseModel
+from mamdr_b200.engine import NamedWeight
+from mamdr_b200.layout import ParamLayout
+from mamdr_b200.schedule import Schedule
+
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+import make_reference_golden as mrg  # noqa: E402
+
+LOOPS = np.load(os.path.join(ROOT, "tests", "golden", "reference_loops_v1.npz"))
+
+
+def _view(p, n):
+    return np.ctypeslib.as_array((C.c_float * int(n)).from_address(p.value))
+
+
+def _merge(a, b, method):
+    return a + b if method == 0 else a * b
+
+
+class _NumpyMetaOps(object):
+    """The K9 / K10 entry points of include/mamdr_b200.h on host arenas, with the formulas of csrc/meta_ops.cuh."""
+
+    def __init__(self):
+        self.launches = 0
+        self.calls = []
+
+    def call(self, name, *a):
+        self.calls.append(name)
+        f32 = np.float32
+        if name == "mamdr_copy":
+            dst, src, n = a[0], a[1], a[2]
+            _view(dst, n)[...] = _view(src, n)
+        elif name == "mamdr_merge":
+            out, th, ti, n, method = a[:5]
+            _view(out, n)[...] = _merge(_view(th, n), _view(ti, n), method)
+        elif name == "mamdr_dn_update":
+            theta, model, beta, n, model_out = a[:5]
+            t = _view(theta, n)
+            t += (_view(model, n) - t) * f32(beta)
+            if model_out is not None and model_out.value:
+                _view(model_out, n)[...] = t
+        elif name == "mamdr_dr_update":
+            ti, th, model, beta, n, method, model_out = a[:7]
+            x, t = _view(ti, n), _view(th, n)
+            x += (_view(model, n) - _merge(t, x, method)) * f32(beta)
+            if model_out is not None and model_out.value:
+                _view(model_out, n)[...] = _merge(t, x, method)
+        elif name == "mamdr_dr_accumulate":
+            acc, model, th, ti, n, method = a[:6]
+            t = _view(th, n)
+            d = _view(model, n) - _merge(t, _view(ti, n), method)
+            _view(acc, n)[...] += d if method == 0 else d * t
+        elif name == "mamdr_dr_apply_accum":
+            ti, acc, sample_num, beta, n = a[:5]
+            g = _view(acc, n)
+            _view(ti, n)[...] += g / f32(sample_num) * f32(beta)
+            g[...] = 0
+        elif name == "mamdr_sub":
+            out, x, y, n = a[:4]
+            _view(out, n)[...] = _view(x, n) - _view(y, n)
+        elif name == "mamdr_axpy_diff":
+            out, x, y, alpha, n = a[:5]
+            _view(out, n)[...] += (_view(x, n) - _view(y, n)) * f32(alpha)
+        else:
+            raise AssertionError("the wrappers called an entry point this harness does not interpret: " + name)
+
+
+class _ToyDeviceModel(object):
+    """What the wrappers touch on `model`: one flat arena in trainable_weights order + the toy train / eval step."""
+
+    def __init__(self):
+        w0 = mrg.toy_init(0)
+        self.layout = ParamLayout(["kernel0", "bias0"], [w.shape for w in w0])
+        self.params = torch.from_numpy(self.layout.pack(w0))
+        self.ctx = _NumpyMetaOps()
+        self.stream = None
+        self.steps = []
+        self.stateful_metric_functions = [self]
+
+    @property
+    def trainable_weights(self):
+        lo = self.layout
+        return [NamedWeight("dnn/%s:0" % n, v, o, k) for n, v, o, k in zip(lo.names, lo.views(self.params), lo.offsets, lo.numels)]
+
+    def views(self):
+        return [v.numpy() for v in self.layout.views(self.params)]
+
+    def reset_states(self):
+        pass
+
+    def reset_optimizer(self):
+        pass
+
+    @contextlib.contextmanager
+    def program(self, enabled=True):
+        yield False
+
+    def evaluate(self, data, steps=None):
+        return mrg.toy_eval(self.views(), data.domain)
+
+
+def _base(name, method, meta_parms=("all",)):
+    model = _ToyDeviceModel()
+    mk = lambda: {d: {"data": types.SimpleNamespace(domain=d), "n_step": mrg.N_STEP[d], "n_data": 4 * mrg.N_STEP[d]} for d in sorted(mrg.N_STEP)}   # noqa: E731
+    info = {d: {"n_train": 4 * mrg.N_STEP[d], "n_val": 2 + d, "n_test": 3 + d} for d in mrg.N_STEP}
+    base = types.SimpleNamespace(
+        model=model, train_config=dict(mrg.LOOP_TC, merged_method=method, meta_parms=list(meta_parms)), model_config={"name": name}, b200_config={},
+        dataset=types.SimpleNamespace(train_dataset=mk(), val_dataset=mk(), test_dataset=mk(), dataset_info=info),
+        n_domain=len(mrg.N_STEP), schedule=Schedule(mrg.LOOP_SEED), checkpoint_path="unused", log=lambda *a: None, saved=None, inits=[0])
+    for meth in ("val_and_test", "early_stop_step", "_weighted_auc", "_format_print_domain_metric", "_build_early_stop"):
+        setattr(base, meth, types.MethodType(getattr(BaseModel, meth), base))
+    base._build_early_stop()
+    base.save_model = lambda path: setattr(base, "saved", model.params.clone())
+    base.load_model = lambda path: model.params.copy_(base.saved)
+    base.stage_epoch_orders = lambda passes, mine=None: None
+
+    def run_train_pass(idx, steps=None):
+        n = base.dataset.train_dataset[idx]["n_step"] if steps is None else steps
+        for _ in range(n):
+            mrg.toy_step(model.views(), idx)
+            model.steps.append(idx)
+    base.run_train_pass = run_train_pass
+
+    def draw_initial_weights():
+        base.inits[0] += 1
+        return mrg.toy_init(base.inits[0])
+    base.draw_initial_weights = draw_initial_weights
+    return base, model
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def _flat(model, flat_tensor):
+    return mrg.flat_any([v.numpy() for v in model.layout.views(flat_tensor)])
+
+
+@pytest.mark.parametrize("kind,name,method", mrg.LOOP_CASES)
+def test_product_wrappers_replay_the_reference_loops(kind, name, method):
+    from mamdr_b200.domain_negotiation import DomainNegotiation
+    from mamdr_b200.mamdr import MAMDR
+    from mamdr_b200.reptile import Reptile
+    base, model = _base(name, method)
+    wrapper = {"mamdr": MAMDR, "dn": DomainNegotiation, "reptile": Reptile}[kind](base)
+    wrapper.train()                                             # the product's own train(): epochs, val, early stop, test
+    key = "%s|%s|" % (name, method)
+    np.testing.assert_array_equal(np.array(model.steps, dtype=np.int32), LOOPS[key + "steps"])
+    np.testing.assert_array_equal(_bits(_flat(model, wrapper.meta_weights.flat)), _bits(LOOPS[key + "theta"]))
+    np.testing.assert_array_equal(np.array([base.counter, base.best_metric], dtype=np.float64), LOOPS[key + "es"])
+    if kind == "mamdr":
+        for d in sorted(mrg.N_STEP):
+            np.testing.assert_array_equal(_bits(_flat(model, wrapper.domain_weights[d].flat)), _bits(LOOPS[key + "theta_%d" % d]),
+                                          err_msg="theta_%d" % d)
+            np.testing.assert_array_equal(_bits(_flat(model, wrapper.best_domain_weights[d].flat)), _bits(LOOPS[key + "best_theta_%d" % d]))
+        np.testing.assert_array_equal(_bits(_flat(model, wrapper.best_shared_weights.flat)), _bits(LOOPS[key + "best_theta"]))
+        used = set(model.ctx.calls)
+        assert "mamdr_merge" in used and ("mamdr_dr_accumulate" in used) == ("batch" in name)
+    else:
+        np.testing.assert_array_equal(_bits(_flat(model, base.saved)), _bits(LOOPS[key + "best"]))
+
+
+@pytest.mark.parametrize("kind,name,method", mrg.SUBSET_CASES)
+def test_product_wrappers_with_a_meta_parameter_subset(kind, name, method):
+    """meta_parms = ["kernel0"]: only the first variable is a meta parameter (as config #4's ["emb", "kernel_shared",
+    "bias_shared"] leaves the specific tensors out).  The product keeps full-arena snapshots and restricts every get / set /
+    update to the meta spans; the non-meta variable must be re-initialised by every init_layer, never reloaded from theta and
+    train through every pass exactly as in the reference run -- steps, theta, theta_d and the FULL live arena, bit for bit."""
+    from mamdr_b200.domain_negotiation import DomainNegotiation
+    from mamdr_b200.mamdr import MAMDR
+    from mamdr_b200.reptile import Reptile
+    base, model = _base(name, method, meta_parms=("kernel0",))
+    wrapper = {"mamdr": MAMDR, "dn": DomainNegotiation, "reptile": Reptile}[kind](base)
+    wrapper.train()
+    key = "%s|%s|subset|" % (name, method)
+    lo = model.layout
+    k = lo.numels[0]
+
+    def meta_part(flat_tensor):
+        return lo.views(flat_tensor)[0].numpy().reshape(-1)
+
+    assert [p.name for p in wrapper.model_meta_parms] == ["dnn/kernel0:0"] and wrapper.meta_ranges == [(0, 32)]
+    np.testing.assert_array_equal(np.array(model.steps, dtype=np.int32), LOOPS[key + "steps"])
+    np.testing.assert_array_equal(_bits(meta_part(wrapper.meta_weights.flat)), _bits(LOOPS[key + "theta"]))
+    if kind == "mamdr":
+        for d in sorted(mrg.N_STEP):
+            np.testing.assert_array_equal(_bits(meta_part(wrapper.domain_weights[d].flat)), _bits(LOOPS[key + "theta_%d" % d]))
+            np.testing.assert_array_equal(_bits(meta_part(wrapper.best_domain_weights[d].flat)), _bits(LOOPS[key + "best_theta_%d" % d]))
+    np.testing.assert_array_equal(_bits(_flat(model, model.params)), _bits(LOOPS[key + "live"]))
+    assert k == LOOPS[key + "theta"].size

@@ -203,6 +203,48 @@ def _toy_data(bs):
 import pytest  # noqa: E402
 
 
+@pytest.mark.parametrize("kind,name,method", mrg.SUBSET_CASES)
+def test_oracle_loops_with_a_meta_parameter_subset(kind, name, method):
+    """meta_parms selecting a SUBSET of the variables (config #4's ["emb", "kernel_shared", "bias_shared"]): in the reference the
+    other variables are re-initialised by every `init_layer` call (so they start from the LAST draw), are never reloaded from
+    theta and evolve through every pass; the oracle's `MetaSubset` view must reproduce that -- steps, theta, theta_d and the
+    full live model when train() returns, bit for bit."""
+    from mamdr_b200.schedule import Schedule
+    bs = 4
+    tc = dict(mrg.LOOP_TC, merged_method=method)
+    model = _ToyOracleModel()
+    sel = mrg.SUBSET_META_IDX
+    key = "%s|%s|subset|" % (name, method)
+    if kind == "mamdr":
+        last = mrg.toy_init(len(mrg.N_STEP))                   # init_layer ran once per domain over ALL layers (mamdr.py:31-33)
+        for i, w in enumerate(model.weights):
+            if i not in sel:
+                w[...] = last[i]
+        om = ometa.OracleMAMDR(ometa.MetaSubset(model, sel), _toy_data(bs), tc, bs, Schedule(mrg.LOOP_SEED),
+                               {d: [mrg.toy_init(d + 1)[i] for i in sel] for d in mrg.N_STEP}, name=name)
+    elif kind == "dn":
+        om = ometa.OracleDN(ometa.MetaSubset(model, sel), _toy_data(bs), tc, bs, Schedule(mrg.LOOP_SEED))
+    else:
+        om = ometa.OracleReptile(ometa.MetaSubset(model, sel), _toy_data(bs), tc, bs, Schedule(mrg.LOOP_SEED), name=name)
+    for epoch in range(tc["epoch"]):
+        om.train_epoch()
+        _, val_auc, _, _ = om.val_and_test("val")
+        if om.early_stop_step(val_auc):
+            break
+        om.val_and_test("test")
+    np.testing.assert_array_equal(np.array(model.steps, dtype=np.int32), LOOPS[key + "steps"])
+    np.testing.assert_array_equal(_bits(mrg.flat_any(om.meta_weights)), _bits(LOOPS[key + "theta"]))
+    if kind == "mamdr":
+        for d in sorted(mrg.N_STEP):
+            np.testing.assert_array_equal(_bits(mrg.flat_any(om.domain_weights[d])), _bits(LOOPS[key + "theta_%d" % d]))
+        np.testing.assert_array_equal(_bits(mrg.flat_any(model.weights)), _bits(LOOPS[key + "live"]))
+    else:
+        # DN / Reptile: `val_and_test("test")` reloads the best h5 (ALL variables); the oracle's snapshot is the meta view, so only
+        # the meta part of the live model is comparable here -- the product harness below compares the full arena
+        k = sum(int(np.prod(model.weights[i].shape)) for i in sel)
+        np.testing.assert_array_equal(_bits(mrg.flat_any([model.weights[i] for i in sel])), _bits(LOOPS[key + "live"][:k]))
+
+
 @pytest.mark.parametrize("kind,name,method", mrg.LOOP_CASES)
 def test_oracle_loops_replay_the_reference_loops(kind, name, method):
     """MAMDR.train / DomainNegotiation.train / Reptile.train of the reference, run for two epochs over a toy model whose train
