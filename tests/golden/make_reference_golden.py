@@ -431,6 +431,53 @@ def make_dataset():
     return out, mats
 
 
+# ---- the joint ('alternate') training loops of the base models: DeepCTR.train (DeepCTR/deepctr.py:63-93), Star.train
+# (Star/star.py:35-68), DeepMTLCTR.train (DeepMTLCTR/deep_mtl_ctr.py:68-98) -- note the reference's quirk that every
+# `val_and_test("test")` reloads the best checkpoint, so the next epoch continues from the BEST weights, not the latest
+JOINT_CASES = ["deepctr", "star", "mtl"]
+JOINT_EPOCHS = 5
+
+
+def make_joint():
+    import collections
+    import contextlib
+    import io
+    import random
+    base_model, dn, mamdr, reptile, sbm = import_reference()
+    import importlib
+    # model_zoo/__init__.py binds the CLASS `Star` over the sub-package name: go through sys.modules, not attribute traversal
+    ref_deepctr = importlib.import_module("model_zoo.DeepCTR.deepctr")
+    ref_mtl = importlib.import_module("model_zoo.DeepMTLCTR.deep_mtl_ctr")
+    ref_star = importlib.import_module("model_zoo.Star.star")
+    g = {}
+    for kind in JOINT_CASES:
+        cls = {"deepctr": ref_deepctr.DeepCTR, "star": ref_star.Star, "mtl": ref_mtl.DeepMTLCTR}[kind]
+        model = _ToyKeras()
+        mk = lambda: collections.OrderedDict((d, {"data": _ToyData(d), "n_step": N_STEP[d]}) for d in sorted(N_STEP))   # noqa: E731
+        info = {d: {"n_train": 4 * N_STEP[d], "n_val": 2 + d, "n_test": 3 + d} for d in N_STEP}
+        obj = cls.__new__(cls)
+        obj.model = model
+        obj.domain_model_dict = {d: model for d in N_STEP}        # DeepMTLCTR: one compiled sub-model per domain over shared variables
+        obj.dataset = types.SimpleNamespace(train_dataset=mk(), val_dataset=mk(), test_dataset=mk(), dataset_info=info)
+        obj.n_domain = len(N_STEP)
+        obj.train_config = dict(LOOP_TC, epoch=JOINT_EPOCHS, patience=2)
+        obj.model_config = {"name": kind}
+        obj.checkpoint_path = "/tmp/unused/model.h5"
+        saved = {}
+        obj.save_model = lambda path, m=model, s=saved: s.__setitem__("w", [w.copy() for w in m.weights])
+        obj.load_model = lambda path, m=model, s=saved: [a.__setitem__(Ellipsis, b) for a, b in zip(m.weights, s["w"])]
+        obj._build_early_stop()
+        random.seed(LOOP_SEED)
+        with contextlib.redirect_stdout(io.StringIO()):
+            obj.train()
+        key = "joint|%s|" % kind
+        g[key + "steps"] = np.array(model.steps, dtype=np.int32)
+        g[key + "live"] = flat_any(model.weights)
+        g[key + "best"] = flat_any(saved["w"])
+        g[key + "es"] = np.array([obj.counter, obj.best_metric, float(obj.early_stop)], dtype=np.float64)
+    return g
+
+
 def flat_any(ws):
     return np.concatenate([np.asarray(w, dtype=np.float32).reshape(-1) for w in ws])
 
@@ -442,7 +489,9 @@ if __name__ == "__main__":
     np.savez_compressed(out, **make())
     print(out, os.path.getsize(out), "bytes")
     out = os.path.join(HERE, "reference_loops_v1.npz")
-    np.savez_compressed(out, **make_loops())
+    loops = make_loops()
+    loops.update(make_joint())
+    np.savez_compressed(out, **loops)
     print(out, os.path.getsize(out), "bytes")
     import json
     out = os.path.join(HERE, "reference_dispatch_v1.json")

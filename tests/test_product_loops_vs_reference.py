@@ -208,3 +208,31 @@ def test_product_wrappers_with_a_meta_parameter_subset(kind, name, method):
             np.testing.assert_array_equal(_bits(meta_part(wrapper.best_domain_weights[d].flat)), _bits(LOOPS[key + "best_theta_%d" % d]))
     np.testing.assert_array_equal(_bits(_flat(model, model.params)), _bits(LOOPS[key + "live"]))
     assert k == LOOPS[key + "theta"].size
+
+
+@pytest.mark.parametrize("kind", mrg.JOINT_CASES)
+def test_product_joint_training_loops_replay_the_reference(kind):
+    """`DeepCTR.train` (DeepCTR/deepctr.py:63-93), `Star.train` (Star/star.py:35-68), `DeepMTLCTR.train`
+    (DeepMTLCTR/deep_mtl_ctr.py:68-98) executed over the toy stand-in vs the product's `train` methods (real code, run on a
+    stand-in `self`): shuffled domains, one full pass each, val -> early stop -> test, INCLUDING the reference's quirk that
+    `val_and_test("test")` reloads the best checkpoint so the next epoch continues from the best weights -- steps, the live
+    model, the kept checkpoint and the early-stop state, bit for bit."""
+    from mamdr_b200.deep_mtl_ctr import DeepMTLCTR
+    from mamdr_b200.deepctr import DeepCTR
+    from mamdr_b200.star import Star
+    cls = {"deepctr": DeepCTR, "star": Star, "mtl": DeepMTLCTR}[kind]
+    base, model = _base(kind, "plus")
+    obj = cls.__new__(cls)                       # no __init__: building the real model needs the GPU
+    for k, v in vars(base).items():
+        setattr(obj, k, v)
+    del obj.val_and_test, obj.early_stop_step, obj._weighted_auc, obj._format_print_domain_metric, obj._build_early_stop   # use the class's own
+    obj.train_config = dict(base.train_config, epoch=mrg.JOINT_EPOCHS, patience=2)
+    obj._build_early_stop()
+    obj.save_model = lambda path: setattr(obj, "saved", model.params.clone())
+    obj.load_model = lambda path: model.params.copy_(obj.saved)
+    obj.train()
+    key = "joint|%s|" % kind
+    np.testing.assert_array_equal(np.array(model.steps, dtype=np.int32), LOOPS[key + "steps"])
+    np.testing.assert_array_equal(_bits(_flat(model, model.params)), _bits(LOOPS[key + "live"]))
+    np.testing.assert_array_equal(_bits(_flat(model, obj.saved)), _bits(LOOPS[key + "best"]))
+    np.testing.assert_array_equal(np.array([obj.counter, obj.best_metric, float(obj.early_stop)], dtype=np.float64), LOOPS[key + "es"])
