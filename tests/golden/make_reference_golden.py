@@ -478,6 +478,55 @@ def make_joint():
     return g
 
 
+# ---- output layout: BaseModel.__init__ paths (base_model.py:23-28) and save_result (base_model.py:183-200) --------------------
+RESULT_CONFIG = {"model": {"name": "mlp_meta_mamdr_finetune", "hidden_dim": [256, 128, 64]},
+                 "train": {"checkpoint_path": "checkpoint", "result_save_path": "result", "patience": 3},
+                 "dataset": {"name": "Taobao", "domain_split_path": "split_by_theme_10", "seed": 123}}
+RESULT_ARGS = (0.512345, 0.734567, {0: 0.5, 1: 0.52}, {0: 0.71, 1: 0.76})
+RESULT_INFO = {"n_user": 7, "n_item": 5, 0: {"n_train": 3, "n_val": 1, "n_test": 2, "ctr_ratio": 0.3}, "total_train": 3}
+
+
+def result_layout(base_model_module, base_cls, root, extra_config=None):
+    """Build a BaseModel subclass instance whose model just records `save_weights`, run save_result under `root` with the
+    clock frozen, and describe what was written."""
+    import copy
+    import json
+    cfg = copy.deepcopy(RESULT_CONFIG)
+    cfg["train"]["checkpoint_path"] = os.path.join(root, "checkpoint")
+    cfg["train"]["result_save_path"] = os.path.join(root, "result")
+    if extra_config:
+        cfg.update(extra_config)
+    written = []
+    toy = types.SimpleNamespace(save_weights=lambda path: (written.append(path), open(path, "wb").close()), load_weights=lambda path: None)
+    sub = type("Toy", (base_cls,), {"build_model": lambda self: toy})
+    dataset = types.SimpleNamespace(n_uid=7, n_pid=5, n_domain=1, conf=cfg["dataset"], dataset_info=RESULT_INFO, device=None)
+    real = base_model_module.time.strftime
+    base_model_module.time.strftime = lambda *a: "Mon-Jan-01-00-00-00"
+    try:
+        obj = sub(dataset, cfg)
+        obj.save_result(*RESULT_ARGS)
+    finally:
+        base_model_module.time.strftime = real
+    rel = lambda p: os.path.relpath(p, root)   # noqa: E731
+    files = {}
+    for dirpath, _, names in os.walk(os.path.join(root, "result")):
+        for n in sorted(names):
+            full = os.path.join(dirpath, n)
+            files[rel(full)] = json.load(open(full)) if n.endswith((".json", ".example")) else "<binary>"
+    for k in list(files):                       # the config echo contains the temp root: normalise
+        if k.endswith("config.json.example"):
+            files[k]["train"]["checkpoint_path"] = rel(files[k]["train"]["checkpoint_path"])
+            files[k]["train"]["result_save_path"] = rel(files[k]["train"]["result_save_path"])
+    return {"checkpoint_path": rel(obj.checkpoint_path), "result_path": rel(obj.result_path), "files": files,
+            "save_weights": [rel(p) for p in written]}
+
+
+def make_result_layout():
+    import tempfile
+    base_model, dn, mamdr, reptile, sbm = import_reference()
+    return result_layout(base_model, base_model.BaseModel, tempfile.mkdtemp(prefix="mamdr_ref_result_"))
+
+
 def flat_any(ws):
     return np.concatenate([np.asarray(w, dtype=np.float32).reshape(-1) for w in ws])
 
@@ -497,6 +546,10 @@ if __name__ == "__main__":
     out = os.path.join(HERE, "reference_dispatch_v1.json")
     with open(out, "w") as f:
         json.dump(make_dispatch(), f, indent=1)
+    print(out, os.path.getsize(out), "bytes")
+    out = os.path.join(HERE, "reference_result_layout_v1.json")
+    with open(out, "w") as f:
+        json.dump(make_result_layout(), f, indent=1)
     print(out, os.path.getsize(out), "bytes")
     info, mats = make_dataset()
     out = os.path.join(HERE, "reference_dataset_v1.json")

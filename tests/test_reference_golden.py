@@ -370,3 +370,17 @@ def test_product_ondisk_ingest_matches_the_reference(tmp_path):
         assert list(getattr(ds, split + "_dataset").keys()) == sorted(getattr(ds, split + "_dataset").keys())   # domains in numeric order
     np.testing.assert_array_equal(_bits(ds.user_table), _bits(emb["user_emb"]))
     np.testing.assert_array_equal(_bits(ds.item_table), _bits(emb["item_emb"]))
+
+
+def test_product_output_layout_matches_the_reference(tmp_path):
+    """`BaseModel.__init__`'s checkpoint / result paths (base_model.py:23-28) and `save_result`
+    (base_model.py:183-200: folder name, dataset_info.json, config.json.example, result.json, model_parameters.h5) EXECUTED
+    with the clock frozen vs mamdr_b200/base_model.py run the same way: the same relative paths, file set and JSON contents."""
+    import mamdr_b200.base_model as p_base
+    ref = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_result_layout_v1.json")))
+    got = mrg.result_layout(p_base, p_base.BaseModel, str(tmp_path))
+    assert got["checkpoint_path"] == ref["checkpoint_path"] and got["result_path"] == ref["result_path"]
+    assert sorted(got["files"]) == sorted(ref["files"])
+    for k in ref["files"]:
+        assert got["files"][k] == ref["files"][k], k
+    assert got["save_weights"] == ref["save_weights"]
