@@ -9,6 +9,30 @@ import time
 from .schedule import Schedule
 
 
+def keras_fit_with_callbacks(model, run_pass, evaluate_val, epochs, patience, min_delta=1e-4):
+    """``model.fit(..., epochs=epochs, callbacks=[EarlyStopping(monitor='val_AUC', patience, mode='max', min_delta=1e-4),
+    ModelCheckpoint(monitor='val_AUC', save_best_only=True, mode='max')])`` as the finetune stage runs it
+    (``base_model.py:76-87``, ``specific_base_model.py:131-142``).  [EXT] tf.keras 1.12 callback semantics:
+    ModelCheckpoint saves when ``current > best`` (its own running best, no min_delta); EarlyStopping resets its wait only when
+    ``current - min_delta > best`` and moves ITS best only then -- a run of sub-``min_delta`` improvements does not ratchet it up;
+    it stops when ``wait >= patience``.  Returns the checkpointed weights (the epoch with the best val_AUC)."""
+    ck_best, best_w = None, None
+    es_best, wait = None, 0
+    for _ in range(epochs):
+        model.reset_states()
+        run_pass()
+        _, val_auc = evaluate_val()
+        if ck_best is None or val_auc > ck_best:                    # ModelCheckpoint(save_best_only, mode=max)
+            ck_best, best_w = val_auc, model.get_weights()
+        if es_best is None or val_auc - min_delta > es_best:        # EarlyStopping(min_delta, mode=max): best starts at -inf
+            es_best, wait = val_auc, 0
+        else:
+            wait += 1
+            if wait >= patience:
+                break
+    return best_w if best_w is not None else model.get_weights()
+
+
 class BaseModel(object):
     def __init__(self, dataset, config):
         self.n_uid = dataset.n_uid
@@ -103,6 +127,46 @@ class BaseModel(object):
         self.samples_trained = getattr(self, 'samples_trained', 0) + min(data.n_data, n * data.batch_size)
         self.last_pass_losses = self.model.fit_pass(data, n, order=order)
         return self.last_pass_losses
+
+    def separate_train_val_test(self, init_parms=True):
+        """base_model.py:41-109 with ``init_parms=False`` -- the ``finetune`` stage of the wrappers WITHOUT domain-specific
+        weights (``*_meta_domain_negotiation_finetune``, ``*_meta_reptile_finetune``; run.py:82-85 loads the best checkpoint
+        first): per domain restart from those weights, plain SGD with ``train_config['learning_rate']`` (:69), Keras
+        EarlyStopping(val_AUC) + best-val_AUC checkpoint, load it, test; the starting weights are restored at the end."""
+        import torch
+        if init_parms:
+            raise NotImplementedError("separate training from scratch is outside the hot path")
+        m = self.model
+        weights = m.get_weights()                                   # :65 save init weight
+        domain_loss, domain_auc = {}, {}
+        all_loss, all_auc = 0, 0
+        ckpt_dir = osp.dirname(self.checkpoint_path)
+        for domain_idx, train_d in self.dataset.train_dataset.items():
+            m.compile(optimizer="sgd", lr=self.train_config['learning_rate'])    # :67-71
+            m.set_weights(weights)                                  # :72
+            self.log("Train on domain: {}".format(domain_idx))
+            if not osp.exists(ckpt_dir):
+                os.makedirs(ckpt_dir)
+            val_d = self.dataset.val_dataset[domain_idx]
+            best_w = keras_fit_with_callbacks(m, lambda: self.run_train_pass(domain_idx),
+                                              lambda: m.evaluate(val_d['data'], steps=val_d['n_step']),
+                                              self.train_config['epoch'], self.train_config['patience'])
+            m.set_weights(best_w)                                   # :89 load_weights(chk_path)
+            torch.save(best_w.cpu(), osp.join(ckpt_dir, "domain_{}.h5".format(domain_idx)))
+            test_d = self.dataset.test_dataset[domain_idx]
+            p_loss, p_auc = m.evaluate(test_d['data'], steps=test_d['n_step'])
+            domain_loss[domain_idx], domain_auc[domain_idx] = p_loss, p_auc
+            all_loss += p_loss
+            all_auc += p_auc
+        m.set_weights(weights)                                      # :102 restore
+        m.compile(optimizer="adam")
+        avg_loss = all_loss / len(domain_loss)
+        avg_auc = all_auc / len(domain_auc)
+        self.log("Loss: ", domain_loss)
+        self._format_print_domain_metric("AUC", domain_auc)
+        weighted_auc = self._weighted_auc("test", domain_auc)
+        self.log("Overall {} Loss: {}, AUC: {}, Weighted AUC: {}".format("test", avg_loss, avg_auc, weighted_auc))
+        return avg_loss, avg_auc, domain_loss, domain_auc
 
     def val_and_test(self, mode):
         """base_model.py:111-144"""

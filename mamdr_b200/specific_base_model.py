@@ -9,6 +9,7 @@ import os.path as osp
 import torch
 
 from . import _lib
+from .base_model import keras_fit_with_callbacks
 from .engine import _ptr
 from .maml import MAML, MetaWeights
 
@@ -124,21 +125,10 @@ class SpecificBase(MAML):
             self.log("Train on domain: {}".format(domain_idx))
             if not osp.exists(ckpt_dir):
                 os.makedirs(ckpt_dir)
-            best_val, best_w, wait = None, None, 0
             val_d = self.dataset.val_dataset[domain_idx]
-            for _ in range(self.train_config['epoch']):             # Keras fit(epochs=...) with callbacks
-                m.reset_states()
-                self.run_train_pass(domain_idx)
-                _, val_auc = m.evaluate(val_d['data'], steps=val_d['n_step'])
-                if best_val is None or val_auc > best_val:          # ModelCheckpoint(save_best_only, max)
-                    best_w = m.get_weights()
-                if best_val is None or val_auc - 1e-4 > best_val:   # EarlyStopping(min_delta=1e-4, max)
-                    best_val, wait = val_auc if best_val is None else max(best_val, val_auc), 0
-                else:
-                    best_val = max(best_val, val_auc)
-                    wait += 1
-                    if wait >= self.train_config['patience']:
-                        break
+            best_w = keras_fit_with_callbacks(m, lambda: self.run_train_pass(domain_idx),      # Keras fit(epochs=...) with the
+                                              lambda: m.evaluate(val_d['data'], steps=val_d['n_step']),   # two callbacks, :131-142
+                                              self.train_config['epoch'], self.train_config['patience'])
             m.set_weights(best_w)                                   # :143 load_weights(chk_path)
             torch.save(best_w.cpu(), osp.join(ckpt_dir, "domain_{}.h5".format(domain_idx)))
             test_d = self.dataset.test_dataset[domain_idx]

@@ -134,15 +134,18 @@ class StarModel(MLPModel):
         return f[0], f[1]
 
     def _train_step(self, data, offset, rows, loss_slot, probs=None, with_auc=True):
-        if self.optimizer != "adam":
-            raise NotImplementedError("the STAR path applies Adam (the reference's compile, star.py:24-27)")
         b = self._batch(data, offset, rows, True)
         st = self.stream
         self.ctx.call("mamdr_star_train_step", C.byref(self.desc), C.byref(b), _ptr(self.user_table), _ptr(self.item_table),
                       _ptr(self.params), _ptr(self.grads), _ptr(self.pn_state), _ptr(self.ws), self.ws_bytes, _ptr(loss_slot),
                       _ptr(probs), _ptr(self.auc_acc if with_auc else None), _ptr(self.thresholds), self.num_thresholds, st)
-        self.ctx.call("mamdr_adam_step", _ptr(self.params), _ptr(self.m), _ptr(self.v), _ptr(self.grads),
-                      self.params.numel(), _ptr(self.opt_state), self.lr, self.beta1, self.beta2, self.eps, st)
+        if self.optimizer == "adam":     # the reference's compile, star.py:24-27
+            self.ctx.call("mamdr_adam_step", _ptr(self.params), _ptr(self.m), _ptr(self.v), _ptr(self.grads),
+                          self.params.numel(), _ptr(self.opt_state), self.lr, self.beta1, self.beta2, self.eps, st)
+        else:                            # the finetune stage's GradientDescentOptimizer (specific_base_model.py:120): the gradient
+            #                              arena is fully written (zero outside the batch's domain slices), one sweep over it
+            self.ctx.call("mamdr_sgd_step", _ptr(self.params), _ptr(self.grads), self.params.numel(), _ptr(self.opt_state),
+                          self.sgd_lr, st)
         L = len(self.hidden)
         self.ctx.launches += 2 + 4 + L + 1 + L + L + 1 + 2 + 1   # memsets, assemble, pn x2, eff, fwd, head, dH/dY, dW, colsum, grads, pn bwd, adam
 

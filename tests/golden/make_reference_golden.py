@@ -199,6 +199,9 @@ class _ToyData(object):
     def make_initializable_iterator(self):
         return types.SimpleNamespace(domain=self.domain, initializer=None)
 
+    def repeat(self):
+        return self
+
 
 class _ToyKeras(object):
     def __init__(self):
@@ -207,9 +210,41 @@ class _ToyKeras(object):
         self.stateful_metric_functions = []
         self.layers = []
 
-    def fit(self, it, steps_per_epoch=1, **kw):
-        for _ in range(steps_per_epoch):
-            self.train_on_batch(it)
+    def fit(self, it, steps_per_epoch=1, callbacks=None, validation_data=None, validation_steps=None, epochs=1, initial_epoch=0, **kw):
+        """One Keras epoch of the training loops; with `callbacks` (the finetune stage) the Keras epoch loop with validation."""
+        if not callbacks:
+            for _ in range(steps_per_epoch):
+                self.train_on_batch(it)
+            return
+        self.stop_training = False
+        for cb in callbacks:
+            cb.model = self
+            cb.on_train_begin()
+        for epoch in range(initial_epoch, epochs):
+            for _ in range(steps_per_epoch):
+                self.train_on_batch(it)
+            val_loss, val_auc = toy_eval(self.weights, validation_data.domain)
+            for cb in callbacks:
+                cb.on_epoch_end(epoch, {"val_loss": val_loss, "val_AUC": val_auc})
+            if self.stop_training:
+                break
+
+    def get_weights(self):
+        return [w.copy() for w in self.weights]
+
+    def set_weights(self, ws):
+        for a, b in zip(self.weights, ws):
+            a[...] = b
+
+    def compile(self, **kw):
+        self.compiles = getattr(self, "compiles", 0) + 1
+
+    def save_weights(self, path, overwrite=True):
+        self.files = getattr(self, "files", {})
+        self.files[os.path.basename(path)] = [w.copy() for w in self.weights]
+
+    def load_weights(self, path):
+        self.set_weights(self.files[os.path.basename(path)])
 
     def train_on_batch(self, it):
         toy_step(self.weights, it.domain)
@@ -431,6 +466,87 @@ def make_dataset():
     return out, mats
 
 
+# ---- [EXT] tf.keras 1.12 callbacks used by the finetune stage, restated (tensorflow/python/keras/callbacks.py) -------------------
+class KerasEarlyStopping(object):
+    def __init__(self, monitor='val_loss', min_delta=0, patience=0, verbose=0, mode='auto', baseline=None):
+        assert mode == 'max'
+        self.monitor, self.patience, self.min_delta = monitor, patience, abs(min_delta)
+
+    def on_train_begin(self, logs=None):
+        self.wait, self.best = 0, -np.inf
+
+    def on_epoch_end(self, epoch, logs=None):
+        current = logs[self.monitor]
+        if np.greater(current - self.min_delta, self.best):
+            self.best, self.wait = current, 0
+        else:
+            self.wait += 1
+            if self.wait >= self.patience:
+                self.model.stop_training = True
+
+
+class KerasModelCheckpoint(object):
+    def __init__(self, filepath, monitor='val_loss', verbose=0, save_best_only=False, save_weights_only=False, mode='auto', period=1):
+        assert mode == 'max' and save_best_only and save_weights_only
+        self.filepath, self.monitor, self.best = filepath, monitor, -np.inf
+
+    def on_train_begin(self, logs=None):
+        pass
+
+    def on_epoch_end(self, epoch, logs=None):
+        current = logs[self.monitor]
+        if np.greater(current, self.best):
+            self.best = current
+            self.model.save_weights(self.filepath, overwrite=True)
+
+
+FINETUNE_CASES = [("mamdr", "mlp_meta_mamdr_finetune", "plus"), ("dn", "mlp_meta_domain_negotiation_finetune", "plus"),
+                  ("reptile", "mlp_meta_reptile_finetune", "plus")]
+FINETUNE_EPOCHS = 40
+
+
+def make_finetune():
+    """run.py:66-85 for `*_finetune` names: train -> val_and_test("test") -> load_model(best) -> separate_train_val_test(False)
+    (specific_base_model.py:99-162 for MAMDR, base_model.py:41-109 for DN / Reptile), over the toy stand-in with the two Keras
+    callbacks restated above."""
+    import contextlib
+    import io
+    import random
+    base_model, dn, mamdr, reptile, sbm = import_reference()
+    cbs = types.SimpleNamespace(EarlyStopping=KerasEarlyStopping, ModelCheckpoint=KerasModelCheckpoint, TensorBoard=_Any)
+    sbm.callbacks = cbs
+    base_model.callbacks = cbs
+    sbm.AUC = base_model.AUC = lambda **kw: "AUC-metric"      # utils/auc.py builds TF variables; only handed to model.compile here
+    g = {}
+    for kind, name, method in FINETUNE_CASES:
+        cls = {"mamdr": mamdr.MAMDR, "dn": dn.DomainNegotiation, "reptile": reptile.Reptile}[kind]
+        tc = dict(LOOP_TC, merged_method=method, loss="binary_crossentropy", learning_rate=0.001)
+        obj, model, base = _toy_wrapper(cls, base_model, tc, name)
+        if kind != "mamdr":
+            base.separate_train_val_test = types.MethodType(base_model.BaseModel.separate_train_val_test, base)
+            base.save_model = lambda path, m=model: m.save_weights(path)         # base_model.py:177-181
+            base.load_model = lambda path, m=model: m.load_weights(path)
+        else:
+            base.save_model = lambda path, m=model: m.save_weights(path)
+            base.load_model = lambda path, m=model: m.load_weights(path)
+        random.seed(LOOP_SEED)
+        with contextlib.redirect_stdout(io.StringIO()):
+            obj.train()
+            obj.val_and_test("test")
+            n_train_steps = len(model.steps)
+            obj.load_model(obj.checkpoint_path)
+            tc["epoch"] = FINETUNE_EPOCHS
+            avg_loss, avg_auc, domain_loss, domain_auc = obj.separate_train_val_test(init_parms=False)
+        key = "finetune|%s|" % name
+        g[key + "steps"] = np.array(model.steps[n_train_steps:], dtype=np.int32)
+        g[key + "result"] = np.array([avg_loss, avg_auc] + [domain_loss[d] for d in sorted(N_STEP)] + [domain_auc[d] for d in sorted(N_STEP)],
+                                     dtype=np.float64)
+        g[key + "live"] = flat_any(model.weights)
+        for d in sorted(N_STEP):
+            g[key + "ckpt_%d" % d] = flat_any(model.files["domain_%d.h5" % d])
+    return g
+
+
 # ---- the joint ('alternate') training loops of the base models: DeepCTR.train (DeepCTR/deepctr.py:63-93), Star.train
 # (Star/star.py:35-68), DeepMTLCTR.train (DeepMTLCTR/deep_mtl_ctr.py:68-98) -- note the reference's quirk that every
 # `val_and_test("test")` reloads the best checkpoint, so the next epoch continues from the BEST weights, not the latest
@@ -540,6 +656,7 @@ if __name__ == "__main__":
     out = os.path.join(HERE, "reference_loops_v1.npz")
     loops = make_loops()
     loops.update(make_joint())
+    loops.update(make_finetune())
     np.savez_compressed(out, **loops)
     print(out, os.path.getsize(out), "bytes")
     import json

@@ -118,6 +118,16 @@ class _ToyDeviceModel(object):
     def evaluate(self, data, steps=None):
         return mrg.toy_eval(self.views(), data.domain)
 
+    # the finetune stage's Keras-like surface (engine.MLPModel: compile / get_weights / set_weights)
+    def compile(self, optimizer="adam", lr=None):
+        self.optimizer = optimizer
+
+    def get_weights(self):
+        return self.params.clone()
+
+    def set_weights(self, flat):
+        self.params.copy_(flat)
+
 
 def _base(name, method, meta_parms=("all",)):
     model = _ToyDeviceModel()
@@ -236,3 +246,36 @@ def test_product_joint_training_loops_replay_the_reference(kind):
     np.testing.assert_array_equal(_bits(_flat(model, model.params)), _bits(LOOPS[key + "live"]))
     np.testing.assert_array_equal(_bits(_flat(model, obj.saved)), _bits(LOOPS[key + "best"]))
     np.testing.assert_array_equal(np.array([obj.counter, obj.best_metric, float(obj.early_stop)], dtype=np.float64), LOOPS[key + "es"])
+
+
+@pytest.mark.parametrize("kind,name,method", mrg.FINETUNE_CASES)
+def test_product_finetune_stage_replays_the_reference(tmp_path, kind, name, method):
+    """run.py:66-85 for `*_finetune` names -- train, test, reload the best checkpoint, then `separate_train_val_test(False)`
+    (specific_base_model.py:99-162 for MAMDR: restart every domain from best theta (+) best theta_d; base_model.py:41-109 for DN /
+    Reptile: restart from the reloaded weights) -- EXECUTED over the toy stand-in with the two Keras callbacks restated
+    ([EXT] tf.keras 1.12 EarlyStopping(min_delta=1e-4) / ModelCheckpoint(save_best_only)), vs the product's own code: the same
+    finetune steps, per-domain checkpoints, returned losses / AUCs and the restored live model, bit for bit.  40 epochs of a
+    contracting toy map make the val_AUC gains fall below min_delta, which is where the EarlyStopping bookkeeping matters."""
+    from mamdr_b200.domain_negotiation import DomainNegotiation
+    from mamdr_b200.mamdr import MAMDR
+    from mamdr_b200.reptile import Reptile
+    base, model = _base(name, method)
+    base.checkpoint_path = str(tmp_path / "ckpt" / "model_parameters.h5")
+    base.train_config.update(loss="binary_crossentropy", learning_rate=0.001)
+    base.separate_train_val_test = types.MethodType(BaseModel.separate_train_val_test, base)
+    wrapper = {"mamdr": MAMDR, "dn": DomainNegotiation, "reptile": Reptile}[kind](base)
+    wrapper.train()
+    wrapper.val_and_test("test")
+    n_train_steps = len(model.steps)
+    wrapper.load_model(wrapper.checkpoint_path)
+    base.train_config["epoch"] = mrg.FINETUNE_EPOCHS
+    avg_loss, avg_auc, domain_loss, domain_auc = wrapper.separate_train_val_test(init_parms=False)
+    key = "finetune|%s|" % name
+    np.testing.assert_array_equal(np.array(model.steps[n_train_steps:], dtype=np.int32), LOOPS[key + "steps"])
+    got = np.array([avg_loss, avg_auc] + [domain_loss[d] for d in sorted(mrg.N_STEP)] + [domain_auc[d] for d in sorted(mrg.N_STEP)])
+    np.testing.assert_array_equal(got, LOOPS[key + "result"])
+    np.testing.assert_array_equal(_bits(_flat(model, model.params)), _bits(LOOPS[key + "live"]))
+    for d in sorted(mrg.N_STEP):
+        ck = torch.load(str(tmp_path / "ckpt" / ("domain_%d.h5" % d)))
+        np.testing.assert_array_equal(_bits(_flat(model, ck)), _bits(LOOPS[key + "ckpt_%d" % d]), err_msg="checkpoint of domain %d" % d)
+    assert model.optimizer == "adam"        # the stage hands the model back compiled with the training optimizer
