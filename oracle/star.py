@@ -2,7 +2,9 @@
 
 Follows ``/root/reference/model_zoo/Star/star.py:70-113`` (topology), ``Star/partitioned_norm.py:44-203``
 (PartitionedNorm) and ``Star/star_fcn.py:50-139`` (StarFCN); compile / loss / optimizer as in ``star.py:23-33``
-(BCE, one AdamOptimizer, AUC(500)).  SURVEY.md Appendix A-8.  Parity unpinned: the [EXT] Keras defaults are defined here.
+(BCE, one AdamOptimizer, AUC(500)).  SURVEY.md Appendix A-8.  The forward of both layers is PINNED to the reference's own `call` methods executed on numpy
+(tests/golden/reference_star_layers_v1.npz, tests/test_reference_golden.py); the [EXT] Keras pieces (zero-debiased moving
+average, initialisers, BCE, Adam) are defined here and remain unpinned.
 
   X = [E_u[uid] | E_i[pid] | E_d[dom]]                                   plain Keras Embeddings, NO l2 regulariser
   PartitionedNorm (norm = "pn"), d = domain of the batch:

@@ -643,6 +643,97 @@ def make_result_layout():
     return result_layout(base_model, base_model.BaseModel, tempfile.mkdtemp(prefix="mamdr_ref_result_"))
 
 
+# ---- the reference's OWN Keras layers of the STAR tower (Star/star_fcn.py:105-139, Star/partitioned_norm.py:102-203) ------------
+# Unlike the mlp / MMOE towers (third-party deepctr), these layers are reference code.  Their `call` methods are executed on numpy
+# arrays with the handful of TF / Keras-backend ops they use replaced by numpy equivalents ([EXT] tf.nn.moments,
+# tf.nn.batch_normalization; K.moving_average_update only RECORDS which moving statistic receives which value).
+STAR_SHAPE = dict(n_domain=3, b=9, emb_dim=(4, 4, 2), n_in=10, hidden=(6, 4), domain=2)
+
+
+class _Arr(np.ndarray):
+    def get_shape(self):
+        return types.SimpleNamespace(as_list=lambda: list(self.shape))
+
+
+def star_problem():
+    rng = np.random.default_rng(2025)
+    S = STAR_SHAPE
+    D, n = S["n_domain"], S["n_in"]
+    w = {"gamma_sp": 1 + 0.3 * rng.standard_normal((D, n)), "beta_sp": 0.2 * rng.standard_normal((D, n)),
+         "gamma_sh": 1 + 0.3 * rng.standard_normal(n), "beta_sh": 0.2 * rng.standard_normal(n),
+         "moving_mean": 0.1 * rng.standard_normal((D, n)), "moving_var": 0.5 + rng.random((D, n)),
+         "user_table": rng.standard_normal((S["b"], S["emb_dim"][0])), "item_table": rng.standard_normal((S["b"], S["emb_dim"][1])),
+         "domain_emb": rng.standard_normal((D, S["emb_dim"][2]))}
+    # the tower's input: [E_u[uid] | E_i[pid] | E_d[dom]] with uid = pid = 0..b-1 (the domain block is constant within a batch)
+    w["X"] = np.concatenate([w["user_table"], w["item_table"], np.broadcast_to(w["domain_emb"][S["domain"]], (S["b"], S["emb_dim"][2]))], axis=1)
+    dims = (n,) + S["hidden"]
+    for l in range(len(S["hidden"])):
+        w["k_sp%d" % l] = 0.4 * rng.standard_normal((D, dims[l], dims[l + 1]))
+        w["b_sp%d" % l] = 0.1 * rng.standard_normal((D, dims[l + 1]))
+        w["k_sh%d" % l] = 0.4 * rng.standard_normal((dims[l], dims[l + 1]))
+        w["b_sh%d" % l] = 0.1 * rng.standard_normal(dims[l + 1])
+    return w
+
+
+def make_star_layers():
+    import importlib
+    import_reference()
+    sf = importlib.import_module("model_zoo.Star.star_fcn")
+    pn = importlib.import_module("model_zoo.Star.partitioned_norm")
+    S, w = STAR_SHAPE, star_problem()
+    dom = S["domain"]
+    ind = np.full((S["b"], 1), dom, dtype=np.int32)
+    ns = types.SimpleNamespace
+    np_tf = ns(cast=lambda x, t: int(x), multiply=np.multiply, add=np.add, int32=None, equal=lambda a, b: a == b,
+               case=lambda pairs, exclusive=False, name=None: next(fn for pred, fn in pairs if pred)())
+    np_nn = ns(embedding_lookup=lambda table, idx: table[idx], bias_add=lambda x, b: x + b)
+    # ---- PartitionedNorm.call
+    updates = []
+
+    def batch_normalization(x, mean, var, beta, gamma, epsilon):        # [EXT] tf.nn.batch_normalization
+        inv = gamma / np.sqrt(var + epsilon)
+        return x * inv + (beta - mean * inv)
+
+    def normalize_batch_in_training(x, gamma, beta, reduction_axes, epsilon):   # [EXT] tf.nn.moments (biased variance)
+        mean = np.mean(x, axis=tuple(reduction_axes))
+        var = np.mean((x - mean) ** 2, axis=tuple(reduction_axes))
+        return batch_normalization(x, mean, var, beta, gamma, epsilon), mean, var
+
+    pn.tf, pn.nn = np_tf, np_nn
+    pn.K = ns(learning_phase=lambda: 1, reshape=np.reshape, batch_normalization=batch_normalization,
+              normalize_batch_in_training=normalize_batch_in_training,
+              moving_average_update=lambda var, value, momentum: updates.append((var["name"], np.array(value), momentum)),
+              in_train_phase=lambda a, b, training=None: a if training else b())
+    layer = pn.PartitionedNorm.__new__(pn.PartitionedNorm)
+    layer.n_domain, layer.axis, layer.momentum, layer.epsilon = S["n_domain"], -1, 0.99, 1e-3
+    layer.PN_Gamma, layer.PN_Beta, layer.Shared_Gamma, layer.Shared_Beta = w["gamma_sp"], w["beta_sp"], w["gamma_sh"], w["beta_sh"]
+    layer.PN_Mean = [{"name": "mean_%d" % d, "value": w["moving_mean"][d]} for d in range(S["n_domain"])]
+    layer.PN_Var = [{"name": "var_%d" % d, "value": w["moving_var"][d]} for d in range(S["n_domain"])]
+    layer.add_update = lambda *a, **k: None
+    X = w["X"].view(_Arr)
+    h0_train = np.asarray(layer.call([X, ind], training=1))
+    g = {"star|h0_train": h0_train}
+    assert [u[0] for u in updates] == ["mean_%d" % dom, "var_%d" % dom] and all(u[2] == 0.99 for u in updates)
+    g["star|batch_mean"], g["star|batch_var"] = updates[0][1], updates[1][1]
+    # inference: the K.batch_normalization branch reads the batch's domain's moving statistics through tf.case
+    pn.K.batch_normalization = lambda x, mean, var, beta, gamma, epsilon: batch_normalization(
+        x, mean["value"] if isinstance(mean, dict) else mean, var["value"] if isinstance(var, dict) else var, beta, gamma, epsilon)
+    g["star|h0_eval"] = np.asarray(layer.call([X, ind], training=0))
+    # ---- StarFCN.call, layer by layer on the training-mode output
+    sf.tf, sf.nn = np_tf, np_nn
+    sf.ops = ns(convert_to_tensor=lambda x, dtype=None: np.asarray(x))
+    sf.common_shapes = ns(rank=lambda x: x.ndim)
+    sf.gen_math_ops = ns(mat_mul=lambda a, b: a @ b)
+    h = h0_train
+    for l in range(len(S["hidden"])):
+        fcn = sf.StarFCN.__new__(sf.StarFCN)
+        fcn.PN_Kernel, fcn.PN_Bias, fcn.Shred_Kernel, fcn.Shared_Bias = w["k_sp%d" % l], w["b_sp%d" % l], w["k_sh%d" % l], w["b_sh%d" % l]
+        fcn.use_bias, fcn.activation, fcn.dtype = True, (lambda x: np.maximum(x, 0)), "float64"
+        h = np.asarray(fcn.call([h, ind]))
+        g["star|h%d" % (l + 1)] = h
+    return g
+
+
 def flat_any(ws):
     return np.concatenate([np.asarray(w, dtype=np.float32).reshape(-1) for w in ws])
 
@@ -667,6 +758,9 @@ if __name__ == "__main__":
     out = os.path.join(HERE, "reference_result_layout_v1.json")
     with open(out, "w") as f:
         json.dump(make_result_layout(), f, indent=1)
+    print(out, os.path.getsize(out), "bytes")
+    out = os.path.join(HERE, "reference_star_layers_v1.npz")
+    np.savez_compressed(out, **make_star_layers())
     print(out, os.path.getsize(out), "bytes")
     info, mats = make_dataset()
     out = os.path.join(HERE, "reference_dataset_v1.json")

@@ -384,3 +384,31 @@ def test_product_output_layout_matches_the_reference(tmp_path):
     for k in ref["files"]:
         assert got["files"][k] == ref["files"][k], k
     assert got["save_weights"] == ref["save_weights"]
+
+
+def test_oracle_star_layers_match_the_reference_layers():
+    """The STAR tower's layers are the reference's OWN code (Star/partitioned_norm.py:102-203, Star/star_fcn.py:105-139), not a
+    third-party dependency: their `call` methods were executed on numpy arrays (the few TF / Keras-backend ops they use replaced
+    by numpy equivalents) and oracle/star.py must reproduce the outputs -- gamma = shared * specific[d], beta = shared +
+    specific[d] with d read from the first row's indicator, batch statistics in training and the batch's DOMAIN's moving
+    statistics at inference, which moving statistic receives the update, W = shared * specific[d], b = shared + specific[d]."""
+    from oracle.star import OracleStar, StarSpec
+    ref = np.load(os.path.join(ROOT, "tests", "golden", "reference_star_layers_v1.npz"))
+    S, w = mrg.STAR_SHAPE, mrg.star_problem()
+    spec = StarSpec(S["b"], S["b"], S["n_domain"], emb_dim=S["emb_dim"], hidden=S["hidden"])
+    named = {"domain_emb": w["domain_emb"], "gamma_specific": w["gamma_sp"], "beta_specific": w["beta_sp"], "gamma_shared": w["gamma_sh"],
+             "beta_shared": w["beta_sh"], "out_kernel": np.zeros((S["hidden"][-1], 1)), "out_bias": np.zeros(1)}
+    for l in range(len(S["hidden"])):
+        named.update({"kernel_specific%d" % l: w["k_sp%d" % l], "bias_specific%d" % l: w["b_sp%d" % l],
+                      "kernel_shared%d" % l: w["k_sh%d" % l], "bias_shared%d" % l: w["b_sh%d" % l]})
+    o = OracleStar(spec, [named[n] for n in spec.names], w["user_table"], w["item_table"], dtype=np.float64)
+    o.moving_mean[...], o.moving_var[...] = w["moving_mean"], w["moving_var"]
+    ids = np.arange(S["b"])
+    H, _, cache = o.forward(ids, ids, S["domain"], train=True)
+    np.testing.assert_allclose(H[0], ref["star|h0_train"], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(cache["mu"], ref["star|batch_mean"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(cache["var"], ref["star|batch_var"], rtol=1e-10, atol=1e-14)
+    for l in range(len(S["hidden"])):
+        np.testing.assert_allclose(H[l + 1], ref["star|h%d" % (l + 1)], rtol=1e-10, atol=1e-12)
+    H_eval, _, _ = o.forward(ids, ids, S["domain"], train=False)
+    np.testing.assert_allclose(H_eval[0], ref["star|h0_eval"], rtol=1e-10, atol=1e-12)
