@@ -25,7 +25,10 @@ oracle's loops replay them bit for bit), and the META ALGEBRA (``mamdr.py:168-19
 bookkeeping (``base_model.py:157-175,208-224``) are PINNED to the reference: those methods are plain
 Python + numpy, ``tests/golden/make_reference_golden.py`` executes the reference's own code (TF / deepctr
 stubbed out) and ``tests/test_reference_golden.py`` holds the oracle to the committed vectors bit for bit.
-**Parity unpinned** for the train step itself (everything below ``model.fit`` / ``train_on_batch``):
+Also pinned by execution: the streaming AUC (``utils/auc.py`` + ``utils/metrics_utils.py``, numpy analogues of the TF
+ops) and the forward of the STAR layers (``Star/partitioned_norm.py``, ``Star/star_fcn.py``).
+**Parity unpinned** for the rest of the train step (everything below ``model.fit`` / ``train_on_batch``: deepctr's DNN /
+MMOE / PLE, Keras BCE, TF Adam, dropout):
 The arithmetic of the train step lives in un-vendored third-party packages
 (``tensorflow-gpu==1.12.0``, ``deepctr==0.9.0``; ``requirements.txt:1,6``)
 which cannot be installed in this image (no wheels for CPython 3.12, no

@@ -734,6 +734,92 @@ def make_star_layers():
     return g
 
 
+# ---- the reference's OWN streaming AUC (utils/auc.py:110-157,159-177,248-281 + utils/metrics_utils.py:194-354) -------------------
+# These two files are part of the reference tree (a back-port of tf.keras.metrics.AUC).  `AUC.__init__`, `update_state` ->
+# `update_confusion_matrix_variables` and `result` are executed with the ~20 TF ops they use replaced by their numpy analogues
+# (float32 like the graph); the two shape-normalising helpers of metrics_utils are bypassed (dense [b] inputs).
+AUC_STREAM = [(1024, 0), (977, 1), (1, 2), (300, 3)]        # (rows, seed) of the batches of one streaming evaluation
+
+
+def auc_batch(rows, seed):
+    rng = np.random.default_rng(500 + seed)
+    y = (rng.random(rows) < 0.3).astype(np.float32)
+    p = np.clip(0.25 * y + rng.random(rows) * 0.75, 0, 1).astype(np.float32)
+    thr = [(i + 1) * 1.0 / 499 for i in range(498)]
+    p[: min(rows, 32)] = np.asarray(thr, dtype=np.float32)[rng.integers(0, 498, min(rows, 32))]   # predictions exactly on thresholds
+    if rows > 2:
+        p[-1], p[-2] = 0.0, 1.0
+    return y, p
+
+
+class _Var(np.ndarray):
+    """A tf.Variable stand-in: a float32 array with assign_add."""
+
+    def assign_add(self, delta):
+        self += np.asarray(delta, dtype=np.float32)
+        return self
+
+
+def _numpy_tf_for_metrics():
+    import contextlib
+    ns = types.SimpleNamespace
+    f32 = np.float32
+
+    def div_no_nan(a, b, name=None):
+        a, b = np.asarray(a, dtype=f32), np.asarray(b, dtype=f32)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            return np.where(b == 0, f32(0), a / b).astype(f32)
+    math_ops = ns(cast=lambda x, dtype=None: np.asarray(getattr(x, "arr", x)).astype(dtype), greater=np.greater, logical_and=np.logical_and,
+                  logical_not=np.logical_not, reduce_sum=lambda x, axis=None, name=None: np.sum(np.asarray(x, dtype=f32), axis=axis, dtype=f32),
+                  div_no_nan=div_no_nan, multiply=lambda a, b: (np.asarray(a, f32) * np.asarray(b, f32)).astype(f32),
+                  maximum=np.maximum, minimum=np.minimum, log=np.log)
+    array_ops = ns(size=lambda x: int(np.asarray(x).size), reshape=lambda x, shape: np.reshape(x, shape), tile=lambda x, m: np.tile(x, [int(k) for k in m]),
+                   expand_dims=lambda x, axis: np.expand_dims(x, axis), constant=lambda x: np.asarray(x, dtype=f32), stack=lambda xs: list(xs),
+                   where=np.where, ones_like=np.ones_like)
+    dtypes = ns(float32=np.float32, bool=np.bool_)
+    ops = ns(control_dependencies=lambda deps: contextlib.nullcontext())
+    check_ops = ns(assert_greater_equal=lambda *a, **k: None, assert_less_equal=lambda *a, **k: None)
+    control_flow_ops = ns(group=lambda ops_: None)
+    return math_ops, array_ops, dtypes, ops, check_ops, control_flow_ops
+
+
+def make_auc():
+    import importlib
+    import_reference()
+    mu = importlib.import_module("utils.metrics_utils")
+    au = importlib.import_module("utils.auc")
+    math_ops, array_ops, dtypes, ops, check_ops, control_flow_ops = _numpy_tf_for_metrics()
+    mu.math_ops, mu.array_ops, mu.dtypes, mu.ops, mu.check_ops, mu.control_flow_ops = math_ops, array_ops, dtypes, ops, check_ops, control_flow_ops
+    mu.to_list = lambda x: list(x) if isinstance(x, (list, tuple)) else [x]
+    compat = types.SimpleNamespace(assert_is_compatible_with=lambda other: None)
+    proxy = lambda a: types.SimpleNamespace(arr=np.asarray(a), shape=compat, dtype=np.float32)   # noqa: E731
+    mu.ragged_assert_compatible_and_get_flat_values = lambda values, mask=None: ([proxy(v) for v in values], mask)
+    mu.squeeze_or_expand_dimensions = lambda y_pred, y_true=None, sample_weight=None: (y_pred.arr, y_true.arr)
+    au.math_ops, au.array_ops = math_ops, array_ops
+    au.K = types.SimpleNamespace(epsilon=lambda: 1e-7)
+    au.tf = types.SimpleNamespace(assign=lambda v, x: None, zeros_like=np.zeros_like)
+    au.AUC.variables = []
+    g = {}
+    for T in (3, 500):
+        a = au.AUC(num_thresholds=T, name="AUC")                       # the real __init__: threshold table, curve / summation enums
+        for nm in ("true_positives", "true_negatives", "false_positives", "false_negatives"):
+            setattr(a, nm, np.zeros(T, dtype=np.float32).view(_Var))
+        g["auc|T%d|thresholds" % T] = np.asarray(a.thresholds, dtype=np.float64)
+        if T == 3:
+            a.update_state(np.float32([0, 0, 1, 1]), np.float32([0, 0.5, 0.3, 0.9]))     # the doc-string example, utils/auc.py:44-56
+            g["auc|T3|acc"] = np.stack([np.asarray(a.true_positives), np.asarray(a.false_positives), np.asarray(a.false_negatives),
+                                        np.asarray(a.true_negatives)])
+            g["auc|T3|result"] = np.float32(a.result())
+            continue
+        for k, (rows, seed) in enumerate(AUC_STREAM):
+            y, p = auc_batch(rows, seed)
+            a.update_state(y, p)
+            g["auc|T500|acc_after_%d" % k] = np.stack([np.asarray(a.true_positives), np.asarray(a.false_positives),
+                                                       np.asarray(a.false_negatives), np.asarray(a.true_negatives)])
+            g["auc|T500|result_after_%d" % k] = np.float32(a.result())
+    return g
+
+
 def flat_any(ws):
     return np.concatenate([np.asarray(w, dtype=np.float32).reshape(-1) for w in ws])
 
@@ -761,6 +847,9 @@ if __name__ == "__main__":
     print(out, os.path.getsize(out), "bytes")
     out = os.path.join(HERE, "reference_star_layers_v1.npz")
     np.savez_compressed(out, **make_star_layers())
+    print(out, os.path.getsize(out), "bytes")
+    out = os.path.join(HERE, "reference_auc_v1.npz")
+    np.savez_compressed(out, **make_auc())
     print(out, os.path.getsize(out), "bytes")
     info, mats = make_dataset()
     out = os.path.join(HERE, "reference_dataset_v1.json")

@@ -176,3 +176,24 @@ def test_cuda_meta_sweeps_match_the_reference_executed_vectors():
     t = dev(th)
     c.call("mamdr_axpy_diff", ptr(t), ptr(acc), ptr(zeros), 0.1, n, stream())
     same(t, "reptile_apply")
+
+
+def test_cuda_auc_matches_the_reference_executed_metric():
+    """tests/golden/reference_auc_v1.npz: the reference's own utils/auc.py + utils/metrics_utils.py executed on a four-batch
+    stream (generator: make_reference_golden.py).  `mamdr_auc_update` reproduces every accumulator exactly, `mamdr_auc_result`
+    the interpolated ROC-AUC within float32 summation order."""
+    from mamdr_b200.auc import thresholds
+    ref = np.load(os.path.join(ROOT, "tests", "golden", "reference_auc_v1.npz"))
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_reference_golden as mrg
+    c = ctx()
+    acc = torch.zeros(4, 500, device="cuda")
+    res = torch.zeros(1, device="cuda")
+    d_thr = dev(thresholds(500))
+    for k, (rows, seed) in enumerate(mrg.AUC_STREAM):
+        y, p = mrg.auc_batch(rows, seed)
+        d_p, d_y = dev(p), dev(y)
+        c.call("mamdr_auc_update", ptr(d_p), ptr(d_y), rows, ptr(acc), ptr(d_thr), 500, stream())
+        np.testing.assert_array_equal(acc.cpu().numpy(), ref["auc|T500|acc_after_%d" % k], err_msg="batch %d" % k)
+        c.call("mamdr_auc_result", ptr(acc), 500, ptr(res), stream())
+        assert abs(res.item() - float(ref["auc|T500|result_after_%d" % k])) < 2e-6

@@ -412,3 +412,27 @@ def test_oracle_star_layers_match_the_reference_layers():
         np.testing.assert_allclose(H[l + 1], ref["star|h%d" % (l + 1)], rtol=1e-10, atol=1e-12)
     H_eval, _, _ = o.forward(ids, ids, S["domain"], train=False)
     np.testing.assert_allclose(H_eval[0], ref["star|h0_eval"], rtol=1e-10, atol=1e-12)
+
+
+def test_oracle_auc_matches_the_reference_metric_code():
+    """utils/auc.py + utils/metrics_utils.py are files of the reference tree; `AUC.__init__` / `update_state` / `result` were
+    executed (numpy analogues of the TF ops) on the doc-string example and on a four-batch stream with predictions sitting
+    exactly on thresholds, 0 and 1.  oracle/auc.py and the product's threshold table reproduce the threshold table and every
+    accumulator exactly, the interpolated ROC-AUC within float32 summation order."""
+    from mamdr_b200.auc import thresholds as product_thresholds
+    from oracle import auc as oauc
+    ref = np.load(os.path.join(ROOT, "tests", "golden", "reference_auc_v1.npz"))
+    for T in (3, 500):
+        want = ref["auc|T%d|thresholds" % T].astype(np.float32)
+        np.testing.assert_array_equal(np.asarray(oauc.thresholds(T), dtype=np.float32), want)
+        np.testing.assert_array_equal(np.asarray(product_thresholds(T), dtype=np.float32), want)
+    a = oauc.AUC(3)
+    a.update_state(np.float32([0, 0, 1, 1]), np.float32([0, 0.5, 0.3, 0.9]))
+    np.testing.assert_array_equal(np.asarray(a.acc, dtype=np.float32), ref["auc|T3|acc"])
+    assert abs(a.result() - float(ref["auc|T3|result"])) < 1e-7
+    a = oauc.AUC(500)
+    for k, (rows, seed) in enumerate(mrg.AUC_STREAM):
+        y, p = mrg.auc_batch(rows, seed)
+        a.update_state(y, p)
+        np.testing.assert_array_equal(np.asarray(a.acc, dtype=np.float32), ref["auc|T500|acc_after_%d" % k], err_msg="batch %d" % k)
+        assert abs(a.result() - float(ref["auc|T500|result_after_%d" % k])) < 2e-6
