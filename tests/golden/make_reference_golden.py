@@ -299,6 +299,17 @@ LOOP_TC = {"epoch": 2, "shuffle_sequence": True, "sample_num": 2, "add_query_dom
 # variables are re-initialised by every init_layer call, never reloaded from theta, and evolve freely through all passes
 SUBSET_CASES = [("mamdr", "mlp_meta_mamdr", "plus"), ("dn", "mlp_meta_domain_negotiation", "plus"), ("reptile", "mlp_meta_reptile", "plus")]
 SUBSET_META_IDX = [0]
+# the config knobs of the loops: each variant overrides LOOP_TC
+VARIANT_CASES = [("mamdr", "mlp_meta_mamdr", {"finetune_every_epoch": True}),
+                 ("mamdr", "mlp_meta_mamdr", {"domain_regulation_step": 1}),
+                 ("mamdr", "mlp_meta_mamdr", {"add_query_domain": False, "sample_num": 3}),
+                 ("mamdr", "mlp_meta_mamdr_batch", {"add_query_domain": False, "merged_method": "times"}),
+                 ("mamdr", "mlp_meta_mamdr", {"shuffle_sequence": False, "meta_sequence": [2, 0, 3, 1]}),
+                 ("dn", "mlp_meta_domain_negotiation", {"meta_train_step": 1}),
+                 ("dn", "mlp_meta_domain_negotiation", {"shuffle_sequence": False, "meta_sequence": [2, 0, 3, 1]}),
+                 ("dn", "mlp_meta_domain_negotiation", {"val_every_step": 2, "epoch": 3}),
+                 ("reptile", "mlp_meta_reptile", {"meta_train_step": 2}),
+                 ("reptile", "mlp_meta_reptile_batch", {"epoch": 3, "meta_learning_rate": 0.5})]
 LOOP_CASES = [("mamdr", "mlp_meta_mamdr", "plus"), ("mamdr", "mlp_meta_mamdr_batch", "plus"), ("mamdr", "mlp_meta_mamdr", "times"),
               ("dn", "mlp_meta_domain_negotiation", "plus"), ("reptile", "mlp_meta_reptile", "plus"),
               ("reptile", "mlp_meta_reptile_batch", "plus")]
@@ -315,14 +326,17 @@ def make_loops():
     for mod_K in (mamdr.K, reptile.K):
         mod_K.int_shape = staticmethod(lambda p: p.shape)
         mod_K.dtype = staticmethod(lambda p: "float32")
-    for kind, name, method, meta_idx in [c + (None,) for c in LOOP_CASES] + [c + (SUBSET_META_IDX,) for c in SUBSET_CASES]:
+    runs = [(k, n, m, None, {}, "%s|%s|" % (n, m)) for k, n, m in LOOP_CASES]
+    runs += [(k, n, m, SUBSET_META_IDX, {}, "%s|%s|subset|" % (n, m)) for k, n, m in SUBSET_CASES]
+    runs += [(k, n, over.get("merged_method", "plus"), None, over, "variant%d|" % i) for i, (k, n, over) in enumerate(VARIANT_CASES)]
+    for kind, name, method, meta_idx, over, key in runs:
         cls = {"mamdr": mamdr.MAMDR, "dn": dn.DomainNegotiation, "reptile": reptile.Reptile}[kind]
         tc = dict(LOOP_TC, merged_method=method)
+        tc.update(over)
         obj, model, base = _toy_wrapper(cls, base_model, tc, name, meta_idx)
         random.seed(LOOP_SEED)
         with contextlib.redirect_stdout(io.StringIO()):
             obj.train()
-        key = "%s|%s|" % (name, method) + ("" if meta_idx is None else "subset|")
         g[key + "live"] = flat_any(model.weights)               # the live model when train() returns (non-meta variables included)
         g[key + "steps"] = numpy.array(model.steps, dtype=numpy.int32)
         if kind == "mamdr":

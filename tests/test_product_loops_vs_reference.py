@@ -279,3 +279,25 @@ def test_product_finetune_stage_replays_the_reference(tmp_path, kind, name, meth
         ck = torch.load(str(tmp_path / "ckpt" / ("domain_%d.h5" % d)))
         np.testing.assert_array_equal(_bits(_flat(model, ck)), _bits(LOOPS[key + "ckpt_%d" % d]), err_msg="checkpoint of domain %d" % d)
     assert model.optimizer == "adam"        # the stage hands the model back compiled with the training optimizer
+
+
+@pytest.mark.parametrize("i", range(len(mrg.VARIANT_CASES)))
+def test_product_wrappers_config_knobs(i):
+    """The loops' config keys as the reference's executed loops handle them vs the product's wrapper code (see
+    tests/test_reference_golden.py::test_oracle_loops_config_knobs for the list)."""
+    from mamdr_b200.domain_negotiation import DomainNegotiation
+    from mamdr_b200.mamdr import MAMDR
+    from mamdr_b200.reptile import Reptile
+    kind, name, over = mrg.VARIANT_CASES[i]
+    base, model = _base(name, over.get("merged_method", "plus"))
+    base.train_config.update(over)
+    wrapper = {"mamdr": MAMDR, "dn": DomainNegotiation, "reptile": Reptile}[kind](base)
+    wrapper.train()
+    key = "variant%d|" % i
+    np.testing.assert_array_equal(np.array(model.steps, dtype=np.int32), LOOPS[key + "steps"])
+    np.testing.assert_array_equal(_bits(_flat(model, wrapper.meta_weights.flat)), _bits(LOOPS[key + "theta"]))
+    np.testing.assert_array_equal(_bits(_flat(model, model.params)), _bits(LOOPS[key + "live"]))
+    if kind == "mamdr":
+        for d in sorted(mrg.N_STEP):
+            np.testing.assert_array_equal(_bits(_flat(model, wrapper.domain_weights[d].flat)), _bits(LOOPS[key + "theta_%d" % d]),
+                                          err_msg="theta_%d" % d)

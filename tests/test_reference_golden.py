@@ -436,3 +436,35 @@ def test_oracle_auc_matches_the_reference_metric_code():
         a.update_state(y, p)
         np.testing.assert_array_equal(np.asarray(a.acc, dtype=np.float32), ref["auc|T500|acc_after_%d" % k], err_msg="batch %d" % k)
         assert abs(a.result() - float(ref["auc|T500|result_after_%d" % k])) < 2e-6
+
+
+@pytest.mark.parametrize("i", range(len(mrg.VARIANT_CASES)))
+def test_oracle_loops_config_knobs(i):
+    """The loops' config keys (finetune_every_epoch, domain_regulation_step, add_query_domain, sample_num, merged_method,
+    an explicit meta_sequence without shuffling, meta_train_step, val_every_step, epoch, meta_learning_rate) as the reference's
+    executed loops handle them vs the oracle."""
+    from mamdr_b200.schedule import Schedule
+    kind, name, over = mrg.VARIANT_CASES[i]
+    bs = 4
+    tc = dict(mrg.LOOP_TC, merged_method=over.get("merged_method", "plus"))
+    tc.update(over)
+    model = _ToyOracleModel()
+    key = "variant%d|" % i
+    if kind == "mamdr":
+        om = ometa.OracleMAMDR(model, _toy_data(bs), tc, bs, Schedule(mrg.LOOP_SEED), {d: mrg.toy_init(d + 1) for d in mrg.N_STEP}, name=name)
+    elif kind == "dn":
+        om = ometa.OracleDN(model, _toy_data(bs), tc, bs, Schedule(mrg.LOOP_SEED))
+    else:
+        om = ometa.OracleReptile(model, _toy_data(bs), tc, bs, Schedule(mrg.LOOP_SEED), name=name)
+    for epoch in range(tc["epoch"]):
+        om.train_epoch()
+        if epoch % tc["val_every_step"] == 0:
+            _, val_auc, _, _ = om.val_and_test("val")
+            if om.early_stop_step(val_auc):
+                break
+            om.val_and_test("test")
+    np.testing.assert_array_equal(np.array(model.steps, dtype=np.int32), LOOPS[key + "steps"])
+    np.testing.assert_array_equal(_bits(mrg.flat_any(om.meta_weights)), _bits(LOOPS[key + "theta"]))
+    if kind == "mamdr":
+        for d in sorted(mrg.N_STEP):
+            np.testing.assert_array_equal(_bits(mrg.flat_any(om.domain_weights[d])), _bits(LOOPS[key + "theta_%d" % d]), err_msg="theta_%d" % d)
