@@ -92,6 +92,7 @@ class _ToyDeviceModel(object):
         w0 = mrg.toy_init(0)
         self.layout = ParamLayout(["kernel0", "bias0"], [w.shape for w in w0])
         self.params = torch.from_numpy(self.layout.pack(w0))
+        self.m, self.v = torch.zeros_like(self.params), torch.zeros_like(self.params)
         self.ctx = _NumpyMetaOps()
         self.stream = None
         self.steps = []
@@ -117,6 +118,13 @@ class _ToyDeviceModel(object):
 
     def evaluate(self, data, steps=None):
         return mrg.toy_eval(self.views(), data.domain)
+
+    # the sharded meta-step's view of the optimizer state (engine.MLPModel: m / v arenas, opt_words / set_opt_words)
+    def opt_words(self):
+        return torch.zeros(3)
+
+    def set_opt_words(self, words):
+        pass
 
     # the finetune stage's Keras-like surface (engine.MLPModel: compile / get_weights / set_weights)
     def compile(self, optimizer="adam", lr=None):
@@ -301,3 +309,51 @@ def test_product_wrappers_config_knobs(i):
         for d in sorted(mrg.N_STEP):
             np.testing.assert_array_equal(_bits(_flat(model, wrapper.domain_weights[d].flat)), _bits(LOOPS[key + "theta_%d" % d]),
                                           err_msg="theta_%d" % d)
+
+
+# ---- two ranks (gloo): DR query domains sharded over the ranks (mamdr_b200/dist.py), one all-reduce per meta-step -------------------
+def _sharded_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    os.environ.update({"MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port), "RANK": str(rank), "WORLD_SIZE": str(world)})
+    dist.init_process_group("gloo")
+    from mamdr_b200.mamdr import MAMDR
+    base, model = _base("mlp_meta_mamdr", "plus")
+    wrapper = MAMDR(base)
+    wrapper.train()
+    owned = sorted(d for d, r in wrapper.dr_owner.items() if r == rank)
+    torch.save({"theta": wrapper.meta_weights.flat.clone(), "theta_d": {d: w.flat.clone() for d, w in wrapper.domain_weights.items()},
+                "best_theta_d": {d: w.flat.clone() for d, w in wrapper.best_domain_weights.items()}, "steps": list(model.steps),
+                "owned": owned, "es": [base.counter, base.best_metric]}, os.path.join(out_dir, "rank%d.pt" % rank))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_product_meta_steps_equal_the_reference_sequential_run(tmp_path):
+    """With a train step that carries no optimizer state, DR chains are independent given theta, so sharding the query domains
+    over two ranks (replicated DN phase, LPT-assigned chains, ONE all-reduce per meta-step) must reproduce the reference's
+    SEQUENTIAL run bit for bit on every rank: theta, every theta_d, the best snapshots and the early-stop state; each rank
+    executes the full DN phase and only its own chains."""
+    import socket
+    import torch.multiprocessing as mp
+    sock = socket.socket()
+    sock.bind(("127.0.0.1", 0))
+    port = sock.getsockname()[1]
+    sock.close()
+    mp.spawn(_sharded_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    key = "mlp_meta_mamdr|plus|"
+    lo = ParamLayout(["kernel0", "bias0"], [w.shape for w in mrg.toy_init(0)])
+    flat = lambda t: mrg.flat_any([v.numpy() for v in lo.views(t)])   # noqa: E731
+    blobs = [torch.load(os.path.join(str(tmp_path), "rank%d.pt" % r), weights_only=False) for r in range(2)]
+    n_seq = len(LOOPS[key + "steps"])
+    assert sorted(blobs[0]["owned"] + blobs[1]["owned"]) == sorted(mrg.N_STEP) and blobs[0]["owned"] and blobs[1]["owned"]
+    dn_steps_per_epoch = sum(mrg.N_STEP.values())
+    for b in blobs:
+        np.testing.assert_array_equal(_bits(flat(b["theta"])), _bits(LOOPS[key + "theta"]))
+        for d in sorted(mrg.N_STEP):
+            np.testing.assert_array_equal(_bits(flat(b["theta_d"][d])), _bits(LOOPS[key + "theta_%d" % d]), err_msg="theta_%d" % d)
+            np.testing.assert_array_equal(_bits(flat(b["best_theta_d"][d])), _bits(LOOPS[key + "best_theta_%d" % d]))
+        np.testing.assert_array_equal(np.array(b["es"], dtype=np.float64), LOOPS[key + "es"])
+        assert len(b["steps"]) < n_seq                                # fewer train steps than the sequential run ...
+    # ... and together exactly the sequential run's steps, the replicated DN phase counted once per epoch
+    total = len(blobs[0]["steps"]) + len(blobs[1]["steps"]) - mrg.LOOP_TC["epoch"] * dn_steps_per_epoch
+    assert total == n_seq
