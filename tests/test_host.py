@@ -200,3 +200,16 @@ def test_mtl_topology_matches_oracle_layout():
             assert [x.shape for x in w] == lo.shapes and all(x.dtype == np.float32 for x in w)
     with pytest.raises(ValueError):
         MTLTopology("cgc", 5, 5, 2, (8, 8, 8), (8,), (8,), (4,))
+
+
+def test_package_exports_the_reference_class_names():
+    """run.py:6-15 of the reference imports these names; `from mamdr_b200 import <name>` must resolve each of them."""
+    import mamdr_b200
+    from mamdr_b200 import MAMDR, MAML, BaseModel, DeepCTR, DeepMTLCTR, DomainNegotiation, MultiDomainDataset, Reptile, Star
+    assert issubclass(MAMDR, MAML) and issubclass(DomainNegotiation, MAML) and issubclass(Reptile, MAML)
+    assert issubclass(DeepCTR, BaseModel) and issubclass(Star, BaseModel) and issubclass(DeepMTLCTR, BaseModel)
+    assert MultiDomainDataset.__module__ == "mamdr_b200.dataset"
+    assert sorted(mamdr_b200.__all__) == sorted(["MAML", "DomainNegotiation", "MAMDR", "Reptile", "BaseModel", "DeepCTR", "Star",
+                                                 "DeepMTLCTR", "MultiDomainDataset"])
+    with pytest.raises(AttributeError):
+        mamdr_b200.PCGrad
