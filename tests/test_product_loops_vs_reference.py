@@ -357,3 +357,41 @@ def test_sharded_product_meta_steps_equal_the_reference_sequential_run(tmp_path)
     # ... and together exactly the sequential run's steps, the replicated DN phase counted once per epoch
     total = len(blobs[0]["steps"]) + len(blobs[1]["steps"]) - mrg.LOOP_TC["epoch"] * dn_steps_per_epoch
     assert total == n_seq
+
+
+@pytest.mark.parametrize("kind,name", [("mamdr", "mlp_meta_mamdr"), ("dn", "mlp_meta_domain_negotiation"), ("reptile", "mlp_meta_reptile_batch")])
+def test_save_state_resume_on_the_cpu_harness(tmp_path, kind, name):
+    """`save_state` after the first meta-step, `load_state` into a fresh wrapper, second meta-step: the same theta / theta_d /
+    live arena / step sequence as the uninterrupted run (which itself equals the reference's executed loop)."""
+    from mamdr_b200.domain_negotiation import DomainNegotiation
+    from mamdr_b200.mamdr import MAMDR
+    from mamdr_b200.reptile import Reptile
+    cls = {"mamdr": MAMDR, "dn": DomainNegotiation, "reptile": Reptile}[kind]
+
+    def fresh():
+        base, model = _base(name, "plus")
+        w = cls(base)
+        if kind == "dn":
+            w._get_model_meta_parms()
+            w.meta_weights = w._get_meta_weights()
+            w.meta_sequence = w.build_meta_data_split()
+        else:
+            w.prepare()
+        return w, base, model
+
+    a, base_a, model_a = fresh()
+    a.train_epoch(0)
+    path = a.save_state(str(tmp_path / "state.pt"), epoch=0)
+    first = len(model_a.steps)
+    a.train_epoch(1)
+    b, base_b, model_b = fresh()
+    assert b.load_state(path) == 0
+    b.train_epoch(1)
+    assert model_b.steps == model_a.steps[first:]
+    assert torch.equal(a.meta_weights.flat, b.meta_weights.flat) and torch.equal(model_a.params, model_b.params)
+    if kind == "mamdr":
+        for d in a.domain_weights:
+            assert torch.equal(a.domain_weights[d].flat, b.domain_weights[d].flat), d
+    # and the uninterrupted two meta-steps are the reference's (no val / early stop in between: theta only)
+    key = "%s|plus|" % name
+    np.testing.assert_array_equal(_bits(_flat(model_a, a.meta_weights.flat)), _bits(LOOPS[key + "theta"]))
