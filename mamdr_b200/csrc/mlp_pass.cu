@@ -10,10 +10,20 @@
 // Why one kernel: at batch 1024 a mini-batch is ~0.7 GFLOP over ~2 MB of L2-resident operands, i.e. ~1 us at
 // the B200 rooflines; a stream of per-layer kernels is bound by launch + pipeline-fill latency (measured 146 us
 // per mini-batch for 14 launches, profiles/r1_v2_*).  Here every SM keeps its barriers, TMEM allocation and
-// pipeline alive for the whole pass and the layers are separated by grid barriers (~1 us) instead of launches.
+// pipeline alive for the whole pass and the layers are separated by grid barriers (~1.2 us) instead of launches.
 //
-// CTA = 6 warps: warps 0-3 = epilogue / element-wise workers (thread t <-> TMEM lane t <-> tile row t),
-// warp 4 lane 0 = TMA producer, warp 5 lane 0 = tcgen05.mma issuer (warp 5 owns the TMEM allocation).
+// CTA = 10 warps: warps 0-7 = epilogue / element-wise workers (warp w <-> TMEM lanes 32 (w % 4) .. +31 <-> tile rows,
+// column half w / 4 of the tile), warp 8 = TMA producer, warp 9 = tcgen05.mma issuer (owns the TMEM allocation).
+// Both issue warps run their loops CONVERGED, one elected lane issuing: TMA and MMA descriptors then live in uniform
+// registers (under `if (lane == 0)` every instruction pays an R2UR waterfall: 130-200 cycles per MMA instead of 50,
+// profiles/r2_probe_mainloop.txt).
+//
+// 3xTF32 (MAMDR_PREC_TF32X3): every GEMM operand is kept in global memory as a PAIR array [2][rows][cols]: plane 0 =
+// the fp32 value (the tensor core truncates it to its tf32 "hi" part), plane 1 = lo = rn_tf32(x - hi), written by the
+// producing epilogue / gather / optimizer apply.  TMA stages [A | A_lo | B | B_lo]; B and B_lo are adjacent and form
+// ONE operand of N = 2 bn, so a k-step is two MMAs: A.[B | B_lo] (two accumulator halves) and A_lo.B (first half);
+// the epilogue adds the halves.  Dropped: A_lo.B_lo (2^-22 relative).
+//
 // Per mini-batch (L hidden layers) the grid walks 2L+1 phases, each a list of independent tile jobs
 // (job j runs on CTA j mod grid):
 //   fwd l < L-1 : H_{l+1} = dropout(relu(H_l . W_l + b_l))         tiles 128 x 32        (l = 0: + E_d[dom] . W_0dom)
@@ -26,38 +36,39 @@
 // datasets), so X is only [E_u | E_i] (K = 256) and the domain block of layer 0 is folded into its bias in fp32
 // (SURVEY.md A-10); its weight gradient is the rank-1 product E_d[dom]^T (x) db_0.
 // No float atomics anywhere: results are bit-reproducible run to run and rank to rank.
-#include <cooperative_groups.h>
-
 #include <vector>
 
 #include "common.cuh"
 #include "meta_ops.cuh"
 #include "philox.cuh"
 #include "program.cuh"
-#include "tc_gemm.cuh"
 #include "tc_tmap.cuh"
 
 namespace passk {
 
 #define WSTAMP(k) do { if (tim && tid == 0) a.timing[tslot + (k)] = (unsigned long long)clock64(); } while (0)
 
-constexpr int kThreads = 192;
-constexpr int kWorkers = 128;
+constexpr int kWorkerWarps = 8;
+constexpr int kWorkers = 32 * kWorkerWarps;   // 256
+constexpr int kProdWarp = kWorkerWarps;       // warp 8
+constexpr int kMmaWarp = kWorkerWarps + 1;    // warp 9
+constexpr int kThreads = 32 * (kWorkerWarps + 2);
 constexpr int KCH = 32;                       // floats per K chunk = one 128-byte swizzle row
-constexpr int A_BYTES = 128 * KCH * 4;        // 16 KB
-constexpr int B_BYTES = 64 * KCH * 4;         // 8 KB (BN <= 64)
-constexpr int kMaxStages = 6;
-constexpr int kScratchBytes = 36 * 1024;
+constexpr int A_BYTES = 128 * KCH * 4;        // 16 KB: one A tile
+constexpr int B_BYTES = 64 * KCH * 4;         // 8 KB: one B tile at BN = 64
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // [A | A_lo | B | B_lo] = 48 KB
+constexpr int kStages = 4;
+constexpr int kScratchBytes = 20 * 1024;
 constexpr int kMaxThr = 1024;
 constexpr int kMaxSplit = 8;
 constexpr int kDomJobs = 8;                   // the domain-embedding gradient GEMV is split over this many CTAs
 constexpr int kMaxMT = 64;                    // 128-row tiles per mini-batch (batch <= 8192)
-constexpr uint32_t kTmemCols = 64;
+constexpr uint32_t kTmemCols = 128;           // one accumulator of up to 2 x 64 columns
 
 enum { J_NONE = 0, J_FWD, J_HEAD, J_DH, J_DW, J_DOM };
 enum { SEG_ED = 0, SEG_KERNEL, SEG_BIAS, SEG_DENSE, SEG_GBIAS };
 
-struct MapTable {   // kernel parameter (param space is a legal tensor-map address space)
+struct MapTable {   // kernel parameter (param space is a legal tensor-map address space); every map is a pair map
     CUtensorMap xk[2], xmn[2];                  // X double buffer: K-major [B, K0] / MN-major view
     CUtensorMap hk[MAMDR_MAX_LAYERS];           // H_l  K-major  (A of fwd l),      l = 1..L-1
     CUtensorMap hmn[MAMDR_MAX_LAYERS];          // H_l  MN-major (A of dW_l)
@@ -89,11 +100,12 @@ struct PassArgs {
     int nseg;
     Seg seg[2 * MAMDR_MAX_LAYERS + 3];
     float *params, *m, *v, *grads;    // grads may be NULL
-    float* wshadow;                   // arena-indexed tf32-rounded copy of the kernels (1-pass TF32 mode)
+    float* wpair;                     // arena-indexed pair shadow of the kernels: plane 0 at wpair, plane 1 at wpair + wz
+    long long wz;
     const float *Eu, *Ei;
     // ---- data
     int bs, max_rows;
-    // ---- workspace
+    // ---- workspace (pair arrays: the lo plane lies max_rows * width floats behind the hi plane)
     float *X[2], *y[2], *H[MAMDR_MAX_LAYERS], *dZ[MAMDR_MAX_LAYERS], *partials[MAMDR_MAX_LAYERS], *db_part[MAMDR_MAX_LAYERS];
     float *dw_part, *dg_part, *db0_red, *gEd_row, *ed_row;
     double *loss_part, *ed_sq;
@@ -108,7 +120,7 @@ struct PassArgs {
     float dropout_scale, l2_emb, frozen_reg;
     float* auc_acc;
     const float* thr;
-    int T, train, passes, stages;
+    int T, train, passes;
     unsigned long long* timing;   // debug: [step][phase][cta][16] time stamps (NULL in production)
     long long timing_cap;
 };
@@ -188,7 +200,7 @@ __device__ __forceinline__ unsigned long long gtime() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ float ldcg_f(const float* p) { return __ldcg(p); }
 __device__ __forceinline__ float4 ldcg_f4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
@@ -225,6 +237,13 @@ __device__ __forceinline__ float rn_tf32(float x) {
     return __uint_as_float(r);
 }
 __device__ __forceinline__ float4 rn_tf32_4(float4 v) { return make_float4(rn_tf32(v.x), rn_tf32(v.y), rn_tf32(v.z), rn_tf32(v.w)); }
+__device__ __forceinline__ float4 tf32_lo_4(float4 v) { return make_float4(tc::tf32_lo(v.x), tc::tf32_lo(v.y), tc::tf32_lo(v.z), tc::tf32_lo(v.w)); }
+
+// store 4 consecutive elements of a pair array: plane 0 = v (pre-rounded in the 1-pass mode), plane 1 = lo (3-pass mode)
+__device__ __forceinline__ void store_pair4(float* hi, long long z, float4 v, bool rnd, bool x3) {
+    *reinterpret_cast<float4*>(hi) = rnd ? rn_tf32_4(v) : v;
+    if (x3) *reinterpret_cast<float4*>(hi + z) = tf32_lo_4(v);
+}
 
 __device__ __forceinline__ void adam1(float& p, float& m, float& v, float g, float alpha, float omb1, float omb2, float eps) {
     m = __fadd_rn(m, __fmul_rn(__fsub_rn(g, m), omb1));
@@ -232,12 +251,34 @@ __device__ __forceinline__ void adam1(float& p, float& m, float& v, float g, flo
     p = __fsub_rn(p, __fdiv_rn(__fmul_rn(m, alpha), __fadd_rn(__fsqrt_rn(v), eps)));
 }
 
-// gather the rows of mini-batch `step` into X[buf] / y[buf]; one warp per row, 16-byte lanes
-__device__ __forceinline__ void gather_rows(const PassArgs& a, const PassDyn& pd, int step, int buf, int warp_rank, int n_warps, int lane, bool rnd) {
+// Column sums over the 32 lanes of a warp (lane = tile row) of C per-lane values, in a fixed butterfly order:
+// afterwards lane l holds the total of column (C == 32 ? l : l >> 1).  31 (C = 32) / 16 (C = 16) shuffles.
+template <int C>
+__device__ __forceinline__ float warp_colsum(float (&v)[C], int lane) {
+    static_assert(C == 16 || C == 32, "16 or 32 columns per lane");
+#pragma unroll
+    for (int step = 0; step < (C == 32 ? 5 : 4); ++step) {
+        const int off = 16 >> step, half = (C / 2) >> step;
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float send = up ? v[i] : v[i + half];
+            const float recv = __shfl_xor_sync(0xffffffffu, send, off);
+            v[i] = (up ? v[i + half] : v[i]) + recv;
+        }
+    }
+    float r = v[0];
+    if (C == 16) r += __shfl_xor_sync(0xffffffffu, r, 1);
+    return r;
+}
+
+// gather the rows of mini-batch `step` into the pair buffer X[buf] / y[buf]; one warp per row, 16-byte lanes
+__device__ __forceinline__ void gather_rows(const PassArgs& a, const PassDyn& pd, int step, int buf, int warp_rank, int n_warps, int lane, bool rnd, bool x3) {
     const long long off = (long long)step * a.bs;
     const long long left = pd.n_data - off;
     const int rows = left < a.bs ? (int)left : a.bs;
     const int K0 = a.du + a.di;
+    const long long xz = (long long)a.max_rows * K0;
     float* X = a.X[buf];
     float* y = a.y[buf];
     for (int r = warp_rank; r < rows; r += n_warps) {
@@ -246,8 +287,8 @@ __device__ __forceinline__ void gather_rows(const PassArgs& a, const PassDyn& pd
         const float* su = a.Eu + u * a.du;
         const float* si = a.Ei + p * a.di;
         float* xr = X + (long long)r * K0;
-        for (int c = lane * 4; c < a.du; c += 128) { const float4 q = ldg_f4(su + c); *reinterpret_cast<float4*>(xr + c) = rnd ? rn_tf32_4(q) : q; }
-        for (int c = lane * 4; c < a.di; c += 128) { const float4 q = ldg_f4(si + c); *reinterpret_cast<float4*>(xr + a.du + c) = rnd ? rn_tf32_4(q) : q; }
+        for (int c = lane * 4; c < a.du; c += 128) store_pair4(xr + c, xz, ldg_f4(su + c), rnd, x3);
+        for (int c = lane * 4; c < a.di; c += 128) store_pair4(xr + a.du + c, xz, ldg_f4(si + c), rnd, x3);
         if (lane == 0) y[r] = __ldg(pd.label + o);
     }
 }
@@ -258,31 +299,31 @@ __global__ void __launch_bounds__(kThreads, 1)
 pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    __shared__ uint64_t bar_full[kMaxStages], bar_empty[kMaxStages], bar_split[kMaxStages], bar_done, bar_tfree;
+    __shared__ uint64_t bar_full[kStages], bar_empty[kStages], bar_done, bar_tfree;
     __shared__ uint32_t tmem_base_s;
     __shared__ float s_thr[kMaxThr];
     __shared__ float s_beff[64];
     __shared__ float s_wd[64];
+    __shared__ float s_z[2][128];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int G = gridDim.x, cta = blockIdx.x;
-    const int STAGES = a.stages;
     const int passes = a.passes;
-    const uint32_t stage_bytes = (uint32_t)(A_BYTES + B_BYTES) * (passes == 3 ? 2u : 1u);
-    unsigned char* scratch = smem + (size_t)STAGES * stage_bytes;
+    const bool x3 = passes == 3;    // 3xTF32: pair operands, N-concatenated MMAs
+    const bool rnd = passes == 1;   // 1-pass TF32: GEMM operands are stored pre-rounded (RN) to tf32
+    unsigned char* scratch = smem + (size_t)kStages * STAGE_BYTES;
 
     if (tid == 0) {
-        for (int s = 0; s < kMaxStages; ++s) {
+        for (int s = 0; s < kStages; ++s) {
             tc::mbar_init(&bar_full[s], 1);
             tc::mbar_init(&bar_empty[s], 1);
-            tc::mbar_init(&bar_split[s], kWorkers);
         }
         tc::mbar_init(&bar_done, 1);
         tc::mbar_init(&bar_tfree, kWorkers);
         tc::fence_barrier_init();
     }
-    if (warp == 5) tc::tmem_alloc(&tmem_base_s, kTmemCols);
-    if (warp == 4 && lane == 0) {
+    if (warp == kMmaWarp) tc::tmem_alloc(&tmem_base_s, kTmemCols);
+    if (warp == kProdWarp && lane == 0) {
         for (int b = 0; b < 2; ++b) { tc::tma_prefetch_desc(&maps.xk[b]); tc::tma_prefetch_desc(&maps.xmn[b]); }
         for (int l = 0; l < a.L; ++l) {
             tc::tma_prefetch_desc(&maps.wf[l]);
@@ -295,17 +336,30 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem = tmem_base_s;
+    const uint32_t smem_base = tc::smem_u32(smem);
 
     // replicated optimizer scalars: every thread advances its own copy with the same fp32 operations
     long long step_ctr = a.state->step;
     float b1pow = a.state->b1pow, b2pow = a.state->b2pow;
     unsigned int bar_target = 0;
-    uint32_t it = 0;      // pipeline chunk counter (producer / MMA / worker copies advance identically)
-    uint32_t njob = 0;    // GEMM jobs run so far by this CTA (parity of bar_done / bar_tfree)
+    int ring_s = 0;            // pipeline stage cursor of this warp's role (producer / MMA issuer)
+    uint32_t ring_ph = 0;      // phase bit of the current lap
+    uint32_t ring_n = 0;       // chunks handled so far (the first kStages need no empty-wait)
+    uint32_t njob = 0;         // GEMM jobs run so far by this CTA (parity of bar_done / bar_tfree)
     const int K0 = a.n[0];
     const int L = a.L;
     const float inv_keep = a.dropout_enabled && a.train ? a.dropout_scale : 1.0f;
-    const bool rnd = passes == 1;   // 1-pass TF32: GEMM operands are stored pre-rounded (RN) to tf32
+    const int nz = x3 ? 2 : 1;
+
+    // refresh the pair shadow of the kernels from the parameter arena (float4 items of this thread)
+    auto refresh_wpair = [&]() {
+        for (int q = 0; q < a.nseg; ++q) {
+            if (a.seg[q].kind != SEG_KERNEL) continue;
+            const long long o0 = a.seg[q].off;
+            for (int i = (cta * kThreads + tid) * 4; i < a.seg[q].numel; i += G * kThreads * 4)
+                store_pair4(a.wpair + o0 + i, a.wz, ldcg_f4(a.params + o0 + i), rnd, x3);
+        }
+    };
 
     const ProgOp* ops = a.ops ? a.ops : &a.inline_op;
     int pass_idx = 0;
@@ -328,17 +382,11 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
     pd.losses = op.losses; pd.probs = op.probs;
     int* const hist_cur = a.hist + (pass_idx & 1) * (2 * (kMaxThr + 1));
 
-    // ---- prologue of a pass: gather mini-batch 0; tf32-rounded weight shadow; |E_d|^2 for the inference loss
-    if (rnd) {
-        for (int q = 0; q < a.nseg; ++q) {
-            if (a.seg[q].kind != SEG_KERNEL) continue;
-            const long long o0 = a.seg[q].off;
-            for (int i = (cta * kThreads + tid) * 4; i < a.seg[q].numel; i += G * kThreads * 4)
-                *reinterpret_cast<float4*>(a.wshadow + o0 + i) = rn_tf32_4(ldcg_f4(a.params + o0 + i));
-        }
-    }
-    if (warp < 4) {
-        gather_rows(a, pd, 0, 0, cta * 4 + warp, G * 4, lane, rnd);
+    // ---- prologue of a pass: gather mini-batch 0; pair shadow of the kernels (the arena may have been rewritten by a
+    // meta sweep or by the host since the last pass); |E_d|^2 for the inference loss
+    refresh_wpair();
+    if (warp < kWorkerWarps) {
+        gather_rows(a, pd, 0, 0, cta * kWorkerWarps + warp, G * kWorkerWarps, lane, rnd, x3);
         if (!a.train && cta == G - 1) {
             double sq = 0.0;
             for (int i = tid; i < a.n_domain * a.dd; i += kWorkers) { const double e = ldcg_f(a.params + a.off_Ed + i); sq += e * e; }
@@ -347,7 +395,11 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
             for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
             if (lane == 0) red[warp] = sq;
             worker_sync();
-            if (tid == 0) *a.ed_sq = red[0] + red[1] + red[2] + red[3];
+            if (tid == 0) {
+                double tot = 0.0;
+                for (int w = 0; w < kWorkerWarps; ++w) tot += red[w];
+                *a.ed_sq = tot;
+            }
         }
     }
     grid_barrier(a.bar, bar_target);
@@ -456,8 +508,9 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
 #pragma unroll
                     for (int t = 0; t < 4; ++t) pp[t] = __fsub_rn(pp[t], __fmul_rn(g[t], a.lr));
                 }
-                *reinterpret_cast<float4*>(a.params + o) = make_float4(pp[0], pp[1], pp[2], pp[3]);
-                if (rnd && sg.kind == SEG_KERNEL) *reinterpret_cast<float4*>(a.wshadow + o) = rn_tf32_4(make_float4(pp[0], pp[1], pp[2], pp[3]));
+                const float4 pnew = make_float4(pp[0], pp[1], pp[2], pp[3]);
+                *reinterpret_cast<float4*>(a.params + o) = pnew;
+                if (sg.kind == SEG_KERNEL) store_pair4(a.wpair + o, a.wz, pnew, rnd, x3);
                 if (a.grads) *reinterpret_cast<float4*>(a.grads + o) = make_float4(g[0], g[1], g[2], g[3]);
             }
         };
@@ -473,9 +526,9 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                     if (J.type == J_DOM) {
                         // ---------- domain-embedding job q of kDomJobs (workers): db_0 (every job, into smem), rows
                         // [q*per, (q+1)*per) of dE_d[dom] = W_0dom . db_0; job 0 also publishes db_0, E_d[dom], |E_d|^2
-                        if (warp < 4) {
+                        if (warp < kWorkerWarps) {
                             const int n1 = a.n[1];
-                            float* s_db0 = reinterpret_cast<float*>(scratch);           // [n1]
+                            float* s_db0 = reinterpret_cast<float*>(scratch);           // [n1] (n1 <= 4096: 16 KB)
                             double* red = reinterpret_cast<double*>(scratch + 16384);
                             for (int c = tid * 4; c < n1; c += kWorkers * 4) {
                                 float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -500,11 +553,15 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                                 for (int k = tid; k < a.dd; k += kWorkers) a.ed_row[k] = ldcg_f(a.params + a.off_Ed + (long long)pd.dom * a.dd + k);
                             }
                             worker_sync();
-                            if (J.m_tile == 0 && tid == 0) *a.ed_sq = red[0] + red[1] + red[2] + red[3];
+                            if (J.m_tile == 0 && tid == 0) {
+                                double tot = 0.0;
+                                for (int w = 0; w < kWorkerWarps; ++w) tot += red[w];
+                                *a.ed_sq = tot;
+                            }
                             const float* W0dom = a.params + a.off_W[0] + (long long)K0 * n1;
                             const int per = cdiv(a.dd, kDomJobs);
                             const int k_end = (J.m_tile + 1) * per < a.dd ? (J.m_tile + 1) * per : a.dd;
-                            for (int k = J.m_tile * per + warp; k < k_end; k += 4) {
+                            for (int k = J.m_tile * per + warp; k < k_end; k += kWorkerWarps) {
                                 const float* wr = W0dom + (long long)k * n1;
                                 float s = 0.f;
                                 for (int c0 = 0; c0 < n1; c0 += 512) {   // 4 x 128 floats per trip, loads first
@@ -532,79 +589,94 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                         continue;
                     }
                     const bool a_mn = J.type == J_DW, b_mn = J.type != J_DH;
-                    if (warp == 4) {
-                        // ---------- TMA producer
-                        if (lane == 0) {
-                            const CUtensorMap* ma;
-                            const CUtensorMap* mb;
-                            if (J.type == J_FWD || J.type == J_HEAD) { ma = l == 0 ? &maps.xk[buf] : &maps.hk[l]; mb = &maps.wf[l]; }
-                            else if (J.type == J_DH) { ma = &maps.dzk[l]; mb = &maps.wb[l]; }
-                            else { ma = l == 0 ? &maps.xmn[buf] : &maps.hmn[l]; mb = &maps.dzmn[l]; }
-                            const uint32_t tx = (uint32_t)(A_BYTES + J.bn * KCH * 4);
-                            if (tim) a.timing[tslot + 13] = (unsigned long long)clock64();
-                            for (int i = 0; i < J.nch; ++i, ++it) {
-                                const int s = it % STAGES, c = J.c_beg + i;
-                                if (it >= (uint32_t)STAGES) tc::mbar_wait(&bar_empty[s], ((it / STAGES) - 1) & 1);
-                                unsigned char* st = smem + (size_t)s * stage_bytes;
-                                unsigned char *sA = st, *sB = st + A_BYTES;
-                                tc::mbar_arrive_expect_tx(&bar_full[s], tx);
-                                if (a_mn) {
+                    if (warp == kProdWarp) {
+                        // ---------- TMA producer (whole warp converged, one elected lane issues)
+                        const CUtensorMap* ma;
+                        const CUtensorMap* mb;
+                        if (J.type == J_FWD || J.type == J_HEAD) { ma = l == 0 ? &maps.xk[buf] : &maps.hk[l]; mb = &maps.wf[l]; }
+                        else if (J.type == J_DH) { ma = &maps.dzk[l]; mb = &maps.wb[l]; }
+                        else { ma = l == 0 ? &maps.xmn[buf] : &maps.hmn[l]; mb = &maps.dzmn[l]; }
+                        const uint32_t b_tile = (uint32_t)J.bn * KCH * 4;
+                        const uint32_t tx = (uint32_t)(A_BYTES + b_tile) * (uint32_t)nz;
+                        const int a_row = J.m_tile * 128, b_col = J.n_tile * J.bn, ngb = J.bn >> 5;
+                        for (int i = 0; i < J.nch; ++i) {
+                            const int kc = (J.c_beg + i) * KCH;
+                            if (ring_n >= (uint32_t)kStages) tc::mbar_wait(&bar_empty[ring_s], ring_ph ^ 1);
+                            unsigned char* sA = smem + (size_t)ring_s * STAGE_BYTES;
+                            unsigned char* sB = sA + 2 * A_BYTES;
+                            uint64_t* fb = &bar_full[ring_s];
+                            if (tc::elect_one()) {
+                                tc::mbar_arrive_expect_tx(fb, tx);
+                                for (int z = 0; z < nz; ++z) {
+                                    if (a_mn) {
 #pragma unroll
-                                    for (int g = 0; g < 4; ++g) tc::tma_load_2d(sA + g * 4096, ma, &bar_full[s], J.m_tile * 128 + g * 32, c * KCH);
-                                } else {
-                                    tc::tma_load_2d(sA, ma, &bar_full[s], c * KCH, J.m_tile * 128);
+                                        for (int g = 0; g < 4; ++g) tc::tma_load_3d(sA + z * A_BYTES + g * 4096, ma, fb, a_row + g * 32, kc, z);
+                                    } else {
+                                        tc::tma_load_3d(sA + z * A_BYTES, ma, fb, kc, a_row, z);
+                                    }
+                                    if (b_mn) {
+                                        for (int g = 0; g < ngb; ++g) tc::tma_load_3d(sB + z * b_tile + g * 4096, mb, fb, b_col + g * 32, kc, z);
+                                    } else {
+                                        tc::tma_load_3d(sB + z * b_tile, mb, fb, kc, b_col, z);
+                                    }
                                 }
-                                if (b_mn) {
-                                    for (int g = 0; g < J.bn / 32; ++g) tc::tma_load_2d(sB + g * 4096, mb, &bar_full[s], J.n_tile * J.bn + g * 32, c * KCH);
-                                } else {
-                                    tc::tma_load_2d(sB, mb, &bar_full[s], c * KCH, J.n_tile * J.bn);
+                                if (tim) {
+                                    if (i == 0) a.timing[tslot + 2] = (unsigned long long)clock64();
+                                    if (i == J.nch - 1) a.timing[tslot + 3] = (unsigned long long)clock64();
                                 }
-                                if (tim && i == 0) a.timing[tslot + 2] = (unsigned long long)clock64();
                             }
-                            if (tim) a.timing[tslot + 3] = (unsigned long long)clock64();
-                        } else {
-                            it += J.nch;
+                            __syncwarp();
+                            ++ring_n;
+                            if (++ring_s == kStages) { ring_s = 0; ring_ph ^= 1; }
                         }
-                        it = __shfl_sync(0xffffffffu, it, 0);
-                    } else if (warp == 5) {
-                        // ---------- MMA issuer
-                        if (lane == 0) {
-                            if (njob > 0) tc::mbar_wait(&bar_tfree, (njob - 1) & 1);
+                    } else if (warp == kMmaWarp) {
+                        // ---------- MMA issuer (whole warp converged, one elected lane issues)
+                        if (njob > 0) tc::mbar_wait(&bar_tfree, (njob - 1) & 1);
+                        tc::tc_fence_after();
+                        const uint32_t idesc1 = tc::make_idesc_tf32(128, J.bn, a_mn ? 1 : 0, b_mn ? 1 : 0);
+                        const uint32_t idesc2 = tc::make_idesc_tf32(128, 2 * J.bn, a_mn ? 1 : 0, b_mn ? 1 : 0);
+                        const uint32_t a_hiw = a_mn ? tc::kDescHiMN : tc::kDescHiK, a_low = a_mn ? tc::kDescLoMN : tc::kDescLoK;
+                        const uint32_t b_hiw = b_mn ? tc::kDescHiMN : tc::kDescHiK, b_low = b_mn ? tc::kDescLoMN : tc::kDescLoK;
+                        const uint32_t a_k = a_mn ? (1024u >> 4) : (32u >> 4), b_k = b_mn ? (1024u >> 4) : (32u >> 4);   // per k-step of 8
+                        uint32_t acc = 0;
+                        for (int i = 0; i < J.nch; ++i) {
+                            tc::mbar_wait(&bar_full[ring_s], ring_ph);
                             tc::tc_fence_after();
-                            const uint32_t idesc = tc::make_idesc_tf32(128, J.bn, a_mn ? 1 : 0, b_mn ? 1 : 0);
-                            uint32_t acc = 0;
-                            for (int i = 0; i < J.nch; ++i, ++it) {
-                                const int s = it % STAGES;
-                                tc::mbar_wait(&bar_full[s], (it / STAGES) & 1);
-                                if (passes == 3) tc::mbar_wait(&bar_split[s], (it / STAGES) & 1);
-                                tc::tc_fence_after();
+                            const uint32_t st = (smem_base + (uint32_t)ring_s * STAGE_BYTES) >> 4;
+                            if (tc::elect_one()) {
                                 if (tim && i == 0) a.timing[tslot + 4] = (unsigned long long)clock64();
-                                const uint32_t st = tc::smem_u32(smem + (size_t)s * stage_bytes);
-                                const uint32_t aA = st, aB = st + A_BYTES, aAlo = st + A_BYTES + B_BYTES, aBlo = aAlo + A_BYTES;
-                                for (int pass = 0; pass < passes; ++pass) {
-                                    const uint32_t pa = (pass == 2) ? aAlo : aA;   // pass 0: A*B, 1: A*B_lo, 2: A_lo*B
-                                    const uint32_t pb = (pass == 1) ? aBlo : aB;
+                                const uint32_t aw = st | a_low, alw = aw + (A_BYTES >> 4);
+                                const uint32_t bw = (st + ((2 * A_BYTES) >> 4)) | b_low;
+                                if (x3) {
 #pragma unroll
                                     for (int k = 0; k < KCH / 8; ++k) {
-                                        const uint64_t da = a_mn ? tc::make_smem_desc(pa + k * 1024, 4096, 512, 1)
-                                                                 : tc::make_smem_desc(pa + k * 32, 16, 1024, tc::kSwizzle128B);
-                                        const uint64_t db = b_mn ? tc::make_smem_desc(pb + k * 1024, 4096, 512, 1)
-                                                                 : tc::make_smem_desc(pb + k * 32, 16, 1024, tc::kSwizzle128B);
-                                        tc::mma_tf32(tmem, da, db, idesc, acc);
+                                        // A.[B | B_lo] -> columns [0, bn) and [bn, 2 bn);  A_lo.B -> columns [0, bn)
+                                        tc::mma_tf32(tmem, tc::desc_words(aw + k * a_k, a_hiw), tc::desc_words(bw + k * b_k, b_hiw), idesc2, acc);
+                                        tc::mma_tf32(tmem, tc::desc_words(alw + k * a_k, a_hiw), tc::desc_words(bw + k * b_k, b_hiw), idesc1, 1u);
+                                        acc = 1;
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int k = 0; k < KCH / 8; ++k) {
+                                        tc::mma_tf32(tmem, tc::desc_words(aw + k * a_k, a_hiw), tc::desc_words(bw + k * b_k, b_hiw), idesc1, acc);
                                         acc = 1;
                                     }
                                 }
-                                tc::mma_commit(&bar_empty[s]);
+                                tc::mma_commit(&bar_empty[ring_s]);
                             }
+                            __syncwarp();
+                            if (++ring_s == kStages) { ring_s = 0; ring_ph ^= 1; }
+                        }
+                        if (tc::elect_one()) {
                             tc::mma_commit(&bar_done);
                             if (tim) a.timing[tslot + 5] = (unsigned long long)clock64();
-                        } else {
-                            it += J.nch;
                         }
-                        it = __shfl_sync(0xffffffffu, it, 0);
+                        __syncwarp();
                     } else {
-                        // ---------- workers
-                        const int row = J.m_tile * 128 + tid;
+                        // ---------- workers: prelude in the shadow of the mainloop, then the epilogue
+                        const int q = warp & 3, hf = warp >> 2;           // TMEM lane quarter, column half of the tile
+                        const int rloc = q * 32 + lane;                   // row inside the tile = TMEM lane
+                        const int row = J.m_tile * 128 + rloc;
                         const bool valid = row < rows;
                         const int N = (J.type == J_DH) ? a.n[l] : a.n[l + 1];   // output row pitch
                         const int col0 = J.n_tile * J.bn;
@@ -613,20 +685,20 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                             const int bn = J.bn;
                             worker_sync();   // the previous job's epilogue may still be reading s_beff / scratch
                             if (l == 0) {
-                                float* part = reinterpret_cast<float*>(scratch);   // [4][bn]
+                                float* part = reinterpret_cast<float*>(scratch);   // [groups][bn]
                                 const int groups = kWorkers / bn, per = cdiv(a.dd, groups);
                                 const int c = tid % bn, gq = tid / bn;
                                 const float* W0dom = a.params + a.off_W[0] + (long long)K0 * N + col0 + c;
                                 const float* ed = a.params + a.off_Ed + (long long)pd.dom * a.dd;
                                 float s = 0.f;
                                 const int k_end = (gq + 1) * per < a.dd ? (gq + 1) * per : a.dd;
-#pragma unroll 8
+#pragma unroll 16
                                 for (int k = gq * per; k < k_end; ++k) s = fmaf(ldcg_f(ed + k), ldcg_f(W0dom + (long long)k * N), s);
                                 part[gq * bn + c] = s;
                                 worker_sync();
                                 if (tid < bn) {
                                     float dsum = 0.f;
-                                    for (int q = 0; q < groups; ++q) dsum += part[q * bn + tid];
+                                    for (int g2 = 0; g2 < groups; ++g2) dsum += part[g2 * bn + tid];
                                     s_beff[tid] = ldcg_f(a.params + a.off_b[0] + col0 + tid) + dsum;
                                 }
                             } else if (tid < bn) {
@@ -635,107 +707,86 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                             if (J.type == J_HEAD && tid >= 64 && tid < 64 + NL) s_wd[tid - 64] = ldcg_f(a.params + a.off_w + tid - 64);
                             worker_sync();
                         }
-                        if (passes == 3) {
-                            // 3xTF32: derive the "lo" operands of every landed chunk in shared memory
-                            const int nv = (A_BYTES + J.bn * KCH * 4) / 16;   // float4 count, A then B (B is contiguous after A)
-                            for (int i = 0; i < J.nch; ++i, ++it) {
-                                const int s = it % STAGES;
-                                tc::mbar_wait(&bar_full[s], (it / STAGES) & 1);
-                                float4* hi = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
-                                float4* lo = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + A_BYTES + B_BYTES);
-                                for (int q = tid; q < nv; q += kWorkers) {
-                                    const float4 x = hi[q];
-                                    // A_lo sits at +0, B_lo at +A_BYTES inside the lo half (same offsets as the hi half)
-                                    lo[q] = make_float4(tcg::tf32_lo(x.x), tcg::tf32_lo(x.y), tcg::tf32_lo(x.z), tcg::tf32_lo(x.w));
-                                }
-                                tc::fence_proxy_async();
-                                tc::mbar_arrive(&bar_split[s]);
-                            }
-                        } else {
-                            it += J.nch;
-                        }
-                        unsigned long long keepmask = ~0ull;   // bit c: column col0 + c of this row survives dropout
+                        // dropout keep bits of this thread's columns (bit c: column cbase + c of this row survives)
+                        constexpr int NLH = NL / 2;
+                        const int cbase = J.type == J_HEAD ? hf * NLH : hf * 16;   // first column (inside the tile) of this thread
+                        uint32_t keepmask = 0xffffffffu;
                         if (dp.enabled && (J.type == J_FWD || J.type == J_HEAD)) {
-                            DropoutParams q = dp;
-                            q.seed = a.dropout_seed + (uint32_t)l;
-                            keepmask = 0ull;
-                            const uint32_t e0 = (uint32_t)row * (uint32_t)N + (uint32_t)col0;
-                            if (J.type == J_FWD) {
+                            DropoutParams dq = dp;
+                            dq.seed = a.dropout_seed + (uint32_t)l;
+                            keepmask = 0u;
+                            const uint32_t e0 = (uint32_t)row * (uint32_t)N + (uint32_t)(col0 + cbase);
+                            const int ncol = J.type == J_HEAD ? NLH : 16;
 #pragma unroll
-                                for (int c = 0; c < 32; c += 4) {
-                                    const uint4 w = dropout_words4(q, e0 + c);
-                                    const unsigned long long nib = (w.x < q.threshold ? 1u : 0u) | (w.y < q.threshold ? 2u : 0u) |
-                                                                   (w.z < q.threshold ? 4u : 0u) | (w.w < q.threshold ? 8u : 0u);
-                                    keepmask |= nib << c;
-                                }
-                            } else {
-#pragma unroll
-                                for (int c = 0; c < NL; c += 4) {
-                                    const uint4 w = dropout_words4(q, e0 + c);
-                                    const unsigned long long nib = (w.x < q.threshold ? 1u : 0u) | (w.y < q.threshold ? 2u : 0u) |
-                                                                   (w.z < q.threshold ? 4u : 0u) | (w.w < q.threshold ? 8u : 0u);
+                            for (int c = 0; c < 32; c += 4) {
+                                if (c < ncol) {
+                                    const uint4 w = dropout_words4(dq, e0 + c);
+                                    const uint32_t nib = (w.x < dq.threshold ? 1u : 0u) | (w.y < dq.threshold ? 2u : 0u) |
+                                                         (w.z < dq.threshold ? 4u : 0u) | (w.w < dq.threshold ? 8u : 0u);
                                     keepmask |= nib << c;
                                 }
                             }
                         }
-                        WSTAMP(12);
+                        float4 hmask[4];   // dH: the forward activations of this thread's 16 columns (all loads before the wait)
+                        if (J.type == J_DH) {
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                hmask[u] = valid ? ldcg_f4(a.H[l] + (long long)row * N + col0 + cbase + u * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
                         tc::mbar_wait(&bar_done, njob & 1);
                         tc::tc_fence_after();
                         if (tim && tid == 0) a.timing[tslot + 6] = (unsigned long long)clock64();
-                        const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+                        const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
 
                         if (J.type == J_FWD) {
                             WSTAMP(8);
-                            float* out = a.H[l + 1];
+                            float* out = a.H[l + 1] + (long long)row * N + col0 + cbase;
+                            const long long oz = (long long)a.max_rows * N;
                             const float dscale = dp.enabled ? dp.scale : 1.0f;
-#pragma unroll
-                            for (int n0 = 0; n0 < 32; n0 += 16) {
-                                float vv[16];
-                                tc::tmem_ld16(tlane + n0, vv);
-                                if (valid) {
-#pragma unroll
-                                    for (int jx = 0; jx < 16; jx += 4) {
-                                        float h[4];
-#pragma unroll
-                                        for (int t = 0; t < 4; ++t) {
-                                            h[t] = fmaxf(vv[jx + t] + s_beff[n0 + jx + t], 0.f);
-                                            h[t] = (keepmask >> (n0 + jx + t)) & 1ull ? h[t] * dscale : 0.f;
-                                        }
-                                        const float4 hv = make_float4(h[0], h[1], h[2], h[3]);
-                                        *reinterpret_cast<float4*>(out + (long long)row * N + col0 + n0 + jx) = rnd ? rn_tf32_4(hv) : hv;
-                                    }
-                                }
-                            }
+                            float vv[16], v2[16];
+                            tc::tmem_ld16(tlane + cbase, vv);
+                            if (x3) tc::tmem_ld16(tlane + 32 + cbase, v2);
                             tc::tc_fence_before();
                             tc::mbar_arrive(&bar_tfree);
+                            if (valid) {
+#pragma unroll
+                                for (int jx = 0; jx < 16; jx += 4) {
+                                    float h[4];
+#pragma unroll
+                                    for (int t = 0; t < 4; ++t) {
+                                        const float accv = x3 ? vv[jx + t] + v2[jx + t] : vv[jx + t];
+                                        h[t] = fmaxf(accv + s_beff[cbase + jx + t], 0.f);
+                                        h[t] = (keepmask >> (jx + t)) & 1u ? h[t] * dscale : 0.f;
+                                    }
+                                    store_pair4(out + jx, oz, make_float4(h[0], h[1], h[2], h[3]), rnd, x3);
+                                }
+                            }
                             WSTAMP(9);
                         } else if (J.type == J_HEAD) {
                             // last hidden layer + Dense(1) + sigmoid + BCE + ds + dZ_{L-1} + per-tile partials + AUC bins
-                            float h[NL];
-                            float z = 0.f;
+                            float h[NLH];
+                            float zp = 0.f;
                             const float dscale = dp.enabled ? dp.scale : 1.0f;
 #pragma unroll
-                            for (int n0 = 0; n0 < NL; n0 += 16) {
-                                float vv[16];
-                                tc::tmem_ld16(tlane + n0, vv);
+                            for (int n0 = 0; n0 < NLH; n0 += 16) {
+                                float vv[16], v2[16];
+                                tc::tmem_ld16(tlane + cbase + n0, vv);
+                                if (x3) tc::tmem_ld16(tlane + NL + cbase + n0, v2);
 #pragma unroll
-                                for (int jx = 0; jx < 16; jx += 4) {
-                                    float hh[4];
-#pragma unroll
-                                    for (int t = 0; t < 4; ++t) {
-                                        hh[t] = fmaxf(vv[jx + t] + s_beff[n0 + jx + t], 0.f);
-                                        hh[t] = (keepmask >> (n0 + jx + t)) & 1ull ? hh[t] * dscale : 0.f;
-                                    }
-                                    const float4 wv = *reinterpret_cast<const float4*>(s_wd + n0 + jx);
-#pragma unroll
-                                    for (int t = 0; t < 4; ++t) h[n0 + jx + t] = valid ? hh[t] : 0.f;
-                                    z = fmaf(hh[0], wv.x, z); z = fmaf(hh[1], wv.y, z);
-                                    z = fmaf(hh[2], wv.z, z); z = fmaf(hh[3], wv.w, z);
+                                for (int jx = 0; jx < 16; ++jx) {
+                                    const float accv = x3 ? vv[jx] + v2[jx] : vv[jx];
+                                    float hh = fmaxf(accv + s_beff[cbase + n0 + jx], 0.f);
+                                    hh = (keepmask >> (n0 + jx)) & 1u ? hh * dscale : 0.f;
+                                    h[n0 + jx] = valid ? hh : 0.f;
+                                    zp = fmaf(hh, s_wd[cbase + n0 + jx], zp);
                                 }
                             }
                             tc::tc_fence_before();
                             tc::mbar_arrive(&bar_tfree);
                             WSTAMP(8);
+                            s_z[hf][rloc] = zp;
+                            worker_sync();
+                            const float z = s_z[0][rloc] + s_z[1][rloc];
                             const float lo_c = 1e-7f, hi_c = 1.0f - 1e-7f;
                             float dsv = 0.f;
                             double bce = 0.0;
@@ -743,161 +794,126 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                                 const float sgm = z + ldcg_f(a.params + a.off_g);
                                 const float pv = 1.0f / (1.0f + expf(-sgm));
                                 const float yv = a.y[buf][row];
-                                const float ph = fminf(fmaxf(pv, lo_c), hi_c);
-                                const float lg = logf(ph / (1.0f - ph));
-                                bce = (double)(fmaxf(lg, 0.f) - lg * yv + log1pf(expf(-fabsf(lg))));
-                                if (pd.probs) pd.probs[(long long)step * a.bs + row] = pv;
                                 if (a.train) dsv = (fabsf(sgm) <= MAMDR_LOGIT_CLIP) ? __fdiv_rn(__fsub_rn(pv, yv), (float)rows) : 0.f;
-                                if (a.auc_acc) {
-                                    int lo_i = 0, hi_i = a.T;
-                                    while (lo_i < hi_i) {
-                                        const int mid = (lo_i + hi_i) >> 1;
-                                        if (s_thr[mid] < pv) lo_i = mid + 1; else hi_i = mid;
+                                if (hf == 0) {
+                                    const float ph = fminf(fmaxf(pv, lo_c), hi_c);
+                                    const float lg = logf(ph / (1.0f - ph));
+                                    bce = (double)(fmaxf(lg, 0.f) - lg * yv + log1pf(expf(-fabsf(lg))));
+                                    if (pd.probs) pd.probs[(long long)step * a.bs + row] = pv;
+                                    if (a.auc_acc) {
+                                        int lo_i = 0, hi_i = a.T;
+                                        while (lo_i < hi_i) {
+                                            const int mid = (lo_i + hi_i) >> 1;
+                                            if (s_thr[mid] < pv) lo_i = mid + 1; else hi_i = mid;
+                                        }
+                                        atomicAdd(&hist_cur[(yv != 0.f ? (a.T + 1) : 0) + lo_i], 1);
                                     }
-                                    atomicAdd(&hist_cur[(yv != 0.f ? (a.T + 1) : 0) + lo_i], 1);
                                 }
                             }
                             WSTAMP(9);
                             double* red_d = reinterpret_cast<double*>(scratch);               // [4]
                             float* red_f = reinterpret_cast<float*>(scratch + 64);            // [4]
-                            float* colbuf = reinterpret_cast<float*>(scratch + 1024);         // [128][NL + 1]
-                            float* gsum = reinterpret_cast<float*>(scratch + 1024 + 128 * (NL + 1) * 4);   // [GROUPS][NL]
-                            double bs = bce;
-                            float dgs = dsv;
+                            float* csum = reinterpret_cast<float*>(scratch + 128);            // [2 kinds][8 warps][NLH]
+                            if (hf == 0) {
+                                double bs = bce;
+                                float dgs = dsv;
 #pragma unroll
-                            for (int o = 16; o > 0; o >>= 1) {
-                                bs += __shfl_xor_sync(0xffffffffu, bs, o);
-                                dgs += __shfl_xor_sync(0xffffffffu, dgs, o);
+                                for (int o = 16; o > 0; o >>= 1) {
+                                    bs += __shfl_xor_sync(0xffffffffu, bs, o);
+                                    dgs += __shfl_xor_sync(0xffffffffu, dgs, o);
+                                }
+                                if (lane == 0) { red_d[q] = bs; red_f[q] = dgs; }
                             }
-                            if (lane == 0) { red_d[warp] = bs; red_f[warp] = dgs; }
                             if (a.train) {
-                                float* dZ = a.dZ[L - 1];
+                                float* dZ = a.dZ[L - 1] + (long long)row * NL + cbase;
+                                const long long oz = (long long)a.max_rows * NL;
                                 const bool store = row < a.max_rows;
+                                float hd[NLH];   // h * ds  (column sums -> gradient of the Dense(1) kernel)
 #pragma unroll
-                                for (int c = 0; c < NL; c += 4) {
-                                    const float4 wv = *reinterpret_cast<const float4*>(s_wd + c);
-                                    const float wq[4] = {wv.x, wv.y, wv.z, wv.w};
+                                for (int c = 0; c < NLH; c += 4) {
                                     float dz[4];
 #pragma unroll
                                     for (int t = 0; t < 4; ++t) {
-                                        const float dh = __fmul_rn(dsv, wq[t]);
+                                        const float dh = __fmul_rn(dsv, s_wd[cbase + c + t]);
                                         dz[t] = h[c + t] > 0.f ? __fmul_rn(dh, inv_keep) : 0.f;
-                                        colbuf[tid * (NL + 1) + c + t] = h[c + t] * dsv;
+                                        hd[c + t] = h[c + t] * dsv;
                                         h[c + t] = dz[t];
                                     }
                                     // rows past the batch get zeros: dW's K loop runs over whole 32-row chunks
-                                    if (store) {
-                                        const float4 dv = make_float4(dz[0], dz[1], dz[2], dz[3]);
-                                        *reinterpret_cast<float4*>(dZ + (long long)row * NL + c) = rnd ? rn_tf32_4(dv) : dv;
-                                    }
+                                    if (store) store_pair4(dZ + c, oz, make_float4(dz[0], dz[1], dz[2], dz[3]), rnd, x3);
+                                }
+                                WSTAMP(10);
+                                const float s_hd = warp_colsum<NLH>(hd, lane);
+                                const float s_dz = warp_colsum<NLH>(h, lane);
+                                const int cl = NLH == 32 ? lane : lane >> 1;
+                                if (NLH == 32 || (lane & 1) == 0) {
+                                    csum[(0 * kWorkerWarps + warp) * NLH + cl] = s_hd;
+                                    csum[(1 * kWorkerWarps + warp) * NLH + cl] = s_dz;
                                 }
                             }
-                            WSTAMP(10);
                             worker_sync();
                             if (tid == 0) {
                                 a.loss_part[buf * kMaxMT + J.m_tile] = red_d[0] + red_d[1] + red_d[2] + red_d[3];
                                 a.dg_part[J.m_tile] = red_f[0] + red_f[1] + red_f[2] + red_f[3];
                             }
-                            if (a.train) {
-                                constexpr int GROUPS = 128 / NL, RPG = 128 / GROUPS;
-                                const int c = tid % NL, gq = tid / NL;
-                                {
-                                    float s4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-                                    for (int r = gq * RPG; r < (gq + 1) * RPG; r += 4) {
+                            if (a.train && tid < 2 * NL) {
+                                // column c of the tile (half c / NLH): the four row-quarter warps in order
+                                const int kind = tid / NL, c = tid - kind * NL, h2 = c / NLH, cc = c - h2 * NLH;
+                                float s = 0.f;
 #pragma unroll
-                                        for (int u = 0; u < 4; ++u) s4[u] += colbuf[(r + u) * (NL + 1) + c];
-                                    }
-                                    gsum[gq * NL + c] = (s4[0] + s4[1]) + (s4[2] + s4[3]);
-                                }
-                                worker_sync();
-                                if (tid < NL) {
-                                    float s = 0.f;
-#pragma unroll
-                                    for (int g2 = 0; g2 < GROUPS; ++g2) s += gsum[g2 * NL + tid];
-                                    a.dw_part[J.m_tile * NL + tid] = s;
-                                }
-                                worker_sync();
-#pragma unroll
-                                for (int cc = 0; cc < NL; ++cc) colbuf[tid * (NL + 1) + cc] = h[cc];   // dZ_{L-1} (zeros on invalid rows)
-                                worker_sync();
-                                {
-                                    float s4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-                                    for (int r = gq * RPG; r < (gq + 1) * RPG; r += 4) {
-#pragma unroll
-                                        for (int u = 0; u < 4; ++u) s4[u] += colbuf[(r + u) * (NL + 1) + c];
-                                    }
-                                    gsum[gq * NL + c] = (s4[0] + s4[1]) + (s4[2] + s4[3]);
-                                }
-                                worker_sync();
-                                if (tid < NL) {
-                                    float s = 0.f;
-#pragma unroll
-                                    for (int g2 = 0; g2 < GROUPS; ++g2) s += gsum[g2 * NL + tid];
-                                    a.db_part[L - 1][J.m_tile * NL + tid] = s;
-                                }
+                                for (int qq = 0; qq < 4; ++qq) s += csum[(kind * kWorkerWarps + h2 * 4 + qq) * NLH + cc];
+                                (kind == 0 ? a.dw_part : a.db_part[L - 1])[J.m_tile * NL + c] = s;
                             }
                             worker_sync();
                             WSTAMP(11);
                         } else if (J.type == J_DH) {
-                            // dZ_{l-1}[row, col0..col0+32) = acc * inv_keep * 1[H_l > 0]; per-tile column sums -> db_{l-1}
-                            const float* Hm = a.H[l];
-                            float* out = a.dZ[l - 1];
-                            float dzv[32];
+                            // dZ_{l-1}[row, col0 + cbase .. +16) = acc * inv_keep * 1[H_l > 0]; per-tile column sums -> db_{l-1}
+                            float* out = a.dZ[l - 1] + (long long)row * N + col0 + cbase;
+                            const long long oz = (long long)a.max_rows * N;
                             const bool store = row < a.max_rows;
-                            float4 hmask[8];   // all loads first: the stores below may alias as far as the compiler knows
-#pragma unroll
-                            for (int u = 0; u < 8; ++u)
-                                hmask[u] = valid ? ldcg_f4(Hm + (long long)row * N + col0 + u * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                            for (int n0 = 0; n0 < 32; n0 += 16) {
-                                float vv[16];
-                                tc::tmem_ld16(tlane + n0, vv);
-#pragma unroll
-                                for (int jx = 0; jx < 16; jx += 4) {
-                                    float r4[4] = {0.f, 0.f, 0.f, 0.f};
-                                    const long long o = (long long)row * N + col0 + n0 + jx;
-                                    if (valid) {
-                                        const float4 hq = hmask[(n0 + jx) >> 2];
-                                        r4[0] = hq.x > 0.f ? vv[jx] * inv_keep : 0.f;
-                                        r4[1] = hq.y > 0.f ? vv[jx + 1] * inv_keep : 0.f;
-                                        r4[2] = hq.z > 0.f ? vv[jx + 2] * inv_keep : 0.f;
-                                        r4[3] = hq.w > 0.f ? vv[jx + 3] * inv_keep : 0.f;
-                                    }
-                                    if (store) {
-                                        const float4 dv = make_float4(r4[0], r4[1], r4[2], r4[3]);
-                                        *reinterpret_cast<float4*>(out + o) = rnd ? rn_tf32_4(dv) : dv;
-                                    }
-#pragma unroll
-                                    for (int t = 0; t < 4; ++t) dzv[n0 + jx + t] = r4[t];
-                                }
-                            }
+                            float vv[16], v2[16], dzv[16];
+                            tc::tmem_ld16(tlane + cbase, vv);
+                            if (x3) tc::tmem_ld16(tlane + 32 + cbase, v2);
                             tc::tc_fence_before();
                             tc::mbar_arrive(&bar_tfree);
-                            float* colbuf = reinterpret_cast<float*>(scratch);                    // [128][33]
-                            float* gsum = reinterpret_cast<float*>(scratch + 128 * 33 * 4);       // [4][32]
 #pragma unroll
-                            for (int c = 0; c < 32; ++c) colbuf[tid * 33 + c] = dzv[c];
-                            worker_sync();
-                            {
-                                const int c = tid & 31, gq = tid >> 5;
-                                float s = 0.f;
-                                for (int r = gq * 32; r < gq * 32 + 32; ++r) s += colbuf[r * 33 + c];
-                                gsum[gq * 32 + c] = s;
+                            for (int jx = 0; jx < 16; jx += 4) {
+                                const float4 hq = hmask[jx >> 2];
+                                const float hm[4] = {hq.x, hq.y, hq.z, hq.w};
+#pragma unroll
+                                for (int t = 0; t < 4; ++t) {
+                                    const float accv = x3 ? vv[jx + t] + v2[jx + t] : vv[jx + t];
+                                    dzv[jx + t] = (valid && hm[t] > 0.f) ? accv * inv_keep : 0.f;
+                                }
+                                if (store) store_pair4(out + jx, oz, make_float4(dzv[jx], dzv[jx + 1], dzv[jx + 2], dzv[jx + 3]), rnd, x3);
                             }
+                            float* csum = reinterpret_cast<float*>(scratch);   // [8 warps][16]
+                            const float s_dz = warp_colsum<16>(dzv, lane);
+                            worker_sync();   // the previous job's readers of csum are done
+                            if ((lane & 1) == 0) csum[warp * 16 + (lane >> 1)] = s_dz;
                             worker_sync();
-                            if (tid < 32) a.db_part[l - 1][(long long)J.m_tile * N + col0 + tid] = gsum[tid] + gsum[32 + tid] + gsum[64 + tid] + gsum[96 + tid];
-                            worker_sync();
+                            if (tid < 32) {
+                                const int h2 = tid >> 4, cc = tid & 15;
+                                float s = 0.f;
+#pragma unroll
+                                for (int qq = 0; qq < 4; ++qq) s += csum[(h2 * 4 + qq) * 16 + cc];
+                                a.db_part[l - 1][(long long)J.m_tile * N + col0 + tid] = s;
+                            }
                         } else {   // J_DW: split-K partial of dW_l -> partials[l][z][tile][128][bn]
                             const int tile = J.m_tile * J.NT + J.n_tile;
-                            float* mine = a.partials[l] + (((long long)J.z * J.tiles + tile) * 128 + tid) * J.bn;
-                            for (int n0 = 0; n0 < J.bn; n0 += 16) {
-                                float vv[16];
-                                tc::tmem_ld16(tlane + n0, vv);
+                            const int half = J.bn >> 1;   // columns per thread: 32 (bn = 64) or 16 (bn = 32)
+                            float* mine = a.partials[l] + (((long long)J.z * J.tiles + tile) * 128 + rloc) * J.bn + hf * half;
+                            for (int n0 = 0; n0 < half; n0 += 16) {
+                                float vv[16], v2[16];
+                                tc::tmem_ld16(tlane + hf * half + n0, vv);
+                                if (x3) tc::tmem_ld16(tlane + J.bn + hf * half + n0, v2);
 #pragma unroll
-                                for (int jx = 0; jx < 16; jx += 4)
-                                    __stcg(reinterpret_cast<float4*>(mine + n0 + jx), make_float4(vv[jx], vv[jx + 1], vv[jx + 2], vv[jx + 3]));
+                                for (int jx = 0; jx < 16; jx += 4) {
+                                    float4 o4;
+                                    if (x3) o4 = make_float4(vv[jx] + v2[jx], vv[jx + 1] + v2[jx + 1], vv[jx + 2] + v2[jx + 2], vv[jx + 3] + v2[jx + 3]);
+                                    else o4 = make_float4(vv[jx], vv[jx + 1], vv[jx + 2], vv[jx + 3]);
+                                    __stcg(reinterpret_cast<float4*>(mine + n0 + jx), o4);
+                                }
                             }
                             tc::tc_fence_before();
                             tc::mbar_arrive(&bar_tfree);
@@ -908,9 +924,9 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                 if (phase == 2 * L - 1 && early_done && cta >= jobs_last_bwd)
                     update_items((long long)(cta - jobs_last_bwd) * kThreads + tid, (long long)(G - jobs_last_bwd) * kThreads, 1);
                 // while the few head tiles run, everyone else stages the next mini-batch
-                if (phase == L - 1 && step + 1 < pd.steps && warp < 4) {
+                if (phase == L - 1 && step + 1 < pd.steps && warp < kWorkerWarps) {
                     const int first = G > 2 * mt ? mt : 0;
-                    if (cta >= first) gather_rows(a, pd, step + 1, buf ^ 1, (cta - first) * 4 + warp, (G - first) * 4, lane, rnd);
+                    if (cta >= first) gather_rows(a, pd, step + 1, buf ^ 1, (cta - first) * kWorkerWarps + warp, (G - first) * kWorkerWarps, lane, rnd, x3);
                 }
             } else {
                 // ---------- update phase: Adam / SGD on the parameters whose gradients became final in the last backward
@@ -986,13 +1002,13 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 5) tc::tmem_dealloc(tmem, kTmemCols);
+    if (warp == kMmaWarp) tc::tmem_dealloc(tmem, kTmemCols);
 }
 
 // ---- workspace layout ---------------------------------------------------------------------------------------------
 struct PassWs {
     size_t bar, hist, X[2], y[2], H[MAMDR_MAX_LAYERS], dZ[MAMDR_MAX_LAYERS], partials[MAMDR_MAX_LAYERS], db_part[MAMDR_MAX_LAYERS];
-    size_t dw_part, dg_part, loss_part, db0_red, gEd_row, ed_row, ed_sq, wshadow, total;
+    size_t dw_part, dg_part, loss_part, db0_red, gEd_row, ed_row, ed_sq, wpair, wz, total;
 };
 
 inline PassWs pass_ws(const mamdr_mlp_desc& d, int B) {
@@ -1009,10 +1025,11 @@ inline PassWs pass_ws(const mamdr_mlp_desc& d, int B) {
     const int mt = Bp / 128;
     w.bar = take(64);
     w.hist = take((size_t)2 * 2 * (kMaxThr + 1) * 4);   // double-buffered by pass parity
-    for (int b = 0; b < 2; ++b) { w.X[b] = take((size_t)Bp * K0 * 4); w.y[b] = take((size_t)Bp * 4); }
+    // GEMM operands are pair arrays [2][Bp][width]: plane 0 = value, plane 1 = its 3xTF32 "lo" part
+    for (int b = 0; b < 2; ++b) { w.X[b] = take((size_t)2 * Bp * K0 * 4); w.y[b] = take((size_t)Bp * 4); }
     for (int l = 0; l < L; ++l) {
-        w.H[l] = l >= 1 ? take((size_t)Bp * d.hidden[l - 1] * 4) : 0;
-        w.dZ[l] = take((size_t)Bp * d.hidden[l] * 4);
+        w.H[l] = l >= 1 ? take((size_t)2 * Bp * d.hidden[l - 1] * 4) : 0;
+        w.dZ[l] = take((size_t)2 * Bp * d.hidden[l] * 4);
         const int in = l == 0 ? K0 : d.hidden[l - 1];
         const int bn = d.hidden[l] < 64 ? d.hidden[l] : 64;
         const size_t tiles = (size_t)((in + 127) / 128) * (d.hidden[l] / bn);
@@ -1026,14 +1043,13 @@ inline PassWs pass_ws(const mamdr_mlp_desc& d, int B) {
     w.gEd_row = take((size_t)d.emb_dim[2] * 4);
     w.ed_row = take((size_t)d.emb_dim[2] * 4);
     w.ed_sq = take(8);
-    w.wshadow = take((size_t)(d.arena_floats - d.off_domain_emb) * 4);   // dense span of the arena only
+    w.wz = ((size_t)(d.arena_floats - d.off_domain_emb) + 31) / 32 * 32;   // floats between the two planes of the kernel shadow
+    w.wpair = take(2 * w.wz * 4);                                          // dense span of the arena only
     w.total = off;
     return w;
 }
 
-inline size_t smem_bytes(int passes, int stages) {
-    return (size_t)stages * (A_BYTES + B_BYTES) * (passes == 3 ? 2 : 1) + kScratchBytes + 1024;
-}
+inline size_t smem_bytes() { return (size_t)kStages * STAGE_BYTES + kScratchBytes + 1024; }
 
 }  // namespace passk
 
@@ -1056,9 +1072,8 @@ static int pass_supported(mamdr_ctx* ctx, const mamdr_mlp_desc* d, int max_batch
 }
 
 int mamdr_pass_init_kernels(mamdr_ctx* ctx) {
-    const size_t big = smem_bytes(1, kMaxStages) > smem_bytes(3, 3) ? smem_bytes(1, kMaxStages) : smem_bytes(3, 3);
-    MAMDR_CUDA_OK(ctx, cudaFuncSetAttribute(pass_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big));
-    MAMDR_CUDA_OK(ctx, cudaFuncSetAttribute(pass_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big));
+    MAMDR_CUDA_OK(ctx, cudaFuncSetAttribute(pass_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
+    MAMDR_CUDA_OK(ctx, cudaFuncSetAttribute(pass_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
     return MAMDR_OK;
 }
 
@@ -1098,7 +1113,7 @@ int mamdr_meta_launch(mamdr_ctx* ctx, int meta_op, const MetaArgs& a, mamdr_stre
 
 static int launch_program(mamdr_ctx* ctx, const MapTable& mp, const PassArgs& a, cudaStream_t st) {
     MAMDR_CUDA_OK(ctx, cudaMemsetAsync(a.bar, 0, 64, st));
-    const size_t smem = smem_bytes(a.passes, a.stages);
+    const size_t smem = smem_bytes();
     void* kargs[] = {(void*)&mp, (void*)&a};
     const void* fn = a.n[a.L] == 64 ? (const void*)pass_kernel<64> : (const void*)pass_kernel<32>;
     MAMDR_CUDA_OK(ctx, cudaLaunchCooperativeKernel(fn, dim3(ctx->sm_count), dim3(kThreads), kargs, smem, st));
@@ -1163,7 +1178,8 @@ static int run_pass(mamdr_ctx* ctx, const mamdr_mlp_desc* d, const mamdr_pass* p
     a.dw_part = (float*)(ws + w.dw_part); a.dg_part = (float*)(ws + w.dg_part); a.loss_part = (double*)(ws + w.loss_part);
     a.db0_red = (float*)(ws + w.db0_red); a.gEd_row = (float*)(ws + w.gEd_row); a.ed_row = (float*)(ws + w.ed_row);
     a.ed_sq = (double*)(ws + w.ed_sq);
-    a.wshadow = (float*)(ws + w.wshadow) - d->off_domain_emb;   // indexed with arena offsets
+    a.wpair = (float*)(ws + w.wpair) - d->off_domain_emb;   // indexed with arena offsets
+    a.wz = (long long)w.wz;
     a.hist = (int*)(ws + w.hist);
     a.bar = (unsigned int*)(ws + w.bar);
     a.state = (OptState*)opt_state;
@@ -1178,25 +1194,27 @@ static int run_pass(mamdr_ctx* ctx, const mamdr_mlp_desc* d, const mamdr_pass* p
     a.auc_acc = auc_acc; a.thr = thr; a.T = auc_acc ? T : 0;
     a.train = train ? 1 : 0;
     a.passes = precision_mode == MAMDR_PREC_TF32X3 ? 3 : 1;
-    a.stages = a.passes == 3 ? 3 : kMaxStages;
     a.timing = (unsigned long long*)ctx->dbg_timing;
     a.timing_cap = ctx->dbg_timing_cap;
 
     MapTable mp;
     memset(&mp, 0, sizeof(mp));
     bool ok = true;
-    const float* wsrc = a.passes == 1 ? a.wshadow : params;   // B operands of fwd / dH
+    // every GEMM operand is a pair array; the lo plane lies Bp * width floats (kernels: wz floats) behind the hi plane
+    const float* wsrc = a.wpair;   // B operands of fwd / dH: the pair shadow of the kernels
     for (int b = 0; b < 2; ++b) {
-        ok = ok && mlptc::kmajor_map(ctx, &mp.xk[b], a.X[b], Bp, a.n[0], 128) && mlptc::mnmajor_map(ctx, &mp.xmn[b], a.X[b], Bp, a.n[0]);
+        const uint64_t z = (uint64_t)Bp * a.n[0];
+        ok = ok && mlptc::pair_kmajor_map(ctx, &mp.xk[b], a.X[b], Bp, a.n[0], 128, z) && mlptc::pair_mnmajor_map(ctx, &mp.xmn[b], a.X[b], Bp, a.n[0], z);
     }
     for (int l = 0; l < L; ++l) {
+        const uint64_t zh = (uint64_t)Bp * a.n[l], zd = (uint64_t)Bp * a.n[l + 1];
         if (l >= 1) {
-            ok = ok && mlptc::kmajor_map(ctx, &mp.hk[l], a.H[l], Bp, a.n[l], 128) && mlptc::mnmajor_map(ctx, &mp.hmn[l], a.H[l], Bp, a.n[l]);
-            ok = ok && mlptc::kmajor_map(ctx, &mp.dzk[l], a.dZ[l], Bp, a.n[l + 1], 128);
-            ok = ok && mlptc::kmajor_map(ctx, &mp.wb[l], wsrc + d->off_kernel[l], a.n[l], a.n[l + 1], 32);
+            ok = ok && mlptc::pair_kmajor_map(ctx, &mp.hk[l], a.H[l], Bp, a.n[l], 128, zh) && mlptc::pair_mnmajor_map(ctx, &mp.hmn[l], a.H[l], Bp, a.n[l], zh);
+            ok = ok && mlptc::pair_kmajor_map(ctx, &mp.dzk[l], a.dZ[l], Bp, a.n[l + 1], 128, zd);
+            ok = ok && mlptc::pair_kmajor_map(ctx, &mp.wb[l], wsrc + d->off_kernel[l], a.n[l], a.n[l + 1], 32, (uint64_t)a.wz);
         }
-        ok = ok && mlptc::mnmajor_map(ctx, &mp.dzmn[l], a.dZ[l], Bp, a.n[l + 1]);
-        ok = ok && mlptc::mnmajor_map(ctx, &mp.wf[l], wsrc + d->off_kernel[l], a.n[l], a.n[l + 1]);
+        ok = ok && mlptc::pair_mnmajor_map(ctx, &mp.dzmn[l], a.dZ[l], Bp, a.n[l + 1], zd);
+        ok = ok && mlptc::pair_mnmajor_map(ctx, &mp.wf[l], wsrc + d->off_kernel[l], a.n[l], a.n[l + 1], (uint64_t)a.wz);
     }
     MAMDR_REQUIRE(ctx, ok, MAMDR_E_CUDA, "cuTensorMapEncodeTiled failed (pass kernel)");
 

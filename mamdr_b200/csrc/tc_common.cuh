@@ -50,6 +50,25 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
+// 3D tile load: coordinates (c0 = innermost element index, c1 = row index, c2 = plane: 0 = hi, 1 = lo of a pair array)
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+// One elected lane of a fully converged warp.  TMA / tcgen05.mma take their descriptors from UNIFORM registers: when the
+// whole warp runs the issue loop and only the instruction itself is predicated on the elected lane, the operands stay in
+// uniform registers; under `if (lane == 0)` every instruction pays an R2UR "waterfall" (measured 130-200 cycles per MMA
+// instead of 50, profiles/r2_probe_mainloop.txt).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // 2D tile store (shared -> global) through a tensor map, bulk-group completion
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
@@ -131,6 +150,13 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
     d |= (uint64_t)(layout_type & 7) << 61;
     return d;
 }
+// the same descriptor as two 32-bit words, for issue loops that only add a k offset to the low word:
+//   lo = (addr >> 4) | (LBO >> 4) << 16        hi = (SBO >> 4) | version 1 << 14 | layout_type << 29
+__device__ __forceinline__ uint64_t desc_words(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+constexpr uint32_t kDescHiK = (1024u >> 4) | (1u << 14) | (2u << 29);    // K-major, SWIZZLE_128B, SBO 1024 (8-row atoms)
+constexpr uint32_t kDescLoK = (16u >> 4) << 16;
+constexpr uint32_t kDescHiMN = (512u >> 4) | (1u << 14) | (1u << 29);    // MN-major, 128B swizzle with 32B atoms, SBO 512
+constexpr uint32_t kDescLoMN = (4096u >> 4) << 16;                       // LBO 4096: stride between 32-column groups
 constexpr uint32_t kSwizzleNone = 0, kSwizzle128B = 2, kSwizzle64B = 4, kSwizzle32B = 6;
 
 // instruction descriptor for kind::tf32 with fp32 accumulate: c_format=F32 [4,6)=1, a_format [7,10)=2 (TF32),
@@ -138,6 +164,14 @@ constexpr uint32_t kSwizzleNone = 0, kSwizzle128B = 2, kSwizzle64B = 4, kSwizzle
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn_major, int b_mn_major) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// 3xTF32: the tensor core truncates an fp32 operand to its tf32 "hi" part; lo = rn_tf32(x - hi) is fed separately
+__device__ __forceinline__ float tf32_lo(float x) {
+    const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+    uint32_t u = __float_as_uint(x - hi);            // exact
+    u += 0x00000FFFu + ((u >> 13) & 1u);             // round to nearest even at 13 dropped bits
+    return __uint_as_float(u & 0xFFFFE000u);
 }
 
 }  // namespace tc
@@ -169,6 +203,18 @@ inline bool make_tmap_2d_f32(CUtensorMap* out, const float* base, uint64_t rows,
     cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
     return fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// pair array [2][rows][cols] (plane 0 = hi, plane 1 = lo, `zstride` floats apart): 3-D map, box = [1, box_rows, box_cols]
+inline bool make_tmap_pair_f32(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint64_t zstride,
+                               uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle swz) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    cuuint64_t dims[3] = {cols, rows, 2};
+    cuuint64_t strides[2] = {ld * sizeof(float), zstride * sizeof(float)};
+    cuuint32_t box[3] = {box_cols, box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    return fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 }  // namespace tc
