@@ -733,6 +733,7 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                             for (int u = 0; u < 4; ++u)
                                 hmask[u] = valid ? ldcg_f4(a.H[l] + (long long)row * N + col0 + cbase + u * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
                         }
+                        WSTAMP(12);
                         tc::mbar_wait(&bar_done, njob & 1);
                         tc::tc_fence_after();
                         if (tim && tid == 0) a.timing[tslot + 6] = (unsigned long long)clock64();

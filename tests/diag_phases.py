@@ -46,8 +46,8 @@ def main(prec="tf32"):
             for cta in np.argsort(-busy)[:3]:
                 c0 = t[s, p, cta, 7]
                 rel = [(t[s, p, cta, k] - c0) / GHZ / 1e3 if t[s, p, cta, k] > 0 else float('nan') for k in (2, 3, 4, 5, 6)]
-                ep = " ".join("%.2f" % ((t[s, p, cta, k] - c0) / GHZ / 1e3) for k in (13, 14, 15, 10, 11, 9, 12, 8) if t[s, p, cta, k] > 0)
-                print("    cta %3d busy %.2f us | tma first-issue %.2f all-issued %.2f | mma first-full %.2f all-issued %.2f | done-seen %.2f | dec/wfull/wsplit/warrive/mma0done/prod-reuse/mask/epi0 %s" % ((cta, busy[cta]) + tuple(rel) + (ep,)))
+                ep = " ".join("%d:%.2f" % (k, (t[s, p, cta, k] - c0) / GHZ / 1e3) for k in (12, 8, 9, 10, 11) if t[s, p, cta, k] > 0)
+                print("    cta %3d busy %.2f us | tma first-issue %.2f all-issued %.2f | mma first-full %.2f all-issued %.2f | done-seen %.2f | prelude-done/epilogue stamps %s" % ((cta, busy[cta]) + tuple(rel) + (ep,)))
 
 
 if __name__ == "__main__":
