@@ -36,7 +36,8 @@ def build(force=False, verbose=False):
         return LIB
     os.makedirs(LIB_DIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-I", INCLUDE, "-o", LIB] + sources()
+    extra = os.environ.get("MAMDR_NVCC_EXTRA", "").split()   # e.g. -DPASS_DBG_SEG=2 for the in-kernel timing probes
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-I", INCLUDE, "-o", LIB] + sources()
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout)

@@ -8,32 +8,41 @@
 // (model_zoo/specific_base_model.py:82-85, model_zoo/base_model.py:130-133).
 //
 // Why one kernel: at batch 1024 a mini-batch is ~0.7 GFLOP over ~2 MB of L2-resident operands, i.e. ~1 us at
-// the B200 rooflines; a stream of per-layer kernels is bound by launch + pipeline-fill latency (measured 146 us
-// per mini-batch for 14 launches, profiles/r1_v2_*).  Here every SM keeps its barriers, TMEM allocation and
-// pipeline alive for the whole pass and the layers are separated by grid barriers (~1.2 us) instead of launches.
+// the B200 rooflines; everything is bound by the latency of DEPENDENT steps.  v1 / v2 of this kernel walked 7 phases
+// of 128-row tile jobs per mini-batch, separated by grid barriers (75 / 64 us per mini-batch; each phase re-loaded
+// 128 x K activation tiles into 64 SMs at the 76 B/clk/SM TMA rate).  v3 (this file) removes the dependence between
+// CTAs from the forward / backward-activation chain altogether:
 //
-// CTA = 10 warps: warps 0-7 = epilogue / element-wise workers (warp w <-> TMEM lanes 32 (w % 4) .. +31 <-> tile rows,
-// column half w / 4 of the tile), warp 8 = TMA producer, warp 9 = tcgen05.mma issuer (owns the TMEM allocation).
-// Both issue warps run their loops CONVERGED, one elected lane issuing: TMA and MMA descriptors then live in uniform
-// registers (under `if (lane == 0)` every instruction pays an R2UR waterfall: 130-200 cycles per MMA instead of 50,
+//   phase 0  "chain":  the mini-batch is cut into row groups of CR = 16 rows; ONE CTA runs the whole chain
+//            X -> H_1 -> .. -> H_L -> Dense(1) -> sigmoid-BCE -> dZ_{L-1} -> .. -> dZ_0 for its rows.  Every GEMM is
+//            computed TRANSPOSED ("swap A/B"): out^T[feature, row] = W^T . act^T, i.e. the WEIGHTS are the M = 128
+//            operand of tcgen05.mma (streamed once through a 4-stage TMA ring, 32 KB per k-chunk) and the activations
+//            are the N = 16 (+16 "lo") operand, which never leaves shared memory: an epilogue thread owns ONE output
+//            feature (= TMEM lane = k index of the next GEMM) for 8 rows, applies bias / ReLU / dropout (or the ReLU mask
+//            of the backward pass) and writes the next B operand straight into the 128B-swizzled K-major layout.
+//            No grid barrier, no global round trip and no pipeline refill between layers; the TMA ring keeps streaming
+//            weights across layer boundaries.  H_l / dZ_l also go to global memory (pair arrays) for phase 1.
+//            CTAs without a row group gather the NEXT mini-batch's embedding rows meanwhile (frozen tables).
+//   phase 1  "dW + update":  every weight gradient dW_l = H_l^T . dZ_l as split-K tile jobs (128 x 64 tiles, K = 128
+//            rows per job) over all CTAs; when the S split-K partials of a tile are in memory (a per-tile counter,
+//            release / acquire) each of the S CTAs reduces ITS 128 / S rows of the tile in fixed order and applies
+//            Adam / SGD to them -- no separate update phase.  The domain jobs (db_0, dE_d[dom], the domain block of W_0
+//            and the next fold) and the column-sum job (biases, Dense(1), the other rows of E_d) apply theirs directly.
+// = 2 grid barriers per mini-batch instead of 7.
+//
+// CTA = 10 warps: warps 0-7 = epilogue / element-wise workers (warp w <-> TMEM lanes 32 (w % 4) .. +31, row half
+// w / 4), warp 8 = TMA producer, warp 9 = tcgen05.mma issuer (owns the TMEM allocation).  Both issue warps run their
+// loops CONVERGED, one elected lane issuing: TMA and MMA descriptors then live in uniform registers (under
+// `if (lane == 0)` every instruction pays an R2UR waterfall: 130-200 cycles per MMA instead of 50,
 // profiles/r2_probe_mainloop.txt).
 //
-// 3xTF32 (MAMDR_PREC_TF32X3): every GEMM operand is kept in global memory as a PAIR array [2][rows][cols]: plane 0 =
-// the fp32 value (the tensor core truncates it to its tf32 "hi" part), plane 1 = lo = rn_tf32(x - hi), written by the
-// producing epilogue / gather / optimizer apply.  TMA stages [A | A_lo | B | B_lo]; B and B_lo are adjacent and form
-// ONE operand of N = 2 bn, so a k-step is two MMAs: A.[B | B_lo] (two accumulator halves) and A_lo.B (first half);
-// the epilogue adds the halves.  Dropped: A_lo.B_lo (2^-22 relative).
+// 3xTF32 (MAMDR_PREC_TF32X3): every GEMM operand exists as a PAIR: plane 0 = the fp32 value (the tensor core
+// truncates it to its tf32 "hi" part), plane 1 = lo = rn_tf32(x - hi), written by whoever produces the operand.  The
+// N operand is [hi rows | lo rows], so a k-step is two MMAs: W_hi.[act_hi | act_lo] (two accumulator halves) and
+// W_lo.act_hi (first half); the epilogue adds the halves.  Dropped: lo.lo (2^-22 relative).
 //
-// Per mini-batch (L hidden layers) the grid walks 2L+1 phases, each a list of independent tile jobs
-// (job j runs on CTA j mod grid):
-//   fwd l < L-1 : H_{l+1} = dropout(relu(H_l . W_l + b_l))         tiles 128 x 32        (l = 0: + E_d[dom] . W_0dom)
-//   fwd L-1     : last hidden layer + Dense(1) + sigmoid + BCE + dZ_{L-1} + AUC bins, tiles 128 x n_L; the other
-//                 CTAs gather the NEXT mini-batch's embedding rows (frozen tables: no dependence on the update)
-//   bwd l>=1    : dZ_{l-1} = (dZ_l . W_l^T) * mask(H_l) (+ db_{l-1} partials)  and  split-K partials of dW_l
-//   bwd l = 0   : split-K partials of dW_0, and the domain-embedding job (db_0, dE_d[dom], |E_d|^2)
-//   update      : fixed-order reduction of the partials fused with the Adam / SGD apply on every parameter
 // The domain embedding row is the same for every sample of a batch (utils/dataset.py:73-99: per-domain
-// datasets), so X is only [E_u | E_i] (K = 256) and the domain block of layer 0 is folded into its bias in fp32
+// datasets), so X is only [E_u | E_i] and the domain block of layer 0 is folded into its bias in fp32
 // (SURVEY.md A-10); its weight gradient is the rank-1 product E_d[dom]^T (x) db_0.
 // No float atomics anywhere: results are bit-reproducible run to run and rank to rank.
 #include <vector>
@@ -54,31 +63,54 @@ constexpr int kProdWarp = kWorkerWarps;       // warp 8
 constexpr int kMmaWarp = kWorkerWarps + 1;    // warp 9
 constexpr int kThreads = 32 * (kWorkerWarps + 2);
 constexpr int KCH = 32;                       // floats per K chunk = one 128-byte swizzle row
-constexpr int A_BYTES = 128 * KCH * 4;        // 16 KB: one A tile
-constexpr int B_BYTES = 64 * KCH * 4;         // 8 KB: one B tile at BN = 64
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // [A | A_lo | B | B_lo] = 48 KB
+constexpr int A_BYTES = 128 * KCH * 4;        // 16 KB: one M = 128 operand tile
+constexpr int B_BYTES = 64 * KCH * 4;         // 8 KB: one dW B tile at BN = 64
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // dW jobs: [A | A_lo | B | B_lo] = 48 KB
 constexpr int kStages = 4;
+constexpr int CR = 16;                        // rows of a chain job (row group)
+constexpr int kChainStage = 2 * A_BYTES;      // chain: [W | W_lo] = 32 KB per stage
+constexpr int kRingBytes = kStages * kChainStage;        // 128 KB; the two activation buffers follow
+constexpr int kMaxWidth = 256;                // widest layer the chain keeps in shared memory
+constexpr int kBChunk = 2 * CR * KCH * 4;     // 4 KB: one K chunk of the N operand, [hi rows | lo rows] x 32 k
+constexpr int kActBytes = (kMaxWidth / KCH) * kBChunk;   // 32 KB
+static_assert(kRingBytes + 2 * kActBytes == kStages * STAGE_BYTES, "the chain and dW layouts overlay the same 192 KB");
 constexpr int kScratchBytes = 20 * 1024;
 constexpr int kMaxThr = 1024;
 constexpr int kMaxSplit = 8;
-constexpr int kDomJobs = 8;                   // the domain-embedding gradient GEMV is split over this many CTAs
-constexpr int kMaxMT = 64;                    // 128-row tiles per mini-batch (batch <= 8192)
-constexpr uint32_t kTmemCols = 128;           // one accumulator of up to 2 x 64 columns
+constexpr int kDomJobs = 16;                  // the domain block (gradient GEMV, optimizer apply, fold) is split over this many CTAs
+constexpr int kRep = 4;                       // copies of the kernel pair shadow: every chain CTA streams ALL weights, and 64 CTAs
+                                              // reading the same L2 lines in lock-step serialise on the L2 slices
+constexpr int kMaxGroups = 8192 / CR;         // row groups per mini-batch (batch <= 8192)
+constexpr int kMaxSegs = 4 * MAMDR_MAX_LAYERS;
+constexpr int kBarBytes = 64 + 4 * 8 * MAMDR_MAX_LAYERS;   // grid-barrier counter + one counter per dW tile (<= 8 per layer)
+constexpr uint32_t kTmemCols = 128;           // dW: one accumulator of up to 2 x 64 columns; chain: two slots of 32
 
-enum { J_NONE = 0, J_FWD, J_HEAD, J_DH, J_DW, J_DOM };
+enum { J_NONE = 0, J_DW, J_DOM, J_RED };
+enum { S_FWD = 0, S_HEAD, S_DH };
 enum { SEG_ED = 0, SEG_KERNEL, SEG_BIAS, SEG_DENSE, SEG_GBIAS };
 
+// chain-phase layout of the scratch area
+constexpr int kScrMask = 0;                   // [kMaxSegs / 2][256] bytes: ReLU / dropout survivor bits of the 8 rows of a thread
+constexpr int kScrZp = 6144;                  // [2][4][8] floats: logit partials per (row half, lane quarter)
+constexpr int kScrDs = 6400;                  // [16] floats: ds of the rows
+constexpr int kScrComb = 6656;                // [2][2][128] floats: row-half combine of column sums
+
 struct MapTable {   // kernel parameter (param space is a legal tensor-map address space); every map is a pair map
-    CUtensorMap xk[2], xmn[2];                  // X double buffer: K-major [B, K0] / MN-major view
-    CUtensorMap hk[MAMDR_MAX_LAYERS];           // H_l  K-major  (A of fwd l),      l = 1..L-1
-    CUtensorMap hmn[MAMDR_MAX_LAYERS];          // H_l  MN-major (A of dW_l)
-    CUtensorMap dzk[MAMDR_MAX_LAYERS];          // dZ_l K-major  (A of dH_l),       l = 1..L-1
-    CUtensorMap dzmn[MAMDR_MAX_LAYERS];         // dZ_l MN-major (B of dW_l),       l = 0..L-1
-    CUtensorMap wf[MAMDR_MAX_LAYERS];           // W_l  MN-major [K, N] (B of fwd l)
-    CUtensorMap wb[MAMDR_MAX_LAYERS];           // W_l  K-major  [N = in, K = out] (B of dH_l), l = 1..L-1
+    CUtensorMap xk[2], xmn[2];                  // X double buffer: K-major [B, K0] (box CR rows) / MN-major view
+    CUtensorMap hmn[MAMDR_MAX_LAYERS];          // H_l  MN-major (A of dW_l), l = 1..L-1
+    CUtensorMap dzmn[MAMDR_MAX_LAYERS];         // dZ_l MN-major (B of dW_l), l = 0..L-1
+    CUtensorMap wf[MAMDR_MAX_LAYERS];           // W_l  MN-major [K = in, M = out] (A of the transposed forward GEMM)
+    CUtensorMap wb[MAMDR_MAX_LAYERS];           // W_l  K-major  [M = in, K = out] (A of the transposed dH GEMM), l = 1..L-1
 };
 
 struct Seg { long long off; int numel; int kind; int layer; };
+
+struct SegD {   // one GEMM of the chain: an M tile of a forward layer or of a dH layer
+    int kind, layer, mtile, nch, ngrp;   // nch = K chunks; ngrp = valid 32-feature groups of the tile (1..4)
+    int dep;                             // the last segment whose epilogue wrote this segment's N operand (-1: X)
+    int bsrc, bdst;                      // activation buffer read by the MMAs / written by the epilogue
+    int mseg;                            // S_DH: the forward segment that holds the ReLU mask bits of these features
+};
 
 struct PassDyn {   // the per-pass fields, loaded from the current ProgOp
     int dom, steps;
@@ -100,14 +132,16 @@ struct PassArgs {
     int nseg;
     Seg seg[2 * MAMDR_MAX_LAYERS + 3];
     float *params, *m, *v, *grads;    // grads may be NULL
-    float* wpair;                     // arena-indexed pair shadow of the kernels: plane 0 at wpair, plane 1 at wpair + wz
-    long long wz;
+    float* wpair;                     // arena-indexed pair shadow of the kernels: plane 0 at wpair, plane 1 at wpair + wz;
+    long long wz, wrep;               // kRep copies, wrep floats apart
     const float *Eu, *Ei;
     // ---- data
     int bs, max_rows;
     // ---- workspace (pair arrays: the lo plane lies max_rows * width floats behind the hi plane)
-    float *X[2], *y[2], *H[MAMDR_MAX_LAYERS], *dZ[MAMDR_MAX_LAYERS], *partials[MAMDR_MAX_LAYERS], *db_part[MAMDR_MAX_LAYERS];
-    float *dw_part, *dg_part, *db0_red, *gEd_row, *ed_row;
+    float *X[2], *y[2], *H[MAMDR_MAX_LAYERS], *dZ[MAMDR_MAX_LAYERS], *partials[MAMDR_MAX_LAYERS];
+    float *db_part[MAMDR_MAX_LAYERS];   // per-row-group column sums of dZ_l
+    float *dw_part, *dg_part, *fold_part;   // fold_part: [kDomJobs][n1] k-slice partials of E_d[dom] . W_0dom
+    unsigned int* tile_ctr;             // per dW tile: split-K partials written so far (monotonic over the launch)
     double *loss_part, *ed_sq;
     int* hist;
     unsigned int* bar;
@@ -126,7 +160,7 @@ struct PassArgs {
 };
 
 struct Job {
-    int type, layer, m_tile, n_tile, z, bn, nch, c_beg, tiles, NT;
+    int type, layer, m_tile, n_tile, z, bn, nch, c_beg, tiles, NT, gtile, S;
 };
 
 __host__ __device__ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
@@ -139,48 +173,34 @@ __host__ __device__ inline void split_plan(int rows, int& chunks, int& S, int& c
 }
 __host__ __device__ inline int dw_tiles(const PassArgs& a, int l) { return cdiv(a.n[l], 128) * (a.n[l + 1] / dw_bn(a, l)); }
 
-__host__ __device__ inline int phase_jobs(const PassArgs& a, int phase, int rows) {
-    const int L = a.L, mt = cdiv(rows, 128);
-    if (phase < L) return phase < L - 1 ? mt * (a.n[phase + 1] / 32) : mt;
-    const int l = L - 1 - (phase - L);
+// jobs of the dW phase: [domain jobs | column-sum job | split-K tile jobs of dW_0, dW_1, ...]
+__host__ __device__ inline int dw_phase_jobs(const PassArgs& a, int rows) {
     int chunks, S, cps;
     split_plan(rows, chunks, S, cps);
-    return (l >= 1 ? mt * (a.n[l] / 32) : kDomJobs) + dw_tiles(a, l) * S;
+    int n = kDomJobs + 1;
+    for (int l = 0; l < a.L; ++l) n += dw_tiles(a, l) * S;
+    return n;
 }
 
-__device__ __forceinline__ Job decode_job(const PassArgs& a, int phase, int rows, int j) {
+__device__ __forceinline__ Job decode_dw_job(const PassArgs& a, int rows, int j) {
     Job J;
-    J.z = 0; J.c_beg = 0; J.tiles = 0; J.NT = 1; J.n_tile = 0;
-    const int L = a.L;
-    if (phase < L) {
-        const int l = phase;
-        J.layer = l;
-        J.nch = a.n[l] / KCH;
-        if (l < L - 1) {
-            const int nt = a.n[l + 1] / 32;
-            J.type = J_FWD; J.m_tile = j / nt; J.n_tile = j - J.m_tile * nt; J.bn = 32;
-        } else {
-            J.type = J_HEAD; J.m_tile = j; J.bn = a.n[L];
-        }
-        return J;
-    }
-    const int l = L - 1 - (phase - L);
-    J.layer = l;
-    const int mt = cdiv(rows, 128);
-    const int nlead = l >= 1 ? mt * (a.n[l] / 32) : kDomJobs;
-    if (j < nlead) {
-        if (l >= 1) {
-            const int nt = a.n[l] / 32;
-            J.type = J_DH; J.m_tile = j / nt; J.n_tile = j - J.m_tile * nt; J.bn = 32; J.nch = a.n[l + 1] / KCH;
-        } else {
-            J.type = J_DOM; J.m_tile = j; J.bn = 0; J.nch = 0;
-        }
-        return J;
-    }
-    const int jj = j - nlead;
+    J.z = 0; J.c_beg = 0; J.tiles = 0; J.NT = 1; J.n_tile = 0; J.layer = 0; J.bn = 0; J.nch = 0; J.m_tile = 0; J.gtile = 0; J.S = 1;
+    if (j < kDomJobs) { J.type = J_DOM; J.m_tile = j; return J; }
+    if (j == kDomJobs) { J.type = J_RED; return J; }
+    int jj = j - kDomJobs - 1;
     int chunks, S, cps;
     split_plan(rows, chunks, S, cps);
+    int l = 0;
+    for (; l < a.L - 1; ++l) {
+        const int cnt = dw_tiles(a, l) * S;
+        if (jj < cnt) break;
+        jj -= cnt;
+    }
     J.type = J_DW;
+    J.layer = l;
+    J.S = S;
+    J.gtile = 0;
+    for (int l2 = 0; l2 < l; ++l2) J.gtile += dw_tiles(a, l2);
     J.bn = dw_bn(a, l);
     J.NT = a.n[l + 1] / J.bn;
     J.tiles = cdiv(a.n[l], 128) * J.NT;
@@ -188,6 +208,7 @@ __device__ __forceinline__ Job decode_job(const PassArgs& a, int phase, int rows
     const int t = jj - J.z * J.tiles;
     J.m_tile = t / J.NT;
     J.n_tile = t - J.m_tile * J.NT;
+    J.gtile += t;
     J.c_beg = J.z * cps;
     const int c_end = chunks < J.c_beg + cps ? chunks : J.c_beg + cps;
     J.nch = c_end - J.c_beg;
@@ -244,6 +265,10 @@ __device__ __forceinline__ void store_pair4(float* hi, long long z, float4 v, bo
     *reinterpret_cast<float4*>(hi) = rnd ? rn_tf32_4(v) : v;
     if (x3) *reinterpret_cast<float4*>(hi + z) = tf32_lo_4(v);
 }
+__device__ __forceinline__ void store_pair1(float* hi, long long z, float v, bool rnd, bool x3) {
+    *hi = rnd ? rn_tf32(v) : v;
+    if (x3) hi[z] = tc::tf32_lo(v);
+}
 
 __device__ __forceinline__ void adam1(float& p, float& m, float& v, float g, float alpha, float omb1, float omb2, float eps) {
     m = __fadd_rn(m, __fmul_rn(__fsub_rn(g, m), omb1));
@@ -251,14 +276,12 @@ __device__ __forceinline__ void adam1(float& p, float& m, float& v, float g, flo
     p = __fsub_rn(p, __fdiv_rn(__fmul_rn(m, alpha), __fadd_rn(__fsqrt_rn(v), eps)));
 }
 
-// Column sums over the 32 lanes of a warp (lane = tile row) of C per-lane values, in a fixed butterfly order:
-// afterwards lane l holds the total of column (C == 32 ? l : l >> 1).  31 (C = 32) / 16 (C = 16) shuffles.
-template <int C>
-__device__ __forceinline__ float warp_colsum(float (&v)[C], int lane) {
-    static_assert(C == 16 || C == 32, "16 or 32 columns per lane");
+// Sums over the 32 lanes of a warp of 8 per-lane values, in a fixed butterfly order: afterwards every lane holds the
+// total of value index ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1).  9 shuffles.
+__device__ __forceinline__ float warp_sum8(float (&v)[8], int lane) {
 #pragma unroll
-    for (int step = 0; step < (C == 32 ? 5 : 4); ++step) {
-        const int off = 16 >> step, half = (C / 2) >> step;
+    for (int step = 0; step < 3; ++step) {
+        const int off = 16 >> step, half = 4 >> step;
         const bool up = (lane & off) != 0;
 #pragma unroll
         for (int i = 0; i < half; ++i) {
@@ -268,8 +291,32 @@ __device__ __forceinline__ float warp_colsum(float (&v)[C], int lane) {
         }
     }
     float r = v[0];
-    if (C == 16) r += __shfl_xor_sync(0xffffffffu, r, 1);
+    r += __shfl_xor_sync(0xffffffffu, r, 2);
+    r += __shfl_xor_sync(0xffffffffu, r, 1);
     return r;
+}
+__device__ __forceinline__ int warp_sum8_index(int lane) { return ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1); }
+
+// fixed-order sum over the row groups g = 0 .. ng-1 of p[g * stride] by one warp (lane-strided, then a butterfly)
+__device__ __forceinline__ float warp_group_sum_f(const float* p, int ng, long long stride, int lane) {
+    float s = 0.f;
+    for (int g0 = 0; g0 < ng; g0 += 128) {
+        float q[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int g = g0 + u * 32 + lane; q[u] = g < ng ? ldcg_f(p + g * stride) : 0.f; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) s += q[u];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    return s;
+}
+__device__ __forceinline__ double warp_group_sum_d(const double* p, int ng, int lane) {
+    double s = 0.0;
+    for (int g = lane; g < ng; g += 32) s += __ldcg(p + g);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    return s;
 }
 
 // gather the rows of mini-batch `step` into the pair buffer X[buf] / y[buf]; one warp per row, 16-byte lanes
@@ -293,18 +340,51 @@ __device__ __forceinline__ void gather_rows(const PassArgs& a, const PassDyn& pd
     }
 }
 
+// k rows [kb, ke) of the domain block handled by domain job q
+__device__ __forceinline__ void dom_rows(const PassArgs& a, int q, int& kb, int& ke) {
+    const int per = cdiv(a.dd, kDomJobs);
+    kb = q * per;
+    ke = kb + per < a.dd ? kb + per : a.dd;
+    if (kb > ke) kb = ke;
+}
+
+// fold partial of domain job q from the CURRENT parameters: fold_part[q][c] = sum_{k in rows(q)} E_d[dom][k] W_0[K0 + k, c]
+// (pass prologue; inside a training pass the domain jobs publish it from the values they have just updated -- same
+// operands, same order, same bits)
+__device__ __forceinline__ void fold_from_params(const PassArgs& a, int dom, int q, int tid) {
+    int kb, ke;
+    dom_rows(a, q, kb, ke);
+    const int n1 = a.n[1], K0 = a.n[0];
+    const float* ed = a.params + a.off_Ed + (long long)dom * a.dd;
+    for (int c = tid; c < n1; c += kWorkers) {
+        const float* w = a.params + a.off_W[0] + (long long)(K0 + kb) * n1 + c;
+        float fp = 0.f;
+        for (int k0 = 0; k0 < ke - kb; k0 += 16) {
+            float wv[16], ev[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const bool in = k0 + u < ke - kb;
+                wv[u] = in ? ldcg_f(w + (long long)(k0 + u) * n1) : 0.f;
+                ev[u] = in ? ldcg_f(ed + kb + k0 + u) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 16; ++u)
+                if (k0 + u < ke - kb) fp = fmaf(ev[u], wv[u], fp);
+        }
+        a.fold_part[q * n1 + c] = fp;
+    }
+}
+
 // ---- the kernel ---------------------------------------------------------------------------------------------------
-template <int NL>
 __global__ void __launch_bounds__(kThreads, 1)
 pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    __shared__ uint64_t bar_full[kStages], bar_empty[kStages], bar_done, bar_tfree;
+    __shared__ uint64_t bar_full[kStages], bar_empty[kStages], bar_done, bar_tfree, bar_x, bar_acc[2], bar_epi[2];
     __shared__ uint32_t tmem_base_s;
     __shared__ float s_thr[kMaxThr];
-    __shared__ float s_beff[64];
-    __shared__ float s_wd[64];
-    __shared__ float s_z[2][128];
+    __shared__ SegD s_seg[kMaxSegs];
+    __shared__ int s_nfwd, s_nseg;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int G = gridDim.x, cta = blockIdx.x;
@@ -312,6 +392,7 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
     const bool x3 = passes == 3;    // 3xTF32: pair operands, N-concatenated MMAs
     const bool rnd = passes == 1;   // 1-pass TF32: GEMM operands are stored pre-rounded (RN) to tf32
     unsigned char* scratch = smem + (size_t)kStages * STAGE_BYTES;
+    const int L = a.L;
 
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -320,15 +401,53 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
         }
         tc::mbar_init(&bar_done, 1);
         tc::mbar_init(&bar_tfree, kWorkers);
+        tc::mbar_init(&bar_x, 1);
+        for (int s = 0; s < 2; ++s) {
+            tc::mbar_init(&bar_acc[s], 1);
+            tc::mbar_init(&bar_epi[s], kWorkers);
+        }
         tc::fence_barrier_init();
+        // the GEMMs of the chain, in issue order
+        int ns = 0, last = -1;
+        for (int l = 0; l < L; ++l) {
+            const int tiles = cdiv(a.n[l + 1], 128);
+            for (int t = 0; t < tiles; ++t) {
+                SegD sd;
+                sd.kind = l == L - 1 ? S_HEAD : S_FWD; sd.layer = l; sd.mtile = t; sd.nch = a.n[l] / KCH;
+                sd.ngrp = (a.n[l + 1] - t * 128) / 32 < 4 ? (a.n[l + 1] - t * 128) / 32 : 4;
+                sd.dep = last; sd.bsrc = l & 1; sd.bdst = (l + 1) & 1; sd.mseg = ns;
+                s_seg[ns++] = sd;
+            }
+            last = ns - 1;
+        }
+        s_nfwd = ns;
+        int bsel = L & 1;   // the head writes dZ_{L-1} here
+        for (int l = L - 1; l >= 1; --l) {
+            const int tiles = cdiv(a.n[l], 128);
+            // forward segments of layer l-1 (their features are this layer's inputs), in tile order
+            int fseg = 0;
+            for (int q = 0; q < s_nfwd; ++q)
+                if (s_seg[q].layer == l - 1) { fseg = q; break; }
+            const int prev_last = last;
+            for (int t = 0; t < tiles; ++t) {
+                SegD sd;
+                sd.kind = S_DH; sd.layer = l; sd.mtile = t; sd.nch = a.n[l + 1] / KCH;
+                sd.ngrp = (a.n[l] - t * 128) / 32 < 4 ? (a.n[l] - t * 128) / 32 : 4;
+                sd.dep = prev_last; sd.bsrc = bsel; sd.bdst = bsel ^ 1; sd.mseg = fseg + t;
+                s_seg[ns++] = sd;
+            }
+            last = ns - 1;
+            bsel ^= 1;
+        }
+        s_nseg = ns;
     }
     if (warp == kMmaWarp) tc::tmem_alloc(&tmem_base_s, kTmemCols);
     if (warp == kProdWarp && lane == 0) {
         for (int b = 0; b < 2; ++b) { tc::tma_prefetch_desc(&maps.xk[b]); tc::tma_prefetch_desc(&maps.xmn[b]); }
-        for (int l = 0; l < a.L; ++l) {
+        for (int l = 0; l < L; ++l) {
             tc::tma_prefetch_desc(&maps.wf[l]);
             tc::tma_prefetch_desc(&maps.dzmn[l]);
-            if (l >= 1) { tc::tma_prefetch_desc(&maps.hk[l]); tc::tma_prefetch_desc(&maps.hmn[l]); tc::tma_prefetch_desc(&maps.dzk[l]); tc::tma_prefetch_desc(&maps.wb[l]); }
+            if (l >= 1) { tc::tma_prefetch_desc(&maps.hmn[l]); tc::tma_prefetch_desc(&maps.wb[l]); }
         }
     }
     for (int i = tid; i < a.T && i < kMaxThr; i += kThreads) s_thr[i] = a.thr ? a.thr[i] : 0.f;
@@ -342,12 +461,16 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
     long long step_ctr = a.state->step;
     float b1pow = a.state->b1pow, b2pow = a.state->b2pow;
     unsigned int bar_target = 0;
+    unsigned int tile_target = 0;   // split-K partials every dW tile has received so far in this launch
     int ring_s = 0;            // pipeline stage cursor of this warp's role (producer / MMA issuer)
     uint32_t ring_ph = 0;      // phase bit of the current lap
     uint32_t ring_n = 0;       // chunks handled so far (the first kStages need no empty-wait)
-    uint32_t njob = 0;         // GEMM jobs run so far by this CTA (parity of bar_done / bar_tfree)
+    uint32_t njob = 0;         // dW jobs run so far by this CTA (parity of bar_done / bar_tfree)
+    uint32_t cseg = 0;         // chain segments run so far by this CTA (slot / parity of bar_acc / bar_epi)
+    uint32_t waited = 0;       // MMA warp: segment epilogues consumed so far
+    uint32_t xjobs = 0;        // chain jobs run so far by this CTA (parity of bar_x)
     const int K0 = a.n[0];
-    const int L = a.L;
+    const int NL = a.n[L];
     const float inv_keep = a.dropout_enabled && a.train ? a.dropout_scale : 1.0f;
     const int nz = x3 ? 2 : 1;
 
@@ -357,7 +480,11 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
             if (a.seg[q].kind != SEG_KERNEL) continue;
             const long long o0 = a.seg[q].off;
             for (int i = (cta * kThreads + tid) * 4; i < a.seg[q].numel; i += G * kThreads * 4)
-                store_pair4(a.wpair + o0 + i, a.wz, ldcg_f4(a.params + o0 + i), rnd, x3);
+            {
+                const float4 w4 = ldcg_f4(a.params + o0 + i);
+#pragma unroll
+                for (int r = 0; r < kRep; ++r) store_pair4(a.wpair + r * a.wrep + o0 + i, a.wz, w4, rnd, x3);
+            }
         }
     };
 
@@ -386,6 +513,7 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
     // meta sweep or by the host since the last pass); |E_d|^2 for the inference loss
     refresh_wpair();
     if (warp < kWorkerWarps) {
+        if (cta < kDomJobs) fold_from_params(a, pd.dom, cta, tid);
         gather_rows(a, pd, 0, 0, cta * kWorkerWarps + warp, G * kWorkerWarps, lane, rnd, x3);
         if (!a.train && cta == G - 1) {
             double sq = 0.0;
@@ -404,11 +532,15 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
     }
     grid_barrier(a.bar, bar_target);
 
-    const int n_phases = a.train ? 2 * L + 1 : L;
+    const int n_phases = a.train ? 2 : 1;
+    // the dW job of this CTA for a full mini-batch, decoded once (integer divisions off the per-step path)
+    const int njobs_full = dw_phase_jobs(a, a.bs);
+    const Job job_full = decode_dw_job(a, a.bs, cta);
     for (int step = 0; step < pd.steps; ++step) {
         const long long left = pd.n_data - (long long)step * a.bs;
         const int rows = left < a.bs ? (int)left : a.bs;
-        const int mt = cdiv(rows, 128);
+        // row groups of the chain: whole 32-row K chunks of the dW GEMMs when training (rows past the batch give zero dZ)
+        const int ngroups = a.train ? cdiv(rows, KCH) * (KCH / CR) : cdiv(rows, CR);
         const int buf = step & 1;
         DropoutParams dp;
         dp.enabled = a.dropout_enabled && a.train;
@@ -417,132 +549,455 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
         dp.step = (uint32_t)(step_ctr & 0xffffffffll);
         dp.seed = a.dropout_seed;
 
-        const int jobs_last_bwd = a.train ? phase_jobs(a, 2 * L - 1, rows) : 0;
-        const bool early_done = a.train && G - jobs_last_bwd >= G / 4;   // enough idle CTAs in the last backward phase
-        // fixed-order reduction of the split-K / per-tile partials fused with the optimizer apply, for the float4 items
-        // first, first + stride, ...;  which: 0 = all, 1 = early items only, 2 = late items only
-        auto update_items = [&](long long first, long long stride, int which) {
-            int chunks, S, cps;
-            split_plan(rows, chunks, S, cps);
-            const float alpha = __fdiv_rn(__fmul_rn(a.lr, __fsqrt_rn(__fsub_rn(1.0f, b2pow))), __fsub_rn(1.0f, b1pow));
-            const float omb1 = __fsub_rn(1.0f, a.beta1), omb2 = __fsub_rn(1.0f, a.beta2);
-            const float two_l2 = 2.0f * a.l2_emb;
-            const long long nv4 = a.arena >> 2;
-            for (long long i4 = first; i4 < nv4; i4 += stride) {
-                const long long o = i4 << 2;
-                int si = -1;
-                for (int q = 0; q < a.nseg; ++q)
-                    if (o >= a.seg[q].off && o < a.seg[q].off + a.seg[q].numel) si = q;
-                if (si < 0) continue;   // alignment padding stays zero
-                const Seg sg = a.seg[si];
-                // early items: everything whose gradient is final before the last backward phase (layers >= 1, dense, global bias)
-                const bool late = sg.kind == SEG_ED || ((sg.kind == SEG_KERNEL || sg.kind == SEG_BIAS) && sg.layer == 0);
-                if ((which == 1 && late) || (which == 2 && !late)) continue;
-                const int e = (int)(o - sg.off);
-                const float4 P = ldcg_f4(a.params + o);
-                float4 M = make_float4(0.f, 0.f, 0.f, 0.f), V = M;
-                if (a.opt_kind == 0) { M = ldcg_f4(a.m + o); V = ldcg_f4(a.v + o); }
-                float g[4] = {0.f, 0.f, 0.f, 0.f};
-                if (sg.kind == SEG_KERNEL) {
-                    const int l = sg.layer, N = a.n[l + 1];
-                    const int k = e / N, c = e - k * N;
-                    if (l == 0 && k >= K0) {   // domain block: rank-1  E_d[dom]^T (x) db_0
-                        const float ev = ldcg_f(a.ed_row + (k - K0));
-                        const float4 d4 = ldcg_f4(a.db0_red + c);
-                        g[0] = __fmul_rn(ev, d4.x); g[1] = __fmul_rn(ev, d4.y); g[2] = __fmul_rn(ev, d4.z); g[3] = __fmul_rn(ev, d4.w);
-                    } else {
-                        const int bn = dw_bn(a, l), NT = N / bn, tiles = cdiv(a.n[l], 128) * NT;
-                        const int tile = (k >> 7) * NT + c / bn;
-                        const float* src = a.partials[l] + ((long long)tile * 128 + (k & 127)) * bn + (c % bn);
-                        const long long zstride = (long long)tiles * 128 * bn;
-                        float4 q4[kMaxSplit];
+        const float alpha = __fdiv_rn(__fmul_rn(a.lr, __fsqrt_rn(__fsub_rn(1.0f, b2pow))), __fsub_rn(1.0f, b1pow));
+        const float omb1 = __fsub_rn(1.0f, a.beta1), omb2 = __fsub_rn(1.0f, a.beta2);
+        // optimizer apply on 4 consecutive parameters at arena offset o with gradient g (TF ApplyAdam order / plain SGD)
+        auto apply4 = [&](long long o, const float (&g)[4], bool kernel) {
+            const float4 P = ldcg_f4(a.params + o);
+            float pp[4] = {P.x, P.y, P.z, P.w};
+            if (a.opt_kind == 0) {
+                const float4 M = ldcg_f4(a.m + o), V = ldcg_f4(a.v + o);
+                float mm[4] = {M.x, M.y, M.z, M.w}, vv[4] = {V.x, V.y, V.z, V.w};
 #pragma unroll
-                        for (int z = 0; z < kMaxSplit; ++z) q4[z] = z < S ? ldcg_f4(src + z * zstride) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int t = 0; t < 4; ++t) adam1(pp[t], mm[t], vv[t], g[t], alpha, omb1, omb2, a.eps);
+                *reinterpret_cast<float4*>(a.m + o) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+                *reinterpret_cast<float4*>(a.v + o) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+            } else {
 #pragma unroll
-                        for (int z = 0; z < kMaxSplit; ++z)
-                            if (z < S) { g[0] += q4[z].x; g[1] += q4[z].y; g[2] += q4[z].z; g[3] += q4[z].w; }
-                    }
-                } else if (sg.kind == SEG_BIAS) {
-                    const int N = a.n[sg.layer + 1];
-                    const float* src = sg.layer == 0 ? nullptr : a.db_part[sg.layer] + e;
-                    if (sg.layer == 0) {
-                        const float4 q4 = ldcg_f4(a.db0_red + e);
-                        g[0] = q4.x; g[1] = q4.y; g[2] = q4.z; g[3] = q4.w;
-                    } else {
-                        for (int m0 = 0; m0 < mt; m0 += 8) {
-                            float4 q4[8];
-#pragma unroll
-                            for (int u = 0; u < 8; ++u) q4[u] = m0 + u < mt ? ldcg_f4(src + (long long)(m0 + u) * N) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                            for (int u = 0; u < 8; ++u)
-                                if (m0 + u < mt) { g[0] += q4[u].x; g[1] += q4[u].y; g[2] += q4[u].z; g[3] += q4[u].w; }
-                        }
-                    }
-                } else if (sg.kind == SEG_DENSE) {
-                    for (int m0 = 0; m0 < mt; m0 += 8) {
-                        float4 q4[8];
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) q4[u] = m0 + u < mt ? ldcg_f4(a.dw_part + (m0 + u) * NL + e) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                        for (int u = 0; u < 8; ++u)
-                            if (m0 + u < mt) { g[0] += q4[u].x; g[1] += q4[u].y; g[2] += q4[u].z; g[3] += q4[u].w; }
-                    }
-                } else if (sg.kind == SEG_GBIAS) {
-                    for (int m = 0; m < mt; ++m) g[0] += ldcg_f(a.dg_part + m);
-                } else {   // SEG_ED: L2 term on every row (+ the batch row's data gradient)
-                    const float4 p4 = P;
-                    g[0] = __fmul_rn(two_l2, p4.x); g[1] = __fmul_rn(two_l2, p4.y); g[2] = __fmul_rn(two_l2, p4.z); g[3] = __fmul_rn(two_l2, p4.w);
-                    if (e / a.dd == pd.dom) {
-                        const float4 d4 = ldcg_f4(a.gEd_row + (e - pd.dom * a.dd));
-                        g[0] = __fadd_rn(g[0], d4.x); g[1] = __fadd_rn(g[1], d4.y); g[2] = __fadd_rn(g[2], d4.z); g[3] = __fadd_rn(g[3], d4.w);
-                    }
-                }
-                float pp[4] = {P.x, P.y, P.z, P.w};
-                if (a.opt_kind == 0) {
-                    float mm[4] = {M.x, M.y, M.z, M.w}, vv[4] = {V.x, V.y, V.z, V.w};
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) adam1(pp[t], mm[t], vv[t], g[t], alpha, omb1, omb2, a.eps);
-                    *reinterpret_cast<float4*>(a.m + o) = make_float4(mm[0], mm[1], mm[2], mm[3]);
-                    *reinterpret_cast<float4*>(a.v + o) = make_float4(vv[0], vv[1], vv[2], vv[3]);
-                } else {
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) pp[t] = __fsub_rn(pp[t], __fmul_rn(g[t], a.lr));
-                }
-                const float4 pnew = make_float4(pp[0], pp[1], pp[2], pp[3]);
-                *reinterpret_cast<float4*>(a.params + o) = pnew;
-                if (sg.kind == SEG_KERNEL) store_pair4(a.wpair + o, a.wz, pnew, rnd, x3);
-                if (a.grads) *reinterpret_cast<float4*>(a.grads + o) = make_float4(g[0], g[1], g[2], g[3]);
+                for (int t = 0; t < 4; ++t) pp[t] = __fsub_rn(pp[t], __fmul_rn(g[t], a.lr));
             }
+            const float4 pnew = make_float4(pp[0], pp[1], pp[2], pp[3]);
+            *reinterpret_cast<float4*>(a.params + o) = pnew;
+            if (kernel) {
+#pragma unroll
+                for (int r = 0; r < kRep; ++r) store_pair4(a.wpair + r * a.wrep + o, a.wz, pnew, rnd, x3);
+            }
+            if (a.grads) *reinterpret_cast<float4*>(a.grads + o) = make_float4(g[0], g[1], g[2], g[3]);
         };
+        auto apply1 = [&](long long o, float g) {
+            float pe = ldcg_f(a.params + o);
+            if (a.opt_kind == 0) {
+                float me = ldcg_f(a.m + o), ve = ldcg_f(a.v + o);
+                adam1(pe, me, ve, g, alpha, omb1, omb2, a.eps);
+                a.m[o] = me; a.v[o] = ve;
+            } else {
+                pe = __fsub_rn(pe, __fmul_rn(g, a.lr));
+            }
+            a.params[o] = pe;
+            if (a.grads) a.grads[o] = g;
+            return pe;
+        };
+
         for (int phase = 0; phase < n_phases; ++phase) {
             const long long tslot = (((long long)step * n_phases + phase) * G + cta) * 16;
             const bool tim = a.timing && tslot + 15 < a.timing_cap;
             if (tim && tid == 0) { a.timing[tslot] = gtime(); a.timing[tslot + 7] = (unsigned long long)clock64(); }
-            if (phase < 2 * L) {
-                const int njobs = phase_jobs(a, phase, rows);
+            if (phase == 0) {
+                // =========================================================================================== chain
+                const int nsegs = a.train ? s_nseg : s_nfwd;
+                for (int j = cta; j < ngroups; j += G) {
+                    const int row0 = j * CR;
+                    if (warp == kProdWarp) {
+                        // ---------- TMA producer: the group's X rows, then every weight tile of the chain in issue order
+                        if (tc::elect_one()) {
+                            const int nch0 = K0 / KCH;
+                            tc::mbar_arrive_expect_tx(&bar_x, (uint32_t)(nch0 * CR * KCH * 4 * nz));
+                            for (int c = 0; c < nch0; ++c)
+                                for (int z = 0; z < nz; ++z)
+                                    tc::tma_load_3d(smem + kRingBytes + c * kBChunk + z * (CR * KCH * 4), &maps.xk[buf], &bar_x, c * KCH, row0, z);
+                        }
+                        __syncwarp();
+                        const int rep = (j >> 3) % kRep;   // with the chunk rotation by j: 32 distinct (copy, offset) streams
+                        for (int s = 0; s < nsegs; ++s) {
+                            const SegD sd = s_seg[s];
+                            const int l = sd.layer;
+                            const bool fwd = sd.kind != S_DH;
+                            const int brow = a.n[l] < 128 ? a.n[l] : 128;   // dH: box rows of the wb map
+                            const uint32_t tx = (uint32_t)(fwd ? sd.ngrp * 4096 : brow * KCH * 4) * (uint32_t)nz;
+                            for (int i0 = 0; i0 < sd.nch; ++i0) {
+                                const int i = (i0 + j) % sd.nch;   // chunk order rotated per row group (see the MMA warp)
+                                if (ring_n >= (uint32_t)kStages) tc::mbar_wait(&bar_empty[ring_s], ring_ph ^ 1);
+                                unsigned char* sA = smem + (size_t)ring_s * kChainStage;
+                                uint64_t* fb = &bar_full[ring_s];
+                                if (tc::elect_one()) {
+                                    tc::mbar_arrive_expect_tx(fb, tx);
+                                    for (int z = 0; z < nz; ++z) {
+                                        if (fwd) {
+                                            for (int g = 0; g < sd.ngrp; ++g) tc::tma_load_4d(sA + z * A_BYTES + g * 4096, &maps.wf[l], fb, sd.mtile * 128 + g * 32, i * KCH, z, rep);
+                                        } else {
+                                            tc::tma_load_4d(sA + z * A_BYTES, &maps.wb[l], fb, i * KCH, sd.mtile * 128, z, rep);
+                                        }
+                                    }
+#ifdef PASS_DBG_SEG
+                                    if (tim && s == PASS_DBG_SEG) {
+                                        if (i0 == 0) a.timing[tslot + 2] = (unsigned long long)clock64();
+                                        if (i0 == 2) a.timing[tslot + 3] = (unsigned long long)clock64();
+                                        if (i0 == 4) a.timing[tslot + 4] = (unsigned long long)clock64();
+                                        if (i0 == 6) a.timing[tslot + 5] = (unsigned long long)clock64();
+                                        if (i0 == 7) a.timing[tslot + 6] = (unsigned long long)clock64();
+                                    }
+#else
+                                    if (tim) {
+                                        if (s == 0 && i0 == 0) a.timing[tslot + 2] = (unsigned long long)clock64();
+                                        if (s == nsegs - 1 && i0 == sd.nch - 1) a.timing[tslot + 3] = (unsigned long long)clock64();
+                                    }
+#endif
+                                }
+                                __syncwarp();
+                                ++ring_n;
+                                if (++ring_s == kStages) { ring_s = 0; ring_ph ^= 1; }
+                            }
+                        }
+                    } else if (warp == kMmaWarp) {
+                        // ---------- MMA issuer: out^T[feature, row] (+)= W^T . act^T, accumulators alternate between two TMEM slots
+                        for (int s = 0; s < nsegs; ++s) {
+                            const SegD sd = s_seg[s];
+                            const uint32_t cs = cseg + (uint32_t)s;
+                            // the slot must be drained (epilogue of segment cs - 2) and the N operand written (epilogue of `dep`)
+                            uint32_t need = cs >= 1 ? cs - 1 : 0;
+                            if (sd.dep >= 0 && cseg + (uint32_t)sd.dep + 1 > need) need = cseg + (uint32_t)sd.dep + 1;
+                            while (waited < need) { tc::mbar_wait(&bar_epi[waited & 1], (waited >> 1) & 1); ++waited; }
+                            if (s == 0) tc::mbar_wait(&bar_x, xjobs & 1);
+                            tc::tc_fence_after();
+                            const bool fwd = sd.kind != S_DH;
+                            const uint32_t idN2 = tc::make_idesc_tf32(128, 2 * CR, fwd ? 1 : 0, 0);
+                            const uint32_t idN1 = tc::make_idesc_tf32(128, CR, fwd ? 1 : 0, 0);
+                            const uint32_t a_hiw = fwd ? tc::kDescHiMN : tc::kDescHiK, a_low = fwd ? tc::kDescLoMN : tc::kDescLoK;
+                            const uint32_t a_k = fwd ? (1024u >> 4) : (32u >> 4);   // per k-step of 8
+                            const uint32_t bbase = ((smem_base + (uint32_t)kRingBytes + (uint32_t)sd.bsrc * kActBytes) >> 4) | tc::kDescLoK;
+                            const uint32_t dcol = tmem + (cs & 1u) * 32u;
+                            uint32_t acc = 0;
+                            for (int i0 = 0; i0 < sd.nch; ++i0) {
+                                // every CTA streams the same weights: starting the K loop at chunk j mod nch keeps the CTAs from
+                                // hammering the same L2 lines in lock-step (the K order of a row group is fixed: deterministic)
+                                const int i = (i0 + j) % sd.nch;
+                                tc::mbar_wait(&bar_full[ring_s], ring_ph);
+                                tc::tc_fence_after();
+                                const uint32_t st = (smem_base + (uint32_t)ring_s * kChainStage) >> 4;
+                                if (tc::elect_one()) {
+#ifdef PASS_DBG_SEG
+                                    if (tim && s == PASS_DBG_SEG && i0 < 8) a.timing[tslot + 8 + i0] = (unsigned long long)clock64();
+#else
+                                    if (tim && s == 0 && i0 == 0) a.timing[tslot + 4] = (unsigned long long)clock64();
+#endif
+                                    const uint32_t aw = st | a_low, alw = aw + (A_BYTES >> 4);
+                                    const uint32_t bw = bbase + (uint32_t)i * (kBChunk >> 4);
+                                    if (x3) {
+#pragma unroll
+                                        for (int k = 0; k < KCH / 8; ++k) {
+                                            // W.[act | act_lo] -> columns [0, CR) and [CR, 2 CR);  W_lo.act -> columns [0, CR)
+                                            tc::mma_tf32(dcol, tc::desc_words(aw + k * a_k, a_hiw), tc::desc_words(bw + k * 2u, tc::kDescHiK), idN2, acc);
+                                            tc::mma_tf32(dcol, tc::desc_words(alw + k * a_k, a_hiw), tc::desc_words(bw + k * 2u, tc::kDescHiK), idN1, 1u);
+                                            acc = 1;
+                                        }
+                                    } else {
+#pragma unroll
+                                        for (int k = 0; k < KCH / 8; ++k) {
+                                            tc::mma_tf32(dcol, tc::desc_words(aw + k * a_k, a_hiw), tc::desc_words(bw + k * 2u, tc::kDescHiK), idN1, acc);
+                                            acc = 1;
+                                        }
+                                    }
+                                    tc::mma_commit(&bar_empty[ring_s]);
+                                }
+                                __syncwarp();
+                                if (++ring_s == kStages) { ring_s = 0; ring_ph ^= 1; }
+                            }
+                            if (tc::elect_one()) {
+                                tc::mma_commit(&bar_acc[cs & 1]);
+#ifndef PASS_DBG_SEG
+                                if (tim && s == nsegs - 1) a.timing[tslot + 5] = (unsigned long long)clock64();
+#endif
+                            }
+                            __syncwarp();
+                        }
+                        // every epilogue of the job has run: the accumulators and the activation buffers are free again
+                        while (waited < cseg + (uint32_t)nsegs) { tc::mbar_wait(&bar_epi[waited & 1], (waited >> 1) & 1); ++waited; }
+                    } else {
+                        // ---------- workers: thread <-> one output feature (TMEM lane) x 8 rows
+                        const int q = warp & 3, hf = warp >> 2;
+                        const int wt = q * 32 + lane;                    // feature inside the M tile
+                        const int r_first = row0 + hf * 8;               // batch row of this thread's value 0
+                        unsigned char* s_mask = scratch + kScrMask;
+                        float* s_zp = reinterpret_cast<float*>(scratch + kScrZp);
+                        float* s_ds = reinterpret_cast<float*>(scratch + kScrDs);
+                        float* s_comb = reinterpret_cast<float*>(scratch + kScrComb);
+                        const float dscale = dp.enabled ? dp.scale : 1.0f;
+                        for (int s = 0; s < nsegs; ++s) {
+                            const SegD sd = s_seg[s];
+                            const uint32_t cs = cseg + (uint32_t)s;
+                            const int l = sd.layer;
+                            const int f = sd.mtile * 128 + wt;            // output feature of this thread
+                            const bool on = q < sd.ngrp;                  // warp-uniform: the tile has this lane quarter
+                            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (cs & 1u) * 32u + (uint32_t)(hf * 8);
+                            // this thread's 8 values of the N operand chunk f / 32: row line hf * 8 + i, swizzled 16-byte chunk
+                            unsigned char* bdst = smem + kRingBytes + sd.bdst * kActBytes + (f >> 5) * kBChunk + (hf * 8) * 128 + (lane & 3) * 4;
+                            float bias = 0.f, wd = 0.f;
+                            uint32_t keep = 0xffu;
+                            if (sd.kind != S_DH) {
+                                // ---- prelude in the shadow of the MMAs: effective bias, dropout keep bits
+                                if (l == 0) {
+                                    // layer 0 adds E_d[dom] . W_0[K0:, f] in fp32: the k-slice partials published by the domain jobs
+                                    // of the previous update (or by the pass prologue)
+                                    if (on) {
+                                        float q8[kDomJobs];
+#pragma unroll
+                                        for (int u = 0; u < kDomJobs; ++u) q8[u] = ldcg_f(a.fold_part + u * a.n[1] + f);
+                                        float fs = 0.f;
+#pragma unroll
+                                        for (int u = 0; u < kDomJobs; ++u) fs += q8[u];
+                                        bias = ldcg_f(a.params + a.off_b[0] + f) + fs;
+                                    }
+                                } else if (on) {
+                                    bias = ldcg_f(a.params + a.off_b[l] + f);
+                                }
+                                if (sd.kind == S_HEAD && on) wd = ldcg_f(a.params + a.off_w + f);
+                                if (dp.enabled && on) {
+                                    // the 4 lanes of a feature quad share one Philox counter per row: each lane draws two rows' words
+                                    DropoutParams dq = dp;
+                                    dq.seed = a.dropout_seed + (uint32_t)l;
+                                    const uint32_t N = (uint32_t)a.n[l + 1];
+                                    uint32_t nib[2];
+#pragma unroll
+                                    for (int u = 0; u < 2; ++u) {
+                                        const uint32_t row = (uint32_t)(r_first + (lane & 3) + 4 * u);
+                                        const uint4 w = dropout_words4(dq, row * N + (uint32_t)(f & ~3));
+                                        nib[u] = (w.x < dq.threshold ? 1u : 0u) | (w.y < dq.threshold ? 2u : 0u) |
+                                                 (w.z < dq.threshold ? 4u : 0u) | (w.w < dq.threshold ? 8u : 0u);
+                                    }
+                                    keep = 0u;
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) {
+                                        const uint32_t nb = __shfl_sync(0xffffffffu, nib[i >> 2], (lane & ~3) | (i & 3));
+                                        keep |= ((nb >> (lane & 3)) & 1u) << i;
+                                    }
+                                }
+                            }
+                            tc::mbar_wait_warp(&bar_acc[cs & 1], (cs >> 1) & 1);
+                            tc::tc_fence_after();
+                            float vv[8], v2[8];
+                            if (on) {
+                                tc::tmem_ld8(taddr, vv);
+                                if (x3) tc::tmem_ld8(taddr + CR, v2);
+                            }
+                            tc::tc_fence_before();
+
+                            if (sd.kind == S_FWD) {
+                                // H_{l+1}[row, f] = dropout(relu(acc + b)) -> N operand of the next layer (+ global copy for dW)
+                                float h[8];
+                                if (on) {
+                                    uint32_t mb = 0u;
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) {
+                                        const float accv = x3 ? vv[i] + v2[i] : vv[i];
+                                        float hh = fmaxf(accv + bias, 0.f);
+                                        hh = (keep >> i) & 1u ? hh * dscale : 0.f;
+                                        h[i] = hh;
+                                        mb |= (hh > 0.f ? 1u : 0u) << i;
+                                        unsigned char* d = bdst + i * 128 + ((((lane >> 2) ^ i) & 7) << 4);
+                                        *reinterpret_cast<float*>(d) = rnd ? rn_tf32(hh) : hh;
+                                        if (x3) *reinterpret_cast<float*>(d + CR * 128) = tc::tf32_lo(hh);
+                                    }
+                                    s_mask[sd.mseg * 256 + tid] = (unsigned char)mb;
+                                }
+                                tc::fence_proxy_async();
+                                tc::mbar_arrive(&bar_epi[cs & 1]);
+                                if (on && a.train) {
+                                    const int N = a.n[l + 1];
+                                    float* out = a.H[l + 1] + (long long)r_first * N + f;
+                                    const long long oz = (long long)a.max_rows * N;
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i)
+                                        if (r_first + i < rows) store_pair1(out + (long long)i * N, oz, h[i], rnd, x3);
+                                }
+                            } else if (sd.kind == S_HEAD) {
+                                // last hidden layer + Dense(1) + sigmoid + BCE + ds + dZ_{L-1} + column-sum partials + AUC bins
+                                float h[8], zp[8];
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) { h[i] = 0.f; zp[i] = 0.f; }
+                                if (on) {
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) {
+                                        const float accv = x3 ? vv[i] + v2[i] : vv[i];
+                                        float hh = fmaxf(accv + bias, 0.f);
+                                        hh = (keep >> i) & 1u ? hh * dscale : 0.f;
+                                        h[i] = hh;
+                                        zp[i] = hh * wd;
+                                    }
+                                    const float zs = warp_sum8(zp, lane);
+                                    if ((lane & 3) == 0) s_zp[(hf * 4 + q) * 8 + warp_sum8_index(lane)] = zs;
+                                }
+                                worker_sync();
+                                float pv = 0.f, yv = 0.f, dsv0 = 0.f;   // warp 0: row lane of the group
+                                const int hrow = row0 + lane;
+                                const bool hvalid = warp == 0 && lane < CR && hrow < rows;
+                                if (warp == 0) {
+                                    if (hvalid) {
+                                        float z = 0.f;
+                                        for (int qq = 0; qq < sd.ngrp; ++qq) z += s_zp[((lane >> 3) * 4 + qq) * 8 + (lane & 7)];
+                                        const float sgm = z + ldcg_f(a.params + a.off_g);
+                                        pv = 1.0f / (1.0f + expf(-sgm));
+                                        yv = a.y[buf][hrow];
+                                        if (a.train) dsv0 = (fabsf(sgm) <= MAMDR_LOGIT_CLIP) ? __fdiv_rn(__fsub_rn(pv, yv), (float)rows) : 0.f;
+                                    }
+                                    if (lane < CR) s_ds[lane] = dsv0;
+                                }
+                                worker_sync();
+                                float hd = 0.f, dbs = 0.f;
+                                float dz[8];
+                                if (on && a.train) {
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) {
+                                        const float dsv = s_ds[hf * 8 + i];
+                                        const float dh = __fmul_rn(dsv, wd);
+                                        dz[i] = h[i] > 0.f ? __fmul_rn(dh, inv_keep) : 0.f;   // rows past the batch: ds = 0
+                                        hd += h[i] * dsv;
+                                        dbs += dz[i];
+                                        unsigned char* d = bdst + i * 128 + ((((lane >> 2) ^ i) & 7) << 4);
+                                        *reinterpret_cast<float*>(d) = rnd ? rn_tf32(dz[i]) : dz[i];
+                                        if (x3) *reinterpret_cast<float*>(d + CR * 128) = tc::tf32_lo(dz[i]);
+                                    }
+                                }
+                                tc::fence_proxy_async();
+                                tc::mbar_arrive(&bar_epi[cs & 1]);
+                                if (warp == 0) {
+                                    // off the critical path: Keras BCE of the clipped probability, probabilities, AUC bins
+                                    const float lo_c = 1e-7f, hi_c = 1.0f - 1e-7f;
+                                    double bce = 0.0;
+                                    if (hvalid) {
+                                        const float ph = fminf(fmaxf(pv, lo_c), hi_c);
+                                        const float lg = logf(ph / (1.0f - ph));
+                                        bce = (double)(fmaxf(lg, 0.f) - lg * yv + log1pf(expf(-fabsf(lg))));
+                                        if (pd.probs) pd.probs[(long long)step * a.bs + hrow] = pv;
+                                        if (a.auc_acc) {
+                                            int lo_i = 0, hi_i = a.T;
+                                            while (lo_i < hi_i) {
+                                                const int mid = (lo_i + hi_i) >> 1;
+                                                if (s_thr[mid] < pv) lo_i = mid + 1; else hi_i = mid;
+                                            }
+                                            atomicAdd(&hist_cur[(yv != 0.f ? (a.T + 1) : 0) + lo_i], 1);
+                                        }
+                                    }
+                                    double bs = bce;
+                                    float dgs = dsv0;
+#pragma unroll
+                                    for (int o = 16; o > 0; o >>= 1) {
+                                        bs += __shfl_xor_sync(0xffffffffu, bs, o);
+                                        dgs += __shfl_xor_sync(0xffffffffu, dgs, o);
+                                    }
+                                    if (lane == 0) { a.loss_part[buf * kMaxGroups + j] = bs; a.dg_part[j] = dgs; }
+                                }
+                                if (a.train) {
+                                    if (on) {
+                                        float* out = a.dZ[L - 1] + (long long)r_first * NL + f;
+                                        const long long oz = (long long)a.max_rows * NL;
+#pragma unroll
+                                        for (int i = 0; i < 8; ++i) store_pair1(out + (long long)i * NL, oz, dz[i], rnd, x3);
+                                    }
+                                    // the two row halves in order -> per-group column sums (Dense(1) kernel gradient, db_{L-1})
+                                    float* comb = s_comb + (cs & 1u) * 256;
+                                    if (on && hf == 1) { comb[wt] = hd; comb[128 + wt] = dbs; }
+                                    worker_sync();
+                                    if (on && hf == 0) {
+                                        a.dw_part[(long long)j * NL + f] = hd + comb[wt];
+                                        a.db_part[L - 1][(long long)j * NL + f] = dbs + comb[128 + wt];
+                                    }
+                                }
+                            } else {
+                                // dZ_{l-1}[row, f] = acc * inv_keep * 1[H_l > 0]; per-group column sums -> db_{l-1}
+                                float dz[8];
+                                float dbs = 0.f;
+                                const bool feed = l >= 2;   // dZ_{l-1} is the N operand of dH_{l-1}
+                                if (on) {
+                                    const uint32_t mb = s_mask[sd.mseg * 256 + tid];
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) {
+                                        const float accv = x3 ? vv[i] + v2[i] : vv[i];
+                                        dz[i] = (r_first + i < rows && ((mb >> i) & 1u)) ? accv * inv_keep : 0.f;
+                                        dbs += dz[i];
+                                        if (feed) {
+                                            unsigned char* d = bdst + i * 128 + ((((lane >> 2) ^ i) & 7) << 4);
+                                            *reinterpret_cast<float*>(d) = rnd ? rn_tf32(dz[i]) : dz[i];
+                                            if (x3) *reinterpret_cast<float*>(d + CR * 128) = tc::tf32_lo(dz[i]);
+                                        }
+                                    }
+                                }
+                                tc::fence_proxy_async();
+                                tc::mbar_arrive(&bar_epi[cs & 1]);
+                                const int N = a.n[l];
+                                if (on) {
+                                    float* out = a.dZ[l - 1] + (long long)r_first * N + f;
+                                    const long long oz = (long long)a.max_rows * N;
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) store_pair1(out + (long long)i * N, oz, dz[i], rnd, x3);
+                                }
+                                float* comb = s_comb + (cs & 1u) * 256;
+                                if (on && hf == 1) comb[wt] = dbs;
+                                worker_sync();
+                                if (on && hf == 0) a.db_part[l - 1][(long long)j * N + f] = dbs + comb[wt];
+                            }
+#ifndef PASS_DBG_SEG
+                            if (tim && tid == 0 && s < 8) a.timing[tslot + 8 + s] = (unsigned long long)clock64();
+#endif
+                        }
+                    }
+                    cseg += (uint32_t)nsegs;
+                    ++xjobs;
+                    __syncthreads();   // the next job's X load overwrites activation buffer 0
+                }
+                // CTAs without a row group stage the next mini-batch meanwhile
+                if (step + 1 < pd.steps && warp < kWorkerWarps) {
+                    const int first = G - ngroups >= G / 4 ? ngroups : 0;
+                    if (cta >= first) gather_rows(a, pd, step + 1, buf ^ 1, (cta - first) * kWorkerWarps + warp, (G - first) * kWorkerWarps, lane, rnd, x3);
+                }
+            } else if (phase == 1) {
+                // =========================================================================================== dW
+                const int njobs = rows == a.bs ? njobs_full : dw_phase_jobs(a, rows);
                 for (int j = cta; j < njobs; j += G) {
-                    const Job J = decode_job(a, phase, rows, j);
+                    const Job J = (rows == a.bs && j == cta) ? job_full : decode_dw_job(a, rows, j);
                     const int l = J.layer;
                     if (J.type == J_DOM) {
-                        // ---------- domain-embedding job q of kDomJobs (workers): db_0 (every job, into smem), rows
-                        // [q*per, (q+1)*per) of dE_d[dom] = W_0dom . db_0; job 0 also publishes db_0, E_d[dom], |E_d|^2
+                        // ---------- domain job q of kDomJobs (workers): db_0 (every job, into smem); for the k rows of this job:
+                        // dE_d[dom][k] = W_0dom[k, :] . db_0, the optimizer apply on E_d[dom][k] and on the rank-1 gradient
+                        // E_d[dom][k] (x) db_0 of W_0dom[k, :], and the fold partial of the UPDATED values for the next chain.
+                        // Job 0 also publishes db_0 and |E_d|^2 (pre-update, for the loss).
                         if (warp < kWorkerWarps) {
                             const int n1 = a.n[1];
-                            float* s_db0 = reinterpret_cast<float*>(scratch);           // [n1] (n1 <= 4096: 16 KB)
+                            float* s_db0 = reinterpret_cast<float*>(scratch);           // [n1 <= 256]
+                            float4* s_sl = reinterpret_cast<float4*>(scratch + 1024);   // [slices][n1 / 4]
+                            float* s_g = reinterpret_cast<float*>(scratch + 5120);      // [32] dE_d[dom][k]
+                            float* s_eo = s_g + 32;                                     // [32] E_d[dom][k] before the apply
+                            float* s_en = s_g + 64;                                     // [32] ... after
                             double* red = reinterpret_cast<double*>(scratch + 16384);
-                            for (int c = tid * 4; c < n1; c += kWorkers * 4) {
+                            const int ncol4 = n1 >> 2, nsl = kWorkers / ncol4;
+                            int kb, ke;
+                            dom_rows(a, J.m_tile, kb, ke);
+                            {
+                                // column sums of the per-group partials: slice sl sums its groups in order, then the slices in order
+                                const int c4 = tid % ncol4, sl = tid / ncol4;
+                                const int per = cdiv(ngroups, nsl);
+                                const int g_end = (sl + 1) * per < ngroups ? (sl + 1) * per : ngroups;
                                 float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                                float4 part[8];
-                                for (int m0 = 0; m0 < mt; m0 += 8) {
+                                if (sl < nsl) {
+                                    for (int g0 = sl * per; g0 < g_end; g0 += 16) {
+                                        float4 part[16];
 #pragma unroll
-                                    for (int u = 0; u < 8; ++u)
-                                        part[u] = m0 + u < mt ? ldcg_f4(a.db_part[0] + (long long)(m0 + u) * n1 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                        for (int u = 0; u < 16; ++u)
+                                            part[u] = g0 + u < g_end ? ldcg_f4(a.db_part[0] + (long long)(g0 + u) * n1 + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                                    for (int u = 0; u < 8; ++u)
-                                        if (m0 + u < mt) { acc.x += part[u].x; acc.y += part[u].y; acc.z += part[u].z; acc.w += part[u].w; }
+                                        for (int u = 0; u < 16; ++u) { acc.x += part[u].x; acc.y += part[u].y; acc.z += part[u].z; acc.w += part[u].w; }
+                                    }
+                                    s_sl[sl * ncol4 + c4] = acc;
                                 }
-                                *reinterpret_cast<float4*>(s_db0 + c) = acc;
-                                if (J.m_tile == 0) *reinterpret_cast<float4*>(a.db0_red + c) = acc;
+                                worker_sync();
+                                if (tid < ncol4) {
+                                    float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                                    for (int s2 = 0; s2 < nsl; ++s2) { const float4 p4 = s_sl[s2 * ncol4 + tid]; t4.x += p4.x; t4.y += p4.y; t4.z += p4.z; t4.w += p4.w; }
+                                    *reinterpret_cast<float4*>(s_db0 + tid * 4) = t4;
+                                    if (J.m_tile == 0) {   // b_0
+                                        const float g4[4] = {t4.x, t4.y, t4.z, t4.w};
+                                        apply4(a.off_b[0] + tid * 4, g4, false);
+                                    }
+                                }
                             }
                             if (J.m_tile == 0) {
                                 double sq = 0.0;
@@ -550,7 +1005,6 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
 #pragma unroll
                                 for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
                                 if (lane == 0) red[warp] = sq;
-                                for (int k = tid; k < a.dd; k += kWorkers) a.ed_row[k] = ldcg_f(a.params + a.off_Ed + (long long)pd.dom * a.dd + k);
                             }
                             worker_sync();
                             if (J.m_tile == 0 && tid == 0) {
@@ -558,12 +1012,10 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                                 for (int w = 0; w < kWorkerWarps; ++w) tot += red[w];
                                 *a.ed_sq = tot;
                             }
-                            const float* W0dom = a.params + a.off_W[0] + (long long)K0 * n1;
-                            const int per = cdiv(a.dd, kDomJobs);
-                            const int k_end = (J.m_tile + 1) * per < a.dd ? (J.m_tile + 1) * per : a.dd;
-                            for (int k = J.m_tile * per + warp; k < k_end; k += kWorkerWarps) {
+                            float* W0dom = a.params + a.off_W[0] + (long long)K0 * n1;
+                            for (int k = kb + warp; k < ke; k += kWorkerWarps) {
                                 const float* wr = W0dom + (long long)k * n1;
-                                float s = 0.f;
+                                float sv = 0.f;
                                 for (int c0 = 0; c0 < n1; c0 += 512) {   // 4 x 128 floats per trip, loads first
                                     float4 wv[4];
 #pragma unroll
@@ -576,26 +1028,102 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                                         const int c = c0 + u * 128 + lane * 4;
                                         if (c < n1) {
                                             const float4 d4 = *reinterpret_cast<const float4*>(s_db0 + c);
-                                            s = fmaf(d4.x, wv[u].x, s); s = fmaf(d4.y, wv[u].y, s); s = fmaf(d4.z, wv[u].z, s); s = fmaf(d4.w, wv[u].w, s);
+                                            sv = fmaf(d4.x, wv[u].x, sv); sv = fmaf(d4.y, wv[u].y, sv); sv = fmaf(d4.z, wv[u].z, sv); sv = fmaf(d4.w, wv[u].w, sv);
                                         }
                                     }
                                 }
 #pragma unroll
-                                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                                if (lane == 0) a.gEd_row[k] = s;
+                                for (int o = 16; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
+                                if (lane == 0) s_g[k - kb] = sv;
+                            }
+                            worker_sync();
+                            if (tid < ke - kb) {
+                                // E_d[dom][k]: g = 2 l2 E + dE   (the other rows of E_d take their l2-only gradient in the column-sum job)
+                                const long long o = a.off_Ed + (long long)pd.dom * a.dd + kb + tid;
+                                const float pe = ldcg_f(a.params + o);
+                                s_eo[tid] = pe;
+                                s_en[tid] = apply1(o, __fadd_rn(__fmul_rn(2.0f * a.l2_emb, pe), s_g[tid]));
+                            }
+                            worker_sync();
+                            for (int c = tid; c < n1; c += kWorkers) {
+                                const long long o0 = a.off_W[0] + (long long)(K0 + kb) * n1 + c;
+                                const float dbc = s_db0[c];
+                                float fp = 0.f;
+                                for (int k0 = 0; k0 < ke - kb; k0 += 16) {
+                                    float pw[16], mw[16], vw[16];
+#pragma unroll
+                                    for (int u = 0; u < 16; ++u) {
+                                        const bool in = k0 + u < ke - kb;
+                                        const long long o = o0 + (long long)(k0 + u) * n1;
+                                        pw[u] = in ? ldcg_f(a.params + o) : 0.f;
+                                        mw[u] = in && a.opt_kind == 0 ? ldcg_f(a.m + o) : 0.f;
+                                        vw[u] = in && a.opt_kind == 0 ? ldcg_f(a.v + o) : 0.f;
+                                    }
+#pragma unroll
+                                    for (int u = 0; u < 16; ++u) {
+                                        if (k0 + u < ke - kb) {
+                                            const long long o = o0 + (long long)(k0 + u) * n1;
+                                            const float g = __fmul_rn(s_eo[k0 + u], dbc);   // rank-1: E_d[dom]^T (x) db_0
+                                            if (a.opt_kind == 0) {
+                                                adam1(pw[u], mw[u], vw[u], g, alpha, omb1, omb2, a.eps);
+                                                a.m[o] = mw[u]; a.v[o] = vw[u];
+                                            } else {
+                                                pw[u] = __fsub_rn(pw[u], __fmul_rn(g, a.lr));
+                                            }
+                                            a.params[o] = pw[u];
+                                            if (a.grads) a.grads[o] = g;
+                                            fp = fmaf(s_en[k0 + u], pw[u], fp);
+                                        }
+                                    }
+                                }
+                                a.fold_part[J.m_tile * n1 + c] = fp;
                             }
                             worker_sync();
                         }
                         continue;
                     }
-                    const bool a_mn = J.type == J_DW, b_mn = J.type != J_DH;
+                    if (J.type == J_RED) {
+                        // ---------- column-sum job (workers): totals of the per-group partials of db_1.., the Dense(1) kernel
+                        // gradient, the global-bias gradient (each applied right away) and the mini-batch loss; thread per column
+                        if (warp < kWorkerWarps) {
+                            int total = NL;
+                            for (int l2 = 1; l2 < L; ++l2) total += a.n[l2 + 1];
+                            for (int c = tid; c < total; c += kWorkers) {
+                                // column c of [db_1 | db_2 | .. | d(Dense kernel)]
+                                int cc = c, l2 = 1;
+                                for (; l2 < L && cc >= a.n[l2 + 1]; ++l2) cc -= a.n[l2 + 1];
+                                const int N = l2 < L ? a.n[l2 + 1] : NL;
+                                const float* src = (l2 < L ? a.db_part[l2] : a.dw_part) + cc;
+                                float sum = 0.f;
+                                for (int g0 = 0; g0 < ngroups; g0 += 16) {
+                                    float pv[16];
+#pragma unroll
+                                    for (int u = 0; u < 16; ++u) pv[u] = g0 + u < ngroups ? ldcg_f(src + (long long)(g0 + u) * N) : 0.f;
+#pragma unroll
+                                    for (int u = 0; u < 16; ++u) sum += pv[u];
+                                }
+                                apply1((l2 < L ? a.off_b[l2] : a.off_w) + cc, sum);
+                            }
+                            if (warp == 0) {
+                                const float s = warp_group_sum_f(a.dg_part, ngroups, 1, lane);
+                                if (lane == 0) apply1(a.off_g, s);
+                            }
+                            // the rows of E_d other than the batch's domain: l2 term only
+                            for (int i = tid; i < a.n_domain * a.dd; i += kWorkers)
+                                if (i / a.dd != pd.dom) apply1(a.off_Ed + i, __fmul_rn(2.0f * a.l2_emb, ldcg_f(a.params + a.off_Ed + i)));
+                            if (warp == 1) {
+                                const double bs = warp_group_sum_d(a.loss_part + buf * kMaxGroups, ngroups, lane);
+                                // |E_d|^2 of this mini-batch is published by domain job 0 in this same phase: the loss is
+                                // completed after the barrier (below)
+                                if (lane == 0) a.loss_part[2 * kMaxGroups + buf] = bs;
+                            }
+                        }
+                        continue;
+                    }
+                    // ---------- split-K tile job of dW_l: partial[z][tile] = H_l[rows of z]^T . dZ_l[rows of z]
                     if (warp == kProdWarp) {
-                        // ---------- TMA producer (whole warp converged, one elected lane issues)
-                        const CUtensorMap* ma;
-                        const CUtensorMap* mb;
-                        if (J.type == J_FWD || J.type == J_HEAD) { ma = l == 0 ? &maps.xk[buf] : &maps.hk[l]; mb = &maps.wf[l]; }
-                        else if (J.type == J_DH) { ma = &maps.dzk[l]; mb = &maps.wb[l]; }
-                        else { ma = l == 0 ? &maps.xmn[buf] : &maps.hmn[l]; mb = &maps.dzmn[l]; }
+                        const CUtensorMap* ma = l == 0 ? &maps.xmn[buf] : &maps.hmn[l];
+                        const CUtensorMap* mb = &maps.dzmn[l];
                         const uint32_t b_tile = (uint32_t)J.bn * KCH * 4;
                         const uint32_t tx = (uint32_t)(A_BYTES + b_tile) * (uint32_t)nz;
                         const int a_row = J.m_tile * 128, b_col = J.n_tile * J.bn, ngb = J.bn >> 5;
@@ -608,17 +1136,9 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                             if (tc::elect_one()) {
                                 tc::mbar_arrive_expect_tx(fb, tx);
                                 for (int z = 0; z < nz; ++z) {
-                                    if (a_mn) {
 #pragma unroll
-                                        for (int g = 0; g < 4; ++g) tc::tma_load_3d(sA + z * A_BYTES + g * 4096, ma, fb, a_row + g * 32, kc, z);
-                                    } else {
-                                        tc::tma_load_3d(sA + z * A_BYTES, ma, fb, kc, a_row, z);
-                                    }
-                                    if (b_mn) {
-                                        for (int g = 0; g < ngb; ++g) tc::tma_load_3d(sB + z * b_tile + g * 4096, mb, fb, b_col + g * 32, kc, z);
-                                    } else {
-                                        tc::tma_load_3d(sB + z * b_tile, mb, fb, kc, b_col, z);
-                                    }
+                                    for (int g = 0; g < 4; ++g) tc::tma_load_3d(sA + z * A_BYTES + g * 4096, ma, fb, a_row + g * 32, kc, z);
+                                    for (int g = 0; g < ngb; ++g) tc::tma_load_3d(sB + z * b_tile + g * 4096, mb, fb, b_col + g * 32, kc, z);
                                 }
                                 if (tim) {
                                     if (i == 0) a.timing[tslot + 2] = (unsigned long long)clock64();
@@ -630,14 +1150,11 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                             if (++ring_s == kStages) { ring_s = 0; ring_ph ^= 1; }
                         }
                     } else if (warp == kMmaWarp) {
-                        // ---------- MMA issuer (whole warp converged, one elected lane issues)
                         if (njob > 0) tc::mbar_wait(&bar_tfree, (njob - 1) & 1);
                         tc::tc_fence_after();
-                        const uint32_t idesc1 = tc::make_idesc_tf32(128, J.bn, a_mn ? 1 : 0, b_mn ? 1 : 0);
-                        const uint32_t idesc2 = tc::make_idesc_tf32(128, 2 * J.bn, a_mn ? 1 : 0, b_mn ? 1 : 0);
-                        const uint32_t a_hiw = a_mn ? tc::kDescHiMN : tc::kDescHiK, a_low = a_mn ? tc::kDescLoMN : tc::kDescLoK;
-                        const uint32_t b_hiw = b_mn ? tc::kDescHiMN : tc::kDescHiK, b_low = b_mn ? tc::kDescLoMN : tc::kDescLoK;
-                        const uint32_t a_k = a_mn ? (1024u >> 4) : (32u >> 4), b_k = b_mn ? (1024u >> 4) : (32u >> 4);   // per k-step of 8
+                        const uint32_t idesc1 = tc::make_idesc_tf32(128, J.bn, 1, 1);
+                        const uint32_t idesc2 = tc::make_idesc_tf32(128, 2 * J.bn, 1, 1);
+                        const uint32_t a_k = 1024u >> 4, b_k = 1024u >> 4;   // per k-step of 8
                         uint32_t acc = 0;
                         for (int i = 0; i < J.nch; ++i) {
                             tc::mbar_wait(&bar_full[ring_s], ring_ph);
@@ -645,20 +1162,20 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                             const uint32_t st = (smem_base + (uint32_t)ring_s * STAGE_BYTES) >> 4;
                             if (tc::elect_one()) {
                                 if (tim && i == 0) a.timing[tslot + 4] = (unsigned long long)clock64();
-                                const uint32_t aw = st | a_low, alw = aw + (A_BYTES >> 4);
-                                const uint32_t bw = (st + ((2 * A_BYTES) >> 4)) | b_low;
+                                const uint32_t aw = st | tc::kDescLoMN, alw = aw + (A_BYTES >> 4);
+                                const uint32_t bw = (st + ((2 * A_BYTES) >> 4)) | tc::kDescLoMN;
                                 if (x3) {
 #pragma unroll
                                     for (int k = 0; k < KCH / 8; ++k) {
                                         // A.[B | B_lo] -> columns [0, bn) and [bn, 2 bn);  A_lo.B -> columns [0, bn)
-                                        tc::mma_tf32(tmem, tc::desc_words(aw + k * a_k, a_hiw), tc::desc_words(bw + k * b_k, b_hiw), idesc2, acc);
-                                        tc::mma_tf32(tmem, tc::desc_words(alw + k * a_k, a_hiw), tc::desc_words(bw + k * b_k, b_hiw), idesc1, 1u);
+                                        tc::mma_tf32(tmem, tc::desc_words(aw + k * a_k, tc::kDescHiMN), tc::desc_words(bw + k * b_k, tc::kDescHiMN), idesc2, acc);
+                                        tc::mma_tf32(tmem, tc::desc_words(alw + k * a_k, tc::kDescHiMN), tc::desc_words(bw + k * b_k, tc::kDescHiMN), idesc1, 1u);
                                         acc = 1;
                                     }
                                 } else {
 #pragma unroll
                                     for (int k = 0; k < KCH / 8; ++k) {
-                                        tc::mma_tf32(tmem, tc::desc_words(aw + k * a_k, a_hiw), tc::desc_words(bw + k * b_k, b_hiw), idesc1, acc);
+                                        tc::mma_tf32(tmem, tc::desc_words(aw + k * a_k, tc::kDescHiMN), tc::desc_words(bw + k * b_k, tc::kDescHiMN), idesc1, acc);
                                         acc = 1;
                                     }
                                 }
@@ -673,266 +1190,72 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                         }
                         __syncwarp();
                     } else {
-                        // ---------- workers: prelude in the shadow of the mainloop, then the epilogue
-                        const int q = warp & 3, hf = warp >> 2;           // TMEM lane quarter, column half of the tile
-                        const int rloc = q * 32 + lane;                   // row inside the tile = TMEM lane
-                        const int row = J.m_tile * 128 + rloc;
-                        const bool valid = row < rows;
-                        const int N = (J.type == J_DH) ? a.n[l] : a.n[l + 1];   // output row pitch
-                        const int col0 = J.n_tile * J.bn;
-                        if (J.type == J_FWD || J.type == J_HEAD) {
-                            // effective bias of this tile's columns; layer 0 adds E_d[dom] . W_0[K0:, cols] in fp32
-                            const int bn = J.bn;
-                            worker_sync();   // the previous job's epilogue may still be reading s_beff / scratch
-                            if (l == 0) {
-                                float* part = reinterpret_cast<float*>(scratch);   // [groups][bn]
-                                const int groups = kWorkers / bn, per = cdiv(a.dd, groups);
-                                const int c = tid % bn, gq = tid / bn;
-                                const float* W0dom = a.params + a.off_W[0] + (long long)K0 * N + col0 + c;
-                                const float* ed = a.params + a.off_Ed + (long long)pd.dom * a.dd;
-                                float s = 0.f;
-                                const int k_end = (gq + 1) * per < a.dd ? (gq + 1) * per : a.dd;
-#pragma unroll 16
-                                for (int k = gq * per; k < k_end; ++k) s = fmaf(ldcg_f(ed + k), ldcg_f(W0dom + (long long)k * N), s);
-                                part[gq * bn + c] = s;
-                                worker_sync();
-                                if (tid < bn) {
-                                    float dsum = 0.f;
-                                    for (int g2 = 0; g2 < groups; ++g2) dsum += part[g2 * bn + tid];
-                                    s_beff[tid] = ldcg_f(a.params + a.off_b[0] + col0 + tid) + dsum;
-                                }
-                            } else if (tid < bn) {
-                                s_beff[tid] = ldcg_f(a.params + a.off_b[l] + col0 + tid);
-                            }
-                            if (J.type == J_HEAD && tid >= 64 && tid < 64 + NL) s_wd[tid - 64] = ldcg_f(a.params + a.off_w + tid - 64);
-                            worker_sync();
-                        }
-                        // dropout keep bits of this thread's columns (bit c: column cbase + c of this row survives)
-                        constexpr int NLH = NL / 2;
-                        const int cbase = J.type == J_HEAD ? hf * NLH : hf * 16;   // first column (inside the tile) of this thread
-                        uint32_t keepmask = 0xffffffffu;
-                        if (dp.enabled && (J.type == J_FWD || J.type == J_HEAD)) {
-                            DropoutParams dq = dp;
-                            dq.seed = a.dropout_seed + (uint32_t)l;
-                            keepmask = 0u;
-                            const uint32_t e0 = (uint32_t)row * (uint32_t)N + (uint32_t)(col0 + cbase);
-                            const int ncol = J.type == J_HEAD ? NLH : 16;
-#pragma unroll
-                            for (int c = 0; c < 32; c += 4) {
-                                if (c < ncol) {
-                                    const uint4 w = dropout_words4(dq, e0 + c);
-                                    const uint32_t nib = (w.x < dq.threshold ? 1u : 0u) | (w.y < dq.threshold ? 2u : 0u) |
-                                                         (w.z < dq.threshold ? 4u : 0u) | (w.w < dq.threshold ? 8u : 0u);
-                                    keepmask |= nib << c;
-                                }
-                            }
-                        }
-                        float4 hmask[4];   // dH: the forward activations of this thread's 16 columns (all loads before the wait)
-                        if (J.type == J_DH) {
-#pragma unroll
-                            for (int u = 0; u < 4; ++u)
-                                hmask[u] = valid ? ldcg_f4(a.H[l] + (long long)row * N + col0 + cbase + u * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        }
-                        WSTAMP(12);
-                        tc::mbar_wait(&bar_done, njob & 1);
+                        // ---------- workers: the split-K partial tile -> partials[l][z][tile][128][bn]
+                        const int q = warp & 3, hf = warp >> 2;
+                        const int rloc = q * 32 + lane;
+                        tc::mbar_wait_warp(&bar_done, njob & 1);
                         tc::tc_fence_after();
                         if (tim && tid == 0) a.timing[tslot + 6] = (unsigned long long)clock64();
                         const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
-
-                        if (J.type == J_FWD) {
-                            WSTAMP(8);
-                            float* out = a.H[l + 1] + (long long)row * N + col0 + cbase;
-                            const long long oz = (long long)a.max_rows * N;
-                            const float dscale = dp.enabled ? dp.scale : 1.0f;
+                        const int tile = J.m_tile * J.NT + J.n_tile;
+                        const int half = J.bn >> 1;   // columns per thread: 32 (bn = 64) or 16 (bn = 32)
+                        float* mine = a.partials[l] + (((long long)J.z * J.tiles + tile) * 128 + rloc) * J.bn + hf * half;
+                        for (int n0 = 0; n0 < half; n0 += 16) {
                             float vv[16], v2[16];
-                            tc::tmem_ld16(tlane + cbase, vv);
-                            if (x3) tc::tmem_ld16(tlane + 32 + cbase, v2);
-                            tc::tc_fence_before();
-                            tc::mbar_arrive(&bar_tfree);
-                            if (valid) {
-#pragma unroll
-                                for (int jx = 0; jx < 16; jx += 4) {
-                                    float h[4];
-#pragma unroll
-                                    for (int t = 0; t < 4; ++t) {
-                                        const float accv = x3 ? vv[jx + t] + v2[jx + t] : vv[jx + t];
-                                        h[t] = fmaxf(accv + s_beff[cbase + jx + t], 0.f);
-                                        h[t] = (keepmask >> (jx + t)) & 1u ? h[t] * dscale : 0.f;
-                                    }
-                                    store_pair4(out + jx, oz, make_float4(h[0], h[1], h[2], h[3]), rnd, x3);
-                                }
-                            }
-                            WSTAMP(9);
-                        } else if (J.type == J_HEAD) {
-                            // last hidden layer + Dense(1) + sigmoid + BCE + ds + dZ_{L-1} + per-tile partials + AUC bins
-                            float h[NLH];
-                            float zp = 0.f;
-                            const float dscale = dp.enabled ? dp.scale : 1.0f;
-#pragma unroll
-                            for (int n0 = 0; n0 < NLH; n0 += 16) {
-                                float vv[16], v2[16];
-                                tc::tmem_ld16(tlane + cbase + n0, vv);
-                                if (x3) tc::tmem_ld16(tlane + NL + cbase + n0, v2);
-#pragma unroll
-                                for (int jx = 0; jx < 16; ++jx) {
-                                    const float accv = x3 ? vv[jx] + v2[jx] : vv[jx];
-                                    float hh = fmaxf(accv + s_beff[cbase + n0 + jx], 0.f);
-                                    hh = (keepmask >> (n0 + jx)) & 1u ? hh * dscale : 0.f;
-                                    h[n0 + jx] = valid ? hh : 0.f;
-                                    zp = fmaf(hh, s_wd[cbase + n0 + jx], zp);
-                                }
-                            }
-                            tc::tc_fence_before();
-                            tc::mbar_arrive(&bar_tfree);
-                            WSTAMP(8);
-                            s_z[hf][rloc] = zp;
-                            worker_sync();
-                            const float z = s_z[0][rloc] + s_z[1][rloc];
-                            const float lo_c = 1e-7f, hi_c = 1.0f - 1e-7f;
-                            float dsv = 0.f;
-                            double bce = 0.0;
-                            if (valid) {
-                                const float sgm = z + ldcg_f(a.params + a.off_g);
-                                const float pv = 1.0f / (1.0f + expf(-sgm));
-                                const float yv = a.y[buf][row];
-                                if (a.train) dsv = (fabsf(sgm) <= MAMDR_LOGIT_CLIP) ? __fdiv_rn(__fsub_rn(pv, yv), (float)rows) : 0.f;
-                                if (hf == 0) {
-                                    const float ph = fminf(fmaxf(pv, lo_c), hi_c);
-                                    const float lg = logf(ph / (1.0f - ph));
-                                    bce = (double)(fmaxf(lg, 0.f) - lg * yv + log1pf(expf(-fabsf(lg))));
-                                    if (pd.probs) pd.probs[(long long)step * a.bs + row] = pv;
-                                    if (a.auc_acc) {
-                                        int lo_i = 0, hi_i = a.T;
-                                        while (lo_i < hi_i) {
-                                            const int mid = (lo_i + hi_i) >> 1;
-                                            if (s_thr[mid] < pv) lo_i = mid + 1; else hi_i = mid;
-                                        }
-                                        atomicAdd(&hist_cur[(yv != 0.f ? (a.T + 1) : 0) + lo_i], 1);
-                                    }
-                                }
-                            }
-                            WSTAMP(9);
-                            double* red_d = reinterpret_cast<double*>(scratch);               // [4]
-                            float* red_f = reinterpret_cast<float*>(scratch + 64);            // [4]
-                            float* csum = reinterpret_cast<float*>(scratch + 128);            // [2 kinds][8 warps][NLH]
-                            if (hf == 0) {
-                                double bs = bce;
-                                float dgs = dsv;
-#pragma unroll
-                                for (int o = 16; o > 0; o >>= 1) {
-                                    bs += __shfl_xor_sync(0xffffffffu, bs, o);
-                                    dgs += __shfl_xor_sync(0xffffffffu, dgs, o);
-                                }
-                                if (lane == 0) { red_d[q] = bs; red_f[q] = dgs; }
-                            }
-                            if (a.train) {
-                                float* dZ = a.dZ[L - 1] + (long long)row * NL + cbase;
-                                const long long oz = (long long)a.max_rows * NL;
-                                const bool store = row < a.max_rows;
-                                float hd[NLH];   // h * ds  (column sums -> gradient of the Dense(1) kernel)
-#pragma unroll
-                                for (int c = 0; c < NLH; c += 4) {
-                                    float dz[4];
-#pragma unroll
-                                    for (int t = 0; t < 4; ++t) {
-                                        const float dh = __fmul_rn(dsv, s_wd[cbase + c + t]);
-                                        dz[t] = h[c + t] > 0.f ? __fmul_rn(dh, inv_keep) : 0.f;
-                                        hd[c + t] = h[c + t] * dsv;
-                                        h[c + t] = dz[t];
-                                    }
-                                    // rows past the batch get zeros: dW's K loop runs over whole 32-row chunks
-                                    if (store) store_pair4(dZ + c, oz, make_float4(dz[0], dz[1], dz[2], dz[3]), rnd, x3);
-                                }
-                                WSTAMP(10);
-                                const float s_hd = warp_colsum<NLH>(hd, lane);
-                                const float s_dz = warp_colsum<NLH>(h, lane);
-                                const int cl = NLH == 32 ? lane : lane >> 1;
-                                if (NLH == 32 || (lane & 1) == 0) {
-                                    csum[(0 * kWorkerWarps + warp) * NLH + cl] = s_hd;
-                                    csum[(1 * kWorkerWarps + warp) * NLH + cl] = s_dz;
-                                }
-                            }
-                            worker_sync();
-                            if (tid == 0) {
-                                a.loss_part[buf * kMaxMT + J.m_tile] = red_d[0] + red_d[1] + red_d[2] + red_d[3];
-                                a.dg_part[J.m_tile] = red_f[0] + red_f[1] + red_f[2] + red_f[3];
-                            }
-                            if (a.train && tid < 2 * NL) {
-                                // column c of the tile (half c / NLH): the four row-quarter warps in order
-                                const int kind = tid / NL, c = tid - kind * NL, h2 = c / NLH, cc = c - h2 * NLH;
-                                float s = 0.f;
-#pragma unroll
-                                for (int qq = 0; qq < 4; ++qq) s += csum[(kind * kWorkerWarps + h2 * 4 + qq) * NLH + cc];
-                                (kind == 0 ? a.dw_part : a.db_part[L - 1])[J.m_tile * NL + c] = s;
-                            }
-                            worker_sync();
-                            WSTAMP(11);
-                        } else if (J.type == J_DH) {
-                            // dZ_{l-1}[row, col0 + cbase .. +16) = acc * inv_keep * 1[H_l > 0]; per-tile column sums -> db_{l-1}
-                            float* out = a.dZ[l - 1] + (long long)row * N + col0 + cbase;
-                            const long long oz = (long long)a.max_rows * N;
-                            const bool store = row < a.max_rows;
-                            float vv[16], v2[16], dzv[16];
-                            tc::tmem_ld16(tlane + cbase, vv);
-                            if (x3) tc::tmem_ld16(tlane + 32 + cbase, v2);
-                            tc::tc_fence_before();
-                            tc::mbar_arrive(&bar_tfree);
+                            tc::tmem_ld16(tlane + hf * half + n0, vv);
+                            if (x3) tc::tmem_ld16(tlane + J.bn + hf * half + n0, v2);
 #pragma unroll
                             for (int jx = 0; jx < 16; jx += 4) {
-                                const float4 hq = hmask[jx >> 2];
-                                const float hm[4] = {hq.x, hq.y, hq.z, hq.w};
-#pragma unroll
-                                for (int t = 0; t < 4; ++t) {
-                                    const float accv = x3 ? vv[jx + t] + v2[jx + t] : vv[jx + t];
-                                    dzv[jx + t] = (valid && hm[t] > 0.f) ? accv * inv_keep : 0.f;
-                                }
-                                if (store) store_pair4(out + jx, oz, make_float4(dzv[jx], dzv[jx + 1], dzv[jx + 2], dzv[jx + 3]), rnd, x3);
+                                float4 o4;
+                                if (x3) o4 = make_float4(vv[jx] + v2[jx], vv[jx + 1] + v2[jx + 1], vv[jx + 2] + v2[jx + 2], vv[jx + 3] + v2[jx + 3]);
+                                else o4 = make_float4(vv[jx], vv[jx + 1], vv[jx + 2], vv[jx + 3]);
+                                __stcg(reinterpret_cast<float4*>(mine + n0 + jx), o4);
                             }
-                            float* csum = reinterpret_cast<float*>(scratch);   // [8 warps][16]
-                            const float s_dz = warp_colsum<16>(dzv, lane);
-                            worker_sync();   // the previous job's readers of csum are done
-                            if ((lane & 1) == 0) csum[warp * 16 + (lane >> 1)] = s_dz;
-                            worker_sync();
-                            if (tid < 32) {
-                                const int h2 = tid >> 4, cc = tid & 15;
-                                float s = 0.f;
-#pragma unroll
-                                for (int qq = 0; qq < 4; ++qq) s += csum[(h2 * 4 + qq) * 16 + cc];
-                                a.db_part[l - 1][(long long)J.m_tile * N + col0 + tid] = s;
-                            }
-                        } else {   // J_DW: split-K partial of dW_l -> partials[l][z][tile][128][bn]
-                            const int tile = J.m_tile * J.NT + J.n_tile;
-                            const int half = J.bn >> 1;   // columns per thread: 32 (bn = 64) or 16 (bn = 32)
-                            float* mine = a.partials[l] + (((long long)J.z * J.tiles + tile) * 128 + rloc) * J.bn + hf * half;
-                            for (int n0 = 0; n0 < half; n0 += 16) {
-                                float vv[16], v2[16];
-                                tc::tmem_ld16(tlane + hf * half + n0, vv);
-                                if (x3) tc::tmem_ld16(tlane + J.bn + hf * half + n0, v2);
-#pragma unroll
-                                for (int jx = 0; jx < 16; jx += 4) {
-                                    float4 o4;
-                                    if (x3) o4 = make_float4(vv[jx] + v2[jx], vv[jx + 1] + v2[jx + 1], vv[jx + 2] + v2[jx + 2], vv[jx + 3] + v2[jx + 3]);
-                                    else o4 = make_float4(vv[jx], vv[jx + 1], vv[jx + 2], vv[jx + 3]);
-                                    __stcg(reinterpret_cast<float4*>(mine + n0 + jx), o4);
-                                }
-                            }
-                            tc::tc_fence_before();
-                            tc::mbar_arrive(&bar_tfree);
                         }
+                        tc::tc_fence_before();
+                        tc::mbar_arrive(&bar_tfree);
+                        // publish: the release covers the partial-tile stores of every worker (ordered by the barrier)
+                        worker_sync();
+                        if (tid == 0) red_release_add_u32(a.tile_ctr + J.gtile, 1u);
                     }
                     ++njob;
                 }
-                if (phase == 2 * L - 1 && early_done && cta >= jobs_last_bwd)
-                    update_items((long long)(cta - jobs_last_bwd) * kThreads + tid, (long long)(G - jobs_last_bwd) * kThreads, 1);
-                // while the few head tiles run, everyone else stages the next mini-batch
-                if (phase == L - 1 && step + 1 < pd.steps && warp < kWorkerWarps) {
-                    const int first = G > 2 * mt ? mt : 0;
-                    if (cta >= first) gather_rows(a, pd, step + 1, buf ^ 1, (cta - first) * kWorkerWarps + warp, (G - first) * kWorkerWarps, lane, rnd, x3);
+                // ---------- second sweep over this CTA's tile jobs (after ALL its partials are published: no wait cycle between
+                // CTAs): when the S partials of the tile are in memory, reduce rows [z, z+1) * 128 / S of it in split order and
+                // apply the optimizer to them
+                {
+                    int chunks, S, cps;
+                    split_plan(rows, chunks, S, cps);
+                    tile_target += (unsigned int)S;
                 }
-            } else {
-                // ---------- update phase: Adam / SGD on the parameters whose gradients became final in the last backward
-                // phase (E_d, W_0, b_0); the rest was already applied by the idle CTAs of that phase (early_done)
-                update_items((long long)cta * kThreads + tid, (long long)G * kThreads, early_done ? 2 : 0);
+                if (warp < kWorkerWarps) {
+                    for (int j = cta; j < njobs; j += G) {
+                        const Job J = (rows == a.bs && j == cta) ? job_full : decode_dw_job(a, rows, j);
+                        if (J.type != J_DW) continue;
+                        if (tid == 0) {
+                            while (ld_acquire_u32(a.tile_ctr + J.gtile) < tile_target) {}
+                        }
+                        worker_sync();
+                        const int l = J.layer, N = a.n[l + 1], bn = J.bn, bn4 = bn >> 2;
+                        const int tile = J.m_tile * J.NT + J.n_tile;
+                        const int vrows = a.n[l] - J.m_tile * 128 < 128 ? a.n[l] - J.m_tile * 128 : 128;
+                        const int rper = cdiv(128, J.S);
+                        const int r_beg = J.z * rper, r_end = r_beg + rper < vrows ? r_beg + rper : vrows;
+                        const long long zstride = (long long)J.tiles * 128 * bn;
+                        for (int idx = tid; idx < (r_end - r_beg) * bn4; idx += kWorkers) {
+                            const int r = r_beg + idx / bn4, c = (idx - (idx / bn4) * bn4) * 4;
+                            const float* src = a.partials[l] + ((long long)tile * 128 + r) * bn + c;
+                            float4 q4[kMaxSplit];
+#pragma unroll
+                            for (int z = 0; z < kMaxSplit; ++z) q4[z] = z < J.S ? ldcg_f4(src + z * zstride) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            float g[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                            for (int z = 0; z < kMaxSplit; ++z)
+                                if (z < J.S) { g[0] += q4[z].x; g[1] += q4[z].y; g[2] += q4[z].z; g[3] += q4[z].w; }
+                            apply4(a.off_W[l] + (long long)(J.m_tile * 128 + r) * N + J.n_tile * bn + c, g, true);
+                        }
+                    }
+                }
                 if (a.opt_kind == 0) {
                     b1pow = __fmul_rn(b1pow, a.beta1);
                     b2pow = __fmul_rn(b2pow, a.beta2);
@@ -946,11 +1269,12 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
             grid_barrier(a.bar, bar_target);
         }
         // the Keras loss of this mini-batch (value only).  loss_part is double-buffered by step parity: the next
-        // write to this buffer is two head phases (>= one grid barrier that this thread also passes) away.
-        if (cta == G - 1 && tid == 0) {
-            double bs = 0.0;
-            for (int m = 0; m < mt; ++m) bs += __ldcg(a.loss_part + buf * kMaxMT + m);
-            pd.losses[step] = (float)(bs / (double)rows + (double)a.frozen_reg + (double)a.l2_emb * __ldcg(a.ed_sq));
+        // write to this buffer is two chain phases (>= one grid barrier that this thread also passes) away.
+        if (cta == G - 1 && warp == 0) {
+            double bs;
+            if (a.train) bs = __ldcg(a.loss_part + 2 * kMaxGroups + buf);
+            else bs = warp_group_sum_d(a.loss_part + buf * kMaxGroups, ngroups, lane);
+            if (lane == 0) pd.losses[step] = (float)(bs / (double)rows + (double)a.frozen_reg + (double)a.l2_emb * __ldcg(a.ed_sq));
         }
     }
 
@@ -1009,7 +1333,7 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
 // ---- workspace layout ---------------------------------------------------------------------------------------------
 struct PassWs {
     size_t bar, hist, X[2], y[2], H[MAMDR_MAX_LAYERS], dZ[MAMDR_MAX_LAYERS], partials[MAMDR_MAX_LAYERS], db_part[MAMDR_MAX_LAYERS];
-    size_t dw_part, dg_part, loss_part, db0_red, gEd_row, ed_row, ed_sq, wpair, wz, total;
+    size_t dw_part, dg_part, loss_part, fold_part, ed_sq, wpair, wz, total;
 };
 
 inline PassWs pass_ws(const mamdr_mlp_desc& d, int B) {
@@ -1023,8 +1347,8 @@ inline PassWs pass_ws(const mamdr_mlp_desc& d, int B) {
     const int L = d.n_layers;
     const int K0 = d.emb_dim[0] + d.emb_dim[1];
     const int Bp = (B + 127) / 128 * 128;   // whole 128-row tiles: the epilogues write zero rows up to the tile edge
-    const int mt = Bp / 128;
-    w.bar = take(64);
+    const int ng = Bp / CR;                 // row groups of the chain
+    w.bar = take(kBarBytes);                 // grid-barrier counter + the dW tile counters
     w.hist = take((size_t)2 * 2 * (kMaxThr + 1) * 4);   // double-buffered by pass parity
     // GEMM operands are pair arrays [2][Bp][width]: plane 0 = value, plane 1 = its 3xTF32 "lo" part
     for (int b = 0; b < 2; ++b) { w.X[b] = take((size_t)2 * Bp * K0 * 4); w.y[b] = take((size_t)Bp * 4); }
@@ -1035,17 +1359,15 @@ inline PassWs pass_ws(const mamdr_mlp_desc& d, int B) {
         const int bn = d.hidden[l] < 64 ? d.hidden[l] : 64;
         const size_t tiles = (size_t)((in + 127) / 128) * (d.hidden[l] / bn);
         w.partials[l] = take(tiles * kMaxSplit * 128 * bn * 4);
-        w.db_part[l] = take((size_t)mt * d.hidden[l] * 4);
+        w.db_part[l] = take((size_t)ng * d.hidden[l] * 4);
     }
-    w.dw_part = take((size_t)mt * d.hidden[L - 1] * 4);
-    w.dg_part = take((size_t)mt * 4);
-    w.loss_part = take((size_t)2 * kMaxMT * 8);
-    w.db0_red = take((size_t)d.hidden[0] * 4);
-    w.gEd_row = take((size_t)d.emb_dim[2] * 4);
-    w.ed_row = take((size_t)d.emb_dim[2] * 4);
+    w.dw_part = take((size_t)ng * d.hidden[L - 1] * 4);
+    w.dg_part = take((size_t)ng * 4);
+    w.loss_part = take((size_t)(2 * kMaxGroups + 2) * 8);
+    w.fold_part = take((size_t)kDomJobs * d.hidden[0] * 4);
     w.ed_sq = take(8);
     w.wz = ((size_t)(d.arena_floats - d.off_domain_emb) + 31) / 32 * 32;   // floats between the two planes of the kernel shadow
-    w.wpair = take(2 * w.wz * 4);                                          // dense span of the arena only
+    w.wpair = take((size_t)kRep * 2 * w.wz * 4);                           // dense span of the arena only, kRep copies
     w.total = off;
     return w;
 }
@@ -1063,18 +1385,18 @@ static int pass_supported(mamdr_ctx* ctx, const mamdr_mlp_desc* d, int max_batch
     MAMDR_REQUIRE(ctx, d->emb_dim[0] % 4 == 0 && d->emb_dim[1] % 4 == 0 && d->emb_dim[2] % 4 == 0 && K0 % 32 == 0, MAMDR_E_UNSUPPORTED,
                   "pass kernel needs emb dims that are multiples of 4 and user+item width a multiple of 32");
     for (int l = 0; l < d->n_layers; ++l)
-        MAMDR_REQUIRE(ctx, d->hidden[l] % 32 == 0 && (d->hidden[l] == 32 || d->hidden[l] % 64 == 0) && d->hidden[l] <= 4096, MAMDR_E_UNSUPPORTED,
-                      "pass kernel needs hidden widths of 32 or multiples of 64");
+        MAMDR_REQUIRE(ctx, d->hidden[l] % 32 == 0 && (d->hidden[l] == 32 || d->hidden[l] % 64 == 0) && d->hidden[l] <= kMaxWidth, MAMDR_E_UNSUPPORTED,
+                      "pass kernel needs hidden widths of 32 or multiples of 64, at most 256 (the row-local chain keeps a layer in shared memory)");
+    MAMDR_REQUIRE(ctx, K0 <= kMaxWidth && d->emb_dim[2] <= 256, MAMDR_E_UNSUPPORTED, "pass kernel needs user+item width <= 256 and domain width <= 256");
     const int nl = d->hidden[d->n_layers - 1];
     MAMDR_REQUIRE(ctx, nl == 32 || nl == 64, MAMDR_E_UNSUPPORTED, "pass kernel needs a last hidden width of 32 or 64");
-    MAMDR_REQUIRE(ctx, max_batch >= 1 && max_batch <= 128 * kMaxMT, MAMDR_E_UNSUPPORTED, "batch too large for the pass kernel");
+    MAMDR_REQUIRE(ctx, max_batch >= 1 && max_batch <= CR * kMaxGroups, MAMDR_E_UNSUPPORTED, "batch too large for the pass kernel");
     MAMDR_REQUIRE(ctx, d->dropout_rate >= 0.f && d->dropout_rate < 1.f, MAMDR_E_INVALID, "dropout_rate must be in [0,1)");
     return MAMDR_OK;
 }
 
 int mamdr_pass_init_kernels(mamdr_ctx* ctx) {
-    MAMDR_CUDA_OK(ctx, cudaFuncSetAttribute(pass_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
-    MAMDR_CUDA_OK(ctx, cudaFuncSetAttribute(pass_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
+    MAMDR_CUDA_OK(ctx, cudaFuncSetAttribute(pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
     return MAMDR_OK;
 }
 
@@ -1113,10 +1435,10 @@ struct Program {
 int mamdr_meta_launch(mamdr_ctx* ctx, int meta_op, const MetaArgs& a, mamdr_stream stream);   // optim.cu
 
 static int launch_program(mamdr_ctx* ctx, const MapTable& mp, const PassArgs& a, cudaStream_t st) {
-    MAMDR_CUDA_OK(ctx, cudaMemsetAsync(a.bar, 0, 64, st));
+    MAMDR_CUDA_OK(ctx, cudaMemsetAsync(a.bar, 0, kBarBytes, st));
     const size_t smem = smem_bytes();
     void* kargs[] = {(void*)&mp, (void*)&a};
-    const void* fn = a.n[a.L] == 64 ? (const void*)pass_kernel<64> : (const void*)pass_kernel<32>;
+    const void* fn = (const void*)pass_kernel;
     MAMDR_CUDA_OK(ctx, cudaLaunchCooperativeKernel(fn, dim3(ctx->sm_count), dim3(kThreads), kargs, smem, st));
     return MAMDR_OK;
 }
@@ -1177,12 +1499,14 @@ static int run_pass(mamdr_ctx* ctx, const mamdr_mlp_desc* d, const mamdr_pass* p
         a.db_part[l] = (float*)(ws + w.db_part[l]);
     }
     a.dw_part = (float*)(ws + w.dw_part); a.dg_part = (float*)(ws + w.dg_part); a.loss_part = (double*)(ws + w.loss_part);
-    a.db0_red = (float*)(ws + w.db0_red); a.gEd_row = (float*)(ws + w.gEd_row); a.ed_row = (float*)(ws + w.ed_row);
+    a.fold_part = (float*)(ws + w.fold_part);
     a.ed_sq = (double*)(ws + w.ed_sq);
     a.wpair = (float*)(ws + w.wpair) - d->off_domain_emb;   // indexed with arena offsets
     a.wz = (long long)w.wz;
+    a.wrep = 2 * (long long)w.wz;
     a.hist = (int*)(ws + w.hist);
     a.bar = (unsigned int*)(ws + w.bar);
+    a.tile_ctr = a.bar + 16;
     a.state = (OptState*)opt_state;
     a.opt_kind = optimizer; a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps;
     const float keep = 1.0f - d->dropout_rate;
@@ -1202,20 +1526,19 @@ static int run_pass(mamdr_ctx* ctx, const mamdr_mlp_desc* d, const mamdr_pass* p
     memset(&mp, 0, sizeof(mp));
     bool ok = true;
     // every GEMM operand is a pair array; the lo plane lies Bp * width floats (kernels: wz floats) behind the hi plane
-    const float* wsrc = a.wpair;   // B operands of fwd / dH: the pair shadow of the kernels
+    const float* wsrc = a.wpair;   // M operands of the chain GEMMs: the pair shadow of the kernels
     for (int b = 0; b < 2; ++b) {
         const uint64_t z = (uint64_t)Bp * a.n[0];
-        ok = ok && mlptc::pair_kmajor_map(ctx, &mp.xk[b], a.X[b], Bp, a.n[0], 128, z) && mlptc::pair_mnmajor_map(ctx, &mp.xmn[b], a.X[b], Bp, a.n[0], z);
+        ok = ok && mlptc::pair_kmajor_map(ctx, &mp.xk[b], a.X[b], Bp, a.n[0], CR, z) && mlptc::pair_mnmajor_map(ctx, &mp.xmn[b], a.X[b], Bp, a.n[0], z);
     }
     for (int l = 0; l < L; ++l) {
         const uint64_t zh = (uint64_t)Bp * a.n[l], zd = (uint64_t)Bp * a.n[l + 1];
         if (l >= 1) {
-            ok = ok && mlptc::pair_kmajor_map(ctx, &mp.hk[l], a.H[l], Bp, a.n[l], 128, zh) && mlptc::pair_mnmajor_map(ctx, &mp.hmn[l], a.H[l], Bp, a.n[l], zh);
-            ok = ok && mlptc::pair_kmajor_map(ctx, &mp.dzk[l], a.dZ[l], Bp, a.n[l + 1], 128, zd);
-            ok = ok && mlptc::pair_kmajor_map(ctx, &mp.wb[l], wsrc + d->off_kernel[l], a.n[l], a.n[l + 1], 32, (uint64_t)a.wz);
+            ok = ok && mlptc::pair_mnmajor_map(ctx, &mp.hmn[l], a.H[l], Bp, a.n[l], zh);
+            ok = ok && mlptc::pair_kmajor_map(ctx, &mp.wb[l], wsrc + d->off_kernel[l], a.n[l], a.n[l + 1], a.n[l] < 128 ? a.n[l] : 128, (uint64_t)a.wz, kRep, (uint64_t)a.wrep);
         }
         ok = ok && mlptc::pair_mnmajor_map(ctx, &mp.dzmn[l], a.dZ[l], Bp, a.n[l + 1], zd);
-        ok = ok && mlptc::pair_mnmajor_map(ctx, &mp.wf[l], wsrc + d->off_kernel[l], a.n[l], a.n[l + 1], (uint64_t)a.wz);
+        ok = ok && mlptc::pair_mnmajor_map(ctx, &mp.wf[l], wsrc + d->off_kernel[l], a.n[l], a.n[l + 1], (uint64_t)a.wz, kRep, (uint64_t)a.wrep);
     }
     MAMDR_REQUIRE(ctx, ok, MAMDR_E_CUDA, "cuTensorMapEncodeTiled failed (pass kernel)");
 

@@ -37,6 +37,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 
+// the same wait by ONE lane of a converged warp (the other lanes park on the warp barrier instead of polling shared memory)
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+    if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+    __syncwarp();
+}
+
 // ---- TMA ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -56,6 +62,15 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
             smem_u32(smem_dst)),
         "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+// 4D tile load: (c0 = innermost element, c1 = row, c2 = plane of a pair array, c3 = replica)
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
 
@@ -137,6 +152,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
 
 // ---- descriptors ----------------------------------------------------------------------------------------------
 // UMMA shared-memory matrix descriptor (SM100): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
@@ -206,15 +231,16 @@ inline bool make_tmap_2d_f32(CUtensorMap* out, const float* base, uint64_t rows,
               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 // pair array [2][rows][cols] (plane 0 = hi, plane 1 = lo, `zstride` floats apart): 3-D map, box = [1, box_rows, box_cols]
+// with reps > 1 the map is 4-D: `reps` copies of the pair array, `rstride` floats apart
 inline bool make_tmap_pair_f32(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint64_t zstride,
-                               uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle swz) {
+                               uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle swz, uint64_t reps = 1, uint64_t rstride = 0) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return false;
-    cuuint64_t dims[3] = {cols, rows, 2};
-    cuuint64_t strides[2] = {ld * sizeof(float), zstride * sizeof(float)};
-    cuuint32_t box[3] = {box_cols, box_rows, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    return fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+    cuuint64_t dims[4] = {cols, rows, 2, reps};
+    cuuint64_t strides[3] = {ld * sizeof(float), zstride * sizeof(float), rstride * sizeof(float)};
+    cuuint32_t box[4] = {box_cols, box_rows, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    return fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, reps > 1 ? 4 : 3, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 }  // namespace tc

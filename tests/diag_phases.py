@@ -22,7 +22,7 @@ def main(prec="tf32"):
     d = base.dataset.train_dataset[idx]
     steps = min(d['n_step'], 6)
     G = m.ctx.sm_count
-    nph = 7
+    nph = 2
     buf = torch.zeros(steps * nph * G * 16, dtype=torch.int64, device=m.device)
     for _ in range(3):
         m.fit_pass(d['data'], steps)
@@ -31,7 +31,7 @@ def main(prec="tf32"):
     torch.cuda.synchronize()
     m.ctx.call("mamdr_debug_pass_timing", None, 0)
     t = buf.cpu().numpy().reshape(steps, nph, G, 16).astype(np.float64)
-    names = ["fwd0", "fwd1", "fwd2+head", "bwd2 (dH2,dW2)", "bwd1 (dH1,dW1)", "bwd0 (dW0,dom)", "update"]
+    names = ["chain", "dW+update"]
     print(prec, "steps", steps, "G", G)
     s = 2
     base_t = t[s, 0, :, 0].min()
@@ -41,13 +41,13 @@ def main(prec="tf32"):
         busy = (en - st) / 1e3
         nxt = t[s, p + 1, :, 0].min() if p + 1 < nph else t[s + 1, 0, :, 0].min()
         print("%-16s start %.2f  work max %.2f med %.2f us  barrier %.2f" % (names[p], (st.min() - base_t) / 1e3, busy.max(), np.median(busy), (nxt - en.max()) / 1e3))
-        if p < 6:
+        if p < 2:
             # the 3 busiest CTAs: clock64 deltas from phase start (us)
             for cta in np.argsort(-busy)[:3]:
                 c0 = t[s, p, cta, 7]
                 rel = [(t[s, p, cta, k] - c0) / GHZ / 1e3 if t[s, p, cta, k] > 0 else float('nan') for k in (2, 3, 4, 5, 6)]
-                ep = " ".join("%d:%.2f" % (k, (t[s, p, cta, k] - c0) / GHZ / 1e3) for k in (12, 8, 9, 10, 11) if t[s, p, cta, k] > 0)
-                print("    cta %3d busy %.2f us | tma first-issue %.2f all-issued %.2f | mma first-full %.2f all-issued %.2f | done-seen %.2f | prelude-done/epilogue stamps %s" % ((cta, busy[cta]) + tuple(rel) + (ep,)))
+                ep = " ".join("%.2f" % ((t[s, p, cta, k] - c0) / GHZ / 1e3) for k in range(8, 16) if t[s, p, cta, k] > 0)
+                print("    cta %3d busy %.2f us | tma first-issue %.2f all-issued %.2f | mma first-full %.2f all-issued %.2f | done-seen %.2f | chain segment epilogues done %s" % ((cta, busy[cta]) + tuple(rel) + (ep,)))
 
 
 if __name__ == "__main__":
