@@ -78,8 +78,6 @@ constexpr int kScratchBytes = 20 * 1024;
 constexpr int kMaxThr = 1024;
 constexpr int kMaxSplit = 8;
 constexpr int kDomJobs = 16;                  // the domain block (gradient GEMV, optimizer apply, fold) is split over this many CTAs
-constexpr int kRep = 4;                       // copies of the kernel pair shadow: every chain CTA streams ALL weights, and 64 CTAs
-                                              // reading the same L2 lines in lock-step serialise on the L2 slices
 constexpr int kMaxGroups = 8192 / CR;         // row groups per mini-batch (batch <= 8192)
 constexpr int kMaxSegs = 4 * MAMDR_MAX_LAYERS;
 constexpr int kBarBytes = 64 + 4 * 8 * MAMDR_MAX_LAYERS;   // grid-barrier counter + one counter per dW tile (<= 8 per layer)
@@ -99,7 +97,7 @@ struct MapTable {   // kernel parameter (param space is a legal tensor-map addre
     CUtensorMap xk[2], xmn[2];                  // X double buffer: K-major [B, K0] (box CR rows) / MN-major view
     CUtensorMap hmn[MAMDR_MAX_LAYERS];          // H_l  MN-major (A of dW_l), l = 1..L-1
     CUtensorMap dzmn[MAMDR_MAX_LAYERS];         // dZ_l MN-major (B of dW_l), l = 0..L-1
-    CUtensorMap wf[MAMDR_MAX_LAYERS];           // W_l  MN-major [K = in, M = out] (A of the transposed forward GEMM)
+    CUtensorMap wf[MAMDR_MAX_LAYERS];           // W_l^T K-major [M = out, K = in] (A of the transposed forward GEMM)
     CUtensorMap wb[MAMDR_MAX_LAYERS];           // W_l  K-major  [M = in, K = out] (A of the transposed dH GEMM), l = 1..L-1
 };
 
@@ -132,8 +130,10 @@ struct PassArgs {
     int nseg;
     Seg seg[2 * MAMDR_MAX_LAYERS + 3];
     float *params, *m, *v, *grads;    // grads may be NULL
-    float* wpair;                     // arena-indexed pair shadow of the kernels: plane 0 at wpair, plane 1 at wpair + wz;
-    long long wz, wrep;               // kRep copies, wrep floats apart
+    float* wpair;                     // arena-indexed pair shadow of the kernels W_l [in, out] (M operand of the dH GEMMs):
+    long long wz;                     // plane 0 at wpair, plane 1 at wpair + wz
+    float* wT[MAMDR_MAX_LAYERS];      // pair shadow of W_l^T [out, in] (M operand of the forward GEMMs; layer 0: the K0 user / item
+                                      // rows only); plane 1 lies n[l + 1] * n[l] floats behind plane 0
     const float *Eu, *Ei;
     // ---- data
     int bs, max_rows;
@@ -174,7 +174,7 @@ __host__ __device__ inline void split_plan(int rows, int& chunks, int& S, int& c
 __host__ __device__ inline int dw_tiles(const PassArgs& a, int l) { return cdiv(a.n[l], 128) * (a.n[l + 1] / dw_bn(a, l)); }
 
 // jobs of the dW phase: [domain jobs | column-sum job | split-K tile jobs of dW_0, dW_1, ...]
-__host__ __device__ inline int dw_phase_jobs(const PassArgs& a, int rows) {
+__host__ __device__ __noinline__ int dw_phase_jobs(const PassArgs& a, int rows) {
     int chunks, S, cps;
     split_plan(rows, chunks, S, cps);
     int n = kDomJobs + 1;
@@ -182,7 +182,7 @@ __host__ __device__ inline int dw_phase_jobs(const PassArgs& a, int rows) {
     return n;
 }
 
-__device__ __forceinline__ Job decode_dw_job(const PassArgs& a, int rows, int j) {
+__device__ __noinline__ Job decode_dw_job(const PassArgs& a, int rows, int j) {
     Job J;
     J.z = 0; J.c_beg = 0; J.tiles = 0; J.NT = 1; J.n_tile = 0; J.layer = 0; J.bn = 0; J.nch = 0; J.m_tile = 0; J.gtile = 0; J.S = 1;
     if (j < kDomJobs) { J.type = J_DOM; J.m_tile = j; return J; }
@@ -376,6 +376,7 @@ __device__ __forceinline__ void fold_from_params(const PassArgs& a, int dom, int
 }
 
 // ---- the kernel ---------------------------------------------------------------------------------------------------
+template <int PASSES>   // 3 = 3xTF32 (pair operands), 1 = 1-pass TF32 (operands pre-rounded)
 __global__ void __launch_bounds__(kThreads, 1)
 pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -388,9 +389,8 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int G = gridDim.x, cta = blockIdx.x;
-    const int passes = a.passes;
-    const bool x3 = passes == 3;    // 3xTF32: pair operands, N-concatenated MMAs
-    const bool rnd = passes == 1;   // 1-pass TF32: GEMM operands are stored pre-rounded (RN) to tf32
+    constexpr bool x3 = PASSES == 3;    // 3xTF32: pair operands, N-concatenated MMAs
+    constexpr bool rnd = PASSES == 1;   // 1-pass TF32: GEMM operands are stored pre-rounded (RN) to tf32
     unsigned char* scratch = smem + (size_t)kStages * STAGE_BYTES;
     const int L = a.L;
 
@@ -472,18 +472,31 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
     const int K0 = a.n[0];
     const int NL = a.n[L];
     const float inv_keep = a.dropout_enabled && a.train ? a.dropout_scale : 1.0f;
-    const int nz = x3 ? 2 : 1;
+    constexpr int nz = x3 ? 2 : 1;
 
-    // refresh the pair shadow of the kernels from the parameter arena (float4 items of this thread)
+    // the GEMM shadows of 4 consecutive elements W_l[k, c .. c+3] (arena offset o): the pair copy of W_l itself (M operand of
+    // dH_l, l >= 1) and the pair copy of W_l^T (M operand of the forward GEMM; layer 0: rows k < K0 only)
+    auto store_shadows = [&](int l, int k, int c, long long o, float4 w4) {
+        if (l >= 1) store_pair4(a.wpair + o, a.wz, w4, rnd, x3);
+        const int K = a.n[l];
+        if (k < K) {
+            float* t = a.wT[l] + (long long)c * K + k;
+            const long long tz = (long long)a.n[l + 1] * K;
+            store_pair1(t, tz, w4.x, rnd, x3);
+            store_pair1(t + K, tz, w4.y, rnd, x3);
+            store_pair1(t + 2 * K, tz, w4.z, rnd, x3);
+            store_pair1(t + 3 * K, tz, w4.w, rnd, x3);
+        }
+    };
+    // refresh the shadows from the parameter arena (float4 items of this thread)
     auto refresh_wpair = [&]() {
         for (int q = 0; q < a.nseg; ++q) {
             if (a.seg[q].kind != SEG_KERNEL) continue;
             const long long o0 = a.seg[q].off;
-            for (int i = (cta * kThreads + tid) * 4; i < a.seg[q].numel; i += G * kThreads * 4)
-            {
-                const float4 w4 = ldcg_f4(a.params + o0 + i);
-#pragma unroll
-                for (int r = 0; r < kRep; ++r) store_pair4(a.wpair + r * a.wrep + o0 + i, a.wz, w4, rnd, x3);
+            const int l = a.seg[q].layer, N = a.n[l + 1];
+            for (int i = (cta * kThreads + tid) * 4; i < a.seg[q].numel; i += G * kThreads * 4) {
+                const int k = i / N;
+                store_shadows(l, k, i - k * N, o0 + i, ldcg_f4(a.params + o0 + i));
             }
         }
     };
@@ -552,7 +565,7 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
         const float alpha = __fdiv_rn(__fmul_rn(a.lr, __fsqrt_rn(__fsub_rn(1.0f, b2pow))), __fsub_rn(1.0f, b1pow));
         const float omb1 = __fsub_rn(1.0f, a.beta1), omb2 = __fsub_rn(1.0f, a.beta2);
         // optimizer apply on 4 consecutive parameters at arena offset o with gradient g (TF ApplyAdam order / plain SGD)
-        auto apply4 = [&](long long o, const float (&g)[4], bool kernel) {
+        auto apply4 = [&](long long o, const float (&g)[4], int kl, int kk, int kc) {   // kl >= 0: element [kk, kc..] of kernel kl
             const float4 P = ldcg_f4(a.params + o);
             float pp[4] = {P.x, P.y, P.z, P.w};
             if (a.opt_kind == 0) {
@@ -568,10 +581,7 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
             }
             const float4 pnew = make_float4(pp[0], pp[1], pp[2], pp[3]);
             *reinterpret_cast<float4*>(a.params + o) = pnew;
-            if (kernel) {
-#pragma unroll
-                for (int r = 0; r < kRep; ++r) store_pair4(a.wpair + r * a.wrep + o, a.wz, pnew, rnd, x3);
-            }
+            if (kl >= 0) store_shadows(kl, kk, kc, o, pnew);
             if (a.grads) *reinterpret_cast<float4*>(a.grads + o) = make_float4(g[0], g[1], g[2], g[3]);
         };
         auto apply1 = [&](long long o, float g) {
@@ -599,21 +609,22 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                     const int row0 = j * CR;
                     if (warp == kProdWarp) {
                         // ---------- TMA producer: the group's X rows, then every weight tile of the chain in issue order
+                        if (tim && lane == 0) a.timing[tslot + 6] = (unsigned long long)clock64();
                         if (tc::elect_one()) {
                             const int nch0 = K0 / KCH;
                             tc::mbar_arrive_expect_tx(&bar_x, (uint32_t)(nch0 * CR * KCH * 4 * nz));
-                            for (int c = 0; c < nch0; ++c)
-                                for (int z = 0; z < nz; ++z)
-                                    tc::tma_load_3d(smem + kRingBytes + c * kBChunk + z * (CR * KCH * 4), &maps.xk[buf], &bar_x, c * KCH, row0, z);
+                            for (int c = 0; c < nch0; ++c)   // box = [plane][CR rows][32 k]: hi rows, then lo rows
+                                tc::tma_load_3d(smem + kRingBytes + c * kBChunk, &maps.xk[buf], &bar_x, c * KCH, row0, 0);
                         }
                         __syncwarp();
-                        const int rep = (j >> 3) % kRep;   // with the chunk rotation by j: 32 distinct (copy, offset) streams
                         for (int s = 0; s < nsegs; ++s) {
                             const SegD sd = s_seg[s];
                             const int l = sd.layer;
                             const bool fwd = sd.kind != S_DH;
-                            const int brow = a.n[l] < 128 ? a.n[l] : 128;   // dH: box rows of the wb map
-                            const uint32_t tx = (uint32_t)(fwd ? sd.ngrp * 4096 : brow * KCH * 4) * (uint32_t)nz;
+                            const int mw = fwd ? a.n[l + 1] : a.n[l];       // M extent of the weight operand
+                            const int brow = mw < 128 ? mw : 128;           // box rows of its map
+                            const uint32_t tx = (uint32_t)(brow * KCH * 4) * (uint32_t)nz;
+                            const CUtensorMap* mp = fwd ? &maps.wf[l] : &maps.wb[l];
                             for (int i0 = 0; i0 < sd.nch; ++i0) {
                                 const int i = (i0 + j) % sd.nch;   // chunk order rotated per row group (see the MMA warp)
                                 if (ring_n >= (uint32_t)kStages) tc::mbar_wait(&bar_empty[ring_s], ring_ph ^ 1);
@@ -621,13 +632,7 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                                 uint64_t* fb = &bar_full[ring_s];
                                 if (tc::elect_one()) {
                                     tc::mbar_arrive_expect_tx(fb, tx);
-                                    for (int z = 0; z < nz; ++z) {
-                                        if (fwd) {
-                                            for (int g = 0; g < sd.ngrp; ++g) tc::tma_load_4d(sA + z * A_BYTES + g * 4096, &maps.wf[l], fb, sd.mtile * 128 + g * 32, i * KCH, z, rep);
-                                        } else {
-                                            tc::tma_load_4d(sA + z * A_BYTES, &maps.wb[l], fb, i * KCH, sd.mtile * 128, z, rep);
-                                        }
-                                    }
+                                    tc::tma_load_3d(sA, mp, fb, i * KCH, sd.mtile * 128, 0);   // one box = [plane][brow rows][32 k]
 #ifdef PASS_DBG_SEG
                                     if (tim && s == PASS_DBG_SEG) {
                                         if (i0 == 0) a.timing[tslot + 2] = (unsigned long long)clock64();
@@ -660,10 +665,12 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                             if (s == 0) tc::mbar_wait(&bar_x, xjobs & 1);
                             tc::tc_fence_after();
                             const bool fwd = sd.kind != S_DH;
-                            const uint32_t idN2 = tc::make_idesc_tf32(128, 2 * CR, fwd ? 1 : 0, 0);
-                            const uint32_t idN1 = tc::make_idesc_tf32(128, CR, fwd ? 1 : 0, 0);
-                            const uint32_t a_hiw = fwd ? tc::kDescHiMN : tc::kDescHiK, a_low = fwd ? tc::kDescLoMN : tc::kDescLoK;
-                            const uint32_t a_k = fwd ? (1024u >> 4) : (32u >> 4);   // per k-step of 8
+                            constexpr uint32_t idN2 = tc::make_idesc_tf32(128, 2 * CR, 0, 0);
+                            constexpr uint32_t idN1 = tc::make_idesc_tf32(128, CR, 0, 0);
+                            constexpr uint32_t a_hiw = tc::kDescHiK, a_low = tc::kDescLoK;
+                            constexpr uint32_t a_k = 32u >> 4;   // per k-step of 8
+                            const int mw = fwd ? a.n[sd.layer + 1] : a.n[sd.layer];
+                            const uint32_t lo_off = (uint32_t)((mw < 128 ? mw : 128) * KCH * 4) >> 4;   // the lo plane follows the hi box
                             const uint32_t bbase = ((smem_base + (uint32_t)kRingBytes + (uint32_t)sd.bsrc * kActBytes) >> 4) | tc::kDescLoK;
                             const uint32_t dcol = tmem + (cs & 1u) * 32u;
                             uint32_t acc = 0;
@@ -680,7 +687,7 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
 #else
                                     if (tim && s == 0 && i0 == 0) a.timing[tslot + 4] = (unsigned long long)clock64();
 #endif
-                                    const uint32_t aw = st | a_low, alw = aw + (A_BYTES >> 4);
+                                    const uint32_t aw = st | a_low, alw = aw + lo_off;
                                     const uint32_t bw = bbase + (uint32_t)i * (kBChunk >> 4);
                                     if (x3) {
 #pragma unroll
@@ -967,7 +974,6 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                             float* s_g = reinterpret_cast<float*>(scratch + 5120);      // [32] dE_d[dom][k]
                             float* s_eo = s_g + 32;                                     // [32] E_d[dom][k] before the apply
                             float* s_en = s_g + 64;                                     // [32] ... after
-                            double* red = reinterpret_cast<double*>(scratch + 16384);
                             const int ncol4 = n1 >> 2, nsl = kWorkers / ncol4;
                             int kb, ke;
                             dom_rows(a, J.m_tile, kb, ke);
@@ -995,23 +1001,12 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                                     *reinterpret_cast<float4*>(s_db0 + tid * 4) = t4;
                                     if (J.m_tile == 0) {   // b_0
                                         const float g4[4] = {t4.x, t4.y, t4.z, t4.w};
-                                        apply4(a.off_b[0] + tid * 4, g4, false);
+                                        apply4(a.off_b[0] + tid * 4, g4, -1, 0, 0);
                                     }
                                 }
                             }
-                            if (J.m_tile == 0) {
-                                double sq = 0.0;
-                                for (int i = tid; i < a.n_domain * a.dd; i += kWorkers) { const double e = ldcg_f(a.params + a.off_Ed + i); sq += e * e; }
-#pragma unroll
-                                for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-                                if (lane == 0) red[warp] = sq;
-                            }
                             worker_sync();
-                            if (J.m_tile == 0 && tid == 0) {
-                                double tot = 0.0;
-                                for (int w = 0; w < kWorkerWarps; ++w) tot += red[w];
-                                *a.ed_sq = tot;
-                            }
+                            WSTAMP(11);
                             float* W0dom = a.params + a.off_W[0] + (long long)K0 * n1;
                             for (int k = kb + warp; k < ke; k += kWorkerWarps) {
                                 const float* wr = W0dom + (long long)k * n1;
@@ -1044,7 +1039,13 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                                 s_eo[tid] = pe;
                                 s_en[tid] = apply1(o, __fadd_rn(__fmul_rn(2.0f * a.l2_emb, pe), s_g[tid]));
                             }
+                            WSTAMP(12);
                             worker_sync();
+                            if (tid == 0) {   // this job's share of |E_d|^2 (pre-update values, for the loss)
+                                double sq = 0.0;
+                                for (int k = 0; k < ke - kb; ++k) sq += (double)s_eo[k] * (double)s_eo[k];
+                                a.ed_sq[1 + J.m_tile] = sq;
+                            }
                             for (int c = tid; c < n1; c += kWorkers) {
                                 const long long o0 = a.off_W[0] + (long long)(K0 + kb) * n1 + c;
                                 const float dbc = s_db0[c];
@@ -1079,6 +1080,7 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                                 a.fold_part[J.m_tile * n1 + c] = fp;
                             }
                             worker_sync();
+                            WSTAMP(13);
                         }
                         continue;
                     }
@@ -1109,14 +1111,31 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                                 if (lane == 0) apply1(a.off_g, s);
                             }
                             // the rows of E_d other than the batch's domain: l2 term only
-                            for (int i = tid; i < a.n_domain * a.dd; i += kWorkers)
-                                if (i / a.dd != pd.dom) apply1(a.off_Ed + i, __fmul_rn(2.0f * a.l2_emb, ldcg_f(a.params + a.off_Ed + i)));
+                            double sq = 0.0;
+                            for (int i = tid; i < a.n_domain * a.dd; i += kWorkers) {
+                                if (i / a.dd == pd.dom) continue;
+                                const float pe = ldcg_f(a.params + a.off_Ed + i);
+                                sq += (double)pe * (double)pe;
+                                apply1(a.off_Ed + i, __fmul_rn(2.0f * a.l2_emb, pe));
+                            }
+                            double* red = reinterpret_cast<double*>(scratch + 16384);
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+                            if (lane == 0) red[warp] = sq;
+                            worker_sync();
+                            if (tid == 0) {
+                                double tot = 0.0;
+                                for (int w = 0; w < kWorkerWarps; ++w) tot += red[w];
+                                a.ed_sq[0] = tot;   // + the domain jobs' shares of the batch's own row
+                            }
                             if (warp == 1) {
                                 const double bs = warp_group_sum_d(a.loss_part + buf * kMaxGroups, ngroups, lane);
                                 // |E_d|^2 of this mini-batch is published by domain job 0 in this same phase: the loss is
                                 // completed after the barrier (below)
                                 if (lane == 0) a.loss_part[2 * kMaxGroups + buf] = bs;
                             }
+                            worker_sync();
+                            WSTAMP(14);
                         }
                         continue;
                     }
@@ -1217,6 +1236,7 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                         // publish: the release covers the partial-tile stores of every worker (ordered by the barrier)
                         worker_sync();
                         if (tid == 0) red_release_add_u32(a.tile_ctr + J.gtile, 1u);
+                        WSTAMP(8);
                     }
                     ++njob;
                 }
@@ -1236,6 +1256,7 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                             while (ld_acquire_u32(a.tile_ctr + J.gtile) < tile_target) {}
                         }
                         worker_sync();
+                        WSTAMP(9);
                         const int l = J.layer, N = a.n[l + 1], bn = J.bn, bn4 = bn >> 2;
                         const int tile = J.m_tile * J.NT + J.n_tile;
                         const int vrows = a.n[l] - J.m_tile * 128 < 128 ? a.n[l] - J.m_tile * 128 : 128;
@@ -1252,8 +1273,9 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
 #pragma unroll
                             for (int z = 0; z < kMaxSplit; ++z)
                                 if (z < J.S) { g[0] += q4[z].x; g[1] += q4[z].y; g[2] += q4[z].z; g[3] += q4[z].w; }
-                            apply4(a.off_W[l] + (long long)(J.m_tile * 128 + r) * N + J.n_tile * bn + c, g, true);
+                            apply4(a.off_W[l] + (long long)(J.m_tile * 128 + r) * N + J.n_tile * bn + c, g, l, J.m_tile * 128 + r, J.n_tile * bn + c);
                         }
+                        WSTAMP(10);
                     }
                 }
                 if (a.opt_kind == 0) {
@@ -1274,7 +1296,12 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
             double bs;
             if (a.train) bs = __ldcg(a.loss_part + 2 * kMaxGroups + buf);
             else bs = warp_group_sum_d(a.loss_part + buf * kMaxGroups, ngroups, lane);
-            if (lane == 0) pd.losses[step] = (float)(bs / (double)rows + (double)a.frozen_reg + (double)a.l2_emb * __ldcg(a.ed_sq));
+            if (lane == 0) {
+                double esq = __ldcg(a.ed_sq);
+                if (a.train)
+                    for (int q = 0; q < kDomJobs; ++q) esq += __ldcg(a.ed_sq + 1 + q);
+                pd.losses[step] = (float)(bs / (double)rows + (double)a.frozen_reg + (double)a.l2_emb * esq);
+            }
         }
     }
 
@@ -1333,7 +1360,7 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
 // ---- workspace layout ---------------------------------------------------------------------------------------------
 struct PassWs {
     size_t bar, hist, X[2], y[2], H[MAMDR_MAX_LAYERS], dZ[MAMDR_MAX_LAYERS], partials[MAMDR_MAX_LAYERS], db_part[MAMDR_MAX_LAYERS];
-    size_t dw_part, dg_part, loss_part, fold_part, ed_sq, wpair, wz, total;
+    size_t dw_part, dg_part, loss_part, fold_part, ed_sq, wpair, wz, wT[MAMDR_MAX_LAYERS], total;
 };
 
 inline PassWs pass_ws(const mamdr_mlp_desc& d, int B) {
@@ -1365,9 +1392,10 @@ inline PassWs pass_ws(const mamdr_mlp_desc& d, int B) {
     w.dg_part = take((size_t)ng * 4);
     w.loss_part = take((size_t)(2 * kMaxGroups + 2) * 8);
     w.fold_part = take((size_t)kDomJobs * d.hidden[0] * 4);
-    w.ed_sq = take(8);
+    w.ed_sq = take((size_t)(1 + kDomJobs) * 8);   // eval: [0] = |E_d|^2; training: [0] = rows other than the batch's, [1 + q] = domain job q's share
     w.wz = ((size_t)(d.arena_floats - d.off_domain_emb) + 31) / 32 * 32;   // floats between the two planes of the kernel shadow
-    w.wpair = take((size_t)kRep * 2 * w.wz * 4);                           // dense span of the arena only, kRep copies
+    w.wpair = take(2 * w.wz * 4);                                          // dense span of the arena only
+    for (int l = 0; l < L; ++l) w.wT[l] = take((size_t)2 * d.hidden[l] * (l == 0 ? K0 : d.hidden[l - 1]) * 4);
     w.total = off;
     return w;
 }
@@ -1396,7 +1424,8 @@ static int pass_supported(mamdr_ctx* ctx, const mamdr_mlp_desc* d, int max_batch
 }
 
 int mamdr_pass_init_kernels(mamdr_ctx* ctx) {
-    MAMDR_CUDA_OK(ctx, cudaFuncSetAttribute(pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
+    MAMDR_CUDA_OK(ctx, cudaFuncSetAttribute(pass_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
+    MAMDR_CUDA_OK(ctx, cudaFuncSetAttribute(pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
     return MAMDR_OK;
 }
 
@@ -1438,7 +1467,7 @@ static int launch_program(mamdr_ctx* ctx, const MapTable& mp, const PassArgs& a,
     MAMDR_CUDA_OK(ctx, cudaMemsetAsync(a.bar, 0, kBarBytes, st));
     const size_t smem = smem_bytes();
     void* kargs[] = {(void*)&mp, (void*)&a};
-    const void* fn = (const void*)pass_kernel;
+    const void* fn = a.passes == 3 ? (const void*)pass_kernel<3> : (const void*)pass_kernel<1>;
     MAMDR_CUDA_OK(ctx, cudaLaunchCooperativeKernel(fn, dim3(ctx->sm_count), dim3(kThreads), kargs, smem, st));
     return MAMDR_OK;
 }
@@ -1503,7 +1532,7 @@ static int run_pass(mamdr_ctx* ctx, const mamdr_mlp_desc* d, const mamdr_pass* p
     a.ed_sq = (double*)(ws + w.ed_sq);
     a.wpair = (float*)(ws + w.wpair) - d->off_domain_emb;   // indexed with arena offsets
     a.wz = (long long)w.wz;
-    a.wrep = 2 * (long long)w.wz;
+    for (int l = 0; l < L; ++l) a.wT[l] = (float*)(ws + w.wT[l]);
     a.hist = (int*)(ws + w.hist);
     a.bar = (unsigned int*)(ws + w.bar);
     a.tile_ctr = a.bar + 16;
@@ -1526,19 +1555,20 @@ static int run_pass(mamdr_ctx* ctx, const mamdr_mlp_desc* d, const mamdr_pass* p
     memset(&mp, 0, sizeof(mp));
     bool ok = true;
     // every GEMM operand is a pair array; the lo plane lies Bp * width floats (kernels: wz floats) behind the hi plane
-    const float* wsrc = a.wpair;   // M operands of the chain GEMMs: the pair shadow of the kernels
+    const float* wsrc = a.wpair;   // M operands of the dH GEMMs: the pair shadow of the kernels
+    const uint32_t nzp = a.passes == 3 ? 2 : 1;   // planes per TMA box
     for (int b = 0; b < 2; ++b) {
         const uint64_t z = (uint64_t)Bp * a.n[0];
-        ok = ok && mlptc::pair_kmajor_map(ctx, &mp.xk[b], a.X[b], Bp, a.n[0], CR, z) && mlptc::pair_mnmajor_map(ctx, &mp.xmn[b], a.X[b], Bp, a.n[0], z);
+        ok = ok && mlptc::pair_kmajor_map(ctx, &mp.xk[b], a.X[b], Bp, a.n[0], CR, z, nzp) && mlptc::pair_mnmajor_map(ctx, &mp.xmn[b], a.X[b], Bp, a.n[0], z);
     }
     for (int l = 0; l < L; ++l) {
         const uint64_t zh = (uint64_t)Bp * a.n[l], zd = (uint64_t)Bp * a.n[l + 1];
         if (l >= 1) {
             ok = ok && mlptc::pair_mnmajor_map(ctx, &mp.hmn[l], a.H[l], Bp, a.n[l], zh);
-            ok = ok && mlptc::pair_kmajor_map(ctx, &mp.wb[l], wsrc + d->off_kernel[l], a.n[l], a.n[l + 1], a.n[l] < 128 ? a.n[l] : 128, (uint64_t)a.wz, kRep, (uint64_t)a.wrep);
+            ok = ok && mlptc::pair_kmajor_map(ctx, &mp.wb[l], wsrc + d->off_kernel[l], a.n[l], a.n[l + 1], a.n[l] < 128 ? a.n[l] : 128, (uint64_t)a.wz, nzp);
         }
         ok = ok && mlptc::pair_mnmajor_map(ctx, &mp.dzmn[l], a.dZ[l], Bp, a.n[l + 1], zd);
-        ok = ok && mlptc::pair_mnmajor_map(ctx, &mp.wf[l], wsrc + d->off_kernel[l], a.n[l], a.n[l + 1], (uint64_t)a.wz, kRep, (uint64_t)a.wrep);
+        ok = ok && mlptc::pair_kmajor_map(ctx, &mp.wf[l], a.wT[l], a.n[l + 1], a.n[l], a.n[l + 1] < 128 ? a.n[l + 1] : 128, (uint64_t)a.n[l + 1] * a.n[l], nzp);
     }
     MAMDR_REQUIRE(ctx, ok, MAMDR_E_CUDA, "cuTensorMapEncodeTiled failed (pass kernel)");
 

@@ -65,15 +65,6 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
-// 4D tile load: (c0 = innermost element, c1 = row, c2 = plane of a pair array, c3 = replica)
-__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
-            smem_u32(smem_dst)),
-        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
-
 // One elected lane of a fully converged warp.  TMA / tcgen05.mma take their descriptors from UNIFORM registers: when the
 // whole warp runs the issue loop and only the instruction itself is predicated on the elected lane, the operands stay in
 // uniform registers; under `if (lane == 0)` every instruction pays an R2UR "waterfall" (measured 130-200 cycles per MMA
@@ -231,16 +222,16 @@ inline bool make_tmap_2d_f32(CUtensorMap* out, const float* base, uint64_t rows,
               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 // pair array [2][rows][cols] (plane 0 = hi, plane 1 = lo, `zstride` floats apart): 3-D map, box = [1, box_rows, box_cols]
-// with reps > 1 the map is 4-D: `reps` copies of the pair array, `rstride` floats apart
+// box_planes = 2 loads both planes with ONE instruction: shared memory then holds [plane][box_rows][box_cols]
 inline bool make_tmap_pair_f32(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint64_t zstride,
-                               uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle swz, uint64_t reps = 1, uint64_t rstride = 0) {
+                               uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle swz, uint32_t box_planes = 1) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return false;
-    cuuint64_t dims[4] = {cols, rows, 2, reps};
-    cuuint64_t strides[3] = {ld * sizeof(float), zstride * sizeof(float), rstride * sizeof(float)};
-    cuuint32_t box[4] = {box_cols, box_rows, 1, 1};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
-    return fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, reps > 1 ? 4 : 3, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+    cuuint64_t dims[3] = {cols, rows, 2};
+    cuuint64_t strides[2] = {ld * sizeof(float), zstride * sizeof(float)};
+    cuuint32_t box[3] = {box_cols, box_rows, box_planes};
+    cuuint32_t estr[3] = {1, 1, 1};
+    return fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 }  // namespace tc

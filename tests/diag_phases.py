@@ -43,11 +43,12 @@ def main(prec="tf32"):
         print("%-16s start %.2f  work max %.2f med %.2f us  barrier %.2f" % (names[p], (st.min() - base_t) / 1e3, busy.max(), np.median(busy), (nxt - en.max()) / 1e3))
         if p < 2:
             # the 3 busiest CTAs: clock64 deltas from phase start (us)
-            for cta in np.argsort(-busy)[:3]:
+            pick = list(np.argsort(-busy)[:3]) + ([0, 5, 16] if p == 1 else [])   # dW phase: + a domain job, the column-sum job
+            for cta in pick:
                 c0 = t[s, p, cta, 7]
                 rel = [(t[s, p, cta, k] - c0) / GHZ / 1e3 if t[s, p, cta, k] > 0 else float('nan') for k in (2, 3, 4, 5, 6)]
-                ep = " ".join("%.2f" % ((t[s, p, cta, k] - c0) / GHZ / 1e3) for k in range(8, 16) if t[s, p, cta, k] > 0)
-                print("    cta %3d busy %.2f us | tma first-issue %.2f all-issued %.2f | mma first-full %.2f all-issued %.2f | done-seen %.2f | chain segment epilogues done %s" % ((cta, busy[cta]) + tuple(rel) + (ep,)))
+                ep = " ".join("%d:%.2f" % (k, (t[s, p, cta, k] - c0) / GHZ / 1e3) for k in range(8, 16) if t[s, p, cta, k] > 0)
+                print("    cta %3d busy %.2f us | tma first-issue %.2f all-issued %.2f | mma first-full %.2f all-issued %.2f | done-seen %.2f | stamps (chain: segment epilogues done; dW: 8 partial published, 9 tile complete, 10 slice applied; domain job: 11 db0, 12 E_d applied, 13 done; 14 column-sum job done) %s" % ((cta, busy[cta]) + tuple(rel) + (ep,)))
 
 
 if __name__ == "__main__":
