@@ -738,7 +738,7 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                             const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (cs & 1u) * 32u + (uint32_t)(hf * 8);
                             // this thread's 8 values of the N operand chunk f / 32: row line hf * 8 + i, swizzled 16-byte chunk
                             unsigned char* bdst = smem + kRingBytes + sd.bdst * kActBytes + (f >> 5) * kBChunk + (hf * 8) * 128 + (lane & 3) * 4;
-                            float bias = 0.f, wd = 0.f;
+                            float bias = 0.f, wd = 0.f, gbias = 0.f, ylab = 0.f;
                             uint32_t keep = 0xffu;
                             if (sd.kind != S_DH) {
                                 // ---- prelude in the shadow of the MMAs: effective bias, dropout keep bits
@@ -757,7 +757,13 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                                 } else if (on) {
                                     bias = ldcg_f(a.params + a.off_b[l] + f);
                                 }
-                                if (sd.kind == S_HEAD && on) wd = ldcg_f(a.params + a.off_w + f);
+                                if (sd.kind == S_HEAD) {
+                                    if (on) wd = ldcg_f(a.params + a.off_w + f);
+                                    if (warp == 0) {   // the row lanes of the sigmoid-BCE head: label and global bias up front
+                                        gbias = ldcg_f(a.params + a.off_g);
+                                        if (lane < CR && row0 + lane < rows) ylab = a.y[buf][row0 + lane];
+                                    }
+                                }
                                 if (dp.enabled && on) {
                                     // the 4 lanes of a feature quad share one Philox counter per row: each lane draws two rows' words
                                     DropoutParams dq = dp;
@@ -841,9 +847,9 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                                     if (hvalid) {
                                         float z = 0.f;
                                         for (int qq = 0; qq < sd.ngrp; ++qq) z += s_zp[((lane >> 3) * 4 + qq) * 8 + (lane & 7)];
-                                        const float sgm = z + ldcg_f(a.params + a.off_g);
+                                        const float sgm = z + gbias;
                                         pv = 1.0f / (1.0f + expf(-sgm));
-                                        yv = a.y[buf][hrow];
+                                        yv = ylab;
                                         if (a.train) dsv0 = (fabsf(sgm) <= MAMDR_LOGIT_CLIP) ? __fdiv_rn(__fsub_rn(pv, yv), (float)rows) : 0.f;
                                     }
                                     if (lane < CR) s_ds[lane] = dsv0;
@@ -1218,7 +1224,10 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                         const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
                         const int tile = J.m_tile * J.NT + J.n_tile;
                         const int half = J.bn >> 1;   // columns per thread: 32 (bn = 64) or 16 (bn = 32)
-                        float* mine = a.partials[l] + (((long long)J.z * J.tiles + tile) * 128 + rloc) * J.bn + hf * half;
+                        float* ptile = a.partials[l] + ((long long)J.z * J.tiles + tile) * 128 * J.bn;
+                        // last job of this CTA in the phase: the ring is idle -> transpose through shared memory for coalesced stores
+                        const bool staged = j + G >= njobs;
+                        float* s_p = reinterpret_cast<float*>(smem);   // [128][bn + 4]
                         for (int n0 = 0; n0 < half; n0 += 16) {
                             float vv[16], v2[16];
                             tc::tmem_ld16(tlane + hf * half + n0, vv);
@@ -1228,11 +1237,20 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                                 float4 o4;
                                 if (x3) o4 = make_float4(vv[jx] + v2[jx], vv[jx + 1] + v2[jx + 1], vv[jx + 2] + v2[jx + 2], vv[jx + 3] + v2[jx + 3]);
                                 else o4 = make_float4(vv[jx], vv[jx + 1], vv[jx + 2], vv[jx + 3]);
-                                __stcg(reinterpret_cast<float4*>(mine + n0 + jx), o4);
+                                if (staged) *reinterpret_cast<float4*>(s_p + rloc * (J.bn + 4) + hf * half + n0 + jx) = o4;
+                                else __stcg(reinterpret_cast<float4*>(ptile + (long long)rloc * J.bn + hf * half + n0 + jx), o4);
                             }
                         }
                         tc::tc_fence_before();
                         tc::mbar_arrive(&bar_tfree);
+                        if (staged) {
+                            worker_sync();
+                            const int bn4 = J.bn >> 2;
+                            for (int idx = tid; idx < 128 * bn4; idx += kWorkers) {
+                                const int r = idx / bn4, c = (idx - r * bn4) * 4;
+                                __stcg(reinterpret_cast<float4*>(ptile + (long long)r * J.bn + c), *reinterpret_cast<const float4*>(s_p + r * (J.bn + 4) + c));
+                            }
+                        }
                         // publish: the release covers the partial-tile stores of every worker (ordered by the barrier)
                         worker_sync();
                         if (tid == 0) red_release_add_u32(a.tile_ctr + J.gtile, 1u);
@@ -1263,18 +1281,53 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                         const int rper = cdiv(128, J.S);
                         const int r_beg = J.z * rper, r_end = r_beg + rper < vrows ? r_beg + rper : vrows;
                         const long long zstride = (long long)J.tiles * 128 * bn;
-                        for (int idx = tid; idx < (r_end - r_beg) * bn4; idx += kWorkers) {
-                            const int r = r_beg + idx / bn4, c = (idx - (idx / bn4) * bn4) * 4;
+                        const int nr = r_end - r_beg;
+                        float* s_t = reinterpret_cast<float*>(smem);   // [nr][bn + 1] updated values (the ring is idle: every job of this CTA is done)
+                        for (int idx = tid; idx < nr * bn4; idx += kWorkers) {
+                            const int rr = idx / bn4, r = r_beg + rr, c = (idx - rr * bn4) * 4;
                             const float* src = a.partials[l] + ((long long)tile * 128 + r) * bn + c;
+                            const long long o = a.off_W[l] + (long long)(J.m_tile * 128 + r) * N + J.n_tile * bn + c;
+                            // every load of the item first: one round trip to L2
                             float4 q4[kMaxSplit];
 #pragma unroll
                             for (int z = 0; z < kMaxSplit; ++z) q4[z] = z < J.S ? ldcg_f4(src + z * zstride) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            const float4 P = ldcg_f4(a.params + o);
+                            float4 M = make_float4(0.f, 0.f, 0.f, 0.f), V = M;
+                            if (a.opt_kind == 0) { M = ldcg_f4(a.m + o); V = ldcg_f4(a.v + o); }
                             float g[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                             for (int z = 0; z < kMaxSplit; ++z)
                                 if (z < J.S) { g[0] += q4[z].x; g[1] += q4[z].y; g[2] += q4[z].z; g[3] += q4[z].w; }
-                            apply4(a.off_W[l] + (long long)(J.m_tile * 128 + r) * N + J.n_tile * bn + c, g, l, J.m_tile * 128 + r, J.n_tile * bn + c);
+                            float pp[4] = {P.x, P.y, P.z, P.w};
+                            if (a.opt_kind == 0) {
+                                float mm[4] = {M.x, M.y, M.z, M.w}, vv[4] = {V.x, V.y, V.z, V.w};
+#pragma unroll
+                                for (int t = 0; t < 4; ++t) adam1(pp[t], mm[t], vv[t], g[t], alpha, omb1, omb2, a.eps);
+                                *reinterpret_cast<float4*>(a.m + o) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+                                *reinterpret_cast<float4*>(a.v + o) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+                            } else {
+#pragma unroll
+                                for (int t = 0; t < 4; ++t) pp[t] = __fsub_rn(pp[t], __fmul_rn(g[t], a.lr));
+                            }
+                            const float4 pnew = make_float4(pp[0], pp[1], pp[2], pp[3]);
+                            *reinterpret_cast<float4*>(a.params + o) = pnew;
+                            if (l >= 1) store_pair4(a.wpair + o, a.wz, pnew, rnd, x3);
+                            if (a.grads) *reinterpret_cast<float4*>(a.grads + o) = make_float4(g[0], g[1], g[2], g[3]);
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) s_t[rr * (bn + 1) + c + t] = pp[t];
                         }
+                        worker_sync();
+                        {
+                            // W_l^T[col, k]: consecutive lanes walk the k rows of the slice -> contiguous runs per column
+                            const int K = a.n[l];
+                            float* wt = a.wT[l] + (long long)(J.n_tile * bn) * K + J.m_tile * 128 + r_beg;
+                            const long long tz = (long long)N * K;
+                            for (int idx = tid; idx < nr * bn; idx += kWorkers) {
+                                const int cc = idx / nr, rr = idx - cc * nr;
+                                store_pair1(wt + (long long)cc * K + rr, tz, s_t[rr * (bn + 1) + cc], rnd, x3);
+                            }
+                        }
+                        worker_sync();   // the next job of the sweep reuses the transpose buffer
                         WSTAMP(10);
                     }
                 }
