@@ -36,10 +36,10 @@
 // `if (lane == 0)` every instruction pays an R2UR waterfall: 130-200 cycles per MMA instead of 50,
 // profiles/r2_probe_mainloop.txt).
 //
-// 3xTF32 (MAMDR_PREC_TF32X3): every GEMM operand exists as a PAIR: plane 0 = the fp32 value (the tensor core
-// truncates it to its tf32 "hi" part), plane 1 = lo = rn_tf32(x - hi), written by whoever produces the operand.  The
+// 3xTF32 (MAMDR_PREC_TF32X3): every GEMM operand exists as a PAIR: plane 0 = hi = rn_tf32(x), plane 1 = lo =
+// rn_tf32(x - hi), written by whoever produces the operand (hi rounded to NEAREST: |lo| <= 2^-12 |x|).  The
 // N operand is [hi rows | lo rows], so a k-step is two MMAs: W_hi.[act_hi | act_lo] (two accumulator halves) and
-// W_lo.act_hi (first half); the epilogue adds the halves.  Dropped: lo.lo (2^-22 relative).
+// W_lo.act_hi (first half); the epilogue adds the halves.  Dropped: lo.lo (2^-24 relative: fp32-level products).
 //
 // The domain embedding row is the same for every sample of a batch (utils/dataset.py:73-99: per-domain
 // datasets), so X is only [E_u | E_i] and the domain block of layer 0 is folded into its bias in fp32
@@ -81,7 +81,11 @@ constexpr int kDomJobs = 16;                  // the domain block (gradient GEMV
 constexpr int kMaxGroups = 8192 / CR;         // row groups per mini-batch (batch <= 8192)
 constexpr int kMaxSegs = 4 * MAMDR_MAX_LAYERS;
 constexpr int kBarBytes = 64 + 4 * 8 * MAMDR_MAX_LAYERS;   // grid-barrier counter + one counter per dW tile (<= 8 per layer)
-constexpr uint32_t kTmemCols = 128;           // dW: one accumulator of up to 2 x 64 columns; chain: two slots of 32
+constexpr int kAccGroups = 4;                 // chain: K chunks of a GEMM are spread over this many TMEM accumulators, summed with
+                                              // round-to-nearest adds in the epilogue (the tensor core's own fp32 accumulation
+                                              // truncates: fewer dependent adds on smaller partial sums per accumulator)
+constexpr uint32_t kSlotCols = kAccGroups * 2 * CR;   // 128 columns per accumulator slot
+constexpr uint32_t kTmemCols = 2 * kSlotCols; // chain: two slots; dW: one accumulator of up to 2 x 64 columns
 
 enum { J_NONE = 0, J_DW, J_DOM, J_RED };
 enum { S_FWD = 0, S_HEAD, S_DH };
@@ -258,16 +262,25 @@ __device__ __forceinline__ float rn_tf32(float x) {
     return __uint_as_float(r);
 }
 __device__ __forceinline__ float4 rn_tf32_4(float4 v) { return make_float4(rn_tf32(v.x), rn_tf32(v.y), rn_tf32(v.z), rn_tf32(v.w)); }
-__device__ __forceinline__ float4 tf32_lo_4(float4 v) { return make_float4(tc::tf32_lo(v.x), tc::tf32_lo(v.y), tc::tf32_lo(v.z), tc::tf32_lo(v.w)); }
+// 3xTF32 split of x: hi = rn_tf32(x) (the tensor core's own truncation of a raw fp32 operand would leave |lo| < 2^-11 |x| and
+// a dropped lo.lo term of 2^-22; rounding hi to NEAREST halves |lo|, so the dropped term is 2^-24: fp32-level products),
+// lo = rn_tf32(x - hi) (x - hi is exact in fp32)
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+    hi = rn_tf32(x);
+    lo = rn_tf32(x - hi);
+}
 
-// store 4 consecutive elements of a pair array: plane 0 = v (pre-rounded in the 1-pass mode), plane 1 = lo (3-pass mode)
+// store 4 consecutive elements of a pair array: plane 0 = hi (the pre-rounded value in both tensor-core modes), plane 1 = lo
+// (3-pass mode only)
 __device__ __forceinline__ void store_pair4(float* hi, long long z, float4 v, bool rnd, bool x3) {
-    *reinterpret_cast<float4*>(hi) = rnd ? rn_tf32_4(v) : v;
-    if (x3) *reinterpret_cast<float4*>(hi + z) = tf32_lo_4(v);
+    const float4 h = (rnd || x3) ? rn_tf32_4(v) : v;
+    *reinterpret_cast<float4*>(hi) = h;
+    if (x3) *reinterpret_cast<float4*>(hi + z) = rn_tf32_4(make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w));
 }
 __device__ __forceinline__ void store_pair1(float* hi, long long z, float v, bool rnd, bool x3) {
-    *hi = rnd ? rn_tf32(v) : v;
-    if (x3) hi[z] = tc::tf32_lo(v);
+    const float h = (rnd || x3) ? rn_tf32(v) : v;
+    *hi = h;
+    if (x3) hi[z] = rn_tf32(v - h);
 }
 
 __device__ __forceinline__ void adam1(float& p, float& m, float& v, float g, float alpha, float omb1, float omb2, float eps) {
@@ -672,8 +685,7 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                             const int mw = fwd ? a.n[sd.layer + 1] : a.n[sd.layer];
                             const uint32_t lo_off = (uint32_t)((mw < 128 ? mw : 128) * KCH * 4) >> 4;   // the lo plane follows the hi box
                             const uint32_t bbase = ((smem_base + (uint32_t)kRingBytes + (uint32_t)sd.bsrc * kActBytes) >> 4) | tc::kDescLoK;
-                            const uint32_t dcol = tmem + (cs & 1u) * 32u;
-                            uint32_t acc = 0;
+                            const uint32_t dslot = tmem + (cs & 1u) * kSlotCols;
                             for (int i0 = 0; i0 < sd.nch; ++i0) {
                                 // every CTA streams the same weights: starting the K loop at chunk j mod nch keeps the CTAs from
                                 // hammering the same L2 lines in lock-step (the K order of a row group is fixed: deterministic)
@@ -689,12 +701,16 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
 #endif
                                     const uint32_t aw = st | a_low, alw = aw + lo_off;
                                     const uint32_t bw = bbase + (uint32_t)i * (kBChunk >> 4);
+                                    // chunk i0 accumulates into group i0 mod kAccGroups of the slot
+                                    const uint32_t dcol = dslot + (uint32_t)(i0 & (kAccGroups - 1)) * (2 * CR);
+                                    uint32_t acc = i0 < kAccGroups ? 0u : 1u;
                                     if (x3) {
 #pragma unroll
                                         for (int k = 0; k < KCH / 8; ++k) {
-                                            // W.[act | act_lo] -> columns [0, CR) and [CR, 2 CR);  W_lo.act -> columns [0, CR)
+                                            // W.[act | act_lo] -> columns [0, CR) and [CR, 2 CR);  W_lo.act -> columns [CR, 2 CR) as well:
+                                            // the first half only ever sees the large hi.hi products
                                             tc::mma_tf32(dcol, tc::desc_words(aw + k * a_k, a_hiw), tc::desc_words(bw + k * 2u, tc::kDescHiK), idN2, acc);
-                                            tc::mma_tf32(dcol, tc::desc_words(alw + k * a_k, a_hiw), tc::desc_words(bw + k * 2u, tc::kDescHiK), idN1, 1u);
+                                            tc::mma_tf32(dcol + CR, tc::desc_words(alw + k * a_k, a_hiw), tc::desc_words(bw + k * 2u, tc::kDescHiK), idN1, 1u);
                                             acc = 1;
                                         }
                                     } else {
@@ -735,7 +751,7 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                             const int l = sd.layer;
                             const int f = sd.mtile * 128 + wt;            // output feature of this thread
                             const bool on = q < sd.ngrp;                  // warp-uniform: the tile has this lane quarter
-                            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (cs & 1u) * 32u + (uint32_t)(hf * 8);
+                            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (cs & 1u) * kSlotCols + (uint32_t)(hf * 8);
                             // this thread's 8 values of the N operand chunk f / 32: row line hf * 8 + i, swizzled 16-byte chunk
                             unsigned char* bdst = smem + kRingBytes + sd.bdst * kActBytes + (f >> 5) * kBChunk + (hf * 8) * 128 + (lane & 3) * 4;
                             float bias = 0.f, wd = 0.f, gbias = 0.f, ylab = 0.f;
@@ -789,8 +805,30 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                             tc::tc_fence_after();
                             float vv[8], v2[8];
                             if (on) {
-                                tc::tmem_ld8(taddr, vv);
-                                if (x3) tc::tmem_ld8(taddr + CR, v2);
+                                // sum of the accumulator groups, (g0 + g1) + (g2 + g3), with round-to-nearest adds
+                                const int ng = sd.nch < kAccGroups ? sd.nch : kAccGroups;
+                                float t0[8], t1[8];
+#pragma unroll
+                                for (int part = 0; part < (x3 ? 2 : 1); ++part) {
+                                    float* dst = part == 0 ? vv : v2;
+                                    const uint32_t ta = taddr + (part == 0 ? 0u : (uint32_t)CR);
+                                    tc::tmem_ld8(ta, dst);
+                                    if (ng > 1) {
+                                        tc::tmem_ld8(ta + 2 * CR, t0);
+#pragma unroll
+                                        for (int i = 0; i < 8; ++i) dst[i] += t0[i];
+                                    }
+                                    if (ng > 2) {
+                                        tc::tmem_ld8(ta + 4 * CR, t0);
+                                        if (ng > 3) {
+                                            tc::tmem_ld8(ta + 6 * CR, t1);
+#pragma unroll
+                                            for (int i = 0; i < 8; ++i) t0[i] += t1[i];
+                                        }
+#pragma unroll
+                                        for (int i = 0; i < 8; ++i) dst[i] += t0[i];
+                                    }
+                                }
                             }
                             tc::tc_fence_before();
 
@@ -807,8 +845,7 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                                         h[i] = hh;
                                         mb |= (hh > 0.f ? 1u : 0u) << i;
                                         unsigned char* d = bdst + i * 128 + ((((lane >> 2) ^ i) & 7) << 4);
-                                        *reinterpret_cast<float*>(d) = rnd ? rn_tf32(hh) : hh;
-                                        if (x3) *reinterpret_cast<float*>(d + CR * 128) = tc::tf32_lo(hh);
+                                        store_pair1(reinterpret_cast<float*>(d), CR * 32, hh, rnd, x3);
                                     }
                                     s_mask[sd.mseg * 256 + tid] = (unsigned char)mb;
                                 }
@@ -866,8 +903,7 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                                         hd += h[i] * dsv;
                                         dbs += dz[i];
                                         unsigned char* d = bdst + i * 128 + ((((lane >> 2) ^ i) & 7) << 4);
-                                        *reinterpret_cast<float*>(d) = rnd ? rn_tf32(dz[i]) : dz[i];
-                                        if (x3) *reinterpret_cast<float*>(d + CR * 128) = tc::tf32_lo(dz[i]);
+                                        store_pair1(reinterpret_cast<float*>(d), CR * 32, dz[i], rnd, x3);
                                     }
                                 }
                                 tc::fence_proxy_async();
@@ -929,8 +965,7 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                                         dbs += dz[i];
                                         if (feed) {
                                             unsigned char* d = bdst + i * 128 + ((((lane >> 2) ^ i) & 7) << 4);
-                                            *reinterpret_cast<float*>(d) = rnd ? rn_tf32(dz[i]) : dz[i];
-                                            if (x3) *reinterpret_cast<float*>(d + CR * 128) = tc::tf32_lo(dz[i]);
+                                            store_pair1(reinterpret_cast<float*>(d), CR * 32, dz[i], rnd, x3);
                                         }
                                     }
                                 }
@@ -1192,9 +1227,9 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                                 if (x3) {
 #pragma unroll
                                     for (int k = 0; k < KCH / 8; ++k) {
-                                        // A.[B | B_lo] -> columns [0, bn) and [bn, 2 bn);  A_lo.B -> columns [0, bn)
+                                        // A.[B | B_lo] -> columns [0, bn) and [bn, 2 bn);  A_lo.B -> columns [bn, 2 bn) too (small terms apart)
                                         tc::mma_tf32(tmem, tc::desc_words(aw + k * a_k, tc::kDescHiMN), tc::desc_words(bw + k * b_k, tc::kDescHiMN), idesc2, acc);
-                                        tc::mma_tf32(tmem, tc::desc_words(alw + k * a_k, tc::kDescHiMN), tc::desc_words(bw + k * b_k, tc::kDescHiMN), idesc1, 1u);
+                                        tc::mma_tf32(tmem + (uint32_t)J.bn, tc::desc_words(alw + k * a_k, tc::kDescHiMN), tc::desc_words(bw + k * b_k, tc::kDescHiMN), idesc1, 1u);
                                         acc = 1;
                                     }
                                 } else {

@@ -129,6 +129,8 @@ class OracleMLP(object):
         self.auc = AUC(500)
 
     # ---- weight plumbing (maml.py:181-194, utils/tool.py:36-45) ---------------------------
+    preact_log = None   # set to a list to record min |pre-activation| per (training forward, layer); see forward()
+
     def w(self, name):
         return self.weights[self.spec.names.index(name)]
 
@@ -157,10 +159,16 @@ class OracleMLP(object):
         for l in range(L):
             Z = mm(H[l], self.w('kernel%d' % l)) + self.w('bias%d' % l)
             A = np.maximum(Z, dt(0))
+            M = None
             if train and sp.dropout > 0:
                 M = masks[l] if masks is not None else philox.dropout_mask(
                     b, sp.hidden[l], sp.dropout_seed + l, self.adam.step, sp.dropout, self.dtype.type)
                 A = A * M
+            if self.preact_log is not None and train:
+                # test diagnostic: the smallest |pre-activation| among the units that survive dropout -- a ReLU gate whose
+                # pre-activation is within rounding distance of zero can open on one implementation and close on another
+                az = np.abs(Z) if M is None else np.where(M > 0, np.abs(Z), np.inf)
+                self.preact_log.append(float(np.min(az)))
             H.append(A)
         z = mm(H[L], self.w('dense_kernel'))                   # [b,1]
         s = z[:, 0] + self.w('global_bias')[0]
