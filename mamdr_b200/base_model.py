@@ -6,6 +6,7 @@ import os
 import os.path as osp
 import time
 
+from .engine import WEIGHT_EXT
 from .schedule import Schedule
 
 
@@ -48,11 +49,18 @@ class BaseModel(object):
         self.checkpoint_path = osp.join(self.train_config['checkpoint_path'], self.model_config['name'],
                                         self.dataset.conf['name'], dataset.conf['domain_split_path'],
                                         time.strftime("%a-%b-%d-%H-%M-%S", time.localtime()),
-                                        "model_parameters.h5")
+                                        "model_parameters" + WEIGHT_EXT)
         self.result_path = osp.join(self.train_config['result_save_path'], self.model_config['name'],
                                     dataset.conf['name'], dataset.conf['domain_split_path'])
+        from . import dist as mdist
+        if mdist.world()[1] > 1:   # the time stamp is taken per process: every rank uses rank 0's path
+            import torch.distributed as tdist
+            box = [self.checkpoint_path]
+            tdist.broadcast_object_list(box, src=0)
+            self.checkpoint_path = box[0]
         # injected schedule (python `random` is unseeded in the reference, run.py:26)
-        self.schedule = Schedule(self.b200_config.get('schedule_seed', dataset.conf['seed']))
+        self.schedule = Schedule(self.b200_config.get('schedule_seed', dataset.conf['seed']),
+                                 shuffle_batches=not dataset.conf.get('fixed_train', False))   # utils/dataset.py:76
         self.verbose = self.b200_config.get('verbose', True)
         self.model = self.build_model()
         self._build_early_stop()
@@ -152,7 +160,7 @@ class BaseModel(object):
                                               lambda: m.evaluate(val_d['data'], steps=val_d['n_step']),
                                               self.train_config['epoch'], self.train_config['patience'])
             m.set_weights(best_w)                                   # :89 load_weights(chk_path)
-            torch.save(best_w.cpu(), osp.join(ckpt_dir, "domain_{}.h5".format(domain_idx)))
+            m.save_weights(osp.join(ckpt_dir, "domain_{}{}".format(domain_idx, WEIGHT_EXT)), best_w)
             test_d = self.dataset.test_dataset[domain_idx]
             p_loss, p_auc = m.evaluate(test_d['data'], steps=test_d['n_step'])
             domain_loss[domain_idx], domain_auc[domain_idx] = p_loss, p_auc
@@ -212,15 +220,25 @@ class BaseModel(object):
         return weighted_auc / total_num
 
     def save_model(self, path):
+        from . import dist as mdist
+        if mdist.world()[0] != 0:      # replicas are bit-identical: rank 0 writes
+            return
         if not osp.exists(osp.dirname(path)):
             os.makedirs(osp.dirname(path))
         self.model.save_weights(path)
 
     def load_model(self, path):
+        from . import dist as mdist
+        if mdist.world()[1] > 1:   # rank 0 wrote it: order the read after the write (every rank calls load_model)
+            import torch.distributed as tdist
+            tdist.barrier()
         self.model.load_weights(path)
 
     def save_result(self, avg_loss, avg_auc, domain_loss, domain_auc):
         """base_model.py:183-200 -- same files, same names."""
+        from . import dist as mdist
+        if mdist.world()[0] != 0:
+            return None
         result_folder_name = "loss_{:.3f}_auc_{:.3f}_{}".format(avg_loss, avg_auc,
                                                                 time.strftime("%a-%b-%d-%H-%M-%S", time.localtime()))
         result_path = osp.join(self.result_path, result_folder_name)
@@ -233,7 +251,7 @@ class BaseModel(object):
         with open(osp.join(result_path, "result.json"), 'w') as f:
             json.dump({"avg_loss": avg_loss, "avg_auc": avg_auc, "domain_loss": domain_loss,
                        "domain_auc": domain_auc}, f)
-        self.save_model(osp.join(result_path, "model_parameters.h5"))
+        self.save_model(osp.join(result_path, "model_parameters" + WEIGHT_EXT))
         return result_path
 
     def _build_early_stop(self):

@@ -9,8 +9,11 @@ SURVEY.md section 8(e) defines the sharded semantics:
     domains are sharded across ranks, LPT-balanced by their cost sum_j (S_j + S_i).
   * ONE collective per meta-step: an all-reduce(sum) over a packed buffer holding, per domain, theta_i
     from its owner and zeros from everyone else (x + 0 is exact, so the exchange is bit-exact), plus the
-    Adam slots (m, v, step, beta powers) of the rank that owns the LAST query domain of the epoch's
-    sequence, which all ranks adopt.  With world_size 1 this is exactly the reference schedule.
+    Adam slots (m, v, step, beta powers) AND the live model state (the whole parameter arena, i.e. also the variables
+    that are not meta parameters when ``meta_parms`` is a subset -- they keep training through every pass and are never
+    reloaded from theta -- and STAR's PartitionedNorm moving statistics) of the rank that owns the LAST query domain of
+    the epoch's sequence, which all ranks adopt: every rank then starts the next replicated DN phase from the same
+    state.  With world_size 1 this is exactly the reference schedule.
 """
 import os
 
@@ -58,26 +61,35 @@ def dr_chain_costs(sequence, supports, n_step, domain_regulation_step=0):
     return costs
 
 
-def exchange(owner, rank, domain_flats, m, v, opt_words, last_owner):
+def exchange(owner, rank, domain_flats, m, v, opt_words, last_owner, extra=()):
     """The one collective of a sharded meta-step (see module docstring).  ``domain_flats``: {idx: flat
-    theta_i tensor}; ``opt_words``: float32 tensor [3] = (step, b1pow, b2pow) of this rank.  All tensors
-    are updated in place on every rank."""
+    theta_i tensor}; ``opt_words``: float32 tensor [3] = (step, b1pow, b2pow) of this rank; ``extra``: further float32
+    tensors (live parameter arena, normalisation state) adopted from ``last_owner``.  All tensors are updated in place
+    on every rank."""
     keys = sorted(domain_flats)
     P = m.numel()
-    buf = torch.zeros((len(keys) + 2) * P + 4, dtype=torch.float32, device=m.device)
+    n_extra = sum(int(t.numel()) for t in extra)
+    buf = torch.zeros((len(keys) + 2) * P + 4 + n_extra, dtype=torch.float32, device=m.device)
     for k, idx in enumerate(keys):
         if owner[idx] == rank:
             buf[k * P:(k + 1) * P].copy_(domain_flats[idx])
+    base = len(keys) * P
     if rank == last_owner:
-        base = len(keys) * P
         buf[base:base + P].copy_(m)
         buf[base + P:base + 2 * P].copy_(v)
         buf[base + 2 * P:base + 2 * P + 3].copy_(opt_words)
+        o = base + 2 * P + 4
+        for t in extra:
+            buf[o:o + t.numel()].copy_(t.reshape(-1))
+            o += t.numel()
     dist.all_reduce(buf, op=dist.ReduceOp.SUM)
     for k, idx in enumerate(keys):
         domain_flats[idx].copy_(buf[k * P:(k + 1) * P])
-    base = len(keys) * P
     m.copy_(buf[base:base + P])
     v.copy_(buf[base + P:base + 2 * P])
     opt_words.copy_(buf[base + 2 * P:base + 2 * P + 3])
+    o = base + 2 * P + 4
+    for t in extra:
+        t.copy_(buf[o:o + t.numel()].reshape(t.shape))
+        o += t.numel()
     return buf.numel() * 4

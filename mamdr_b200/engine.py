@@ -486,13 +486,26 @@ class MLPModel(object):
         self.ctx.launches += 1
         return float(self._auc_out.item())
 
-    # ---- persistence (the reference writes Keras h5; SURVEY.md 8(f) row f3 keeps the directory layout)
-    def save_weights(self, path):
-        torch.save({"names": self.layout.names, "shapes": self.layout.shapes,
-                    "weights": [w.cpu() for w in self.layout.views(self.params)]}, path)
+    # ---- persistence.  The reference writes Keras HDF5 (base_model.py:177-181); h5py is not available here, so the weight
+    # files are numpy .npz archives keyed by the variables' TF names (WEIGHT_EXT; INTEGRATION.md shows the h5 converter).
+    def state_arrays(self, flat=None):
+        """{TF variable name: array} of a weight snapshot (default: the live model)."""
+        flat = self.params if flat is None else flat
+        return {w.name: v.detach().cpu().numpy() for w, v in zip(self.trainable_weights, self.layout.views(flat[:self.params.numel()]))}
+
+    def save_weights(self, path, flat=None):
+        import numpy as np
+        with open(path, "wb") as f:
+            np.savez(f, **self.state_arrays(flat))
 
     def load_weights(self, path):
-        blob = torch.load(path, map_location="cpu")
-        if blob["names"] != self.layout.names:
+        import numpy as np
+        blob = np.load(path)
+        names = [w.name for w in self.trainable_weights]
+        if sorted(names) != sorted(k for k in blob.files if not k.startswith("__")):
             raise ValueError("checkpoint layout mismatch")
-        self.params.copy_(torch.from_numpy(self.layout.pack([w.numpy() for w in blob["weights"]])))
+        self.params.copy_(torch.from_numpy(self.layout.pack([blob[n] for n in names])))
+        return blob
+
+
+WEIGHT_EXT = ".npz"

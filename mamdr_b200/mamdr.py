@@ -128,8 +128,18 @@ class MAMDR(SpecificBase):
             # that owns the last query domain of the sequence
             m = self.model
             words = m.opt_words()
+            # the live model of the last chain's owner too: with a subset of meta parameters (config #4: STAR) the other
+            # variables and the PartitionedNorm moving statistics train through every pass and are never reloaded from theta
+            extra = [m.params]
+            pn_steps = None
+            if getattr(m, "pn_state", None) is not None:
+                pn_f, pn_steps = m.pn_parts()          # float statistics; int32 update counters (exact as fp32 below 2^24)
+                steps_f = pn_steps.to(torch.float32)
+                extra += [pn_f, steps_f]
             self.comm_bytes = mdist.exchange(owner, rank, {k: v.flat for k, v in self.domain_weights.items()},
-                                             m.m, m.v, words, owner[train_sequence[-1]])
+                                             m.m, m.v, words, owner[train_sequence[-1]], extra)
+            if pn_steps is not None:
+                pn_steps.copy_(steps_f.to(torch.int32))
             m.set_opt_words(words)
 
     # ---- :168-171

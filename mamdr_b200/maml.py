@@ -132,7 +132,7 @@ class MAML(object):
     def load_state(self, path):
         """Restore a `save_state` blob into a freshly built (and `prepare`d, where the wrapper has one) wrapper.  Returns the
         epoch the state was saved after."""
-        blob = torch.load(path, map_location="cpu", weights_only=False)
+        blob = torch.load(path, map_location="cpu", weights_only=True)   # tensors, ints, strings, lists / tuples only
         m = self.model
         base = self.base_model
         if blob["names"] != m.layout.names:

@@ -10,7 +10,7 @@ import torch
 
 from . import _lib
 from .base_model import keras_fit_with_callbacks
-from .engine import _ptr
+from .engine import WEIGHT_EXT, _ptr
 from .maml import MAML, MetaWeights
 
 
@@ -130,7 +130,7 @@ class SpecificBase(MAML):
                                               lambda: m.evaluate(val_d['data'], steps=val_d['n_step']),   # two callbacks, :131-142
                                               self.train_config['epoch'], self.train_config['patience'])
             m.set_weights(best_w)                                   # :143 load_weights(chk_path)
-            torch.save(best_w.cpu(), osp.join(ckpt_dir, "domain_{}.h5".format(domain_idx)))
+            m.save_weights(osp.join(ckpt_dir, "domain_{}{}".format(domain_idx, WEIGHT_EXT)), best_w)
             test_d = self.dataset.test_dataset[domain_idx]
             p_loss, p_auc = m.evaluate(test_d['data'], steps=test_d['n_step'])
             domain_loss[domain_idx], domain_auc[domain_idx] = p_loss, p_auc

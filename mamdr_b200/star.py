@@ -128,6 +128,37 @@ class StarModel(MLPModel):
             out.append(NamedWeight(tf_name, view, off, n))
         return out
 
+    # ---- weight snapshots.  Keras get_weights / set_weights / save_weights / load_weights include the NON-trainable
+    # PartitionedNorm moving statistics (Star/partitioned_norm.py:74-99), so the best checkpoint, the finetune stage's
+    # per-domain restarts and val_and_test("test") all carry them: a snapshot here is [arena | pn_state words].
+    def pn_parts(self):
+        """(float32 view of the statistics [4, D, n] flattened, int32 view of the per-domain update counters)."""
+        n, D = sum(self.emb_dim), self.n_domain
+        return self.pn_state[:16 * D * n].view(torch.float32), self.pn_state[16 * D * n:].view(torch.int32)
+
+    def get_weights(self):
+        return torch.cat([self.params, self.pn_state.view(torch.float32)])
+
+    def set_weights(self, flat):
+        P_ = self.params.numel()
+        self.copy_(self.params, flat[:P_])
+        if flat.numel() > P_:
+            self.pn_state.view(torch.float32).copy_(flat[P_:])
+
+    def save_weights(self, path, flat=None):
+        import numpy as np
+        arrays = self.state_arrays(flat)
+        pn = self.pn_state if flat is None or flat.numel() == self.params.numel() else flat[self.params.numel():].view(torch.uint8)
+        arrays["__pn_state__"] = pn.detach().cpu().numpy().view(np.uint8)
+        with open(path, "wb") as f:
+            np.savez(f, **arrays)
+
+    def load_weights(self, path):
+        blob = super(StarModel, self).load_weights(path)
+        if "__pn_state__" in blob.files:
+            self.pn_state.copy_(torch.from_numpy(blob["__pn_state__"].copy()))
+        return blob
+
     def moving_stats(self):
         n, D = sum(self.emb_dim), self.n_domain
         f = self.pn_state[:16 * D * n].view(torch.float32).view(4, D, n)

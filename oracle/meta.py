@@ -330,12 +330,29 @@ class OracleMAMDR(object):
                     merged = merge_weights(self.meta_weights, self.domain_weights[idx], tc['merged_method'])
             if r == owner[seq[-1]]:
                 final = (deepcopy(adam.m), deepcopy(adam.v), adam.b1pow, adam.b2pow, adam.step)
+                final_live = self._live_state()
         for mm_, s_ in zip(adam.m, final[0]):
             mm_[...] = s_
         for vv_, s_ in zip(adam.v, final[1]):
             vv_[...] = s_
         adam.b1pow, adam.b2pow, adam.step = final[2], final[3], final[4]
+        self._set_live_state(final_live)
         return owner
+
+    _LIVE_EXTRA = ("biased_mean", "biased_var", "pn_steps", "moving_mean", "moving_var")   # OracleStar's non-trainable state
+
+    def _live_state(self):
+        """Everything of the live model a rank hands over at the end of a sharded meta-step: ALL variables (also the ones
+        outside the meta-parameter subset) and the non-trainable normalisation state."""
+        base = getattr(self.model, "_model", self.model)
+        return ([w.copy() for w in base.weights], {k: np.copy(getattr(base, k)) for k in self._LIVE_EXTRA if hasattr(base, k)})
+
+    def _set_live_state(self, state):
+        base = getattr(self.model, "_model", self.model)
+        for w, s_ in zip(base.weights, state[0]):
+            w[...] = s_
+        for k, v in state[1].items():
+            getattr(base, k)[...] = v
 
     def val_and_test(self, mode):  # specific_base_model.py:64-97
         if mode == 'val':

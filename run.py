@@ -64,6 +64,17 @@ def build(config, dataset=None):
 
 
 def main(config):
+    # torchrun: one process per GPU.  The process group is initialised from the environment, every rank takes the GPU of its
+    # LOCAL_RANK, and only rank 0 writes checkpoints / results (mamdr_b200/base_model.py: save_model, save_result).
+    import os
+    from mamdr_b200 import dist as mdist
+    rank, world = mdist.init_from_env()
+    if world > 1:
+        import torch
+        local = int(os.environ.get("LOCAL_RANK", rank))
+        config.setdefault('b200', {})['device'] = "cuda:%d" % local
+        if torch.cuda.is_available():
+            torch.cuda.set_device(local)
     model = build(config)
     name = config['model']['name']
 

@@ -136,6 +136,11 @@ class _ToyDeviceModel(object):
     def set_weights(self, flat):
         self.params.copy_(flat)
 
+    def save_weights(self, path, flat=None):   # engine.MLPModel.save_weights: an .npz keyed by the variables' TF names
+        flat = self.params if flat is None else flat
+        with open(path, "wb") as f:
+            np.savez(f, **{w.name: v.numpy() for w, v in zip(self.trainable_weights, self.layout.views(flat))})
+
 
 def _base(name, method, meta_parms=("all",)):
     model = _ToyDeviceModel()
@@ -168,6 +173,11 @@ def _base(name, method, meta_parms=("all",)):
 
 def _bits(a):
     return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def _load_ckpt(model, path):
+    blob = np.load(path)
+    return torch.from_numpy(model.layout.pack([blob[w.name] for w in model.trainable_weights]))
 
 
 def _flat(model, flat_tensor):
@@ -268,7 +278,7 @@ def test_product_finetune_stage_replays_the_reference(tmp_path, kind, name, meth
     from mamdr_b200.mamdr import MAMDR
     from mamdr_b200.reptile import Reptile
     base, model = _base(name, method)
-    base.checkpoint_path = str(tmp_path / "ckpt" / "model_parameters.h5")
+    base.checkpoint_path = str(tmp_path / "ckpt" / "model_parameters.npz")
     base.train_config.update(loss="binary_crossentropy", learning_rate=0.001)
     base.separate_train_val_test = types.MethodType(BaseModel.separate_train_val_test, base)
     wrapper = {"mamdr": MAMDR, "dn": DomainNegotiation, "reptile": Reptile}[kind](base)
@@ -284,7 +294,7 @@ def test_product_finetune_stage_replays_the_reference(tmp_path, kind, name, meth
     np.testing.assert_array_equal(got, LOOPS[key + "result"])
     np.testing.assert_array_equal(_bits(_flat(model, model.params)), _bits(LOOPS[key + "live"]))
     for d in sorted(mrg.N_STEP):
-        ck = torch.load(str(tmp_path / "ckpt" / ("domain_%d.h5" % d)))
+        ck = _load_ckpt(model, str(tmp_path / "ckpt" / ("domain_%d.npz" % d)))
         np.testing.assert_array_equal(_bits(_flat(model, ck)), _bits(LOOPS[key + "ckpt_%d" % d]), err_msg="checkpoint of domain %d" % d)
     assert model.optimizer == "adam"        # the stage hands the model back compiled with the training optimizer
 
@@ -357,6 +367,41 @@ def test_sharded_product_meta_steps_equal_the_reference_sequential_run(tmp_path)
     # ... and together exactly the sequential run's steps, the replicated DN phase counted once per epoch
     total = len(blobs[0]["steps"]) + len(blobs[1]["steps"]) - mrg.LOOP_TC["epoch"] * dn_steps_per_epoch
     assert total == n_seq
+
+
+def _sharded_subset_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    os.environ.update({"MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port), "RANK": str(rank), "WORLD_SIZE": str(world)})
+    dist.init_process_group("gloo")
+    from mamdr_b200.mamdr import MAMDR
+    base, model = _base("mlp_meta_mamdr", "plus", meta_parms=("kernel",))   # bias0 is NOT a meta parameter
+    wrapper = MAMDR(base)
+    wrapper.train()
+    torch.save({"theta": wrapper.meta_weights.flat.clone(), "theta_d": {d: w.flat.clone() for d, w in wrapper.domain_weights.items()},
+                "live": model.params.clone(), "owner": dict(wrapper.dr_owner), "last": wrapper.train_sequence[-1]},
+               os.path.join(out_dir, "sub%d.pt" % rank))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_meta_steps_with_a_subset_of_meta_parameters_keep_the_replicas_identical(tmp_path):
+    """meta_parms = a subset (config #4 ships ['emb', 'kernel_shared', 'bias_shared']): the other variables train through every
+    pass and are never reloaded from theta, so each rank's copy follows its own chains.  The one all-reduce of the meta-step
+    therefore also carries the live model of the rank that owns the last chain; afterwards (and hence at the start of the next
+    replicated DN phase) every rank holds the same live arena, theta and theta_d -- bit for bit."""
+    import socket
+    import torch.multiprocessing as mp
+    sock = socket.socket()
+    sock.bind(("127.0.0.1", 0))
+    port = sock.getsockname()[1]
+    sock.close()
+    mp.spawn(_sharded_subset_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a, b = [torch.load(os.path.join(str(tmp_path), "sub%d.pt" % r), weights_only=False) for r in range(2)]
+    assert a["owner"] == b["owner"] and set(a["owner"].values()) == {0, 1}
+    assert torch.equal(a["live"], b["live"])
+    assert torch.equal(a["theta"], b["theta"])
+    for d in a["theta_d"]:
+        assert torch.equal(a["theta_d"][d], b["theta_d"][d]), d
 
 
 @pytest.mark.parametrize("kind,name", [("mamdr", "mlp_meta_mamdr"), ("dn", "mlp_meta_domain_negotiation"), ("reptile", "mlp_meta_reptile_batch")])
