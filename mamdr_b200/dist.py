@@ -61,6 +61,48 @@ def dr_chain_costs(sequence, supports, n_step, domain_regulation_step=0):
     return costs
 
 
+def dr_pair_costs(sequence, supports, n_step, domain_regulation_step=0):
+    """'batch' names: cost of the (query at sequence position pos, k-th support) pair = S_j + S_i' mini-batches
+    (mamdr.py:85-101); keys (pos, k)."""
+    costs = {}
+    for pos, idx in enumerate(sequence):
+        s_i = n_step[idx]
+        if domain_regulation_step and domain_regulation_step > 0:
+            s_i = min(s_i, domain_regulation_step)
+        for k, j in enumerate(supports[idx]):
+            costs[(pos, k)] = n_step[j] + s_i
+    return costs
+
+
+def exchange_sum(accum_all, m, v, opt_words, rank, last_owner, extra=()):
+    """The one collective of a pair-sharded ('batch') meta-step: the per-query-domain delta accumulators [n_domain, P] are
+    SUMMED over the ranks; the Adam slots / beta powers / ``extra`` tensors are adopted from ``last_owner`` (everyone else
+    contributes zeros).  In place on every rank."""
+    P = m.numel()
+    n_acc = accum_all.numel()
+    n_extra = sum(int(t.numel()) for t in extra)
+    buf = torch.zeros(n_acc + 2 * P + 4 + n_extra, dtype=torch.float32, device=m.device)
+    buf[:n_acc].copy_(accum_all.reshape(-1))
+    if rank == last_owner:
+        buf[n_acc:n_acc + P].copy_(m)
+        buf[n_acc + P:n_acc + 2 * P].copy_(v)
+        buf[n_acc + 2 * P:n_acc + 2 * P + 3].copy_(opt_words)
+        o = n_acc + 2 * P + 4
+        for t in extra:
+            buf[o:o + t.numel()].copy_(t.reshape(-1))
+            o += t.numel()
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+    accum_all.copy_(buf[:n_acc].reshape(accum_all.shape))
+    m.copy_(buf[n_acc:n_acc + P])
+    v.copy_(buf[n_acc + P:n_acc + 2 * P])
+    opt_words.copy_(buf[n_acc + 2 * P:n_acc + 2 * P + 3])
+    o = n_acc + 2 * P + 4
+    for t in extra:
+        t.copy_(buf[o:o + t.numel()].reshape(t.shape))
+        o += t.numel()
+    return buf.numel() * 4
+
+
 def exchange(owner, rank, domain_flats, m, v, opt_words, last_owner, extra=()):
     """The one collective of a sharded meta-step (see module docstring).  ``domain_flats``: {idx: flat
     theta_i tensor}; ``opt_words``: float32 tensor [3] = (step, b1pow, b2pow) of this rank; ``extra``: further float32

@@ -63,17 +63,28 @@ class MAMDR(SpecificBase):
         # multi-GPU: DN replicated, DR query domains LPT-sharded (mamdr_b200/dist.py)
         rank, world = mdist.world()
         n_step = {i: self.dataset.train_dataset[i]['n_step'] for i in train_sequence}
+        batch_mode = "batch" in self.model_config['name']
+        # 'batch' names (:100-108): every (query i, support j) pair starts from the same theta (+|*) theta_i, so the PAIRS are
+        # the independent units (60 at Taobao-10 instead of 10 chains): LPT-sharded by S_j + S_i, the accumulated deltas of
+        # all theta_i all-reduced once per meta-step.  finetune_every_epoch chains a pass per domain behind the update:
+        # those configs keep the chain sharding.
+        pair_mode = batch_mode and world > 1 and not tc['finetune_every_epoch']
         owner = mdist.lpt_assign(mdist.dr_chain_costs(train_sequence, supports, n_step,
                                                       tc['domain_regulation_step']), world)
-        self.dr_owner = owner
+        pair_owner = None
+        if pair_mode:
+            pair_owner = mdist.lpt_assign(mdist.dr_pair_costs(train_sequence, supports, n_step,
+                                                              tc['domain_regulation_step']), world)
+            owner = {idx: pair_owner[(pos, len(supports[idx]) - 1)] for pos, idx in enumerate(train_sequence)}
+        self.dr_owner, self.dr_pair_owner = owner, pair_owner
         passes, mine = list(train_sequence), [True] * len(train_sequence)
-        for idx in train_sequence:
-            k = 2 * len(supports[idx]) + (1 if tc['finetune_every_epoch'] else 0)
-            for aux_idx in supports[idx]:
+        for pos, idx in enumerate(train_sequence):
+            for k, aux_idx in enumerate(supports[idx]):
                 passes += [aux_idx, idx]
+                mine += [(pair_owner[(pos, k)] if pair_mode else owner[idx]) == rank] * 2
             if tc['finetune_every_epoch']:
                 passes.append(idx)
-            mine += [owner[idx] == rank] * k
+                mine.append(owner[idx] == rank)
         self.stage_epoch_orders(passes, mine if world > 1 else None)
 
         # In the tcgen05 modes the DN phase and every DR chain of this rank are each recorded and run as ONE persistent
@@ -88,7 +99,9 @@ class MAMDR(SpecificBase):
             self._update_meta_weight(self.meta_weights, meta_lr=beta)
 
         # ---- Update specific (DR), :59-108
-        batch_mode = "batch" in self.model_config['name']
+        if pair_mode:
+            self._dr_pairs_sharded(train_sequence, supports, pair_owner, rank, use_program)
+            return
         for idx in train_sequence:
             if owner[idx] != rank:
                 continue
@@ -141,6 +154,49 @@ class MAMDR(SpecificBase):
             if pn_steps is not None:
                 pn_steps.copy_(steps_f.to(torch.int32))
             m.set_opt_words(words)
+
+    def _dr_pairs_sharded(self, train_sequence, supports, pair_owner, rank, use_program):
+        """DR of a 'batch' name on world > 1 ranks: this rank runs its (query, support) pairs, accumulating the deltas per query
+        domain (:182-191); ONE all-reduce sums the accumulators of all theta_i (and carries the Adam slots / live model of the
+        rank that owns the last pair of the sequence); every rank then applies :193-196 to every theta_i -- replicas stay
+        bit-identical."""
+        tc = self.train_config
+        m = self.model
+        P_ = m.params.numel()
+        if getattr(self, "_accum_all", None) is None or self._accum_all.shape[0] != len(train_sequence):
+            self._accum_all = torch.zeros(len(train_sequence), P_, dtype=torch.float32, device=m.params.device)
+        else:
+            self._accum_all.zero_()
+        for pos, idx in enumerate(train_sequence):
+            ks = [k for k in range(len(supports[idx])) if pair_owner[(pos, k)] == rank]
+            if not ks:
+                continue
+            with self.model.program(use_program):
+                d = self.dataset.train_dataset[idx]
+                theta_i = self.domain_weights[idx]
+                self._accum = self._accum_all[pos]
+                self._set_model_merged(self.meta_weights, theta_i)
+                for k in ks:
+                    aux_idx = supports[idx][k]
+                    self.log(f"Support Domain: {aux_idx}, Query Domain: {idx}")
+                    self.run_train_pass(aux_idx)   # staged orders are consumed in this (global) order
+                    train_step = d['n_step']
+                    if tc['domain_regulation_step'] > 0:
+                        train_step = min(train_step, tc['domain_regulation_step'])
+                    self.run_train_pass(idx, train_step)
+                    self._accumulate_grad(theta_i)
+                    self._set_model_merged(self.meta_weights, theta_i)
+        self._accum = None
+        words = m.opt_words()
+        last_pos = len(train_sequence) - 1
+        last_owner = pair_owner[(last_pos, len(supports[train_sequence[-1]]) - 1)]
+        extra = [m.params]
+        self.comm_bytes = mdist.exchange_sum(self._accum_all, m.m, m.v, words, rank, last_owner, extra)
+        m.set_opt_words(words)
+        for pos, idx in enumerate(train_sequence):
+            self._accum = self._accum_all[pos]
+            self._update_meta_weight_by_grads(self.domain_weights[idx])
+        self._accum = None
 
     # ---- :168-171
     def _update_domain_weights(self, domain_weights, merged_weights):

@@ -273,7 +273,8 @@ class OracleMAMDR(object):
         LPT-sharded by cost sum_j (S_j + S_i); every rank continues from the post-DN Adam state with its
         own chains in sequence order; afterwards all ranks adopt the Adam state of the rank owning the
         last query domain of the sequence.  Sample orders use the global (sequential) pass ids.
-        Non-'batch' names, 'plus'/'times' merge, no finetune_every_epoch."""
+        'plus'/'times' merge, no finetune_every_epoch.  'batch' names shard the (query, support) PAIRS instead
+        (`_train_epoch_pair_sharded`)."""
         tc, model = self.tc, self.model
         beta = tc['meta_learning_rate']
         if tc['shuffle_sequence']:
@@ -292,6 +293,8 @@ class OracleMAMDR(object):
             r = min(range(world), key=lambda q: (load[q], q))
             owner[i] = r
             load[r] += cost[i]
+        if 'batch' in self.name:
+            return self._train_epoch_pair_sharded(world, seq, supports, S)
         n_pass = len(seq) + sum(2 * len(supports[i]) for i in seq)
         pid = self.schedule.reserve(n_pass)
         # ---- DN (replicated)
@@ -331,6 +334,73 @@ class OracleMAMDR(object):
             if r == owner[seq[-1]]:
                 final = (deepcopy(adam.m), deepcopy(adam.v), adam.b1pow, adam.b2pow, adam.step)
                 final_live = self._live_state()
+        for mm_, s_ in zip(adam.m, final[0]):
+            mm_[...] = s_
+        for vv_, s_ in zip(adam.v, final[1]):
+            vv_[...] = s_
+        adam.b1pow, adam.b2pow, adam.step = final[2], final[3], final[4]
+        self._set_live_state(final_live)
+        return owner
+
+    def _train_epoch_pair_sharded(self, world, seq, supports, S):
+        """'batch' names (mamdr.py:100-108): every (query i, support j) pair starts from theta (+|*) theta_i, so the pairs are
+        LPT-sharded by S_j + S_i; each rank accumulates its pairs' deltas per query domain (:182-191) from the post-DN Adam
+        state; the accumulators are summed over the ranks (rank order) and every theta_i takes :193-196; the Adam state and
+        the live model of the rank that owns the LAST pair of the sequence are adopted by all."""
+        tc, model = self.tc, self.model
+        beta = tc['meta_learning_rate']
+        cost = {(pos, k): S[j] + S[i] for pos, i in enumerate(seq) for k, j in enumerate(supports[i])}
+        load, owner = [0] * world, {}
+        for key in sorted(cost, key=lambda q: (-cost[q], q)):
+            r = min(range(world), key=lambda q: (load[q], q))
+            owner[key] = r
+            load[r] += cost[key]
+        n_pass = len(seq) + sum(2 * len(supports[i]) for i in seq)
+        pid = self.schedule.reserve(n_pass)
+        model.set_weights(self.meta_weights)
+        for idx in seq:
+            d = self.data['train'][idx]
+            train_pass(model, d, idx, self.schedule.batch_order_at(pid, idx, len(d['uid'])), self.bs)
+            pid += 1
+        self._update_meta_weight(self.meta_weights, meta_lr=beta)
+        ids = {}
+        for idx in seq:
+            ids[idx] = pid
+            pid += 2 * len(supports[idx])
+        adam = model.adam
+        snap = (deepcopy(adam.m), deepcopy(adam.v), adam.b1pow, adam.b2pow, adam.step)
+        merged = {i: merge_weights(self.meta_weights, self.domain_weights[i], tc['merged_method']) for i in seq}
+        accum_r = []
+        final = final_live = None
+        last_key = (len(seq) - 1, len(supports[seq[-1]]) - 1)
+        for r in range(world):
+            for mm_, s_ in zip(adam.m, snap[0]):
+                mm_[...] = s_
+            for vv_, s_ in zip(adam.v, snap[1]):
+                vv_[...] = s_
+            adam.b1pow, adam.b2pow, adam.step = snap[2], snap[3], snap[4]
+            acc = {i: [np.zeros_like(w) for w in merged[i]] for i in seq}
+            for pos, idx in enumerate(seq):
+                d = self.data['train'][idx]
+                for k, aux_idx in enumerate(supports[idx]):
+                    if owner[(pos, k)] != r:
+                        continue
+                    p = ids[idx] + 2 * k
+                    model.set_weights(merged[idx])
+                    aux_d = self.data['train'][aux_idx]
+                    train_pass(model, aux_d, aux_idx, self.schedule.batch_order_at(p, aux_idx, len(aux_d['uid'])), self.bs)
+                    train_pass(model, d, idx, self.schedule.batch_order_at(p + 1, idx, len(d['uid'])), self.bs)
+                    self._accumulate_grad(acc[idx], merged[idx], self.meta_weights)
+            accum_r.append(acc)
+            if r == owner[last_key]:
+                final = (deepcopy(adam.m), deepcopy(adam.v), adam.b1pow, adam.b2pow, adam.step)
+                final_live = self._live_state()
+        for idx in seq:
+            total = [np.zeros_like(w) for w in merged[idx]]
+            for r in range(world):
+                for t_, a_ in zip(total, accum_r[r][idx]):
+                    t_ += a_
+            self._update_meta_weight_by_grads(total, self.domain_weights[idx])
         for mm_, s_ in zip(adam.m, final[0]):
             mm_[...] = s_
         for vv_, s_ in zip(adam.v, final[1]):

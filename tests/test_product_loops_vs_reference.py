@@ -369,6 +369,50 @@ def test_sharded_product_meta_steps_equal_the_reference_sequential_run(tmp_path)
     assert total == n_seq
 
 
+def _pair_sharded_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    os.environ.update({"MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port), "RANK": str(rank), "WORLD_SIZE": str(world)})
+    dist.init_process_group("gloo")
+    from mamdr_b200.mamdr import MAMDR
+    base, model = _base("mlp_meta_mamdr_batch", "plus")
+    wrapper = MAMDR(base)
+    wrapper.train()
+    mine = sorted(k for k, r in wrapper.dr_pair_owner.items() if r == rank)
+    torch.save({"theta": wrapper.meta_weights.flat.clone(), "theta_d": {d: w.flat.clone() for d, w in wrapper.domain_weights.items()},
+                "steps": list(model.steps), "pairs": mine, "n_pairs": len(wrapper.dr_pair_owner), "live": model.params.clone()},
+               os.path.join(out_dir, "pair%d.pt" % rank))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_pair_sharded_batch_meta_steps_equal_the_reference_sequential_run(tmp_path):
+    """'batch' names (mamdr.py:100-108,182-196): every (query, support) pair starts from theta (+) theta_i, so with a train step
+    that carries no optimizer state the PAIRS are independent.  Two gloo ranks each run their LPT share of the pairs, ONE
+    all-reduce sums the accumulated deltas, every rank applies them: theta equals the reference's executed SEQUENTIAL run bit
+    for bit, every theta_d to the last ulps (the two ranks' partial sums are added in a different association), the replicas
+    are bit-identical, and together the ranks execute exactly the sequential run's train steps."""
+    import socket
+    import torch.multiprocessing as mp
+    sock = socket.socket()
+    sock.bind(("127.0.0.1", 0))
+    port = sock.getsockname()[1]
+    sock.close()
+    mp.spawn(_pair_sharded_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    key = "mlp_meta_mamdr_batch|plus|"
+    lo = ParamLayout(["kernel0", "bias0"], [w.shape for w in mrg.toy_init(0)])
+    flat = lambda t: mrg.flat_any([v.numpy() for v in lo.views(t)])   # noqa: E731
+    a, b = [torch.load(os.path.join(str(tmp_path), "pair%d.pt" % r), weights_only=False) for r in range(2)]
+    assert a["pairs"] and b["pairs"] and not set(a["pairs"]) & set(b["pairs"]) and len(a["pairs"]) + len(b["pairs"]) == a["n_pairs"]
+    assert torch.equal(a["theta"], b["theta"]) and torch.equal(a["live"], b["live"])
+    np.testing.assert_array_equal(_bits(flat(a["theta"])), _bits(LOOPS[key + "theta"]))
+    for d in sorted(mrg.N_STEP):
+        assert torch.equal(a["theta_d"][d], b["theta_d"][d])
+        np.testing.assert_allclose(flat(a["theta_d"][d]), LOOPS[key + "theta_%d" % d], rtol=2e-6, atol=1e-7, err_msg="theta_%d" % d)
+    dn_steps_per_epoch = sum(mrg.N_STEP.values())
+    total = len(a["steps"]) + len(b["steps"]) - mrg.LOOP_TC["epoch"] * dn_steps_per_epoch
+    assert total == len(LOOPS[key + "steps"])
+
+
 def _sharded_subset_worker(rank, world, port, out_dir):
     import torch.distributed as dist
     os.environ.update({"MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port), "RANK": str(rank), "WORLD_SIZE": str(world)})
