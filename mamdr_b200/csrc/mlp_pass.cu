@@ -877,6 +877,7 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                                     if ((lane & 3) == 0) s_zp[(hf * 4 + q) * 8 + warp_sum8_index(lane)] = zs;
                                 }
                                 worker_sync();
+                                WSTAMP(15);
                                 float pv = 0.f, yv = 0.f, dsv0 = 0.f;   // warp 0: row lane of the group
                                 const int hrow = row0 + lane;
                                 const bool hvalid = warp == 0 && lane < CR && hrow < rows;
@@ -1371,6 +1372,11 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                     b2pow = __fmul_rn(b2pow, a.beta2);
                 }
                 step_ctr += 1;
+            }
+            if (warp == kProdWarp && lane == 0) {
+                // the next phase's first tensor maps: fetched into the descriptor cache while this CTA waits at the barrier
+                if (phase == 0 && a.train) { tc::tma_prefetch_desc(&maps.xmn[buf]); tc::tma_prefetch_desc(&maps.dzmn[0]); }
+                else { tc::tma_prefetch_desc(&maps.xk[buf ^ 1]); tc::tma_prefetch_desc(&maps.wf[0]); }
             }
             if (a.timing) {
                 __syncthreads();
