@@ -31,6 +31,7 @@ WORKLOAD_CONFIG = {"Taobao-10": "config/Taobao-10/deepctr_DN+DR.json", "Taobao-2
                    "Amazon-13-ple": "config/Amazon_13/ple_DN.json", "Amazon-13-mmoe-sharded": "config/Amazon_13/mmoe_DN.json",
                    "Amazon-13-ple-sharded": "config/Amazon_13/ple_DN.json"}
 METRIC = "MAMDR meta-train samples/sec (Taobao-10 shape)"
+_emit = lambda line: print(json.dumps(line), flush=True)   # noqa: E731  (main() re-binds it to the real stdout)
 
 
 def load_config(workload):
@@ -177,7 +178,7 @@ def run_reference(args):
             "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def workload_desc(config, workload, n_gpus, model=None):
@@ -280,6 +281,31 @@ def micro_rooflines(model, peaks, torch):
     gb = (24.0 * n_el + 4.0 * rows_t) / 1e9
     out["table_adam"] = {"bound": "hbm", "achieved": gb / (ms * 1e-3), "peak": hbm, "unit": "GB/s",
                          "frac": gb / (ms * 1e-3) / hbm, "rows": rows_t, "dim": dim_t, "ms": ms}
+    del tp, tm, tv, p, m, v
+    # sparse-gradient de-duplication at HBM scale (multi-CTA path): 2 Mi gradient rows x 128 over Zipf ids -> read n x 512 B once,
+    # write u x 512 B
+    n_s, dim_s = 1 << 21, 128
+    zi = torch.from_numpy((__import__("numpy").random.default_rng(5).zipf(1.05, n_s) - 1).clip(0, 445788).astype("int32")).to(model.device)
+    grows = torch.randn(n_s, dim_s, device=model.device)
+    uo = torch.empty(n_s, dtype=torch.int32, device=model.device)
+    ro = torch.empty(n_s, dim_s, device=model.device)
+    nu = torch.zeros(1, dtype=torch.int32, device=model.device)
+    sws = torch.zeros(ctx.lib.mamdr_scatter_large_workspace_bytes(n_s, dim_s), dtype=torch.uint8, device=model.device)
+    sargs = (_ptr(zi), _ptr(grows), dim_s, n_s, dim_s, _ptr(uo), _ptr(ro), _ptr(nu), _ptr(sws), sws.numel(), st)
+    for _ in range(3):
+        ctx.call("mamdr_scatter_dedup_large_f32", *sargs)
+    a, b = ev(), ev()
+    a.record()
+    for _ in range(reps):
+        ctx.call("mamdr_scatter_dedup_large_f32", *sargs)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / reps
+    u = int(nu.item())
+    gb = (n_s + u) * dim_s * 4.0 / 1e9
+    out["scatter"] = {"bound": "hbm", "achieved": gb / (ms * 1e-3), "peak": hbm, "unit": "GB/s", "frac": gb / (ms * 1e-3) / hbm,
+                      "rows": n_s, "unique": u, "dim": dim_s, "ms": ms,
+                      "note": "whole call: 4-pass radix sort of (id, position) + head scan + ONE pass over the gradient rows"}
     return out
 
 
@@ -372,7 +398,7 @@ def run_amazon(args):
                          "alg_bytes_per_minibatch": alg_bytes, "us_per_minibatch": 1e3 * ms / mb,
                          "note": "achieved / frac = the table sweep alone (24 B per table element + 4 B per row); step_* = all algorithmic "
                                  "bytes of a mini-batch (tables + 28 B per dense parameter that trains) over the whole step time"}}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def run_sharded(args):
@@ -441,13 +467,13 @@ def run_sharded(args):
     if rank == 0:
         msv = float(ms.item())
         alg = 24.0 * (n_uid + n_pid) * 128
-        print(json.dumps({"metric": "joint-train samples/sec (Amazon-13 shape, row-sharded trainable tables)", "value": mb * 1024 / (msv * 1e-3),
+        _emit(({"metric": "joint-train samples/sec (Amazon-13 shape, row-sharded trainable tables)", "value": mb * 1024 / (msv * 1e-3),
                           "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": msv,
                           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                           "config": {"workload": "%s train steps, trainable tables row-sharded over %d rank(s), NCCL all-to-all, %d mini-batches of 1024 per step%s" % (tower, world, mb, ", one CUDA graph per (sub-model, rows) incl. the collectives" if args.graphs else "")},
                           "roofline": {"bound": "hbm", "achieved": alg * mb / (msv * 1e-3) / 1e9, "unit": "GB/s",
                                        "note": "aggregate table-sweep bytes (24 B per table element per mini-batch) over all ranks / step time"},
-                          "us_per_minibatch": 1e3 * msv / mb}), flush=True)
+                          "us_per_minibatch": 1e3 * msv / mb}))
     dist.destroy_process_group()
 
 
@@ -681,7 +707,7 @@ def run_b200(args):
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "micro": micro, "cpu_baseline": cpu,
             "parity_mode": parity_mode,
             "minibatches_per_step": steps_per_epoch, "wall_s": t_wall}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def main():
@@ -698,6 +724,11 @@ def main():
                     "NCCL collectives (opt-in, unreliable: 1.7x at 2 GPUs for the mmoe tower, but the capture hangs for the mlp tower)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: everything the library prints while building (dataset banners ...) goes to stderr
+    real_stdout = sys.stdout
+    sys.stdout = sys.stderr
+    global _emit
+    _emit = lambda line: (real_stdout.write(json.dumps(line) + "\n"), real_stdout.flush())   # noqa: E731
     if args.impl == "reference":
         run_reference(args)
     elif args.workload in ("Amazon-6", "Amazon-13-mmoe", "Amazon-13-ple"):

@@ -78,6 +78,17 @@ int mamdr_scatter_dedup_f32(mamdr_ctx* ctx, const int32_t* ids_dev, const float*
                             float* uniq_rows_dev, int32_t* n_uniq_dev, void* ws_dev, size_t ws_bytes,
                             mamdr_stream stream);
 
+/* The same de-duplication for n beyond mamdr_scatter_max_n() (any n < 2^31), multi-CTA: a stable radix sort of
+ * (id, position) + head scan, then ONE pass over the n gradient rows at HBM bandwidth.  uniq_ids: ascending, bit-exact.
+ * Summation order (deterministic): windows of 256 consecutive SORTED positions; inside a window the rows of an id are
+ * added sequentially in batch order, the window partials of an id are added in window order (ids with <= 256
+ * occurrences inside one window: exactly the numpy add.at order). */
+size_t mamdr_scatter_large_workspace_bytes(int64_t n, int32_t dim);
+int mamdr_scatter_dedup_large_f32(mamdr_ctx* ctx, const int32_t* ids_dev, const float* grad_rows_dev,
+                                  int64_t grad_stride, int64_t n, int32_t dim, int32_t* uniq_ids_dev,
+                                  float* uniq_rows_dev, int32_t* n_uniq_dev, void* ws_dev, size_t ws_bytes,
+                                  mamdr_stream stream);
+
 /* ---- model description (replaces DeepCTR.build_inputs/build_emb/build_mlp,
  * model_zoo/DeepCTR/deepctr.py:95-136).  Offsets are in floats into a parameter "arena": one flat
  * fp32 buffer holding every trainable tensor in model.trainable_weights order

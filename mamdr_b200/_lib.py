@@ -118,6 +118,8 @@ SIGNATURES = {
     "mamdr_scatter_max_n": (_I64, []),
     "mamdr_scatter_workspace_bytes": (_SZ, [_I64]),
     "mamdr_scatter_dedup_f32": (C.c_int, [_P, _P, _P, _I64, _I64, _I32, _P, _P, _P, _P, _SZ, _P]),
+    "mamdr_scatter_large_workspace_bytes": (_SZ, [_I64, _I32]),
+    "mamdr_scatter_dedup_large_f32": (C.c_int, [_P, _P, _P, _I64, _I64, _I32, _P, _P, _P, _P, _SZ, _P]),
     "mamdr_opt_state_bytes": (_SZ, []),
     "mamdr_opt_state_init": (C.c_int, [_P, _P, _F, _F, _P]),
     "mamdr_opt_state_read": (C.c_int, [_P, _P, C.POINTER(_I64), C.POINTER(_F), C.POINTER(_F), _P]),

@@ -516,6 +516,7 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
 
     const ProgOp* ops = a.ops ? a.ops : &a.inline_op;
     int pass_idx = 0;
+    bool shadows_valid = false;   // the GEMM shadows match the arena: true after a training pass, until a meta sweep runs
     for (int oi = 0; oi < a.n_ops; ++oi) {
     const ProgOp& op = ops[oi];
     if (op.kind == PROG_META) {
@@ -527,6 +528,7 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
         const int64_t nv4 = op.n >> 2;
         for (int64_t i = (int64_t)cta * kThreads + tid; i < nv4; i += (int64_t)G * kThreads) meta_float4(mop, ma, i);
         grid_barrier(a.bar, bar_target);
+        shadows_valid = false;   // (conservative: the sweep may have rewritten the live arena)
         continue;
     }
     PassDyn pd;
@@ -537,7 +539,7 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
 
     // ---- prologue of a pass: gather mini-batch 0; pair shadow of the kernels (the arena may have been rewritten by a
     // meta sweep or by the host since the last pass); |E_d|^2 for the inference loss
-    refresh_wpair();
+    if (!shadows_valid) refresh_wpair();
     if (warp < kWorkerWarps) {
         if (cta < kDomJobs) fold_from_params(a, pd.dom, cta, tid);
         gather_rows(a, pd, 0, 0, cta * kWorkerWarps + warp, G * kWorkerWarps, lane, rnd, x3);
@@ -1436,8 +1438,10 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
         }
         __syncthreads();
     }
-    // the next op of a program may reset or read the accumulators: order it after the fold
-    if (a.auc_acc && oi + 1 < a.n_ops) grid_barrier(a.bar, bar_target);
+    // a following sweep over the accumulators (AUC.reset_states recorded into the program) must come after the fold; any
+    // other op is ordered by its own barriers (the histogram is double-buffered by pass parity)
+    if (a.auc_acc && oi + 1 < a.n_ops && ops[oi + 1].kind == PROG_META && ops[oi + 1].w0 == a.auc_acc) grid_barrier(a.bar, bar_target);
+    shadows_valid = a.train != 0;
     ++pass_idx;
     }   // program ops
 

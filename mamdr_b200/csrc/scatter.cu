@@ -137,6 +137,302 @@ __global__ void __launch_bounds__(256) segment_sum_kernel(const __grid_constant_
 
 inline size_t al(size_t x) { return (x + 255) / 256 * 256; }
 
+// ================================================================================================================
+// Large-n path (n > kMaxN): multi-CTA.  Stable LSD radix sort of (id << 32 | position) by id (4 passes of 8 bits: per-tile
+// digit histograms, one scan, a stable scatter), head flags + scan -> unique ids / segment starts / permutation, then the
+// HBM-bound part: the n gradient rows are read ONCE by warps that each own a window of kWin consecutive sorted positions.
+// Summation order (deterministic, restated by the numpy oracle in tests/test_gpu_kernels.py): inside a window the rows of
+// an id are added sequentially in batch order; the window partials of an id that spans several windows are added in window
+// order.  For n <= kWin rows per id this is exactly the add.at order of the single-CTA path.
+// ================================================================================================================
+constexpr int kTile = 4096;      // keys per radix tile (256 threads x 16 rounds)
+constexpr int kRadixThreads = 256;
+constexpr int kWin = 256;        // sorted positions per window of the segment sum
+
+__global__ void __launch_bounds__(256) lg_key_init_kernel(const int32_t* __restrict__ ids, unsigned long long* __restrict__ keys, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keys[i] = ids[i] >= 0 ? (((unsigned long long)(uint32_t)ids[i]) << 32) | (unsigned long long)(uint32_t)i : ~0ull;
+}
+
+// per-tile digit histogram -> hist[digit * n_tiles + tile]
+__global__ void __launch_bounds__(kRadixThreads) lg_hist_kernel(const unsigned long long* __restrict__ keys, int64_t n, int shift,
+                                                                int* __restrict__ hist, int n_tiles) {
+    __shared__ int cnt[256];
+    const int t = threadIdx.x;
+    cnt[t] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * kTile;
+    for (int r = 0; r < kTile / kRadixThreads; ++r) {
+        const int64_t i = base + r * kRadixThreads + t;
+        if (i < n) atomicAdd(&cnt[(int)((keys[i] >> shift) & 0xffull)], 1);
+    }
+    __syncthreads();
+    hist[t * n_tiles + blockIdx.x] = cnt[t];
+}
+
+// exclusive scan of an int array by ONE block (the per-tile histograms: 256 * n_tiles entries; the per-block head counts)
+__global__ void __launch_bounds__(1024) lg_scan_kernel(int* __restrict__ a, int64_t m, int* __restrict__ total_out) {
+    __shared__ int part[1024];
+    const int t = threadIdx.x;
+    const int64_t per = (m + 1023) / 1024;
+    const int64_t beg = t * per, end = beg + per < m ? beg + per : m;
+    int sum = 0;
+    for (int64_t i = beg; i < end; ++i) sum += a[i];
+    part[t] = sum;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+        const int add = t >= off ? part[t - off] : 0;
+        __syncthreads();
+        part[t] += add;
+        __syncthreads();
+    }
+    int run = part[t] - sum;
+    for (int64_t i = beg; i < end; ++i) { const int v = a[i]; a[i] = run; run += v; }
+    if (t == 1023 && total_out) *total_out = part[t];
+}
+
+// stable scatter of one tile: 16 rounds of 256 keys in thread order; rank of a key = keys of the same digit in earlier
+// tiles (scanned histogram) + earlier rounds + earlier warps of the round + earlier lanes of the warp
+__global__ void __launch_bounds__(kRadixThreads) lg_scatter_kernel(const unsigned long long* __restrict__ in, unsigned long long* __restrict__ out,
+                                                                   int64_t n, int shift, const int* __restrict__ hist, int n_tiles) {
+    __shared__ int running[256];          // position of the next key of each digit
+    __shared__ int warp_cnt[8][256];
+    const int t = threadIdx.x, w = t >> 5, lane = t & 31;
+    running[t] = hist[t * n_tiles + blockIdx.x];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) warp_cnt[q][t] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * kTile;
+    for (int r = 0; r < kTile / kRadixThreads; ++r) {
+        const int64_t i = base + r * kRadixThreads + t;
+        const bool valid = i < n;
+        const unsigned long long key = valid ? in[i] : 0ull;
+        const int d = valid ? (int)((key >> shift) & 0xffull) : 256 + lane;   // invalid lanes never match anyone
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const int rank_in_warp = __popc(peers & ((1u << lane) - 1u));
+        if (valid && rank_in_warp == 0) warp_cnt[w][d] = __popc(peers);
+        __syncthreads();
+        if (valid) {
+            int pos = running[d] + rank_in_warp;
+            for (int q = 0; q < w; ++q) pos += warp_cnt[q][d];
+            out[pos] = key;
+        }
+        __syncthreads();
+        {   // digit t: advance by this round's keys, clear the per-warp counts
+            int add = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { add += warp_cnt[q][t]; warp_cnt[q][t] = 0; }
+            running[t] += add;
+        }
+        __syncthreads();
+    }
+}
+
+// head flags: per block of 1024 sorted keys, the number of segment heads among the real (non-padding) keys
+__global__ void __launch_bounds__(1024) lg_head_count_kernel(const unsigned long long* __restrict__ keys, int64_t n, int* __restrict__ blk_heads,
+                                                             int* __restrict__ n_valid) {
+    __shared__ int cnt;
+    if (threadIdx.x == 0) cnt = 0;
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+    bool head = false;
+    if (i < n && keys[i] != ~0ull) {
+        head = i == 0 || (uint32_t)(keys[i - 1] >> 32) != (uint32_t)(keys[i] >> 32);
+        if (i + 1 == n || keys[i + 1] == ~0ull) *n_valid = (int)(i + 1);
+    }
+    const unsigned b = __ballot_sync(0xffffffffu, head);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(&cnt, __popc(b));
+    __syncthreads();
+    if (threadIdx.x == 0) blk_heads[blockIdx.x] = cnt;
+}
+
+// unique ids, segment starts, permutation and the segment index of every sorted position
+__global__ void __launch_bounds__(1024) lg_head_write_kernel(const unsigned long long* __restrict__ keys, int64_t n, const int* __restrict__ blk_base,
+                                                             int32_t* __restrict__ uniq_ids, int32_t* __restrict__ seg_start, int32_t* __restrict__ perm,
+                                                             int32_t* __restrict__ seg_of) {
+    __shared__ int wsum[32];
+    const int t = threadIdx.x, w = t >> 5, lane = t & 31;
+    const int64_t i = (int64_t)blockIdx.x * 1024 + t;
+    const bool real = i < n && keys[i] != ~0ull;
+    const bool head = real && (i == 0 || (uint32_t)(keys[i - 1] >> 32) != (uint32_t)(keys[i] >> 32));
+    const unsigned b = __ballot_sync(0xffffffffu, head);
+    if (lane == 0) wsum[w] = __popc(b);
+    __syncthreads();
+    int before = blk_base[blockIdx.x];
+    for (int q = 0; q < w; ++q) before += wsum[q];
+    const int seg = before + __popc(b & ((1u << lane) - 1u)) + (head ? 1 : 0) - 1;   // index of the segment this position belongs to
+    if (real) {
+        perm[i] = (int32_t)(keys[i] & 0xffffffffull);
+        seg_of[i] = seg;
+        if (head) { uniq_ids[seg] = (int32_t)(keys[i] >> 32); seg_start[seg] = (int32_t)i; }
+    }
+}
+
+__global__ void lg_finish_kernel(const int* __restrict__ total, const int* __restrict__ n_valid, int32_t* __restrict__ n_uniq, int32_t* __restrict__ seg_start) {
+    n_uniq[0] = *total;
+    seg_start[*total] = *n_valid;
+}
+
+// warp per window of kWin sorted positions: pieces of segments inside the window are summed sequentially in batch order.  A
+// piece that is the whole segment goes to uniq_rows; a piece of a segment that started in an earlier window goes to
+// part[w][0], a piece of a segment that continues into the next window to part[w][1] (flags in pflag[w]).
+__global__ void __launch_bounds__(256) lg_window_sum_kernel(const float* __restrict__ grad_rows, int64_t grad_stride, int dim,
+                                                            const int32_t* __restrict__ perm, const int32_t* __restrict__ seg_of,
+                                                            const int32_t* __restrict__ seg_start, const int* __restrict__ n_valid_p,
+                                                            float* __restrict__ uniq_rows, float* __restrict__ part, int* __restrict__ pflag) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n_valid = *n_valid_p;
+    const int64_t w_beg = w * kWin;
+    if (w_beg >= n_valid) return;
+    const int64_t w_end = w_beg + kWin < n_valid ? w_beg + kWin : n_valid;
+    int flags = 0;
+    int64_t i = w_beg;
+    while (i < w_end) {
+        const int seg = seg_of[i];
+        const int64_t s_beg = seg_start[seg], s_end = seg_start[seg + 1];
+        const int64_t p_end = s_end < w_end ? s_end : w_end;            // this piece: [i, p_end)
+        const bool from_before = s_beg < w_beg, goes_on = s_end > w_end;
+        float* dst = (!from_before && !goes_on) ? uniq_rows + (int64_t)seg * dim
+                                                : part + ((int64_t)w * 2 + (from_before ? 0 : 1)) * dim;
+        if (from_before) flags |= 1;
+        else if (goes_on) flags |= 2;
+        for (int cc = 0; cc < dim; cc += 128) {
+            const int c = cc + lane * 4;
+            const bool active = c < dim;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int64_t b0 = i; b0 < p_end; b0 += 32) {
+                const int cnt = (int)(p_end - b0 < 32 ? p_end - b0 : 32);
+                const int myp = lane < cnt ? perm[b0 + lane] : 0;
+                for (int k = 0; k < cnt; k += 8) {
+                    float4 v[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int pq = __shfl_sync(0xffffffffu, myp, k + q < cnt ? k + q : cnt - 1);
+                        v[q] = (active && k + q < cnt) ? __ldcs(reinterpret_cast<const float4*>(grad_rows + (int64_t)pq * grad_stride + c))
+                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        if (k + q >= cnt) break;
+                        if (b0 == i && k + q == 0) {
+                            acc = v[q];
+                        } else {
+                            acc.x = __fadd_rn(acc.x, v[q].x); acc.y = __fadd_rn(acc.y, v[q].y);
+                            acc.z = __fadd_rn(acc.z, v[q].z); acc.w = __fadd_rn(acc.w, v[q].w);
+                        }
+                    }
+                }
+            }
+            if (active) *reinterpret_cast<float4*>(dst + c) = acc;
+        }
+        i = p_end;
+    }
+    if (lane == 0) pflag[w] = flags;
+}
+
+// warp per window that holds the FIRST piece of a segment spanning several windows: the following windows' part[.][0]
+// pieces are added in window order
+__global__ void __launch_bounds__(256) lg_window_merge_kernel(int dim, const int32_t* __restrict__ seg_of, const int32_t* __restrict__ seg_start,
+                                                              const int* __restrict__ n_valid_p, float* __restrict__ uniq_rows,
+                                                              const float* __restrict__ part, const int* __restrict__ pflag) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n_valid = *n_valid_p;
+    const int64_t w_beg = w * kWin;
+    if (w_beg >= n_valid || !(pflag[w] & 2)) return;
+    const int64_t w_end = w_beg + kWin;                    // < n_valid because the last segment of the window goes on
+    const int seg = seg_of[w_end - 1];
+    const int64_t s_end = seg_start[seg + 1];
+    const int64_t w_last = (s_end - 1) / kWin;
+    for (int cc = 0; cc < dim; cc += 128) {
+        const int c = cc + lane * 4;
+        if (c >= dim) continue;
+        float4 acc = *reinterpret_cast<const float4*>(part + ((int64_t)w * 2 + 1) * dim + c);
+        for (int64_t x = w + 1; x <= w_last; ++x) {
+            const float4 v = *reinterpret_cast<const float4*>(part + ((int64_t)x * 2 + 0) * dim + c);
+            acc.x = __fadd_rn(acc.x, v.x); acc.y = __fadd_rn(acc.y, v.y); acc.z = __fadd_rn(acc.z, v.z); acc.w = __fadd_rn(acc.w, v.w);
+        }
+        *reinterpret_cast<float4*>(uniq_rows + (int64_t)seg * dim + c) = acc;
+    }
+}
+
+struct LargeWs { size_t keys[2], hist, blk, scal, perm, seg_start, seg_of, part, pflag, total; };
+inline LargeWs large_ws(int64_t n, int dim) {
+    LargeWs w;
+    size_t off = 0;
+    auto take = [&](size_t b) { size_t o = off; off += al(b); return o; };
+    const int64_t n_tiles = (n + kTile - 1) / kTile, n_blk = (n + 1023) / 1024, n_win = (n + kWin - 1) / kWin;
+    w.keys[0] = take((size_t)n * 8); w.keys[1] = take((size_t)n * 8);
+    w.hist = take((size_t)256 * n_tiles * 4);
+    w.blk = take((size_t)n_blk * 4);
+    w.scal = take(64);
+    w.perm = take((size_t)n * 4); w.seg_start = take((size_t)(n + 1) * 4); w.seg_of = take((size_t)n * 4);
+    w.part = take((size_t)n_win * 2 * dim * 4); w.pflag = take((size_t)n_win * 4);
+    w.total = off;
+    return w;
+}
+
+}  // namespace
+
+extern "C" size_t mamdr_scatter_large_workspace_bytes(int64_t n, int32_t dim) {
+    if (n < 0 || dim <= 0) return 0;
+    return large_ws(n, dim).total;
+}
+
+extern "C" int mamdr_scatter_dedup_large_f32(mamdr_ctx* ctx, const int32_t* ids, const float* grad_rows, int64_t grad_stride, int64_t n,
+                                             int32_t dim, int32_t* uniq_ids, float* uniq_rows, int32_t* n_uniq, void* ws_, size_t ws_bytes,
+                                             mamdr_stream stream) {
+    MAMDR_REQUIRE(ctx, ctx != nullptr, MAMDR_E_INVALID, "ctx is NULL");
+    MAMDR_REQUIRE(ctx, n >= 1 && n < (1ll << 31), MAMDR_E_UNSUPPORTED, "n=%lld outside 1..2^31-1", (long long)n);
+    MAMDR_REQUIRE(ctx, ids && grad_rows && uniq_ids && uniq_rows && n_uniq && ws_, MAMDR_E_INVALID, "NULL pointer");
+    MAMDR_REQUIRE(ctx, dim > 0 && dim % 4 == 0 && grad_stride >= dim && grad_stride % 4 == 0, MAMDR_E_INVALID, "bad dim/stride");
+    MAMDR_REQUIRE(ctx, aligned16(grad_rows) && aligned16(uniq_rows) && aligned16(ws_), MAMDR_E_INVALID, "misaligned pointer");
+    const LargeWs w = large_ws(n, dim);
+    MAMDR_REQUIRE(ctx, ws_bytes >= w.total, MAMDR_E_WORKSPACE, "workspace too small: %zu < %zu", ws_bytes, w.total);
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned char* ws = (unsigned char*)ws_;
+    unsigned long long* keys[2] = {(unsigned long long*)(ws + w.keys[0]), (unsigned long long*)(ws + w.keys[1])};
+    int* hist = (int*)(ws + w.hist);
+    int* blk = (int*)(ws + w.blk);
+    int* scal = (int*)(ws + w.scal);   // [0] = number of unique ids, [1] = number of real (non-padding) entries
+    int32_t* perm = (int32_t*)(ws + w.perm);
+    int32_t* seg_start = (int32_t*)(ws + w.seg_start);
+    int32_t* seg_of = (int32_t*)(ws + w.seg_of);
+    float* part = (float*)(ws + w.part);
+    int* pflag = (int*)(ws + w.pflag);
+    const int n_tiles = (int)((n + kTile - 1) / kTile), n_blk = (int)((n + 1023) / 1024), n_win = (int)((n + kWin - 1) / kWin);
+    MAMDR_CUDA_OK(ctx, cudaMemsetAsync(scal, 0, 64, st));
+    lg_key_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ids, keys[0], n);
+    MAMDR_LAUNCH_OK(ctx);
+    int cur = 0;
+    for (int pass = 0; pass < 4; ++pass) {   // stable LSD passes over the id (bits 32..63); padding keys (all ones) end up last
+        const int shift = 32 + 8 * pass;
+        lg_hist_kernel<<<n_tiles, kRadixThreads, 0, st>>>(keys[cur], n, shift, hist, n_tiles);
+        MAMDR_LAUNCH_OK(ctx);
+        lg_scan_kernel<<<1, 1024, 0, st>>>(hist, (int64_t)256 * n_tiles, nullptr);
+        MAMDR_LAUNCH_OK(ctx);
+        lg_scatter_kernel<<<n_tiles, kRadixThreads, 0, st>>>(keys[cur], keys[cur ^ 1], n, shift, hist, n_tiles);
+        MAMDR_LAUNCH_OK(ctx);
+        cur ^= 1;
+    }
+    lg_head_count_kernel<<<n_blk, 1024, 0, st>>>(keys[cur], n, blk, scal + 1);
+    MAMDR_LAUNCH_OK(ctx);
+    lg_scan_kernel<<<1, 1024, 0, st>>>(blk, n_blk, scal);
+    MAMDR_LAUNCH_OK(ctx);
+    lg_head_write_kernel<<<n_blk, 1024, 0, st>>>(keys[cur], n, blk, uniq_ids, seg_start, perm, seg_of);
+    MAMDR_LAUNCH_OK(ctx);
+    lg_finish_kernel<<<1, 1, 0, st>>>(scal, scal + 1, n_uniq, seg_start);
+    MAMDR_LAUNCH_OK(ctx);
+    const unsigned wblocks = (unsigned)((n_win + 7) / 8);
+    lg_window_sum_kernel<<<wblocks, 256, 0, st>>>(grad_rows, grad_stride, dim, perm, seg_of, seg_start, scal + 1, uniq_rows, part, pflag);
+    MAMDR_LAUNCH_OK(ctx);
+    lg_window_merge_kernel<<<wblocks, 256, 0, st>>>(dim, seg_of, seg_start, scal + 1, uniq_rows, part, pflag);
+    MAMDR_LAUNCH_OK(ctx);
+    return MAMDR_OK;
+}
+
+namespace {
 }  // namespace
 
 int mamdr_scatter_init_kernels(mamdr_ctx* ctx) {

@@ -78,6 +78,60 @@ def test_scatter_dedup_bit_exact(n, n_ids, dim):
     np.testing.assert_array_equal(bits(ro[:k].cpu().numpy()), bits(er))
 
 
+def _oracle_dedup_windowed(ids, rows, win=256):
+    """numpy restatement of the large-n summation order (include/mamdr_b200.h: mamdr_scatter_dedup_large_f32): stable sort by
+    id; windows of `win` consecutive sorted positions; inside a window the rows of an id are added sequentially in batch order;
+    the window partials of an id are added in window order.  Negative ids are padding."""
+    keep = np.nonzero(ids >= 0)[0]
+    order = keep[np.argsort(ids[keep], kind="stable")]
+    sid = ids[order]
+    uniq, start = np.unique(sid, return_index=True)
+    end = np.append(start[1:], len(sid))
+    out = np.zeros((len(uniq), rows.shape[1]), dtype=np.float32)
+    for k, (s0, e0) in enumerate(zip(start, end)):
+        acc = None
+        w = s0 // win
+        while w * win < e0:
+            a, b = max(s0, w * win), min(e0, (w + 1) * win)
+            part = rows[order[a]].copy()
+            for p in order[a + 1:b]:
+                part = (part + rows[p]).astype(np.float32)
+            acc = part if acc is None else (acc + part).astype(np.float32)
+            w += 1
+        out[k] = acc
+    return uniq.astype(np.int32), out
+
+
+@pytest.mark.parametrize("n,n_ids,dim,zipf", [(20000, 3000, 128, True), (8193, 50, 64, False), (70001, 100000, 32, True), (300000, 5, 8, False)])
+def test_scatter_dedup_large_bit_exact(n, n_ids, dim, zipf):
+    """The multi-CTA path (n beyond the single-CTA limit): unique ids bit-exact, sums bit-exact against the numpy restatement of
+    its windowed order; hot ids (Zipf draws / 5 ids over 300 000 rows) span hundreds of windows; padding ids are skipped."""
+    rng = np.random.default_rng(n)
+    if zipf:
+        ids = np.minimum(rng.zipf(1.2, n) - 1, n_ids - 1).astype(np.int32)
+    else:
+        ids = rng.integers(0, n_ids, n).astype(np.int32)
+    ids[rng.integers(0, n, n // 50)] = -1            # padding entries
+    rows = rng.standard_normal((n, dim)).astype(np.float32)
+    lib = ctx().lib
+    assert n > lib.mamdr_scatter_max_n()
+    ws = torch.zeros(lib.mamdr_scatter_large_workspace_bytes(n, dim), dtype=torch.uint8, device="cuda")
+    uo = torch.full((n,), -1, dtype=torch.int32, device="cuda")
+    ro = torch.zeros(n, dim, device="cuda")
+    nu = torch.zeros(1, dtype=torch.int32, device="cuda")
+    d_ids, d_rows = dev(ids), dev(rows)
+    ctx().call("mamdr_scatter_dedup_large_f32", ptr(d_ids), ptr(d_rows), dim, n, dim, ptr(uo), ptr(ro), ptr(nu),
+               ptr(ws), ws.numel(), stream())
+    k = int(nu.item())
+    eu, er = _oracle_dedup_windowed(ids, rows)
+    assert k == len(eu)
+    np.testing.assert_array_equal(uo[:k].cpu().numpy(), eu)
+    np.testing.assert_array_equal(bits(ro[:k].cpu().numpy()), bits(er))
+    # linearity / conservation: the de-duplicated rows sum to the sum of all real rows (fp64 check, size independent)
+    tot = rows[ids >= 0].astype(np.float64).sum(axis=0)
+    np.testing.assert_allclose(ro[:k].cpu().numpy().astype(np.float64).sum(axis=0), tot, rtol=1e-4, atol=1e-2)
+
+
 # ---- K7 Adam / SGD --------------------------------------------------------------------------------------------
 def test_adam_bit_exact_over_steps():
     rng = np.random.default_rng(3)
