@@ -81,8 +81,9 @@ int mamdr_scatter_dedup_f32(mamdr_ctx* ctx, const int32_t* ids_dev, const float*
 /* The same de-duplication for n beyond mamdr_scatter_max_n() (any n < 2^31), multi-CTA: a stable radix sort of
  * (id, position) + head scan, then ONE pass over the n gradient rows at HBM bandwidth.  uniq_ids: ascending, bit-exact.
  * Summation order (deterministic): windows of 256 consecutive SORTED positions; inside a window the rows of an id are
- * added sequentially in batch order, the window partials of an id are added in window order (ids with <= 256
- * occurrences inside one window: exactly the numpy add.at order). */
+ * added sequentially in batch order; the window partials of an id are added in window order inside groups of 32
+ * windows (counted from the id's first window), then the group sums in order (an id whose rows lie inside one
+ * window: exactly the numpy add.at order). */
 size_t mamdr_scatter_large_workspace_bytes(int64_t n, int32_t dim);
 int mamdr_scatter_dedup_large_f32(mamdr_ctx* ctx, const int32_t* ids_dev, const float* grad_rows_dev,
                                   int64_t grad_stride, int64_t n, int32_t dim, int32_t* uniq_ids_dev,
@@ -124,6 +125,9 @@ typedef struct {
     int64_t        offset;      /* first position of the batch inside order */
     int32_t        rows;        /* b, 1..max_batch */
     int32_t        domain;      /* domain id shared by the whole batch */
+    int32_t        row0;        /* index of row 0 inside the (global) mini-batch: 0, or a rank's slice start when the batch is
+                                   split data-parallel (row-sharded tables) -- the dropout masks are indexed by the global row */
+    int32_t        reserved;
 } mamdr_batch;
 
 /* ---- optimizer state (replaces tf.train.AdamOptimizer's non-slot variables beta1_power /

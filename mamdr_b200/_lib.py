@@ -57,6 +57,8 @@ class Batch(C.Structure):
         ("offset", C.c_int64),
         ("rows", C.c_int32),
         ("domain", C.c_int32),
+        ("row0", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 

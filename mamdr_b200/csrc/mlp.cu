@@ -36,7 +36,7 @@ struct FwdEpilogue {  // H_out = dropout(relu(acc + bias))
         if (dp.enabled) {
             DropoutParams q = dp;
             q.step = (uint32_t)(state->step & 0xffffffffll);
-            const uint4 w = dropout_words4(q, (uint32_t)m * (uint32_t)N + (uint32_t)n);
+            const uint4 w = dropout_words4(q, ((uint32_t)m + q.row0) * (uint32_t)N + (uint32_t)n);   // element index of the GLOBAL batch row
             v[0] = dropout_apply(q, w.x, v[0]);
             v[1] = dropout_apply(q, w.y, v[1]);
             v[2] = dropout_apply(q, w.z, v[2]);
@@ -434,6 +434,7 @@ int run_forward(mamdr_ctx* ctx, const mamdr_mlp_desc* d, const mamdr_batch* b, c
         epi.dp.enabled = (train && d->dropout_rate > 0.f) ? 1 : 0;
         epi.dp.seed = d->dropout_seed + (uint32_t)l;
         epi.dp.step = 0;
+        epi.dp.row0 = (uint32_t)b->row0;
         double thr = floor((double)keep * 4294967296.0);
         epi.dp.threshold = thr >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)thr;
         epi.dp.scale = 1.0f / keep;

@@ -576,6 +576,7 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
         dp.scale = a.dropout_scale;
         dp.step = (uint32_t)(step_ctr & 0xffffffffll);
         dp.seed = a.dropout_seed;
+        dp.row0 = 0;
 
         const float alpha = __fdiv_rn(__fmul_rn(a.lr, __fsqrt_rn(__fsub_rn(1.0f, b2pow))), __fsub_rn(1.0f, b1pow));
         const float omb1 = __fsub_rn(1.0f, a.beta1), omb2 = __fsub_rn(1.0f, a.beta2);

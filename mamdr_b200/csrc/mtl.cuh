@@ -298,12 +298,13 @@ domain_grad_kernel(const float* __restrict__ Ed, const float* __restrict__ dsum,
     }
 }
 
-inline DropoutParams dropout_params(const mamdr_mtl_desc& d, bool train, uint32_t stream) {
+inline DropoutParams dropout_params(const mamdr_mtl_desc& d, bool train, uint32_t stream, uint32_t row0) {
     DropoutParams dp;
     const float keep = 1.0f - d.dropout_rate;
     dp.enabled = (train && d.dropout_rate > 0.f) ? 1 : 0;
     dp.seed = d.dropout_seed + stream;
     dp.step = 0;
+    dp.row0 = row0;
     const double thr = floor((double)keep * 4294967296.0);
     dp.threshold = thr >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)thr;
     dp.scale = 1.0f / keep;
@@ -342,7 +343,7 @@ static int validate(mamdr_ctx* ctx, const mamdr_mtl_desc* d, const mamdr_mtl_dom
 // one dense layer forward (bias + ReLU + dropout fused) for `ng` independent inputs / kernels of one shape
 static int fwd_layer(mamdr_ctx* ctx, int ng, const float* const* A, const float* const* W, const float* const* bias, float* const* out,
                      const uint32_t* streams, const mamdr_mtl_desc* d, bool train, const OptState* state, int rows, int K, int N,
-                     float* partials, unsigned int* tickets, cudaStream_t st) {
+                     float* partials, unsigned int* tickets, cudaStream_t st, uint32_t row0) {
     simt::GemmShape s{rows, N, K, K, N};
     // a lone narrow layer (gate, tower) has too few tiles to fill the GPU: split K, the last CTA of a tile runs the epilogue
     simt::LaunchPlan p = simt::plan(rows, N, K, ng == 1 ? ctx->sm_count : 0, ng == 1 ? kSmallSplit : 1);
@@ -355,7 +356,7 @@ static int fwd_layer(mamdr_ctx* ctx, int ng, const float* const* A, const float*
         ga.epi[g].out = out[g];
         ga.epi[g].N = N;
         ga.epi[g].state = state;
-        ga.epi[g].dp = dropout_params(*d, train, streams[g]);
+        ga.epi[g].dp = dropout_params(*d, train, streams[g], row0);
     }
     ga.split = (int)p.grid.z; ga.partial_stride = 0; ga.ticket_stride = 0;
     p.grid.z = ga.split * ng;
@@ -429,7 +430,7 @@ static int forward(mamdr_ctx* ctx, const mamdr_mtl_desc* d, const mamdr_mtl_doma
             out[j] = (float*)(ws + w.E[j][l + 1]);
             streams[j] = 8u * (uint32_t)dm->expert_id[j] + (uint32_t)l;
         }
-        rc = fwd_layer(ctx, k, A, W, bs, out, streams, d, train, state, rows, K, N, (float*)(ws + w.partials), (unsigned int*)(ws + w.tickets), st);
+        rc = fwd_layer(ctx, k, A, W, bs, out, streams, d, train, state, rows, K, N, (float*)(ws + w.partials), (unsigned int*)(ws + w.tickets), st, (uint32_t)b->row0);
         if (rc) return rc;
         K = N;
     }
@@ -443,7 +444,7 @@ static int forward(mamdr_ctx* ctx, const mamdr_mtl_desc* d, const mamdr_mtl_doma
             bs[0] = params + dm->off_gate_bias[l];
             out[0] = (float*)(ws + w.G[l + 1]);
             streams[0] = 4096u + 8u * (uint32_t)t + (uint32_t)l;
-            rc = fwd_layer(ctx, 1, A, W, bs, out, streams, d, train, state, rows, K, N, (float*)(ws + w.partials), (unsigned int*)(ws + w.tickets), st);
+            rc = fwd_layer(ctx, 1, A, W, bs, out, streams, d, train, state, rows, K, N, (float*)(ws + w.partials), (unsigned int*)(ws + w.tickets), st, (uint32_t)b->row0);
             if (rc) return rc;
             K = N;
         }
@@ -465,7 +466,7 @@ static int forward(mamdr_ctx* ctx, const mamdr_mtl_desc* d, const mamdr_mtl_doma
         bs[0] = params + dm->off_tower_bias[l];
         out[0] = (float*)(ws + w.T[l + 1]);
         streams[0] = 8192u + 8u * (uint32_t)t + (uint32_t)l;
-        rc = fwd_layer(ctx, 1, A, W, bs, out, streams, d, train, state, rows, K, N, (float*)(ws + w.partials), (unsigned int*)(ws + w.tickets), st);
+        rc = fwd_layer(ctx, 1, A, W, bs, out, streams, d, train, state, rows, K, N, (float*)(ws + w.partials), (unsigned int*)(ws + w.tickets), st, (uint32_t)b->row0);
         if (rc) return rc;
         K = N;
     }

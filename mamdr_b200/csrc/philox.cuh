@@ -27,6 +27,7 @@ struct DropoutParams {
     uint32_t threshold;  // keep iff word < threshold
     float    scale;      // 1 / keep_prob
     int      enabled;
+    uint32_t row0;       // batch row of local row 0 (a rank's slice of a data-parallel mini-batch; 0 otherwise)
 };
 
 // random words for the 4 consecutive elements starting at element index e (e % 4 == 0)

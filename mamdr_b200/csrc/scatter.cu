@@ -143,7 +143,8 @@ inline size_t al(size_t x) { return (x + 255) / 256 * 256; }
 // HBM-bound part: the n gradient rows are read ONCE by warps that each own a window of kWin consecutive sorted positions.
 // Summation order (deterministic, restated by the numpy oracle in tests/test_gpu_kernels.py): inside a window the rows of
 // an id are added sequentially in batch order; the window partials of an id that spans several windows are added in window
-// order.  For n <= kWin rows per id this is exactly the add.at order of the single-CTA path.
+// order within groups of 32 windows, then the group sums in order.  An id whose rows lie inside one window: exactly the
+// add.at order of the single-CTA path.
 // ================================================================================================================
 constexpr int kTile = 4096;      // keys per radix tile (256 threads x 16 rounds)
 constexpr int kRadixThreads = 256;
@@ -170,25 +171,93 @@ __global__ void __launch_bounds__(kRadixThreads) lg_hist_kernel(const unsigned l
     hist[t * n_tiles + blockIdx.x] = cnt[t];
 }
 
-// exclusive scan of an int array by ONE block (the per-tile histograms: 256 * n_tiles entries; the per-block head counts)
+// exclusive scan of an int array by ONE block (the per-tile histograms: 256 * n_tiles entries; the per-block head counts):
+// tiles of 4096 entries, 4 consecutive ints per thread (coalesced), warp shuffles + one cross-warp step per tile
 __global__ void __launch_bounds__(1024) lg_scan_kernel(int* __restrict__ a, int64_t m, int* __restrict__ total_out) {
-    __shared__ int part[1024];
-    const int t = threadIdx.x;
-    const int64_t per = (m + 1023) / 1024;
-    const int64_t beg = t * per, end = beg + per < m ? beg + per : m;
-    int sum = 0;
-    for (int64_t i = beg; i < end; ++i) sum += a[i];
-    part[t] = sum;
+    __shared__ int wsum[32];
+    __shared__ int carry_s;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    if (t == 0) carry_s = 0;
     __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {
-        const int add = t >= off ? part[t - off] : 0;
+    for (int64_t base = 0; base < m; base += 4096) {
+        const int64_t i0 = base + (int64_t)t * 4;
+        int v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = i0 + q < m ? a[i0 + q] : 0;
+        const int mine = v[0] + v[1] + v[2] + v[3];
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+        }
+        if (lane == 31) wsum[w] = incl;
         __syncthreads();
-        part[t] += add;
+        const int carry = carry_s;
+        if (w == 0) {
+            int ws = wsum[lane];
+            int wi = ws;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int up = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += up;
+            }
+            wsum[lane] = wi - ws;                      // exclusive prefix of the warp sums
+            if (lane == 31) carry_s = carry + wi;      // running total after this tile
+        }
+        __syncthreads();
+        int run = carry + wsum[w] + incl - mine;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (i0 + q < m) a[i0 + q] = run;
+            run += v[q];
+        }
         __syncthreads();
     }
-    int run = part[t] - sum;
-    for (int64_t i = beg; i < end; ++i) { const int v = a[i]; a[i] = run; run += v; }
-    if (t == 1023 && total_out) *total_out = part[t];
+    if (t == 0 && total_out) *total_out = carry_s;
+}
+
+// the histogram scan, parallel over the digits: hist is [digit][tile]; block d scans its row (exclusive) and publishes the row
+// total; a second launch adds the totals of the smaller digits.  (One 1024-thread block over 256 * n_tiles entries is a
+// serial tail of ~60 us per pass at 2 Mi keys.)
+__global__ void __launch_bounds__(256) lg_digit_scan_kernel(int* __restrict__ hist, int n_tiles, int* __restrict__ digit_total) {
+    __shared__ int wsum[8];
+    __shared__ int carry_s;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    int* row = hist + (int64_t)blockIdx.x * n_tiles;
+    if (t == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < n_tiles; base += 256) {
+        const int i = base + t;
+        const int v = i < n_tiles ? row[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+        }
+        if (lane == 31) wsum[w] = incl;
+        __syncthreads();
+        const int carry = carry_s;
+        int before = 0;
+        for (int q = 0; q < w; ++q) before += wsum[q];
+        if (i < n_tiles) row[i] = carry + before + incl - v;
+        __syncthreads();
+        if (t == 255) carry_s = carry + before + incl;
+        __syncthreads();
+    }
+    if (t == 0) digit_total[blockIdx.x] = carry_s;
+}
+__global__ void __launch_bounds__(256) lg_digit_base_kernel(int* __restrict__ hist, int n_tiles, const int* __restrict__ digit_total) {
+    __shared__ int base_s;
+    if (threadIdx.x == 0) {
+        int b = 0;
+        for (int d = 0; d < (int)blockIdx.x; ++d) b += digit_total[d];
+        base_s = b;
+    }
+    __syncthreads();
+    int* row = hist + (int64_t)blockIdx.x * n_tiles;
+    for (int i = threadIdx.x; i < n_tiles; i += 256) row[i] += base_s;
 }
 
 // stable scatter of one tile: 16 rounds of 256 keys in thread order; rank of a key = keys of the same digit in earlier
@@ -275,64 +344,131 @@ __global__ void lg_finish_kernel(const int* __restrict__ total, const int* __res
 
 // warp per window of kWin sorted positions: pieces of segments inside the window are summed sequentially in batch order.  A
 // piece that is the whole segment goes to uniq_rows; a piece of a segment that started in an earlier window goes to
-// part[w][0], a piece of a segment that continues into the next window to part[w][1] (flags in pflag[w]).
-__global__ void __launch_bounds__(256) lg_window_sum_kernel(const float* __restrict__ grad_rows, int64_t grad_stride, int dim,
-                                                            const int32_t* __restrict__ perm, const int32_t* __restrict__ seg_of,
-                                                            const int32_t* __restrict__ seg_start, const int* __restrict__ n_valid_p,
-                                                            float* __restrict__ uniq_rows, float* __restrict__ part, int* __restrict__ pflag) {
-    const int lane = threadIdx.x & 31;
+// part[w][0], a piece of a segment that continues into the next window to part[w][1] (flags in pflag[w]).  The window's
+// permutation and segment indices are staged in shared memory first, so the row loads run 16 deep across piece boundaries
+// (cold ids make one-row pieces: a per-piece dependent load chain would serialise the whole window).
+__global__ void __launch_bounds__(256, 2) lg_window_sum_kernel(const float* __restrict__ grad_rows, int64_t grad_stride, int dim,
+                                                               const int32_t* __restrict__ perm, const int32_t* __restrict__ seg_of,
+                                                               const int32_t* __restrict__ seg_start, const int* __restrict__ n_valid_p,
+                                                               float* __restrict__ uniq_rows, float* __restrict__ part, int* __restrict__ pflag) {
+    __shared__ int s_perm[8][kWin], s_seg[8][kWin];
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
     const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n_valid = *n_valid_p;
     const int64_t w_beg = w * kWin;
     if (w_beg >= n_valid) return;
     const int64_t w_end = w_beg + kWin < n_valid ? w_beg + kWin : n_valid;
-    int flags = 0;
-    int64_t i = w_beg;
-    while (i < w_end) {
-        const int seg = seg_of[i];
-        const int64_t s_beg = seg_start[seg], s_end = seg_start[seg + 1];
-        const int64_t p_end = s_end < w_end ? s_end : w_end;            // this piece: [i, p_end)
-        const bool from_before = s_beg < w_beg, goes_on = s_end > w_end;
-        float* dst = (!from_before && !goes_on) ? uniq_rows + (int64_t)seg * dim
-                                                : part + ((int64_t)w * 2 + (from_before ? 0 : 1)) * dim;
-        if (from_before) flags |= 1;
-        else if (goes_on) flags |= 2;
-        for (int cc = 0; cc < dim; cc += 128) {
-            const int c = cc + lane * 4;
-            const bool active = c < dim;
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int64_t b0 = i; b0 < p_end; b0 += 32) {
-                const int cnt = (int)(p_end - b0 < 32 ? p_end - b0 : 32);
-                const int myp = lane < cnt ? perm[b0 + lane] : 0;
-                for (int k = 0; k < cnt; k += 8) {
-                    float4 v[8];
+    const int total = (int)(w_end - w_beg);
+    for (int q = lane; q < total; q += 32) { s_perm[wl][q] = perm[w_beg + q]; s_seg[wl][q] = seg_of[w_beg + q]; }
+    __syncwarp();
+    const int first_seg = s_seg[wl][0], last_seg = s_seg[wl][total - 1];
+    const bool from_before = seg_start[first_seg] < w_beg, goes_on = seg_start[last_seg + 1] > w_end;
+    for (int cc = 0; cc < dim; cc += 128) {
+        const int c = cc + lane * 4;
+        const bool active = c < dim;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        int cur = first_seg;
+        bool fresh = true;
+        auto flush = [&](int seg) {
+            float* dst = (seg == first_seg && from_before) ? part + ((int64_t)w * 2 + 0) * dim
+                       : (seg == last_seg && goes_on)      ? part + ((int64_t)w * 2 + 1) * dim
+                                                           : uniq_rows + (int64_t)seg * dim;
+            if (active) *reinterpret_cast<float4*>(dst + c) = acc;
+        };
+        auto load8 = [&](int r0, float4 (&v)[8]) {
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const int pq = __shfl_sync(0xffffffffu, myp, k + q < cnt ? k + q : cnt - 1);
-                        v[q] = (active && k + q < cnt) ? __ldcs(reinterpret_cast<const float4*>(grad_rows + (int64_t)pq * grad_stride + c))
-                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
+            for (int q = 0; q < 8; ++q)
+                v[q] = (active && r0 + q < total) ? __ldcs(reinterpret_cast<const float4*>(grad_rows + (int64_t)s_perm[wl][r0 + q] * grad_stride + c))
+                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        auto add8 = [&](int r0, const float4 (&v)[8]) {
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        if (k + q >= cnt) break;
-                        if (b0 == i && k + q == 0) {
-                            acc = v[q];
-                        } else {
-                            acc.x = __fadd_rn(acc.x, v[q].x); acc.y = __fadd_rn(acc.y, v[q].y);
-                            acc.z = __fadd_rn(acc.z, v[q].z); acc.w = __fadd_rn(acc.w, v[q].w);
-                        }
-                    }
+            for (int q = 0; q < 8; ++q) {
+                if (r0 + q >= total) break;
+                const int seg = s_seg[wl][r0 + q];
+                if (seg != cur) { flush(cur); cur = seg; fresh = true; }
+                if (fresh) {
+                    acc = v[q];
+                    fresh = false;
+                } else {
+                    acc.x = __fadd_rn(acc.x, v[q].x); acc.y = __fadd_rn(acc.y, v[q].y);
+                    acc.z = __fadd_rn(acc.z, v[q].z); acc.w = __fadd_rn(acc.w, v[q].w);
                 }
             }
-            if (active) *reinterpret_cast<float4*>(dst + c) = acc;
+        };
+        float4 va[8], vb[8];
+        load8(0, va);
+        for (int r0 = 0; r0 < total; r0 += 16) {
+            if (r0 + 8 < total) load8(r0 + 8, vb);
+            add8(r0, va);
+            if (r0 + 16 < total) load8(r0 + 16, va);
+            if (r0 + 8 < total) add8(r0 + 8, vb);
         }
-        i = p_end;
+        flush(cur);
     }
-    if (lane == 0) pflag[w] = flags;
+    if (lane == 0) pflag[w] = (from_before ? 1 : 0) | ((goes_on && !(from_before && first_seg == last_seg)) ? 2 : 0);
 }
 
-// warp per window that holds the FIRST piece of a segment spanning several windows: the following windows' part[.][0]
-// pieces are added in window order
+// Segments that span several windows: the window pieces are first summed in GROUPS of kGroup consecutive windows (offset
+// from the segment's first window in [kGroup g, kGroup g + kGroup), added in window order, in place into the group's first
+// piece), then the group sums are added in order.  A hot id (Zipf head) spans thousands of windows: one level would be one
+// long serial chain.
+constexpr int kGroup = 32;
+
+__device__ __forceinline__ void lg_sum_pieces(const float* part, int dim, int lane, int64_t x_first, int64_t x_last, int64_t step, float4* acc, int cc) {
+    const int c = cc + lane * 4;
+    for (int64_t x0 = x_first; x0 <= x_last; x0 += 16 * step) {   // the (independent) loads run 16 ahead of the ordered adds
+        float4 v[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+            v[q] = x0 + q * step <= x_last ? __ldcs(reinterpret_cast<const float4*>(part + ((int64_t)(x0 + q * step) * 2 + 0) * dim + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            if (x0 + q * step > x_last) break;
+            acc->x = __fadd_rn(acc->x, v[q].x); acc->y = __fadd_rn(acc->y, v[q].y); acc->z = __fadd_rn(acc->z, v[q].z); acc->w = __fadd_rn(acc->w, v[q].w);
+        }
+    }
+}
+
+// level 1: warp per window; a window leads a group when its piece has offset 0 (the segment starts here and goes on: slot 1)
+// or an offset that is a multiple of kGroup (slot 0)
+__global__ void __launch_bounds__(256) lg_window_group_kernel(int dim, const int32_t* __restrict__ seg_of, const int32_t* __restrict__ seg_start,
+                                                              const int* __restrict__ n_valid_p, float* __restrict__ part, const int* __restrict__ pflag) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n_valid = *n_valid_p;
+    const int64_t w_beg = w * kWin;
+    if (w_beg >= n_valid) return;
+    const int flags = pflag[w];
+    for (int role = 0; role < 2; ++role) {
+        int seg;
+        int slot;
+        if (role == 0) {          // the segment that starts in this window and continues
+            if (!(flags & 2)) continue;
+            seg = seg_of[w_beg + kWin - 1];
+            slot = 1;
+        } else {                  // the segment that came from an earlier window
+            if (!(flags & 1)) continue;
+            seg = seg_of[w_beg];
+            const int64_t w_first = seg_start[seg] / kWin;
+            if ((w - w_first) % kGroup != 0) continue;
+            slot = 0;
+        }
+        const int64_t w_last = ((int64_t)seg_start[seg + 1] - 1) / kWin;
+        const int64_t x_last = w + kGroup - 1 < w_last ? w + kGroup - 1 : w_last;
+        if (x_last <= w) continue;
+        for (int cc = 0; cc < dim; cc += 128) {
+            const int c = cc + lane * 4;
+            if (c >= dim) continue;
+            float* mine = part + ((int64_t)w * 2 + slot) * dim + c;
+            float4 acc = *reinterpret_cast<const float4*>(mine);
+            lg_sum_pieces(part, dim, lane, w + 1, x_last, 1, &acc, cc);
+            *reinterpret_cast<float4*>(mine) = acc;
+        }
+    }
+}
+
+// level 2: warp per window in which a spanning segment starts: the group sums in order
 __global__ void __launch_bounds__(256) lg_window_merge_kernel(int dim, const int32_t* __restrict__ seg_of, const int32_t* __restrict__ seg_start,
                                                               const int* __restrict__ n_valid_p, float* __restrict__ uniq_rows,
                                                               const float* __restrict__ part, const int* __restrict__ pflag) {
@@ -341,23 +477,18 @@ __global__ void __launch_bounds__(256) lg_window_merge_kernel(int dim, const int
     const int n_valid = *n_valid_p;
     const int64_t w_beg = w * kWin;
     if (w_beg >= n_valid || !(pflag[w] & 2)) return;
-    const int64_t w_end = w_beg + kWin;                    // < n_valid because the last segment of the window goes on
-    const int seg = seg_of[w_end - 1];
-    const int64_t s_end = seg_start[seg + 1];
-    const int64_t w_last = (s_end - 1) / kWin;
+    const int seg = seg_of[w_beg + kWin - 1];            // < n_valid because the last segment of the window goes on
+    const int64_t w_last = ((int64_t)seg_start[seg + 1] - 1) / kWin;
     for (int cc = 0; cc < dim; cc += 128) {
         const int c = cc + lane * 4;
         if (c >= dim) continue;
         float4 acc = *reinterpret_cast<const float4*>(part + ((int64_t)w * 2 + 1) * dim + c);
-        for (int64_t x = w + 1; x <= w_last; ++x) {
-            const float4 v = *reinterpret_cast<const float4*>(part + ((int64_t)x * 2 + 0) * dim + c);
-            acc.x = __fadd_rn(acc.x, v.x); acc.y = __fadd_rn(acc.y, v.y); acc.z = __fadd_rn(acc.z, v.z); acc.w = __fadd_rn(acc.w, v.w);
-        }
+        lg_sum_pieces(part, dim, lane, w + kGroup, w_last, kGroup, &acc, cc);
         *reinterpret_cast<float4*>(uniq_rows + (int64_t)seg * dim + c) = acc;
     }
 }
 
-struct LargeWs { size_t keys[2], hist, blk, scal, perm, seg_start, seg_of, part, pflag, total; };
+struct LargeWs { size_t keys[2], hist, dtot, blk, scal, perm, seg_start, seg_of, part, pflag, total; };
 inline LargeWs large_ws(int64_t n, int dim) {
     LargeWs w;
     size_t off = 0;
@@ -365,6 +496,7 @@ inline LargeWs large_ws(int64_t n, int dim) {
     const int64_t n_tiles = (n + kTile - 1) / kTile, n_blk = (n + 1023) / 1024, n_win = (n + kWin - 1) / kWin;
     w.keys[0] = take((size_t)n * 8); w.keys[1] = take((size_t)n * 8);
     w.hist = take((size_t)256 * n_tiles * 4);
+    w.dtot = take(256 * 4);
     w.blk = take((size_t)n_blk * 4);
     w.scal = take(64);
     w.perm = take((size_t)n * 4); w.seg_start = take((size_t)(n + 1) * 4); w.seg_of = take((size_t)n * 4);
@@ -394,6 +526,7 @@ extern "C" int mamdr_scatter_dedup_large_f32(mamdr_ctx* ctx, const int32_t* ids,
     unsigned char* ws = (unsigned char*)ws_;
     unsigned long long* keys[2] = {(unsigned long long*)(ws + w.keys[0]), (unsigned long long*)(ws + w.keys[1])};
     int* hist = (int*)(ws + w.hist);
+    int* dtot = (int*)(ws + w.dtot);
     int* blk = (int*)(ws + w.blk);
     int* scal = (int*)(ws + w.scal);   // [0] = number of unique ids, [1] = number of real (non-padding) entries
     int32_t* perm = (int32_t*)(ws + w.perm);
@@ -410,7 +543,9 @@ extern "C" int mamdr_scatter_dedup_large_f32(mamdr_ctx* ctx, const int32_t* ids,
         const int shift = 32 + 8 * pass;
         lg_hist_kernel<<<n_tiles, kRadixThreads, 0, st>>>(keys[cur], n, shift, hist, n_tiles);
         MAMDR_LAUNCH_OK(ctx);
-        lg_scan_kernel<<<1, 1024, 0, st>>>(hist, (int64_t)256 * n_tiles, nullptr);
+        lg_digit_scan_kernel<<<256, 256, 0, st>>>(hist, n_tiles, dtot);
+        MAMDR_LAUNCH_OK(ctx);
+        lg_digit_base_kernel<<<256, 256, 0, st>>>(hist, n_tiles, dtot);
         MAMDR_LAUNCH_OK(ctx);
         lg_scatter_kernel<<<n_tiles, kRadixThreads, 0, st>>>(keys[cur], keys[cur ^ 1], n, shift, hist, n_tiles);
         MAMDR_LAUNCH_OK(ctx);
@@ -426,6 +561,8 @@ extern "C" int mamdr_scatter_dedup_large_f32(mamdr_ctx* ctx, const int32_t* ids,
     MAMDR_LAUNCH_OK(ctx);
     const unsigned wblocks = (unsigned)((n_win + 7) / 8);
     lg_window_sum_kernel<<<wblocks, 256, 0, st>>>(grad_rows, grad_stride, dim, perm, seg_of, seg_start, scal + 1, uniq_rows, part, pflag);
+    MAMDR_LAUNCH_OK(ctx);
+    lg_window_group_kernel<<<wblocks, 256, 0, st>>>(dim, seg_of, seg_start, scal + 1, part, pflag);
     MAMDR_LAUNCH_OK(ctx);
     lg_window_merge_kernel<<<wblocks, 256, 0, st>>>(dim, seg_of, seg_start, scal + 1, uniq_rows, part, pflag);
     MAMDR_LAUNCH_OK(ctx);

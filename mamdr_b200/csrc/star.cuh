@@ -285,7 +285,7 @@ static int star_forward(mamdr_ctx* ctx, const mamdr_star_desc* d, const mamdr_ba
         epi.out = (float*)(ws + w.H[l + 1]);
         epi.N = N;
         epi.state = nullptr;
-        epi.dp.enabled = 0; epi.dp.seed = 0; epi.dp.step = 0; epi.dp.threshold = 0; epi.dp.scale = 1.f;
+        epi.dp.enabled = 0; epi.dp.seed = 0; epi.dp.step = 0; epi.dp.threshold = 0; epi.dp.scale = 1.f; epi.dp.row0 = 0;
         simt::GemmShape s{rows, N, K, K, N};
         simt::LaunchPlan p = simt::plan(rows, N, K, 0, 1);
         simt::gemm_kernel<true, true, FwdEpilogue><<<p.grid, simt::THREADS, 0, st>>>((const float*)(ws + w.H[l]), (const float*)(ws + w.Weff[l]), s,

@@ -15,8 +15,8 @@ the mathematically identical data-parallel restatement of one Keras train step o
 Index bucketing (sort by owner, bincount, inverse permutation) uses torch tensor ops: plumbing around the collectives.  The
 exchange buffers have a FIXED capacity (world x local-batch entries, -1 padded ids that the de-duplication skips), so every
 all-to-all has static, equal splits and a step never synchronises with the host.
-Dropout masks are indexed by the LOCAL row, so with dropout > 0 the masks are a different (equally distributed) draw than
-the single-GPU schedule; parity against the oracle is asserted with dropout = 0 (tests/test_gpu_sharded.py).
+Dropout masks are indexed by the GLOBAL batch row (``mamdr_batch.row0`` = the slice start), so the sharded step draws exactly
+the masks of the unsharded one; parity against the oracle is asserted with dropout 0 and 0.5 (tests/test_gpu_sharded.py).
 """
 import ctypes as C
 
@@ -225,6 +225,7 @@ class ShardedJointTrainer(_GraphedSteps):
             m.user_table, m.item_table = rows_u, rows_i
             data = self._local_data(y, domain, bl)
             b = m._batch(data, 0, bl, False)
+            b.row0 = start            # dropout masks follow the GLOBAL batch row: the same draw as the unsharded step
             m.ctx.call("mamdr_mlp_train_step", C.byref(m.desc), C.byref(b), _ptr(rows_u), _ptr(rows_i), _ptr(m.params), _ptr(m.grads),
                        _ptr(m.ws), m.ws_bytes, _ptr(m.opt_state), _ptr(self.loss_local), None, _ptr(m.auc_acc), _ptr(m.thresholds),
                        m.num_thresholds, m.precision, st)
@@ -322,6 +323,7 @@ class ShardedMTLTrainer(_GraphedSteps):
         if bl:
             data = self._local_data(y, t, bl)
             b = m._batch(data, 0, bl, False)
+            b.row0 = start            # dropout masks follow the GLOBAL batch row: the same draw as the unsharded step
             m.ctx.call("mamdr_mtl_train_step", C.byref(m.desc), C.byref(m.domains[t]), C.byref(b), _ptr(rows_u), _ptr(rows_i),
                        _ptr(m.params), _ptr(m.grads), _ptr(m.ws), m.ws_bytes, _ptr(m.opt_state), _ptr(self.loss_local), None,
                        _ptr(m.auc_acc), _ptr(m.thresholds), m.num_thresholds, st)

@@ -32,7 +32,7 @@ def test_struct_sizes_match_header():
     from mamdr_b200 import _lib
     # mamdr_mlp_desc: 4 + 12 + 32 + 4 + 4 (+0 pad) + 16 + 4*4 + 3*8 + 64 + 64 + 16 + 8
     assert ctypes.sizeof(_lib.MlpDesc) == 264
-    assert ctypes.sizeof(_lib.Batch) == 48
+    assert ctypes.sizeof(_lib.Batch) == 56
     assert _lib.load().mamdr_opt_state_bytes() == 32
 
 

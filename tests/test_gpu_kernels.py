@@ -78,10 +78,11 @@ def test_scatter_dedup_bit_exact(n, n_ids, dim):
     np.testing.assert_array_equal(bits(ro[:k].cpu().numpy()), bits(er))
 
 
-def _oracle_dedup_windowed(ids, rows, win=256):
+def _oracle_dedup_windowed(ids, rows, win=256, group=32):
     """numpy restatement of the large-n summation order (include/mamdr_b200.h: mamdr_scatter_dedup_large_f32): stable sort by
     id; windows of `win` consecutive sorted positions; inside a window the rows of an id are added sequentially in batch order;
-    the window partials of an id are added in window order.  Negative ids are padding."""
+    the window partials of an id are added in window order inside groups of `group` windows, then the group sums in order.
+    Negative ids are padding."""
     keep = np.nonzero(ids >= 0)[0]
     order = keep[np.argsort(ids[keep], kind="stable")]
     sid = ids[order]
@@ -89,15 +90,24 @@ def _oracle_dedup_windowed(ids, rows, win=256):
     end = np.append(start[1:], len(sid))
     out = np.zeros((len(uniq), rows.shape[1]), dtype=np.float32)
     for k, (s0, e0) in enumerate(zip(start, end)):
-        acc = None
+        pieces = []
         w = s0 // win
         while w * win < e0:
             a, b = max(s0, w * win), min(e0, (w + 1) * win)
             part = rows[order[a]].copy()
             for p in order[a + 1:b]:
                 part = (part + rows[p]).astype(np.float32)
-            acc = part if acc is None else (acc + part).astype(np.float32)
+            pieces.append(part)
             w += 1
+        groups = []
+        for g0 in range(0, len(pieces), group):
+            acc = pieces[g0]
+            for part in pieces[g0 + 1:g0 + group]:
+                acc = (acc + part).astype(np.float32)
+            groups.append(acc)
+        acc = groups[0]
+        for gsum in groups[1:]:
+            acc = (acc + gsum).astype(np.float32)
         out[k] = acc
     return uniq.astype(np.int32), out
 
