@@ -470,7 +470,7 @@ def run_sharded(args):
         _emit(({"metric": "joint-train samples/sec (Amazon-13 shape, row-sharded trainable tables)", "value": mb * 1024 / (msv * 1e-3),
                           "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": msv,
                           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                          "config": {"workload": "%s train steps, trainable tables row-sharded over %d rank(s), NCCL all-to-all, %d mini-batches of 1024 per step%s" % (tower, world, mb, ", one CUDA graph per (sub-model, rows) incl. the collectives" if args.graphs else "")},
+                          "config": {"workload": "%s train steps, trainable tables row-sharded over %d rank(s), NCCL all-to-all, %d mini-batches of 1024 per step%s" % (tower, world, mb, "")},
                           "roofline": {"bound": "hbm", "achieved": alg * mb / (msv * 1e-3) / 1e9, "unit": "GB/s",
                                        "note": "aggregate table-sweep bytes (24 B per table element per mini-batch) over all ranks / step time"},
                           "us_per_minibatch": 1e3 * msv / mb}))
@@ -720,8 +720,8 @@ def main():
     ap.add_argument("--precision", default=None, choices=[None, "fp32", "tf32", "tf32x3"],
                     help="tower GEMM mode (default tf32x3: tcgen05 with fp32-equivalent products)")
     ap.add_argument("--no-micro", action="store_true")
-    ap.add_argument("--graphs", action="store_true", help="sharded workloads: replay each step from a CUDA graph that includes the "
-                    "NCCL collectives (opt-in, unreliable: 1.7x at 2 GPUs for the mmoe tower, but the capture hangs for the mlp tower)")
+    ap.add_argument("--graphs", action="store_true", help="removed: CUDA-graph replay of sharded steps (NCCL collectives inside captures "
+                    "dead-locked); the flag is rejected")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: everything the library prints while building (dataset banners ...) goes to stderr

@@ -122,53 +122,21 @@ def _uneven_gather(parts, mine, sizes):
         p.copy_(b[:p.shape[0]])
 
 
-class _GraphedSteps(object):
-    """CUDA-graph replay of whole train steps, NCCL collectives included: with fixed-capacity exchange buffers every shape
-    in a step is static, so one graph per (sub-model, batch rows) is captured on first use and replayed afterwards -- the
-    ~100 host-side launches / collectives of a step collapse into one `cudaGraphLaunch`."""
+class _Steps(object):
+    """`step` = one eager `train_on_batch`.  (Round 1 had an opt-in CUDA-graph replay of whole steps including the NCCL
+    collectives; captures of collectives dead-locked for some shapes on this stack and the path was removed -- the routing /
+    packing work it was hiding is device-side now and the eager step never synchronises with the host.)"""
 
-    def _init_graphs(self, use_graphs):
-        self.use_graphs = bool(use_graphs)
-        self._graphs = {}
-        bs = self.batch_size
-        self._in_uid = torch.zeros(bs, dtype=torch.int32, device=self.device)
-        self._in_pid = torch.zeros(bs, dtype=torch.int32, device=self.device)
-        self._in_lab = torch.zeros(bs, dtype=torch.float32, device=self.device)
-        if self.use_graphs:
-            # the communicator and every peer-to-peer / ring connection are established eagerly, before any capture (NCCL
-            # sets connections up lazily on first use; doing that inside a capture can dead-lock against a peer that is
-            # already replaying)
-            x = torch.zeros(4 * self.world, dtype=torch.float32, device=self.device)
-            y = torch.empty_like(x)
-            dist.all_to_all_single(y, x)
-            dist.all_reduce(x)
-            dist.barrier()
-            torch.cuda.synchronize(self.device)
+    def _init_graphs(self, use_graphs=False):
+        if use_graphs:
+            raise ValueError("CUDA-graph replay of sharded steps was removed (NCCL collectives inside captures dead-locked); "
+                             "use the eager step")
 
     def step(self, uid, pid, label, domain):
-        """`train_on_batch`, replayed from a CUDA graph when enabled.  Returns a fresh [2] loss tensor."""
-        if not self.use_graphs:
-            return self.train_on_batch(uid, pid, label, domain)
-        n = int(uid.numel())
-        self._in_uid[:n].copy_(uid)
-        self._in_pid[:n].copy_(pid)
-        self._in_lab[:n].copy_(label)
-        key = (int(domain), n)
-        entry = self._graphs.get(key)
-        if entry is None:
-            g = torch.cuda.CUDAGraph()
-            before = self.model.ctx.launches
-            torch.cuda.synchronize(self.device)
-            with torch.cuda.graph(g):
-                out = self.train_on_batch(self._in_uid[:n], self._in_pid[:n], self._in_lab[:n], domain)
-            entry = self._graphs[key] = (g, out, self.model.ctx.launches - before)
-            self.model.ctx.launches = before
-        entry[0].replay()
-        self.model.ctx.launches += entry[2]
-        return entry[1].clone()
+        return self.train_on_batch(uid, pid, label, domain)
 
 
-class ShardedJointTrainer(_GraphedSteps):
+class ShardedJointTrainer(_Steps):
     """Joint `mlp` training (``DeepCTR.train``) with row-sharded trainable tables; one instance per rank."""
 
     def __init__(self, n_uid, n_pid, n_domain, user_init, item_init, dense_init, emb_dim=(128, 128, 128), hidden=(256, 128, 64),
@@ -266,7 +234,7 @@ class ShardedJointTrainer(_GraphedSteps):
         return self.model.layout.unpack(self.model.params.cpu().numpy())
 
 
-class ShardedMTLTrainer(_GraphedSteps):
+class ShardedMTLTrainer(_Steps):
     """BASELINE config #5 end to end: DomainNegotiation (``model_zoo/domain_negotiation.py:18-123``) over an MMOE / PLE /
     SharedBottom tower (``DeepMTLCTR/deep_mtl_ctr.py:21-66``) whose trainable user / item tables are row-sharded over the
     ranks.  One instance per rank.  A Keras train step of sub-model t on a global batch: all-to-all(ids) -> owners gather ->

@@ -1,7 +1,7 @@
 """-m gpu (needs >= 2 GPUs, skipped otherwise): row-sharded trainable embedding tables with NCCL all-to-all
 (mamdr_b200/sharded.py) -- a data-parallel joint `mlp` pass on two ranks against the single-process oracle on the same
-global batches.  Dropout is off (the masks are indexed by the local row in the sharded mode); rel 1e-5 after one batch,
-1e-4 after a ragged multi-batch pass; both ranks hold bit-identical dense replicas."""
+global batches, with dropout 0 and 0.5 (the masks are indexed by the GLOBAL batch row, mamdr_batch.row0, so the sharded step
+draws exactly the unsharded masks); rel 1e-4 after a ragged multi-batch pass; both ranks hold bit-identical dense replicas."""
 import os
 import socket
 import sys
@@ -37,7 +37,7 @@ def _problem():
     return g, lo, w
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, dropout=0.0):
     sys.path.insert(0, HERE)
     sys.path.insert(0, os.path.dirname(HERE))
     os.environ.update({"MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port), "RANK": str(rank), "WORLD_SIZE": str(world)})
@@ -47,7 +47,7 @@ def _worker(rank, world, port, out_dir):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl")
     g, lo, w = _problem()
-    t = ShardedJointTrainer(g["n_uid"], g["n_pid"], g["n_domain"], w[0], w[1], w[2:], dropout=0.0, batch_size=1024,
+    t = ShardedJointTrainer(g["n_uid"], g["n_pid"], g["n_domain"], w[0], w[1], w[2:], dropout=dropout, batch_size=1024,
                             device="cuda:%d" % rank)
     d = 0
     split = g["train"][d]
@@ -65,19 +65,20 @@ def _worker(rank, world, port, out_dir):
 
 @pytest.mark.timeout(240)
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="row-sharded tables need 2 GPUs (NCCL all-to-all)")
-def test_row_sharded_tables_two_ranks_match_oracle(tmp_path):
+@pytest.mark.parametrize("dropout", [0.0, 0.5])
+def test_row_sharded_tables_two_ranks_match_oracle(tmp_path, dropout):
     import torch.multiprocessing as mp
     from conftest import rel_err
     from mamdr_b200.schedule import Schedule
     from oracle.meta import train_pass
     from oracle.mlp import MLPSpec, OracleMLP
     port = _free_port()
-    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, str(tmp_path), dropout), nprocs=2, join=True)
     a = torch.load(os.path.join(str(tmp_path), "rank0.pt"), weights_only=False)
     b = torch.load(os.path.join(str(tmp_path), "rank1.pt"), weights_only=False)
     assert torch.equal(a["dense"], b["dense"]) and a["step"] == b["step"]
     g, lo, w = _problem()
-    spec = MLPSpec(g["n_uid"], g["n_pid"], g["n_domain"], (128, 128, 128), (256, 128, 64), dropout=0.0, emb_trainable=True)
+    spec = MLPSpec(g["n_uid"], g["n_pid"], g["n_domain"], (128, 128, 128), (256, 128, 64), dropout=dropout, emb_trainable=True)
     o = OracleMLP(spec, w, None, None, lr=1e-3)
     split = g["train"][0]
     order = Schedule(3).batch_order(0, len(split["uid"]))
