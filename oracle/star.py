@@ -27,7 +27,7 @@ value is rounding noise of the batch statistics).
 import numpy as np
 
 from . import auc as auc_mod
-from .mlp import CLIP_HI, CLIP_LO, LOGIT_CLIP, AdamState, mm
+from .mlp import CLIP_HI, CLIP_LO, LOGIT_CLIP, AdamState, mm, sgd_apply
 
 PN_EPS = 1e-3
 PN_MOMENTUM = 0.99
@@ -176,7 +176,10 @@ class OracleStar(object):
 
     def train_on_batch(self, uid, pid, domain, label, masks=None, optimizer='adam', sgd_lr=None):
         loss, p, grads = self.gradients(uid, pid, domain, label)
-        self.adam.apply(self.weights, grads)
+        if optimizer == 'adam':
+            self.adam.apply(self.weights, grads)
+        else:   # the finetune stage's GradientDescentOptimizer (specific_base_model.py:118-122)
+            sgd_apply(self.weights, grads, sgd_lr)
         self.auc.update_state(label, p.astype(np.float32))
         return loss, self.auc.result()
 

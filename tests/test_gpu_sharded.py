@@ -112,7 +112,7 @@ def _mtl_problem(kind):
     return g, topo, w
 
 
-def _mtl_worker(rank, world, port, out_dir, kind):
+def _mtl_worker(rank, world, port, out_dir, kind, dropout=0.0):
     sys.path.insert(0, HERE)
     sys.path.insert(0, os.path.dirname(HERE))
     os.environ.update({"MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port), "RANK": str(rank), "WORLD_SIZE": str(world)})
@@ -122,7 +122,7 @@ def _mtl_worker(rank, world, port, out_dir, kind):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl")
     g, topo, w = _mtl_problem(kind)
-    t = ShardedMTLTrainer(kind, g["n_uid"], g["n_pid"], g["n_domain"], w[0], w[1], w[2:], dropout=0.0, lr=1e-4, batch_size=1024,
+    t = ShardedMTLTrainer(kind, g["n_uid"], g["n_pid"], g["n_domain"], w[0], w[1], w[2:], dropout=dropout, lr=1e-4, batch_size=1024,
                           device="cuda:%d" % rank, **MTL_ARCH[kind])
     t.dn_prepare()
     sched = Schedule(7)
@@ -143,10 +143,11 @@ def _mtl_worker(rank, world, port, out_dir, kind):
 
 @pytest.mark.timeout(240)
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="row-sharded tables need 2 GPUs (NCCL all-to-all)")
-@pytest.mark.parametrize("kind", ["mmoe", "ple"])
-def test_sharded_mtl_domain_negotiation_two_ranks_match_oracle(tmp_path, kind):
+@pytest.mark.parametrize("kind,dropout", [("mmoe", 0.0), ("ple", 0.0), ("mmoe", 0.5)])
+def test_sharded_mtl_domain_negotiation_two_ranks_match_oracle(tmp_path, kind, dropout):
     """Two DN meta-steps of `<kind>_meta_domain_negotiation` with the tables row-sharded over 2 ranks vs the single-process
-    oracle (OracleDN over OracleMTL) on the same global batches: theta (dense + both tables) rel 1e-4, replicas bit-identical."""
+    oracle (OracleDN over OracleMTL) on the same global batches: theta (dense + both tables) rel 1e-4, replicas bit-identical;
+    with dropout 0.5 the masks follow the global batch row (mamdr_batch.row0), i.e. the sharded run draws the oracle's masks."""
     import torch.multiprocessing as mp
     from conftest import BASE_CONFIG, rel_err
     from mamdr_b200.deep_mtl_ctr import MTLTopology
@@ -154,7 +155,7 @@ def test_sharded_mtl_domain_negotiation_two_ranks_match_oracle(tmp_path, kind):
     from oracle.meta import OracleDN
     from oracle.mtl import MTLSpec, OracleMTL
     port = _free_port()
-    mp.spawn(_mtl_worker, args=(2, port, str(tmp_path), kind), nprocs=2, join=True)
+    mp.spawn(_mtl_worker, args=(2, port, str(tmp_path), kind, dropout), nprocs=2, join=True)
     a = torch.load(os.path.join(str(tmp_path), "mtl_rank0.pt"), weights_only=False)
     b = torch.load(os.path.join(str(tmp_path), "mtl_rank1.pt"), weights_only=False)
     assert torch.equal(a["dense"], b["dense"]) and torch.equal(a["live"], b["live"]) and a["step"] == b["step"]
@@ -163,7 +164,7 @@ def test_sharded_mtl_domain_negotiation_two_ranks_match_oracle(tmp_path, kind):
     spec = MTLSpec(g["n_uid"], g["n_pid"], g["n_domain"], kind=kind, expert_hidden=arch["expert_hidden"], tower_hidden=arch["tower_hidden"],
                    gate_hidden=arch["gate_hidden"], num_experts=arch.get("num_experts", 0),
                    specific_expert_num=arch.get("specific_expert_num", 0), shared_expert_num=arch.get("shared_expert_num", 0),
-                   dropout=0.0, emb_trainable=True)
+                   dropout=dropout, emb_trainable=True)
     assert spec.names == topo.layout.names
     o = OracleMTL(spec, w, None, None, lr=1e-4)
     tc = dict(BASE_CONFIG["train"], meta_learning_rate=0.1, shuffle_sequence=True, meta_train_step=0)
