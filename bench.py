@@ -317,7 +317,9 @@ def run_amazon(args):
     import torch
     import run as runpy
     config = load_config(args.workload)
-    config["b200"]["precision"] = "fp32"
+    # config #2 (the mlp tower): tcgen05 pass kernel per mini-batch by default; the multi-task towers are fp32 SIMT
+    prec = (args.precision or "tf32x3") if args.workload == "Amazon-6" else "fp32"
+    config["b200"]["precision"] = prec
     base = runpy.build(config)
     base = getattr(base, "base_model", base)   # config #5 wraps the MTL base model in DomainNegotiation
     model = base.model
@@ -386,7 +388,7 @@ def run_amazon(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "%s train steps of sub-model %d, trainable user/item tables, synthetic %s (%d + %d rows x 128), "
                                    "%d mini-batches of 1024 per step" % (config["model"]["name"], idx, shape, model.n_uid, model.n_pid, mb),
-                       "precision": "fp32", "l2": "tables + Adam slots (%.0f MB per sweep) are far beyond L2" % (12e-6 * n_table)},
+                       "precision": prec, "l2": "tables + Adam slots (%.0f MB per sweep) are far beyond L2" % (12e-6 * n_table)},
             "gpu_launches": model.ctx.launches - launches0, "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json (burst copy bandwidth)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",

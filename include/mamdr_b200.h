@@ -325,6 +325,16 @@ int mamdr_mlp_eval_pass(mamdr_ctx* ctx, const mamdr_mlp_desc* desc, const mamdr_
                         float* probs_dev, float* auc_acc_dev, const float* thresholds_dev,
                         int32_t num_thresholds, int32_t precision_mode, mamdr_stream stream);
 
+/* Trainable user / item tables (desc->emb_trainable, config #2) through the pass kernel: ONE mini-batch per launch
+ * (steps == 1, not recordable).  The tables are read from the arena, the tcgen05 chain also produces dX = dZ_0 .
+ * W_0[0:K0]^T, the dense variables take their optimizer apply in-kernel, and the launch is followed by the
+ * de-duplication of the two sparse gradients; mamdr_mlp_pass_sparse_grads returns them (sorted unique ids, summed
+ * rows, device count) for mamdr_adam_table_step, which must read the beta powers of BEFORE the launch (pass a copy
+ * of the optimizer state taken before it). */
+int mamdr_mlp_pass_sparse_grads(const mamdr_mlp_desc* desc, int32_t batch_size, void* ws_dev, int32_t table,
+                                const int32_t** uniq_ids_dev, const float** uniq_rows_dev,
+                                const int32_t** n_uniq_dev);
+
 /* ---- a whole meta-step in ONE launch: deferred execution of passes and meta sweeps ------------------------------
  * Between mamdr_program_begin and mamdr_program_end, mamdr_mlp_train_pass and the K9/K10 meta sweeps (mamdr_copy,
  * mamdr_merge, mamdr_dn_update, mamdr_dr_update, mamdr_dr_accumulate, mamdr_dr_apply_accum, mamdr_sub,

@@ -158,6 +158,7 @@ SIGNATURES = {
     "mamdr_debug_pass_timing": (C.c_int, [_P, _P, _I64]),
     "mamdr_mlp_input_grads": (C.c_int, [_P, C.POINTER(MlpDesc), _I32, _P, _P, _SZ, _P, _P]),
     "mamdr_mlp_sparse_grads": (C.c_int, [C.POINTER(MlpDesc), _I32, _P, _I32, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
+    "mamdr_mlp_pass_sparse_grads": (C.c_int, [C.POINTER(MlpDesc), _I32, _P, _I32, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
     "mamdr_adam_table_workspace_bytes": (_SZ, []),
     "mamdr_adam_table_step": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _P, _P, _P, _I64, _P, _F, _P, _F, _F, _F, _F, _P, _P,
                                         _SZ, _P]),

@@ -88,7 +88,7 @@ constexpr uint32_t kSlotCols = kAccGroups * 2 * CR;   // 128 columns per accumul
 constexpr uint32_t kTmemCols = 2 * kSlotCols; // chain: two slots; dW: one accumulator of up to 2 x 64 columns
 
 enum { J_NONE = 0, J_DW, J_DOM, J_RED };
-enum { S_FWD = 0, S_HEAD, S_DH };
+enum { S_FWD = 0, S_HEAD, S_DH, S_DX };   // S_DX: dX = dZ_0 . W_0[0:K0]^T (trainable user / item tables only)
 enum { SEG_ED = 0, SEG_KERNEL, SEG_BIAS, SEG_DENSE, SEG_GBIAS };
 
 // chain-phase layout of the scratch area
@@ -146,6 +146,11 @@ struct PassArgs {
     float *db_part[MAMDR_MAX_LAYERS];   // per-row-group column sums of dZ_l
     float *dw_part, *dg_part, *fold_part;   // fold_part: [kDomJobs][n1] k-slice partials of E_d[dom] . W_0dom
     unsigned int* tile_ctr;             // per dW tile: split-K partials written so far (monotonic over the launch)
+    // ---- trainable user / item tables (config #2): the tables live in the arena, one mini-batch per launch; the kernel
+    // leaves dX [rows, K0] and the batch's ids for the sparse-gradient de-duplication + table sweeps that follow it
+    int emb_trainable;
+    float* dX;
+    int32_t* bid[2];
     double *loss_part, *ed_sq;
     int* hist;
     unsigned int* bar;
@@ -349,7 +354,10 @@ __device__ __forceinline__ void gather_rows(const PassArgs& a, const PassDyn& pd
         float* xr = X + (long long)r * K0;
         for (int c = lane * 4; c < a.du; c += 128) store_pair4(xr + c, xz, ldg_f4(su + c), rnd, x3);
         for (int c = lane * 4; c < a.di; c += 128) store_pair4(xr + a.du + c, xz, ldg_f4(si + c), rnd, x3);
-        if (lane == 0) y[r] = __ldg(pd.label + o);
+        if (lane == 0) {
+            y[r] = __ldg(pd.label + o);
+            if (a.bid[0]) { a.bid[0][r] = (int32_t)u; a.bid[1][r] = (int32_t)p; }
+        }
     }
 }
 
@@ -452,6 +460,17 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
             last = ns - 1;
             bsel ^= 1;
         }
+        if (a.emb_trainable) {   // dX^T[k, row] = W_0[k, :] . dZ_0[row, :]  (k < K0)
+            const int tiles = cdiv(a.n[0], 128);
+            const int prev_last = last;
+            for (int t = 0; t < tiles; ++t) {
+                SegD sd;
+                sd.kind = S_DX; sd.layer = 0; sd.mtile = t; sd.nch = a.n[1] / KCH;
+                sd.ngrp = (a.n[0] - t * 128) / 32 < 4 ? (a.n[0] - t * 128) / 32 : 4;
+                sd.dep = prev_last; sd.bsrc = bsel; sd.bdst = bsel ^ 1; sd.mseg = 0;
+                s_seg[ns++] = sd;
+            }
+        }
         s_nseg = ns;
     }
     if (warp == kMmaWarp) tc::tmem_alloc(&tmem_base_s, kTmemCols);
@@ -490,7 +509,7 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
     // the GEMM shadows of 4 consecutive elements W_l[k, c .. c+3] (arena offset o): the pair copy of W_l itself (M operand of
     // dH_l, l >= 1) and the pair copy of W_l^T (M operand of the forward GEMM; layer 0: rows k < K0 only)
     auto store_shadows = [&](int l, int k, int c, long long o, float4 w4) {
-        if (l >= 1) store_pair4(a.wpair + o, a.wz, w4, rnd, x3);
+        if (l >= 1 || (a.emb_trainable && k < a.n[0])) store_pair4(a.wpair + o, a.wz, w4, rnd, x3);
         const int K = a.n[l];
         if (k < K) {
             float* t = a.wT[l] + (long long)c * K + k;
@@ -636,7 +655,7 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                         for (int s = 0; s < nsegs; ++s) {
                             const SegD sd = s_seg[s];
                             const int l = sd.layer;
-                            const bool fwd = sd.kind != S_DH;
+                            const bool fwd = sd.kind == S_FWD || sd.kind == S_HEAD;
                             const int mw = fwd ? a.n[l + 1] : a.n[l];       // M extent of the weight operand
                             const int brow = mw < 128 ? mw : 128;           // box rows of its map
                             const uint32_t tx = (uint32_t)(brow * KCH * 4) * (uint32_t)nz;
@@ -680,7 +699,7 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                             while (waited < need) { tc::mbar_wait(&bar_epi[waited & 1], (waited >> 1) & 1); ++waited; }
                             if (s == 0) tc::mbar_wait(&bar_x, xjobs & 1);
                             tc::tc_fence_after();
-                            const bool fwd = sd.kind != S_DH;
+                            const bool fwd = sd.kind == S_FWD || sd.kind == S_HEAD;
                             constexpr uint32_t idN2 = tc::make_idesc_tf32(128, 2 * CR, 0, 0);
                             constexpr uint32_t idN1 = tc::make_idesc_tf32(128, CR, 0, 0);
                             constexpr uint32_t a_hiw = tc::kDescHiK, a_low = tc::kDescLoK;
@@ -759,7 +778,7 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                             unsigned char* bdst = smem + kRingBytes + sd.bdst * kActBytes + (f >> 5) * kBChunk + (hf * 8) * 128 + (lane & 3) * 4;
                             float bias = 0.f, wd = 0.f, gbias = 0.f, ylab = 0.f;
                             uint32_t keep = 0xffu;
-                            if (sd.kind != S_DH) {
+                            if (sd.kind == S_FWD || sd.kind == S_HEAD) {
                                 // ---- prelude in the shadow of the MMAs: effective bias, dropout keep bits
                                 if (l == 0) {
                                     // layer 0 adds E_d[dom] . W_0[K0:, f] in fp32: the k-slice partials published by the domain jobs
@@ -955,11 +974,20 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                                         a.db_part[L - 1][(long long)j * NL + f] = dbs + comb[128 + wt];
                                     }
                                 }
+                            } else if (sd.kind == S_DX) {
+                                // dX[row, k] (fp32, plain): gradient rows of the gathered user / item embeddings
+                                tc::mbar_arrive(&bar_epi[cs & 1]);
+                                if (on) {
+                                    float* out = a.dX + (long long)r_first * K0 + f;
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i)
+                                        if (r_first + i < rows) out[(long long)i * K0] = x3 ? vv[i] + v2[i] : vv[i];
+                                }
                             } else {
                                 // dZ_{l-1}[row, f] = acc * inv_keep * 1[H_l > 0]; per-group column sums -> db_{l-1}
                                 float dz[8];
                                 float dbs = 0.f;
-                                const bool feed = l >= 2;   // dZ_{l-1} is the N operand of dH_{l-1}
+                                const bool feed = l >= 2 || a.emb_trainable;   // dZ_{l-1} is the N operand of dH_{l-1} (of the dX GEMM for l = 1)
                                 if (on) {
                                     const uint32_t mb = s_mask[sd.mseg * 256 + tid];
 #pragma unroll
@@ -1350,7 +1378,7 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                             }
                             const float4 pnew = make_float4(pp[0], pp[1], pp[2], pp[3]);
                             *reinterpret_cast<float4*>(a.params + o) = pnew;
-                            if (l >= 1) store_pair4(a.wpair + o, a.wz, pnew, rnd, x3);
+                            if (l >= 1 || a.emb_trainable) store_pair4(a.wpair + o, a.wz, pnew, rnd, x3);
                             if (a.grads) *reinterpret_cast<float4*>(a.grads + o) = make_float4(g[0], g[1], g[2], g[3]);
 #pragma unroll
                             for (int t = 0; t < 4; ++t) s_t[rr * (bn + 1) + c + t] = pp[t];
@@ -1459,7 +1487,7 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
 // ---- workspace layout ---------------------------------------------------------------------------------------------
 struct PassWs {
     size_t bar, hist, X[2], y[2], H[MAMDR_MAX_LAYERS], dZ[MAMDR_MAX_LAYERS], partials[MAMDR_MAX_LAYERS], db_part[MAMDR_MAX_LAYERS];
-    size_t dw_part, dg_part, loss_part, fold_part, ed_sq, wpair, wz, wT[MAMDR_MAX_LAYERS], total;
+    size_t dw_part, dg_part, loss_part, fold_part, ed_sq, wpair, wz, wT[MAMDR_MAX_LAYERS], dX, bid[2], uids[2], urows[2], ucnt, sws[2], total;
 };
 
 inline PassWs pass_ws(const mamdr_mlp_desc& d, int B) {
@@ -1495,6 +1523,18 @@ inline PassWs pass_ws(const mamdr_mlp_desc& d, int B) {
     w.wz = ((size_t)(d.arena_floats - d.off_domain_emb) + 31) / 32 * 32;   // floats between the two planes of the kernel shadow
     w.wpair = take(2 * w.wz * 4);                                          // dense span of the arena only
     for (int l = 0; l < L; ++l) w.wT[l] = take((size_t)2 * d.hidden[l] * (l == 0 ? K0 : d.hidden[l - 1]) * 4);
+    w.dX = 0; w.ucnt = 0;
+    for (int t = 0; t < 2; ++t) w.bid[t] = w.uids[t] = w.urows[t] = w.sws[t] = 0;
+    if (d.emb_trainable) {   // what the sparse-gradient de-duplication behind a launch consumes / produces
+        w.dX = take((size_t)Bp * K0 * 4);
+        w.ucnt = take(64);
+        for (int t = 0; t < 2; ++t) {
+            w.bid[t] = take((size_t)Bp * 4);
+            w.uids[t] = take((size_t)Bp * 4);
+            w.urows[t] = take((size_t)Bp * d.emb_dim[t] * 4);
+            w.sws[t] = take(mamdr_scatter_workspace_bytes(Bp));
+        }
+    }
     w.total = off;
     return w;
 }
@@ -1507,7 +1547,9 @@ using namespace passk;
 
 static int pass_supported(mamdr_ctx* ctx, const mamdr_mlp_desc* d, int max_batch) {
     MAMDR_REQUIRE(ctx, d->n_layers >= 1 && d->n_layers <= MAMDR_MAX_LAYERS, MAMDR_E_INVALID, "n_layers out of range");
-    MAMDR_REQUIRE(ctx, !d->emb_trainable, MAMDR_E_UNSUPPORTED, "the pass kernel covers frozen user/item tables (trainable tables use the per-step path)");
+    if (d->emb_trainable)
+        MAMDR_REQUIRE(ctx, max_batch <= mamdr_scatter_max_n() && d->off_user_emb >= 0 && d->off_item_emb >= 0, MAMDR_E_UNSUPPORTED,
+                      "trainable tables: the batch must fit the sparse-gradient de-duplication and the tables must live in the arena");
     const int K0 = d->emb_dim[0] + d->emb_dim[1];
     MAMDR_REQUIRE(ctx, d->emb_dim[0] % 4 == 0 && d->emb_dim[1] % 4 == 0 && d->emb_dim[2] % 4 == 0 && K0 % 32 == 0, MAMDR_E_UNSUPPORTED,
                   "pass kernel needs emb dims that are multiples of 4 and user+item width a multiple of 32");
@@ -1583,7 +1625,7 @@ static int run_pass(mamdr_ctx* ctx, const mamdr_mlp_desc* d, const mamdr_pass* p
     MAMDR_REQUIRE(ctx, ps->steps >= 1 && ps->n_data >= 1 && ps->batch_size >= 1, MAMDR_E_INVALID, "empty pass");
     MAMDR_REQUIRE(ctx, (int64_t)(ps->steps - 1) * ps->batch_size < ps->n_data, MAMDR_E_INVALID, "steps * batch_size runs past n_data");
     MAMDR_REQUIRE(ctx, ps->domain >= 0 && ps->domain < d->n_domain, MAMDR_E_INVALID, "domain id out of range");
-    MAMDR_REQUIRE(ctx, ps->uid_dev && ps->pid_dev && ps->label_dev && ut && it, MAMDR_E_INVALID, "NULL data column / table");
+    MAMDR_REQUIRE(ctx, ps->uid_dev && ps->pid_dev && ps->label_dev && (d->emb_trainable || (ut && it)), MAMDR_E_INVALID, "NULL data column / table");
     MAMDR_REQUIRE(ctx, params && aligned16(params) && ws_ && aligned16(ws_) && losses && opt_state, MAMDR_E_INVALID, "NULL or misaligned buffer");
     if (train) MAMDR_REQUIRE(ctx, optimizer == 1 || (m && v && aligned16(m) && aligned16(v)), MAMDR_E_INVALID, "Adam slots NULL or misaligned");
     if (auc_acc) MAMDR_REQUIRE(ctx, thr && T >= 2 && T <= kMaxThr - 1, MAMDR_E_INVALID, "bad AUC thresholds (2 <= T <= 1023)");
@@ -1613,6 +1655,13 @@ static int run_pass(mamdr_ctx* ctx, const mamdr_mlp_desc* d, const mamdr_pass* p
     a.seg[ns++] = Seg{d->off_global_bias, 1, SEG_GBIAS, 0};
     a.nseg = ns;
     a.params = params; a.m = m; a.v = v; a.grads = grads; a.Eu = ut; a.Ei = it;
+    a.emb_trainable = d->emb_trainable ? 1 : 0;
+    if (d->emb_trainable) {
+        MAMDR_REQUIRE(ctx, !train || (ps->steps == 1 && !ctx->prog), MAMDR_E_UNSUPPORTED,
+                      "trainable tables: one mini-batch per launch (the table sweeps run between mini-batches), not recordable");
+        a.Eu = params + d->off_user_emb;
+        a.Ei = params + d->off_item_emb;
+    }
     a.bs = ps->batch_size; a.max_rows = Bp;
     ProgOp op;
     memset(&op, 0, sizeof(op));
@@ -1628,6 +1677,10 @@ static int run_pass(mamdr_ctx* ctx, const mamdr_mlp_desc* d, const mamdr_pass* p
     }
     a.dw_part = (float*)(ws + w.dw_part); a.dg_part = (float*)(ws + w.dg_part); a.loss_part = (double*)(ws + w.loss_part);
     a.fold_part = (float*)(ws + w.fold_part);
+    if (d->emb_trainable) {
+        a.dX = (float*)(ws + w.dX);
+        a.bid[0] = (int32_t*)(ws + w.bid[0]); a.bid[1] = (int32_t*)(ws + w.bid[1]);
+    }
     a.ed_sq = (double*)(ws + w.ed_sq);
     a.wpair = (float*)(ws + w.wpair) - d->off_domain_emb;   // indexed with arena offsets
     a.wz = (long long)w.wz;
@@ -1666,6 +1719,8 @@ static int run_pass(mamdr_ctx* ctx, const mamdr_mlp_desc* d, const mamdr_pass* p
             ok = ok && mlptc::pair_mnmajor_map(ctx, &mp.hmn[l], a.H[l], Bp, a.n[l], zh);
             ok = ok && mlptc::pair_kmajor_map(ctx, &mp.wb[l], wsrc + d->off_kernel[l], a.n[l], a.n[l + 1], a.n[l] < 128 ? a.n[l] : 128, (uint64_t)a.wz, nzp);
         }
+        if (l == 0 && d->emb_trainable)
+            ok = ok && mlptc::pair_kmajor_map(ctx, &mp.wb[0], wsrc + d->off_kernel[0], a.n[0], a.n[1], a.n[0] < 128 ? a.n[0] : 128, (uint64_t)a.wz, nzp);
         ok = ok && mlptc::pair_mnmajor_map(ctx, &mp.dzmn[l], a.dZ[l], Bp, a.n[l + 1], zd);
         ok = ok && mlptc::pair_kmajor_map(ctx, &mp.wf[l], a.wT[l], a.n[l + 1], a.n[l], a.n[l + 1] < 128 ? a.n[l + 1] : 128, (uint64_t)a.n[l + 1] * a.n[l], nzp);
     }
@@ -1688,7 +1743,29 @@ static int run_pass(mamdr_ctx* ctx, const mamdr_mlp_desc* d, const mamdr_pass* p
         return MAMDR_OK;
     }
     a.ops = nullptr; a.n_ops = 1; a.inline_op = op;
-    return launch_program(ctx, mp, a, st);
+    rc = launch_program(ctx, mp, a, st);
+    if (rc || !d->emb_trainable || !train) return rc;
+    // de-duplicate the two sparse gradients of this mini-batch (K6): sorted unique ids + rows summed in batch order
+    const int rows = (int)(ps->n_data < ps->batch_size ? ps->n_data : ps->batch_size);
+    DedupJob jobs[2];
+    for (int t = 0; t < 2; ++t) {
+        jobs[t] = DedupJob{a.bid[t], a.dX + (t == 0 ? 0 : d->emb_dim[0]), (int64_t)a.n[0], d->emb_dim[t], (int32_t*)(ws + w.uids[t]),
+                           (float*)(ws + w.urows[t]), (int32_t*)(ws + w.ucnt) + t, nullptr, nullptr};
+        mamdr_scatter_job_ws(&jobs[t], ws + w.sws[t], Bp);
+    }
+    return mamdr_scatter_dedup_jobs(ctx, jobs, 2, rows, st);
+}
+
+/* the de-duplicated sparse gradients left by the last trainable-table launch of the pass kernel (see mamdr_mlp_sparse_grads) */
+extern "C" int mamdr_mlp_pass_sparse_grads(const mamdr_mlp_desc* desc, int32_t batch_size, void* ws_dev, int32_t table,
+                                           const int32_t** uniq_ids_dev, const float** uniq_rows_dev, const int32_t** n_uniq_dev) {
+    if (!desc || !ws_dev || table < 0 || table > 1 || !desc->emb_trainable) return MAMDR_E_INVALID;
+    const PassWs w = pass_ws(*desc, batch_size);
+    unsigned char* ws = (unsigned char*)ws_dev;
+    *uniq_ids_dev = (const int32_t*)(ws + w.uids[table]);
+    *uniq_rows_dev = (const float*)(ws + w.urows[table]);
+    *n_uniq_dev = (const int32_t*)(ws + w.ucnt) + table;
+    return MAMDR_OK;
 }
 
 bool mamdr_prog_recording(const mamdr_ctx* ctx) { return ctx && ctx->prog; }

@@ -111,9 +111,7 @@ class MLPModel(object):
             self.item_table = torch.from_numpy(it).to(dev)
         else:
             # trainable tables live inside the arena (user_emb, item_emb first, like model.trainable_weights)
-            self.user_table = self.item_table = None
-            if self.precision != _lib.PREC_FP32:
-                raise ValueError("trainable embedding tables run in the fp32 mode (b200.precision = 'fp32')")
+            self.user_table = self.item_table = None   # (tcgen05 modes: one pass-kernel launch per mini-batch, _train_step_tc_tables)
         # ---- C-ABI descriptor
         d = _lib.MlpDesc()
         d.n_layers = len(hidden)
@@ -160,6 +158,7 @@ class MLPModel(object):
             self.l2_emb = float(l2_emb)
             self._sq = torch.zeros(1, dtype=torch.float64, device=dev)
             self.dense_off = lo.offset("domain_emb")
+            self._opt_prev = torch.zeros_like(self.opt_state)   # the optimizer state before the current step (table sweeps)
         # the tcgen05 modes are served by the persistent pass kernel only (one cooperative launch per domain
         # pass); fp32 is the per-mini-batch SIMT path.  No silent fallback between them.
         self.pass_kernel = False
@@ -336,6 +335,9 @@ class MLPModel(object):
 
     def _train_step(self, data, offset, rows, loss_slot, probs=None, with_auc=True):
         """One mini-batch (forward + backward + optimizer apply); gradients are left in ``self.grads``."""
+        if self.pass_kernel and self.emb_trainable:
+            self._train_step_tc_tables(data, offset, rows, loss_slot, with_auc)
+            return
         if self.pass_kernel:
             self._train_pass(self._pass(data, 1, True, offset, rows), loss_slot, with_auc)
             return
@@ -376,6 +378,29 @@ class MLPModel(object):
                           _ptr(self.opt_state), self.sgd_lr, st)
         self.ctx.launches += 3 + 3 * len(self.hidden) + 3  # memset, assemble, L fwd, head, L-1 dH, L dW, colsum, dEd, opt
 
+    def _train_step_tc_tables(self, data, offset, rows, loss_slot, with_auc=True):
+        """Config #2 in the tcgen05 modes: one mini-batch = the pass kernel (tables gathered from the arena, tower + dX on the
+        tensor cores, dense variables applied in-kernel, the two sparse gradients de-duplicated behind it) + the fused
+        sparse-merge / l2 / non-lazy Adam sweep of each table, which reads the beta powers of BEFORE the step."""
+        if self.optimizer != "adam":
+            raise NotImplementedError("trainable tables are updated by Adam only (the finetune SGD stage follows frozen-table configs)")
+        st = self.stream
+        self.desc.frozen_reg = 0.0   # training adds the tables' l2 penalty inside the fused table sweep
+        self._opt_prev.copy_(self.opt_state)
+        self._train_pass(self._pass(data, 1, True, offset, rows), loss_slot, with_auc)
+        for t, (off, n_rows, dim, slot) in enumerate(self._tables):
+            ids, srows, cnt = C.c_void_p(), C.c_void_p(), C.c_void_p()
+            rc = self.ctx.lib.mamdr_mlp_pass_sparse_grads(C.byref(self.desc), int(rows), _ptr(self.pass_ws), t, C.byref(ids),
+                                                          C.byref(srows), C.byref(cnt))
+            if rc != 0:
+                raise _lib.MamdrError(rc, "mamdr_mlp_pass_sparse_grads")
+            n_el = n_rows * dim
+            self.ctx.call("mamdr_adam_table_step", _ptr(self.params[off:off + n_el]), _ptr(self.m[off:off + n_el]),
+                          _ptr(self.v[off:off + n_el]), n_rows, dim, ids, srows, cnt, int(rows), _ptr(slot),
+                          self.l2_emb, _ptr(self._opt_prev), self.lr, self.beta1, self.beta2, self.eps,
+                          _ptr(loss_slot), _ptr(self.table_ws), self.table_ws_bytes, st)
+        self.ctx.launches += 2 + 2 * 2   # sort + segment-sum (both tables per launch), 2 x (slot scatter, table sweep)
+
     def train_on_batch(self, data, offset, rows):
         """``Model.train_on_batch`` -> (loss, auc) host floats.  Synchronises: debugging / parity only;
         the wrappers use ``fit_pass``."""
@@ -402,6 +427,13 @@ class MLPModel(object):
         losses = self._loss_bufs.get(key)
         if losses is None:
             losses = self._loss_bufs[key] = torch.zeros(steps, dtype=torch.float32, device=self.device)
+        if self.pass_kernel and self.emb_trainable:
+            # the tables change between mini-batches: one launch (+ the two table sweeps) per mini-batch
+            if order is not None:
+                data.order.copy_(order, non_blocking=True)
+            for s, (off, rows) in enumerate(self._pass_plan(data, steps)):
+                self._train_step_tc_tables(data, off, rows, losses[s:s + 1])
+            return losses
         if self.pass_kernel:
             self._train_pass(self._pass(data, steps, True, order=order), losses)
             return losses
