@@ -144,6 +144,9 @@ class BaseModel(object):
         import torch
         if init_parms:
             raise NotImplementedError("separate training from scratch is outside the hot path")
+        hook = getattr(self, "_discard_lookahead", None)   # a staged look-ahead meta-step will not run
+        if hook is not None:
+            hook()
         m = self.model
         weights = m.get_weights()                                   # :65 save init weight
         domain_loss, domain_auc = {}, {}

@@ -29,6 +29,17 @@ class MAMDR(SpecificBase):
                     break
                 self.log("Test Result: ")
                 self.val_and_test("test")
+        self._discard_plan()
+
+    def _discard_plan(self):
+        """Drop a look-ahead plan that will not run (early stop, last epoch, the finetune stage follows): the schedule goes back
+        to its state from before the look-ahead, so whatever draws next sees exactly what the reference order implies."""
+        nxt = getattr(self, "_next_plan", None)
+        self._next_plan = None
+        if nxt is not None and nxt["schedule"] is self.schedule:
+            self.schedule._rng.setstate(nxt["rng_before"][0])
+            self.schedule._pass = nxt["rng_before"][1]
+            self.base_model._staged_orders = None
 
     def prepare(self):
         """:26-37 -- theta = the model's first initialisation; theta_d^0 = an independent
@@ -43,20 +54,24 @@ class MAMDR(SpecificBase):
         self.train_sequence = self.build_meta_data_split()
         self._accum = None
 
-    def train_epoch(self, epoch=0):
-        """One MAMDR meta-step: the body of the epoch loop, :44-143."""
+    def _plan_epoch(self):
+        """Everything of a meta-step that does not depend on the weights: the schedule draws (sequence shuffle :45-46, DR support
+        samples :66-70, in the reference's order), the multi-GPU assignment, and the staging of every pass's sample order (host
+        permutations + ONE pinned H2D copy).  Run for meta-step k+1 right after the launches of meta-step k were enqueued, it
+        overlaps ~10 ms of host work with the GPU instead of serialising it behind the step's result read-back."""
         tc = self.train_config
-        beta = tc['meta_learning_rate']
-        if tc['shuffle_sequence']:                                   # :45-46
-            self.train_sequence = self.schedule.shuffle_sequence(self.train_sequence)
+        sched = self.schedule
+        plan = {"schedule": sched, "rng_before": (sched._rng.getstate(), sched._pass), "sequence_before": list(self.train_sequence)}
         train_sequence = self.train_sequence
+        if tc['shuffle_sequence']:                                   # :45-46
+            train_sequence = sched.shuffle_sequence(train_sequence)
         # the DR support samples (:66-70) are drawn up-front, in the reference's order (the per-pass
         # sample orders come from an independent keyed stream), so the whole meta-step can be staged
         supports = {}
         for idx in train_sequence:
             candidate_domains = list(train_sequence)
             candidate_domains.remove(idx)
-            aux_idxs = self.schedule.sample_support(candidate_domains, tc['sample_num'])   # :68
+            aux_idxs = sched.sample_support(candidate_domains, tc['sample_num'])   # :68
             if tc['add_query_domain']:
                 aux_idxs = list(aux_idxs) + [idx]
             supports[idx] = aux_idxs
@@ -76,7 +91,6 @@ class MAMDR(SpecificBase):
             pair_owner = mdist.lpt_assign(mdist.dr_pair_costs(train_sequence, supports, n_step,
                                                               tc['domain_regulation_step']), world)
             owner = {idx: pair_owner[(pos, len(supports[idx]) - 1)] for pos, idx in enumerate(train_sequence)}
-        self.dr_owner, self.dr_pair_owner = owner, pair_owner
         passes, mine = list(train_sequence), [True] * len(train_sequence)
         for pos, idx in enumerate(train_sequence):
             for k, aux_idx in enumerate(supports[idx]):
@@ -86,6 +100,25 @@ class MAMDR(SpecificBase):
                 passes.append(idx)
                 mine.append(owner[idx] == rank)
         self.stage_epoch_orders(passes, mine if world > 1 else None)
+        plan.update(train_sequence=train_sequence, supports=supports, owner=owner, pair_owner=pair_owner, pair_mode=pair_mode,
+                    batch_mode=batch_mode, rank=rank, world=world,
+                    staged=(getattr(self.base_model, "_staged_orders", None), getattr(self.base_model, "_order_pool", None)))
+        return plan
+
+    def train_epoch(self, epoch=0):
+        """One MAMDR meta-step: the body of the epoch loop, :44-143."""
+        tc = self.train_config
+        beta = tc['meta_learning_rate']
+        plan = getattr(self, "_next_plan", None)
+        self._next_plan = None
+        if plan is None or plan["schedule"] is not self.schedule or plan["sequence_before"] != list(self.train_sequence):
+            plan = self._plan_epoch()
+        elif plan["staged"][0] is not None:      # the staged orders of the prefetched plan become the live ones
+            self.base_model._staged_orders, self.base_model._order_pool = plan["staged"]
+        self.train_sequence = train_sequence = plan["train_sequence"]
+        supports, owner, pair_owner, pair_mode, batch_mode = plan["supports"], plan["owner"], plan["pair_owner"], plan["pair_mode"], plan["batch_mode"]
+        rank, world = plan["rank"], plan["world"]
+        self.dr_owner, self.dr_pair_owner = owner, pair_owner
 
         # In the tcgen05 modes the DN phase and every DR chain of this rank are each recorded and run as ONE persistent
         # launch (engine.program: passes + meta sweeps executed in-kernel); recording chain k+1 overlaps the execution
@@ -101,6 +134,7 @@ class MAMDR(SpecificBase):
         # ---- Update specific (DR), :59-108
         if pair_mode:
             self._dr_pairs_sharded(train_sequence, supports, pair_owner, rank, use_program)
+            self._prefetch_plan()
             return
         for idx in train_sequence:
             if owner[idx] != rank:
@@ -154,6 +188,14 @@ class MAMDR(SpecificBase):
             if pn_steps is not None:
                 pn_steps.copy_(steps_f.to(torch.int32))
             m.set_opt_words(words)
+        self._prefetch_plan()
+
+    def _prefetch_plan(self):
+        """Stage the NEXT meta-step while the GPU still runs this one (`b200.lookahead`, default on).  The draws happen in the
+        reference's order either way; `save_state` stores the schedule state from before the look-ahead."""
+        if self.b200_config.get('lookahead', True) and not self.train_config['finetune_every_epoch']:
+            self._next_plan = self._plan_epoch()
+            self.base_model._discard_lookahead = self._discard_plan
 
     def _dr_pairs_sharded(self, train_sequence, supports, pair_owner, rank, use_program):
         """DR of a 'batch' name on world > 1 ranks: this rank runs its (query, support) pairs, accumulating the deltas per query

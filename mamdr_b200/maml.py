@@ -111,14 +111,15 @@ class MAML(object):
         m = self.model
         base = self.base_model
         sched = base.schedule
+        nxt = getattr(self, "_next_plan", None)
+        rng_state, pass_ctr = (sched._rng.getstate(), sched._pass) if nxt is None else nxt["rng_before"]
+        seqs = {k: list(getattr(self, k)) for k in self._STATE_SEQS if hasattr(self, k)}
         blob = {"epoch": int(epoch), "names": m.layout.names,
                 "model": {k: getattr(m, k).detach().cpu() for k in self._STATE_TENSORS if getattr(m, k, None) is not None},
                 "meta_weights": self.meta_weights.flat.cpu(),
-                "schedule": {"seed": sched.seed, "rng": sched._rng.getstate(), "pass": sched._pass},
+                "schedule": {"seed": sched.seed, "rng": rng_state, "pass": pass_ctr},   # from before a look-ahead plan, if any
                 "early_stop": {"counter": base.counter, "best_metric": base.best_metric, "early_stop": base.early_stop}}
-        for k in self._STATE_SEQS:
-            if hasattr(self, k):
-                blob[k] = list(getattr(self, k))
+        blob.update(seqs)
         for k in ("domain_weights", "best_domain_weights"):
             if getattr(self, k, None):
                 blob[k] = {d: w.flat.cpu() for d, w in getattr(self, k).items()}
@@ -163,6 +164,7 @@ class MAML(object):
         sched = base.schedule
         sched.seed, sched._pass = blob["schedule"]["seed"], blob["schedule"]["pass"]
         sched._rng.setstate(blob["schedule"]["rng"])
+        self._next_plan = None
         es = blob["early_stop"]
         base.counter, base.best_metric, base.early_stop = es["counter"], es["best_metric"], es["early_stop"]
         return blob["epoch"]

@@ -113,6 +113,9 @@ class SpecificBase(MAML):
         best-``val_AUC`` checkpoint, then test."""
         if init_parms:
             raise NotImplementedError("separate training from scratch is outside the hot path")
+        hook = getattr(self, "_discard_lookahead", None)   # a staged look-ahead meta-step will not run
+        if hook is not None:
+            hook()
         m = self.model
         weights = m.get_weights()                                   # :116 save init weight
         domain_loss, domain_auc = {}, {}
