@@ -1431,8 +1431,10 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
     }
 
     // ---- epilogue of the pass: AUC accumulators (suffix sums of the pass histogram; the histogram is double-buffered
-    // by pass parity, so the next pass of a program may already be filling the other one)
-    if (cta == 0) {
+    // by pass parity, so the next pass of a program may already be filling the other one).  Done by the LAST CTA: it has no
+    // row group (batch <= 16 x (G - 1) rows) and no dW job at the usual sizes, so the fold overlaps the next pass's first chain
+    // phase instead of delaying CTA 0's chain
+    if (cta == G - 1) {
         if (a.auc_acc && warp < 2) {
             // warp 0: negatives, warp 1: positives.  lane owns a contiguous run of bins; suffix scan across lanes.
             const int T1 = a.T + 1;

@@ -12,6 +12,14 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # The oracle's fp32 GEMMs run on torch-CPU: their summation order -- and with it which near-zero ReLU gates open in a
+    # free-running trajectory -- depends on the BLAS thread count, i.e. on the host.  Pin it so the checker is the same
+    # function on every box.
+    try:
+        import torch
+        torch.set_num_threads(4)
+    except Exception:
+        pass
 
 
 BASE_CONFIG = {
