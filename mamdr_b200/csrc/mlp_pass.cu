@@ -825,6 +825,9 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                             }
                             tc::mbar_wait_warp(&bar_acc[cs & 1], (cs >> 1) & 1);
                             tc::tc_fence_after();
+#ifdef PASS_DBG_HEAD
+                            if (sd.kind == S_HEAD) WSTAMP(8);
+#endif
                             float vv[8], v2[8];
                             if (on) {
                                 // sum of the accumulator groups, (g0 + g1) + (g2 + g3), with round-to-nearest adds
@@ -853,6 +856,9 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                                 }
                             }
                             tc::tc_fence_before();
+#ifdef PASS_DBG_HEAD
+                            if (sd.kind == S_HEAD) WSTAMP(9);
+#endif
 
                             if (sd.kind == S_FWD) {
                                 // H_{l+1}[row, f] = dropout(relu(acc + b)) -> N operand of the next layer (+ global copy for dW)
@@ -898,8 +904,13 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                                     const float zs = warp_sum8(zp, lane);
                                     if ((lane & 3) == 0) s_zp[(hf * 4 + q) * 8 + warp_sum8_index(lane)] = zs;
                                 }
+#ifdef PASS_DBG_HEAD
+                                WSTAMP(10);
+#endif
                                 worker_sync();
-                                WSTAMP(15);
+#ifdef PASS_DBG_HEAD
+                                WSTAMP(11);
+#endif
                                 float pv = 0.f, yv = 0.f, dsv0 = 0.f;   // warp 0: row lane of the group
                                 const int hrow = row0 + lane;
                                 const bool hvalid = warp == 0 && lane < CR && hrow < rows;
@@ -914,7 +925,13 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                                     }
                                     if (lane < CR) s_ds[lane] = dsv0;
                                 }
+#ifdef PASS_DBG_HEAD
+                                WSTAMP(12);
+#endif
                                 worker_sync();
+#ifdef PASS_DBG_HEAD
+                                WSTAMP(13);
+#endif
                                 float hd = 0.f, dbs = 0.f;
                                 float dz[8];
                                 if (on && a.train) {
@@ -931,6 +948,9 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                                 }
                                 tc::fence_proxy_async();
                                 tc::mbar_arrive(&bar_epi[cs & 1]);
+#ifdef PASS_DBG_HEAD
+                                WSTAMP(14);
+#endif
                                 if (warp == 0) {
                                     // off the critical path: Keras BCE of the clipped probability, probabilities, AUC bins
                                     const float lo_c = 1e-7f, hi_c = 1.0f - 1e-7f;
@@ -1015,8 +1035,11 @@ pass_kernel(const __grid_constant__ MapTable maps, const __grid_constant__ PassA
                                 worker_sync();
                                 if (on && hf == 0) a.db_part[l - 1][(long long)j * N + f] = dbs + comb[wt];
                             }
-#ifndef PASS_DBG_SEG
+#if !defined(PASS_DBG_SEG) && !defined(PASS_DBG_HEAD)
                             if (tim && tid == 0 && s < 8) a.timing[tslot + 8 + s] = (unsigned long long)clock64();
+#endif
+#ifdef PASS_DBG_HEAD
+                            if (sd.kind == S_HEAD) WSTAMP(15);
 #endif
                         }
                     }
