@@ -51,33 +51,51 @@ class ClockSampler(object):
 
     def __init__(self, gpu_index):
         self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.t0 = self.t1 = None
 
     def start(self):
+        """Start sampling (20 ms period).  Call `mark_begin()` / `mark_end()` around the timed region: the summary uses the samples
+        taken inside it (a multi-GPU timed region can be shorter than nvidia-smi's start-up: the sampler is started before the warm-up
+        and, if no sample fell inside the region, the samples of the loaded second before its end are used)."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        if self.t1 is None:
+            self.t1 = time.time()
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        t0 = self.t0 if self.t0 is not None else 0.0
+        inside = [r for t, r in self.rows if t0 <= t <= self.t1 + 0.02]
+        window = "timed region"
+        if not inside:
+            inside = [r for t, r in self.rows if self.t1 - 1.0 <= t <= self.t1 + 0.02]
+            window = "the loaded second before the end of the timed region (the region is shorter than the sampling period)"
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in inside:
             try:
                 sm.append(float(r[1]))
                 mx = float(r[2])
@@ -88,7 +106,7 @@ class ClockSampler(object):
                 pass
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 # ---- the reference arm / cpu_baseline: the oracle on the host cores --------------------------------------
@@ -536,16 +554,17 @@ def run_b200(args):
         for k in ("uid", "pid", "label"):
             pinned[(dd.domain, k)] = torch.from_numpy(dd.host[k]).pin_memory()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         one_step(False)
     barrier()
     # ---- device-resident timing: K steps, per-step CUDA events, L2 flushed between steps
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     base.samples_trained = 0
     launches0 = model.ctx.launches
     evs = []
     barrier()
+    sampler.mark_begin()
     t_wall = time.perf_counter()
     for _ in range(args.steps):
         flush.fill_(1)
@@ -556,6 +575,7 @@ def run_b200(args):
         evs.append((a, b))
     barrier()
     t_wall = time.perf_counter() - t_wall
+    sampler.mark_end()
     clocks = sampler.stop()
     ms = sum(a.elapsed_time(b) for a, b in evs)
     launches = model.ctx.launches - launches0
@@ -727,10 +747,13 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: everything the library prints while building (dataset banners ...) goes to stderr
-    real_stdout = sys.stdout
+    # (file-descriptor level: NCCL prints its version banner on fd 1 from C)
+    sys.stdout.flush()
+    real_fd = os.dup(1)
+    os.dup2(2, 1)
     sys.stdout = sys.stderr
     global _emit
-    _emit = lambda line: (real_stdout.write(json.dumps(line) + "\n"), real_stdout.flush())   # noqa: E731
+    _emit = lambda line: os.write(real_fd, (json.dumps(line) + "\n").encode())   # noqa: E731
     if args.impl == "reference":
         run_reference(args)
     elif args.workload in ("Amazon-6", "Amazon-13-mmoe", "Amazon-13-ple"):
