@@ -415,6 +415,13 @@ int mamdr_sub(mamdr_ctx* ctx, float* out_dev, const float* a_dev, const float* b
 int mamdr_axpy_diff(mamdr_ctx* ctx, float* out_dev, const float* a_dev, const float* b_dev, float alpha,
                     int64_t n, mamdr_stream stream);
 
+/* PCGrad's gradient projection (model_zoo/pcgrad.py:152-160, host numpy in the reference) for ONE variable viewed as
+ * [rows, cols] (a 1-D variable is one row): per row, dot = <final, aux>; where dot > 0 (the reference's test)
+ * aux' = aux - dot / ||final_row||_2 * final_row; final_row += aux'.  `final_grads` aliases `current_grads` in the
+ * reference (pcgrad.py:104), hence one in/out buffer.  Deterministic (one warp per row, fixed-order reductions). */
+int mamdr_pcgrad_project(mamdr_ctx* ctx, float* final_grads_dev, const float* aux_grads_dev, int64_t rows,
+                         int32_t cols, mamdr_stream stream);
+
 /* ---- K8: streaming AUC (replaces utils/auc.py AUC.update_state / result / reset_states) ------ */
 int mamdr_auc_update(mamdr_ctx* ctx, const float* probs_dev, const float* labels_dev, int64_t n,
                      float* acc_dev, const float* thresholds_dev, int32_t num_thresholds,

@@ -9,7 +9,7 @@ __version__ = "0.1.0"
 # model_zoo.mamdr import MAMDR`, `from model_zoo.DeepCTR import DeepCTR`, ..., `from utils import MultiDomainDataset`), resolved
 # lazily so that importing the package does not import torch / load the CUDA library.
 _EXPORTS = {"MAML": "maml", "DomainNegotiation": "domain_negotiation", "MAMDR": "mamdr", "Reptile": "reptile",
-            "BaseModel": "base_model", "DeepCTR": "deepctr", "Star": "star", "DeepMTLCTR": "deep_mtl_ctr",
+            "MLDG": "mldg", "PCGrad": "pcgrad", "BaseModel": "base_model", "DeepCTR": "deepctr", "Star": "star", "DeepMTLCTR": "deep_mtl_ctr",
             "MultiDomainDataset": "dataset"}
 __all__ = sorted(_EXPORTS)
 

@@ -173,6 +173,7 @@ SIGNATURES = {
     "mamdr_dr_apply_accum": (C.c_int, [_P, _P, _P, _F, _F, _I64, _P]),
     "mamdr_sub": (C.c_int, [_P, _P, _P, _P, _I64, _P]),
     "mamdr_axpy_diff": (C.c_int, [_P, _P, _P, _P, _F, _I64, _P]),
+    "mamdr_pcgrad_project": (C.c_int, [_P, _P, _P, _I64, _I32, _P]),
     "mamdr_auc_update": (C.c_int, [_P, _P, _P, _I64, _P, _P, _I32, _P]),
     "mamdr_auc_result": (C.c_int, [_P, _P, _I32, _P, _P]),
 }

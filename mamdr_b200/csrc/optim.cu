@@ -296,3 +296,50 @@ extern "C" int mamdr_axpy_diff(mamdr_ctx* ctx, float* out, const float* a_, cons
     MetaArgs a{out, nullptr, a_, b_, nullptr, alpha, 0.f, 0, n};
     return launch_meta<OP_AXPY_DIFF>(ctx, a, stream);
 }
+
+// ---- PCGrad's host-side projection (model_zoo/pcgrad.py:152-160) on the device: per variable of shape [rows, cols] (a 1-D
+// variable is ONE row) and per row r:  dot = sum_c cur[r,c] * aux[r,c];  if dot > 0 (the reference's test -- it projects
+// the AGREEING rows):  aux' = aux - (dot / ||cur[r]||_2) * cur[r]  (divided by the norm, not its square, as the reference
+// does);  cur[r] += aux'.  `final_grads` IS `current_grads` in the reference (pcgrad.py:104 aliases the list), so the sum
+// is accumulated into the buffer the next support domain projects against: one in/out buffer here.  One warp per row,
+// lanes stride the columns, fixed-order shuffle reductions (no atomics: deterministic).
+__global__ void __launch_bounds__(256)
+pcgrad_project_kernel(float* __restrict__ cur, const float* __restrict__ aux, const int64_t rows, const int cols) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t r = warp; r < rows; r += nwarps) {
+        float* c = cur + r * cols;
+        const float* a = aux + r * cols;
+        float dot = 0.f, sq = 0.f;
+        for (int j = lane; j < cols; j += 32) {
+            const float cv = c[j], av = __ldg(a + j);
+            dot = __fadd_rn(dot, __fmul_rn(cv, av));
+            sq = __fadd_rn(sq, __fmul_rn(cv, cv));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            dot = __fadd_rn(dot, __shfl_xor_sync(0xffffffffu, dot, o));
+            sq = __fadd_rn(sq, __shfl_xor_sync(0xffffffffu, sq, o));
+        }
+        const bool project = dot > 0.f;
+        const float coef = project ? __fdiv_rn(dot, __fsqrt_rn(sq)) : 0.f;
+        for (int j = lane; j < cols; j += 32) {
+            const float cv = c[j];
+            float av = __ldg(a + j);
+            if (project) av = __fsub_rn(av, __fmul_rn(coef, cv));
+            c[j] = __fadd_rn(cv, av);
+        }
+    }
+}
+
+extern "C" int mamdr_pcgrad_project(mamdr_ctx* ctx, float* final_grads, const float* aux_grads, int64_t rows, int32_t cols,
+                                    mamdr_stream stream) {
+    MAMDR_REQUIRE(ctx, ctx && final_grads && aux_grads, MAMDR_E_INVALID, "NULL pointer");
+    MAMDR_REQUIRE(ctx, rows > 0 && cols > 0, MAMDR_E_INVALID, "rows and cols must be positive");
+    const int64_t want = (rows + 7) / 8;
+    const int64_t cap = (int64_t)ctx->sm_count * 8;
+    pcgrad_project_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(final_grads, aux_grads, rows, cols);
+    MAMDR_LAUNCH_OK(ctx);
+    return MAMDR_OK;
+}

@@ -53,6 +53,34 @@ class DomainData(object):
         self.order.copy_(order, non_blocking=True)
 
 
+class SplitView(object):
+    """A sub-dataset of one ``DomainData`` that shares its device columns: the ``dataset.take(n)`` / ``dataset.skip(n)``
+    meta-train / meta-val split of ``model_zoo/maml.py:296-318``.  The view covers the samples ``[lo, hi)`` of the split
+    (file order); a pass runs over ``n_data`` of them in the order installed by ``set_order`` (a permutation of the
+    window, of which the positions ``pick`` are kept -- ``shuffle(...).take(n)`` / ``.skip(n)`` of the non-exclusive mode)."""
+
+    def __init__(self, data, lo, hi, pick=None):
+        self.base, self.lo, self.hi = data, int(lo), int(hi)
+        self.pick = pick if pick is not None else slice(0, self.hi - self.lo)
+        self.domain, self.batch_size, self.device = data.domain, data.batch_size, data.device
+        self.n_data = len(range(self.hi - self.lo)[self.pick])
+        self.n_step = int(np.ceil(self.n_data / float(self.batch_size))) if self.n_data else 0
+        self.uid, self.pid, self.label = data.uid, data.pid, data.label
+        self.order = None
+        if data.uid is not None:
+            self.order = (torch.arange(self.lo, self.hi, dtype=torch.int32)[self.pick]).to(data.uid.device)
+            if self.order.numel() == 0:
+                self.order = torch.zeros(1, dtype=torch.int32, device=data.uid.device)
+
+    def window_order(self, perm):
+        """Sample ids of the next pass from a permutation of ``range(hi - lo)`` (host int32)."""
+        return (np.asarray(perm, dtype=np.int32)[self.pick] + np.int32(self.lo)).astype(np.int32)
+
+    def set_order(self, perm):
+        if self.n_data and self.order is not None:   # (not uploaded: host-only use)
+            self.order[:self.n_data].copy_(torch.from_numpy(np.ascontiguousarray(self.window_order(perm))), non_blocking=True)
+
+
 class NamedWeight(object):
     """Minimal stand-in for a ``tf.Variable`` in ``model.trainable_weights`` (has ``.name``)."""
 
@@ -400,6 +428,36 @@ class MLPModel(object):
                           self.l2_emb, _ptr(self._opt_prev), self.lr, self.beta1, self.beta2, self.eps,
                           _ptr(loss_slot), _ptr(self.table_ws), self.table_ws_bytes, st)
         self.ctx.launches += 2 + 2 * 2   # sort + segment-sum (both tables per launch), 2 x (slot scatter, table sweep)
+
+    # ---- gradient-only step + a second optimizer: what MAML / MLDG / PCGrad add to the compiled model ----------------
+    def grads_on_batch(self, data, offset, rows, loss_slot, with_auc=True):
+        """The ``K.function(model._feed_inputs + model._feed_targets, [total_loss] + metrics_tensors, updates=...)`` that
+        ``_make_meta_train_function`` builds (model_zoo/maml.py:196-233, mldg.py, pcgrad.py): forward + backward of
+        ``model.total_loss`` at the live weights WITHOUT an optimizer apply; the gradients of every variable are left in
+        ``self.grads``.  [EXT] the function is built without ``K.learning_phase()`` among its inputs, so the placeholder
+        takes its default 0: the forward is the INFERENCE one (no dropout); the stateful AUC is updated like in any step.
+        Runs the fp32 tower (the per-mini-batch path that leaves the gradients in memory) whatever ``self.precision`` is."""
+        if self.emb_trainable:
+            raise NotImplementedError("gradient accumulation over trainable tables (sparse IndexedSlices) is not built: the "
+                                      "shipped MAML / MLDG / PCGrad configs train on frozen pretrained tables")
+        d = getattr(self, "_desc_nodrop", None)
+        if d is None:
+            d = self._desc_nodrop = type(self.desc).from_buffer_copy(self.desc)
+            d.dropout_rate = 0.0
+        b = self._batch(data, offset, rows, True)
+        self.ctx.call("mamdr_mlp_train_step", C.byref(d), C.byref(b), _ptr(self.user_table), _ptr(self.item_table),
+                      _ptr(self.params), _ptr(self.grads), _ptr(self.ws), self.ws_bytes, _ptr(self.opt_state),
+                      _ptr(loss_slot), None, _ptr(self.auc_acc if with_auc else None), _ptr(self.thresholds),
+                      self.num_thresholds, _lib.PREC_FP32, self.stream)
+        self.ctx.launches += 2 + 3 * len(self.hidden) + 3
+
+    def new_optimizer_slots(self):
+        """Slots of a SECOND ``tf.train.AdamOptimizer`` (``self.meta_optimizer``, maml.py:201): (m, v, beta-power state)."""
+        m2, v2 = torch.zeros_like(self.params), torch.zeros_like(self.params)
+        st = torch.zeros_like(self.opt_state)
+        self.ctx.call("mamdr_opt_state_init", _ptr(st), self.beta1, self.beta2, self.stream)
+        self.ctx.launches += 1
+        return m2, v2, st
 
     def train_on_batch(self, data, offset, rows):
         """``Model.train_on_batch`` -> (loss, auc) host floats.  Synchronises: debugging / parity only;

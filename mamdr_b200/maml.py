@@ -1,16 +1,19 @@
 """Meta-parameter plumbing shared by the DN / MAMDR wrappers -- mirrors the parts of
 ``/root/reference/model_zoo/maml.py`` that are on the hot path: ``__getattr__`` delegation (:27-33),
 ``_get_model_meta_parms`` (:153-179), ``_set_model_meta_parms`` (:181-187), ``_get_meta_weights``
-(:189-194) and ``val`` (:343-353).  (The MAML training loop itself is out of scope, SURVEY.md 2.1 #3.)
+(:189-194) and ``val`` (:343-353) -- plus, as SURVEY.md section 8(f) row f4, the first-order MAML loop itself
+(``train`` :35-151, ``_make_meta_train_function`` :196-233, ``_meta_train_step`` :235-242, ``build_meta_data_split`` :289-341)
+that MLDG and PCGrad (``mldg.py`` / ``pcgrad.py`` here) re-order.
 
 The reference keeps weights as lists of host numpy arrays and crosses PCIe on every get / set; here a
 weight set is one device arena (``MetaWeights``) and get / set are device-side multi-tensor copies.
 """
 import ctypes as C
+import math
 
 import torch
 
-from .engine import _ptr
+from .engine import SplitView, _ptr
 
 
 class MetaWeights(object):
@@ -91,6 +94,166 @@ class MAML(object):
     # ---- maml.py:189-194
     def _get_meta_weights(self):
         return MetaWeights(self.model.params.clone(), self.model.layout, self.meta_ranges)
+
+    # ---- maml.py:196-233: the gradient-accumulating function and the second (meta) Adam --------------------------------
+    def _make_meta_train_function(self):
+        """``accum_grads`` (one arena, only the meta spans are used), the ``meta_optimizer`` slots and the function that
+        accumulates the gradients of ``model.total_loss`` w.r.t. the meta parameters (inference-mode forward, see
+        ``engine.MLPModel.grads_on_batch``)."""
+        tc = self.train_config
+        mode = tc.get('average_meta_grad', 'none')
+        if mode in ("moving_mean", "drop"):   # :220-229 ([EXT] K.moving_average_update / a Dropout layer's unseeded mask on g)
+            raise NotImplementedError("average_meta_grad = %r is not built (no shipped config uses it)" % mode)
+        m = self.model
+        self.accum_grads = torch.zeros_like(m.params)                  # :202
+        self._zeros = torch.zeros_like(m.params)
+        self._meta_m, self._meta_v, self._meta_opt_state = m.new_optimizer_slots()   # :201 AdamOptimizer(meta_learning_rate)
+        self._grad_scale = None
+        if mode == "mean" and tc['meta_train_step'] > 0:               # :208-210  ag / float(n_domain * meta_train_step)
+            self._grad_scale = float(self.n_domain * tc['meta_train_step'])
+            self._scaled = torch.zeros_like(m.params)
+            self._scratch = torch.zeros_like(m.params)
+        n = len(self.meta_ranges)
+        if n > 16:
+            raise NotImplementedError("more than 16 disjoint meta-parameter spans")
+        self._meta_begin = (C.c_int64 * n)(*[off for off, _ in self.meta_ranges])
+        self._meta_len = (C.c_int64 * n)(*[ln for _, ln in self.meta_ranges])
+        self._loss_slot = torch.zeros(1, dtype=torch.float32, device=m.params.device)
+        return self.meta_train
+
+    def meta_train(self, data, offset, rows):
+        """One call of the K.function: gradients of one mini-batch added into ``accum_grads`` (:231  K.update_add(ag, g))."""
+        m = self.model
+        m.grads_on_batch(data, offset, rows, self._loss_slot)
+        for n, (acc, g, zero) in self._ranges(self.accum_grads, m.grads, self._zeros):
+            m.ctx.call("mamdr_axpy_diff", _ptr(acc), _ptr(g), _ptr(zero), 1.0, n, m.stream)   # acc += (g - 0) * 1: exact
+            m.ctx.launches += 1
+
+    def meta_train_pass(self, data, steps):
+        """``for _ in range(steps): meta_train(next(iterator))`` over the order installed on ``data``."""
+        bs = data.batch_size
+        for s in range(int(steps)):
+            self.meta_train(data, s * bs, min(bs, data.n_data - s * bs))
+
+    def clear_grads(self):                                             # :203
+        m = self.model
+        for n, (acc, zero) in self._ranges(self.accum_grads, self._zeros):
+            m.ctx.call("mamdr_copy", _ptr(acc), _ptr(zero), n, m.stream)
+            m.ctx.launches += 1
+
+    def meta_parms_update_step(self):
+        """``meta_optimizer.apply_gradients(zip(accum_grads, model_meta_parms))`` (:214): one TF ApplyAdam of the SECOND
+        optimizer on the live meta parameters; the accumulators are left as they are."""
+        m = self.model
+        tc = self.train_config
+        grads = self.accum_grads
+        if self._grad_scale is not None:
+            # scaled = accum / scale, exact: theta_i += accum / sample_num * beta with theta_i = 0, beta = 1 (clears ITS input, a copy)
+            for n, (scr, acc, out, zero) in self._ranges(self._scratch, self.accum_grads, self._scaled, self._zeros):
+                m.ctx.call("mamdr_copy", _ptr(scr), _ptr(acc), n, m.stream)
+                m.ctx.call("mamdr_copy", _ptr(out), _ptr(zero), n, m.stream)
+                m.ctx.call("mamdr_dr_apply_accum", _ptr(out), _ptr(scr), self._grad_scale, 1.0, n, m.stream)
+                m.ctx.launches += 3
+            grads = self._scaled
+        m.ctx.call("mamdr_adam_ranges_step", _ptr(m.params), _ptr(self._meta_m), _ptr(self._meta_v), _ptr(grads),
+                   self._meta_begin, self._meta_len, len(self.meta_ranges), _ptr(self._meta_opt_state),
+                   float(tc['meta_learning_rate']), m.beta1, m.beta2, m.eps, m.stream)
+        m.ctx.launches += 1
+
+    # ---- maml.py:235-242
+    def _meta_train_step(self):
+        self.meta_parms_update_step()
+        self.clear_grads()
+        return self._get_meta_weights()
+
+    # ---- maml.py:289-341
+    def build_meta_data_split(self):
+        """Per domain: the meta-train and meta-val datasets as views of the device-resident split.  ``meta-train/val``: the
+        first ``int(n * ratio)`` samples / the rest, each reshuffled per pass (take-then-shuffle, exclusive);
+        ``meta-train/val-no-exclusive``: the first ``n_train`` / the last ``n - n_train`` of two INDEPENDENT shuffles (the two
+        iterators of the reference re-shuffle separately); anything else ("train-train"): both over all samples."""
+        tc = self.train_config
+        if tc['target_domain'] >= 0:
+            raise NotImplementedError("target_domain >= 0 is not used by any shipped config")
+        split = {}
+        for idx, d in self.dataset.train_dataset.items():
+            data, n = d['data'], d['n_data']
+            if tc['meta_split'] == "meta-train/val":
+                n_train = int(n * tc['meta_split_ratio'])
+                train_view, meta_view = SplitView(data, 0, n_train), SplitView(data, n_train, n)
+            elif tc['meta_split'] == "meta-train/val-no-exclusive":
+                n_train = int(n * tc['meta_split_ratio'])
+                train_view, meta_view = SplitView(data, 0, n, slice(0, n_train)), SplitView(data, 0, n, slice(n_train, n))
+            else:
+                n_train = n
+                train_view, meta_view = SplitView(data, 0, n), SplitView(data, 0, n)
+            n_test = n - n_train if n_train != n else n
+            bs = float(self.dataset.batch_size)
+            split[idx] = {"train_iter": train_view, "train_step": int(math.ceil(n_train / bs)),
+                          "meta_iter": meta_view, "meta_val_step": int(math.ceil(n_test / bs))}
+        return split
+
+    def _init_iter(self, view):
+        """``K.get_session().run(iterator.initializer)``: the next pass's shuffle, from the injected schedule."""
+        view.set_order(self.schedule.batch_order(view.domain, view.hi - view.lo))
+
+    # ---- maml.py:35-151 (first-order MAML: Adam inner steps on meta-train, gradients of meta-val at the adapted weights,
+    # applied to theta by the meta Adam -- per domain, or summed over the epoch for `batch` names)
+    def prepare(self):
+        self._get_model_meta_parms()                               # :48
+        self.meta_weights = self._get_meta_weights()               # :50
+        self._make_meta_train_function()                           # :51
+        self.model.reset_optimizer()                               # :53 global_variables_initializer (both optimizers' slots)
+        self.meta_data_split = self.build_meta_data_split()        # :55
+        self.train_sequence = list(range(self.n_domain))           # :56
+
+    def _inner_loop(self, idx, d):
+        """:86-104 -- `train_step` x model.train_on_batch(train_iter), then `meta_val_step` x meta_train(meta_iter)."""
+        tc = self.train_config
+        train_step, meta_val_step = d['train_step'], d['meta_val_step']
+        if tc['meta_train_step'] > 0:
+            train_step = min(train_step, tc['meta_train_step'])
+            meta_val_step = min(meta_val_step, tc['meta_train_step'])
+        self.run_view_train_pass(d['train_iter'], train_step)
+        self.meta_train_pass(d['meta_iter'], meta_val_step)
+
+    def run_view_train_pass(self, view, steps):
+        """`steps` x ``model.train_on_batch`` over a split view (the model's own Adam)."""
+        if steps > 0:
+            self.last_pass_losses = self.model.fit_pass(view, steps)
+
+    def train_epoch(self, epoch=0):
+        batch = "batch" in self.model_config['name']
+        self.train_sequence = self.schedule.shuffle_sequence(self.train_sequence)   # :66
+        for idx in self.train_sequence:
+            d = self.meta_data_split[idx]
+            for metric in self.model.stateful_metric_functions:    # :72-73
+                metric.reset_states()
+            self._set_model_meta_parms(self.meta_weights)          # :76
+            self._init_iter(d['train_iter'])                       # :84
+            self._init_iter(d['meta_iter'])                        # :85
+            self._inner_loop(idx, d)
+            if batch:                                              # :112-113
+                continue
+            self._set_model_meta_parms(self.meta_weights)          # :115
+            self.meta_weights = self._meta_train_step()            # :116
+        if batch:                                                  # :119-121
+            self._set_model_meta_parms(self.meta_weights)
+            self.meta_weights = self._meta_train_step()
+        self._set_model_meta_parms(self.meta_weights)              # :122
+
+    def train(self):
+        self.log("Start {} training on model: {}".format(type(self).__name__, self.model_config['name']))
+        self.prepare()
+        for epoch in range(self.train_config['epoch']):
+            self.log("Epoch: {}".format(epoch), "-" * 30)
+            self.train_epoch(epoch)
+            if epoch % self.train_config['val_every_step'] == 0:   # :130-144
+                val_avg_loss, val_avg_auc, val_domain_loss, val_domain_auc = self.val()
+                if self.early_stop_step(val_avg_auc):
+                    break
+                self.log("Test Result: ")
+                self.val_and_test("test")
 
     # ---- maml.py:343-353
     def val(self):

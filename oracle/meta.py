@@ -166,6 +166,157 @@ class OracleReptile(OracleDN):
         self.model.set_weights(self.meta_weights)                    # :99
 
 
+class OracleMAML(OracleDN):
+    """First-order MAML, ``model_zoo/maml.py:35-151,196-242,289-341`` with ``target_domain=-1``: per domain the model is reset
+    to theta, trained with its own Adam on the meta-train part, the gradients of the meta-val batches at the adapted weights
+    are accumulated (inference-mode forward, ``OracleMLP.gradients(train=False)``) and a SECOND Adam (``meta_learning_rate``)
+    applies them to theta -- per domain, or once per epoch for ``batch`` names."""
+
+    def __init__(self, model, data, train_config, batch_size, schedule, name='mlp_meta'):
+        from .mlp import AdamState
+        OracleDN.__init__(self, model, data, train_config, batch_size, schedule)
+        self.name = name
+        self.sequence = list(range(len(data['train'])))                      # :56
+        mode = train_config.get('average_meta_grad', 'none')
+        if mode in ('moving_mean', 'drop'):
+            raise NotImplementedError(mode)
+        self.scale = None
+        if mode == 'mean' and train_config['meta_train_step'] > 0:          # :208-210
+            self.scale = np.float32(float(len(self.sequence) * train_config['meta_train_step']))
+        self.accum = [np.zeros_like(w) for w in self.meta_weights]           # :202
+        self.meta_adam = AdamState(self.meta_weights, lr=train_config['meta_learning_rate'])   # :201
+        self.split = self.build_meta_data_split()
+
+    def build_meta_data_split(self):                                         # :289-341
+        tc = self.tc
+        out = {}
+        for idx, d in self.data['train'].items():
+            n = len(d['uid'])
+            if tc['meta_split'] == "meta-train/val":
+                n_train = int(n * tc['meta_split_ratio'])
+                tr, mv = (0, n_train, slice(0, n_train)), (n_train, n, slice(0, n - n_train))
+            elif tc['meta_split'] == "meta-train/val-no-exclusive":
+                n_train = int(n * tc['meta_split_ratio'])
+                tr, mv = (0, n, slice(0, n_train)), (0, n, slice(n_train, n))
+            else:
+                n_train = n
+                tr, mv = (0, n, slice(0, n)), (0, n, slice(0, n))
+            n_test = n - n_train if n_train != n else n
+            out[idx] = {'train': tr, 'meta': mv, 'train_step': n_steps(n_train, self.bs), 'meta_val_step': n_steps(n_test, self.bs)}
+        return out
+
+    def _order(self, idx, window):
+        lo, hi, pick = window
+        return (self.schedule.batch_order(idx, hi - lo)[pick] + np.int32(lo)).astype(np.int32)
+
+    def meta_train_pass(self, idx, order, steps):
+        """`steps` calls of the accumulating K.function (:231 update_add)."""
+        d = self.data['train'][idx]
+        for s in range(steps):
+            sel = order[s * self.bs:(s + 1) * self.bs]
+            loss, p, grads = self.model.gradients(d['uid'][sel], d['pid'][sel], idx, d['label'][sel], train=False)
+            self.model.auc.update_state(d['label'][sel], p.astype(np.float32))
+            for a, g in zip(self.accum, grads):
+                a += g
+
+    def meta_parms_update_step(self):                                        # :214 (on the LIVE variables)
+        grads = self.accum if self.scale is None else [a / self.scale for a in self.accum]
+        self.meta_adam.apply(self.model.weights, grads)
+
+    def _meta_train_step(self):                                              # :235-242
+        self.meta_parms_update_step()
+        for a in self.accum:
+            a[...] = 0
+        return self.model.get_weights()
+
+    def _inner_loop(self, idx, sp, order_train, order_meta):
+        tc = self.tc
+        train_step, meta_val_step = sp['train_step'], sp['meta_val_step']
+        if tc['meta_train_step'] > 0:
+            train_step, meta_val_step = min(train_step, tc['meta_train_step']), min(meta_val_step, tc['meta_train_step'])
+        if train_step > 0:
+            train_pass(self.model, self.data['train'][idx], idx, order_train, self.bs, train_step)   # :86-93
+        self.meta_train_pass(idx, order_meta, meta_val_step)                # :101-104
+
+    def train_epoch(self):
+        batch = "batch" in self.name
+        self.sequence = self.schedule.shuffle_sequence(self.sequence)       # :66
+        for idx in self.sequence:
+            sp = self.split[idx]
+            self.model.auc.reset_states()
+            self.model.set_weights(self.meta_weights)                        # :76
+            order_train = self._order(idx, sp['train'])                      # :84
+            order_meta = self._order(idx, sp['meta'])                        # :85
+            self._inner_loop(idx, sp, order_train, order_meta)
+            if batch:
+                continue
+            self.model.set_weights(self.meta_weights)                        # :115
+            self.meta_weights = self._meta_train_step()                      # :116
+        if batch:                                                            # :119-121
+            self.model.set_weights(self.meta_weights)
+            self.meta_weights = self._meta_train_step()
+        self.model.set_weights(self.meta_weights)                            # :122
+
+
+class OracleMLDG(OracleMAML):
+    """``model_zoo/mldg.py:35-155``: accumulate at theta over meta-train, one meta-Adam apply (accumulators kept), accumulate
+    over meta-val at the moved weights, reset to theta, apply + clear."""
+
+    def _inner_loop(self, idx, sp, order_train, order_meta):
+        tc = self.tc
+        train_step, meta_val_step = sp['train_step'], sp['meta_val_step']
+        if tc['meta_train_step'] > 0:
+            train_step, meta_val_step = min(train_step, tc['meta_train_step']), min(meta_val_step, tc['meta_train_step'])
+        self.meta_train_pass(idx, order_train, train_step)                   # :92-96
+        self.meta_parms_update_step()                                        # :107-108
+        self.meta_train_pass(idx, order_meta, meta_val_step)                 # :112-114
+
+
+def pcgrad_project(final_grads, current_grads, aux_grads):
+    """``PCGrad.PCGrad`` (model_zoo/pcgrad.py:152-160), verbatim semantics (the caller passes the SAME list as final and current)."""
+    for var in range(len(final_grads)):
+        grad_dot = np.sum(current_grads[var] * aux_grads[var], axis=-1)
+        aux_grads[var][grad_dot > 0] -= np.expand_dims(
+            grad_dot[grad_dot > 0] / np.linalg.norm(current_grads[var][grad_dot > 0], axis=-1), -1) * current_grads[var][grad_dot > 0]
+        final_grads[var] += aux_grads[var]
+
+
+class OraclePCGrad(OracleMAML):
+    """``model_zoo/pcgrad.py:35-150``."""
+
+    def build_meta_data_split(self):                                         # :324-330
+        return {idx: {'train_step': n_steps(len(d['uid']), self.bs)} for idx, d in self.data['train'].items()}
+
+    def train_epoch(self):
+        tc = self.tc
+        self.sequence = self.schedule.shuffle_sequence(self.sequence)       # :65
+        for idx in self.sequence:
+            self.model.auc.reset_states()
+            n = len(self.data['train'][idx]['uid'])
+            order = self.schedule.batch_order(idx, n)                        # :79
+            train_step = self.split[idx]['train_step']
+            if tc['meta_train_step'] > 0:
+                train_step = min(train_step, tc['meta_train_step'])
+            for a in self.accum:                                             # :86
+                a[...] = 0
+            self.meta_train_pass(idx, order, train_step)                     # :88-91
+            current = [a.copy() for a in self.accum]                         # :103
+            final = current                                                  # :104 (alias)
+            candidates = list(self.sequence)
+            candidates.remove(idx)
+            for aux_idx in self.schedule.sample_support(candidates, tc['sample_num']):   # :109-111
+                na = len(self.data['train'][aux_idx]['uid'])
+                aux_order = self.schedule.batch_order(aux_idx, na)           # :115
+                for a in self.accum:                                         # :118
+                    a[...] = 0
+                self.meta_train_pass(aux_idx, aux_order, self.split[aux_idx]['train_step'])   # :120-121
+                aux = [a.copy() for a in self.accum]                         # :123
+                pcgrad_project(final, current, aux)                          # :124
+            for a, f in zip(self.accum, final):                              # :127
+                a[...] = f
+            self._meta_train_step()                                          # :128
+
+
 class MetaSubset(object):
     """View of a model whose ``get_weights`` / ``set_weights`` only cover the meta parameters selected by
     ``MAML._get_model_meta_parms`` (``model_zoo/maml.py:153-179``: name-substring lists such as STAR's

@@ -189,14 +189,16 @@ class OracleMLP(object):
         return float(np.mean(bce, dtype=np.float64)) + reg
 
     # ---- one training mini-batch ------------------------------------------------------------
-    def gradients(self, uid, pid, domain, label, masks=None):
+    def gradients(self, uid, pid, domain, label, masks=None, train=True):
+        """``train=False``: the gradients of the INFERENCE-mode loss (no dropout) -- what the K.function of
+        ``model_zoo/maml.py:196-233`` computes, which is built without the learning-phase placeholder ([EXT] default 0)."""
         sp, dt = self.spec, self.dtype.type
         b = len(uid)
         y = np.asarray(label, dtype=self.dtype).reshape(-1)
-        H, p = self.forward(uid, pid, domain, train=True, masks=masks)
+        H, p = self.forward(uid, pid, domain, train=train, masks=masks)
         loss = self.loss_from_p(p, y)
         L = len(sp.hidden)
-        inv_keep = (np.float32(1.0) / np.float32(1.0 - sp.dropout)).astype(self.dtype) if sp.dropout > 0 else dt(1)
+        inv_keep = (np.float32(1.0) / np.float32(1.0 - sp.dropout)).astype(self.dtype) if (sp.dropout > 0 and train) else dt(1)
         ds = (p - y) / dt(b)
         ds = np.where(np.abs(self._last_logit) <= dt(LOGIT_CLIP), ds, dt(0)).astype(self.dtype)
         g = {}

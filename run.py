@@ -46,7 +46,8 @@ def build(config, dataset=None):
     if "uncertainty_weight" in name:
         raise NotImplementedError("uncertainty_weight is out of scope (baseline method, SURVEY.md 2.1 #10)")
     if "pcgrad" in name:
-        raise NotImplementedError("pcgrad is out of scope (baseline method, SURVEY.md 2.1 #9)")
+        from mamdr_b200.pcgrad import PCGrad
+        model = PCGrad(model)
 
     if "meta" in name:
         if "domain_negotiation" in name:
@@ -57,9 +58,11 @@ def build(config, dataset=None):
             from mamdr_b200.reptile import Reptile
             model = Reptile(model)
         elif "mldg" in name:
-            raise NotImplementedError("mldg is out of scope (baseline method, SURVEY.md 2.1 #8)")
+            from mamdr_b200.mldg import MLDG
+            model = MLDG(model)
         else:
-            raise NotImplementedError("plain MAML is out of scope (SURVEY.md 2.1 #3)")
+            from mamdr_b200.maml import MAML
+            model = MAML(model)
     return model
 
 

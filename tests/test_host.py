@@ -162,10 +162,15 @@ def test_dispatch_rules(monkeypatch):
     for name in ("mlp_meta_reptile_finetune", "mlp_meta_reptile_batch"):
         c["model"]["name"] = name
         assert type(run.build(c, dataset=ds)) is Reptile
-    for name in ("mlp_meta_mldg", "mlp_meta_maml_finetune", "mlp_pcgrad", "mlp_uncertainty_weight"):
+    from mamdr_b200.maml import MAML
+    from mamdr_b200.mldg import MLDG
+    from mamdr_b200.pcgrad import PCGrad
+    for name, cls in (("mlp_meta_mldg", MLDG), ("mlp_meta_maml_finetune", MAML), ("mlp_pcgrad", PCGrad)):   # row f4
         c["model"]["name"] = name
-        with pytest.raises(NotImplementedError):
-            run.build(c, dataset=ds)
+        assert type(run.build(c, dataset=ds)) is cls
+    c["model"]["name"] = "mlp_uncertainty_weight"
+    with pytest.raises(NotImplementedError):
+        run.build(c, dataset=ds)
 
 
 def test_mtl_topology_matches_oracle_layout():
@@ -209,7 +214,8 @@ def test_package_exports_the_reference_class_names():
     assert issubclass(MAMDR, MAML) and issubclass(DomainNegotiation, MAML) and issubclass(Reptile, MAML)
     assert issubclass(DeepCTR, BaseModel) and issubclass(Star, BaseModel) and issubclass(DeepMTLCTR, BaseModel)
     assert MultiDomainDataset.__module__ == "mamdr_b200.dataset"
-    assert sorted(mamdr_b200.__all__) == sorted(["MAML", "DomainNegotiation", "MAMDR", "Reptile", "BaseModel", "DeepCTR", "Star",
+    assert sorted(mamdr_b200.__all__) == sorted(["MAML", "DomainNegotiation", "MAMDR", "Reptile", "MLDG", "PCGrad", "BaseModel", "DeepCTR", "Star",
                                                  "DeepMTLCTR", "MultiDomainDataset"])
+    assert issubclass(mamdr_b200.PCGrad, MAML) and issubclass(mamdr_b200.MLDG, MAML)
     with pytest.raises(AttributeError):
-        mamdr_b200.PCGrad
+        mamdr_b200.UncertaintyWeight

@@ -283,8 +283,7 @@ def test_oracle_loops_replay_the_reference_loops(kind, name, method):
 import json  # noqa: E402
 
 DISPATCH = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_dispatch_v1.json")))
-OUT_OF_SCOPE = {"mlp_meta_mldg": NotImplementedError, "mlp_meta": NotImplementedError, "mlp_pcgrad": NotImplementedError,
-                "mlp_uncertainty_weight": NotImplementedError, "nothing": ValueError}
+OUT_OF_SCOPE = {"mlp_uncertainty_weight": NotImplementedError, "nothing": ValueError}
 
 
 @pytest.mark.parametrize("name", sorted(DISPATCH["dispatch"]))
@@ -297,13 +296,18 @@ def test_product_cli_dispatch_matches_the_reference(monkeypatch, name):
     import mamdr_b200.deep_mtl_ctr as p_mtl
     import mamdr_b200.deepctr as p_ctr
     import mamdr_b200.domain_negotiation as p_dn
+    import mamdr_b200.maml as p_maml
     import mamdr_b200.mamdr as p_mamdr
+    import mamdr_b200.mldg as p_mldg
+    import mamdr_b200.pcgrad as p_pcgrad
     import mamdr_b200.reptile as p_rep
     import mamdr_b200.star as p_star
     trace = []
-    rec = mrg.recorder_classes(["MultiDomainDataset", "Star", "DeepCTR", "DeepMTLCTR", "DomainNegotiation", "MAMDR", "Reptile"], trace)
+    rec = mrg.recorder_classes(["MultiDomainDataset", "Star", "DeepCTR", "DeepMTLCTR", "DomainNegotiation", "MAMDR", "Reptile", "MAML",
+                                "MLDG", "PCGrad"], trace)
     for mod, cls in ((p_dataset, "MultiDomainDataset"), (p_star, "Star"), (p_ctr, "DeepCTR"), (p_mtl, "DeepMTLCTR"),
-                     (p_dn, "DomainNegotiation"), (p_mamdr, "MAMDR"), (p_rep, "Reptile")):
+                     (p_dn, "DomainNegotiation"), (p_mamdr, "MAMDR"), (p_rep, "Reptile"), (p_maml, "MAML"), (p_mldg, "MLDG"),
+                     (p_pcgrad, "PCGrad")):
         monkeypatch.setattr(mod, cls, rec[cls])
     config = {"model": {"name": name}, "dataset": {"seed": 1}}
     if name in OUT_OF_SCOPE:
