@@ -222,25 +222,31 @@ class MAML(object):
         if steps > 0:
             self.last_pass_losses = self.model.fit_pass(view, steps)
 
+    def domain_step(self, idx):
+        """The body of the per-domain loop (:67-116)."""
+        d = self.meta_data_split[idx]
+        for metric in self.model.stateful_metric_functions:    # :72-73
+            metric.reset_states()
+        self._set_model_meta_parms(self.meta_weights)          # :76
+        self._init_iter(d['train_iter'])                       # :84
+        self._init_iter(d['meta_iter'])                        # :85
+        self._inner_loop(idx, d)
+        if "batch" in self.model_config['name']:               # :112-113
+            return
+        self._set_model_meta_parms(self.meta_weights)          # :115
+        self.meta_weights = self._meta_train_step()            # :116
+
     def train_epoch(self, epoch=0):
-        batch = "batch" in self.model_config['name']
         self.train_sequence = self.schedule.shuffle_sequence(self.train_sequence)   # :66
         for idx in self.train_sequence:
-            d = self.meta_data_split[idx]
-            for metric in self.model.stateful_metric_functions:    # :72-73
-                metric.reset_states()
-            self._set_model_meta_parms(self.meta_weights)          # :76
-            self._init_iter(d['train_iter'])                       # :84
-            self._init_iter(d['meta_iter'])                        # :85
-            self._inner_loop(idx, d)
-            if batch:                                              # :112-113
-                continue
-            self._set_model_meta_parms(self.meta_weights)          # :115
-            self.meta_weights = self._meta_train_step()            # :116
-        if batch:                                                  # :119-121
+            self.domain_step(idx)
+        self.finish_epoch()
+
+    def finish_epoch(self):
+        if "batch" in self.model_config['name']:               # :119-121
             self._set_model_meta_parms(self.meta_weights)
             self.meta_weights = self._meta_train_step()
-        self._set_model_meta_parms(self.meta_weights)              # :122
+        self._set_model_meta_parms(self.meta_weights)          # :122
 
     def train(self):
         self.log("Start {} training on model: {}".format(type(self).__name__, self.model_config['name']))

@@ -31,32 +31,33 @@ class PCGrad(MAML):
                        rows, cols, m.stream)
             m.ctx.launches += 1
 
-    def train_epoch(self, epoch=0):
+    def finish_epoch(self):
+        pass
+
+    def domain_step(self, idx):
         tc = self.train_config
         m = self.model
-        self.train_sequence = self.schedule.shuffle_sequence(self.train_sequence)    # :65
-        for idx in self.train_sequence:
-            d = self.meta_data_split[idx]
-            for metric in m.stateful_metric_functions:                               # :71-72
-                metric.reset_states()
-            self._init_iter(d['train_iter'])                                         # :79
-            train_step = d['train_step']
-            if tc['meta_train_step'] > 0:                                            # :82-83
-                train_step = min(train_step, tc['meta_train_step'])
-            self.clear_grads()                                                       # :86
-            self.meta_train_pass(d['train_iter'], train_step)                        # :88-91
-            for n, (fin, acc) in self._ranges(self._final, self.accum_grads):        # :103-104 current_grads = final_grads
-                m.ctx.call("mamdr_copy", _ptr(fin), _ptr(acc), n, m.stream)
-                m.ctx.launches += 1
-            candidates = list(self.train_sequence)                                   # :107-109
-            candidates.remove(idx)
-            for aux_idx in self.schedule.sample_support(candidates, tc['sample_num']):
-                aux_d = self.meta_data_split[aux_idx]
-                self._init_iter(aux_d['train_iter'])                                 # :115
-                self.clear_grads()                                                   # :118
-                self.meta_train_pass(aux_d['train_iter'], aux_d['train_step'])       # :120-121 (no meta_train_step cap here)
-                self.project(self._final, self.accum_grads)                          # :123-124
-            for n, (acc, fin) in self._ranges(self.accum_grads, self._final):        # :127 set_accum_grads(final_grads)
-                m.ctx.call("mamdr_copy", _ptr(acc), _ptr(fin), n, m.stream)
-                m.ctx.launches += 1
-            self._meta_train_step()                                                  # :128
+        d = self.meta_data_split[idx]
+        for metric in m.stateful_metric_functions:                               # :71-72
+            metric.reset_states()
+        self._init_iter(d['train_iter'])                                         # :79
+        train_step = d['train_step']
+        if tc['meta_train_step'] > 0:                                            # :82-83
+            train_step = min(train_step, tc['meta_train_step'])
+        self.clear_grads()                                                       # :86
+        self.meta_train_pass(d['train_iter'], train_step)                        # :88-91
+        for n, (fin, acc) in self._ranges(self._final, self.accum_grads):        # :103-104 current_grads = final_grads
+            m.ctx.call("mamdr_copy", _ptr(fin), _ptr(acc), n, m.stream)
+            m.ctx.launches += 1
+        candidates = list(self.train_sequence)                                   # :107-109
+        candidates.remove(idx)
+        for aux_idx in self.schedule.sample_support(candidates, tc['sample_num']):
+            aux_d = self.meta_data_split[aux_idx]
+            self._init_iter(aux_d['train_iter'])                                 # :115
+            self.clear_grads()                                                   # :118
+            self.meta_train_pass(aux_d['train_iter'], aux_d['train_step'])       # :120-121 (no meta_train_step cap here)
+            self.project(self._final, self.accum_grads)                          # :123-124
+        for n, (acc, fin) in self._ranges(self.accum_grads, self._final):        # :127 set_accum_grads(final_grads)
+            m.ctx.call("mamdr_copy", _ptr(acc), _ptr(fin), n, m.stream)
+            m.ctx.launches += 1
+        self._meta_train_step()                                                  # :128

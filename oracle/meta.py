@@ -238,24 +238,29 @@ class OracleMAML(OracleDN):
             train_pass(self.model, self.data['train'][idx], idx, order_train, self.bs, train_step)   # :86-93
         self.meta_train_pass(idx, order_meta, meta_val_step)                # :101-104
 
-    def train_epoch(self):
-        batch = "batch" in self.name
-        self.sequence = self.schedule.shuffle_sequence(self.sequence)       # :66
-        for idx in self.sequence:
-            sp = self.split[idx]
-            self.model.auc.reset_states()
-            self.model.set_weights(self.meta_weights)                        # :76
-            order_train = self._order(idx, sp['train'])                      # :84
-            order_meta = self._order(idx, sp['meta'])                        # :85
-            self._inner_loop(idx, sp, order_train, order_meta)
-            if batch:
-                continue
-            self.model.set_weights(self.meta_weights)                        # :115
-            self.meta_weights = self._meta_train_step()                      # :116
-        if batch:                                                            # :119-121
+    def domain_step(self, idx):
+        sp = self.split[idx]
+        self.model.auc.reset_states()
+        self.model.set_weights(self.meta_weights)                            # :76
+        order_train = self._order(idx, sp['train'])                          # :84
+        order_meta = self._order(idx, sp['meta'])                            # :85
+        self._inner_loop(idx, sp, order_train, order_meta)
+        if "batch" in self.name:
+            return
+        self.model.set_weights(self.meta_weights)                            # :115
+        self.meta_weights = self._meta_train_step()                          # :116
+
+    def finish_epoch(self):
+        if "batch" in self.name:                                             # :119-121
             self.model.set_weights(self.meta_weights)
             self.meta_weights = self._meta_train_step()
         self.model.set_weights(self.meta_weights)                            # :122
+
+    def train_epoch(self):
+        self.sequence = self.schedule.shuffle_sequence(self.sequence)       # :66
+        for idx in self.sequence:
+            self.domain_step(idx)
+        self.finish_epoch()
 
 
 class OracleMLDG(OracleMAML):
@@ -287,34 +292,35 @@ class OraclePCGrad(OracleMAML):
     def build_meta_data_split(self):                                         # :324-330
         return {idx: {'train_step': n_steps(len(d['uid']), self.bs)} for idx, d in self.data['train'].items()}
 
-    def train_epoch(self):
+    def finish_epoch(self):
+        pass
+
+    def domain_step(self, idx):
         tc = self.tc
-        self.sequence = self.schedule.shuffle_sequence(self.sequence)       # :65
-        for idx in self.sequence:
-            self.model.auc.reset_states()
-            n = len(self.data['train'][idx]['uid'])
-            order = self.schedule.batch_order(idx, n)                        # :79
-            train_step = self.split[idx]['train_step']
-            if tc['meta_train_step'] > 0:
-                train_step = min(train_step, tc['meta_train_step'])
-            for a in self.accum:                                             # :86
+        self.model.auc.reset_states()
+        n = len(self.data['train'][idx]['uid'])
+        order = self.schedule.batch_order(idx, n)                        # :79
+        train_step = self.split[idx]['train_step']
+        if tc['meta_train_step'] > 0:
+            train_step = min(train_step, tc['meta_train_step'])
+        for a in self.accum:                                             # :86
+            a[...] = 0
+        self.meta_train_pass(idx, order, train_step)                     # :88-91
+        current = [a.copy() for a in self.accum]                         # :103
+        final = current                                                  # :104 (alias)
+        candidates = list(self.sequence)
+        candidates.remove(idx)
+        for aux_idx in self.schedule.sample_support(candidates, tc['sample_num']):   # :109-111
+            na = len(self.data['train'][aux_idx]['uid'])
+            aux_order = self.schedule.batch_order(aux_idx, na)           # :115
+            for a in self.accum:                                         # :118
                 a[...] = 0
-            self.meta_train_pass(idx, order, train_step)                     # :88-91
-            current = [a.copy() for a in self.accum]                         # :103
-            final = current                                                  # :104 (alias)
-            candidates = list(self.sequence)
-            candidates.remove(idx)
-            for aux_idx in self.schedule.sample_support(candidates, tc['sample_num']):   # :109-111
-                na = len(self.data['train'][aux_idx]['uid'])
-                aux_order = self.schedule.batch_order(aux_idx, na)           # :115
-                for a in self.accum:                                         # :118
-                    a[...] = 0
-                self.meta_train_pass(aux_idx, aux_order, self.split[aux_idx]['train_step'])   # :120-121
-                aux = [a.copy() for a in self.accum]                         # :123
-                pcgrad_project(final, current, aux)                          # :124
-            for a, f in zip(self.accum, final):                              # :127
-                a[...] = f
-            self._meta_train_step()                                          # :128
+            self.meta_train_pass(aux_idx, aux_order, self.split[aux_idx]['train_step'])   # :120-121
+            aux = [a.copy() for a in self.accum]                         # :123
+            pcgrad_project(final, current, aux)                          # :124
+        for a, f in zip(self.accum, final):                              # :127
+            a[...] = f
+        self._meta_train_step()                                          # :128
 
 
 class MetaSubset(object):

@@ -164,7 +164,7 @@ class OracleMLP(object):
                 M = masks[l] if masks is not None else philox.dropout_mask(
                     b, sp.hidden[l], sp.dropout_seed + l, self.adam.step, sp.dropout, self.dtype.type)
                 A = A * M
-            if self.preact_log is not None and train:
+            if self.preact_log is not None:
                 # test diagnostic: the smallest |pre-activation| among the units that survive dropout -- a ReLU gate whose
                 # pre-activation is within rounding distance of zero can open on one implementation and close on another
                 az = np.abs(Z) if M is None else np.where(M > 0, np.abs(Z), np.inf)
