@@ -56,6 +56,11 @@ int         mamdr_ctx_create(mamdr_ctx** out, int device);
 void        mamdr_ctx_destroy(mamdr_ctx* ctx);
 const char* mamdr_last_error(const mamdr_ctx* ctx); /* ctx may be NULL: last create error */
 int         mamdr_sm_count(const mamdr_ctx* ctx);
+/* Number of CTAs the persistent pass kernel of THIS context launches (0 = one per SM, the default).  With n < SM count
+ * several contexts can run their passes CONCURRENTLY on disjoint SMs of one GPU, each on its own stream -- the opt-in
+ * "virtual ranks" mode (SURVEY.md 7.3 hard part 1(c): independent DR chains side by side; the semantics are those of the
+ * multi-GPU sharded schedule, model_zoo/mamdr.py:59-108 with the chains of different query domains run in parallel). */
+int         mamdr_ctx_set_pass_ctas(mamdr_ctx* ctx, int32_t n_ctas);
 
 /* ---- K1: embedding gather  (replaces tf.gather under Embedding, DeepCTR/deepctr.py:125-128) --
  * out[i, 0:dim] = table[ids[i], 0:dim], i < n.  dim % 4 == 0, rows 16-byte aligned, out_stride in

@@ -116,6 +116,7 @@ SIGNATURES = {
     "mamdr_ctx_destroy": (None, [_P]),
     "mamdr_last_error": (C.c_char_p, [_P]),
     "mamdr_sm_count": (C.c_int, [_P]),
+    "mamdr_ctx_set_pass_ctas": (C.c_int, [_P, _I32]),
     "mamdr_gather_f32": (C.c_int, [_P, _P, _I64, _I32, _P, _I64, _P, _I64, _P]),
     "mamdr_scatter_max_n": (_I64, []),
     "mamdr_scatter_workspace_bytes": (_SZ, [_I64]),

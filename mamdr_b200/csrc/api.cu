@@ -71,3 +71,11 @@ extern "C" void mamdr_ctx_destroy(mamdr_ctx* ctx) {
 extern "C" const char* mamdr_last_error(const mamdr_ctx* ctx) { return ctx ? ctx->err : g_mamdr_create_err; }
 
 extern "C" int mamdr_sm_count(const mamdr_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+
+extern "C" int mamdr_ctx_set_pass_ctas(mamdr_ctx* ctx, int32_t n_ctas) {
+    if (!ctx) return MAMDR_E_INVALID;
+    MAMDR_REQUIRE(ctx, n_ctas == 0 || (n_ctas >= 32 && n_ctas <= ctx->sm_count), MAMDR_E_INVALID,
+                  "pass kernel CTAs must be 0 (one per SM) or in [32, %d] (a CTA runs at most one domain job per mini-batch)", ctx->sm_count);
+    ctx->pass_ctas = n_ctas;
+    return MAMDR_OK;
+}

@@ -11,6 +11,7 @@ struct mamdr_ctx {
     int   device;
     int   sm_count;
     int   max_smem_optin;
+    int   pass_ctas;   // CTAs of the persistent pass kernel (0 = one per SM); mamdr_ctx_set_pass_ctas
     void* tmap_cache;  // tensor-map cache of the pass kernel (tc_tmap.cuh)
     void* prog;        // program being recorded (mamdr_program_begin .. mamdr_program_end), else NULL
     void* dbg_timing;  // debug: phase time stamps of the pass kernel (mamdr_debug_pass_timing)

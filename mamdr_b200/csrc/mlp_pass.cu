@@ -1634,7 +1634,7 @@ static int launch_program(mamdr_ctx* ctx, const MapTable& mp, const PassArgs& a,
     const size_t smem = smem_bytes();
     void* kargs[] = {(void*)&mp, (void*)&a};
     const void* fn = a.passes == 3 ? (const void*)pass_kernel<3> : (const void*)pass_kernel<1>;
-    MAMDR_CUDA_OK(ctx, cudaLaunchCooperativeKernel(fn, dim3(ctx->sm_count), dim3(kThreads), kargs, smem, st));
+    MAMDR_CUDA_OK(ctx, cudaLaunchCooperativeKernel(fn, dim3(ctx->pass_ctas > 0 ? ctx->pass_ctas : ctx->sm_count), dim3(kThreads), kargs, smem, st));
     return MAMDR_OK;
 }
 

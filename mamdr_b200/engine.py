@@ -103,6 +103,10 @@ class MLPModel(object):
                  dropout_seed=1024, l2_emb=1e-5, emb_trainable=False, user_table=None, item_table=None,
                  init_weights=None, lr=1e-3, max_batch=1024, precision=_lib.PREC_FP32, device="cuda:0",
                  use_graphs=True):
+        self._ctor = dict(n_uid=n_uid, n_pid=n_pid, n_domain=n_domain, emb_dim=emb_dim, hidden=hidden, dropout=dropout,
+                          dropout_seed=dropout_seed, l2_emb=l2_emb, emb_trainable=emb_trainable, user_table=user_table,
+                          item_table=item_table, lr=lr, max_batch=max_batch, precision=precision, device=device,
+                          use_graphs=use_graphs)
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("mamdr_b200 runs on CUDA devices only (no CPU fallback)")
@@ -428,6 +432,24 @@ class MLPModel(object):
                           self.l2_emb, _ptr(self._opt_prev), self.lr, self.beta1, self.beta2, self.eps,
                           _ptr(loss_slot), _ptr(self.table_ws), self.table_ws_bytes, st)
         self.ctx.launches += 2 + 2 * 2   # sort + segment-sum (both tables per launch), 2 x (slot scatter, table sweep)
+
+    # ---- virtual ranks: several models side by side on ONE GPU, each pass kernel on its own SM partition -------------
+    def set_pass_ctas(self, n):
+        """CTAs of this model's persistent pass kernel (0 = one per SM): ``mamdr_ctx_set_pass_ctas``."""
+        self.ctx.call("mamdr_ctx_set_pass_ctas", int(n))
+
+    def clone_lane(self):
+        """A second model of the same architecture on the same device with its own context, arena, optimizer slots and
+        workspaces (a "virtual rank").  State is brought over with ``copy_state_from``."""
+        lane = type(self)(init_weights=None, **self._ctor)
+        lane.optimizer, lane.sgd_lr, lane.lr = self.optimizer, self.sgd_lr, self.lr
+        return lane
+
+    def copy_state_from(self, other):
+        """params, Adam slots and beta powers / global step of ``other`` -> this model (device copies on the current stream)."""
+        for dst, src in ((self.params, other.params), (self.m, other.m), (self.v, other.v)):
+            self.copy_(dst, src)
+        self.opt_state.copy_(other.opt_state, non_blocking=True)
 
     # ---- gradient-only step + a second optimizer: what MAML / MLDG / PCGrad add to the compiled model ----------------
     def grads_on_batch(self, data, offset, rows, loss_slot, with_auc=True):

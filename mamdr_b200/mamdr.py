@@ -53,6 +53,38 @@ class MAMDR(SpecificBase):
         self.model.reset_optimizer()
         self.train_sequence = self.build_meta_data_split()
         self._accum = None
+        self._setup_lanes()
+
+    # ---- "virtual ranks" (opt-in, b200.virtual_ranks = V > 1, one process / one GPU): the DR chains of different query domains
+    # run CONCURRENTLY on V models ("lanes"), each lane's persistent pass kernel on 1 / V of the SMs and on its own stream.  The
+    # semantics are exactly those of the V-rank sharded schedule (replicated DN -> here: DN once at the full grid, then copied;
+    # LPT-assigned chains with per-rank Adam state; the last owner's optimizer state and live model adopted by all), judged
+    # against `OracleMAMDR.train_epoch_sharded(V)`.  A row-local chain keeps 64 of the 148 SMs busy: two
+    # chains side by side fill the machine (SURVEY.md 7.3 hard part 1(c)).  Never the default: V = 1 is the reference schedule.
+    def _setup_lanes(self):
+        self._lane_models = None
+        V = int(self.b200_config.get('virtual_ranks', 1))
+        if V <= 1:
+            return
+        if mdist.world()[1] > 1:
+            raise NotImplementedError("b200.virtual_ranks applies to single-process runs (use torchrun ranks OR virtual ranks)")
+        m = self.model
+        if not getattr(m, "pass_kernel", False) or m.emb_trainable or not hasattr(m, "clone_lane"):
+            raise NotImplementedError("b200.virtual_ranks needs the persistent pass kernel (frozen-table mlp, tf32 / tf32x3)")
+        if self.train_config['finetune_every_epoch'] or "batch" in self.model_config['name']:
+            raise NotImplementedError("b200.virtual_ranks with finetune_every_epoch / 'batch' names (their sharded schedule shards pairs)")
+        dev = m.device
+        self._lane_models = [(m, None)] + [(m.clone_lane(), torch.cuda.Stream(device=dev)) for _ in range(V - 1)]
+        self._lane_ctas = max(32, m.ctx.sm_count // V)
+        for lm, _ in self._lane_models[1:]:
+            lm.set_pass_ctas(self._lane_ctas)
+        self._lane_accum = [None] * V
+
+    def _n_shards(self):
+        world = mdist.world()[1]
+        if world > 1:
+            return world
+        return len(self._lane_models) if getattr(self, "_lane_models", None) else 1
 
     def _plan_epoch(self):
         """Everything of a meta-step that does not depend on the weights: the schedule draws (sequence shuffle :45-46, DR support
@@ -85,7 +117,7 @@ class MAMDR(SpecificBase):
         # those configs keep the chain sharding.
         pair_mode = batch_mode and world > 1 and not tc['finetune_every_epoch']
         owner = mdist.lpt_assign(mdist.dr_chain_costs(train_sequence, supports, n_step,
-                                                      tc['domain_regulation_step']), world)
+                                                      tc['domain_regulation_step']), self._n_shards())
         pair_owner = None
         if pair_mode:
             pair_owner = mdist.lpt_assign(mdist.dr_pair_costs(train_sequence, supports, n_step,
@@ -136,39 +168,15 @@ class MAMDR(SpecificBase):
             self._dr_pairs_sharded(train_sequence, supports, pair_owner, rank, use_program)
             self._prefetch_plan()
             return
+        lanes = getattr(self, "_lane_models", None) if world == 1 else None
+        if lanes:
+            self._dr_chains_on_lanes(train_sequence, supports, owner, batch_mode, beta, use_program, lanes)
+            self._prefetch_plan()
+            return
         for idx in train_sequence:
             if owner[idx] != rank:
                 continue
-            with self.model.program(use_program):
-                d = self.dataset.train_dataset[idx]
-                aux_idxs = supports[idx]
-                theta_i = self.domain_weights[idx]
-                # merged = theta (+|*) theta_i is never materialised on the host: model <- merged (:72,78)
-                self._set_model_merged(self.meta_weights, theta_i)
-                if batch_mode:
-                    self._zero_accum()
-                for k, aux_idx in enumerate(aux_idxs):
-                    self.log(f"Support Domain: {aux_idx}, Query Domain: {idx}")
-                    self.run_train_pass(aux_idx)                         # :85-86
-                    train_step = d['n_step']                             # :92-97
-                    if tc['domain_regulation_step'] > 0:
-                        train_step = min(train_step, tc['domain_regulation_step'])
-                    self.run_train_pass(idx, train_step)
-                    if batch_mode:                                       # :100-101
-                        self._accumulate_grad(theta_i)
-                        self._set_model_merged(self.meta_weights, theta_i)
-                    else:                                                # :103-105 + next iteration's :78
-                        self._dr_update(theta_i, beta)
-                if batch_mode:                                           # :107-108
-                    self._update_meta_weight_by_grads(theta_i)
-
-                if tc['finetune_every_epoch']:                           # :110-143
-                    merged = self._merge_weights(self.meta_weights, theta_i)
-                    self._set_model_meta_parms(merged)
-                    for m in self.model.stateful_metric_functions:
-                        m.reset_states()
-                    self.run_train_pass(idx)
-                    self._update_domain_weights(theta_i, merged)
+            self._dr_chain(idx, supports[idx], batch_mode, beta, use_program)
 
         if world > 1:
             # the one collective of the meta-step: theta_i from their owners + the Adam slots of the rank
@@ -189,6 +197,76 @@ class MAMDR(SpecificBase):
                 pn_steps.copy_(steps_f.to(torch.int32))
             m.set_opt_words(words)
         self._prefetch_plan()
+
+    def _dr_chain(self, idx, aux_idxs, batch_mode, beta, use_program):
+        """The DR chain of query domain `idx` (:62-143) on the current model / stream."""
+        tc = self.train_config
+        with self.model.program(use_program):
+            d = self.dataset.train_dataset[idx]
+            theta_i = self.domain_weights[idx]
+            # merged = theta (+|*) theta_i is never materialised on the host: model <- merged (:72,78)
+            self._set_model_merged(self.meta_weights, theta_i)
+            if batch_mode:
+                self._zero_accum()
+            for k, aux_idx in enumerate(aux_idxs):
+                self.log(f"Support Domain: {aux_idx}, Query Domain: {idx}")
+                self.run_train_pass(aux_idx)                         # :85-86
+                train_step = d['n_step']                             # :92-97
+                if tc['domain_regulation_step'] > 0:
+                    train_step = min(train_step, tc['domain_regulation_step'])
+                self.run_train_pass(idx, train_step)
+                if batch_mode:                                       # :100-101
+                    self._accumulate_grad(theta_i)
+                    self._set_model_merged(self.meta_weights, theta_i)
+                else:                                                # :103-105 + next iteration's :78
+                    self._dr_update(theta_i, beta)
+            if batch_mode:                                           # :107-108
+                self._update_meta_weight_by_grads(theta_i)
+
+            if tc['finetune_every_epoch']:                           # :110-143
+                merged = self._merge_weights(self.meta_weights, theta_i)
+                self._set_model_meta_parms(merged)
+                for m in self.model.stateful_metric_functions:
+                    m.reset_states()
+                self.run_train_pass(idx)
+                self._update_domain_weights(theta_i, merged)
+
+    def _dr_chains_on_lanes(self, train_sequence, supports, owner, batch_mode, beta, use_program, lanes):
+        """Virtual ranks: chain `idx` runs on lane owner[idx]; lanes differ in model, context and stream, so consecutive
+        chains of different lanes execute side by side.  The chains are ENQUEUED in sequence order (the staged sample orders
+        are consumed in that order); each lane executes its own chains in sequence order, like a rank of the sharded schedule."""
+        base = self.base_model
+        lane0 = lanes[0][0]
+        dev = lane0.device
+        main = torch.cuda.current_stream(dev)
+        after_dn = torch.cuda.Event()
+        after_dn.record(main)
+        for lm, ls in lanes[1:]:
+            with torch.cuda.stream(ls):
+                ls.wait_event(after_dn)          # theta, the staged orders and lane 0's post-DN state are ready
+                lm.copy_state_from(lane0)
+        lane0.set_pass_ctas(self._lane_ctas)
+        main_accum = self._accum
+        try:
+            for idx in train_sequence:
+                r = owner[idx]
+                lm, ls = lanes[r]
+                base.model = lm
+                self._accum = self._lane_accum[r]
+                with torch.cuda.stream(ls if ls is not None else main):
+                    self._dr_chain(idx, supports[idx], batch_mode, beta, use_program)
+                self._lane_accum[r] = self._accum
+        finally:
+            base.model = lane0
+            self._accum = main_accum
+            lane0.set_pass_ctas(0)
+        for lm, ls in lanes[1:]:
+            e = torch.cuda.Event()
+            e.record(ls)
+            main.wait_event(e)
+        last = owner[train_sequence[-1]]
+        if last != 0:                            # the Adam state and live model of the last chain's owner are adopted
+            lane0.copy_state_from(lanes[last][0])
 
     def _prefetch_plan(self):
         """Stage the NEXT meta-step while the GPU still runs this one (`b200.lookahead`, default on).  The draws happen in the
