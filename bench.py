@@ -356,7 +356,7 @@ def run_amazon(args):
     sampler = ClockSampler(0)
     sampler.start()
     evs = []
-    launches0 = model.ctx.launches
+    launches0 = sum(lm.ctx.launches for lm in lane_models)
     for _ in range(args.steps):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
@@ -512,10 +512,13 @@ def run_b200(args):
     config = load_config(args.workload)
     config["b200"]["device"] = "cuda:%d" % local_rank
     config["b200"]["precision"] = args.precision or ("fp32" if "star" in config["model"]["name"] else "tf32x3")   # STAR: fp32 path only
+    if args.virtual_ranks:
+        config["b200"]["virtual_ranks"] = args.virtual_ranks
     wrapper = runpy.build(config)
     base = wrapper.base_model
     model = base.model
     wrapper.prepare()
+    lane_models = [lm for lm, _ in (getattr(wrapper, "_lane_models", None) or [(model, None)])]
     dev = model.device
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     peaks = {}
@@ -561,7 +564,7 @@ def run_b200(args):
     barrier()
     # ---- device-resident timing: K steps, per-step CUDA events, L2 flushed between steps
     base.samples_trained = 0
-    launches0 = model.ctx.launches
+    launches0 = sum(lm.ctx.launches for lm in lane_models)
     evs = []
     barrier()
     sampler.mark_begin()
@@ -578,7 +581,7 @@ def run_b200(args):
     sampler.mark_end()
     clocks = sampler.stop()
     ms = sum(a.elapsed_time(b) for a, b in evs)
-    launches = model.ctx.launches - launches0
+    launches = sum(lm.ctx.launches for lm in lane_models) - launches0
     my_samples = base.samples_trained
     # whole-job samples: DN passes are replicated (count once), DR passes are sharded (sum over ranks)
     dn_samples = args.steps * sum(d["n_data"] for d in base.dataset.train_dataset.values())
@@ -621,10 +624,14 @@ def run_b200(args):
         alg_bytes_mb = 1572864 + 12288 + 4096 + 6 * 4 * 141057 + 32 * P
     flops_mb = 0.72e9
     if model.pass_kernel:
-        model.launch_times = []
+        for lm in lane_models:
+            lm.launch_times = []
         one_step(False)
         torch.cuda.synchronize()
-        launches_ev, model.launch_times = model.launch_times, None
+        launches_ev = []
+        for lm in lane_models:   # (virtual ranks: the lanes' launches overlap in time; their durations are summed)
+            launches_ev += lm.launch_times
+            lm.launch_times = None
     else:
         orig_fit = model.fit_pass
         launches_ev = []
@@ -652,11 +659,12 @@ def run_b200(args):
 
     # ---- the parity mode beside the benched one (N = 1): the same meta-step in fp32 mode (FFMA SIMT tower), the mode whose
     # free-running parameters meet the north-star 1e-4 bar (tests/test_gpu_trajectory.py)
-    parity_mode = None
-    if world == 1 and model.pass_kernel and not args.no_micro:
+    def side_run(over, steps):
+        """The same meta-step under another b200 setting, device-timed (2 warm-up steps, `steps` timed)."""
         c2 = load_config(args.workload)
         c2["b200"]["device"] = "cuda:%d" % local_rank
-        c2["b200"]["precision"] = "fp32"
+        c2["b200"]["precision"] = config["b200"]["precision"]
+        c2["b200"].update(over)
         w2 = runpy.build(c2)
         w2.prepare()
         for _ in range(2):
@@ -665,13 +673,25 @@ def run_b200(args):
         w2.base_model.samples_trained = 0
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        for _ in range(2):
+        for _ in range(steps):
+            flush.fill_(1)
             w2.train_epoch(0)
         b.record()
         torch.cuda.synchronize()
-        parity_mode = {"precision": "fp32", "value": w2.base_model.samples_trained / (a.elapsed_time(b) * 1e-3), "unit": "samples/s",
-                       "steps": 2, "note": "device-timed, same workload; fp32 FFMA tower (per-pass parity vs the CPU oracle 1e-6 in both modes, tests/test_gpu_trajectory.py)"}
+        v = w2.base_model.samples_trained / (a.elapsed_time(b) * 1e-3)
         del w2
+        return v
+
+    parity_mode = fill_mode = None
+    if world == 1 and model.pass_kernel and not args.no_micro and not args.virtual_ranks:
+        parity_mode = {"precision": "fp32", "value": side_run({"precision": "fp32"}, 2), "unit": "samples/s",
+                       "steps": 2, "note": "device-timed, same workload; fp32 FFMA tower (per-pass parity vs the CPU oracle 1e-6 in both modes, tests/test_gpu_trajectory.py)"}
+        if "batch" not in config["model"]["name"] and not config["train"].get("finetune_every_epoch"):
+            fill_mode = {"virtual_ranks": 2, "value": side_run({"virtual_ranks": 2}, 5), "unit": "samples/s", "steps": 5,
+                         "note": "OPT-IN, NOT the headline: b200.virtual_ranks = 2 runs the DR chains of different query domains side by side on two "
+                                 "74-SM partitions of this GPU (a row-local chain occupies 64 SMs).  Semantics = the 2-rank sharded schedule "
+                                 "(per-lane Adam state during DR, the last owner's state adopted), bit-identical to two real ranks and judged against "
+                                 "OracleMAMDR.train_epoch_sharded(2) (tests/test_gpu_virtual_ranks.py); `value` above is the reference's sequential schedule"}
 
     if rank != 0:
         return
@@ -727,8 +747,13 @@ def run_b200(args):
             "precision": config["b200"]["precision"], "precision_note": PRECISION_NOTE,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "micro": micro, "cpu_baseline": cpu,
-            "parity_mode": parity_mode,
+            "parity_mode": parity_mode, "fill_the_machine": fill_mode,
             "minibatches_per_step": steps_per_epoch, "wall_s": t_wall}
+    if args.virtual_ranks:
+        line["virtual_ranks"] = args.virtual_ranks
+        line["config"]["schedule"] = ("OPT-IN virtual ranks: the %d-rank sharded schedule on ONE GPU (DR chains side by side on SM partitions); "
+                                      "not the reference's sequential schedule -- compare with a --gpus %d line, not with the default line"
+                                      % (args.virtual_ranks, args.virtual_ranks))
     _emit(line)
 
 
@@ -742,6 +767,8 @@ def main():
     ap.add_argument("--precision", default=None, choices=[None, "fp32", "tf32", "tf32x3"],
                     help="tower GEMM mode (default tf32x3: tcgen05 with fp32-equivalent products)")
     ap.add_argument("--no-micro", action="store_true")
+    ap.add_argument("--virtual-ranks", type=int, default=0, help="opt-in: V DR chains side by side on SM partitions of one GPU "
+                    "(the V-rank sharded schedule; a separate bench line, never the headline)")
     ap.add_argument("--graphs", action="store_true", help="removed: CUDA-graph replay of sharded steps (NCCL collectives inside captures "
                     "dead-locked); the flag is rejected")
     ap.add_argument("--no-cpu", action="store_true")

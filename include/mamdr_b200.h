@@ -64,8 +64,9 @@ int         mamdr_ctx_set_pass_ctas(mamdr_ctx* ctx, int32_t n_ctas);
 
 /* ---- K1: embedding gather  (replaces tf.gather under Embedding, DeepCTR/deepctr.py:125-128) --
  * out[i, 0:dim] = table[ids[i], 0:dim], i < n.  dim % 4 == 0, rows 16-byte aligned, out_stride in
- * floats (>= dim, % 4 == 0).  Bit-exact.  ids outside [0, rows) -> row of zeros is NOT produced:
- * the call is undefined for such ids (the reference would raise inside tf.gather). */
+ * floats (>= dim, % 4 == 0).  Bit-exact.  NEGATIVE ids are padding (the fixed-capacity exchange blocks of
+ * the row-sharded tables): their output row is left untouched.  ids >= rows: undefined (the reference
+ * would raise inside tf.gather). */
 int mamdr_gather_f32(mamdr_ctx* ctx, const float* table_dev, int64_t rows, int32_t dim,
                      const int32_t* ids_dev, int64_t n, float* out_dev, int64_t out_stride,
                      mamdr_stream stream);
@@ -82,6 +83,18 @@ int mamdr_scatter_dedup_f32(mamdr_ctx* ctx, const int32_t* ids_dev, const float*
                             int64_t grad_stride, int64_t n, int32_t dim, int32_t* uniq_ids_dev,
                             float* uniq_rows_dev, int32_t* n_uniq_dev, void* ws_dev, size_t ws_bytes,
                             mamdr_stream stream);
+
+/* ---- routing for ROW-SHARDED tables (north_star: "tables that exceed a single GPU are row-sharded with NCCL all-to-all";
+ * row r lives on rank r % world at local index r / world; the reference keeps whole tables in one TF variable,
+ * DeepCTR/deepctr.py:105-126).  mamdr_route_plan: for the n local ids of one (or two: ids_b != NULL) id columns,
+ * slot[i] = owner * cap + (number of earlier local ids with the same owner), send[slot[i]] = id / world and every other
+ * entry of send[world * cap] = -1: fixed-capacity blocks, so the all-to-all splits are static.  n <= cap, world <= 64.
+ * mamdr_route_pack_rows: dst[slot[i], 0:dim] = src[i, 0:dim] * scale (gradient rows into the exchange buffer). */
+int mamdr_route_plan(mamdr_ctx* ctx, const int32_t* ids_a_dev, const int32_t* ids_b_dev, int32_t n, int32_t world,
+                     int32_t cap, int32_t* slot_a_dev, int32_t* slot_b_dev, int32_t* send_a_dev, int32_t* send_b_dev,
+                     mamdr_stream stream);
+int mamdr_route_pack_rows(mamdr_ctx* ctx, const float* src_dev, int64_t src_stride, const int32_t* slot_dev, int32_t n,
+                          int32_t dim, float scale, float* dst_dev, mamdr_stream stream);
 
 /* The same de-duplication for n beyond mamdr_scatter_max_n() (any n < 2^31), multi-CTA: a stable radix sort of
  * (id, position) + head scan, then ONE pass over the n gradient rows at HBM bandwidth.  uniq_ids: ascending, bit-exact.

@@ -12,7 +12,8 @@ the mathematically identical data-parallel restatement of one Keras train step o
     (``mamdr_scatter_dedup_f32``) and run the fused l2 + non-lazy Adam sweep over their shard (``mamdr_adam_table_step``);
   * dense tower gradients: one all-reduce(sum) of the B_r / B weighted arenas, then ``mamdr_adam_step`` on every rank
     (replicas stay bit-identical: same reduced bits, same update).
-Index bucketing (sort by owner, bincount, inverse permutation) uses torch tensor ops: plumbing around the collectives.  The
+Index bucketing is ONE kernel per step for both id columns (`mamdr_route_plan`), the gradient rows are packed into the exchange
+buffer by `mamdr_route_pack_rows`, rows are picked out of the received blocks by `mamdr_gather_f32`: no tensor-op plumbing.  The
 exchange buffers have a FIXED capacity (world x local-batch entries, -1 padded ids that the de-duplication skips), so every
 all-to-all has static, equal splits and a step never synchronises with the host.
 Dropout masks are indexed by the GLOBAL batch row (``mamdr_batch.row0`` = the slice start), so the sharded step draws exactly
@@ -30,24 +31,26 @@ from .engine import DomainData, MLPModel, _ptr
 
 class _Plan(object):
     """Routing of one id column with FIXED-capacity exchange buffers: every rank sends each owner a `cap`-entry block
-    (local row index, -1 = padding), so all split sizes are static -- no host synchronisation anywhere in a step."""
+    (local row index, -1 = padding), so all split sizes are static -- no host synchronisation anywhere in a step.  The plan
+    itself is ONE kernel for both id columns of a step (`mamdr_route_plan`: owner, stable position within the owner's block);
+    the buffers are persistent."""
 
-    def __init__(self, ids, world, cap):
-        self.n, self.world, self.cap = int(ids.numel()), int(world), int(cap)
-        dev = ids.device
-        ids64 = ids.to(torch.int64)
-        owner = ids64 % world
-        self.perm = torch.argsort(owner, stable=True)
-        sorted_owner = owner[self.perm]
-        counts = (owner.unsqueeze(1) == torch.arange(world, device=dev).unsqueeze(0)).sum(0)   # bincount would sync the host
-        starts = torch.cumsum(counts, 0) - counts
-        pos = torch.arange(self.n, device=dev) - starts[sorted_owner]
-        self.flat = sorted_owner * cap + pos                       # slot of the perm-ordered rows in the exchange buffers
-        send = torch.full((world * cap,), -1, dtype=torch.int32, device=dev)
-        send[self.flat] = (ids64[self.perm] // world).to(torch.int32)
-        self.recv_idx = torch.empty_like(send)                     # [world * cap]: block r = the rows rank r asks of me
-        dist.all_to_all_single(self.recv_idx, send)
-        self.n_recv = world * cap
+    def __init__(self, world, cap, device):
+        self.world, self.cap, self.n = int(world), int(cap), 0
+        self.n_recv = self.world * self.cap
+        self.slot = torch.zeros(self.cap, dtype=torch.int32, device=device)        # slot of local row i in the exchange buffers
+        self.send = torch.full((self.n_recv,), -1, dtype=torch.int32, device=device)
+        self.recv_idx = torch.empty_like(self.send)                                # block r = the rows rank r asks of me
+
+
+def route(ctx, plan_a, plan_b, ids_a, ids_b, n, stream):
+    """Plans for the two id columns of a slice of n rows (one launch), then the two id all-to-alls."""
+    ctx.call("mamdr_route_plan", _ptr(ids_a), _ptr(ids_b), int(n), plan_a.world, plan_a.cap, _ptr(plan_a.slot), _ptr(plan_b.slot),
+             _ptr(plan_a.send), _ptr(plan_b.send), stream)
+    ctx.launches += 1
+    for pl in (plan_a, plan_b):
+        pl.n = int(n)
+        dist.all_to_all_single(pl.recv_idx, pl.send)
 
 
 class ShardedTable(object):
@@ -72,22 +75,28 @@ class ShardedTable(object):
         f32 = dict(dtype=torch.float32, device=device)
         self.got, self.back = torch.zeros(max_recv, self.dim, **f32), torch.zeros(max_recv, self.dim, **f32)
         self.send, self.recv = torch.zeros(max_recv, self.dim, **f32), torch.zeros(max_recv, self.dim, **f32)
+        self.out = torch.zeros(int(cap), self.dim, **f32)
 
     def fetch(self, plan, stream):
-        """Rows of the ids behind ``plan`` in their original order (the plan already exchanged the ids)."""
+        """Rows of the ids behind ``plan`` in their original order (the plan already exchanged the ids): owners gather (the
+        -1 padding entries are skipped), equal-split all-to-all back, rows picked out of the received blocks by slot."""
         if self.rows:
-            self.ctx.call("mamdr_gather_f32", _ptr(self.table), self.rows, self.dim, _ptr(plan.recv_idx.clamp_min(0)), plan.n_recv,
+            self.ctx.call("mamdr_gather_f32", _ptr(self.table), self.rows, self.dim, _ptr(plan.recv_idx), plan.n_recv,
                           _ptr(self.got), self.dim, stream)
             self.ctx.launches += 1
         dist.all_to_all_single(self.back, self.got)
-        out = torch.empty(plan.n, self.dim, dtype=torch.float32, device=self.table.device)
-        out[plan.perm] = self.back[plan.flat]
-        return out
+        if plan.n:
+            self.ctx.call("mamdr_gather_f32", _ptr(self.back), plan.n_recv, self.dim, _ptr(plan.slot), plan.n, _ptr(self.out), self.dim, stream)
+            self.ctx.launches += 1
+        return self.out
 
-    def apply(self, plan, grad_rows, opt_state, lr, beta1, beta2, eps, loss_slot, stream):
-        """Send the gradient rows to their owners, de-duplicate, fused l2 + Adam over the local shard."""
-        self.send.zero_()
-        self.send[plan.flat] = grad_rows[plan.perm]
+    def apply(self, plan, grad_ptr, grad_stride, scale, opt_state, lr, beta1, beta2, eps, loss_slot, stream):
+        """Send the gradient rows (x scale) to their owners, de-duplicate, fused l2 + Adam over the local shard.  The padding
+        rows of the exchange buffer are never read (their ids are -1)."""
+        if plan.n:
+            self.ctx.call("mamdr_route_pack_rows", grad_ptr, int(grad_stride), _ptr(plan.slot), plan.n, self.dim, float(scale),
+                          _ptr(self.send), stream)
+            self.ctx.launches += 1
         dist.all_to_all_single(self.recv, self.send)
         self.ctx.call("mamdr_scatter_dedup_f32", _ptr(plan.recv_idx), _ptr(self.recv), self.dim, plan.n_recv, self.dim,
                       _ptr(self.uniq_ids), _ptr(self.uniq_rows), _ptr(self.n_uniq), _ptr(self.sc_ws), self.sc_ws.numel(), stream)
@@ -159,6 +168,7 @@ class ShardedJointTrainer(_Steps):
         self.users = ShardedTable(ctx, user_init, self.rank, self.world, self.device, l2_emb, bl)
         self.items = ShardedTable(ctx, item_init, self.rank, self.world, self.device, l2_emb, bl)
         self.arange = torch.arange(bl, dtype=torch.int32, device=self.device)
+        self.plan_u, self.plan_i = _Plan(self.world, bl, self.device), _Plan(self.world, bl, self.device)
         self.dX = torch.zeros(bl, emb_dim[0] + emb_dim[1], dtype=torch.float32, device=self.device)
         self.loss_local = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.loss_tab = torch.zeros(1, dtype=torch.float32, device=self.device)
@@ -183,8 +193,9 @@ class ShardedJointTrainer(_Steps):
         st = m.stream
         n = int(uid.numel())
         start, bl = self._slice(n)
-        u, p, y = uid[start:start + bl].contiguous(), pid[start:start + bl].contiguous(), label[start:start + bl].contiguous()
-        plan_u, plan_i = _Plan(u, self.world, self.max_local), _Plan(p, self.world, self.max_local)
+        u, p, y = uid[start:start + bl], pid[start:start + bl], label[start:start + bl]    # contiguous views of the columns
+        plan_u, plan_i = self.plan_u, self.plan_i
+        route(m.ctx, plan_u, plan_i, u, p, bl, st)
         rows_u, rows_i = self.users.fetch(plan_u, st), self.items.fetch(plan_i, st)
         w = float(bl) / float(n)                         # this rank's share of the batch mean
         self.loss_local.zero_()
@@ -201,15 +212,13 @@ class ShardedJointTrainer(_Steps):
             m.ctx.launches += 14
             m.grads.mul_(w)
             self.loss_local.mul_(w)
-            du = self.users.dim
-            gu, gi = (self.dX[:bl, :du] * w).contiguous(), (self.dX[:bl, du:] * w).contiguous()
         else:
             m.grads.zero_()
-            gu = torch.zeros(0, self.users.dim, dtype=torch.float32, device=self.device)
-            gi = torch.zeros(0, self.items.dim, dtype=torch.float32, device=self.device)
-        # tables first (they read the beta powers), then the dense arena (its apply advances them)
-        self.users.apply(plan_u, gu, m.opt_state, m.lr, m.beta1, m.beta2, m.eps, self.loss_tab, st)
-        self.items.apply(plan_i, gi, m.opt_state, m.lr, m.beta1, m.beta2, m.eps, self.loss_tab, st)
+        # tables first (they read the beta powers), then the dense arena (its apply advances them); the gradient rows are
+        # the two column blocks of dX [bl, du + di], weighted by this rank's share while they are packed
+        du, dxs = self.users.dim, self.dX.shape[1]
+        self.users.apply(plan_u, _ptr(self.dX), dxs, w, m.opt_state, m.lr, m.beta1, m.beta2, m.eps, self.loss_tab, st)
+        self.items.apply(plan_i, C.c_void_p(self.dX.data_ptr() + 4 * du), dxs, w, m.opt_state, m.lr, m.beta1, m.beta2, m.eps, self.loss_tab, st)
         dist.all_reduce(m.grads)
         m.ctx.call("mamdr_adam_step", _ptr(m.params), _ptr(m.m), _ptr(m.v), _ptr(m.grads), m.params.numel(), _ptr(m.opt_state), m.lr,
                    m.beta1, m.beta2, m.eps, st)
@@ -264,6 +273,7 @@ class ShardedMTLTrainer(_Steps):
         self.users = ShardedTable(m.ctx, user_init, self.rank, self.world, self.device, l2_emb, bl)
         self.items = ShardedTable(m.ctx, item_init, self.rank, self.world, self.device, l2_emb, bl)
         self.arange = torch.arange(bl, dtype=torch.int32, device=self.device)
+        self.plan_u, self.plan_i = _Plan(self.world, bl, self.device), _Plan(self.world, bl, self.device)
         self.dX = torch.zeros(bl, emb_dim[0] + emb_dim[1], dtype=torch.float32, device=self.device)
         self.loss_local = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.loss_tab = torch.zeros(1, dtype=torch.float32, device=self.device)
@@ -280,8 +290,9 @@ class ShardedMTLTrainer(_Steps):
         t = int(domain)
         n = int(uid.numel())
         start, bl = self._slice(n)
-        u, p, y = uid[start:start + bl].contiguous(), pid[start:start + bl].contiguous(), label[start:start + bl].contiguous()
-        plan_u, plan_i = _Plan(u, self.world, self.max_local), _Plan(p, self.world, self.max_local)
+        u, p, y = uid[start:start + bl], pid[start:start + bl], label[start:start + bl]    # contiguous views of the columns
+        plan_u, plan_i = self.plan_u, self.plan_i
+        route(m.ctx, plan_u, plan_i, u, p, bl, st)
         rows_u, rows_i = self.users.fetch(plan_u, st), self.items.fetch(plan_i, st)
         w = float(bl) / float(n)
         self.loss_local.zero_()
@@ -301,16 +312,13 @@ class ShardedMTLTrainer(_Steps):
             for g in spans:
                 g.mul_(w)
             self.loss_local.mul_(w)
-            du = self.users.dim
-            gu, gi = (self.dX[:bl, :du] * w).contiguous(), (self.dX[:bl, du:] * w).contiguous()
         else:
             for g in spans:
                 g.zero_()
-            gu = torch.zeros(0, self.users.dim, dtype=torch.float32, device=self.device)
-            gi = torch.zeros(0, self.items.dim, dtype=torch.float32, device=self.device)
         # tables first (they read the beta powers), then sub-model t's spans of the dense arena (that apply advances them)
-        self.users.apply(plan_u, gu, m.opt_state, m.lr, m.beta1, m.beta2, m.eps, self.loss_tab, st)
-        self.items.apply(plan_i, gi, m.opt_state, m.lr, m.beta1, m.beta2, m.eps, self.loss_tab, st)
+        du, dxs = self.users.dim, self.dX.shape[1]
+        self.users.apply(plan_u, _ptr(self.dX), dxs, w, m.opt_state, m.lr, m.beta1, m.beta2, m.eps, self.loss_tab, st)
+        self.items.apply(plan_i, C.c_void_p(self.dX.data_ptr() + 4 * du), dxs, w, m.opt_state, m.lr, m.beta1, m.beta2, m.eps, self.loss_tab, st)
         for g in spans:
             dist.all_reduce(g)
         m.ctx.call("mamdr_adam_ranges_step", _ptr(m.params), _ptr(m.m), _ptr(m.v), _ptr(m.grads), begin, length, n_spans,

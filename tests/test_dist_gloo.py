@@ -107,7 +107,7 @@ def test_sharded_oracle_equals_sequential_oracle_at_world1():
 def _routing_worker(rank, world, port, out_dir):
     os.environ.update({"MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port), "RANK": str(rank), "WORLD_SIZE": str(world)})
     dist.init_process_group("gloo")
-    from mamdr_b200.sharded import _Plan
+    from oracle.route import pack_rows, route_plan
     n_rows, dim, cap = 37, 4, 16
     g = torch.Generator().manual_seed(7)
     full = torch.randn(n_rows, dim, generator=g)                     # the "true" table, same on both ranks
@@ -116,26 +116,28 @@ def _routing_worker(rank, world, port, out_dir):
     n = cap - 3 * rank                                               # ragged slices: ranks hold different row counts
     ids = torch.randint(0, n_rows, (n,), generator=gi, dtype=torch.int32)
     ids[: n // 3] = ids[0]                                           # a hot id (duplicates) like the Zipf batches
-    plan = _Plan(ids, world, cap)
-    assert plan.recv_idx.numel() == world * cap and plan.n_recv == world * cap
-    valid = plan.recv_idx >= 0
-    assert int(valid.sum()) <= world * cap and bool((plan.recv_idx[valid] < local.shape[0]).all())
-    # fetch: owners gather (padding -> any row), equal-split all-to-all back, un-permute
-    got = local[plan.recv_idx.clamp_min(0).long()]
+    # the plan (mamdr_route_plan's contract, numpy restatement) and the id all-to-all with static, equal splits
+    slot_np, send_np = route_plan(ids.numpy(), world, cap)
+    slot, send_idx = torch.from_numpy(slot_np).long(), torch.from_numpy(send_np)
+    recv_idx = torch.empty_like(send_idx)
+    dist.all_to_all_single(recv_idx, send_idx)
+    assert recv_idx.numel() == world * cap
+    valid = recv_idx >= 0
+    assert int(valid.sum()) <= world * cap and bool((recv_idx[valid] < local.shape[0]).all())
+    # fetch: owners gather (padding entries skipped), equal-split all-to-all back, rows picked out by slot
+    got = torch.zeros(world * cap, dim)
+    got[valid] = local[recv_idx[valid].long()]
     back = torch.empty_like(got)
     dist.all_to_all_single(back, got)
-    out = torch.empty(n, dim)
-    out[plan.perm] = back[plan.flat]
+    out = back[slot]
     assert torch.equal(out, full[ids.long()])
-    # apply: gradient rows travel to their owners aligned with recv_idx; padding rows are zero and carry id -1
+    # apply: gradient rows travel to their owners aligned with recv_idx; padding rows carry id -1 and are never read
     grads = torch.randn(n, dim, generator=gi)
-    send = torch.zeros(world * cap, dim)
-    send[plan.flat] = grads[plan.perm]
+    send = torch.from_numpy(pack_rows(grads.numpy(), slot_np, world, cap))
     recv = torch.empty_like(send)
     dist.all_to_all_single(recv, send)
-    assert bool((recv[~valid] == 0).all())
     mine = torch.zeros_like(local)
-    mine.index_add_(0, plan.recv_idx[valid].long(), recv[valid])
+    mine.index_add_(0, recv_idx[valid].long(), recv[valid])
     # the truth: scatter-add of every rank's gradient rows into the full table, restricted to my rows
     all_ids = [torch.empty(cap, dtype=torch.int32) for _ in range(world)]
     all_g = [torch.empty(cap, dim) for _ in range(world)]
@@ -156,8 +158,9 @@ def _routing_worker(rank, world, port, out_dir):
 
 
 def test_fixed_capacity_routing_plan_world2_gloo(tmp_path):
-    """`_Plan`: ids -> owners with static, equal all-to-all splits (-1 padded), rows back in the original order, gradient rows
-    to their owners; checked against the unsharded table on two gloo ranks."""
+    """The routing contract of `mamdr_route_plan` / `mamdr_route_pack_rows` (oracle/route.py restates it; the kernels are checked
+    against that restatement bit for bit in tests/test_gpu_kernels.py): ids -> owners with static, equal all-to-all splits (-1
+    padded), rows back in the original order, gradient rows to their owners; against the unsharded table on two gloo ranks."""
     port = _free_port()
     mp.spawn(_routing_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert os.path.exists(os.path.join(str(tmp_path), "routing0.pt")) and os.path.exists(os.path.join(str(tmp_path), "routing1.pt"))

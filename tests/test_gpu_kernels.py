@@ -277,3 +277,45 @@ def test_auc_kat_and_counts_bit_exact():
     np.testing.assert_array_equal(acc.cpu().numpy(), o.acc)
     c.call("mamdr_auc_result", ptr(acc), 500, ptr(out), stream())
     assert abs(out.item() - o.result()) < 2e-6
+
+
+# ---- routing of the row-sharded tables (route.cu) -----------------------------------------------------------
+@pytest.mark.parametrize("n,world,cap,n_rows", [(512, 2, 512, 718_000), (128, 8, 128, 50_000), (1024, 1, 1024, 300), (977, 3, 1000, 5000),
+                                                (0, 4, 16, 100), (2500, 64, 2500, 9000)])
+def test_route_plan_and_pack_rows_bit_exact(n, world, cap, n_rows):
+    """`mamdr_route_plan` (both id columns in one launch) and `mamdr_route_pack_rows` vs the numpy restatement of their
+    contract (oracle/route.py), and the gather that skips the -1 padding entries."""
+    from oracle.route import pack_rows, route_plan
+    rng = np.random.default_rng(n + world)
+    ids_a = (rng.zipf(1.2, n) % n_rows).astype(np.int32)      # hot ids: long runs of one owner
+    ids_b = rng.integers(0, n_rows, n).astype(np.int32)
+    c = ctx()
+    da, db = dev(ids_a) if n else torch.zeros(1, dtype=torch.int32, device="cuda"), dev(ids_b) if n else torch.zeros(1, dtype=torch.int32, device="cuda")
+    slot_a, slot_b = torch.full((cap,), -5, dtype=torch.int32, device="cuda"), torch.full((cap,), -5, dtype=torch.int32, device="cuda")
+    send_a, send_b = torch.full((world * cap,), 7, dtype=torch.int32, device="cuda"), torch.full((world * cap,), 7, dtype=torch.int32, device="cuda")
+    c.call("mamdr_route_plan", ptr(da), ptr(db), n, world, cap, ptr(slot_a), ptr(slot_b), ptr(send_a), ptr(send_b), stream())
+    for ids, slot, send in ((ids_a, slot_a, send_a), (ids_b, slot_b, send_b)):
+        want_slot, want_send = route_plan(ids, world, cap)
+        np.testing.assert_array_equal(slot.cpu().numpy()[:n], want_slot)
+        np.testing.assert_array_equal(send.cpu().numpy(), want_send)
+    if n == 0:
+        return
+    dim = 36
+    src = rng.standard_normal((n, dim + 12)).astype(np.float32)
+    dst = torch.full((world * cap, dim), -3.0, device="cuda")
+    want_slot, want_send = route_plan(ids_a, world, cap)
+    c.call("mamdr_route_pack_rows", ptr(dev(src)), dim + 12, ptr(slot_a), n, dim, 0.37, ptr(dst), stream())
+    want = pack_rows(src[:, :dim], want_slot, world, cap, 0.37)
+    got = dst.cpu().numpy()
+    np.testing.assert_array_equal(bits(got[want_slot]), bits(want[want_slot]))
+    untouched = np.ones(world * cap, bool)
+    untouched[want_slot] = False
+    assert np.all(got[untouched] == -3.0)
+    # the owners' gather over a block with -1 padding: valid rows bit-exact, padding rows untouched
+    table = rng.standard_normal((n_rows // world + 1, dim)).astype(np.float32)
+    out = torch.full((world * cap, dim), -9.0, device="cuda")
+    c.call("mamdr_gather_f32", ptr(dev(table)), table.shape[0], dim, ptr(send_a), world * cap, ptr(out), dim, stream())
+    got = out.cpu().numpy()
+    valid = want_send >= 0
+    np.testing.assert_array_equal(bits(got[valid]), bits(table[want_send[valid]]))
+    assert np.all(got[~valid] == -9.0)
