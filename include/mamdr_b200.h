@@ -88,11 +88,20 @@ int mamdr_scatter_dedup_f32(mamdr_ctx* ctx, const int32_t* ids_dev, const float*
  * row r lives on rank r % world at local index r / world; the reference keeps whole tables in one TF variable,
  * DeepCTR/deepctr.py:105-126).  mamdr_route_plan: for the n local ids of one (or two: ids_b != NULL) id columns,
  * slot[i] = owner * cap + (number of earlier local ids with the same owner), send[slot[i]] = id / world and every other
- * entry of send[world * cap] = -1: fixed-capacity blocks, so the all-to-all splits are static.  n <= cap, world <= 64.
- * mamdr_route_pack_rows: dst[slot[i], 0:dim] = src[i, 0:dim] * scale (gradient rows into the exchange buffer). */
+ * entry of the cap-entry blocks = -1: fixed-capacity blocks, so the all-to-all splits are static.  n <= cap, world <= 64.
+ * `block` is the distance between consecutive owner blocks of a send buffer: cap (separate buffers), or 2 * cap with
+ * send_b = send_a + cap: both columns share ONE exchange buffer (owner block r = [cap entries of a | cap entries of b]) and
+ * every slot indexes that shared buffer (slot_b values are offset by send_b - send_a): one all-to-all per direction for
+ * both tables.  mamdr_route_pack_rows: dst[slot[i], 0:dim] = src[i, 0:dim] * scale (gradient rows into the exchange buffer).
+ * mamdr_route_gather2: the owners' gather over a shared buffer -- out[e, :] = (entry e belongs to column b ? table_b :
+ * table_a)[recv_idx[e], :] for recv_idx[e] >= 0, plus the received ids split per table for the de-duplication
+ * (ids_a[e] = recv_idx[e] for a's entries, -1 elsewhere; ids_b likewise). */
 int mamdr_route_plan(mamdr_ctx* ctx, const int32_t* ids_a_dev, const int32_t* ids_b_dev, int32_t n, int32_t world,
-                     int32_t cap, int32_t* slot_a_dev, int32_t* slot_b_dev, int32_t* send_a_dev, int32_t* send_b_dev,
-                     mamdr_stream stream);
+                     int32_t cap, int32_t block, int32_t* slot_a_dev, int32_t* slot_b_dev, int32_t* send_a_dev,
+                     int32_t* send_b_dev, mamdr_stream stream);
+int mamdr_route_gather2(mamdr_ctx* ctx, const float* table_a_dev, const float* table_b_dev, const int32_t* recv_idx_dev,
+                        int32_t world, int32_t cap, int32_t dim, float* out_dev, int32_t* ids_a_dev, int32_t* ids_b_dev,
+                        mamdr_stream stream);
 int mamdr_route_pack_rows(mamdr_ctx* ctx, const float* src_dev, int64_t src_stride, const int32_t* slot_dev, int32_t n,
                           int32_t dim, float scale, float* dst_dev, mamdr_stream stream);
 

@@ -175,7 +175,8 @@ SIGNATURES = {
     "mamdr_sub": (C.c_int, [_P, _P, _P, _P, _I64, _P]),
     "mamdr_axpy_diff": (C.c_int, [_P, _P, _P, _P, _F, _I64, _P]),
     "mamdr_pcgrad_project": (C.c_int, [_P, _P, _P, _I64, _I32, _P]),
-    "mamdr_route_plan": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _P, _P, _P, _P, _P]),
+    "mamdr_route_plan": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P]),
+    "mamdr_route_gather2": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _P, _P, _P, _P]),
     "mamdr_route_pack_rows": (C.c_int, [_P, _P, _I64, _P, _I32, _I32, _F, _P, _P]),
     "mamdr_auc_update": (C.c_int, [_P, _P, _P, _I64, _P, _P, _I32, _P]),
     "mamdr_auc_result": (C.c_int, [_P, _P, _I32, _P, _P]),

@@ -18,7 +18,7 @@ struct PlanArgs {
     const int32_t* ids[2];
     int32_t*       slot[2];
     int32_t*       send[2];
-    int            n, world, cap;
+    int            n, world, cap, block;   // block = entries per owner block of the exchange buffer (>= cap)
 };
 
 __global__ void __launch_bounds__(kPlanThreads)
@@ -29,7 +29,7 @@ route_plan_kernel(const PlanArgs a) {
     int32_t* slot = a.slot[blockIdx.x];
     int32_t* send = a.send[blockIdx.x];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < a.world * a.cap; i += kPlanThreads) send[i] = -1;
+    for (int i = tid; i < a.world * a.cap; i += kPlanThreads) send[(i / a.cap) * a.block + (i % a.cap)] = -1;
     if (tid < a.world) base[tid] = 0;
     __syncthreads();
     for (int i0 = 0; i0 < a.n; i0 += kPlanThreads) {
@@ -46,8 +46,8 @@ route_plan_kernel(const PlanArgs a) {
         if (live) {
             int pos = base[o] + in_warp;
             for (int w = 0; w < warp; ++w) pos += warp_cnt[w][o];
-            const int s = o * a.cap + pos;
-            slot[i] = s;
+            const int s = o * a.block + pos;
+            slot[i] = s + (a.block > a.cap ? (int)blockIdx.x * a.cap : 0);   // shared buffer: slots index the buffer that starts at send_a
             send[s] = id / a.world;
         }
         __syncthreads();
@@ -72,10 +72,45 @@ route_pack_rows_kernel(const float* __restrict__ src, const int64_t src_stride, 
     }
 }
 
+// The owners' side of a FUSED exchange (both tables in one buffer: block r = [cap user entries | cap item entries]):
+// out[e, :] = (column of e ? table_b : table_a)[recv_idx[e], :] for recv_idx[e] >= 0 (padding rows untouched), and the received
+// id list split per table for the de-duplication: ids_a[e] = recv_idx[e] if e is a user entry else -1; ids_b likewise.
+__global__ void __launch_bounds__(256)
+route_gather2_kernel(const float* __restrict__ ta, const float* __restrict__ tb, const int32_t* __restrict__ recv_idx, const int n_entries,
+                     const int cap, const int dv, float* __restrict__ out, int32_t* __restrict__ ids_a, int32_t* __restrict__ ids_b) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int e = warp; e < n_entries; e += nwarps) {
+        const int32_t id = __ldg(recv_idx + e);
+        const int col = (e / cap) & 1;
+        if (lane == 0) {
+            ids_a[e] = col == 0 ? id : -1;
+            ids_b[e] = col == 1 ? id : -1;
+        }
+        if (id < 0) continue;
+        const float* src = (col ? tb : ta) + (int64_t)id * dv * 4;
+        float* dst = out + (int64_t)e * dv * 4;
+        for (int c = lane; c < dv; c += 32) st_stream_f4(dst + c * 4, ldg_f4(src + c * 4));
+    }
+}
+
 }  // namespace
 
+extern "C" int mamdr_route_gather2(mamdr_ctx* ctx, const float* table_a, const float* table_b, const int32_t* recv_idx, int32_t world,
+                                   int32_t cap, int32_t dim, float* out, int32_t* ids_a, int32_t* ids_b, mamdr_stream stream) {
+    MAMDR_REQUIRE(ctx, ctx != nullptr, MAMDR_E_INVALID, "ctx is NULL");
+    MAMDR_REQUIRE(ctx, recv_idx && out && ids_a && ids_b, MAMDR_E_INVALID, "NULL pointer");
+    MAMDR_REQUIRE(ctx, world >= 1 && cap >= 1 && dim > 0 && dim % 4 == 0, MAMDR_E_INVALID, "bad world / cap / dim");
+    MAMDR_REQUIRE(ctx, aligned16(out) && (!table_a || aligned16(table_a)) && (!table_b || aligned16(table_b)), MAMDR_E_INVALID, "misaligned table / out");
+    const int n_entries = world * 2 * cap;
+    const int want = (n_entries + 7) / 8, capg = ctx->sm_count * 8;
+    route_gather2_kernel<<<want < capg ? want : capg, 256, 0, (cudaStream_t)stream>>>(table_a, table_b, recv_idx, n_entries, cap, dim / 4, out, ids_a, ids_b);
+    MAMDR_LAUNCH_OK(ctx);
+    return MAMDR_OK;
+}
+
 extern "C" int mamdr_route_plan(mamdr_ctx* ctx, const int32_t* ids_a, const int32_t* ids_b, int32_t n, int32_t world, int32_t cap,
-                                int32_t* slot_a, int32_t* slot_b, int32_t* send_a, int32_t* send_b, mamdr_stream stream) {
+                                int32_t block, int32_t* slot_a, int32_t* slot_b, int32_t* send_a, int32_t* send_b, mamdr_stream stream) {
     MAMDR_REQUIRE(ctx, ctx != nullptr, MAMDR_E_INVALID, "ctx is NULL");
     MAMDR_REQUIRE(ctx, world >= 1 && world <= kMaxWorld, MAMDR_E_INVALID, "world must be in [1, %d]", kMaxWorld);
     MAMDR_REQUIRE(ctx, n >= 0 && cap >= 1 && n <= cap, MAMDR_E_INVALID, "need 0 <= n <= cap (every owner block can take the whole slice)");
@@ -85,7 +120,9 @@ extern "C" int mamdr_route_plan(mamdr_ctx* ctx, const int32_t* ids_a, const int3
     PlanArgs a;
     a.ids[0] = ids_a; a.slot[0] = slot_a; a.send[0] = send_a;
     a.ids[1] = ids_b; a.slot[1] = slot_b; a.send[1] = send_b;
-    a.n = n; a.world = world; a.cap = cap;
+    MAMDR_REQUIRE(ctx, block == cap || (block == 2 * cap && two && send_b == send_a + cap), MAMDR_E_INVALID,
+                  "block must be cap (separate buffers) or 2 * cap with send_b == send_a + cap (one shared buffer)");
+    a.n = n; a.world = world; a.cap = cap; a.block = block;
     route_plan_kernel<<<two ? 2 : 1, kPlanThreads, 0, (cudaStream_t)stream>>>(a);
     MAMDR_LAUNCH_OK(ctx);
     return MAMDR_OK;

@@ -30,27 +30,51 @@ from .engine import DomainData, MLPModel, _ptr
 
 
 class _Plan(object):
-    """Routing of one id column with FIXED-capacity exchange buffers: every rank sends each owner a `cap`-entry block
-    (local row index, -1 = padding), so all split sizes are static -- no host synchronisation anywhere in a step.  The plan
-    itself is ONE kernel for both id columns of a step (`mamdr_route_plan`: owner, stable position within the owner's block);
-    the buffers are persistent."""
+    """Routing of the two id columns of a step with FIXED-capacity exchange buffers: every rank sends each owner a block of
+    [cap user entries | cap item entries] (local row index, -1 = padding), so all split sizes are static -- no host
+    synchronisation anywhere in a step -- and both tables travel in ONE all-to-all per direction.  The plan itself is one
+    kernel (`mamdr_route_plan`: owner, stable position within the owner's block); the buffers are persistent."""
 
-    def __init__(self, world, cap, device):
-        self.world, self.cap, self.n = int(world), int(cap), 0
-        self.n_recv = self.world * self.cap
-        self.slot = torch.zeros(self.cap, dtype=torch.int32, device=device)        # slot of local row i in the exchange buffers
-        self.send = torch.full((self.n_recv,), -1, dtype=torch.int32, device=device)
+    def __init__(self, world, cap, dim, device):
+        self.world, self.cap, self.dim, self.n = int(world), int(cap), int(dim), 0
+        self.block = 2 * self.cap
+        self.n_recv = self.world * self.block
+        i32, f32 = dict(dtype=torch.int32, device=device), dict(dtype=torch.float32, device=device)
+        self.slot_u, self.slot_i = torch.zeros(self.cap, **i32), torch.zeros(self.cap, **i32)   # slots of local row i in the exchange buffers
+        self.send = torch.full((self.n_recv,), -1, **i32)
         self.recv_idx = torch.empty_like(self.send)                                # block r = the rows rank r asks of me
+        self.ids_u, self.ids_i = torch.empty_like(self.send), torch.empty_like(self.send)   # recv_idx split per table (-1 elsewhere)
+        self.got, self.back = torch.zeros(self.n_recv, self.dim, **f32), torch.zeros(self.n_recv, self.dim, **f32)
+        self.gsend, self.grecv = torch.zeros(self.n_recv, self.dim, **f32), torch.zeros(self.n_recv, self.dim, **f32)
+        self.out_u, self.out_i = torch.zeros(self.cap, self.dim, **f32), torch.zeros(self.cap, self.dim, **f32)
 
+    def fetch(self, ctx, users, items, ids_u, ids_i, n, stream):
+        """ids -> owners (one all-to-all), owners gather both tables (padding skipped), rows back (one all-to-all), rows picked
+        out of the received blocks by slot: returns (user rows [n, dim], item rows [n, dim]) in the original order."""
+        self.n = int(n)
+        ctx.call("mamdr_route_plan", _ptr(ids_u), _ptr(ids_i), self.n, self.world, self.cap, self.block, _ptr(self.slot_u), _ptr(self.slot_i),
+                 _ptr(self.send), C.c_void_p(self.send.data_ptr() + 4 * self.cap), stream)
+        dist.all_to_all_single(self.recv_idx, self.send)
+        ctx.call("mamdr_route_gather2", _ptr(users.table), _ptr(items.table), _ptr(self.recv_idx), self.world, self.cap, self.dim,
+                 _ptr(self.got), _ptr(self.ids_u), _ptr(self.ids_i), stream)
+        dist.all_to_all_single(self.back, self.got)
+        ctx.launches += 2
+        if self.n:
+            for slot, out in ((self.slot_u, self.out_u), (self.slot_i, self.out_i)):
+                ctx.call("mamdr_gather_f32", _ptr(self.back), self.n_recv, self.dim, _ptr(slot), self.n, _ptr(out), self.dim, stream)
+            ctx.launches += 2
+        return self.out_u, self.out_i
 
-def route(ctx, plan_a, plan_b, ids_a, ids_b, n, stream):
-    """Plans for the two id columns of a slice of n rows (one launch), then the two id all-to-alls."""
-    ctx.call("mamdr_route_plan", _ptr(ids_a), _ptr(ids_b), int(n), plan_a.world, plan_a.cap, _ptr(plan_a.slot), _ptr(plan_b.slot),
-             _ptr(plan_a.send), _ptr(plan_b.send), stream)
-    ctx.launches += 1
-    for pl in (plan_a, plan_b):
-        pl.n = int(n)
-        dist.all_to_all_single(pl.recv_idx, pl.send)
+    def send_grads(self, ctx, dX, du, scale, stream):
+        """The gradient rows of both tables (the two column blocks of dX [n, du + di], x scale) to their owners: one all-to-all.
+        The padding rows of the exchange buffer are never read (their ids are -1)."""
+        if self.n:
+            stride = dX.shape[1]
+            ctx.call("mamdr_route_pack_rows", _ptr(dX), stride, _ptr(self.slot_u), self.n, self.dim, float(scale), _ptr(self.gsend), stream)
+            ctx.call("mamdr_route_pack_rows", C.c_void_p(dX.data_ptr() + 4 * du), stride, _ptr(self.slot_i), self.n, self.dim, float(scale),
+                     _ptr(self.gsend), stream)
+            ctx.launches += 2
+        dist.all_to_all_single(self.grecv, self.gsend)
 
 
 class ShardedTable(object):
@@ -63,7 +87,7 @@ class ShardedTable(object):
         self.slot = torch.full((max(self.rows, 1),), -1, dtype=torch.int32, device=device)
         self.ws_bytes = ctx.lib.mamdr_adam_table_workspace_bytes()
         self.ws = torch.zeros(self.ws_bytes, dtype=torch.uint8, device=device)
-        max_recv = int(world) * int(cap)
+        max_recv = int(world) * 2 * int(cap)       # the shared exchange buffer of both tables (_Plan)
         if max_recv > ctx.lib.mamdr_scatter_max_n():
             raise ValueError("world x local batch = %d exceeds the de-duplication limit %d" % (max_recv, ctx.lib.mamdr_scatter_max_n()))
         self.sc_bytes = ctx.lib.mamdr_scatter_workspace_bytes(max_recv)
@@ -72,33 +96,11 @@ class ShardedTable(object):
         self.uniq_rows = torch.zeros(max_recv, self.dim, dtype=torch.float32, device=device)
         self.n_uniq = torch.zeros(4, dtype=torch.int32, device=device)
         self.max_recv = max_recv
-        f32 = dict(dtype=torch.float32, device=device)
-        self.got, self.back = torch.zeros(max_recv, self.dim, **f32), torch.zeros(max_recv, self.dim, **f32)
-        self.send, self.recv = torch.zeros(max_recv, self.dim, **f32), torch.zeros(max_recv, self.dim, **f32)
-        self.out = torch.zeros(int(cap), self.dim, **f32)
 
-    def fetch(self, plan, stream):
-        """Rows of the ids behind ``plan`` in their original order (the plan already exchanged the ids): owners gather (the
-        -1 padding entries are skipped), equal-split all-to-all back, rows picked out of the received blocks by slot."""
-        if self.rows:
-            self.ctx.call("mamdr_gather_f32", _ptr(self.table), self.rows, self.dim, _ptr(plan.recv_idx), plan.n_recv,
-                          _ptr(self.got), self.dim, stream)
-            self.ctx.launches += 1
-        dist.all_to_all_single(self.back, self.got)
-        if plan.n:
-            self.ctx.call("mamdr_gather_f32", _ptr(self.back), plan.n_recv, self.dim, _ptr(plan.slot), plan.n, _ptr(self.out), self.dim, stream)
-            self.ctx.launches += 1
-        return self.out
-
-    def apply(self, plan, grad_ptr, grad_stride, scale, opt_state, lr, beta1, beta2, eps, loss_slot, stream):
-        """Send the gradient rows (x scale) to their owners, de-duplicate, fused l2 + Adam over the local shard.  The padding
-        rows of the exchange buffer are never read (their ids are -1)."""
-        if plan.n:
-            self.ctx.call("mamdr_route_pack_rows", grad_ptr, int(grad_stride), _ptr(plan.slot), plan.n, self.dim, float(scale),
-                          _ptr(self.send), stream)
-            self.ctx.launches += 1
-        dist.all_to_all_single(self.recv, self.send)
-        self.ctx.call("mamdr_scatter_dedup_f32", _ptr(plan.recv_idx), _ptr(self.recv), self.dim, plan.n_recv, self.dim,
+    def apply(self, plan, ids, opt_state, lr, beta1, beta2, eps, loss_slot, stream):
+        """De-duplicate the received gradient rows of this table (`ids`: the received id list with -1 for padding and for the
+        other table's entries) and run the fused l2 + Adam sweep over the local shard."""
+        self.ctx.call("mamdr_scatter_dedup_f32", _ptr(ids), _ptr(plan.grecv), self.dim, plan.n_recv, self.dim,
                       _ptr(self.uniq_ids), _ptr(self.uniq_rows), _ptr(self.n_uniq), _ptr(self.sc_ws), self.sc_ws.numel(), stream)
         self.ctx.launches += 2
         if self.rows:
@@ -168,7 +170,9 @@ class ShardedJointTrainer(_Steps):
         self.users = ShardedTable(ctx, user_init, self.rank, self.world, self.device, l2_emb, bl)
         self.items = ShardedTable(ctx, item_init, self.rank, self.world, self.device, l2_emb, bl)
         self.arange = torch.arange(bl, dtype=torch.int32, device=self.device)
-        self.plan_u, self.plan_i = _Plan(self.world, bl, self.device), _Plan(self.world, bl, self.device)
+        if emb_dim[0] != emb_dim[1]:
+            raise NotImplementedError("the shared exchange buffer needs user_dim == item_dim (every shipped config: 128 / 128)")
+        self.plan = _Plan(self.world, bl, emb_dim[0], self.device)
         self.dX = torch.zeros(bl, emb_dim[0] + emb_dim[1], dtype=torch.float32, device=self.device)
         self.loss_local = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.loss_tab = torch.zeros(1, dtype=torch.float32, device=self.device)
@@ -194,9 +198,8 @@ class ShardedJointTrainer(_Steps):
         n = int(uid.numel())
         start, bl = self._slice(n)
         u, p, y = uid[start:start + bl], pid[start:start + bl], label[start:start + bl]    # contiguous views of the columns
-        plan_u, plan_i = self.plan_u, self.plan_i
-        route(m.ctx, plan_u, plan_i, u, p, bl, st)
-        rows_u, rows_i = self.users.fetch(plan_u, st), self.items.fetch(plan_i, st)
+        plan = self.plan
+        rows_u, rows_i = plan.fetch(m.ctx, self.users, self.items, u, p, bl, st)
         w = float(bl) / float(n)                         # this rank's share of the batch mean
         self.loss_local.zero_()
         self.loss_tab.zero_()
@@ -216,14 +219,14 @@ class ShardedJointTrainer(_Steps):
             m.grads.zero_()
         # tables first (they read the beta powers), then the dense arena (its apply advances them); the gradient rows are
         # the two column blocks of dX [bl, du + di], weighted by this rank's share while they are packed
-        du, dxs = self.users.dim, self.dX.shape[1]
-        self.users.apply(plan_u, _ptr(self.dX), dxs, w, m.opt_state, m.lr, m.beta1, m.beta2, m.eps, self.loss_tab, st)
-        self.items.apply(plan_i, C.c_void_p(self.dX.data_ptr() + 4 * du), dxs, w, m.opt_state, m.lr, m.beta1, m.beta2, m.eps, self.loss_tab, st)
+        plan.send_grads(m.ctx, self.dX, self.users.dim, w, st)
+        self.users.apply(plan, plan.ids_u, m.opt_state, m.lr, m.beta1, m.beta2, m.eps, self.loss_tab, st)
+        self.items.apply(plan, plan.ids_i, m.opt_state, m.lr, m.beta1, m.beta2, m.eps, self.loss_tab, st)
         dist.all_reduce(m.grads)
         m.ctx.call("mamdr_adam_step", _ptr(m.params), _ptr(m.m), _ptr(m.v), _ptr(m.grads), m.params.numel(), _ptr(m.opt_state), m.lr,
                    m.beta1, m.beta2, m.eps, st)
         m.ctx.launches += 1
-        self.comm_bytes += 4 * m.grads.numel() + 4 * (plan_u.n_recv + plan_i.n_recv) * (1 + 2 * self.users.dim)   # ids + rows out + gradient rows back, fixed-capacity blocks
+        self.comm_bytes += 4 * m.grads.numel() + 4 * plan.n_recv * (1 + 2 * self.users.dim)   # ids + rows out + gradient rows back, fixed-capacity blocks
         both = torch.cat([self.loss_local, self.loss_tab])
         dist.all_reduce(both)
         return both   # [mean BCE + l2 |E_d|^2, l2 (|E_u|^2 + |E_i|^2)]; their sum is the Keras loss
@@ -273,7 +276,9 @@ class ShardedMTLTrainer(_Steps):
         self.users = ShardedTable(m.ctx, user_init, self.rank, self.world, self.device, l2_emb, bl)
         self.items = ShardedTable(m.ctx, item_init, self.rank, self.world, self.device, l2_emb, bl)
         self.arange = torch.arange(bl, dtype=torch.int32, device=self.device)
-        self.plan_u, self.plan_i = _Plan(self.world, bl, self.device), _Plan(self.world, bl, self.device)
+        if emb_dim[0] != emb_dim[1]:
+            raise NotImplementedError("the shared exchange buffer needs user_dim == item_dim (every shipped config: 128 / 128)")
+        self.plan = _Plan(self.world, bl, emb_dim[0], self.device)
         self.dX = torch.zeros(bl, emb_dim[0] + emb_dim[1], dtype=torch.float32, device=self.device)
         self.loss_local = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.loss_tab = torch.zeros(1, dtype=torch.float32, device=self.device)
@@ -291,9 +296,8 @@ class ShardedMTLTrainer(_Steps):
         n = int(uid.numel())
         start, bl = self._slice(n)
         u, p, y = uid[start:start + bl], pid[start:start + bl], label[start:start + bl]    # contiguous views of the columns
-        plan_u, plan_i = self.plan_u, self.plan_i
-        route(m.ctx, plan_u, plan_i, u, p, bl, st)
-        rows_u, rows_i = self.users.fetch(plan_u, st), self.items.fetch(plan_i, st)
+        plan = self.plan
+        rows_u, rows_i = plan.fetch(m.ctx, self.users, self.items, u, p, bl, st)
         w = float(bl) / float(n)
         self.loss_local.zero_()
         self.loss_tab.zero_()
@@ -316,14 +320,14 @@ class ShardedMTLTrainer(_Steps):
             for g in spans:
                 g.zero_()
         # tables first (they read the beta powers), then sub-model t's spans of the dense arena (that apply advances them)
-        du, dxs = self.users.dim, self.dX.shape[1]
-        self.users.apply(plan_u, _ptr(self.dX), dxs, w, m.opt_state, m.lr, m.beta1, m.beta2, m.eps, self.loss_tab, st)
-        self.items.apply(plan_i, C.c_void_p(self.dX.data_ptr() + 4 * du), dxs, w, m.opt_state, m.lr, m.beta1, m.beta2, m.eps, self.loss_tab, st)
+        plan.send_grads(m.ctx, self.dX, self.users.dim, w, st)
+        self.users.apply(plan, plan.ids_u, m.opt_state, m.lr, m.beta1, m.beta2, m.eps, self.loss_tab, st)
+        self.items.apply(plan, plan.ids_i, m.opt_state, m.lr, m.beta1, m.beta2, m.eps, self.loss_tab, st)
         for g in spans:
             dist.all_reduce(g)
         m.ctx.call("mamdr_adam_ranges_step", _ptr(m.params), _ptr(m.m), _ptr(m.v), _ptr(m.grads), begin, length, n_spans,
                    _ptr(m.opt_state), m.lr, m.beta1, m.beta2, m.eps, st)
-        self.comm_bytes += 4 * sum(g.numel() for g in spans) + 4 * (plan_u.n_recv + plan_i.n_recv) * (1 + 2 * self.users.dim)
+        self.comm_bytes += 4 * sum(g.numel() for g in spans) + 4 * plan.n_recv * (1 + 2 * self.users.dim)
         both = torch.cat([self.loss_local, self.loss_tab])
         dist.all_reduce(both)
         return both

@@ -25,6 +25,19 @@ def route_plan(ids, world, cap):
     return slot, send
 
 
+def route_plan_shared(ids_a, ids_b, world, cap):
+    """Both id columns in ONE exchange buffer (block = 2 * cap): owner block r = [cap entries of a | cap entries of b].
+    -> (slot_a, slot_b, send [world * 2 * cap]); the slots index the shared buffer."""
+    sa, xa = route_plan(ids_a, world, cap)
+    sb, xb = route_plan(ids_b, world, cap)
+    send = np.full(world * 2 * cap, -1, dtype=np.int32)
+    send.reshape(world, 2, cap)[:, 0, :] = xa.reshape(world, cap)
+    send.reshape(world, 2, cap)[:, 1, :] = xb.reshape(world, cap)
+    slot_a = (sa // cap) * 2 * cap + sa % cap
+    slot_b = (sb // cap) * 2 * cap + cap + sb % cap
+    return slot_a.astype(np.int32), slot_b.astype(np.int32), send
+
+
 def pack_rows(src, slot, world, cap, scale=1.0):
     """dst[slot[i]] = src[i] * scale; the other rows of dst [world * cap, dim] are padding (zero here)."""
     src = np.asarray(src, dtype=np.float32)

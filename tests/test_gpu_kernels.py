@@ -293,7 +293,7 @@ def test_route_plan_and_pack_rows_bit_exact(n, world, cap, n_rows):
     da, db = dev(ids_a) if n else torch.zeros(1, dtype=torch.int32, device="cuda"), dev(ids_b) if n else torch.zeros(1, dtype=torch.int32, device="cuda")
     slot_a, slot_b = torch.full((cap,), -5, dtype=torch.int32, device="cuda"), torch.full((cap,), -5, dtype=torch.int32, device="cuda")
     send_a, send_b = torch.full((world * cap,), 7, dtype=torch.int32, device="cuda"), torch.full((world * cap,), 7, dtype=torch.int32, device="cuda")
-    c.call("mamdr_route_plan", ptr(da), ptr(db), n, world, cap, ptr(slot_a), ptr(slot_b), ptr(send_a), ptr(send_b), stream())
+    c.call("mamdr_route_plan", ptr(da), ptr(db), n, world, cap, cap, ptr(slot_a), ptr(slot_b), ptr(send_a), ptr(send_b), stream())
     for ids, slot, send in ((ids_a, slot_a, send_a), (ids_b, slot_b, send_b)):
         want_slot, want_send = route_plan(ids, world, cap)
         np.testing.assert_array_equal(slot.cpu().numpy()[:n], want_slot)
@@ -319,3 +319,40 @@ def test_route_plan_and_pack_rows_bit_exact(n, world, cap, n_rows):
     valid = want_send >= 0
     np.testing.assert_array_equal(bits(got[valid]), bits(table[want_send[valid]]))
     assert np.all(got[~valid] == -9.0)
+
+
+@pytest.mark.parametrize("n,world,cap", [(512, 2, 512), (100, 8, 128), (977, 3, 1000), (0, 4, 16)])
+def test_route_shared_buffer_plan_and_two_table_gather_bit_exact(n, world, cap):
+    """Both id columns in ONE exchange buffer (block = 2 * cap, `mamdr_route_plan`) and the owners' two-table gather with the
+    per-table split of the received ids (`mamdr_route_gather2`) vs oracle/route.py."""
+    from oracle.route import route_plan_shared
+    rng = np.random.default_rng(n * 7 + world)
+    rows_a, rows_b, dim = 4001, 977, 128
+    ids_a = (rng.zipf(1.3, n) % (rows_a * world)).astype(np.int32)
+    ids_b = rng.integers(0, rows_b * world, n).astype(np.int32)
+    c = ctx()
+    z = torch.zeros(1, dtype=torch.int32, device="cuda")
+    da, db = (dev(ids_a), dev(ids_b)) if n else (z, z)
+    slot_a, slot_b = torch.zeros(cap, dtype=torch.int32, device="cuda"), torch.zeros(cap, dtype=torch.int32, device="cuda")
+    send = torch.full((world * 2 * cap,), 7, dtype=torch.int32, device="cuda")
+    c.call("mamdr_route_plan", ptr(da), ptr(db), n, world, cap, 2 * cap, ptr(slot_a), ptr(slot_b), ptr(send), C.c_void_p(send.data_ptr() + 4 * cap), stream())
+    wa, wb, wsend = route_plan_shared(ids_a, ids_b, world, cap)
+    np.testing.assert_array_equal(send.cpu().numpy(), wsend)
+    np.testing.assert_array_equal(slot_a.cpu().numpy()[:n], wa)
+    np.testing.assert_array_equal(slot_b.cpu().numpy()[:n], wb)
+    # the owner's side: treat `send` as what arrived
+    ta, tb = rng.standard_normal((rows_a, dim)).astype(np.float32), rng.standard_normal((rows_b, dim)).astype(np.float32)
+    out = torch.full((world * 2 * cap, dim), -9.0, device="cuda")
+    ia, ib = torch.zeros_like(send), torch.zeros_like(send)
+    c.call("mamdr_route_gather2", ptr(dev(ta)), ptr(dev(tb)), ptr(send), world, cap, dim, ptr(out), ptr(ia), ptr(ib), stream())
+    got = out.cpu().numpy().reshape(world, 2, cap, dim)
+    w3 = wsend.reshape(world, 2, cap)
+    for col, table in ((0, ta), (1, tb)):
+        valid = w3[:, col, :] >= 0
+        np.testing.assert_array_equal(bits(got[:, col][valid]), bits(table[w3[:, col, :][valid]]))
+        assert np.all(got[:, col][~valid] == -9.0)
+    want_a, want_b = w3.copy(), w3.copy()
+    want_a[:, 1, :] = -1
+    want_b[:, 0, :] = -1
+    np.testing.assert_array_equal(ia.cpu().numpy(), want_a.reshape(-1))
+    np.testing.assert_array_equal(ib.cpu().numpy(), want_b.reshape(-1))
