@@ -24,7 +24,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD_CONFIG = {"Taobao-10": "config/Taobao-10/deepctr_DN+DR.json", "Taobao-20": "config/Taobao_20/deepctr_DN+DR.json",
+WORKLOAD_CONFIG = {"Taobao-10": "config/Taobao-10/deepctr_DN+DR.json", "Taobao-10-batch": "config/Taobao-10/deepctr_DN+DR.json", "Taobao-20": "config/Taobao_20/deepctr_DN+DR.json",
                    "Taobao-20-star": "config/Taobao_20/star_DN+DR.json",
                    "Taobao-30": "config/Taobao_30/deepctr_DN+DR.json", "Amazon-6": "config/Amazon_6/deepctr.json",
                    "Amazon-13-sharded": "config/Amazon_6/deepctr.json", "Amazon-13-mmoe": "config/Amazon_13/mmoe_DN.json",
@@ -38,6 +38,8 @@ def load_config(workload):
     with open(os.path.join(ROOT, WORKLOAD_CONFIG[workload])) as f:
         c = json.load(f)
     c.setdefault("b200", {})["verbose"] = False
+    if workload.endswith("-batch"):     # the `batch` variant of the wrapper (mamdr.py:100-108,182-196): (query, support) PAIRS are the shards
+        c["model"]["name"] = "mlp_meta_mamdr_batch"
     c["train"]["result_save_path"] = "/tmp/mamdr_bench/result"
     c["train"]["checkpoint_path"] = "/tmp/mamdr_bench/checkpoint"
     return c
@@ -484,6 +486,18 @@ def run_sharded(args):
     torch.cuda.synchronize()
     ms = torch.tensor([a.elapsed_time(b) / args.steps], dtype=torch.float64, device="cuda")
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    # where a mini-batch goes (rank 0, one extra untimed step): CUDA-event marks between the phases of train_on_batch, and the
+    # host time to ENQUEUE a step (no synchronisation inside): host-bound if it is not below the device time
+    t.phase_events = []
+    t0 = time.perf_counter()
+    step()
+    host_us = 1e6 * (time.perf_counter() - t0) / mb
+    torch.cuda.synchronize()
+    marks, t.phase_events = t.phase_events, None
+    phases = {}
+    for (n0, e0), (n1, e1) in zip(marks[:-1], marks[1:]):
+        if n1 != "begin":
+            phases[n1] = phases.get(n1, 0.0) + 1e3 * e0.elapsed_time(e1) / mb
     if rank == 0:
         msv = float(ms.item())
         alg = 24.0 * (n_uid + n_pid) * 128
@@ -493,7 +507,7 @@ def run_sharded(args):
                           "config": {"workload": "%s train steps, trainable tables row-sharded over %d rank(s), NCCL all-to-all, %d mini-batches of 1024 per step%s" % (tower, world, mb, "")},
                           "roofline": {"bound": "hbm", "achieved": alg * mb / (msv * 1e-3) / 1e9, "unit": "GB/s",
                                        "note": "aggregate table-sweep bytes (24 B per table element per mini-batch) over all ranks / step time"},
-                          "us_per_minibatch": 1e3 * msv / mb}))
+                          "us_per_minibatch": 1e3 * msv / mb, "phase_us_per_minibatch": phases, "host_enqueue_us_per_minibatch": host_us}))
     dist.destroy_process_group()
 
 

@@ -146,6 +146,14 @@ class _Steps(object):
     def step(self, uid, pid, label, domain):
         return self.train_on_batch(uid, pid, label, domain)
 
+    phase_events = None   # bench / diagnostics: set to a list to get (phase name, CUDA event) marks of every step
+
+    def _mark(self, name):
+        if self.phase_events is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(torch.cuda.current_stream(self.device))
+            self.phase_events.append((name, e))
+
 
 class ShardedJointTrainer(_Steps):
     """Joint `mlp` training (``DeepCTR.train``) with row-sharded trainable tables; one instance per rank."""
@@ -199,7 +207,9 @@ class ShardedJointTrainer(_Steps):
         start, bl = self._slice(n)
         u, p, y = uid[start:start + bl], pid[start:start + bl], label[start:start + bl]    # contiguous views of the columns
         plan = self.plan
+        self._mark("begin")
         rows_u, rows_i = plan.fetch(m.ctx, self.users, self.items, u, p, bl, st)
+        self._mark("fetch")
         w = float(bl) / float(n)                         # this rank's share of the batch mean
         self.loss_local.zero_()
         self.loss_tab.zero_()
@@ -219,9 +229,12 @@ class ShardedJointTrainer(_Steps):
             m.grads.zero_()
         # tables first (they read the beta powers), then the dense arena (its apply advances them); the gradient rows are
         # the two column blocks of dX [bl, du + di], weighted by this rank's share while they are packed
+        self._mark("tower")
         plan.send_grads(m.ctx, self.dX, self.users.dim, w, st)
+        self._mark("send_grads")
         self.users.apply(plan, plan.ids_u, m.opt_state, m.lr, m.beta1, m.beta2, m.eps, self.loss_tab, st)
         self.items.apply(plan, plan.ids_i, m.opt_state, m.lr, m.beta1, m.beta2, m.eps, self.loss_tab, st)
+        self._mark("tables")
         dist.all_reduce(m.grads)
         m.ctx.call("mamdr_adam_step", _ptr(m.params), _ptr(m.m), _ptr(m.v), _ptr(m.grads), m.params.numel(), _ptr(m.opt_state), m.lr,
                    m.beta1, m.beta2, m.eps, st)
@@ -229,6 +242,7 @@ class ShardedJointTrainer(_Steps):
         self.comm_bytes += 4 * m.grads.numel() + 4 * plan.n_recv * (1 + 2 * self.users.dim)   # ids + rows out + gradient rows back, fixed-capacity blocks
         both = torch.cat([self.loss_local, self.loss_tab])
         dist.all_reduce(both)
+        self._mark("dense")
         return both   # [mean BCE + l2 |E_d|^2, l2 (|E_u|^2 + |E_i|^2)]; their sum is the Keras loss
 
     def train_pass(self, host_split, domain, order, dev_cols=None):
@@ -297,7 +311,9 @@ class ShardedMTLTrainer(_Steps):
         start, bl = self._slice(n)
         u, p, y = uid[start:start + bl], pid[start:start + bl], label[start:start + bl]    # contiguous views of the columns
         plan = self.plan
+        self._mark("begin")
         rows_u, rows_i = plan.fetch(m.ctx, self.users, self.items, u, p, bl, st)
+        self._mark("fetch")
         w = float(bl) / float(n)
         self.loss_local.zero_()
         self.loss_tab.zero_()
@@ -320,9 +336,12 @@ class ShardedMTLTrainer(_Steps):
             for g in spans:
                 g.zero_()
         # tables first (they read the beta powers), then sub-model t's spans of the dense arena (that apply advances them)
+        self._mark("tower")
         plan.send_grads(m.ctx, self.dX, self.users.dim, w, st)
+        self._mark("send_grads")
         self.users.apply(plan, plan.ids_u, m.opt_state, m.lr, m.beta1, m.beta2, m.eps, self.loss_tab, st)
         self.items.apply(plan, plan.ids_i, m.opt_state, m.lr, m.beta1, m.beta2, m.eps, self.loss_tab, st)
+        self._mark("tables")
         for g in spans:
             dist.all_reduce(g)
         m.ctx.call("mamdr_adam_ranges_step", _ptr(m.params), _ptr(m.m), _ptr(m.v), _ptr(m.grads), begin, length, n_spans,
@@ -330,6 +349,7 @@ class ShardedMTLTrainer(_Steps):
         self.comm_bytes += 4 * sum(g.numel() for g in spans) + 4 * plan.n_recv * (1 + 2 * self.users.dim)
         both = torch.cat([self.loss_local, self.loss_tab])
         dist.all_reduce(both)
+        self._mark("dense")
         return both
 
     train_pass = ShardedJointTrainer.train_pass
