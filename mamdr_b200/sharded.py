@@ -228,14 +228,16 @@ class ShardedJointTrainer(_Steps):
         else:
             m.grads.zero_()
         # tables first (they read the beta powers), then the dense arena (its apply advances them); the gradient rows are
-        # the two column blocks of dX [bl, du + di], weighted by this rank's share while they are packed
+        # the two column blocks of dX [bl, du + di], weighted by this rank's share while they are packed.  The all-reduce of
+        # the dense gradients is issued first and runs on NCCL's stream under the table sweeps
         self._mark("tower")
+        dense_work = dist.all_reduce(m.grads, async_op=True)
         plan.send_grads(m.ctx, self.dX, self.users.dim, w, st)
         self._mark("send_grads")
         self.users.apply(plan, plan.ids_u, m.opt_state, m.lr, m.beta1, m.beta2, m.eps, self.loss_tab, st)
         self.items.apply(plan, plan.ids_i, m.opt_state, m.lr, m.beta1, m.beta2, m.eps, self.loss_tab, st)
         self._mark("tables")
-        dist.all_reduce(m.grads)
+        dense_work.wait()
         m.ctx.call("mamdr_adam_step", _ptr(m.params), _ptr(m.m), _ptr(m.v), _ptr(m.grads), m.params.numel(), _ptr(m.opt_state), m.lr,
                    m.beta1, m.beta2, m.eps, st)
         m.ctx.launches += 1
@@ -335,15 +337,17 @@ class ShardedMTLTrainer(_Steps):
         else:
             for g in spans:
                 g.zero_()
-        # tables first (they read the beta powers), then sub-model t's spans of the dense arena (that apply advances them)
+        # tables first (they read the beta powers), then sub-model t's spans of the dense arena (that apply advances them).  The
+        # all-reduces of the spans are issued first and run on NCCL's stream under the table sweeps
         self._mark("tower")
+        dense_work = [dist.all_reduce(g, async_op=True) for g in spans]
         plan.send_grads(m.ctx, self.dX, self.users.dim, w, st)
         self._mark("send_grads")
         self.users.apply(plan, plan.ids_u, m.opt_state, m.lr, m.beta1, m.beta2, m.eps, self.loss_tab, st)
         self.items.apply(plan, plan.ids_i, m.opt_state, m.lr, m.beta1, m.beta2, m.eps, self.loss_tab, st)
         self._mark("tables")
-        for g in spans:
-            dist.all_reduce(g)
+        for wk in dense_work:
+            wk.wait()
         m.ctx.call("mamdr_adam_ranges_step", _ptr(m.params), _ptr(m.m), _ptr(m.v), _ptr(m.grads), begin, length, n_spans,
                    _ptr(m.opt_state), m.lr, m.beta1, m.beta2, m.eps, st)
         self.comm_bytes += 4 * sum(g.numel() for g in spans) + 4 * plan.n_recv * (1 + 2 * self.users.dim)
