@@ -229,10 +229,10 @@ class ShardedJointTrainer(_Steps):
             m.grads.zero_()
         # tables first (they read the beta powers), then the dense arena (its apply advances them); the gradient rows are
         # the two column blocks of dX [bl, du + di], weighted by this rank's share while they are packed.  The all-reduce of
-        # the dense gradients is issued first and runs on NCCL's stream under the table sweeps
+        # the dense gradients runs on NCCL's stream under the table sweeps
         self._mark("tower")
-        dense_work = dist.all_reduce(m.grads, async_op=True)
         plan.send_grads(m.ctx, self.dX, self.users.dim, w, st)
+        dense_work = dist.all_reduce(m.grads, async_op=True)     # queued on NCCL's stream BEHIND the gradient-row exchange
         self._mark("send_grads")
         self.users.apply(plan, plan.ids_u, m.opt_state, m.lr, m.beta1, m.beta2, m.eps, self.loss_tab, st)
         self.items.apply(plan, plan.ids_i, m.opt_state, m.lr, m.beta1, m.beta2, m.eps, self.loss_tab, st)
@@ -338,10 +338,10 @@ class ShardedMTLTrainer(_Steps):
             for g in spans:
                 g.zero_()
         # tables first (they read the beta powers), then sub-model t's spans of the dense arena (that apply advances them).  The
-        # all-reduces of the spans are issued first and run on NCCL's stream under the table sweeps
+        # all-reduces of the spans run on NCCL's stream under the table sweeps
         self._mark("tower")
-        dense_work = [dist.all_reduce(g, async_op=True) for g in spans]
         plan.send_grads(m.ctx, self.dX, self.users.dim, w, st)
+        dense_work = [dist.all_reduce(g, async_op=True) for g in spans]     # queued on NCCL's stream BEHIND the gradient-row exchange
         self._mark("send_grads")
         self.users.apply(plan, plan.ids_u, m.opt_state, m.lr, m.beta1, m.beta2, m.eps, self.loss_tab, st)
         self.items.apply(plan, plan.ids_i, m.opt_state, m.lr, m.beta1, m.beta2, m.eps, self.loss_tab, st)
