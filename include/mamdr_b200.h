@@ -402,6 +402,12 @@ int mamdr_adam_table_step(mamdr_ctx* ctx, float* table_dev, float* m_dev, float*
 
 /* sum(x^2) in double with a fixed reduction order (the l2 penalty of a trainable table in `evaluate`); ws as for
  * mamdr_adam_table_step; *out_dev is a device double */
+/* The same sweep for the finetune stage's plain SGD (GradientDescentOptimizer, specific_base_model.py:120,
+ * base_model.py:69) on a trainable table: table[r,:] -= (2*l2*table[r,:] (+ uniq_rows[k,:] if r == uniq_ids[k])) * lr on
+ * every row; *loss_dev += l2*sum(E^2) of the pre-update values.  8 B per element. */
+int mamdr_sgd_table_step(mamdr_ctx* ctx, float* table_dev, int64_t rows, int32_t dim, const int32_t* uniq_ids_dev,
+                         const float* uniq_rows_dev, const int32_t* n_uniq_dev, int64_t max_uniq, int32_t* slot_map_dev,
+                         float l2, float lr, float* loss_dev, void* ws_dev, size_t ws_bytes, mamdr_stream stream);
 int mamdr_sum_squares_f64(mamdr_ctx* ctx, const float* x_dev, int64_t n, double* out_dev, void* ws_dev,
                           size_t ws_bytes, mamdr_stream stream);
 

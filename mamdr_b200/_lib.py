@@ -163,6 +163,7 @@ SIGNATURES = {
     "mamdr_adam_table_workspace_bytes": (_SZ, []),
     "mamdr_adam_table_step": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _P, _P, _P, _I64, _P, _F, _P, _F, _F, _F, _F, _P, _P,
                                         _SZ, _P]),
+    "mamdr_sgd_table_step": (C.c_int, [_P, _P, _I64, _I32, _P, _P, _P, _I64, _P, _F, _F, _P, _P, _SZ, _P]),
     "mamdr_sum_squares_f64": (C.c_int, [_P, _P, _I64, _P, _P, _SZ, _P]),
     "mamdr_adam_step": (C.c_int, [_P, _P, _P, _P, _P, _I64, _P, _F, _F, _F, _F, _P]),
     "mamdr_sgd_step": (C.c_int, [_P, _P, _P, _I64, _P, _F, _P]),

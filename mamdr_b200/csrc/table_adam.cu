@@ -47,8 +47,11 @@ struct TableArgs {
     float* loss;              // optional: += l2 * sum(E^2)
 };
 
+// SGD = true: the finetune stage's GradientDescentOptimizer (specific_base_model.py:120, base_model.py:69) on a trainable table:
+// p -= (2*l2*p + sparse) * lr on every row; m / v are not touched (8 B per element instead of 24).
+template <bool SGD>
 __global__ void __launch_bounds__(kThreads) adam_table_kernel(TableArgs a) {
-    const float b1p = a.st->b1pow, b2p = a.st->b2pow;
+    const float b1p = SGD ? 0.f : a.st->b1pow, b2p = SGD ? 0.f : a.st->b2pow;
     const float alpha = __fdiv_rn(__fmul_rn(a.lr, __fsqrt_rn(__fsub_rn(1.0f, b2p))), __fsub_rn(1.0f, b1p));
     const float omb1 = __fsub_rn(1.0f, a.beta1), omb2 = __fsub_rn(1.0f, a.beta2);
     const float two_l2 = 2.0f * a.l2;
@@ -64,8 +67,12 @@ __global__ void __launch_bounds__(kThreads) adam_table_kernel(TableArgs a) {
         for (int c = lane * 4; c < a.dim; c += 128) {
             const long long o0 = row0 * a.dim + c, o1 = row1 * a.dim + c;
             float4 P[2], M[2], V[2], S[2];
-            P[0] = ld_stream_f4(a.p + o0); M[0] = ld_stream_f4(a.m + o0); V[0] = ld_stream_f4(a.v + o0);
-            if (has1) { P[1] = ld_stream_f4(a.p + o1); M[1] = ld_stream_f4(a.m + o1); V[1] = ld_stream_f4(a.v + o1); }
+            P[0] = ld_stream_f4(a.p + o0);
+            if (!SGD) { M[0] = ld_stream_f4(a.m + o0); V[0] = ld_stream_f4(a.v + o0); }
+            if (has1) {
+                P[1] = ld_stream_f4(a.p + o1);
+                if (!SGD) { M[1] = ld_stream_f4(a.m + o1); V[1] = ld_stream_f4(a.v + o1); }
+            }
             S[0] = slot0 >= 0 ? ldg_f4(a.uniq_rows + (long long)slot0 * a.dim + c) : make_float4(0.f, 0.f, 0.f, 0.f);
             S[1] = slot1 >= 0 ? ldg_f4(a.uniq_rows + (long long)slot1 * a.dim + c) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -77,14 +84,20 @@ __global__ void __launch_bounds__(kThreads) adam_table_kernel(TableArgs a) {
                     G.x = __fadd_rn(G.x, S[r].x); G.y = __fadd_rn(G.y, S[r].y); G.z = __fadd_rn(G.z, S[r].z); G.w = __fadd_rn(G.w, S[r].w);
                 }
                 sq += (double)P[r].x * P[r].x + (double)P[r].y * P[r].y + (double)P[r].z * P[r].z + (double)P[r].w * P[r].w;
-                adam1(P[r].x, M[r].x, V[r].x, G.x, alpha, omb1, omb2, a.eps);
-                adam1(P[r].y, M[r].y, V[r].y, G.y, alpha, omb1, omb2, a.eps);
-                adam1(P[r].z, M[r].z, V[r].z, G.z, alpha, omb1, omb2, a.eps);
-                adam1(P[r].w, M[r].w, V[r].w, G.w, alpha, omb1, omb2, a.eps);
                 const long long o = r == 0 ? o0 : o1;
-                st_stream_f4(a.p + o, P[r]);
-                st_stream_f4(a.m + o, M[r]);
-                st_stream_f4(a.v + o, V[r]);
+                if (SGD) {
+                    P[r].x = __fsub_rn(P[r].x, __fmul_rn(G.x, a.lr)); P[r].y = __fsub_rn(P[r].y, __fmul_rn(G.y, a.lr));
+                    P[r].z = __fsub_rn(P[r].z, __fmul_rn(G.z, a.lr)); P[r].w = __fsub_rn(P[r].w, __fmul_rn(G.w, a.lr));
+                    st_stream_f4(a.p + o, P[r]);
+                } else {
+                    adam1(P[r].x, M[r].x, V[r].x, G.x, alpha, omb1, omb2, a.eps);
+                    adam1(P[r].y, M[r].y, V[r].y, G.y, alpha, omb1, omb2, a.eps);
+                    adam1(P[r].z, M[r].z, V[r].z, G.z, alpha, omb1, omb2, a.eps);
+                    adam1(P[r].w, M[r].w, V[r].w, G.w, alpha, omb1, omb2, a.eps);
+                    st_stream_f4(a.p + o, P[r]);
+                    st_stream_f4(a.m + o, M[r]);
+                    st_stream_f4(a.v + o, V[r]);
+                }
             }
         }
         if (lane == 0) {   // leave the map clean for the next mini-batch
@@ -168,13 +181,13 @@ extern "C" int mamdr_sum_squares_f64(mamdr_ctx* ctx, const float* x_dev, int64_t
 
 extern "C" size_t mamdr_adam_table_workspace_bytes(void) { return (size_t)(kMaxBlocks + 2) * sizeof(double) + 64; }
 
-extern "C" int mamdr_adam_table_step(mamdr_ctx* ctx, float* table_dev, float* m_dev, float* v_dev, int64_t rows, int32_t dim,
-                                     const int32_t* uniq_ids_dev, const float* uniq_rows_dev, const int32_t* n_uniq_dev,
-                                     int64_t max_uniq, int32_t* slot_map_dev, float l2, const void* opt_state_dev, float lr,
-                                     float beta1, float beta2, float eps, float* loss_dev, void* ws_dev, size_t ws_bytes,
-                                     mamdr_stream stream) {
+static int table_step(mamdr_ctx* ctx, bool sgd, float* table_dev, float* m_dev, float* v_dev, int64_t rows, int32_t dim,
+                      const int32_t* uniq_ids_dev, const float* uniq_rows_dev, const int32_t* n_uniq_dev,
+                      int64_t max_uniq, int32_t* slot_map_dev, float l2, const void* opt_state_dev, float lr,
+                      float beta1, float beta2, float eps, float* loss_dev, void* ws_dev, size_t ws_bytes,
+                      mamdr_stream stream) {
     MAMDR_REQUIRE(ctx, ctx != nullptr, MAMDR_E_INVALID, "ctx is NULL");
-    MAMDR_REQUIRE(ctx, table_dev && m_dev && v_dev && slot_map_dev && opt_state_dev && ws_dev, MAMDR_E_INVALID, "NULL pointer");
+    MAMDR_REQUIRE(ctx, table_dev && slot_map_dev && ws_dev && (sgd || (m_dev && v_dev && opt_state_dev)), MAMDR_E_INVALID, "NULL pointer");
     MAMDR_REQUIRE(ctx, rows > 0 && dim > 0 && dim % 4 == 0, MAMDR_E_INVALID, "bad table shape");
     MAMDR_REQUIRE(ctx, aligned16(table_dev) && aligned16(m_dev) && aligned16(v_dev) && aligned16(ws_dev), MAMDR_E_INVALID, "misaligned pointer");
     MAMDR_REQUIRE(ctx, ws_bytes >= mamdr_adam_table_workspace_bytes(), MAMDR_E_WORKSPACE, "workspace too small");
@@ -199,7 +212,24 @@ extern "C" int mamdr_adam_table_step(mamdr_ctx* ctx, float* table_dev, float* m_
     long long cap = (long long)ctx->sm_count * per_sm;
     if (cap > kMaxBlocks) cap = kMaxBlocks;
     const int grid = (int)(want < cap ? want : cap);
-    adam_table_kernel<<<grid, kThreads, 0, st>>>(a);
+    if (sgd) adam_table_kernel<true><<<grid, kThreads, 0, st>>>(a);
+    else adam_table_kernel<false><<<grid, kThreads, 0, st>>>(a);
     MAMDR_LAUNCH_OK(ctx);
     return MAMDR_OK;
+}
+
+extern "C" int mamdr_adam_table_step(mamdr_ctx* ctx, float* table_dev, float* m_dev, float* v_dev, int64_t rows, int32_t dim,
+                                     const int32_t* uniq_ids_dev, const float* uniq_rows_dev, const int32_t* n_uniq_dev,
+                                     int64_t max_uniq, int32_t* slot_map_dev, float l2, const void* opt_state_dev, float lr,
+                                     float beta1, float beta2, float eps, float* loss_dev, void* ws_dev, size_t ws_bytes,
+                                     mamdr_stream stream) {
+    return table_step(ctx, false, table_dev, m_dev, v_dev, rows, dim, uniq_ids_dev, uniq_rows_dev, n_uniq_dev, max_uniq, slot_map_dev, l2,
+                      opt_state_dev, lr, beta1, beta2, eps, loss_dev, ws_dev, ws_bytes, stream);
+}
+
+extern "C" int mamdr_sgd_table_step(mamdr_ctx* ctx, float* table_dev, int64_t rows, int32_t dim, const int32_t* uniq_ids_dev,
+                                    const float* uniq_rows_dev, const int32_t* n_uniq_dev, int64_t max_uniq, int32_t* slot_map_dev,
+                                    float l2, float lr, float* loss_dev, void* ws_dev, size_t ws_bytes, mamdr_stream stream) {
+    return table_step(ctx, true, table_dev, nullptr, nullptr, rows, dim, uniq_ids_dev, uniq_rows_dev, n_uniq_dev, max_uniq, slot_map_dev, l2,
+                      nullptr, lr, 0.f, 0.f, 0.f, loss_dev, ws_dev, ws_bytes, stream);
 }

@@ -384,23 +384,21 @@ class MLPModel(object):
         if self.emb_trainable:
             # K6 + K7 fused per table: de-duplicated sparse rows + dense l2 term + Adam over every row, BEFORE the
             # dense apply advances the beta powers; then the dense part of the arena
-            if self.optimizer != "adam":
-                raise NotImplementedError("trainable tables are updated by Adam only (the finetune SGD stage follows frozen-table configs)")
             for t, (off, n_rows, dim, slot) in enumerate(self._tables):
                 ids, srows, cnt = C.c_void_p(), C.c_void_p(), C.c_void_p()
                 rc = self.ctx.lib.mamdr_mlp_sparse_grads(C.byref(self.desc), int(rows), _ptr(self.ws), t, C.byref(ids),
                                                          C.byref(srows), C.byref(cnt))
                 if rc != 0:
                     raise _lib.MamdrError(rc, "mamdr_mlp_sparse_grads")
-                n_el = n_rows * dim
-                self.ctx.call("mamdr_adam_table_step", _ptr(self.params[off:off + n_el]), _ptr(self.m[off:off + n_el]),
-                              _ptr(self.v[off:off + n_el]), n_rows, dim, ids, srows, cnt, int(rows), _ptr(slot),
-                              self.l2_emb, _ptr(self.opt_state), self.lr, self.beta1, self.beta2, self.eps,
-                              _ptr(loss_slot), _ptr(self.table_ws), self.table_ws_bytes, st)
+                self._table_sweep(off, n_rows, dim, slot, ids, srows, cnt, int(rows), self.opt_state, loss_slot, st)
             do = self.dense_off
-            self.ctx.call("mamdr_adam_step", _ptr(self.params[do:]), _ptr(self.m[do:]), _ptr(self.v[do:]),
-                          _ptr(self.grads[do:]), self.params.numel() - do, _ptr(self.opt_state), self.lr, self.beta1,
-                          self.beta2, self.eps, st)
+            if self.optimizer == "adam":
+                self.ctx.call("mamdr_adam_step", _ptr(self.params[do:]), _ptr(self.m[do:]), _ptr(self.v[do:]),
+                              _ptr(self.grads[do:]), self.params.numel() - do, _ptr(self.opt_state), self.lr, self.beta1,
+                              self.beta2, self.eps, st)
+            else:
+                self.ctx.call("mamdr_sgd_step", _ptr(self.params[do:]), _ptr(self.grads[do:]), self.params.numel() - do,
+                              _ptr(self.opt_state), self.sgd_lr, st)
             self.ctx.launches += 1 + 2 + 2 * 2   # dX GEMM, sort + segment-sum (both tables per launch), 2 x (slot scatter, table sweep)
         elif self.optimizer == "adam":
             self.ctx.call("mamdr_adam_step", _ptr(self.params), _ptr(self.m), _ptr(self.v), _ptr(self.grads),
@@ -414,8 +412,6 @@ class MLPModel(object):
         """Config #2 in the tcgen05 modes: one mini-batch = the pass kernel (tables gathered from the arena, tower + dX on the
         tensor cores, dense variables applied in-kernel, the two sparse gradients de-duplicated behind it) + the fused
         sparse-merge / l2 / non-lazy Adam sweep of each table, which reads the beta powers of BEFORE the step."""
-        if self.optimizer != "adam":
-            raise NotImplementedError("trainable tables are updated by Adam only (the finetune SGD stage follows frozen-table configs)")
         st = self.stream
         self.desc.frozen_reg = 0.0   # training adds the tables' l2 penalty inside the fused table sweep
         self._opt_prev.copy_(self.opt_state)
@@ -426,12 +422,21 @@ class MLPModel(object):
                                                           C.byref(srows), C.byref(cnt))
             if rc != 0:
                 raise _lib.MamdrError(rc, "mamdr_mlp_pass_sparse_grads")
-            n_el = n_rows * dim
-            self.ctx.call("mamdr_adam_table_step", _ptr(self.params[off:off + n_el]), _ptr(self.m[off:off + n_el]),
-                          _ptr(self.v[off:off + n_el]), n_rows, dim, ids, srows, cnt, int(rows), _ptr(slot),
-                          self.l2_emb, _ptr(self._opt_prev), self.lr, self.beta1, self.beta2, self.eps,
-                          _ptr(loss_slot), _ptr(self.table_ws), self.table_ws_bytes, st)
+            self._table_sweep(off, n_rows, dim, slot, ids, srows, cnt, int(rows), self._opt_prev, loss_slot, st)
         self.ctx.launches += 2 + 2 * 2   # sort + segment-sum (both tables per launch), 2 x (slot scatter, table sweep)
+
+    def _table_sweep(self, off, n_rows, dim, slot, ids, srows, cnt, max_uniq, opt_state, loss_slot, st):
+        """K6 + K7 fused for one trainable table: the de-duplicated sparse rows + the dense l2 term, then the non-lazy Adam over
+        every row -- or, in the finetune stage (``compile('sgd')``), plain SGD over every row."""
+        n_el = n_rows * dim
+        if self.optimizer == "adam":
+            self.ctx.call("mamdr_adam_table_step", _ptr(self.params[off:off + n_el]), _ptr(self.m[off:off + n_el]),
+                          _ptr(self.v[off:off + n_el]), n_rows, dim, ids, srows, cnt, max_uniq, _ptr(slot),
+                          self.l2_emb, _ptr(opt_state), self.lr, self.beta1, self.beta2, self.eps,
+                          _ptr(loss_slot), _ptr(self.table_ws), self.table_ws_bytes, st)
+        else:
+            self.ctx.call("mamdr_sgd_table_step", _ptr(self.params[off:off + n_el]), n_rows, dim, ids, srows, cnt, max_uniq,
+                          _ptr(slot), self.l2_emb, self.sgd_lr, _ptr(loss_slot), _ptr(self.table_ws), self.table_ws_bytes, st)
 
     # ---- virtual ranks: several models side by side on ONE GPU, each pass kernel on its own SM partition -------------
     def set_pass_ctas(self, n):

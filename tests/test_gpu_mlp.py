@@ -115,7 +115,7 @@ def test_train_step_gradients_match_oracle(rows, prec):
     for name, a, b, b64 in zip(names, g, og, og64):
         e_gpu = rel_err(a, b64)
         e_np = rel_err(b, b64)
-        tol = 2e-5 if prec == "fp32" else 5e-5   # 3xTF32 keeps ~2^-21 per product (tc_gemm.cuh)
+        tol = 2e-5 if prec == "fp32" else 5e-5   # 3xTF32 keeps ~2^-21 per product (mlp_pass.cu)
         assert rel_err(a, b) < tol, (name, rel_err(a, b))
         # vs fp64 truth: the SIMT path is as accurate as numpy fp32; 3xTF32 stays within 1e-5
         assert e_gpu < (max(4 * e_np, 2e-6) if prec == "fp32" else 1e-5), (name, e_gpu, e_np)

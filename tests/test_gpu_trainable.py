@@ -147,3 +147,53 @@ def test_table_sweep_properties_at_amazon6_size():
     gl2 = (2e-5 * p0[untouched])
     expect = -1e-3 * gl2 / (gl2.abs() + 1e-8 / (1 - 0.999) ** 0.5)
     assert torch.allclose(delta[untouched], expect, rtol=2e-3, atol=1e-9)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32x3"])
+def test_trainable_sgd_steps_match_oracle(prec):
+    """The finetune stage's plain SGD (specific_base_model.py:120, base_model.py:69) on a model with TRAINABLE tables
+    (config/Amazon_6/deepctr_DN+DR.json is such a `_finetune` name): every table row moves by (2 l2 E + sparse) * lr
+    (`mamdr_sgd_table_step`), the dense variables by their gradient * lr -- three steps vs the oracle (dropout 0: the oracle's
+    SGD does not advance the dropout step counter)."""
+    base = _build(_amazon(**{"b200.precision": prec, "model.dropout": 0.0}))
+    m = base.model
+    rng = np.random.default_rng(3)
+    w = _weights(m)
+    for i, n in enumerate(m.layout.names):
+        if n.endswith('_emb'):
+            w[i] = (rng.standard_normal(w[i].shape) * 0.05).astype(np.float32)
+    m.params.copy_(torch.from_numpy(m.layout.pack(w)))
+    o = _oracle_for(base, weights=w)
+    m.compile(optimizer="sgd", lr=0.05)
+    data = base.dataset.train_dataset[1]['data']
+    order = Schedule(2).batch_order(1, data.n_data)
+    data.set_order(order)
+    h = data.host
+    rows = min(700, data.n_data)
+    loss = torch.zeros(1, device="cuda")
+    m_before, v_before = m.m.clone(), m.v.clone()
+    for s in range(3):
+        off = (s * 37) % max(1, data.n_data - rows)
+        loss.zero_()
+        m._train_step(data, off, rows, loss)
+        sel = order[off:off + rows]
+        ol, _ = o.train_on_batch(h['uid'][sel], h['pid'][sel], 1, h['label'][sel], optimizer='sgd', sgd_lr=0.05)
+        assert abs(loss.item() - ol) < 2e-5 * abs(ol), (s, loss.item(), ol)
+    for name, a, b in zip(m.layout.names, _weights(m), o.weights):
+        assert rel_err(a, b) < (1e-5 if prec == "fp32" else 5e-5), (name, rel_err(a, b))
+    assert torch.equal(m.m, m_before) and torch.equal(m.v, v_before)      # SGD leaves the Adam slots alone
+    for _, _, _, slot in m._tables:
+        assert int((slot != -1).sum().item()) == 0
+    m.compile(optimizer="adam")
+
+
+def test_trainable_mamdr_finetune_name_runs_end_to_end(tmp_path):
+    """`mlp_meta_mamdr_finetune` with trainable tables (the shape of config/Amazon_6/deepctr_DN+DR.json) through run.main:
+    meta-training, test, reload, the per-domain SGD finetune stage, result files."""
+    import os
+    import run
+    c = _amazon(scale=0.001, **{"model.name": "mlp_meta_mamdr_finetune", "b200.precision": "tf32x3", "train.epoch": 2, "train.sample_num": 1})
+    c["train"]["result_save_path"], c["train"]["checkpoint_path"] = str(tmp_path / "result"), str(tmp_path / "ckpt")
+    avg_loss, avg_auc, domain_loss, domain_auc = run.main(c)
+    assert np.isfinite(avg_loss) and 0.0 <= avg_auc <= 1.0 and len(domain_auc) == 6
+    assert any(f == "result.json" for _, _, fs in os.walk(str(tmp_path / "result")) for f in fs)
