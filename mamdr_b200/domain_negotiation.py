@@ -10,12 +10,15 @@ class DomainNegotiation(MAML):
     def __init__(self, base_model):
         super(DomainNegotiation, self).__init__(base_model)
 
-    def train(self):
-        self.log("Start Domain Negotiation on model: {}".format(self.model_config['name']))
+    def prepare(self):
         self._get_model_meta_parms()                          # :27
         self.meta_weights = self._get_meta_weights()          # :29
         self.model.reset_optimizer()                          # :31 global_variables_initializer
         self.meta_sequence = self.build_meta_data_split()     # :33
+
+    def train(self):
+        self.log("Start Domain Negotiation on model: {}".format(self.model_config['name']))
+        self.prepare()
         for epoch in range(self.train_config['epoch']):
             self.log("Epoch: {}".format(epoch), "-" * 30)
             self.train_epoch(epoch)
