@@ -296,8 +296,8 @@ class MLPModel(object):
         sequence runs as ONE persistent cooperative launch at the end of the block (``mamdr_program_begin / _end``).
         Only the tcgen05 modes have the in-kernel executor; otherwise (or with ``enabled=False``) this is a no-op and
         calls execute immediately."""
-        if not (enabled and self.pass_kernel) or self._recording:
-            yield False
+        if not (enabled and self.pass_kernel) or self._recording or self.emb_trainable:   # (trainable tables: the table sweeps run
+            yield False                                                                    #  between mini-batches -- not recordable)
             return
         self.ctx.call("mamdr_program_begin")
         self._recording = True

@@ -187,12 +187,13 @@ def test_trainable_sgd_steps_match_oracle(prec):
     m.compile(optimizer="adam")
 
 
-def test_trainable_mamdr_finetune_name_runs_end_to_end(tmp_path):
+@pytest.mark.parametrize("prec", ["tf32x3", "fp32"])
+def test_trainable_mamdr_finetune_name_runs_end_to_end(tmp_path, prec):
     """`mlp_meta_mamdr_finetune` with trainable tables (the shape of config/Amazon_6/deepctr_DN+DR.json) through run.main:
     meta-training, test, reload, the per-domain SGD finetune stage, result files."""
     import os
     import run
-    c = _amazon(scale=0.001, **{"model.name": "mlp_meta_mamdr_finetune", "b200.precision": "tf32x3", "train.epoch": 2, "train.sample_num": 1})
+    c = _amazon(scale=0.001, **{"model.name": "mlp_meta_mamdr_finetune", "b200.precision": prec, "train.epoch": 2, "train.sample_num": 1})
     c["train"]["result_save_path"], c["train"]["checkpoint_path"] = str(tmp_path / "result"), str(tmp_path / "ckpt")
     avg_loss, avg_auc, domain_loss, domain_auc = run.main(c)
     assert np.isfinite(avg_loss) and 0.0 <= avg_auc <= 1.0 and len(domain_auc) == 6
