@@ -344,6 +344,20 @@ def micro_rooflines(model, peaks, torch):
     gb = (24.0 * n_el + 4.0 * rows_t) / 1e9
     out["table_adam"] = {"bound": "hbm", "achieved": gb / (ms * 1e-3), "peak": hbm, "unit": "GB/s",
                          "frac": gb / (ms * 1e-3) / hbm, "rows": rows_t, "dim": dim_t, "ms": ms}
+    # the finetune stage's plain SGD over a trainable table (mamdr_sgd_table_step): 8 B per element
+    sargs = (_ptr(tp), rows_t, dim_t, _ptr(uids), _ptr(urows), _ptr(ucnt), 1024, _ptr(slot), 1e-5, 1e-3, None, _ptr(tws), tws.numel(), st)
+    for _ in range(3):
+        ctx.call("mamdr_sgd_table_step", *sargs)
+    a, b = ev(), ev()
+    a.record()
+    for _ in range(reps):
+        ctx.call("mamdr_sgd_table_step", *sargs)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / reps
+    gb = (8.0 * n_el + 4.0 * rows_t) / 1e9
+    out["table_sgd"] = {"bound": "hbm", "achieved": gb / (ms * 1e-3), "peak": hbm, "unit": "GB/s",
+                        "frac": gb / (ms * 1e-3) / hbm, "rows": rows_t, "dim": dim_t, "ms": ms}
     del tp, tm, tv, p, m, v
     # sparse-gradient de-duplication at HBM scale (multi-CTA path): 2 Mi gradient rows x 128 over Zipf ids -> read n x 512 B once,
     # write u x 512 B
@@ -739,12 +753,19 @@ def run_b200(args):
         del w2
         return v
 
+    def guarded(over, steps):
+        try:
+            return side_run(over, steps)
+        except Exception as e:     # a side measurement must never cost the headline line
+            sys.stderr.write("side run %r failed: %r\n" % (over, e))
+            return None
+
     parity_mode = fill_mode = None
     if world == 1 and model.pass_kernel and not args.no_micro and not args.virtual_ranks:
-        parity_mode = {"precision": "fp32", "value": side_run({"precision": "fp32"}, 2), "unit": "samples/s",
+        parity_mode = {"precision": "fp32", "value": guarded({"precision": "fp32"}, 2), "unit": "samples/s",
                        "steps": 2, "note": "device-timed, same workload; fp32 FFMA tower (per-pass parity vs the CPU oracle 1e-6 in both modes, tests/test_gpu_trajectory.py)"}
         if "batch" not in config["model"]["name"] and not config["train"].get("finetune_every_epoch"):
-            fill_mode = {"virtual_ranks": 2, "value": side_run({"virtual_ranks": 2}, 5), "unit": "samples/s", "steps": 5,
+            fill_mode = {"virtual_ranks": 2, "value": guarded({"virtual_ranks": 2}, 5), "unit": "samples/s", "steps": 5,
                          "note": "OPT-IN, NOT the headline: b200.virtual_ranks = 2 runs the DR chains of different query domains side by side on two "
                                  "74-SM partitions of this GPU (a row-local chain occupies 64 SMs).  Semantics = the 2-rank sharded schedule "
                                  "(per-lane Adam state during DR, the last owner's state adopted), bit-identical to two real ranks and judged against "

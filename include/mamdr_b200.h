@@ -64,9 +64,8 @@ int         mamdr_ctx_set_pass_ctas(mamdr_ctx* ctx, int32_t n_ctas);
 
 /* ---- K1: embedding gather  (replaces tf.gather under Embedding, DeepCTR/deepctr.py:125-128) --
  * out[i, 0:dim] = table[ids[i], 0:dim], i < n.  dim % 4 == 0, rows 16-byte aligned, out_stride in
- * floats (>= dim, % 4 == 0).  Bit-exact.  NEGATIVE ids are padding (the fixed-capacity exchange blocks of
- * the row-sharded tables): their output row is left untouched.  ids >= rows: undefined (the reference
- * would raise inside tf.gather). */
+ * floats (>= dim, % 4 == 0).  Bit-exact.  ids outside [0, rows) -> row of zeros is NOT produced:
+ * the call is undefined for such ids (the reference would raise inside tf.gather). */
 int mamdr_gather_f32(mamdr_ctx* ctx, const float* table_dev, int64_t rows, int32_t dim,
                      const int32_t* ids_dev, int64_t n, float* out_dev, int64_t out_stride,
                      mamdr_stream stream);

@@ -24,7 +24,6 @@ gather_rows_f32_kernel(const float* __restrict__ table, const int32_t* __restric
         float4  val[kGatherUnroll];
         int64_t r[kGatherUnroll];
         int     c[kGatherUnroll];
-        bool    ok[kGatherUnroll];
 #pragma unroll
         for (int u = 0; u < kGatherUnroll; ++u) {
             const int64_t vv = v + u * stride;
@@ -34,18 +33,16 @@ gather_rows_f32_kernel(const float* __restrict__ table, const int32_t* __restric
 #pragma unroll
         for (int u = 0; u < kGatherUnroll; ++u) {
             const int64_t id = __ldg(ids + r[u]);
-            ok[u] = id >= 0;   // negative ids are padding (fixed-capacity exchange blocks of the row-sharded tables): row left untouched
-            val[u] = ok[u] ? ldg_f4(table + id * row_floats + c[u] * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            val[u] = ldg_f4(table + id * row_floats + c[u] * 4);
         }
 #pragma unroll
-        for (int u = 0; u < kGatherUnroll; ++u)
-            if (ok[u]) st_stream_f4(out + r[u] * out_stride + c[u] * 4, val[u]);
+        for (int u = 0; u < kGatherUnroll; ++u) st_stream_f4(out + r[u] * out_stride + c[u] * 4, val[u]);
     }
     for (; v < total; v += stride) {
         const int64_t r  = v / dv;
         const int     c  = (int)(v - r * dv);
         const int64_t id = __ldg(ids + r);
-        if (id >= 0) st_stream_f4(out + r * out_stride + c * 4, ldg_f4(table + id * row_floats + c * 4));
+        st_stream_f4(out + r * out_stride + c * 4, ldg_f4(table + id * row_floats + c * 4));
     }
 }
 
