@@ -134,14 +134,32 @@ def _uneven_gather(parts, mine, sizes):
 
 
 class _Steps(object):
-    """`step` = one eager `train_on_batch`.  (Round 1 had an opt-in CUDA-graph replay of whole steps including the NCCL
-    collectives; captures of collectives dead-locked for some shapes on this stack and the path was removed -- the routing /
-    packing work it was hiding is device-side now and the eager step never synchronises with the host.)"""
+    """`step` = one `train_on_batch`.  The collectives of a step are always issued eagerly (round 1's CUDA-graph replay of WHOLE
+    steps, NCCL collectives inside the capture, dead-locked for some shapes and was removed).  `use_graphs=True` captures only
+    the TOWER part of a step -- the ~15 (mlp) / ~40 (multi-task) kernel launches between the row fetch and the gradient
+    exchange, no collective inside -- once per (sub-model, slice) and replays it: at 8 GPUs the eager step is bound by the host's
+    launch rate, not by the device."""
 
     def _init_graphs(self, use_graphs=False):
-        if use_graphs:
-            raise ValueError("CUDA-graph replay of sharded steps was removed (NCCL collectives inside captures dead-locked); "
-                             "use the eager step")
+        self.tower_graphs = bool(use_graphs)
+        self._tower_cache = {}
+
+    def _tower(self, key, fn):
+        if not self.tower_graphs:
+            fn()
+            return
+        ent = self._tower_cache.get(key)
+        ctx = self.model.ctx
+        if ent is None:
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize(self.device)
+            before = ctx.launches
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                fn()
+            ent = self._tower_cache[key] = (g, ctx.launches - before)
+            ctx.launches = before
+        ent[0].replay()
+        ctx.launches += ent[1]
 
     def step(self, uid, pid, label, domain):
         return self.train_on_batch(uid, pid, label, domain)
@@ -184,6 +202,7 @@ class ShardedJointTrainer(_Steps):
         self.dX = torch.zeros(bl, emb_dim[0] + emb_dim[1], dtype=torch.float32, device=self.device)
         self.loss_local = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.loss_tab = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.y_buf = torch.zeros(bl, dtype=torch.float32, device=self.device)
         self.comm_bytes = 0
 
     def _slice(self, n):
@@ -215,16 +234,22 @@ class ShardedJointTrainer(_Steps):
         self.loss_tab.zero_()
         if bl:
             m.user_table, m.item_table = rows_u, rows_i
-            data = self._local_data(y, domain, bl)
-            b = m._batch(data, 0, bl, False)
-            b.row0 = start            # dropout masks follow the GLOBAL batch row: the same draw as the unsharded step
-            m.ctx.call("mamdr_mlp_train_step", C.byref(m.desc), C.byref(b), _ptr(rows_u), _ptr(rows_i), _ptr(m.params), _ptr(m.grads),
-                       _ptr(m.ws), m.ws_bytes, _ptr(m.opt_state), _ptr(self.loss_local), None, _ptr(m.auc_acc), _ptr(m.thresholds),
-                       m.num_thresholds, m.precision, st)
-            m.ctx.call("mamdr_mlp_input_grads", C.byref(m.desc), bl, _ptr(m.params), _ptr(m.ws), m.ws_bytes, _ptr(self.dX), st)
-            m.ctx.launches += 14
-            m.grads.mul_(w)
-            self.loss_local.mul_(w)
+            self.y_buf[:bl].copy_(y)
+
+            def tower():
+                stt = m.stream
+                self.loss_local.zero_()
+                data = self._local_data(self.y_buf, domain, bl)
+                b = m._batch(data, 0, bl, False)
+                b.row0 = start            # dropout masks follow the GLOBAL batch row: the same draw as the unsharded step
+                m.ctx.call("mamdr_mlp_train_step", C.byref(m.desc), C.byref(b), _ptr(rows_u), _ptr(rows_i), _ptr(m.params), _ptr(m.grads),
+                           _ptr(m.ws), m.ws_bytes, _ptr(m.opt_state), _ptr(self.loss_local), None, _ptr(m.auc_acc), _ptr(m.thresholds),
+                           m.num_thresholds, m.precision, stt)
+                m.ctx.call("mamdr_mlp_input_grads", C.byref(m.desc), bl, _ptr(m.params), _ptr(m.ws), m.ws_bytes, _ptr(self.dX), stt)
+                m.ctx.launches += 14
+                m.grads.mul_(w)
+                self.loss_local.mul_(w)
+            self._tower((int(domain), bl, start, n), tower)
         else:
             m.grads.zero_()
         # tables first (they read the beta powers), then the dense arena (its apply advances them); the gradient rows are
@@ -298,6 +323,7 @@ class ShardedMTLTrainer(_Steps):
         self.dX = torch.zeros(bl, emb_dim[0] + emb_dim[1], dtype=torch.float32, device=self.device)
         self.loss_local = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.loss_tab = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.y_buf = torch.zeros(bl, dtype=torch.float32, device=self.device)
         self.theta = None
         self.comm_bytes = 0
 
@@ -322,18 +348,24 @@ class ShardedMTLTrainer(_Steps):
         begin, length, n_spans = m.spans[t]
         spans = [m.grads[int(begin[q]):int(begin[q]) + int(length[q])] for q in range(n_spans)]
         if bl:
-            data = self._local_data(y, t, bl)
-            b = m._batch(data, 0, bl, False)
-            b.row0 = start            # dropout masks follow the GLOBAL batch row: the same draw as the unsharded step
-            m.ctx.call("mamdr_mtl_train_step", C.byref(m.desc), C.byref(m.domains[t]), C.byref(b), _ptr(rows_u), _ptr(rows_i),
-                       _ptr(m.params), _ptr(m.grads), _ptr(m.ws), m.ws_bytes, _ptr(m.opt_state), _ptr(self.loss_local), None,
-                       _ptr(m.auc_acc), _ptr(m.thresholds), m.num_thresholds, st)
-            m.ctx.call("mamdr_mtl_input_grads", C.byref(m.desc), C.byref(m.domains[t]), bl, _ptr(m.params), _ptr(m.ws), m.ws_bytes,
-                       _ptr(self.dX), st)
-            m.ctx.launches += m.launches_per_train_step()
-            for g in spans:
-                g.mul_(w)
-            self.loss_local.mul_(w)
+            self.y_buf[:bl].copy_(y)
+
+            def tower():
+                stt = m.stream
+                self.loss_local.zero_()
+                data = self._local_data(self.y_buf, t, bl)
+                b = m._batch(data, 0, bl, False)
+                b.row0 = start            # dropout masks follow the GLOBAL batch row: the same draw as the unsharded step
+                m.ctx.call("mamdr_mtl_train_step", C.byref(m.desc), C.byref(m.domains[t]), C.byref(b), _ptr(rows_u), _ptr(rows_i),
+                           _ptr(m.params), _ptr(m.grads), _ptr(m.ws), m.ws_bytes, _ptr(m.opt_state), _ptr(self.loss_local), None,
+                           _ptr(m.auc_acc), _ptr(m.thresholds), m.num_thresholds, stt)
+                m.ctx.call("mamdr_mtl_input_grads", C.byref(m.desc), C.byref(m.domains[t]), bl, _ptr(m.params), _ptr(m.ws), m.ws_bytes,
+                           _ptr(self.dX), stt)
+                m.ctx.launches += m.launches_per_train_step()
+                for g in spans:
+                    g.mul_(w)
+                self.loss_local.mul_(w)
+            self._tower((t, bl, start, n), tower)
         else:
             for g in spans:
                 g.zero_()

@@ -37,7 +37,7 @@ def _problem():
     return g, lo, w
 
 
-def _worker(rank, world, port, out_dir, dropout=0.0):
+def _worker(rank, world, port, out_dir, dropout=0.0, graphs=False):
     sys.path.insert(0, HERE)
     sys.path.insert(0, os.path.dirname(HERE))
     os.environ.update({"MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port), "RANK": str(rank), "WORLD_SIZE": str(world)})
@@ -48,7 +48,7 @@ def _worker(rank, world, port, out_dir, dropout=0.0):
     dist.init_process_group("nccl")
     g, lo, w = _problem()
     t = ShardedJointTrainer(g["n_uid"], g["n_pid"], g["n_domain"], w[0], w[1], w[2:], dropout=dropout, batch_size=1024,
-                            device="cuda:%d" % rank)
+                            device="cuda:%d" % rank, use_graphs=graphs)
     d = 0
     split = g["train"][d]
     order = Schedule(3).batch_order(d, len(split["uid"]))
@@ -65,15 +65,15 @@ def _worker(rank, world, port, out_dir, dropout=0.0):
 
 @pytest.mark.timeout(240)
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="row-sharded tables need 2 GPUs (NCCL all-to-all)")
-@pytest.mark.parametrize("dropout", [0.0, 0.5])
-def test_row_sharded_tables_two_ranks_match_oracle(tmp_path, dropout):
+@pytest.mark.parametrize("dropout,graphs", [(0.0, False), (0.5, False), (0.5, True)])
+def test_row_sharded_tables_two_ranks_match_oracle(tmp_path, dropout, graphs):
     import torch.multiprocessing as mp
     from conftest import rel_err
     from mamdr_b200.schedule import Schedule
     from oracle.meta import train_pass
     from oracle.mlp import MLPSpec, OracleMLP
     port = _free_port()
-    mp.spawn(_worker, args=(2, port, str(tmp_path), dropout), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, str(tmp_path), dropout, graphs), nprocs=2, join=True)   # graphs: the tower part of a step replayed from a CUDA graph
     a = torch.load(os.path.join(str(tmp_path), "rank0.pt"), weights_only=False)
     b = torch.load(os.path.join(str(tmp_path), "rank1.pt"), weights_only=False)
     assert torch.equal(a["dense"], b["dense"]) and a["step"] == b["step"]
@@ -112,7 +112,7 @@ def _mtl_problem(kind):
     return g, topo, w
 
 
-def _mtl_worker(rank, world, port, out_dir, kind, dropout=0.0):
+def _mtl_worker(rank, world, port, out_dir, kind, dropout=0.0, graphs=False):
     sys.path.insert(0, HERE)
     sys.path.insert(0, os.path.dirname(HERE))
     os.environ.update({"MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port), "RANK": str(rank), "WORLD_SIZE": str(world)})
@@ -123,7 +123,7 @@ def _mtl_worker(rank, world, port, out_dir, kind, dropout=0.0):
     dist.init_process_group("nccl")
     g, topo, w = _mtl_problem(kind)
     t = ShardedMTLTrainer(kind, g["n_uid"], g["n_pid"], g["n_domain"], w[0], w[1], w[2:], dropout=dropout, lr=1e-4, batch_size=1024,
-                          device="cuda:%d" % rank, **MTL_ARCH[kind])
+                          device="cuda:%d" % rank, use_graphs=graphs, **MTL_ARCH[kind])
     t.dn_prepare()
     sched = Schedule(7)
     seq = list(range(g["n_domain"]))
@@ -143,8 +143,8 @@ def _mtl_worker(rank, world, port, out_dir, kind, dropout=0.0):
 
 @pytest.mark.timeout(240)
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="row-sharded tables need 2 GPUs (NCCL all-to-all)")
-@pytest.mark.parametrize("kind,dropout", [("mmoe", 0.0), ("ple", 0.0), ("mmoe", 0.5)])
-def test_sharded_mtl_domain_negotiation_two_ranks_match_oracle(tmp_path, kind, dropout):
+@pytest.mark.parametrize("kind,dropout,graphs", [("mmoe", 0.0, False), ("ple", 0.0, False), ("mmoe", 0.5, False), ("mmoe", 0.5, True)])
+def test_sharded_mtl_domain_negotiation_two_ranks_match_oracle(tmp_path, kind, dropout, graphs):
     """Two DN meta-steps of `<kind>_meta_domain_negotiation` with the tables row-sharded over 2 ranks vs the single-process
     oracle (OracleDN over OracleMTL) on the same global batches: theta (dense + both tables) rel 1e-4, replicas bit-identical;
     with dropout 0.5 the masks follow the global batch row (mamdr_batch.row0), i.e. the sharded run draws the oracle's masks."""
@@ -155,7 +155,7 @@ def test_sharded_mtl_domain_negotiation_two_ranks_match_oracle(tmp_path, kind, d
     from oracle.meta import OracleDN
     from oracle.mtl import MTLSpec, OracleMTL
     port = _free_port()
-    mp.spawn(_mtl_worker, args=(2, port, str(tmp_path), kind, dropout), nprocs=2, join=True)
+    mp.spawn(_mtl_worker, args=(2, port, str(tmp_path), kind, dropout, graphs), nprocs=2, join=True)
     a = torch.load(os.path.join(str(tmp_path), "mtl_rank0.pt"), weights_only=False)
     b = torch.load(os.path.join(str(tmp_path), "mtl_rank1.pt"), weights_only=False)
     assert torch.equal(a["dense"], b["dense"]) and torch.equal(a["live"], b["live"]) and a["step"] == b["step"]
