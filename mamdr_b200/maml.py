@@ -296,6 +296,8 @@ class MAML(object):
             blob["best_shared_weights"] = self.best_shared_weights.flat.cpu()
         if getattr(self, "accum_grads", None) is not None:
             blob["accum_grads"] = self.accum_grads.cpu()
+        if getattr(self, "_meta_m", None) is not None:     # the second (meta) Adam of MAML / MLDG / PCGrad
+            blob["meta_optimizer"] = {"m": self._meta_m.cpu(), "v": self._meta_v.cpu(), "state": self._meta_opt_state.cpu()}
         torch.save(blob, path)
         return path
 
@@ -330,6 +332,10 @@ class MAML(object):
             self.best_shared_weights.flat.copy_(blob["best_shared_weights"])
         if "accum_grads" in blob and getattr(self, "accum_grads", None) is not None:
             self.accum_grads.copy_(blob["accum_grads"])
+        if "meta_optimizer" in blob and getattr(self, "_meta_m", None) is not None:
+            self._meta_m.copy_(blob["meta_optimizer"]["m"])
+            self._meta_v.copy_(blob["meta_optimizer"]["v"])
+            self._meta_opt_state.copy_(blob["meta_optimizer"]["state"])
         sched = base.schedule
         sched.seed, sched._pass = blob["schedule"]["seed"], blob["schedule"]["pass"]
         sched._rng.setstate(blob["schedule"]["rng"])

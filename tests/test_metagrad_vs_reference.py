@@ -114,14 +114,14 @@ class _MetaGradOps(_NumpyMetaOps):
 
     def __init__(self):
         _NumpyMetaOps.__init__(self)
-        self.pows = {}
 
     def call(self, name, *a):
         f32 = np.float32
         if name == "mamdr_adam_ranges_step":
             params, m, v, g, begin, length, n, state, lr, b1, b2, eps = a[:12]
             self.calls.append(name)
-            b1pow, b2pow = self.pows.setdefault(state.value, [f32(b1), f32(b2)])
+            pw = _view(state, 4)                                              # [step (int64) | b1pow | b2pow] like the device state
+            b1pow, b2pow = f32(pw[2]), f32(pw[3])
             one = f32(1.0)
             alpha = f32(lr) * np.sqrt(one - b2pow) / (one - b1pow)            # oracle.mlp.AdamState.apply == TF ApplyAdam
             for k in range(n):
@@ -131,7 +131,7 @@ class _MetaGradOps(_NumpyMetaOps):
                 mm += (gg - mm) * (one - f32(b1))
                 vv += (gg * gg - vv) * (one - f32(b2))
                 w -= (mm * alpha) / (np.sqrt(vv) + f32(eps))
-            self.pows[state.value] = [f32(b1pow * f32(b1)), f32(b2pow * f32(b2))]
+            pw[2], pw[3] = f32(b1pow * f32(b1)), f32(b2pow * f32(b2))
         elif name == "mamdr_pcgrad_project":
             final, aux, rows, cols = a[:4]
             self.calls.append(name)
@@ -166,7 +166,9 @@ def _metagrad_base(name, tc):
     model.grads_on_batch = grads_on_batch
 
     def new_optimizer_slots():
-        return torch.zeros_like(model.params), torch.zeros_like(model.params), torch.zeros(16, dtype=torch.uint8)
+        st = torch.zeros(4, dtype=torch.float32)                              # mamdr_opt_state_init: beta powers start at beta
+        st[2], st[3] = model.beta1, model.beta2
+        return torch.zeros_like(model.params), torch.zeros_like(model.params), st.view(torch.uint8)
     model.new_optimizer_slots = new_optimizer_slots
 
     def fit_pass(data, steps=None, order=None):
@@ -210,3 +212,34 @@ def test_split_view_windows():
     assert (a.n_data, b.n_data) == (3, 2)
     np.testing.assert_array_equal(a.window_order(perm), [4, 0, 3])
     np.testing.assert_array_equal(b.window_order(perm), [1, 2])
+
+
+@pytest.mark.parametrize("i", [0, 1, 3, 5])
+def test_metagrad_save_state_resume_on_the_cpu_harness(tmp_path, i):
+    """`save_state` after the first epoch (theta, live model, the accumulators, BOTH optimizers' slots, the schedule),
+    `load_state` into a freshly prepared wrapper, second epoch: the same steps, gradient calls, theta and live arena as the
+    uninterrupted run."""
+    from mamdr_b200.maml import MAML
+    from mamdr_b200.mldg import MLDG
+    from mamdr_b200.pcgrad import PCGrad
+    kind, name, over = mg.CASES[i]
+    tc = dict(mg.TC)
+    tc.update(over)
+
+    def fresh():
+        base, model = _metagrad_base(name, tc)
+        w = {"maml": MAML, "mldg": MLDG, "pcgrad": PCGrad}[kind](base)
+        w.prepare()
+        return w, model
+
+    a, model_a = fresh()
+    a.train_epoch(0)
+    path = a.save_state(str(tmp_path / "state.pt"), epoch=0)
+    first = (len(model_a.steps), len(model_a.grad_calls))
+    a.train_epoch(1)
+    b, model_b = fresh()
+    assert b.load_state(path) == 0
+    b.train_epoch(1)
+    assert model_b.steps == model_a.steps[first[0]:] and model_b.grad_calls == model_a.grad_calls[first[1]:]
+    assert torch.equal(model_a.params, model_b.params) and torch.equal(a.meta_weights.flat, b.meta_weights.flat)
+    assert torch.equal(a._meta_m, b._meta_m) and torch.equal(a._meta_v, b._meta_v) and torch.equal(a._meta_opt_state, b._meta_opt_state)
