@@ -11,6 +11,11 @@ value = real samples pushed through training mini-batches per second, whole job.
                     sharded, one NCCL all-reduce per meta-step.  Prints ONE JSON line on rank 0.
   --impl reference  the CPU oracle restatement of the reference's TF path (TF 1.12 cannot be installed:
                     BASELINE.md section 2) timed on the host cores, a bounded sample per step.
+  --workload W      secondary workloads (Taobao-10-batch / -20 / -20-star / -30, Amazon-6, Amazon-13-{mmoe,ple}[-sharded],
+                    Amazon-13-sharded); the default line is config #1.
+  --virtual-ranks V opt-in, a SEPARATE line: V DR chains side by side on SM partitions of one GPU (the V-rank sharded
+                    schedule, bit-identical to V real ranks); the default line also reports it as `fill_the_machine`.
+  --graphs          sharded workloads: the tower part of a step is replayed from a CUDA graph (collectives stay eager).
 """
 import argparse
 import copy
