@@ -271,7 +271,8 @@ class MAMDR(SpecificBase):
     def _prefetch_plan(self):
         """Stage the NEXT meta-step while the GPU still runs this one (`b200.lookahead`, default on).  The draws happen in the
         reference's order either way; `save_state` stores the schedule state from before the look-ahead."""
-        if self.b200_config.get('lookahead', True) and not self.train_config['finetune_every_epoch']:
+        if (self.b200_config.get('lookahead', True) and not self.train_config['finetune_every_epoch']
+                and not self.train_config.get('meta_finetune_step', 0) > 0):   # (val() would train between the meta-steps)
             self._next_plan = self._plan_epoch()
             self.base_model._discard_lookahead = self._discard_plan
 

@@ -263,10 +263,37 @@ class MAML(object):
 
     # ---- maml.py:343-353
     def val(self):
-        if self.train_config['meta_finetune_step'] > 0:
-            raise NotImplementedError("meta_finetune_step > 0 is not used by any shipped DN / MAMDR config")
         self.log("Val Result: ")
+        if self.train_config['meta_finetune_step'] > 0:
+            return self.meta_finetune_val()      # finetune a few epochs per domain to evaluate the meta parameters
         return self.val_and_test("val")
+
+    # ---- maml.py:244-287
+    def meta_finetune_val(self):
+        """Per domain: restart from the current weights, ``meta_finetune_step`` Keras epochs (one shuffled pass each, the model's
+        own optimizer -- whose slots are NOT part of get_weights / set_weights and keep advancing, as in the reference), evaluate
+        on the domain's validation split; the weights are restored at the end."""
+        train_dataset, val_dataset = self.dataset.train_dataset, self.dataset.val_dataset
+        train_epoch = self.train_config['meta_finetune_step']
+        domain_loss, domain_auc = {}, {}
+        all_loss, all_auc = 0, 0
+        weights = self.model.get_weights()                       # :258
+        for domain_idx, train_d in train_dataset.items():
+            self.model.set_weights(weights)                      # :260
+            self.log("Finetune on domain: {}".format(domain_idx))
+            for epoch in range(train_epoch):                     # :264-267 model.fit(..., epochs=epoch + 1, initial_epoch=epoch)
+                self.run_train_pass(domain_idx)
+            p_loss, p_auc = self.model.evaluate(val_dataset[domain_idx]['data'], steps=val_dataset[domain_idx]['n_step'])   # :269-271
+            domain_loss[domain_idx], domain_auc[domain_idx] = p_loss, p_auc
+            all_loss += p_loss
+            all_auc += p_auc
+        self.model.set_weights(weights)                          # :279
+        avg_loss = all_loss / len(domain_loss)
+        avg_auc = all_auc / len(domain_auc)
+        self.log("Loss: ", domain_loss)
+        self.log("AUC: ", domain_auc)
+        self.log("Overall val Loss: {}, AUC: {}".format(avg_loss, avg_auc))
+        return avg_loss, avg_auc, domain_loss, domain_auc
 
     # ---- resume (SURVEY.md 8(f) row f3: what the reference lacks -- theta, theta_d[], the Adam state and the schedule are
     # only in RAM there, base_model.py:177-181 saves the live Keras weights alone) ------------------------------------

@@ -130,6 +130,27 @@ class OracleDN(object):
             self.best_weights = self.model.get_weights()             # save_model(h5)
         return self.es.step(metric, keep)
 
+    def val(self):                                                   # maml.py:343-353
+        if self.tc.get('meta_finetune_step', 0) > 0:
+            return self.meta_finetune_val()
+        return self.val_and_test("val")
+
+    def meta_finetune_val(self):                                     # maml.py:244-287
+        domain_loss, domain_auc = {}, {}
+        all_loss, all_auc = 0, 0
+        weights = self.model.get_weights()
+        for idx, d in self.data['train'].items():
+            self.model.set_weights(weights)
+            for epoch in range(self.tc['meta_finetune_step']):
+                train_pass(self.model, d, idx, self.schedule.batch_order(idx, len(d['uid'])), self.bs)
+            v = self.data['val'][idx]
+            l, a = self.model.evaluate(v['uid'], v['pid'], idx, v['label'], self.bs)
+            domain_loss[idx], domain_auc[idx] = float(l), float(a)
+            all_loss += domain_loss[idx]
+            all_auc += domain_auc[idx]
+        self.model.set_weights(weights)
+        return all_loss / len(domain_loss), all_auc / len(domain_auc), domain_loss, domain_auc
+
 
 class OracleReptile(OracleDN):
     """``Reptile.train`` with ``target_domain=-1`` (``model_zoo/reptile.py:45-99,127-142``): the model is reset to theta

@@ -34,7 +34,9 @@ TC = dict(mrg.LOOP_TC, meta_learning_rate=0.05, meta_split="meta-train/val", met
           sample_num=2)
 CASES = [("maml", "mlp_meta", {}), ("maml", "mlp_meta_batch", {}), ("maml", "mlp_meta", {"meta_split": "train-train", "meta_train_step": 1}),
          ("mldg", "mlp_meta_mldg", {}), ("mldg", "mlp_meta_mldg_batch", {"epoch": 3}),
-         ("pcgrad", "mlp_pcgrad", {}), ("pcgrad", "mlp_pcgrad", {"meta_train_step": 1, "sample_num": 3})]
+         ("pcgrad", "mlp_pcgrad", {}), ("pcgrad", "mlp_pcgrad", {"meta_train_step": 1, "sample_num": 3}),
+         # meta_finetune_step > 0: `val()` finetunes a few epochs per domain before evaluating (maml.py:244-287, 343-353)
+         ("maml", "mlp_meta", {"meta_finetune_step": 2}), ("mldg", "mlp_meta_mldg_batch", {"meta_finetune_step": 1})]
 
 
 def toy_grad(weights, domain):

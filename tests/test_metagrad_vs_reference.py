@@ -74,7 +74,7 @@ def test_oracle_replays_the_reference_metagrad_loops(i):
     om = cls(model, _toy_data(), tc, mg.BATCH, Schedule(mrg.LOOP_SEED), name=name)
     for epoch in range(tc["epoch"]):
         om.train_epoch()
-        _, val_auc, _, _ = om.val_and_test("val")
+        _, val_auc, _, _ = om.val()
         if om.early_stop_step(val_auc):
             break
         om.val_and_test("test")      # reloads the best checkpoint into the live model, like the reference (base_model.py:121)
