@@ -32,28 +32,32 @@ class DomainNegotiation(MAML):
                 self.val_and_test("test")
 
     def train_epoch(self, epoch=0):
-        """One DN meta-step (:41-88)."""
+        """One DN meta-step (:41-93)."""
         tc = self.train_config
-        if tc['target_domain'] >= 0:
-            raise NotImplementedError("target_domain >= 0 is not used by any shipped config")
+        target = tc['target_domain']
         if tc['shuffle_sequence']:                            # :41-42
             self.meta_sequence = self.schedule.shuffle_sequence(self.meta_sequence)
-        self.stage_epoch_orders(list(self.meta_sequence))
+        train_sequence = list(self.meta_sequence) + ([target] if target >= 0 else [])   # :44-47
+        self.stage_epoch_orders(train_sequence + ([target] if target >= 0 else []))
         # the whole meta-step is recorded and runs as ONE persistent launch in the tcgen05 modes (engine.program)
         with self.model.program(self.b200_config.get('program', True)):
             self._set_model_meta_parms(self.meta_weights)         # :50
-            for idx in self.meta_sequence:                        # :53-84
+            for idx in train_sequence:                            # :53-84
                 d = self.dataset.train_dataset[idx]
                 for m in self.model.stateful_metric_functions:    # :56-57
                     m.reset_states()
                 train_step = d['n_step']
-                if tc['meta_train_step'] > 0:
+                if tc['meta_train_step'] > 0 and idx != target:   # :67
                     train_step = min(train_step, tc['meta_train_step'])
                 # per-pass loss / AUC prints of :80-84 would force a host sync per pass; the per-batch
                 # losses stay on the device (fit_pass returns them) and are read only on request
                 self.last_pass_losses = self.run_train_pass(idx, train_step)
             self._update_meta_weight(self.meta_weights)           # :87
             # :88 _set_model_meta_parms(meta_weights) is fused into the update (model_out)
+            if target >= 0:                                       # :89-93 model.fit(target_iter, steps_per_epoch=target_step)
+                for m in self.model.stateful_metric_functions:
+                    m.reset_states()
+                self.last_pass_losses = self.run_train_pass(target)
 
     def _update_meta_weight(self, old_vars):
         """:118-123  old += (new - old) * meta_learning_rate, and the model is reloaded with it (:88)."""
@@ -65,7 +69,8 @@ class DomainNegotiation(MAML):
 
     def build_meta_data_split(self):
         """:125-146 -- the meta sequence (data iterators are the device-resident column stores)."""
-        meta_sequence = list(self.dataset.train_dataset.keys())
+        target = self.train_config['target_domain']           # :138-140 the target domain is not part of the meta sequence
+        meta_sequence = [k for k in self.dataset.train_dataset.keys() if not (target >= 0 and k == target)]
         ms = self.train_config.get('meta_sequence')
         if isinstance(ms, list):
             if len(ms) != len(meta_sequence):

@@ -30,7 +30,9 @@ class Reptile(MAML):
             self.train_epoch(epoch)
             if epoch % self.train_config['val_every_step'] == 0:   # :105-118
                 val_avg_loss, val_avg_auc, val_domain_loss, val_domain_auc = self.val()
-                if self.early_stop_step(val_avg_auc):
+                val_metric = val_domain_auc[self.train_config['target_domain']] \
+                    if self.train_config['target_domain'] >= 0 else val_avg_auc     # :112-113
+                if self.early_stop_step(val_metric):
                     break
                 self.log("Test Result: ")
                 self.val_and_test("test")
@@ -38,16 +40,19 @@ class Reptile(MAML):
     def train_epoch(self, epoch=0):
         """One Reptile epoch (:45-97)."""
         tc = self.train_config
-        if tc['target_domain'] >= 0:
-            raise NotImplementedError("target_domain >= 0 is not used by any shipped config")
+        target = tc['target_domain']
         batch = "batch" in self.model_config['name']
         m = self.model
         beta = tc['meta_learning_rate']
         self.train_sequence = self.schedule.shuffle_sequence(self.train_sequence)     # :46
-        self.stage_epoch_orders(list(self.train_sequence))
+        inner = [idx for idx in self.train_sequence if not (target >= 0 and idx == target)]          # :47-48
+        passes = []
+        for idx in inner:
+            passes += [idx] + ([target] if target >= 0 else [])
+        self.stage_epoch_orders(passes + ([target] if target >= 0 else []))
         with m.program(self.b200_config.get('program', True)):
             self._set_model_meta_parms(self.meta_weights)        # :57 (first domain; later ones are fused into the update)
-            for idx in self.train_sequence:
+            for idx in inner:
                 d = self.dataset.train_dataset[idx]
                 for metric in m.stateful_metric_functions:       # :53-54
                     metric.reset_states()
@@ -55,6 +60,8 @@ class Reptile(MAML):
                 if tc['meta_train_step'] > 0:
                     train_step = min(train_step, tc['meta_train_step'])
                 self.last_pass_losses = self.run_train_pass(idx, train_step)
+                if target >= 0:                                  # :82-85 one step on the target domain before the update
+                    self.run_train_pass(target, 1)
                 if batch:                                        # :90-91  accum += model - theta ; then model <- theta (:57)
                     for n, (acc, model, theta) in self._ranges(self.accum_grads, m.params, self.meta_weights.flat):
                         m.ctx.call("mamdr_axpy_diff", _ptr(acc), _ptr(model), _ptr(theta), 1.0, n, m.stream)
@@ -70,3 +77,7 @@ class Reptile(MAML):
                     m.ctx.call("mamdr_copy", _ptr(acc), _ptr(zeros), n, m.stream)
                     m.ctx.call("mamdr_copy", _ptr(model), _ptr(theta), n, m.stream)
                     m.ctx.launches += 3
+            if target >= 0:                                      # :98-102 model.fit(target_iter, steps_per_epoch=target_step)
+                for metric in m.stateful_metric_functions:
+                    metric.reset_states()
+                self.last_pass_losses = self.run_train_pass(target)

@@ -20,9 +20,8 @@ class SpecificBase(MAML):
 
     def build_meta_data_split(self):
         """:20-42"""
-        if self.train_config['target_domain'] >= 0:
-            raise NotImplementedError("target_domain >= 0 is not used by any shipped config")
-        meta_sequence = list(self.dataset.train_dataset.keys())
+        target = self.train_config['target_domain']           # :33-36 the target domain is skipped (it is only evaluated)
+        meta_sequence = [k for k in self.dataset.train_dataset.keys() if not (target >= 0 and k == target)]
         ms = self.train_config.get('meta_sequence')
         if isinstance(ms, list):
             if len(ms) != len(meta_sequence):

@@ -82,7 +82,8 @@ class OracleDN(object):
     def __init__(self, model, data, train_config, batch_size, schedule):
         self.model, self.data, self.tc, self.bs, self.schedule = model, data, train_config, batch_size, schedule
         self.meta_weights = model.get_weights()                     # :29
-        self.sequence = sorted(data['train'].keys())                # :135-141
+        self.target = train_config.get('target_domain', -1)
+        self.sequence = [k for k in sorted(data['train'].keys()) if not (self.target >= 0 and k == self.target)]   # :135-141
         if isinstance(train_config.get('meta_sequence'), list):    # :142-145
             if len(train_config['meta_sequence']) != len(self.sequence):
                 raise ValueError("All the domains must be given in the sequence")
@@ -96,17 +97,26 @@ class OracleDN(object):
         if tc['shuffle_sequence']:                                   # :41-42
             self.sequence = self.schedule.shuffle_sequence(self.sequence)
         self.model.set_weights(self.meta_weights)                    # :50
-        for idx in self.sequence:                                    # :53-84
+        train_sequence = list(self.sequence) + ([self.target] if self.target >= 0 else [])   # :44-47
+        for idx in train_sequence:                                   # :53-84
             self.model.auc.reset_states()                            # :56-57
             d = self.data['train'][idx]
             order = self.schedule.batch_order(idx, len(d['uid']))
-            loss, auc, steps = train_pass(self.model, d, idx, order, self.bs, tc.get('meta_train_step', 0))
+            cap = tc.get('meta_train_step', 0) if idx != self.target else 0   # :67 (the target domain always trains a full pass)
+            loss, auc, steps = train_pass(self.model, d, idx, order, self.bs, cap)
             self.log.append((idx, loss, auc, steps))
         new = self.model.get_weights()                               # :118-123
         beta = tc['meta_learning_rate']
         for var in range(len(new)):
             self.meta_weights[var] += (new[var] - self.meta_weights[var]) * beta
         self.model.set_weights(self.meta_weights)                    # :88
+        self._fit_target()                                           # :89-93
+
+    def _fit_target(self, steps=0):
+        """``model.fit(self.target_iter, steps_per_epoch=...)`` on the target domain (a full pass unless `steps` is given)."""
+        if self.target >= 0:
+            d = self.data['train'][self.target]
+            train_pass(self.model, d, self.target, self.schedule.batch_order(self.target, len(d['uid'])), self.bs, steps)
 
     def val_and_test(self, mode, weights=None):  # base_model.py:111-144
         if mode not in ('val', 'test'):
@@ -159,7 +169,7 @@ class OracleReptile(OracleDN):
     def __init__(self, model, data, train_config, batch_size, schedule, name='mlp_meta_reptile'):
         OracleDN.__init__(self, model, data, train_config, batch_size, schedule)
         self.name = name
-        self.sequence = list(range(len(data['train'])))             # :36
+        self.sequence = list(range(len(data['train'])))             # :36 (the target domain stays in the list and is skipped, :47)
         self.accum = [np.zeros_like(w) for w in self.meta_weights]  # :31
 
     def train_epoch(self):
@@ -167,12 +177,15 @@ class OracleReptile(OracleDN):
         beta = np.float32(tc['meta_learning_rate'])
         self.sequence = self.schedule.shuffle_sequence(self.sequence)   # :46
         for idx in self.sequence:
+            if self.target >= 0 and idx == self.target:              # :47-48
+                continue
             self.model.auc.reset_states()                            # :53-54
             self.model.set_weights(self.meta_weights)                # :57
             d = self.data['train'][idx]
             order = self.schedule.batch_order(idx, len(d['uid']))
             loss, auc, steps = train_pass(self.model, d, idx, order, self.bs, tc.get('meta_train_step', 0))
             self.log.append((idx, loss, auc, steps))
+            self._fit_target(steps=1)                                # :82-85 one step on the target domain
             new = self.model.get_weights()
             if "batch" in self.name:                                 # :134-137
                 for var in range(len(new)):
@@ -185,6 +198,7 @@ class OracleReptile(OracleDN):
                 self.meta_weights[var] += self.accum[var] * beta
                 self.accum[var] = np.zeros_like(self.accum[var])
         self.model.set_weights(self.meta_weights)                    # :99
+        self._fit_target()                                           # :98-102
 
 
 class OracleMAML(OracleDN):
@@ -373,7 +387,8 @@ class OracleMAMDR(object):
         self.meta_weights = model.get_weights()                      # :29
         # :30-33  theta_d^0 = an independent re-initialisation of every layer (injected)
         self.domain_weights = {k: [np.array(w, dtype=model.dtype) for w in v] for k, v in domain_weights.items()}
-        self.sequence = sorted(data['train'].keys())
+        target = train_config.get('target_domain', -1)               # specific_base_model.py:33-36: the target domain is skipped
+        self.sequence = [k for k in sorted(data['train'].keys()) if not (target >= 0 and k == target)]
         if isinstance(train_config.get('meta_sequence'), list):
             if len(train_config['meta_sequence']) != len(self.sequence):
                 raise ValueError("All the domains must be given in the sequence")

@@ -309,7 +309,14 @@ VARIANT_CASES = [("mamdr", "mlp_meta_mamdr", {"finetune_every_epoch": True}),
                  ("dn", "mlp_meta_domain_negotiation", {"shuffle_sequence": False, "meta_sequence": [2, 0, 3, 1]}),
                  ("dn", "mlp_meta_domain_negotiation", {"val_every_step": 2, "epoch": 3}),
                  ("reptile", "mlp_meta_reptile", {"meta_train_step": 2}),
-                 ("reptile", "mlp_meta_reptile_batch", {"epoch": 3, "meta_learning_rate": 0.5})]
+                 ("reptile", "mlp_meta_reptile_batch", {"epoch": 3, "meta_learning_rate": 0.5}),
+                 # target_domain >= 0: the target is left out of the meta sequence, trained after the outer update (DN, Reptile; one
+                 # step per inner domain in Reptile), only evaluated by MAMDR; the early-stop metric is ITS validation AUC
+                 ("dn", "mlp_meta_domain_negotiation", {"target_domain": 2}),
+                 ("dn", "mlp_meta_domain_negotiation", {"target_domain": 0, "meta_train_step": 1, "epoch": 3}),
+                 ("mamdr", "mlp_meta_mamdr", {"target_domain": 3}),
+                 ("reptile", "mlp_meta_reptile", {"target_domain": 0}),
+                 ("reptile", "mlp_meta_reptile_batch", {"target_domain": 2, "meta_train_step": 1})]
 LOOP_CASES = [("mamdr", "mlp_meta_mamdr", "plus"), ("mamdr", "mlp_meta_mamdr_batch", "plus"), ("mamdr", "mlp_meta_mamdr", "times"),
               ("dn", "mlp_meta_domain_negotiation", "plus"), ("reptile", "mlp_meta_reptile", "plus"),
               ("reptile", "mlp_meta_reptile_batch", "plus")]

@@ -448,8 +448,8 @@ def test_oracle_auc_matches_the_reference_metric_code():
 @pytest.mark.parametrize("i", range(len(mrg.VARIANT_CASES)))
 def test_oracle_loops_config_knobs(i):
     """The loops' config keys (finetune_every_epoch, domain_regulation_step, add_query_domain, sample_num, merged_method,
-    an explicit meta_sequence without shuffling, meta_train_step, val_every_step, epoch, meta_learning_rate) as the reference's
-    executed loops handle them vs the oracle."""
+    an explicit meta_sequence without shuffling, meta_train_step, val_every_step, epoch, meta_learning_rate, target_domain >= 0)
+    as the reference's executed loops handle them vs the oracle."""
     from mamdr_b200.schedule import Schedule
     kind, name, over = mrg.VARIANT_CASES[i]
     bs = 4
@@ -466,8 +466,9 @@ def test_oracle_loops_config_knobs(i):
     for epoch in range(tc["epoch"]):
         om.train_epoch()
         if epoch % tc["val_every_step"] == 0:
-            _, val_auc, _, _ = om.val_and_test("val")
-            if om.early_stop_step(val_auc):
+            _, val_auc, _, val_domain_auc = om.val_and_test("val")
+            metric = val_domain_auc[tc["target_domain"]] if tc["target_domain"] >= 0 else val_auc   # the target domain's own AUC
+            if om.early_stop_step(metric):
                 break
             om.val_and_test("test")
     np.testing.assert_array_equal(np.array(model.steps, dtype=np.int32), LOOPS[key + "steps"])
