@@ -137,23 +137,28 @@ class BaseModel(object):
         return self.last_pass_losses
 
     def separate_train_val_test(self, init_parms=True):
-        """base_model.py:41-109 with ``init_parms=False`` -- the ``finetune`` stage of the wrappers WITHOUT domain-specific
+        """base_model.py:41-109.  ``init_parms=True`` (`<name>_separate`, run.py:67-68): one model per domain trained from a fresh
+        initialisation with the compiled Adam.  ``init_parms=False`` -- the ``finetune`` stage of the wrappers WITHOUT domain-specific
         weights (``*_meta_domain_negotiation_finetune``, ``*_meta_reptile_finetune``; run.py:82-85 loads the best checkpoint
         first): per domain restart from those weights, plain SGD with ``train_config['learning_rate']`` (:69), Keras
         EarlyStopping(val_AUC) + best-val_AUC checkpoint, load it, test; the starting weights are restored at the end."""
         import torch
-        if init_parms:
-            raise NotImplementedError("separate training from scratch is outside the hot path")
         hook = getattr(self, "_discard_lookahead", None)   # a staged look-ahead meta-step will not run
         if hook is not None:
             hook()
         m = self.model
+        if init_parms:
+            # :61-63 `<name>_separate`: tf.global_variables_initializer() -- every variable is re-drawn (a fresh injected draw)
+            # and the optimizer slots are zeroed; the compiled Adam is KEPT (no re-compile below) and threads through all domains
+            m.params.copy_(torch.from_numpy(m.layout.pack(self.draw_initial_weights())))
+            m.reset_optimizer()
         weights = m.get_weights()                                   # :65 save init weight
         domain_loss, domain_auc = {}, {}
         all_loss, all_auc = 0, 0
         ckpt_dir = osp.dirname(self.checkpoint_path)
         for domain_idx, train_d in self.dataset.train_dataset.items():
-            m.compile(optimizer="sgd", lr=self.train_config['learning_rate'])    # :67-71
+            if not init_parms:
+                m.compile(optimizer="sgd", lr=self.train_config['learning_rate'])    # :67-71
             m.set_weights(weights)                                  # :72
             self.log("Train on domain: {}".format(domain_idx))
             if not osp.exists(ckpt_dir):

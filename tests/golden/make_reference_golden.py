@@ -568,6 +568,44 @@ def make_finetune():
     return g
 
 
+def make_separate():
+    """run.py:67-68 for `<name>_separate`: `BaseModel.separate_train_val_test()` with init_parms=True (base_model.py:41-109):
+    tf.global_variables_initializer() (here: the toy model's next initialisation), then per domain restart from those
+    weights, train with the compiled optimizer under the two Keras callbacks, load the best checkpoint, test."""
+    import contextlib
+    import io
+    base_model, dn, mamdr, reptile, sbm = import_reference()
+    cbs = types.SimpleNamespace(EarlyStopping=KerasEarlyStopping, ModelCheckpoint=KerasModelCheckpoint, TensorBoard=_Any)
+    base_model.callbacks = cbs
+    base_model.AUC = lambda **kw: "AUC-metric"
+    tc = dict(LOOP_TC, loss="binary_crossentropy", learning_rate=0.001, epoch=SEPARATE_EPOCHS, patience=2)
+    obj, model, base = _toy_wrapper(dn.DomainNegotiation, base_model, tc, "mlp_separate")
+    inits = [0]
+
+    def reinit(op=None):
+        inits[0] += 1
+        for a, b in zip(model.weights, toy_init(inits[0])):
+            a[...] = b
+    saved_backend = base_model.backend
+    base_model.backend = types.SimpleNamespace(get_session=lambda: types.SimpleNamespace(run=reinit))
+    base.separate_train_val_test = types.MethodType(base_model.BaseModel.separate_train_val_test, base)
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            avg_loss, avg_auc, domain_loss, domain_auc = base.separate_train_val_test()
+    finally:
+        base_model.backend = saved_backend
+    g = {"separate|steps": np.array(model.steps, dtype=np.int32),
+         "separate|result": np.array([avg_loss, avg_auc] + [domain_loss[d] for d in sorted(N_STEP)] + [domain_auc[d] for d in sorted(N_STEP)],
+                                     dtype=np.float64),
+         "separate|live": flat_any(model.weights), "separate|compiles": np.array([getattr(model, "compiles", 0)], dtype=np.int32)}
+    for d in sorted(N_STEP):
+        g["separate|ckpt_%d" % d] = flat_any(model.files["domain_%d.h5" % d])
+    return g
+
+
+SEPARATE_EPOCHS = 12
+
+
 # ---- the joint ('alternate') training loops of the base models: DeepCTR.train (DeepCTR/deepctr.py:63-93), Star.train
 # (Star/star.py:35-68), DeepMTLCTR.train (DeepMTLCTR/deep_mtl_ctr.py:68-98) -- note the reference's quirk that every
 # `val_and_test("test")` reloads the best checkpoint, so the next epoch continues from the BEST weights, not the latest
@@ -855,6 +893,7 @@ if __name__ == "__main__":
     loops = make_loops()
     loops.update(make_joint())
     loops.update(make_finetune())
+    loops.update(make_separate())
     np.savez_compressed(out, **loops)
     print(out, os.path.getsize(out), "bytes")
     import json

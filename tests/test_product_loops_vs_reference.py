@@ -484,3 +484,24 @@ def test_save_state_resume_on_the_cpu_harness(tmp_path, kind, name):
     # and the uninterrupted two meta-steps are the reference's (no val / early stop in between: theta only)
     key = "%s|plus|" % name
     np.testing.assert_array_equal(_bits(_flat(model_a, a.meta_weights.flat)), _bits(LOOPS[key + "theta"]))
+
+
+def test_product_separate_training_replays_the_reference(tmp_path):
+    """run.py:67-68 for `<name>_separate`: `BaseModel.separate_train_val_test()` with init_parms=True (base_model.py:41-109)
+    EXECUTED over the toy stand-in (global_variables_initializer = the toy model's next initialisation, the two Keras callbacks
+    restated) vs the product's own code: one model per domain from the fresh initialisation, the compiled optimizer kept (no SGD
+    re-compile), best-val_AUC checkpoints, test -- steps, results, per-domain checkpoints and the restored model, bit for bit."""
+    base, model = _base("mlp_separate", "plus")
+    base.checkpoint_path = str(tmp_path / "ckpt" / "model_parameters.npz")
+    base.train_config.update(loss="binary_crossentropy", learning_rate=0.001, epoch=mrg.SEPARATE_EPOCHS, patience=2)
+    base.separate_train_val_test = types.MethodType(BaseModel.separate_train_val_test, base)
+    model.optimizer = "adam"
+    avg_loss, avg_auc, domain_loss, domain_auc = base.separate_train_val_test()
+    np.testing.assert_array_equal(np.array(model.steps, dtype=np.int32), LOOPS["separate|steps"])
+    got = np.array([avg_loss, avg_auc] + [domain_loss[d] for d in sorted(mrg.N_STEP)] + [domain_auc[d] for d in sorted(mrg.N_STEP)])
+    np.testing.assert_array_equal(got, LOOPS["separate|result"])
+    np.testing.assert_array_equal(_bits(_flat(model, model.params)), _bits(LOOPS["separate|live"]))
+    for d in sorted(mrg.N_STEP):
+        ck = _load_ckpt(model, str(tmp_path / "ckpt" / ("domain_%d.npz" % d)))
+        np.testing.assert_array_equal(_bits(_flat(model, ck)), _bits(LOOPS["separate|ckpt_%d" % d]), err_msg="checkpoint of domain %d" % d)
+    assert model.optimizer == "adam" and int(LOOPS["separate|compiles"][0]) == 0      # the compiled optimizer is never replaced
