@@ -239,6 +239,8 @@ class MAML(object):
     def train_epoch(self, epoch=0):
         self.train_sequence = self.schedule.shuffle_sequence(self.train_sequence)   # :66
         for idx in self.train_sequence:
+            if self.train_config['target_domain'] >= 0 and idx == self.train_config['target_domain']:   # :68-69 (PCGrad; MAML / MLDG
+                continue                                                                            #  refuse the knob in their split)
             self.domain_step(idx)
         self.finish_epoch()
 
@@ -256,7 +258,9 @@ class MAML(object):
             self.train_epoch(epoch)
             if epoch % self.train_config['val_every_step'] == 0:   # :130-144
                 val_avg_loss, val_avg_auc, val_domain_loss, val_domain_auc = self.val()
-                if self.early_stop_step(val_avg_auc):
+                val_metric = val_domain_auc[self.train_config['target_domain']] \
+                    if self.train_config['target_domain'] >= 0 else val_avg_auc     # :137-138
+                if self.early_stop_step(val_metric):
                     break
                 self.log("Test Result: ")
                 self.val_and_test("test")

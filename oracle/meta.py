@@ -224,6 +224,8 @@ class OracleMAML(OracleDN):
 
     def build_meta_data_split(self):                                         # :289-341
         tc = self.tc
+        if tc.get('target_domain', -1) >= 0:
+            raise NotImplementedError("target_domain >= 0 under MAML / MLDG (meta-val on the target domain) is not restated")
         out = {}
         for idx, d in self.data['train'].items():
             n = len(d['uid'])
@@ -294,6 +296,8 @@ class OracleMAML(OracleDN):
     def train_epoch(self):
         self.sequence = self.schedule.shuffle_sequence(self.sequence)       # :66
         for idx in self.sequence:
+            if self.target >= 0 and idx == self.target:                      # :68-69
+                continue
             self.domain_step(idx)
         self.finish_epoch()
 

@@ -36,7 +36,10 @@ CASES = [("maml", "mlp_meta", {}), ("maml", "mlp_meta_batch", {}), ("maml", "mlp
          ("mldg", "mlp_meta_mldg", {}), ("mldg", "mlp_meta_mldg_batch", {"epoch": 3}),
          ("pcgrad", "mlp_pcgrad", {}), ("pcgrad", "mlp_pcgrad", {"meta_train_step": 1, "sample_num": 3}),
          # meta_finetune_step > 0: `val()` finetunes a few epochs per domain before evaluating (maml.py:244-287, 343-353)
-         ("maml", "mlp_meta", {"meta_finetune_step": 2}), ("mldg", "mlp_meta_mldg_batch", {"meta_finetune_step": 1})]
+         ("maml", "mlp_meta", {"meta_finetune_step": 2}), ("mldg", "mlp_meta_mldg_batch", {"meta_finetune_step": 1}),
+         # target_domain >= 0 under PCGrad: the target is skipped as a query domain (it can still be drawn as a support domain) and
+         # its validation AUC drives the early stop (pcgrad.py:68-69,137-138)
+         ("pcgrad", "mlp_pcgrad", {"target_domain": 1, "epoch": 3})]
 
 
 def toy_grad(weights, domain):

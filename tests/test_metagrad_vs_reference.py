@@ -74,8 +74,8 @@ def test_oracle_replays_the_reference_metagrad_loops(i):
     om = cls(model, _toy_data(), tc, mg.BATCH, Schedule(mrg.LOOP_SEED), name=name)
     for epoch in range(tc["epoch"]):
         om.train_epoch()
-        _, val_auc, _, _ = om.val()
-        if om.early_stop_step(val_auc):
+        _, val_auc, _, val_domain_auc = om.val()
+        if om.early_stop_step(val_domain_auc[tc["target_domain"]] if tc["target_domain"] >= 0 else val_auc):
             break
         om.val_and_test("test")      # reloads the best checkpoint into the live model, like the reference (base_model.py:121)
     key = "case%d|" % i
